@@ -1,0 +1,110 @@
+// common.cuh -- context object, error plumbing, shared device helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+#include "../../include/stein_b200.h"
+
+namespace stein {
+
+constexpr int TILE = 128;          // particle tile edge (rows/cols of one distance tile)
+constexpr int LD_ALIGN = 32;       // leading dimension granularity (floats)
+constexpr int HIST_MAX_BINS = 16384;
+constexpr int NUM_SMS_B200 = 148;
+
+}  // namespace stein
+
+struct stein_ctx {
+    int device = 0;
+    int num_sms = stein::NUM_SMS_B200;
+    cudaStream_t stream = nullptr;
+    bool has_comm = false;
+    stein_comm comm{};
+    int phi_impl = STEIN_PHI_AUTO;
+    int64_t launches = 0;
+    std::string error;
+    // pinned host staging + device scratch for the median loop
+    uint64_t *h_counts = nullptr;   // pinned, HIST_MAX_BINS + 2
+    uint64_t *d_counts = nullptr;   // device, HIST_MAX_BINS + 2
+    uint32_t *d_pilot_keys = nullptr;
+    uint32_t *d_sel = nullptr;      // device, 2 keys
+    uint32_t *h_sel = nullptr;      // pinned
+    int64_t pilot_cap = 0;
+};
+
+namespace stein {
+
+extern thread_local std::string g_last_error;
+
+int fail(stein_ctx *ctx, int code, const char *fmt, ...);
+
+#define STEIN_CHECK_CUDA(ctx, expr)                                                        \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return stein::fail((ctx), STEIN_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, \
+                               #expr, cudaGetErrorString(_e));                             \
+    } while (0)
+
+#define STEIN_CHECK_LAUNCH(ctx)                                                            \
+    do {                                                                                   \
+        (ctx)->launches++;                                                                 \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess)                                                             \
+            return stein::fail((ctx), STEIN_ERR_CUDA, "%s:%d: kernel launch -> %s", __FILE__, \
+                               __LINE__, cudaGetErrorString(_e));                          \
+    } while (0)
+
+#define STEIN_REQUIRE(ctx, cond, ...)                                     \
+    do {                                                                  \
+        if (!(cond)) return stein::fail((ctx), STEIN_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+#define STEIN_TRY(expr)              \
+    do {                             \
+        int _rc = (expr);            \
+        if (_rc != STEIN_OK) return _rc; \
+    } while (0)
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// order-preserving fp32 -> u32 (ascending); -0 folded onto +0
+__host__ __device__ inline uint32_t float_to_key(float f) {
+    f = f + 0.0f;
+#ifdef __CUDA_ARCH__
+    uint32_t b = __float_as_uint(f);
+#else
+    uint32_t b;
+    memcpy(&b, &f, 4);
+#endif
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ inline float key_to_float(uint32_t k) {
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+
+// map linear upper-triangular tile index t (row-major over I<=J) to (I, J)
+__host__ __device__ inline void tri_tile(int64_t t, int64_t T, int &I, int &J) {
+    // row I starts at offset I*T - I*(I-1)/2
+    double Td = (double)T;
+    double disc = (2.0 * Td + 1.0) * (2.0 * Td + 1.0) - 8.0 * (double)t;
+    int64_t i = (int64_t)(((2.0 * Td + 1.0) - sqrt(disc)) * 0.5);
+    if (i < 0) i = 0;
+    if (i >= T) i = T - 1;
+    while (i > 0 && i * T - i * (i - 1) / 2 > t) --i;
+    while ((i + 1) * T - (i + 1) * i / 2 <= t) ++i;
+    I = (int)i;
+    J = (int)(i + (t - (i * T - i * (i - 1) / 2)));
+}
+
+}  // namespace stein

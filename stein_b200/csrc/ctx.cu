@@ -1,0 +1,148 @@
+// ctx.cu -- context lifetime, error text, collective hooks, phi dispatch.
+#include <stdarg.h>
+
+#include "phi_common.cuh"
+
+namespace stein {
+
+thread_local std::string g_last_error;
+
+int fail(stein_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (ctx) ctx->error = buf;
+    return code;
+}
+
+}  // namespace stein
+
+using namespace stein;
+
+extern "C" {
+
+int stein_abi_version(void) { return STEIN_ABI_VERSION; }
+
+int64_t stein_ld(int64_t d) { return round_up(d < 1 ? 1 : d, LD_ALIGN); }
+int64_t stein_rows_padded(int64_t n) { return round_up(n < 1 ? 1 : n, TILE); }
+
+int stein_ctx_create(stein_ctx **out, int device, void *cuda_stream) {
+    if (!out) return fail(nullptr, STEIN_ERR_INVALID, "null output pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, STEIN_ERR_CUDA,
+                    "no CUDA device available (%s): libstein_b200 has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= count)
+        return fail(nullptr, STEIN_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+    stein_ctx *ctx = new stein_ctx();
+    ctx->device = device;
+    e = cudaSetDevice(device);
+    cudaDeviceProp prop{};
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, STEIN_ERR_CUDA, "cudaSetDevice/GetDeviceProperties: %s", cudaGetErrorString(e));
+    }
+    if (prop.major != 10) {
+        const int major = prop.major, minor = prop.minor;
+        delete ctx;
+        return fail(nullptr, STEIN_ERR_UNSUPPORTED,
+                    "device is sm_%d%d; libstein_b200 is built for sm_100a (B200) only", major, minor);
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    *out = ctx;
+    return STEIN_OK;
+}
+
+int stein_ctx_destroy(stein_ctx *ctx) {
+    if (!ctx) return STEIN_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->d_counts) cudaFree(ctx->d_counts);
+    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+    if (ctx->d_pilot_keys) cudaFree(ctx->d_pilot_keys);
+    if (ctx->d_sel) cudaFree(ctx->d_sel);
+    if (ctx->h_sel) cudaFreeHost(ctx->h_sel);
+    delete ctx;
+    return STEIN_OK;
+}
+
+int stein_ctx_set_stream(stein_ctx *ctx, void *cuda_stream) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return STEIN_OK;
+}
+
+int stein_ctx_set_comm(stein_ctx *ctx, const stein_comm *comm) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    if (!comm || comm->world <= 1) {
+        ctx->has_comm = false;
+        return STEIN_OK;
+    }
+    STEIN_REQUIRE(ctx, comm->rank >= 0 && comm->rank < comm->world, "rank %d outside world %d",
+                  comm->rank, comm->world);
+    STEIN_REQUIRE(ctx, comm->allreduce_sum_u64 && comm->allreduce_sum_f64 && comm->allgather_f32,
+                  "all three collective hooks are required when world > 1");
+    ctx->comm = *comm;
+    ctx->has_comm = true;
+    return STEIN_OK;
+}
+
+int stein_ctx_set_phi_impl(stein_ctx *ctx, int impl) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    STEIN_REQUIRE(ctx, impl >= STEIN_PHI_AUTO && impl <= STEIN_PHI_FLASH_TC, "unknown phi impl %d", impl);
+    ctx->phi_impl = impl;
+    return STEIN_OK;
+}
+
+const char *stein_last_error(const stein_ctx *ctx) {
+    return ctx ? ctx->error.c_str() : g_last_error.c_str();
+}
+
+int64_t stein_ctx_launch_count(const stein_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static int pick_phi_impl(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
+    if (ctx->phi_impl != STEIN_PHI_AUTO) return ctx->phi_impl;
+    return flash_tc_supported(ctx, n_local, n_total, d) ? STEIN_PHI_FLASH_TC : STEIN_PHI_DENSE_SIMT;
+}
+
+int64_t stein_phi_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
+    if (!ctx) return -1;
+    // sized so that either implementation can run (the impl may be switched later)
+    int64_t b = dense_workspace_bytes(n_local, n_total, d);
+    if (flash_tc_supported(ctx, n_local, n_total, d))
+        b = std::max(b, flash_tc_workspace_bytes(ctx, n_local, n_total, d));
+    return b;
+}
+
+int stein_phi(stein_ctx *ctx, const float *X_all_dev, const float *S_all_dev, const float *r_all_dev,
+              int64_t n_total, int64_t d, int64_t ld, int64_t row_begin, int64_t n_local,
+              float bandwidth, void *workspace_dev, int64_t workspace_bytes, float *phi_dev,
+              double *sumsq_dev) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    STEIN_REQUIRE(ctx, X_all_dev && S_all_dev && r_all_dev && workspace_dev && phi_dev && sumsq_dev,
+                  "null pointer");
+    STEIN_REQUIRE(ctx, n_total >= 1 && d >= 1 && ld >= d && ld % LD_ALIGN == 0, "bad shape");
+    STEIN_REQUIRE(ctx, row_begin >= 0 && n_local >= 1 && row_begin % TILE == 0,
+                  "row_begin=%lld must be a non-negative multiple of %d", (long long)row_begin, TILE);
+    STEIN_REQUIRE(ctx, bandwidth > 0.0f && bandwidth == bandwidth, "bandwidth must be positive and finite");
+    const float h2 = bandwidth * bandwidth;  // squared_exponential_kernel.py:22 tf.square(bandwidth)
+    const int impl = pick_phi_impl(ctx, n_local, n_total, d);
+    if (impl == STEIN_PHI_FLASH_TC) {
+        if (!flash_tc_supported(ctx, n_local, n_total, d))
+            return fail(ctx, STEIN_ERR_UNSUPPORTED, "flash tcgen05 phi does not take n=%lld d=%lld",
+                        (long long)n_total, (long long)d);
+        return phi_flash_tc(ctx, X_all_dev, S_all_dev, r_all_dev, n_total, d, ld, row_begin, n_local, h2,
+                            workspace_dev, workspace_bytes, phi_dev, sumsq_dev);
+    }
+    return phi_dense(ctx, X_all_dev, S_all_dev, r_all_dev, n_total, d, ld, row_begin, n_local, h2,
+                     workspace_dev, workspace_bytes, phi_dev, sumsq_dev);
+}
+
+}  // extern "C"

@@ -1,0 +1,298 @@
+// engine.cu -- device-resident particles + optimizer state, one SVGD
+// update_particles() per stein_engine_step().
+//
+// Reference: AbstractSteinSampler.update_particles
+//            stein/samplers/abstract_stein_sampler.py:107-127
+//   theta_array  <- dict->array                      (:121, converters.py:4-55)
+//   phi          <- compute_phi(theta_array, grads)  (:123 -> :100-105)
+//   phi          *= 10 / max(10, ||phi||_F)          (:125)
+//   theta_array  += gd.update(phi)                   (:126)
+// The reference keeps theta as float64 NumPy on the host and round-trips through
+// TensorFlow every iteration; here the particles, scores, phi and the optimizer
+// moments live in HBM (fp32, padded layout) and only cross PCIe when the caller
+// asks (set_/get_ functions, update_particles_host).
+//
+// Sharding (ctx collective hooks set): rank g owns global rows
+// [g*q, g*q + q) with q = rows_padded(ceil(n/world)); X_all/S_all hold all
+// world*q rows and are refreshed by an in-place all-gather each step.
+#include <algorithm>
+
+#include "phi_common.cuh"
+
+struct stein_engine {
+    stein_ctx *ctx = nullptr;
+    int64_t n_total = 0, d = 0, ld = 0;
+    int world = 1, rank = 0;
+    int64_t q = 0;          // padded rows per rank
+    int64_t row_begin = 0;  // first global row owned
+    int64_t n_local = 0;    // valid rows owned
+    int opt = STEIN_OPT_ADAM;
+    double lr = 1e-3, decay = 1.0, p1 = 0.9, p2 = 0.999;
+    int64_t n_iters = 0;
+    float *X_all = nullptr, *S_all = nullptr, *phi = nullptr, *m1 = nullptr, *m2 = nullptr;
+    float *r_all = nullptr;
+    double *sumsq = nullptr;
+    double *h_sumsq = nullptr;
+    void *ws = nullptr;
+    int64_t ws_bytes = 0;
+    void *stage = nullptr;  // device staging for float64 host arrays
+    float last_med = 0.f, last_bw = 0.f;
+    int32_t last_sweeps = 0;
+    float *X_local() const { return X_all + (int64_t)rank * q * ld; }
+    float *S_local() const { return S_all + (int64_t)rank * q * ld; }
+};
+
+namespace stein {
+
+// padded fp32 [rows x ld]  <->  dense float64 [rows x d]
+__global__ void f64_to_padded_kernel(const double *__restrict__ src, int64_t rows, int64_t d, int64_t ld,
+                                     float *__restrict__ dst) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * d) return;
+    const int64_t r = e / d, c = e % d;
+    dst[r * ld + c] = (float)src[e];
+}
+__global__ void padded_to_f64_kernel(const float *__restrict__ src, int64_t rows, int64_t d, int64_t ld,
+                                     double *__restrict__ dst) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * d) return;
+    const int64_t r = e / d, c = e % d;
+    dst[e] = (double)src[r * ld + c];
+}
+
+static int upload(stein_engine *e, const void *host, int is_f64, float *dst) {
+    stein_ctx *ctx = e->ctx;
+    STEIN_REQUIRE(ctx, host != nullptr, "null host pointer");
+    if (e->n_local == 0) return STEIN_OK;
+    if (!is_f64) {
+        STEIN_CHECK_CUDA(ctx, cudaMemcpy2DAsync(dst, e->ld * 4, host, e->d * 4, e->d * 4, e->n_local,
+                                                cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(e->stage, host, e->n_local * e->d * 8,
+                                              cudaMemcpyHostToDevice, ctx->stream));
+        const int64_t total = e->n_local * e->d;
+        f64_to_padded_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+            (const double *)e->stage, e->n_local, e->d, e->ld, dst);
+        STEIN_CHECK_LAUNCH(ctx);
+    }
+    return STEIN_OK;
+}
+
+static int download(stein_engine *e, const float *src, void *host, int is_f64) {
+    stein_ctx *ctx = e->ctx;
+    STEIN_REQUIRE(ctx, host != nullptr, "null host pointer");
+    if (e->n_local == 0) return STEIN_OK;
+    if (!is_f64) {
+        STEIN_CHECK_CUDA(ctx, cudaMemcpy2DAsync(host, e->d * 4, src, e->ld * 4, e->d * 4, e->n_local,
+                                                cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        const int64_t total = e->n_local * e->d;
+        padded_to_f64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+            src, e->n_local, e->d, e->ld, (double *)e->stage);
+        STEIN_CHECK_LAUNCH(ctx);
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(host, e->stage, total * 8, cudaMemcpyDeviceToHost,
+                                              ctx->stream));
+    }
+    STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return STEIN_OK;
+}
+
+}  // namespace stein
+
+using namespace stein;
+
+extern "C" {
+
+int stein_engine_create(stein_engine **out, stein_ctx *ctx, int64_t n_total, int64_t d, int optimizer,
+                        double learning_rate, double decay, double p1, double p2) {
+    STEIN_REQUIRE(ctx, ctx != nullptr && out != nullptr, "null ctx/out");
+    *out = nullptr;
+    STEIN_REQUIRE(ctx, n_total >= 2, "n_particles=%lld: the bandwidth needs ln(n) > 0", (long long)n_total);
+    STEIN_REQUIRE(ctx, d >= 1, "d must be positive");
+    STEIN_REQUIRE(ctx, optimizer == STEIN_OPT_ADAM || optimizer == STEIN_OPT_ADAGRAD, "unknown optimizer");
+    STEIN_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    stein_engine *e = new stein_engine();
+    e->ctx = ctx;
+    e->n_total = n_total;
+    e->d = d;
+    e->ld = stein_ld(d);
+    e->world = ctx->has_comm ? ctx->comm.world : 1;
+    e->rank = ctx->has_comm ? ctx->comm.rank : 0;
+    e->q = stein_rows_padded((n_total + e->world - 1) / e->world);
+    e->row_begin = (int64_t)e->rank * e->q;
+    e->n_local = std::max<int64_t>(0, std::min<int64_t>(e->q, n_total - e->row_begin));
+    e->opt = optimizer;
+    e->lr = learning_rate;
+    e->decay = decay;
+    e->p1 = p1;
+    e->p2 = p2;
+    const int64_t all = e->q * e->world * e->ld * 4, loc = e->q * e->ld * 4;
+    e->ws_bytes = stein_phi_workspace_bytes(ctx, std::max<int64_t>(e->n_local, 1), n_total, d);
+    cudaError_t err = cudaSuccess;
+    auto alloc0 = [&](void **p, int64_t bytes) {
+        if (err != cudaSuccess) return;
+        err = cudaMalloc(p, bytes);
+        if (err == cudaSuccess) err = cudaMemsetAsync(*p, 0, bytes, ctx->stream);
+    };
+    alloc0((void **)&e->X_all, all);
+    alloc0((void **)&e->S_all, all);
+    alloc0((void **)&e->phi, loc);
+    alloc0((void **)&e->m1, loc);
+    alloc0((void **)&e->m2, loc);
+    alloc0((void **)&e->r_all, e->q * e->world * 4);
+    alloc0((void **)&e->sumsq, 64);
+    alloc0(&e->ws, e->ws_bytes);
+    alloc0(&e->stage, std::max<int64_t>(e->q * d * 8, 256));
+    if (err == cudaSuccess) err = cudaMallocHost(&e->h_sumsq, 64);
+    if (err != cudaSuccess) {
+        stein_engine_destroy(e);
+        return fail(ctx, err == cudaErrorMemoryAllocation ? STEIN_ERR_NOMEM : STEIN_ERR_CUDA,
+                    "engine allocation failed: %s", cudaGetErrorString(err));
+    }
+    *out = e;
+    return STEIN_OK;
+}
+
+int stein_engine_destroy(stein_engine *e) {
+    if (!e) return STEIN_OK;
+    cudaSetDevice(e->ctx->device);
+    cudaStreamSynchronize(e->ctx->stream);
+    void *ptrs[] = {e->X_all, e->S_all, e->phi, e->m1, e->m2, e->r_all, e->sumsq, e->ws, e->stage};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (e->h_sumsq) cudaFreeHost(e->h_sumsq);
+    delete e;
+    return STEIN_OK;
+}
+
+int stein_engine_local_rows(const stein_engine *e, int64_t *row_begin, int64_t *n_local) {
+    if (!e) return STEIN_ERR_INVALID;
+    if (row_begin) *row_begin = e->row_begin;
+    if (n_local) *n_local = e->n_local;
+    return STEIN_OK;
+}
+
+int stein_engine_buffers(stein_engine *e, float **X_local_dev, float **S_local_dev,
+                         float **phi_local_dev, int64_t *ld, int64_t *rows_padded_local) {
+    if (!e) return STEIN_ERR_INVALID;
+    if (X_local_dev) *X_local_dev = e->X_local();
+    if (S_local_dev) *S_local_dev = e->S_local();
+    if (phi_local_dev) *phi_local_dev = e->phi;
+    if (ld) *ld = e->ld;
+    if (rows_padded_local) *rows_padded_local = e->q;
+    return STEIN_OK;
+}
+
+int stein_engine_set_particles(stein_engine *e, const void *X_host, int is_f64) {
+    if (!e) return STEIN_ERR_INVALID;
+    STEIN_TRY(upload(e, X_host, is_f64, e->X_local()));
+    STEIN_CHECK_CUDA(e->ctx, cudaStreamSynchronize(e->ctx->stream));
+    return STEIN_OK;
+}
+
+int stein_engine_get_particles(stein_engine *e, void *X_host, int is_f64) {
+    if (!e) return STEIN_ERR_INVALID;
+    return download(e, e->X_local(), X_host, is_f64);
+}
+
+int stein_engine_set_scores(stein_engine *e, const void *S_host, int is_f64) {
+    if (!e) return STEIN_ERR_INVALID;
+    return upload(e, S_host, is_f64, e->S_local());
+}
+
+int stein_engine_get_phi(stein_engine *e, void *phi_host, int is_f64) {
+    if (!e) return STEIN_ERR_INVALID;
+    return download(e, e->phi, phi_host, is_f64);
+}
+
+int stein_engine_step(stein_engine *e) {
+    if (!e) return STEIN_ERR_INVALID;
+    stein_ctx *ctx = e->ctx;
+    STEIN_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t rows_all = e->q * e->world;
+    if (e->world > 1) {
+        const int64_t cnt = e->q * e->ld;
+        if (ctx->comm.allgather_f32(ctx->comm.user, e->X_local(), e->X_all, cnt) != 0 ||
+            ctx->comm.allgather_f32(ctx->comm.user, e->S_local(), e->S_all, cnt) != 0)
+            return fail(ctx, STEIN_ERR_COMM, "allgather_f32 hook failed");
+    }
+    // abstract_kernel.py:34 -- r = sum(T*T, 1), contract order
+    STEIN_TRY(stein_row_norms(ctx, e->X_all, rows_all, e->d, e->ld, e->r_all));
+    // compute_median.py + abstract_kernel.py:40
+    float med = 0.f;
+    STEIN_TRY(stein_median_sqdist(ctx, e->X_all, e->r_all, e->n_total, e->d, e->ld, &med, nullptr,
+                                  &e->last_sweeps));
+    const float bw = stein_bandwidth(med, e->n_total);
+    e->last_med = med;
+    e->last_bw = bw;
+    if (!(bw > 0.0f) || bw != bw)
+        return fail(ctx, STEIN_ERR_INVALID,
+                    "median squared distance is %g: bandwidth undefined (all particles equal?)", (double)med);
+    // abstract_stein_sampler.py:100-105
+    STEIN_TRY(stein_phi(ctx, e->X_all, e->S_all, e->r_all, e->n_total, e->d, e->ld, e->row_begin,
+                        std::max<int64_t>(e->n_local, 1), bw, e->ws, e->ws_bytes, e->phi, e->sumsq));
+    if (e->world > 1) {
+        if (ctx->comm.allreduce_sum_f64(ctx->comm.user, e->sumsq, 1) != 0)
+            return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_f64 hook failed");
+    }
+    // abstract_stein_sampler.py:125-126
+    const int64_t count = e->q * e->ld;
+    if (e->opt == STEIN_OPT_ADAM) {
+        STEIN_TRY(stein_clip_adam_step(ctx, e->X_local(), e->phi, e->m1, e->m2, count, e->sumsq, e->lr,
+                                       e->p1, e->p2, e->n_iters));
+        e->lr *= e->decay;  // adam_gradient_descent.py:56
+    } else {
+        // adagrad_gradient_descent.py never applies `decay`
+        STEIN_TRY(stein_clip_adagrad_step(ctx, e->X_local(), e->phi, e->m1, count, e->sumsq, e->lr,
+                                          e->p1, e->n_iters));
+    }
+    e->n_iters += 1;
+    return STEIN_OK;
+}
+
+int stein_engine_update_particles_host(stein_engine *e, const void *S_host, void *X_host_out,
+                                       int is_f64) {
+    if (!e) return STEIN_ERR_INVALID;
+    STEIN_TRY(stein_engine_set_scores(e, S_host, is_f64));
+    STEIN_TRY(stein_engine_step(e));
+    if (X_host_out) return stein_engine_get_particles(e, X_host_out, is_f64);
+    return STEIN_OK;
+}
+
+int stein_engine_last(const stein_engine *e, float *median, float *bandwidth, double *phi_norm,
+                      int32_t *sweeps) {
+    if (!e) return STEIN_ERR_INVALID;
+    stein_ctx *ctx = e->ctx;
+    if (median) *median = e->last_med;
+    if (bandwidth) *bandwidth = e->last_bw;
+    if (sweeps) *sweeps = e->last_sweeps;
+    if (phi_norm) {
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(e->h_sumsq, e->sumsq, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *phi_norm = sqrt(*e->h_sumsq);
+    }
+    return STEIN_OK;
+}
+
+int stein_engine_get_state(stein_engine *e, int64_t *n_iters, double *learning_rate, void *m1_host,
+                           void *m2_host, int is_f64) {
+    if (!e) return STEIN_ERR_INVALID;
+    if (n_iters) *n_iters = e->n_iters;
+    if (learning_rate) *learning_rate = e->lr;
+    if (m1_host) STEIN_TRY(download(e, e->m1, m1_host, is_f64));
+    if (m2_host) STEIN_TRY(download(e, e->m2, m2_host, is_f64));
+    return STEIN_OK;
+}
+
+int stein_engine_set_state(stein_engine *e, int64_t n_iters, double learning_rate, const void *m1_host,
+                           const void *m2_host, int is_f64) {
+    if (!e) return STEIN_ERR_INVALID;
+    e->n_iters = n_iters;
+    e->lr = learning_rate;
+    if (m1_host) STEIN_TRY(upload(e, m1_host, is_f64, e->m1));
+    if (m2_host) STEIN_TRY(upload(e, m2_host, is_f64, e->m2));
+    STEIN_CHECK_CUDA(e->ctx, cudaStreamSynchronize(e->ctx->stream));
+    return STEIN_OK;
+}
+
+}  // extern "C"

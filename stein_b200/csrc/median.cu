@@ -1,0 +1,423 @@
+// median.cu -- kernel (2): exact median of the n x n squared-distance matrix
+// without materialising it.
+//
+// Reference: stein/kernels/abstract_kernel.py:33-40 (D, bandwidth) and
+// stein/utilities/compute_median.py:4-16 (top_k median over all n*n entries).
+//
+// Method: D is symmetric, so only the upper-triangular 128x128 tiles are
+// computed (off-diagonal tiles weigh 2).  Each sweep recomputes the tiles with
+// the FFMA mainloop in contract arithmetic and histograms the order-preserving
+// u32 keys that fall into a window [key_lo, key_lo + nbins << shift); keys
+// below the window are only counted.  A cheap pilot (2^20 sampled pairs) puts
+// the window around the median so that one sweep usually resolves individual
+// fp32 values (shift == 0); otherwise the window is narrowed and swept again
+// (radix select).  Counts are u64 (n*n = 2^32 at n = 65 536).
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "gemm_simt.cuh"
+
+namespace stein {
+
+// ---- r_i = sum_k x_ik^2, fma chain over k ascending ------------------------
+__global__ void row_norms_kernel(const float *__restrict__ X, int64_t rows, int64_t ld,
+                                 float *__restrict__ r) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const float4 *row = reinterpret_cast<const float4 *>(X + i * ld);
+    float acc = 0.0f;
+    for (int64_t k4 = 0; k4 < ld / 4; ++k4) {
+        const float4 v = row[k4];
+        acc = __fmaf_rn(v.x, v.x, acc);
+        acc = __fmaf_rn(v.y, v.y, acc);
+        acc = __fmaf_rn(v.z, v.z, acc);
+        acc = __fmaf_rn(v.w, v.w, acc);
+    }
+    r[i] = acc;
+}
+
+// ---- one histogram sweep ------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+sqdist_hist_kernel(const float *__restrict__ X, const float *__restrict__ r, int64_t n, int64_t ld,
+                   int64_t T, int64_t tile_begin, int64_t tile_end, uint32_t key_lo, uint32_t shift,
+                   uint32_t nbins, unsigned long long *__restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GemmSmem &gs = *reinterpret_cast<GemmSmem *>(smem_raw);
+    unsigned int *hist = reinterpret_cast<unsigned int *>(smem_raw + sizeof(GemmSmem));
+    unsigned int *below_s = hist + nbins;
+
+    for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) hist[b] = 0u;
+    if (threadIdx.x == 0) *below_s = 0u;
+    __syncthreads();
+
+    unsigned int below = 0u;
+    float acc[8][8];
+    for (int64_t t = tile_begin + blockIdx.x; t < tile_end; t += gridDim.x) {
+        int I, J;
+        tri_tile(t, T, I, J);
+        const int64_t m0 = (int64_t)I * TILE, n0 = (int64_t)J * TILE;
+        gemm_tile<true>(X, ld, m0, X, ld, n0, 0, (int)ld, gs, acc);
+        const unsigned int w = (I == J) ? 1u : 2u;
+        float ri[8], rj[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            ri[q] = r[m0 + acc_row(q)];
+            rj[q] = r[n0 + acc_col(q)];
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int64_t i = m0 + acc_row(a);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int64_t j = n0 + acc_col(c);
+                if (i < n && j < n) {
+                    const float tsum = ri[a] + rj[c];
+                    const float dist = tsum - 2.0f * acc[a][c];
+                    const uint32_t key = float_to_key(dist);
+                    if (key < key_lo) {
+                        below += w;
+                    } else {
+                        const uint32_t b = (key - key_lo) >> shift;
+                        if (b < nbins) atomicAdd(&hist[b], w);
+                    }
+                }
+            }
+        }
+    }
+    // per-thread "below" -> warp -> block
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if ((threadIdx.x & 31) == 0 && below) atomicAdd(below_s, below);
+    __syncthreads();
+    if (threadIdx.x == 0 && *below_s) atomicAdd(&counts[0], (unsigned long long)*below_s);
+    for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) {
+        const unsigned int v = hist[b];
+        if (v) atomicAdd(&counts[1 + b], (unsigned long long)v);
+    }
+}
+
+// ---- pilot: keys of sampled pairs -----------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void pilot_kernel(const float *__restrict__ X, const float *__restrict__ r, int64_t n,
+                             int64_t ld, int64_t m, uint64_t seed, uint32_t *__restrict__ keys) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= m) return;
+    const uint64_t h = splitmix64(seed + (uint64_t)s);
+    const int64_t i = (int64_t)((h >> 32) % (uint64_t)n);
+    const int64_t j = (int64_t)((h & 0xffffffffull) % (uint64_t)n);
+    const float4 *a = reinterpret_cast<const float4 *>(X + i * ld);
+    const float4 *b = reinterpret_cast<const float4 *>(X + j * ld);
+    float acc = 0.0f;
+    for (int64_t k4 = 0; k4 < ld / 4; ++k4) {
+        const float4 u = a[k4], v = b[k4];
+        acc = __fmaf_rn(u.x, v.x, acc);
+        acc = __fmaf_rn(u.y, v.y, acc);
+        acc = __fmaf_rn(u.z, v.z, acc);
+        acc = __fmaf_rn(u.w, v.w, acc);
+    }
+    const float tsum = r[i] + r[j];
+    keys[s] = float_to_key(tsum - 2.0f * acc);
+}
+
+// single-block radix select of two ranks among m keys
+__global__ void __launch_bounds__(1024, 1)
+select_keys_kernel(const uint32_t *__restrict__ keys, int64_t m, uint64_t rank0, uint64_t rank1,
+                   uint32_t *__restrict__ out) {
+    __shared__ unsigned int hist[256];
+    __shared__ uint32_t s_prefix, s_mask;
+    __shared__ unsigned long long s_rank;
+    for (int q = 0; q < 2; ++q) {
+        if (threadIdx.x == 0) {
+            s_prefix = 0u;
+            s_mask = 0u;
+            s_rank = q == 0 ? rank0 : rank1;
+        }
+        __syncthreads();
+        for (int pass = 0; pass < 4; ++pass) {
+            const int sh = 24 - 8 * pass;
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
+            __syncthreads();
+            const uint32_t prefix = s_prefix, mask = s_mask;
+            // keys cluster in very few digits: aggregate equal digits within the warp
+            for (int64_t base = 0; base < m; base += blockDim.x) {
+                const int64_t idx = base + threadIdx.x;
+                bool ok = idx < m;
+                const uint32_t k = ok ? keys[idx] : 0u;
+                ok = ok && ((k & mask) == prefix);
+                const unsigned dg = ok ? ((k >> sh) & 255u) : 256u;
+                const unsigned peers = __match_any_sync(0xffffffffu, dg);
+                if (ok && (int)(threadIdx.x & 31) == __ffs(peers) - 1)
+                    atomicAdd(&hist[dg], (unsigned)__popc(peers));
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long cum = 0, rk = s_rank;
+                int dgt = 0;
+                for (; dgt < 255; ++dgt) {
+                    if (cum + hist[dgt] > rk) break;
+                    cum += hist[dgt];
+                }
+                s_rank = rk - cum;
+                s_prefix = prefix | ((uint32_t)dgt << sh);
+                s_mask = mask | (255u << sh);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[q] = s_prefix;
+        __syncthreads();
+    }
+}
+
+__global__ void values_to_keys_kernel(const float *__restrict__ v, int64_t m, uint32_t *__restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) keys[i] = float_to_key(v[i]);
+}
+
+static int ensure_scratch(stein_ctx *ctx, int64_t pilot_m) {
+    if (!ctx->d_counts) {
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_counts, sizeof(uint64_t) * (HIST_MAX_BINS + 2)));
+        STEIN_CHECK_CUDA(ctx, cudaMallocHost(&ctx->h_counts, sizeof(uint64_t) * (HIST_MAX_BINS + 2)));
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_sel, sizeof(uint32_t) * 2));
+        STEIN_CHECK_CUDA(ctx, cudaMallocHost(&ctx->h_sel, sizeof(uint32_t) * 2));
+    }
+    if (pilot_m > ctx->pilot_cap) {
+        if (ctx->d_pilot_keys) cudaFree(ctx->d_pilot_keys);
+        ctx->d_pilot_keys = nullptr;
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_pilot_keys, sizeof(uint32_t) * pilot_m));
+        ctx->pilot_cap = pilot_m;
+    }
+    return STEIN_OK;
+}
+
+static int check_layout(stein_ctx *ctx, const void *X, int64_t n, int64_t d, int64_t ld) {
+    STEIN_REQUIRE(ctx, X != nullptr, "null particle pointer");
+    STEIN_REQUIRE(ctx, n >= 1 && d >= 1, "n=%lld d=%lld must be positive", (long long)n, (long long)d);
+    STEIN_REQUIRE(ctx, ld >= d && ld % LD_ALIGN == 0, "ld=%lld must be a multiple of %d and >= d=%lld",
+                  (long long)ld, LD_ALIGN, (long long)d);
+    STEIN_REQUIRE(ctx, ((uintptr_t)X & 15u) == 0, "particle pointer must be 16-byte aligned");
+    return STEIN_OK;
+}
+
+struct Window {
+    uint32_t key_lo, shift, nbins;
+    bool operator==(const Window &o) const {
+        return key_lo == o.key_lo && shift == o.shift && nbins == o.nbins;
+    }
+};
+static const Window kFullWindow = {0u, 18u, (uint32_t)HIST_MAX_BINS};
+
+}  // namespace stein
+
+using namespace stein;
+
+extern "C" {
+
+int64_t stein_num_tiles(int64_t n) {
+    const int64_t T = (n + TILE - 1) / TILE;
+    return T * (T + 1) / 2;
+}
+
+int stein_tile_coords(int64_t t, int64_t n, int32_t *I, int32_t *J) {
+    if (!I || !J || t < 0 || t >= stein_num_tiles(n)) return STEIN_ERR_INVALID;
+    int i, j;
+    tri_tile(t, (n + TILE - 1) / TILE, i, j);
+    *I = i;
+    *J = j;
+    return STEIN_OK;
+}
+
+uint32_t stein_float_to_key(float f) { return float_to_key(f); }
+float stein_key_to_float(uint32_t k) { return key_to_float(k); }
+
+float stein_bandwidth(float median, int64_t n_particles) {
+    // abstract_kernel.py:40 -- np.log(n) is folded into an fp32 constant
+    const float ln_n = (float)log((double)n_particles);
+    return sqrtf(median / ln_n);
+}
+
+int stein_row_norms(stein_ctx *ctx, const float *X_dev, int64_t n, int64_t d, int64_t ld,
+                    float *r_dev) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    STEIN_TRY(check_layout(ctx, X_dev, n, d, ld));
+    const int64_t rows = stein_rows_padded(n);
+    const int threads = 128;
+    row_norms_kernel<<<(unsigned)((rows + threads - 1) / threads), threads, 0, ctx->stream>>>(
+        X_dev, rows, ld, r_dev);
+    STEIN_CHECK_LAUNCH(ctx);
+    return STEIN_OK;
+}
+
+int stein_sqdist_hist(stein_ctx *ctx, const float *X_dev, const float *r_dev, int64_t n, int64_t d,
+                      int64_t ld, int64_t tile_begin, int64_t tile_end, uint32_t key_lo,
+                      uint32_t shift, uint32_t nbins, uint64_t *counts_dev) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    STEIN_TRY(check_layout(ctx, X_dev, n, d, ld));
+    STEIN_REQUIRE(ctx, nbins >= 1 && nbins <= (uint32_t)HIST_MAX_BINS, "nbins=%u out of range", nbins);
+    STEIN_REQUIRE(ctx, shift < 32, "shift=%u out of range", shift);
+    STEIN_REQUIRE(ctx, tile_begin >= 0 && tile_end <= stein_num_tiles(n) && tile_begin <= tile_end,
+                  "tile range [%lld,%lld) invalid", (long long)tile_begin, (long long)tile_end);
+    if (tile_begin == tile_end) return STEIN_OK;
+    const size_t smem = sizeof(GemmSmem) + sizeof(unsigned int) * (nbins + 4);
+    static bool attr_set = false;
+    if (!attr_set) {
+        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(sqdist_hist_kernel,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)(sizeof(GemmSmem) + sizeof(unsigned int) * (HIST_MAX_BINS + 4))));
+        attr_set = true;
+    }
+    const int64_t ntiles = tile_end - tile_begin;
+    const int64_t grid = std::min<int64_t>(ntiles, 2 * (int64_t)ctx->num_sms);
+    const int64_t T = (n + TILE - 1) / TILE;
+    sqdist_hist_kernel<<<(unsigned)grid, GEMM_THREADS, smem, ctx->stream>>>(
+        X_dev, r_dev, n, ld, T, tile_begin, tile_end, key_lo, shift, nbins,
+        reinterpret_cast<unsigned long long *>(counts_dev));
+    STEIN_CHECK_LAUNCH(ctx);
+    return STEIN_OK;
+}
+
+int stein_median_narrow(const uint64_t *counts, uint32_t key_lo, uint32_t shift, uint32_t nbins,
+                        uint64_t rank, uint32_t *key_out, uint32_t *key_lo_out,
+                        uint32_t *shift_out, uint32_t *nbins_out) {
+    if (rank < counts[0]) {
+        *key_lo_out = 0u;  // below the window
+        return -1;
+    }
+    uint64_t cum = counts[0];
+    uint32_t b = 0;
+    for (; b < nbins; ++b) {
+        if (cum + counts[1 + b] > rank) break;
+        cum += counts[1 + b];
+    }
+    if (b == nbins) {
+        *key_lo_out = 1u;  // above the window
+        return -1;
+    }
+    const uint32_t lo = key_lo + (b << shift);
+    if (shift == 0) {
+        *key_out = lo;
+        return 1;
+    }
+    // the bin holds 2^shift consecutive keys: split it into up to HIST_MAX_BINS bins
+    uint32_t nb_log = 0;
+    while ((1u << nb_log) < (uint32_t)HIST_MAX_BINS && nb_log < shift) ++nb_log;
+    *key_lo_out = lo;
+    *shift_out = shift - nb_log;
+    *nbins_out = 1u << nb_log;
+    return 0;
+}
+
+int stein_median_values(stein_ctx *ctx, const float *V_dev, int64_t m, float *median_host) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    STEIN_REQUIRE(ctx, V_dev && median_host && m >= 1, "bad arguments");
+    STEIN_TRY(ensure_scratch(ctx, m));
+    values_to_keys_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(V_dev, m, ctx->d_pilot_keys);
+    STEIN_CHECK_LAUNCH(ctx);
+    // compute_median.py:9-15
+    const uint64_t r0 = (m % 2 == 0) ? (uint64_t)m / 2 - 1 : (uint64_t)m / 2, r1 = (uint64_t)m / 2;
+    select_keys_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_pilot_keys, m, r0, r1, ctx->d_sel);
+    STEIN_CHECK_LAUNCH(ctx);
+    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_sel, ctx->d_sel, sizeof(uint32_t) * 2,
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+    STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const float lo = key_to_float(ctx->h_sel[0]), hi = key_to_float(ctx->h_sel[1]);
+    *median_host = (m % 2 == 0) ? (lo + hi) / 2.0f : lo;
+    return STEIN_OK;
+}
+
+int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, int64_t n, int64_t d,
+                        int64_t ld, float *median_host, float *mid_host, int32_t *sweeps_host) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    STEIN_TRY(check_layout(ctx, X_dev, n, d, ld));
+    STEIN_REQUIRE(ctx, median_host != nullptr, "null output pointer");
+    const uint64_t dim = (uint64_t)n * (uint64_t)n;
+    // compute_median.py:9-15: 0-based ascending ranks of the middle value(s)
+    const uint64_t ranks[2] = {dim % 2 == 0 ? dim / 2 - 1 : dim / 2, dim / 2};
+    const int64_t pilot_m = (dim >= (1ull << 24)) ? (1ll << 20) : 0;
+    STEIN_TRY(ensure_scratch(ctx, pilot_m));
+
+    Window win[2] = {kFullWindow, kFullWindow};
+    if (pilot_m) {
+        // sample ranks m/2 -+ 3.5 sqrt(m): the true median lies between them with
+        // probability ~1 - 1e-11; a miss is caught below and falls back to the
+        // full-range radix select.
+        pilot_kernel<<<(unsigned)((pilot_m + 255) / 256), 256, 0, ctx->stream>>>(
+            X_dev, r_dev, n, ld, pilot_m, 0x5eedull, ctx->d_pilot_keys);
+        STEIN_CHECK_LAUNCH(ctx);
+        const uint64_t delta = (uint64_t)(3.5 * sqrt((double)pilot_m));
+        select_keys_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_pilot_keys, pilot_m,
+                                                        pilot_m / 2 - delta, pilot_m / 2 + delta,
+                                                        ctx->d_sel);
+        STEIN_CHECK_LAUNCH(ctx);
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_sel, ctx->d_sel, sizeof(uint32_t) * 2,
+                                              cudaMemcpyDeviceToHost, ctx->stream));
+        STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const uint32_t ka = ctx->h_sel[0], kb = ctx->h_sel[1];
+        if (kb >= ka) {
+            const uint64_t span = (uint64_t)kb - ka + 1;
+            uint32_t sh = 0;
+            while (((span - 1) >> sh) >= (uint64_t)HIST_MAX_BINS) ++sh;
+            Window w = {ka, sh, (uint32_t)(((span - 1) >> sh) + 1)};
+            win[0] = win[1] = w;
+        }
+    }
+
+    const int world = ctx->has_comm ? ctx->comm.world : 1;
+    const int rank = ctx->has_comm ? ctx->comm.rank : 0;
+    const int64_t ntiles = stein_num_tiles(n);
+    const int64_t t0 = ntiles * rank / world, t1 = ntiles * (rank + 1) / world;
+
+    bool done[2] = {false, false};
+    uint32_t key[2] = {0u, 0u};
+    int sweeps = 0;
+    for (int iter = 0; iter < 16 && !(done[0] && done[1]); ++iter) {
+        const int q0 = done[0] ? 1 : 0;
+        const Window w = win[q0];
+        const size_t bytes = sizeof(uint64_t) * (w.nbins + 1);
+        STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->d_counts, 0, bytes, ctx->stream));
+        STEIN_TRY(stein_sqdist_hist(ctx, X_dev, r_dev, n, d, ld, t0, t1, w.key_lo, w.shift, w.nbins,
+                                    ctx->d_counts));
+        if (world > 1) {
+            if (ctx->comm.allreduce_sum_u64(ctx->comm.user, ctx->d_counts, (int64_t)w.nbins + 1) != 0)
+                return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+        }
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, bytes,
+                                              cudaMemcpyDeviceToHost, ctx->stream));
+        STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ++sweeps;
+        for (int q = q0; q < 2; ++q) {
+            if (done[q] || !(win[q] == w)) continue;
+            Window nw = w;
+            const int rc = stein_median_narrow(ctx->h_counts, w.key_lo, w.shift, w.nbins, ranks[q],
+                                               &key[q], &nw.key_lo, &nw.shift, &nw.nbins);
+            if (rc == 1) {
+                done[q] = true;
+            } else if (rc == 0) {
+                win[q] = nw;
+            } else {
+                if (w == kFullWindow)
+                    return fail(ctx, STEIN_ERR_INTERNAL, "rank outside the full key range");
+                win[q] = kFullWindow;  // pilot window missed: exact fallback
+            }
+        }
+    }
+    if (!(done[0] && done[1])) return fail(ctx, STEIN_ERR_INTERNAL, "median select did not converge");
+    const float lo = key_to_float(key[0]), hi = key_to_float(key[1]);
+    // compute_median.py:13 -- tf.reduce_mean of two fp32 values
+    *median_host = (dim % 2 == 0) ? (lo + hi) / 2.0f : lo;
+    if (mid_host) {
+        mid_host[0] = lo;
+        mid_host[1] = hi;
+    }
+    if (sweeps_host) *sweeps_host = sweeps;
+    return STEIN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,30 @@
+// phi_common.cuh -- declarations shared by the phi paths (dense FFMA, tcgen05 flash).
+#pragma once
+#include "common.cuh"
+
+namespace stein {
+
+constexpr int FINALIZE_MAX_BLOCKS = 1184;  // 8 x 148 SMs
+
+int launch_make_y(stein_ctx *ctx, const float *X, const float *S, int64_t rows, int64_t ld, float h2,
+                  float *Y);
+// phi = (sum over nslots partial O buffers + x * (sum of ksum slots) / h2) / n_total,
+// sum(phi^2) -> *sumsq (double, device) through `partials` (FINALIZE_MAX_BLOCKS doubles)
+int launch_finalize(stein_ctx *ctx, const float *O, int64_t slot_stride, int nslots, const float *ksum,
+                    int64_t ksum_slot_stride, const float *X_local, int64_t rows_valid, int64_t rows,
+                    int64_t ld, float h2, int64_t n_total, float *phi, double *partials,
+                    double *sumsq);
+
+int64_t dense_workspace_bytes(int64_t n_local, int64_t n_total, int64_t d);
+int phi_dense(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all,
+              int64_t n_total, int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2,
+              void *ws, int64_t ws_bytes, float *phi, double *sumsq);
+
+// tcgen05 flash path (phi_tc.cu)
+bool flash_tc_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d);
+int64_t flash_tc_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d);
+int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all,
+                 int64_t n_total, int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2,
+                 void *ws, int64_t ws_bytes, float *phi, double *sumsq);
+
+}  // namespace stein

@@ -1,0 +1,88 @@
+"""Collective hooks (include/stein_b200.h `stein_comm`) backed by
+torch.distributed -- NCCL over NVLink/NVSwitch on a B200 node.
+
+The engine is particle-row sharded: per iteration one
+all-gather of the particle and score shards, one u64 all-reduce per median
+sweep, one f64 all-reduce of sum(phi^2).  No other cross-GPU traffic.
+"""
+import ctypes
+
+from . import _lib
+
+
+class _DevMem:
+    """View of raw device memory for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {
+            "shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def make_comm(ctx, group=None):
+    """Build a `stein_comm` for `ctx` from the default (or given) process group
+    and install it.  Returns the struct (kept alive on the context)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = "cuda:%d" % ctx.device
+
+    def _tensor(ptr, count, typestr):
+        return torch.as_tensor(_DevMem(ptr, count, typestr), device=dev)
+
+    def allreduce_u64(_user, buf, count):
+        try:
+            # counts stay far below 2^63, so the int64 sum has the same bits
+            dist.all_reduce(_tensor(buf, count, "<i8"), group=group)
+            return 0
+        except Exception:       # surfaced by the C side as STEIN_ERR_COMM
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    def allreduce_f64(_user, buf, count):
+        try:
+            dist.all_reduce(_tensor(buf, count, "<f8"), group=group)
+            return 0
+        except Exception:
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    def allgather_f32(_user, send, recv, count):
+        try:
+            out = _tensor(recv, count * world, "<f4")
+            # `send` is the rank's own slice of `recv` (in-place all-gather)
+            inp = out[rank * count:(rank + 1) * count] if send == recv + 4 * rank * count \
+                else _tensor(send, count, "<f4")
+            dist.all_gather_into_tensor(out, inp, group=group)
+            return 0
+        except Exception:
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    comm = _lib.SteinComm(rank, world, None, _lib.HOOK(allreduce_u64), _lib.HOOK(allreduce_f64),
+                          _lib.HOOK_GATHER(allgather_f32))
+    ctx.check(ctx.lib.stein_ctx_set_comm(ctx.handle, ctypes.byref(comm)))
+    ctx._comm_keepalive = comm      # the C side copied the struct; keep the callbacks alive
+    return comm
+
+
+def shard_rows(n_total, world, rank, tile=128):
+    """Row range owned by `rank`: q = tile-padded ceil(n/world) rows per rank,
+    global rows [rank*q, min(n, (rank+1)*q)).  Mirrors stein_engine_create."""
+    per_rank = -(-n_total // world)              # ceil(n / world)
+    q = -(-per_rank // tile) * tile              # padded to whole tiles
+    begin = rank * q
+    n_local = max(0, min(q, n_total - begin))
+    return begin, n_local, q
+
+
+def shard_tiles(n_total, world, rank, tile=128):
+    """Upper-triangular distance-tile range swept by `rank` in the median
+    (mirrors stein_median_sqdist): contiguous, equal-cost chunks."""
+    T = -(-n_total // tile)
+    ntiles = T * (T + 1) // 2
+    return ntiles * rank // world, ntiles * (rank + 1) // world

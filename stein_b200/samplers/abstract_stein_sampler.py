@@ -1,0 +1,152 @@
+import ctypes
+from abc import abstractmethod
+
+import numpy as np
+
+from ..engine import SvgdEngine
+from ..kernels import SquaredExponentialKernel
+from ..log_p.base import LogPosterior, Output
+from ..optimizers._fused import FusedGradientDescent
+from ..runtime import context, ptr
+from ..utilities import convert_array_to_dictionary, convert_dictionary_to_array
+
+
+class AbstractSteinSampler:
+    """Stein variational gradient descent (Liu & Wang 2016) on a B200.
+
+    Mirrors stein/samplers/abstract_stein_sampler.py:7-196.  Same public surface:
+    `n_particles`, `model_vars`, `log_p`, `theta` (dict variable -> (n, *shape)
+    float64 array), `compute_phi`, `update_particles`, `function_posterior`.
+
+    Differences in mechanism, not in results: the particles, scores and optimizer
+    moments are device resident (fp32) in a `stein_engine` and `theta` is
+    materialised on the host only when read; there is no tf.Session (`sess` is
+    None).
+    """
+
+    def __init__(self, n_particles, log_p, theta=None):
+        if not isinstance(log_p, LogPosterior):
+            raise TypeError(
+                "log_p must be a stein_b200.log_p.LogPosterior (LinearRegression, "
+                "LogisticRegression, RegressionNeuralNetwork or TorchLogPosterior); "
+                "TensorFlow graphs are not supported")
+        self.n_particles = n_particles
+        self.sess = None
+        self.log_p = log_p
+        self.model_vars = list(log_p.model_vars)       # abstract_stein_sampler.py:49-51
+        self.grad_log_p = log_p.scores                 # :55 -- batched, all particles at once
+        self._access_indices = log_p.column_slices()
+        self._theta_cache = None
+        if theta is not None:
+            self._init_theta = dict(theta)             # :66-67
+        else:
+            # :69-74 -- same NumPy global-RNG draws, in model_vars (creation) order
+            self._init_theta = {
+                v: np.random.normal(size=[self.n_particles] + v.get_shape().as_list()) * 0.01
+                for v in self.model_vars
+            }
+        self._engine = None
+
+    # -- engine -------------------------------------------------------------------
+    def _make_engine(self, gd):
+        hyper = gd._hyper() if isinstance(gd, FusedGradientDescent) else dict(optimizer="adam")
+        self._engine = SvgdEngine(self.n_particles, self.log_p.n_params, **hyper)
+        if isinstance(gd, FusedGradientDescent):
+            gd._bind(self._engine)
+        full = convert_dictionary_to_array(self._init_theta)[0]
+        if full.shape != (self.n_particles, self.log_p.n_params):
+            raise ValueError("theta has shape %r, expected %r"
+                             % (full.shape, (self.n_particles, self.log_p.n_params)))
+        e = self._engine
+        e.set_particles(full[e.row_begin:e.row_begin + e.n_local])
+        self._init_theta = None
+
+    @property
+    def engine(self):
+        return self._engine
+
+    # -- particles as the reference exposes them -------------------------------------
+    @property
+    def theta(self):
+        """{variable: (n_local, *shape) float64}.  With one GPU n_local == n_particles."""
+        if self._theta_cache is None:
+            arr = self._engine.get_particles(np.float64)
+            self._theta_cache = convert_array_to_dictionary(arr, self._access_indices)
+        return self._theta_cache
+
+    @theta.setter
+    def theta(self, dictionary):
+        arr = convert_dictionary_to_array(dictionary)[0]
+        self._engine.set_particles(arr)
+        self._theta_cache = None
+
+    # -- phi ----------------------------------------------------------------------------
+    def compute_phi(self, theta_array, grads_array):
+        """(K.S + dK) / n for host arrays (abstract_stein_sampler.py:76-105), through
+        the fused GPU path: median -> bandwidth -> phi, K never materialised."""
+        import torch
+        if not isinstance(self.kernel, SquaredExponentialKernel):
+            raise NotImplementedError("only the squared-exponential kernel has a fused phi path")
+        ctx = context()
+        theta_array = np.asarray(theta_array)
+        n, d = theta_array.shape
+        X, S = ctx.to_padded(theta_array), ctx.to_padded(grads_array)
+        rows, ld = X.shape
+        r = torch.empty(rows, dtype=torch.float32, device=X.device)
+        ctx.check(ctx.lib.stein_row_norms(ctx.handle, ptr(X), n, d, ld, ptr(r)))
+        bw = self.kernel._bandwidth_dev(ctx, X, r, n, d)
+        ws_bytes = int(ctx.lib.stein_phi_workspace_bytes(ctx.handle, n, n, d))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)
+        phi = torch.empty_like(X)
+        sumsq = torch.zeros(1, dtype=torch.float64, device=X.device)
+        ctx.check(ctx.lib.stein_phi(ctx.handle, ptr(X), ptr(S), ptr(r), n, d, ld, 0, n, float(bw),
+                                    ptr(ws), ws_bytes, ptr(phi), ptr(sumsq)))
+        return phi[:n, :d].double().cpu().numpy()
+
+    def update_particles(self, grads_array):
+        """abstract_stein_sampler.py:107-127 for a host score matrix."""
+        e = self._engine
+        grads_array = np.ascontiguousarray(grads_array)
+        if isinstance(self.gd, FusedGradientDescent):
+            e.update_particles_host(grads_array)
+            self.gd._after_engine_step()
+        else:
+            # user-defined step rule: same sequence as the reference, phi from the GPU
+            e.set_scores(grads_array)
+            self._device_phi_only()
+            phi = e.get_phi(np.float64)
+            phi *= 10. / max(10., np.linalg.norm(phi))
+            e.set_particles(e.get_particles(np.float64) + self.gd.update(phi))
+        self._theta_cache = None
+
+    def _device_phi_only(self):
+        """phi for the scores in the engine, without the optimizer step."""
+        import torch
+        e, ctx = self._engine, self._engine.ctx
+        X, S = e.particles_dev, e.scores_dev
+        r = torch.empty(e.rows_padded, dtype=torch.float32, device=X.device)
+        ctx.check(ctx.lib.stein_row_norms(ctx.handle, ptr(X), e.n_particles, e.n_params, e.ld, ptr(r)))
+        bw = self.kernel._bandwidth_dev(ctx, X, r, e.n_particles, e.n_params)
+        ws_bytes = int(ctx.lib.stein_phi_workspace_bytes(ctx.handle, e.n_particles, e.n_particles, e.n_params))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)
+        sumsq = torch.zeros(1, dtype=torch.float64, device=X.device)
+        ctx.check(ctx.lib.stein_phi(ctx.handle, ptr(X), ptr(S), ptr(r), e.n_particles, e.n_params, e.ld,
+                                    0, e.n_particles, float(bw), ptr(ws), ws_bytes, ptr(e.phi_dev),
+                                    ptr(sumsq)))
+
+    # -- posterior functionals --------------------------------------------------------------
+    def function_posterior(self, func, feed_dict, axis=None):
+        """abstract_stein_sampler.py:129-168: `func` evaluated for every particle,
+        one row per particle; `axis` averages.  `func` is an Output handle of the
+        model (e.g. model.logits, model.pred): all particles in one kernel."""
+        if not isinstance(func, Output):
+            raise TypeError("func must be an Output handle of the model (e.g. model.logits)")
+        dist = func.model.evaluate(func, self._engine, feed_dict)
+        dist = dist.reshape(dist.shape[0], -1)
+        if axis is not None:
+            return dist.double().mean(dim=axis).cpu().numpy()
+        return dist.double().cpu().numpy()
+
+    @abstractmethod
+    def train_on_batch(self, batch_feed):
+        raise NotImplementedError()

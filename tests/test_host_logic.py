@@ -1,0 +1,196 @@
+"""CPU tests: the C-ABI library loads and exports every declared symbol, and the
+host-side logic (layout converters, key order, tile enumeration, radix-select
+narrowing, sharding plans) is correct.  No CUDA compute is called here."""
+import ctypes
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+
+from oracle import svgd_oracle as orc
+from stein_b200 import _lib
+from stein_b200.distributed import shard_rows, shard_tiles
+from stein_b200.utilities.converters import convert_array_to_dictionary, convert_dictionary_to_array
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "stein_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(stein_[a-z0-9_]+)\s*\(", header))
+    declared -= {"stein_comm"}
+    assert len(declared) >= 40
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libstein_b200.so lacks %s" % name
+    # and the Python binding table covers the header one to one
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_no_cpu_fallback_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = ctypes.c_void_p()
+    rc = lib.stein_ctx_create(ctypes.byref(h), 0, None)
+    assert rc == -2 and b"no CPU fallback" in lib.stein_last_error(None)
+    from stein_b200.runtime import context
+    with pytest.raises(_lib.SteinLibraryError):
+        context()
+
+
+def test_layout_helpers(lib):
+    assert [lib.stein_ld(d) for d in (1, 10, 32, 33, 55, 256, 753)] == [32, 32, 32, 64, 64, 256, 768]
+    assert [lib.stein_rows_padded(n) for n in (1, 100, 128, 129, 65536)] == [128, 128, 128, 256, 65536]
+
+
+def test_key_transform_is_monotone_and_invertible(lib):
+    rng = np.random.default_rng(0)
+    v = np.concatenate([rng.standard_normal(2000).astype(np.float32) * 10.0 ** rng.integers(-20, 20, 2000),
+                        np.array([0.0, -0.0, 1e-45, -1e-45, 3.4e38, -3.4e38], np.float32)]).astype(np.float32)
+    keys = np.array([lib.stein_float_to_key(ctypes.c_float(float(x))) for x in v], dtype=np.uint64)
+    order = np.argsort(v, kind="stable")
+    assert np.all(np.diff(keys[order].astype(np.int64)) >= 0)
+    back = np.array([lib.stein_key_to_float(ctypes.c_uint32(int(k))) for k in keys], np.float32)
+    np.testing.assert_array_equal(back, v + np.float32(0.0))
+    assert lib.stein_float_to_key(ctypes.c_float(-0.0)) == lib.stein_float_to_key(ctypes.c_float(0.0))
+
+
+def test_bandwidth_matches_oracle(lib):
+    for med, n in [(512.0, 65536), (0.73801529, 50), (18.559925, 100), (1e-6, 2), (3.0, 262144)]:
+        got = lib.stein_bandwidth(ctypes.c_float(med), n)
+        assert np.float32(got) == orc.bandwidth(np.float32(med), n)
+
+
+@pytest.mark.parametrize("n", [1, 100, 128, 129, 1000, 5000, 65536, 262144])
+def test_tile_enumeration(lib, n):
+    T = -(-n // 128)
+    nt = lib.stein_num_tiles(n)
+    assert nt == T * (T + 1) // 2
+    I, J = ctypes.c_int32(), ctypes.c_int32()
+    ts = list(range(min(nt, 300))) + list(range(max(0, nt - 300), nt)) + \
+        list(np.random.default_rng(n).integers(0, nt, 300))
+    for t in ts:
+        assert lib.stein_tile_coords(int(t), n, ctypes.byref(I), ctypes.byref(J)) == 0
+        i, j = I.value, J.value
+        assert 0 <= i <= j < T
+        assert i * T - i * (i - 1) // 2 + (j - i) == t
+    assert lib.stein_tile_coords(nt, n, ctypes.byref(I), ctypes.byref(J)) != 0
+
+
+def _hist(keys, key_lo, shift, nbins):
+    counts = np.zeros(nbins + 1, np.uint64)
+    counts[0] = np.sum(keys < key_lo)
+    inw = keys[keys >= key_lo]
+    b = (inw - key_lo) >> np.uint64(shift)
+    b = b[b < nbins]
+    np.add.at(counts, 1 + b.astype(np.int64), 1)
+    return counts
+
+
+def _select(lib, keys, rank, window):
+    """Drive stein_median_narrow exactly like stein_median_sqdist does."""
+    key_lo, shift, nbins = window
+    full = (0, 18, 16384)
+    sweeps = 0
+    for _ in range(10):
+        counts = _hist(keys, key_lo, shift, nbins)
+        sweeps += 1
+        ko, lo, sh, nb = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        rc = lib.stein_median_narrow(counts.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), key_lo, shift,
+                                     nbins, rank, ctypes.byref(ko), ctypes.byref(lo), ctypes.byref(sh),
+                                     ctypes.byref(nb))
+        if rc == 1:
+            return ko.value, sweeps
+        if rc == 0:
+            key_lo, shift, nbins = lo.value, sh.value, nb.value
+        else:
+            assert (key_lo, shift, nbins) != full
+            key_lo, shift, nbins = full
+    raise AssertionError("did not converge")
+
+
+def test_narrowing_selects_exact_rank(lib):
+    rng = np.random.default_rng(1)
+    vals = np.concatenate([rng.standard_normal(20000).astype(np.float32) * 3 + 500,
+                           np.zeros(300, np.float32), -rng.random(50).astype(np.float32) * 1e-6])
+    keys = np.array([lib.stein_float_to_key(ctypes.c_float(float(x))) for x in vals], dtype=np.uint64)
+    skeys = np.sort(keys)
+    for rank in [0, 1, 299, 350, len(keys) // 2 - 1, len(keys) // 2, len(keys) - 1]:
+        got, sweeps = _select(lib, keys, rank, (0, 18, 16384))
+        assert got == skeys[rank] and sweeps == 3
+    # a pilot-style window around the median: one or two sweeps
+    lo, hi = int(skeys[len(keys) // 2 - 400]), int(skeys[len(keys) // 2 + 400])
+    span = hi - lo + 1
+    sh = 0
+    while ((span - 1) >> sh) >= 16384:
+        sh += 1
+    got, sweeps = _select(lib, keys, len(keys) // 2, (lo, sh, ((span - 1) >> sh) + 1))
+    assert got == skeys[len(keys) // 2] and sweeps <= 2
+    # a window that misses the rank falls back to the full range and still succeeds
+    got, sweeps = _select(lib, keys, 10, (lo, sh, ((span - 1) >> sh) + 1))
+    assert got == skeys[10]
+    got, sweeps = _select(lib, keys, len(keys) - 5, (lo, sh, ((span - 1) >> sh) + 1))
+    assert got == skeys[len(keys) - 5]
+
+
+class FakeVar:
+    def __init__(self, name, shape):
+        self.name, self._shape = name, list(shape)
+
+    def get_shape(self):
+        return types.SimpleNamespace(as_list=lambda: list(self._shape))
+
+
+def test_product_converters_match_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "converters.npz"))
+    shapes = [[int(x) for x in s.split(",")] if s else [] for s in g["shapes"]]
+    vs = [FakeVar(str(nm), sh) for nm, sh in zip(g["names"], shapes)]
+    dictionary = {v: g["value_%d" % i] for i, v in enumerate(vs)}
+    array, access = convert_dictionary_to_array(dictionary)
+    np.testing.assert_array_equal(array, g["array"])
+    assert array.dtype == np.float64
+    assert [access[v] for v in vs] == list(zip(g["starts"], g["stops"]))
+    back = convert_array_to_dictionary(array, access)
+    for v in vs:
+        np.testing.assert_array_equal(back[v], dictionary[v])
+        assert back[v].shape == dictionary[v].shape
+
+
+def test_model_layouts_follow_the_name_sort():
+    from stein_b200.log_p import LinearRegression, LogisticRegression, RegressionNeuralNetwork
+    m = LogisticRegression(54, 464809)
+    assert m.n_params == 55 and m.column_slices()[m.w] == (0, 54) and m.column_slices()[m.log_alpha] == (54, 55)
+    b = RegressionNeuralNetwork(13, 50, 506)
+    sl = b.column_slices()
+    assert b.n_params == 753
+    assert [sl[v] for v in (b.log_lambda, b.log_gamma, b.w_1, b.b_1, b.w_2, b.b_2)] == \
+        [(0, 1), (1, 2), (2, 652), (652, 702), (702, 752), (752, 753)]
+    assert RegressionNeuralNetwork(90, 50, 515345).n_params == 4603
+    assert LinearRegression(10).n_params == 10
+    assert [v.name for v in b.model_vars][:2] == ["model/Variable:0", "model/Variable_1:0"]
+
+
+@pytest.mark.parametrize("n,world", [(65536, 8), (65536, 1), (1000, 2), (100, 4), (262144, 8), (129, 2)])
+def test_shard_plans_cover_everything_once(n, world):
+    rows = [shard_rows(n, world, r) for r in range(world)]
+    q = rows[0][2]
+    assert q % 128 == 0 and q * world >= n
+    covered = []
+    for r, (b, nl, qq) in enumerate(rows):
+        assert qq == q and b == r * q
+        covered += list(range(b, b + nl))
+    assert covered == list(range(n))
+    tiles = [shard_tiles(n, world, r) for r in range(world)]
+    T = -(-n // 128)
+    assert tiles[0][0] == 0 and tiles[-1][1] == T * (T + 1) // 2
+    assert all(tiles[r][1] == tiles[r + 1][0] for r in range(world - 1))
+    sizes = [b - a for a, b in tiles]
+    assert max(sizes) - min(sizes) <= 1
