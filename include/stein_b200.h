@@ -76,6 +76,15 @@ const char *stein_last_error(const stein_ctx *ctx /* NULL = last error of any ct
 /* number of kernels of this library launched on ctx since creation */
 int64_t stein_ctx_launch_count(const stein_ctx *ctx);
 
+/* Optional per-region device timing (CUDA events on the ctx stream), used by
+ * bench.py for the live roofline figure.  Regions: 0 = phi main kernel(s),
+ * 1 = median distance sweeps.  read() synchronises the stream, returns the
+ * accumulated milliseconds and launch count since the last reset, and resets. */
+#define STEIN_REGION_PHI 0
+#define STEIN_REGION_SWEEP 1
+int stein_ctx_profile_enable(stein_ctx *ctx, int enable);
+int stein_ctx_profile_read(stein_ctx *ctx, int region, double *ms_total, int64_t *launches);
+
 int64_t stein_ld(int64_t d);           /* leading dimension for d columns     */
 int64_t stein_rows_padded(int64_t n);  /* rows to allocate for n particles    */
 
@@ -187,6 +196,15 @@ int stein_score_logistic(stein_ctx *ctx, const float *theta_dev, int64_t n, int6
 int stein_score_bnn(stein_ctx *ctx, const float *theta_dev, int64_t n, int64_t F, int64_t H,
                     int64_t ld, const float *Xb_dev, const float *yb_dev, int64_t B,
                     double n_train, double prior_a, double prior_b, float *S_dev);
+
+/* Synthetic targets of BASELINE.json configs D/E (no data): isotropic Gaussian
+ * mixture with `ncomp` equal-weight components, means mu_dev (ncomp x d, dense)
+ * and common variance sigma2: S_i = sum_k r_ik (mu_k - x_i) / sigma2, r_ik the
+ * responsibilities.  ncomp = 1 with mu_dev = NULL is the standard normal target
+ * S = -X / sigma2.                                                             */
+int stein_score_gaussian_mixture(stein_ctx *ctx, const float *theta_dev, int64_t n, int64_t d,
+                                 int64_t ld, const float *mu_dev, int64_t ncomp, double sigma2,
+                                 float *S_dev);
 
 /* ---- function_posterior for the built-in models ----------------------------
  * replaces  AbstractSteinSampler.function_posterior  abstract_stein_sampler.py:157-159

@@ -40,6 +40,8 @@ SIGNATURES = {
     "stein_ctx_set_phi_impl": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "stein_last_error": (ctypes.c_char_p, [c_vp]),
     "stein_ctx_launch_count": (c_i64, [c_vp]),
+    "stein_ctx_profile_enable": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "stein_ctx_profile_read": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64)]),
     "stein_ld": (c_i64, [c_i64]),
     "stein_rows_padded": (c_i64, [c_i64]),
     "stein_row_norms": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
@@ -71,6 +73,7 @@ SIGNATURES = {
                                             c_f64, c_f64, c_vp]),
     "stein_score_bnn": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64,
                                        c_f64, c_f64, c_f64, c_vp]),
+    "stein_score_gaussian_mixture": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_f64, c_vp]),
     "stein_predict_linear": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "stein_predict_bnn": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "stein_engine_create": (ctypes.c_int, [ctypes.POINTER(c_vp), c_vp, c_i64, c_i64, ctypes.c_int,

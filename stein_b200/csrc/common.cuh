@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/stein_b200.h"
 
@@ -33,6 +35,10 @@ struct stein_ctx {
     uint32_t *d_sel = nullptr;      // device, 2 keys
     uint32_t *h_sel = nullptr;      // pinned
     int64_t pilot_cap = 0;
+    // optional region timing (bench.py): event pairs recorded on `stream`
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[2];
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;
 };
 
 namespace stein {
@@ -68,6 +74,32 @@ int fail(stein_ctx *ctx, int code, const char *fmt, ...);
         int _rc = (expr);            \
         if (_rc != STEIN_OK) return _rc; \
     } while (0)
+
+// RAII region timer: records an event pair around a region when profiling is on
+struct RegionTimer {
+    stein_ctx *ctx;
+    int region;
+    std::pair<cudaEvent_t, cudaEvent_t> ev{};
+    bool on;
+    RegionTimer(stein_ctx *c, int r) : ctx(c), region(r), on(c->profile) {
+        if (!on) return;
+        if (!ctx->prof_pool.empty()) {
+            ev = ctx->prof_pool.back();
+            ctx->prof_pool.pop_back();
+        } else {
+            cudaEventCreate(&ev.first);
+            cudaEventCreate(&ev.second);
+        }
+        cudaEventRecord(ev.first, ctx->stream);
+    }
+    void stop() {
+        if (!on) return;
+        cudaEventRecord(ev.second, ctx->stream);
+        ctx->prof_events[region].push_back(ev);
+        on = false;
+    }
+    ~RegionTimer() { stop(); }
+};
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 

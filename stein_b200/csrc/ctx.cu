@@ -69,6 +69,12 @@ int stein_ctx_destroy(stein_ctx *ctx) {
     if (ctx->d_pilot_keys) cudaFree(ctx->d_pilot_keys);
     if (ctx->d_sel) cudaFree(ctx->d_sel);
     if (ctx->h_sel) cudaFreeHost(ctx->h_sel);
+    for (int r = 0; r < 2; ++r)
+        for (auto &ev : ctx->prof_events[r]) ctx->prof_pool.push_back(ev);
+    for (auto &ev : ctx->prof_pool) {
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
     delete ctx;
     return STEIN_OK;
 }
@@ -103,6 +109,29 @@ int stein_ctx_set_phi_impl(stein_ctx *ctx, int impl) {
 
 const char *stein_last_error(const stein_ctx *ctx) {
     return ctx ? ctx->error.c_str() : g_last_error.c_str();
+}
+
+int stein_ctx_profile_enable(stein_ctx *ctx, int enable) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    ctx->profile = enable != 0;
+    return STEIN_OK;
+}
+
+int stein_ctx_profile_read(stein_ctx *ctx, int region, double *ms_total, int64_t *launches) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    STEIN_REQUIRE(ctx, region == STEIN_REGION_PHI || region == STEIN_REGION_SWEEP, "unknown region");
+    STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double total = 0.0;
+    for (auto &ev : ctx->prof_events[region]) {
+        float ms = 0.f;
+        STEIN_CHECK_CUDA(ctx, cudaEventElapsedTime(&ms, ev.first, ev.second));
+        total += ms;
+        ctx->prof_pool.push_back(ev);
+    }
+    if (ms_total) *ms_total = total;
+    if (launches) *launches = (int64_t)ctx->prof_events[region].size();
+    ctx->prof_events[region].clear();
+    return STEIN_OK;
 }
 
 int64_t stein_ctx_launch_count(const stein_ctx *ctx) { return ctx ? ctx->launches : 0; }

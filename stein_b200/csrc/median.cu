@@ -276,6 +276,7 @@ int stein_sqdist_hist(stein_ctx *ctx, const float *X_dev, const float *r_dev, in
     const int64_t ntiles = tile_end - tile_begin;
     const int64_t grid = std::min<int64_t>(ntiles, 2 * (int64_t)ctx->num_sms);
     const int64_t T = (n + TILE - 1) / TILE;
+    RegionTimer timer(ctx, STEIN_REGION_SWEEP);
     sqdist_hist_kernel<<<(unsigned)grid, GEMM_THREADS, smem, ctx->stream>>>(
         X_dev, r_dev, n, ld, T, tile_begin, tile_end, key_lo, shift, nbins,
         reinterpret_cast<unsigned long long *>(counts_dev));

@@ -231,6 +231,7 @@ int phi_dense(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
     const int64_t slab = dense_slab_rows(rows, cols);
 
     STEIN_TRY(launch_make_y(ctx, X_all, S_all, cols, ld, h2, Y));
+    RegionTimer timer(ctx, STEIN_REGION_PHI);   // gram_exp + rowsum + gemm_nn
     for (int64_t s0 = 0; s0 < rows; s0 += slab) {
         const int64_t sr = std::min(slab, rows - s0);
         dim3 g1((unsigned)(cols / TILE), (unsigned)(sr / TILE));
@@ -243,6 +244,7 @@ int phi_dense(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
         gemm_nn_kernel<<<g2, GEMM_THREADS, 0, ctx->stream>>>(K, cols, cols, Y, ld, O + s0 * ld, ld);
         STEIN_CHECK_LAUNCH(ctx);
     }
+    timer.stop();
     const int64_t rows_valid = std::max<int64_t>(0, std::min<int64_t>(n_local, n_total - row_begin));
     return launch_finalize(ctx, O, 0, 1, ksum, 0, X_all + row_begin * ld, rows_valid, rows, ld, h2,
                            n_total, phi, partials, sumsq);

@@ -237,6 +237,44 @@ predict_bnn_kernel(const float *__restrict__ theta, int64_t F, int64_t H, int64_
     out[(int64_t)blockIdx.y * N + t] = pred;
 }
 
+// S_i = sum_k r_ik (mu_k - x_i) / sigma2 ; one warp per particle
+__global__ void __launch_bounds__(256)
+gmm_score_kernel(const float *__restrict__ theta, int64_t n, int64_t d, int64_t ld,
+                 const float *__restrict__ mu, int ncomp, float inv_s2, float *__restrict__ S) {
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
+    const float *x = theta + i * ld;
+    float *out = S + i * ld;
+    if (ncomp == 1 && mu == nullptr) {
+        for (int64_t c = lane; c < d; c += 32) out[c] = -x[c] * inv_s2;
+        return;
+    }
+    // responsibilities from squared distances to the means (max-shifted softmax)
+    float logit[8];
+    float mx = -3.4e38f;
+    for (int k = 0; k < ncomp; ++k) {
+        float s = 0.0f;
+        for (int64_t c = lane; c < d; c += 32) {
+            const float df = x[c] - mu[(int64_t)k * d + c];
+            s = fmaf(df, df, s);
+        }
+        s = warp_sum(s);
+        logit[k] = -0.5f * s * inv_s2;
+        mx = fmaxf(mx, logit[k]);
+    }
+    float den = 0.0f;
+    for (int k = 0; k < ncomp; ++k) {
+        logit[k] = expf(logit[k] - mx);
+        den += logit[k];
+    }
+    for (int64_t c = lane; c < d; c += 32) {
+        float g = 0.0f;
+        for (int k = 0; k < ncomp; ++k) g = fmaf(logit[k], mu[(int64_t)k * d + c] - x[c], g);
+        out[c] = g / den * inv_s2;
+    }
+}
+
 static int glm_launch(stein_ctx *ctx, int model, const float *theta, int64_t n, int64_t F, int64_t ld,
                       const float *Xd, const float *y, int64_t N, float scale, float pa, float pb,
                       float *S) {
@@ -300,6 +338,20 @@ int stein_score_bnn(stein_ctx *ctx, const float *theta_dev, int64_t n, int64_t F
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bnn_score_kernel<<<(unsigned)n, SCORE_THREADS, smem, ctx->stream>>>(
         theta_dev, F, H, ld, Xb_dev, yb_dev, B, (float)n_train, (float)prior_a, (float)prior_b, S_dev);
+    STEIN_CHECK_LAUNCH(ctx);
+    return STEIN_OK;
+}
+
+int stein_score_gaussian_mixture(stein_ctx *ctx, const float *theta_dev, int64_t n, int64_t d, int64_t ld,
+                                 const float *mu_dev, int64_t ncomp, double sigma2, float *S_dev) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    STEIN_REQUIRE(ctx, theta_dev && S_dev, "null pointer");
+    STEIN_REQUIRE(ctx, n >= 1 && d >= 1 && ld >= d, "bad shape");
+    STEIN_REQUIRE(ctx, ncomp >= 1 && ncomp <= 8 && (mu_dev != nullptr || ncomp == 1),
+                  "1..8 components, means required when ncomp > 1");
+    STEIN_REQUIRE(ctx, sigma2 > 0, "sigma2 must be positive");
+    gmm_score_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(theta_dev, n, d, ld, mu_dev, (int)ncomp,
+                                                                     (float)(1.0 / sigma2), S_dev);
     STEIN_CHECK_LAUNCH(ctx);
     return STEIN_OK;
 }

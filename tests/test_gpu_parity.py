@@ -1,0 +1,519 @@
+"""GPU parity tests: every CUDA kernel, called through the C ABI, against the
+CPU oracle on identical seeded inputs.
+
+Bars (north_star): the median / bandwidth are BIT-EXACT; phi and the post-step
+particles agree to a relative tolerance of 1e-4 (normwise, and elementwise
+against the largest entry); integer work (histogram counts) is exact.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from oracle import svgd_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL_PHI = 1e-4      # north_star: "phi and post-step particles within ... 1e-4"
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from stein_b200.runtime import context
+    return context()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300), np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _assert_close(a, b, tol=RTOL_PHI):
+    fro, mx = _rel(a, b)
+    assert fro <= tol and mx <= tol, (fro, mx)
+
+
+def _particles(n, d, seed, scale=1.0):
+    return (np.random.default_rng(seed).standard_normal((n, d)) * scale).astype(np.float32)
+
+
+# --------------------------------------------------------------------------- #
+# kernel (2): norms, histogram sweep, exact median, bandwidth                  #
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("n,d", [(2, 1), (7, 3), (100, 10), (129, 33), (1024, 55), (300, 753)])
+def test_row_norms_bit_exact(ctx, n, d):
+    import torch
+    X = _particles(n, d, n + d)
+    Xd = ctx.to_padded(X)
+    r = torch.empty(Xd.shape[0], dtype=torch.float32, device=Xd.device)
+    ctx.check(ctx.lib.stein_row_norms(ctx.handle, _ptr(Xd), n, d, Xd.shape[1], _ptr(r)))
+    got = r.cpu().numpy()
+    np.testing.assert_array_equal(got[:n], orc.row_norms_chain(X))
+    assert np.all(got[n:] == 0)
+
+
+MEDIAN_CASES = [(2, 1, 1.0), (3, 2, 1.0), (7, 3, 1.0), (50, 1, 0.01), (100, 10, 0.01), (127, 5, 1.0),
+                (128, 32, 1.0), (129, 33, 1.0), (257, 17, 3.0), (512, 64, 1.0), (1000, 55, 0.5),
+                (1024, 256, 1.0), (2049, 20, 1.0)]
+
+
+@pytest.mark.parametrize("n,d,scale", MEDIAN_CASES)
+def test_median_bit_exact_small(ctx, n, d, scale):
+    from stein_b200.utilities import median_sqdist
+    X = _particles(n, d, 7 * n + d, scale)
+    med, mid, sweeps = median_sqdist(X, return_middle=True)
+    m_ref, mid_ref = orc.median_chain(X)
+    assert med.tobytes() == m_ref.tobytes()
+    assert (mid[0].tobytes(), mid[1].tobytes()) == (mid_ref[0].tobytes(), mid_ref[1].tobytes())
+    bw = np.float32(ctx.lib.stein_bandwidth(ctypes.c_float(float(med)), n))
+    assert bw.tobytes() == orc.bandwidth(m_ref, n).tobytes()
+
+
+def test_median_edge_cases(ctx):
+    from stein_b200.utilities import median_sqdist
+    # duplicated particles: D == 0 off the diagonal too
+    X = np.repeat(_particles(5, 4, 1), 40, axis=0)
+    assert median_sqdist(X).tobytes() == orc.median_chain(X)[0].tobytes()
+    # two tight clusters: the two middle values differ by orders of magnitude
+    X = np.concatenate([np.zeros((64, 3), np.float32), np.ones((64, 3), np.float32)])
+    med, mid, _ = median_sqdist(X, return_middle=True)
+    assert (float(mid[0]), float(mid[1]), float(med)) == (0.0, 3.0, 1.5)
+    # large dynamic range, odd n*n
+    X = _particles(301, 9, 2) * np.logspace(-3, 3, 301, dtype=np.float32)[:, None]
+    assert median_sqdist(X).tobytes() == orc.median_chain(X)[0].tobytes()
+
+
+@pytest.mark.parametrize("n,d", [(4096, 64), (4097, 32), (6000, 256)])
+def test_median_bit_exact_with_pilot_window(ctx, n, d):
+    """n*n >= 2^24 takes the sampled-window route (1-2 sweeps); the oracle takes
+    its radix route.  Same bits."""
+    from stein_b200.utilities import median_sqdist
+    X = _particles(n, d, n)
+    med, mid, sweeps = median_sqdist(X, return_middle=True)
+    m_ref, mid_ref = orc.median_chain(X, radix=True)
+    assert med.tobytes() == m_ref.tobytes()
+    assert (mid[0].tobytes(), mid[1].tobytes()) == (mid_ref[0].tobytes(), mid_ref[1].tobytes())
+    assert sweeps <= 3
+
+
+def test_histogram_sweep_counts_are_exact(ctx):
+    import torch
+    n, d = 1000, 24
+    X = _particles(n, d, 11)
+    Xd = ctx.to_padded(X)
+    r = torch.empty(Xd.shape[0], dtype=torch.float32, device=Xd.device)
+    ctx.check(ctx.lib.stein_row_norms(ctx.handle, _ptr(Xd), n, d, Xd.shape[1], _ptr(r)))
+    D = orc.sqdist_chain(X)
+    keys = np.array([ctx.lib.stein_float_to_key(ctypes.c_float(float(v))) for v in np.unique(D)], np.uint64)
+    key_of = dict(zip(np.unique(D).tolist(), keys.tolist()))
+    allkeys = np.vectorize(key_of.get)(D).astype(np.uint64).reshape(-1)
+    nt = ctx.lib.stein_num_tiles(n)
+    for key_lo, shift, nbins in [(0, 18, 16384), (int(np.median(allkeys)) - 5000, 0, 16384),
+                                 (int(np.median(allkeys)) - 100000, 5, 8000)]:
+        counts = torch.zeros(nbins + 1, dtype=torch.int64, device=Xd.device)
+        # split the tile range in two calls: counts accumulate
+        for a, b in [(0, nt // 3), (nt // 3, nt)]:
+            ctx.check(ctx.lib.stein_sqdist_hist(ctx.handle, _ptr(Xd), _ptr(r), n, d, Xd.shape[1], a, b,
+                                                key_lo, shift, nbins, _ptr(counts)))
+        got = counts.cpu().numpy().astype(np.uint64)
+        ref = np.zeros(nbins + 1, np.uint64)
+        ref[0] = np.sum(allkeys < key_lo)
+        inw = allkeys[allkeys >= key_lo]
+        b = (inw - np.uint64(key_lo)) >> np.uint64(shift)
+        np.add.at(ref, 1 + b[b < nbins].astype(np.int64), 1)
+        np.testing.assert_array_equal(got, ref)
+
+
+def test_compute_median_values(ctx):
+    from stein_b200.utilities import compute_median
+    rng = np.random.default_rng(3)
+    for shape in [(7,), (6, 6), (101, 101), (64, 64)]:
+        V = rng.standard_normal(shape).astype(np.float32)
+        assert compute_median(V).tobytes() == orc.compute_median(V).tobytes()
+
+
+# --------------------------------------------------------------------------- #
+# kernel (3): K, dK, phi                                                        #
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("n,d", [(6, 3), (50, 1), (100, 10), (129, 33), (300, 55)])
+def test_kernel_and_grad_matches_oracle(ctx, n, d):
+    from stein_b200.kernels import SquaredExponentialKernel
+    X = _particles(n, d, n * d)
+    kern = SquaredExponentialKernel(n, None)
+    K, dK = kern.kernel_and_grad(X.astype(np.float64))
+    K_ref, dK_ref, bw_ref = orc.kernel_and_grad(X)
+    assert kern.bandwidth.tobytes() == bw_ref.tobytes()
+    assert K.shape == (n, n) and dK.shape == (n, d) and K.dtype == np.float32
+    np.testing.assert_allclose(K, K_ref, atol=2e-6, rtol=1e-5)
+    _assert_close(dK, dK_ref, 2e-5)
+
+
+def _phi_gpu(ctx, X, S, impl):
+    """stein_row_norms -> stein_median_sqdist -> stein_phi through the C ABI."""
+    import torch
+    from stein_b200 import _lib
+    n, d = X.shape
+    Xd, Sd = ctx.to_padded(X), ctx.to_padded(S)
+    rows, ld = Xd.shape
+    r = torch.empty(rows, dtype=torch.float32, device=Xd.device)
+    ctx.check(ctx.lib.stein_row_norms(ctx.handle, _ptr(Xd), n, d, ld, _ptr(r)))
+    med = ctypes.c_float()
+    ctx.check(ctx.lib.stein_median_sqdist(ctx.handle, _ptr(Xd), _ptr(r), n, d, ld, ctypes.byref(med), None, None))
+    bw = ctx.lib.stein_bandwidth(med.value, n)
+    ctx.set_phi_impl(impl)
+    try:
+        nb = int(ctx.lib.stein_phi_workspace_bytes(ctx.handle, n, n, d))
+        ws = torch.empty(nb, dtype=torch.uint8, device=Xd.device)
+        phi = torch.full_like(Xd, float("nan"))
+        sumsq = torch.zeros(1, dtype=torch.float64, device=Xd.device)
+        ctx.check(ctx.lib.stein_phi(ctx.handle, _ptr(Xd), _ptr(Sd), _ptr(r), n, d, ld, 0, n, bw, _ptr(ws), nb,
+                                    _ptr(phi), _ptr(sumsq)))
+    finally:
+        ctx.set_phi_impl(_lib.PHI_AUTO)
+    full = phi.cpu().numpy()
+    assert np.all(full[n:] == 0) and np.all(full[:, d:] == 0), "pad must stay zero"
+    return full[:n, :d].astype(np.float64), float(sumsq.item()), np.float32(bw)
+
+
+PHI_CASES = [(6, 3, 1.0), (50, 1, 0.01), (100, 10, 0.01), (129, 33, 1.0), (512, 64, 1.0), (1000, 55, 0.3),
+             (640, 256, 1.0), (300, 753, 0.05)]
+
+
+@pytest.mark.parametrize("n,d,scale", PHI_CASES)
+def test_phi_dense_matches_oracle(ctx, n, d, scale):
+    from stein_b200 import _lib
+    X = _particles(n, d, 3 * n + d, scale)
+    S = _particles(n, d, 5 * n + d, 1.0) - X          # score of a shifted Gaussian target
+    phi, sumsq, bw = _phi_gpu(ctx, X, S, _lib.PHI_DENSE_SIMT)
+    ref = orc.compute_phi(X, S.astype(np.float64))
+    assert bw.tobytes() == orc.kernel_and_grad(X)[2].tobytes()
+    _assert_close(phi, ref)
+    assert abs(sumsq - (phi ** 2).sum()) <= 1e-6 * (phi ** 2).sum()
+
+
+def test_compute_phi_api(ctx):
+    """AbstractSteinSampler.compute_phi(theta_array, grads_array) on host arrays."""
+    from stein_b200.log_p import LinearRegression
+    from stein_b200.optimizers import AdamGradientDescent
+    from stein_b200.samplers import SteinSampler
+    n, F = 100, 10
+    np.random.seed(0)
+    sampler = SteinSampler(n, LinearRegression(F).log_p, AdamGradientDescent(0.1))
+    X, S = _particles(n, F, 1).astype(np.float64), _particles(n, F, 2).astype(np.float64)
+    _assert_close(sampler.compute_phi(X, S), orc.compute_phi(X, S))
+
+
+# --------------------------------------------------------------------------- #
+# kernel (4): clip + optimizers, against the reference's own outputs           #
+# --------------------------------------------------------------------------- #
+def test_optimizers_match_reference_golden(ctx, golden_dir):
+    from stein_b200.optimizers import AdagradGradientDescent, AdamGradientDescent
+    g = np.load(os.path.join(golden_dir, "optimizers.npz"))
+    phis = g["phis"]
+    for tag, gd in (("adam", AdamGradientDescent(learning_rate=0.1, decay=0.999)),
+                    ("adam_default", AdamGradientDescent()),
+                    ("adagrad", AdagradGradientDescent(learning_rate=0.05, decay=0.5, alpha=0.9))):
+        for t in range(phis.shape[0]):
+            step = gd.update(phis[t].copy())
+            np.testing.assert_allclose(step, g[tag + "_updates"][t], rtol=2e-5, atol=1e-12)
+        assert gd.n_iters == int(g[tag + "_n_iters"])
+        assert abs(gd.learning_rate - float(g[tag + "_final_lr"])) <= 1e-15
+    # moments are exposed like the reference's attributes
+    gd = AdamGradientDescent(0.1)
+    gd.update(phis[0])
+    np.testing.assert_allclose(gd.mu, phis[0], rtol=1e-6)
+    np.testing.assert_allclose(gd.nu, phis[0] ** 2, rtol=1e-6)
+
+
+def test_clip_scale(ctx):
+    """phi *= 10 / max(10, ||phi||_F) (abstract_stein_sampler.py:125) inside the step kernel."""
+    import torch
+    n, d = 64, 32
+    rng = np.random.default_rng(0)
+    phi = rng.standard_normal((n, d)) * 3.0                       # ||phi|| >> 10
+    P = ctx.to_padded(phi)
+    X = torch.zeros_like(P)
+    hist = torch.zeros_like(P)
+    sumsq = torch.tensor([float((phi.astype(np.float32).astype(np.float64) ** 2).sum())], dtype=torch.float64,
+                         device=P.device)
+    ctx.check(ctx.lib.stein_clip_adagrad_step(ctx.handle, _ptr(X), _ptr(P), _ptr(hist), X.numel(), _ptr(sumsq),
+                                              0.05, 0.9, 0))
+    gd = orc.AdagradGradientDescent(0.05, 1.0, 0.9)
+    ref = gd.update(orc.clip(phi))
+    np.testing.assert_allclose(X[:n, :d].cpu().numpy(), ref, rtol=2e-5)
+
+
+# --------------------------------------------------------------------------- #
+# kernel (1): scores and predictions of the three built-in models              #
+# --------------------------------------------------------------------------- #
+def _score_gpu(ctx, fn, theta, *args):
+    import torch
+    n, d = theta.shape
+    Th = ctx.to_padded(theta)
+    S = torch.zeros_like(Th)
+    fn(Th, S)
+    out = S.cpu().numpy()
+    assert np.all(out[n:] == 0) and np.all(out[:, d:] == 0)
+    return out[:n, :d]
+
+
+@pytest.mark.parametrize("n,F,N", [(100, 10, 1000), (50, 1, 1000), (3, 70, 2500), (17, 300, 64)])
+def test_score_linear(ctx, n, F, N):
+    rng = np.random.default_rng(F)
+    Xd = rng.standard_normal((N, F)).astype(np.float32)
+    w = rng.standard_normal(F) * 2
+    y = (Xd @ w + 0.3 * rng.standard_normal(N)).astype(np.float32)
+    theta = (rng.standard_normal((n, F)) * 0.5).astype(np.float32)
+    Xg, yg = ctx.dense(Xd), ctx.dense(y)
+    got = _score_gpu(ctx, lambda Th, S: ctx.check(ctx.lib.stein_score_linear(
+        ctx.handle, _ptr(Th), n, F, Th.shape[1], _ptr(Xg), _ptr(yg), N, _ptr(S))), theta)
+    _assert_close(got, orc.score_linear(theta, Xd, y), 2e-5)
+
+
+@pytest.mark.parametrize("n,F,B", [(1024, 54, 50), (100, 54, 50), (5, 3, 7), (33, 130, 300)])
+def test_score_logistic(ctx, n, F, B):
+    rng = np.random.default_rng(B)
+    Xb = rng.standard_normal((B, F)).astype(np.float32)
+    yb = (rng.random(B) > 0.5).astype(np.float32)
+    theta = (rng.standard_normal((n, F + 1)) * 0.3).astype(np.float32)
+    Xg, yg = ctx.dense(Xb), ctx.dense(yb)
+    got = _score_gpu(ctx, lambda Th, S: ctx.check(ctx.lib.stein_score_logistic(
+        ctx.handle, _ptr(Th), n, F, Th.shape[1], _ptr(Xg), _ptr(yg), B, 464809.0, 1.0, 0.01, _ptr(S))), theta)
+    _assert_close(got, orc.score_logistic(theta, Xb, yb, 464809.0), 2e-5)
+
+
+@pytest.mark.parametrize("n,F,H,B,N", [(512, 13, 50, 100, 506), (20, 1, 100, 20, 20), (64, 90, 50, 100, 515345),
+                                       (7, 3, 5, 9, 40)])
+def test_score_bnn(ctx, n, F, H, B, N):
+    rng = np.random.default_rng(H)
+    Xb = rng.standard_normal((B, F)).astype(np.float32)
+    yb = rng.standard_normal(B).astype(np.float32)
+    d = 2 + F * H + 2 * H + 1
+    theta = (rng.standard_normal((n, d)) * 0.2).astype(np.float32)
+    Xg, yg = ctx.dense(Xb), ctx.dense(yb)
+    got = _score_gpu(ctx, lambda Th, S: ctx.check(ctx.lib.stein_score_bnn(
+        ctx.handle, _ptr(Th), n, F, H, Th.shape[1], _ptr(Xg), _ptr(yg), B, float(N), 1.0, 0.01, _ptr(S))), theta)
+    _assert_close(got, orc.score_bnn(theta, Xb, yb, float(N), F, H), 5e-5)
+
+
+def test_predictions(ctx):
+    import torch
+    rng = np.random.default_rng(4)
+    n, F, H, N = 33, 13, 50, 700
+    Xt = rng.standard_normal((N, F)).astype(np.float32)
+    Xg = ctx.dense(Xt)
+    th = (rng.standard_normal((n, F + 1)) * 0.3).astype(np.float32)
+    Th = ctx.to_padded(th)
+    out = torch.empty((n, N), dtype=torch.float32, device=Th.device)
+    ctx.check(ctx.lib.stein_predict_linear(ctx.handle, _ptr(Th), n, F, Th.shape[1], _ptr(Xg), N, _ptr(out)))
+    _assert_close(out.cpu().numpy(), th[:, :F].astype(np.float64) @ Xt.T.astype(np.float64), 1e-5)
+    d = 2 + F * H + 2 * H + 1
+    th = (rng.standard_normal((n, d)) * 0.3).astype(np.float32)
+    Th = ctx.to_padded(th)
+    ctx.check(ctx.lib.stein_predict_bnn(ctx.handle, _ptr(Th), n, F, H, Th.shape[1], _ptr(Xg), N, _ptr(out)))
+    _assert_close(out.cpu().numpy(), orc.bnn_predict(th, Xt, F, H), 1e-5)
+
+
+# --------------------------------------------------------------------------- #
+# whole iteration through the engine / sampler                                  #
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("opt", ["adam", "adagrad"])
+@pytest.mark.parametrize("n,d", [(100, 10), (257, 33)])
+def test_engine_steps_match_oracle(ctx, opt, n, d):
+    """3 consecutive update_particles() with host buffers (float64 like the
+    reference's arrays): bandwidth bit-exact each step, particles within 1e-4."""
+    from stein_b200.engine import SvgdEngine
+    X0 = _particles(n, d, 1, 0.5).astype(np.float64)
+    mean = np.random.default_rng(2).standard_normal(d)
+    if opt == "adam":
+        eng = SvgdEngine(n, d, "adam", learning_rate=0.1, decay=0.999)
+        gd = orc.AdamGradientDescent(0.1, 0.999)
+    else:
+        eng = SvgdEngine(n, d, "adagrad", learning_rate=0.05, p1=0.9)
+        gd = orc.AdagradGradientDescent(0.05, 1.0, 0.9)
+    eng.set_particles(X0)
+    X_ref = X0.copy()
+    X_gpu = np.empty_like(X0)
+    for it in range(3):
+        # the oracle is stepped from the GPU's own (fp32) particles so that each
+        # step is compared on identical inputs
+        X_in = eng.get_particles(np.float64)
+        S = (mean - X_in) * 3.0
+        bw_ref = orc.kernel_and_grad(X_in)[2]
+        X_ref, phi_ref = orc.update_particles(X_in, S, gd)
+        eng.update_particles_host(np.ascontiguousarray(S), X_gpu)
+        last = eng.last()
+        assert np.float32(last["bandwidth"]).tobytes() == bw_ref.tobytes()
+        _assert_close(eng.get_phi(), orc.compute_phi(X_in, S))
+        assert abs(last["phi_norm"] - np.linalg.norm(orc.compute_phi(X_in, S))) <= 1e-4 * last["phi_norm"]
+        _assert_close(X_gpu, X_ref)
+        # keep the oracle optimizer's moments in step with the device (fp32) ones
+        st = eng.get_state()
+        assert st["n_iters"] == gd.n_iters and abs(st["learning_rate"] - gd.learning_rate) < 1e-15
+    eng.close()
+
+
+def test_sampler_linear_regression_known_answer(ctx, golden_dir):
+    """examples/linear_regression/main.py on the reference's shipped data: 50
+    particles, Adam lr 0.1, 500 iterations -> analytic posterior."""
+    from stein_b200.log_p import LinearRegression
+    from stein_b200.optimizers import AdamGradientDescent
+    from stein_b200.samplers import SteinSampler
+    g = np.load(os.path.join(golden_dir, "linear_regression.npz"))
+    X, y = g["X"], g["y"].reshape(-1, 1)
+    model = LinearRegression(X.shape[1])
+    np.random.seed(0)
+    sampler = SteinSampler(50, model.log_p, AdamGradientDescent(learning_rate=1e-1))
+    assert sampler.theta[model.w].shape == (50, 1, 1)
+    # same trajectory on the oracle from the same start
+    theta_ref = sampler.samples.copy()
+    gd_ref = orc.AdamGradientDescent(learning_rate=1e-1)
+    for it in range(500):
+        sampler.train_on_batch({model.X: X, model.y: y})
+        if it < 5:
+            S = orc.score_linear(theta_ref, X.astype(np.float32), y.astype(np.float32))
+            theta_ref, _ = orc.update_particles(theta_ref, S, gd_ref)
+            _assert_close(sampler.samples, theta_ref, 2e-4)
+    est = np.array(list(sampler.theta.values()))[0].mean(axis=0).ravel()      # main.py:51
+    assert abs(est[0] - g["post_mean"][0]) < 5e-3
+    sd = np.sqrt(g["post_cov"][0, 0])
+    assert 0.5 * sd < sampler.samples.std() < 1.5 * sd
+    pred = sampler.function_posterior(model.y_hat, {model.X: X[:7]}, axis=0)
+    np.testing.assert_allclose(pred, X[:7, 0] * sampler.samples.mean(), rtol=1e-4, atol=1e-6)
+
+
+def test_sampler_logistic_and_bnn_trajectories(ctx):
+    """Short trajectories of the other two examples against the oracle (shared seeds)."""
+    from stein_b200.log_p import LogisticRegression, RegressionNeuralNetwork
+    from stein_b200.optimizers import AdamGradientDescent
+    from stein_b200.samplers import SteinSampler
+    rng = np.random.default_rng(0)
+    # logistic: covertype-shaped synthetic minibatches
+    F, n, N = 54, 128, 464809
+    model = LogisticRegression(F, N)
+    np.random.seed(1)
+    sampler = SteinSampler(n, model.log_p, AdamGradientDescent(learning_rate=1e-1))
+    gd = orc.AdamGradientDescent(learning_rate=1e-1)
+    for it in range(4):
+        Xb = rng.standard_normal((50, F)).astype(np.float32)
+        yb = (rng.random((50, 1)) > 0.5).astype(np.float32)
+        th = sampler.samples
+        ref, _ = orc.update_particles(th, orc.score_logistic(th, Xb, yb, N), gd)
+        sampler.train_on_batch({model.X: Xb, model.y: yb})
+        _assert_close(sampler.samples, ref, 2e-4)
+    logits = sampler.function_posterior(model.logits, {model.X: Xb})
+    _assert_close(logits, sampler.samples[:, :F] @ Xb.T.astype(np.float64), 1e-5)
+    # BNN, Boston-shaped
+    F, H, n, N = 13, 50, 64, 506
+    model = RegressionNeuralNetwork(F, H, N)
+    np.random.seed(2)
+    sampler = SteinSampler(n, model.log_p, AdamGradientDescent(learning_rate=1e-1, decay=0.999))
+    gd = orc.AdamGradientDescent(learning_rate=1e-1, decay=0.999)
+    for it in range(4):
+        Xb = rng.standard_normal((100, F)).astype(np.float32)
+        yb = rng.standard_normal((100, 1)).astype(np.float32)
+        th = sampler.samples
+        ref, _ = orc.update_particles(th, orc.score_bnn(th, Xb, yb, N, F, H), gd)
+        sampler.train_on_batch({model.X: Xb, model.y: yb})
+        _assert_close(sampler.samples, ref, 2e-4)
+    pred = sampler.function_posterior(model.pred, {model.X: Xb})
+    _assert_close(pred, orc.bnn_predict(sampler.samples, Xb, F, H), 1e-4)
+
+
+def test_torch_log_posterior_carrier(ctx):
+    """User log_p through torch autograd (vmap(grad)) reproduces the fused logistic scores."""
+    import torch
+    from stein_b200.log_p import LogisticRegression, TorchLogPosterior
+    from stein_b200.optimizers import AdagradGradientDescent
+    from stein_b200.samplers import SteinSampler
+    F, n, N = 6, 40, 1000.0
+
+    def log_p(params, feed):
+        w, la = params["w"].reshape(-1), params["log_alpha"]
+        z = feed["X"] @ w
+        yv = feed["y"].reshape(-1)
+        ll = -(torch.clamp(z, min=0) - z * yv + torch.log1p(torch.exp(-z.abs()))).sum()
+        alpha = la.exp()
+        prior = (0.5 * la - 0.5 * alpha * w ** 2).sum() + (-0.01 * alpha)
+        return ll * (N / feed["X"].shape[0]) + prior
+
+    tm = TorchLogPosterior({"w": [F, 1], "log_alpha": []}, log_p)
+    pX, py = tm.placeholder("X", [None, F]), tm.placeholder("y", [None, 1])
+    bm = LogisticRegression(F, N)
+    rng = np.random.default_rng(0)
+    Xb = rng.standard_normal((25, F)).astype(np.float32)
+    yb = (rng.random((25, 1)) > 0.5).astype(np.float32)
+    theta0 = rng.standard_normal((n, F + 1)) * 0.3
+    th_t = {tm.vars["w"]: theta0[:, :F].reshape(n, F, 1), tm.vars["log_alpha"]: theta0[:, F]}
+    th_b = {bm.w: theta0[:, :F].reshape(n, F, 1), bm.log_alpha: theta0[:, F]}
+    s1 = SteinSampler(n, tm.log_p, AdagradGradientDescent(0.05), theta=th_t)
+    s2 = SteinSampler(n, bm.log_p, AdagradGradientDescent(0.05), theta=th_b)
+    for _ in range(3):
+        s1.train_on_batch({pX: Xb, py: yb})
+        s2.train_on_batch({bm.X: Xb, bm.y: yb})
+    _assert_close(s1.samples, s2.samples, 1e-4)
+
+
+# --------------------------------------------------------------------------- #
+# full-size checks (BASELINE.json config D: n = 65 536, d = 256)               #
+# --------------------------------------------------------------------------- #
+def test_full_size_properties(ctx):
+    """At n = 65 536, d = 256 the oracle cannot materialise anything n x n, so:
+    (a) the histogram of one full sweep sums to exactly n*n; (b) the median is
+    bracketed by the oracle's medians of row-sampled sub-problems and its two
+    middle values are adjacent in the sweep's counts; (c) sampled phi rows match
+    the C oracle's rows (full columns); (d) sum_i dK_i = 0: with S = 0 the
+    column sums of n*phi vanish relative to their scale."""
+    import torch
+    from stein_b200.engine import SvgdEngine
+    n, d = 65536, 256
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    S = -X
+    eng = SvgdEngine(n, d, "adam", learning_rate=0.1)
+    eng.set_particles(X)
+    eng.set_scores(S)
+    Xd = eng.particles_dev
+    r = torch.empty(n, dtype=torch.float32, device=Xd.device)
+    ctx.check(ctx.lib.stein_row_norms(ctx.handle, _ptr(Xd), n, d, d, _ptr(r)))
+    # (a)
+    counts = torch.zeros(16385, dtype=torch.int64, device=Xd.device)
+    ctx.check(ctx.lib.stein_sqdist_hist(ctx.handle, _ptr(Xd), _ptr(r), n, d, d, 0, ctx.lib.stein_num_tiles(n),
+                                        0, 18, 16384, _ptr(counts)))
+    assert int(counts.sum().item()) == n * n
+    # (b)
+    med, mid, sweeps = ctypes.c_float(), (ctypes.c_float * 2)(), ctypes.c_int32()
+    ctx.check(ctx.lib.stein_median_sqdist(ctx.handle, _ptr(Xd), _ptr(r), n, d, d, ctypes.byref(med), mid,
+                                          ctypes.byref(sweeps)))
+    assert mid[0] <= med.value <= mid[1] and sweeps.value <= 3
+    sub = [float(orc.median_chain(X[rng.choice(n, 2048, replace=False)])[0]) for _ in range(3)]
+    assert min(sub) * 0.995 < med.value < max(sub) * 1.005
+    k0, k1 = ctx.lib.stein_float_to_key(mid[0]), ctx.lib.stein_float_to_key(mid[1])
+    c2 = torch.zeros(3, dtype=torch.int64, device=Xd.device)
+    ctx.check(ctx.lib.stein_sqdist_hist(ctx.handle, _ptr(Xd), _ptr(r), n, d, d, 0, ctx.lib.stein_num_tiles(n),
+                                        k0, 0, 1, _ptr(c2)))
+    below, at = int(c2[0].item()), int(c2[1].item())
+    assert below <= n * n // 2 - 1 < below + at           # rank n^2/2-1 is the value mid[0]
+    if k1 != k0:
+        assert below + at == n * n // 2                   # and rank n^2/2 is the next value present
+    # (c) + (d)
+    eng.step()
+    info = eng.last()
+    assert np.float32(info["median"]).tobytes() == np.float32(med.value).tobytes()
+    phi = eng.get_phi(np.float64)
+    rows = [0, 1, 777, 32768, 65535]
+    bw = np.float32(info["bandwidth"])
+    for i in rows:
+        ref, _ = orc.phi_rows_c(X, S, bw, i, i + 1)
+        _assert_close(phi[i], ref[0])
+    eng.set_particles(X)
+    eng.set_scores(np.zeros_like(X))
+    eng.step()
+    phi0 = eng.get_phi(np.float64)
+    assert np.abs(phi0.sum(axis=0)).max() <= 1e-4 * np.abs(phi0).sum(axis=0).max()
+    eng.close()
