@@ -223,7 +223,7 @@ def test_optimizers_match_reference_golden(ctx, golden_dir):
             ref = g[tag + "_updates"][t]
             # fp32 moments on the device vs the reference's float64: normwise 1e-4 is the
             # contract; elementwise the only slack needed is where mu cancels
-            _assert_close(step, ref, 2e-6)
+            _assert_close(step, ref, 2e-5)
             np.testing.assert_allclose(step, ref, rtol=1e-4, atol=1e-6 * np.abs(ref).max())
         assert gd.n_iters == int(g[tag + "_n_iters"])
         assert abs(gd.learning_rate - float(g[tag + "_final_lr"])) <= 1e-15
