@@ -1,14 +1,526 @@
-// phi_tc.cu -- kernel (3), tcgen05/TMEM/TMA flash path (placeholder until the
-// tensor-core kernel lands; AUTO dispatch uses the dense FFMA path meanwhile).
+// phi_tc.cu -- kernel (3): fused "flash" phi on the Blackwell tensor path
+// (tcgen05.mma + TMEM accumulators + TMA operand staging).  K is never stored.
+//
+// Reference math: stein/kernels/squared_exponential_kernel.py:22-35 and
+// stein/samplers/abstract_stein_sampler.py:100-105, in the algebraic form of
+// phi_dense.cu:   O_i = sum_j K_ij y_j,  y_j = s_j - x_j/h^2,  ksum_i = sum_j K_ij,
+//                 phi_i = (O_i + x_i ksum_i / h^2) / n.
+//
+// One CTA owns a 128-row particle tile I (A operand, resident in shared memory)
+// and streams column tiles J of 128 particles:
+//   GEMM1  S   = X_I X_J^T                (tcgen05.mma kind::tf32, SS, D in TMEM, 128 columns)
+//   exp    P   = exp2(S c1 + a_i + b_j)   (4 warps: tcgen05.ld -> FFMA/MUFU -> tcgen05.st, in place)
+//   GEMM2  O  += P Y_J                    (tcgen05.mma kind::tf32, A = P from TMEM, D = O in TMEM)
+// TMEM columns: [0, DP) = O accumulator, [256,384) and [384,512) = two S/P buffers, so
+// GEMM1 of tile j+1 overlaps the exponentials of tile j (FlashAttention-4 style pipeline).
+// Operands arrive through a 6-stage ring of 16 KB TMA boxes (128 rows x 128 B,
+// SWIZZLE_128B, K-major).  Work is split stream-K style: the nI*nJ tile pairs are
+// cut into gridDim.x equal contiguous ranges, partial O / ksum of a range go to a
+// per-(I tile) slot and are summed in fixed order by finalize_phi_kernel.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warps 2..5 = exponential/epilogue warpgroup (warp w owns TMEM lanes 32*(w%4)..).
+#include <algorithm>
+#include <vector>
+
 #include "phi_common.cuh"
+#include "tc_common.cuh"
 
 namespace stein {
 
-bool flash_tc_supported(const stein_ctx *, int64_t, int64_t, int64_t) { return false; }
-int64_t flash_tc_workspace_bytes(const stein_ctx *, int64_t, int64_t, int64_t) { return 0; }
-int phi_flash_tc(stein_ctx *ctx, const float *, const float *, const float *, int64_t, int64_t, int64_t,
-                 int64_t, int64_t, float, void *, int64_t, float *, double *) {
-    return fail(ctx, STEIN_ERR_UNSUPPORTED, "flash tcgen05 phi kernel not built");
+using namespace tc;
+
+constexpr int FL_THREADS = 192;
+constexpr int FL_STAGES = 6;
+constexpr uint32_t FL_UNIT_BYTES = 128 * 128;   // one TMA box: 128 rows x 128 bytes
+constexpr int FL_MAX_DP = 256;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TMEM_S0 = 256, TMEM_S1 = 384;
+
+struct FlashParams {
+    int nJ;              // column tiles
+    int kblocks;         // DP / 32: 128-byte K blocks per row
+    int nhalf;           // DP / 128: 128-column halves of the O accumulator
+    int DP;
+    long long U;         // nI * nJ tile pairs
+    int row_tile0;       // first global tile of the local row block
+    float c1;            // log2(e) / h^2
+    const float *nrm;    // -r_j log2(e) / (2 h^2); -inf for j >= n
+    float *Opart;        // [slot][rows_local][DP]
+    long long o_slot_stride;
+    float *ksum_part;    // [slot][rows_local]
+    long long k_slot_stride;
+};
+
+struct FlashBarriers {
+    uint64_t full[FL_STAGES], empty[FL_STAGES];
+    uint64_t a_full, a_empty;
+    uint64_t s_full[2], p_full[2];
+    uint64_t o_full, o_empty;
+};
+
+// segment iteration shared by the three roles: CTA c owns pairs [c*U/G, (c+1)*U/G)
+struct SegIter {
+    long long u, u1;
+    int nJ;
+    __device__ SegIter(const FlashParams &p) : nJ(p.nJ) {
+        const long long G = gridDim.x, c = blockIdx.x;
+        u = c * p.U / G;
+        u1 = (c + 1) * p.U / G;
+    }
+    __device__ bool next(int &t, int &j0, int &j1) {
+        if (u >= u1) return false;
+        t = (int)(u / nJ);
+        j0 = (int)(u % nJ);
+        const long long left = u1 - u;
+        j1 = (int)((long long)j0 + left < (long long)nJ ? (long long)j0 + left : (long long)nJ);
+        u += j1 - j0;
+        return true;
+    }
+};
+
+__global__ void __launch_bounds__(FL_THREADS, 1)
+flash_phi_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
+                 const FlashParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B-swizzle atoms
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;                                           // kblocks x 16 KB
+    uint8_t *sRing = sA + (size_t)p.kblocks * FL_UNIT_BYTES;      // FL_STAGES x 16 KB
+    uint8_t *tail = sRing + (size_t)FL_STAGES * FL_UNIT_BYTES;
+    FlashBarriers *bars = reinterpret_cast<FlashBarriers *>(tail);
+    float *sB = reinterpret_cast<float *>(tail + 256);            // [2][128]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 256 + 1024);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < FL_STAGES; ++s) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], 1);
+        }
+        mbar_init(&bars->a_full, 1);
+        mbar_init(&bars->a_empty, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars->s_full[b], 1);
+            mbar_init(&bars->p_full[b], 128);
+        }
+        mbar_init(&bars->o_full, 1);
+        mbar_init(&bars->o_empty, 128);
+        fence_barrier_init();
+        fence_proxy_async();
+        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapY);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            auto emit = [&](const CUtensorMap *map, int c_inner, int c_outer) {
+                mbar_wait(&bars->empty[stage], phase ^ 1);
+                mbar_expect_tx(&bars->full[stage], FL_UNIT_BYTES);
+                tma_load_2d(sRing + (size_t)stage * FL_UNIT_BYTES, map, &bars->full[stage], c_inner, c_outer);
+                if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
+            };
+            auto emit_g1 = [&](int j) {
+                for (int kb = 0; kb < p.kblocks; ++kb) emit(&mapX, kb * 32, j * 128);
+            };
+            auto emit_g2 = [&](int j) {
+                for (int kb2 = 0; kb2 < 4; ++kb2)
+                    for (int h = 0; h < p.nhalf; ++h) emit(&mapY, j * 128 + kb2 * 32, h * 128);
+            };
+            SegIter it(p);
+            int t, j0, j1, seg = 0;
+            while (it.next(t, j0, j1)) {
+                if (seg > 0) mbar_wait(&bars->a_empty, (uint32_t)((seg - 1) & 1));
+                mbar_expect_tx(&bars->a_full, (uint32_t)p.kblocks * FL_UNIT_BYTES);
+                for (int kb = 0; kb < p.kblocks; ++kb)
+                    tma_load_2d(sA + (size_t)kb * FL_UNIT_BYTES, &mapX, &bars->a_full, kb * 32,
+                                (p.row_tile0 + t) * 128);
+                emit_g1(j0);
+                for (int j = j0; j < j1; ++j) {
+                    if (j + 1 < j1) emit_g1(j + 1);
+                    emit_g2(j);
+                }
+                ++seg;
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(FMT_TF32, 128, 128);
+            int stage = 0;
+            uint32_t phase = 0;
+            long long jj = 0;   // running column-tile counter of this CTA (S/P buffer = jj & 1)
+            auto g1 = [&](long long jcount) {
+                const uint32_t d_tmem = tmem + ((jcount & 1) ? TMEM_S1 : TMEM_S0);
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(&bars->full[stage], phase);
+                    tcgen05_fence_after();
+                    const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(sA + (size_t)kb * FL_UNIT_BYTES));
+                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sRing + (size_t)stage * FL_UNIT_BYTES));
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        umma_tf32_ss(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0);
+                    tcgen05_commit(&bars->empty[stage]);
+                    if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(&bars->s_full[jcount & 1]);
+            };
+            auto g2 = [&](long long jcount, bool first_of_segment) {
+                const uint32_t a_tmem = tmem + ((jcount & 1) ? TMEM_S1 : TMEM_S0);
+                for (int kb2 = 0; kb2 < 4; ++kb2) {
+                    for (int h = 0; h < p.nhalf; ++h) {
+                        mbar_wait(&bars->full[stage], phase);
+                        tcgen05_fence_after();
+                        const uint64_t bdesc =
+                            make_kmajor_sw128_desc(smem_u32(sRing + (size_t)stage * FL_UNIT_BYTES));
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            umma_tf32_ts(tmem + h * 128, a_tmem + kb2 * 32 + k4 * 8, bdesc + 2 * k4, idesc,
+                                         !(first_of_segment && kb2 == 0 && k4 == 0));
+                        tcgen05_commit(&bars->empty[stage]);
+                        if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            };
+            SegIter it(p);
+            int t, j0, j1, seg = 0;
+            while (it.next(t, j0, j1)) {
+                mbar_wait(&bars->a_full, (uint32_t)(seg & 1));
+                tcgen05_fence_after();
+                g1(jj);
+                for (int j = j0; j < j1; ++j, ++jj) {
+                    if (j + 1 < j1) g1(jj + 1);
+                    mbar_wait(&bars->p_full[jj & 1], (uint32_t)((jj >> 1) & 1));
+                    tcgen05_fence_after();
+                    if (j == j0 && seg > 0) {
+                        mbar_wait(&bars->o_empty, (uint32_t)((seg - 1) & 1));
+                        tcgen05_fence_after();
+                    }
+                    g2(jj, j == j0);
+                }
+                tcgen05_commit(&bars->o_full);
+                tcgen05_commit(&bars->a_empty);
+                ++seg;
+            }
+        }
+    } else {
+        // ===================== exponential / epilogue warpgroup =====================
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;                // row within the 128-row tile
+        const int tid128 = (warp - 2) * 32 + lane;    // 0..127 within the warpgroup
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        SegIter it(p);
+        int t, j0, j1, seg = 0;
+        long long jj = 0;
+        // slot of this CTA's partial for tile t: index among the CTAs that cover t
+        const long long G = gridDim.x;
+        while (it.next(t, j0, j1)) {
+            const long long T0 = (long long)t * p.nJ;
+            const long long c_first = ((T0 + 1) * G + p.U - 1) / p.U - 1;
+            const int slot = (int)((long long)blockIdx.x - c_first);
+            const float a_i = p.nrm[(size_t)(p.row_tile0 + t) * 128 + row];
+            float ksum = 0.0f;
+            for (int j = j0; j < j1; ++j, ++jj) {
+                const int b = (int)(jj & 1);
+                sB[b * 128 + tid128] = p.nrm[(size_t)j * 128 + tid128];
+                named_bar_sync(1, 128);
+                mbar_wait(&bars->s_full[b], (uint32_t)((jj >> 1) & 1));
+                tcgen05_fence_after();
+                const uint32_t s_addr = tmem + (b ? TMEM_S1 : TMEM_S0) + lane_addr;
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(s_addr + ch * 32, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float arg = fmaf(__uint_as_float(v[c]), p.c1, a_i + sB[b * 128 + ch * 32 + c]);
+                        const float pv = to_tf32_rn(ex2_approx(arg));
+                        ksum += pv;
+                        v[c] = __float_as_uint(pv);
+                    }
+                    tmem_st32(s_addr + ch * 32, v);
+                }
+                tmem_wait_st();
+                tcgen05_fence_before();
+                mbar_arrive(&bars->p_full[b]);
+            }
+            // drain the O accumulator of this segment
+            mbar_wait(&bars->o_full, (uint32_t)(seg & 1));
+            tcgen05_fence_after();
+            float *orow = p.Opart + (size_t)slot * p.o_slot_stride + ((size_t)t * 128 + row) * p.DP;
+#pragma unroll 1
+            for (int ch = 0; ch < p.DP / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(tmem + lane_addr + ch * 32, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4)
+                    *reinterpret_cast<float4 *>(orow + ch * 32 + c4 * 4) =
+                        make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]),
+                                    __uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3]));
+            }
+            p.ksum_part[(size_t)slot * p.k_slot_stride + (size_t)t * 128 + row] = ksum;
+            tcgen05_fence_before();
+            mbar_arrive(&bars->o_empty);
+            ++seg;
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem, TMEM_COLS);
+    }
+}
+
+// ---- operand preparation ------------------------------------------------------------
+// Xr = tf32_rn(X); nrm[j] = -r_j log2(e) / (2 h^2) (or -inf for j >= n)
+__global__ void prep_x_kernel(const float *__restrict__ X, const float *__restrict__ r, int64_t rows,
+                              int64_t n, int64_t ld, float half_l2e_over_h2, float *__restrict__ Xr,
+                              float *__restrict__ nrm) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t ld4 = ld / 4;
+    if (e < rows * ld4) {
+        const float4 x = reinterpret_cast<const float4 *>(X)[e];
+        reinterpret_cast<float4 *>(Xr)[e] =
+            make_float4(to_tf32_rn(x.x), to_tf32_rn(x.y), to_tf32_rn(x.z), to_tf32_rn(x.w));
+    }
+    if (e < rows) nrm[e] = (e < n) ? -r[e] * half_l2e_over_h2 : -INFINITY;
+}
+
+// YrT[c][j] = tf32_rn(S[j][c] - X[j][c] / h2)   (transpose through shared memory)
+__global__ void prep_yt_kernel(const float *__restrict__ X, const float *__restrict__ S, int64_t rows,
+                               int64_t ld, float inv_h2, float *__restrict__ YrT) {
+    __shared__ float tile[32][33];
+    const int64_t j0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int64_t j = j0 + rr, c = c0 + threadIdx.x;
+        tile[rr][threadIdx.x] = to_tf32_rn(S[j * ld + c] - X[j * ld + c] * inv_h2);
+    }
+    __syncthreads();
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int64_t c = c0 + rr, j = j0 + threadIdx.x;
+        YrT[c * rows + j] = tile[threadIdx.x][rr];
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+int make_tensor_map_2d(stein_ctx *ctx, CUtensorMap *map, const float *base, uint64_t inner, uint64_t outer,
+                       uint64_t row_stride_bytes, uint32_t box_rows) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        STEIN_CHECK_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess)
+            return fail(ctx, STEIN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+        encode = (EncodeTiledFn)fn;
+    }
+    const cuuint64_t gdim[2] = {inner, outer};
+    const cuuint64_t gstride[1] = {row_stride_bytes};
+    const cuuint32_t box[2] = {32, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(ctx, STEIN_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)rc);
+    return STEIN_OK;
+}
+
+static size_t flash_smem_bytes(int64_t DP) {
+    return 1024 + (size_t)(DP / 32) * FL_UNIT_BYTES + (size_t)FL_STAGES * FL_UNIT_BYTES + 256 + 1024 + 64;
+}
+
+bool flash_tc_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
+    (void)ctx; (void)n_local;
+    const int64_t DP = stein_ld(d);
+    return (DP == 128 || DP == 256) && n_total >= 2;
+}
+
+struct FlashPlan {
+    int64_t rows, cols, DP, nI, nJ, U;
+    int G, maxslots;
+    std::vector<int> tile_nslots;
+};
+
+static FlashPlan flash_plan(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
+    FlashPlan pl;
+    pl.rows = stein_rows_padded(n_local);
+    pl.cols = stein_rows_padded(n_total);
+    pl.DP = stein_ld(d);
+    pl.nI = pl.rows / TILE;
+    pl.nJ = (n_total + TILE - 1) / TILE;
+    pl.U = pl.nI * pl.nJ;
+    pl.G = (int)std::min<int64_t>(ctx->num_sms, pl.U);
+    pl.tile_nslots.resize(pl.nI);
+    pl.maxslots = 1;
+    for (int64_t t = 0; t < pl.nI; ++t) {
+        const int64_t T0 = t * pl.nJ, T1 = (t + 1) * pl.nJ;
+        const int64_t c_first = ((T0 + 1) * pl.G + pl.U - 1) / pl.U - 1;
+        int64_t c_last = (T1 * pl.G + pl.U - 1) / pl.U - 1;
+        c_last = std::min<int64_t>(c_last, pl.G - 1);
+        pl.tile_nslots[t] = (int)(c_last - c_first + 1);
+        pl.maxslots = std::max(pl.maxslots, pl.tile_nslots[t]);
+    }
+    return pl;
+}
+
+// workspace: [Xr | YrT | nrm | Opart slots | ksum slots | partials | tile_nslots]
+int64_t flash_tc_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
+    const FlashPlan pl = flash_plan(ctx, n_local, n_total, d);
+    int64_t b = 0;
+    b += pl.cols * pl.DP * 4 * 2;                       // Xr, YrT
+    b += pl.cols * 4;                                   // nrm
+    b += (int64_t)pl.maxslots * pl.rows * pl.DP * 4;    // Opart
+    b += (int64_t)pl.maxslots * pl.rows * 4;            // ksum
+    b += FINALIZE_MAX_BLOCKS * 8;
+    b += pl.nI * 4;
+    return b + 4096;
+}
+
+// finalize with a per-tile slot count (unused slots are never read)
+__global__ void __launch_bounds__(256)
+finalize_slots_kernel(const float *__restrict__ O, int64_t slot_stride, const int *__restrict__ tile_nslots,
+                      const float *__restrict__ ksum, int64_t ksum_slot_stride,
+                      const float *__restrict__ X_local, int64_t rows_valid, int64_t rows, int64_t ld,
+                      float inv_h2, float inv_n, float *__restrict__ phi, double *__restrict__ partials) {
+    const int64_t ld4 = ld / 4;
+    const int64_t total4 = rows * ld4;
+    double local = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total4;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = e / ld4;
+        const int ns = tile_nslots[row / TILE];
+        float4 o = reinterpret_cast<const float4 *>(O)[e];
+        float ks = ksum[row];
+        for (int s = 1; s < ns; ++s) {
+            const float4 o2 = reinterpret_cast<const float4 *>(O + s * slot_stride)[e];
+            o.x += o2.x; o.y += o2.y; o.z += o2.z; o.w += o2.w;
+            ks += ksum[row + s * ksum_slot_stride];
+        }
+        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < rows_valid) {
+            const float4 x = reinterpret_cast<const float4 *>(X_local)[e];
+            const float w = ks * inv_h2;
+            pv.x = (o.x + x.x * w) * inv_n;
+            pv.y = (o.y + x.y * w) * inv_n;
+            pv.z = (o.z + x.z * w) * inv_n;
+            pv.w = (o.w + x.w * w) * inv_n;
+        }
+        reinterpret_cast<float4 *>(phi)[e] = pv;
+        local += (double)pv.x * pv.x + (double)pv.y * pv.y + (double)pv.z * pv.z + (double)pv.w * pv.w;
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = local;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(256)
+reduce_partials2_kernel(const double *__restrict__ partials, int count, double *__restrict__ out) {
+    __shared__ double red[256];
+    double local = 0.0;
+    for (int i = threadIdx.x; i < count; i += 256) local += partials[i];
+    red[threadIdx.x] = local;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = red[0];
+}
+
+int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all, int64_t n_total,
+                 int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
+                 int64_t ws_bytes, float *phi, double *sumsq) {
+    const FlashPlan pl = flash_plan(ctx, n_local, n_total, d);
+    STEIN_REQUIRE(ctx, ld == pl.DP, "flash phi needs ld == stein_ld(d)");
+    STEIN_REQUIRE(ctx, ws_bytes >= flash_tc_workspace_bytes(ctx, n_local, n_total, d), "phi workspace too small");
+    STEIN_REQUIRE(ctx, row_begin % TILE == 0, "row_begin must be a multiple of %d", TILE);
+    char *pws = (char *)ws;
+    float *Xr = (float *)pws;            pws += pl.cols * pl.DP * 4;
+    float *YrT = (float *)pws;           pws += pl.cols * pl.DP * 4;
+    float *nrm = (float *)pws;           pws += pl.cols * 4;
+    float *Opart = (float *)pws;         pws += (int64_t)pl.maxslots * pl.rows * pl.DP * 4;
+    float *ksum = (float *)pws;          pws += (int64_t)pl.maxslots * pl.rows * 4;
+    double *partials = (double *)(((uintptr_t)pws + 7) & ~(uintptr_t)7);
+    pws = (char *)partials + FINALIZE_MAX_BLOCKS * 8;
+    int *tile_nslots = (int *)pws;
+
+    const float l2e = 1.4426950408889634f;
+    {
+        const int64_t tot = std::max<int64_t>(pl.cols * pl.DP / 4, pl.cols);
+        prep_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(X_all, r_all, pl.cols, n_total, ld,
+                                                                             0.5f * l2e / h2, Xr, nrm);
+        STEIN_CHECK_LAUNCH(ctx);
+        dim3 g((unsigned)(pl.cols / 32), (unsigned)(pl.DP / 32)), b(32, 8);
+        prep_yt_kernel<<<g, b, 0, ctx->stream>>>(X_all, S_all, pl.cols, ld, 1.0f / h2, YrT);
+        STEIN_CHECK_LAUNCH(ctx);
+    }
+    // pageable source: the runtime stages the bytes before returning, so `pl` may go away
+    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(tile_nslots, pl.tile_nslots.data(), pl.nI * sizeof(int),
+                                          cudaMemcpyHostToDevice, ctx->stream));
+
+    CUtensorMap mapX, mapY;
+    STEIN_TRY(make_tensor_map_2d(ctx, &mapX, Xr, (uint64_t)pl.DP, (uint64_t)pl.cols, (uint64_t)pl.DP * 4, 128));
+    STEIN_TRY(make_tensor_map_2d(ctx, &mapY, YrT, (uint64_t)pl.cols, (uint64_t)pl.DP, (uint64_t)pl.cols * 4, 128));
+
+    FlashParams p{};
+    p.nJ = (int)pl.nJ;
+    p.kblocks = (int)(pl.DP / 32);
+    p.nhalf = (int)(pl.DP / 128);
+    p.DP = (int)pl.DP;
+    p.U = pl.U;
+    p.row_tile0 = (int)(row_begin / TILE);
+    p.c1 = l2e / h2;
+    p.nrm = nrm;
+    p.Opart = Opart;
+    p.o_slot_stride = pl.rows * pl.DP;
+    p.ksum_part = ksum;
+    p.k_slot_stride = pl.rows;
+
+    const size_t smem = flash_smem_bytes(pl.DP);
+    static bool attr_set = false;
+    if (!attr_set) {
+        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)flash_smem_bytes(FL_MAX_DP)));
+        attr_set = true;
+    }
+    {
+        RegionTimer timer(ctx, STEIN_REGION_PHI);
+        flash_phi_kernel<<<pl.G, FL_THREADS, smem, ctx->stream>>>(mapX, mapY, p);
+        STEIN_CHECK_LAUNCH(ctx);
+    }
+    const int64_t rows_valid = std::max<int64_t>(0, std::min<int64_t>(n_local, n_total - row_begin));
+    const int64_t total4 = pl.rows * ld / 4;
+    const int blocks = (int)std::min<int64_t>((total4 + 255) / 256, FINALIZE_MAX_BLOCKS);
+    finalize_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(Opart, pl.rows * pl.DP, tile_nslots, ksum, pl.rows,
+                                                           X_all + row_begin * ld, rows_valid, pl.rows, ld,
+                                                           1.0f / h2, 1.0f / (float)n_total, phi, partials);
+    STEIN_CHECK_LAUNCH(ctx);
+    reduce_partials2_kernel<<<1, 256, 0, ctx->stream>>>(partials, blocks, sumsq);
+    STEIN_CHECK_LAUNCH(ctx);
+    return STEIN_OK;
 }
 
 }  // namespace stein

@@ -196,6 +196,25 @@ def test_phi_dense_matches_oracle(ctx, n, d, scale):
     assert abs(sumsq - (phi ** 2).sum()) <= 1e-6 * (phi ** 2).sum()
 
 
+FLASH_CASES = [(128, 256, 1.0), (130, 256, 1.0), (640, 256, 1.0), (1000, 128, 0.3), (3000, 256, 1.0),
+               (2500, 200, 0.01), (4096, 100, 1.0)]
+
+
+@pytest.mark.parametrize("n,d,scale", FLASH_CASES)
+def test_phi_flash_tcgen05_matches_oracle(ctx, n, d, scale):
+    """The tcgen05/TMEM/TMA fused kernel (TF32 tensor-core GEMMs, FP32 accumulate):
+    1e-4 relative to the oracle, and to the FFMA dense path on the same device."""
+    from stein_b200 import _lib
+    X = _particles(n, d, 3 * n + d, scale)
+    S = _particles(n, d, 5 * n + d, 1.0) - X
+    phi, sumsq, bw = _phi_gpu(ctx, X, S, _lib.PHI_FLASH_TC)
+    ref = orc.compute_phi(X, S.astype(np.float64))
+    _assert_close(phi, ref)
+    dense, _, _ = _phi_gpu(ctx, X, S, _lib.PHI_DENSE_SIMT)
+    _assert_close(phi, dense)
+    assert abs(sumsq - (phi ** 2).sum()) <= 1e-6 * (phi ** 2).sum()
+
+
 def test_compute_phi_api(ctx):
     """AbstractSteinSampler.compute_phi(theta_array, grads_array) on host arrays."""
     from stein_b200.log_p import LinearRegression
