@@ -8,11 +8,16 @@
 //
 // One CTA owns a 128-row particle tile I (A operand, resident in shared memory)
 // and streams column tiles J of 128 particles:
-//   GEMM1  S   = X_I X_J^T                (tcgen05.mma kind::tf32, SS, D in TMEM, 128 columns)
+//   GEMM1  S   = X_I X_J^T                (tcgen05.mma kind::f16 on a 2-term BF16 split of X:
+//                                          hi.hi + lo.hi + hi.lo, ~2^-17 relative; D in TMEM)
 //   exp    P   = exp2(S c1 + a_i + b_j)   (4 warps: tcgen05.ld -> FFMA/MUFU -> tcgen05.st, in place)
 //   GEMM2  O  += P Y_J                    (tcgen05.mma kind::tf32, A = P from TMEM, D = O in TMEM)
 // TMEM columns: [0, DP) = O accumulator, [256,384) and [384,512) = two S/P buffers, so
 // GEMM1 of tile j+1 overlaps the exponentials of tile j (FlashAttention-4 style pipeline).
+// Why the split: with plain TF32 inputs the error of S has a part that is constant along
+// a row of K (x_i . (x_i - tf32(x_i))), which does not average out in the sums over j and
+// cost 2.6e-4 relative on phi; the 3-pass BF16 form costs 1.5x the TF32 GEMM1 and is exact
+// to ~1e-6.  P and Y are TF32 (round-to-nearest); their errors are independent per term.
 // Operands arrive through a 6-stage ring of 16 KB TMA boxes (128 rows x 128 B,
 // SWIZZLE_128B, K-major).  Work is split stream-K style: the nI*nJ tile pairs are
 // cut into gridDim.x equal contiguous ranges, partial O / ksum of a range go to a
@@ -22,6 +27,8 @@
 // warps 2..5 = exponential/epilogue warpgroup (warp w owns TMEM lanes 32*(w%4)..).
 #include <algorithm>
 #include <vector>
+
+#include <cuda_bf16.h>
 
 #include "phi_common.cuh"
 #include "tc_common.cuh"
@@ -39,7 +46,7 @@ constexpr uint32_t TMEM_S0 = 256, TMEM_S1 = 384;
 
 struct FlashParams {
     int nJ;              // column tiles
-    int kblocks;         // DP / 32: 128-byte K blocks per row
+    int kblocks;         // DP / 64: 128-byte K blocks per row of the BF16 hi / lo arrays
     int nhalf;           // DP / 128: 128-column halves of the O accumulator
     int DP;
     long long U;         // nI * nJ tile pairs
@@ -80,13 +87,13 @@ struct SegIter {
 };
 
 __global__ void __launch_bounds__(FL_THREADS, 1)
-flash_phi_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
-                 const FlashParams p) {
+flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
+                 const __grid_constant__ CUtensorMap mapY, const FlashParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B-swizzle atoms
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *sA = smem;                                           // kblocks x 16 KB
-    uint8_t *sRing = sA + (size_t)p.kblocks * FL_UNIT_BYTES;      // FL_STAGES x 16 KB
+    uint8_t *sA = smem;                                           // [hi | lo] x kblocks x 16 KB
+    uint8_t *sRing = sA + (size_t)2 * p.kblocks * FL_UNIT_BYTES;  // FL_STAGES x 16 KB
     uint8_t *tail = sRing + (size_t)FL_STAGES * FL_UNIT_BYTES;
     FlashBarriers *bars = reinterpret_cast<FlashBarriers *>(tail);
     float *sB = reinterpret_cast<float *>(tail + 256);            // [2][128]
@@ -109,7 +116,8 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         mbar_init(&bars->o_empty, 128);
         fence_barrier_init();
         fence_proxy_async();
-        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapXh);
+        tma_prefetch_desc(&mapXl);
         tma_prefetch_desc(&mapY);
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -130,7 +138,10 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
             };
             auto emit_g1 = [&](int j) {
-                for (int kb = 0; kb < p.kblocks; ++kb) emit(&mapX, kb * 32, j * 128);
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    emit(&mapXh, kb * 64, j * 128);
+                    emit(&mapXl, kb * 64, j * 128);
+                }
             };
             auto emit_g2 = [&](int j) {
                 for (int kb2 = 0; kb2 < 4; ++kb2)
@@ -140,10 +151,13 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             int t, j0, j1, seg = 0;
             while (it.next(t, j0, j1)) {
                 if (seg > 0) mbar_wait(&bars->a_empty, (uint32_t)((seg - 1) & 1));
-                mbar_expect_tx(&bars->a_full, (uint32_t)p.kblocks * FL_UNIT_BYTES);
-                for (int kb = 0; kb < p.kblocks; ++kb)
-                    tma_load_2d(sA + (size_t)kb * FL_UNIT_BYTES, &mapX, &bars->a_full, kb * 32,
+                mbar_expect_tx(&bars->a_full, (uint32_t)(2 * p.kblocks) * FL_UNIT_BYTES);
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    tma_load_2d(sA + (size_t)kb * FL_UNIT_BYTES, &mapXh, &bars->a_full, kb * 64,
                                 (p.row_tile0 + t) * 128);
+                    tma_load_2d(sA + (size_t)(p.kblocks + kb) * FL_UNIT_BYTES, &mapXl, &bars->a_full, kb * 64,
+                                (p.row_tile0 + t) * 128);
+                }
                 emit_g1(j0);
                 for (int j = j0; j < j1; ++j) {
                     if (j + 1 < j1) emit_g1(j + 1);
@@ -155,20 +169,34 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(FMT_TF32, 128, 128);
+            const uint32_t idesc = make_idesc(FMT_TF32, 128, 128);       // GEMM2
+            const uint32_t idesc1 = make_idesc(FMT_BF16, 128, 128);      // GEMM1
             int stage = 0;
             uint32_t phase = 0;
             long long jj = 0;   // running column-tile counter of this CTA (S/P buffer = jj & 1)
             auto g1 = [&](long long jcount) {
                 const uint32_t d_tmem = tmem + ((jcount & 1) ? TMEM_S1 : TMEM_S0);
                 for (int kb = 0; kb < p.kblocks; ++kb) {
+                    const uint64_t ah = make_kmajor_sw128_desc(smem_u32(sA + (size_t)kb * FL_UNIT_BYTES));
+                    const uint64_t al =
+                        make_kmajor_sw128_desc(smem_u32(sA + (size_t)(p.kblocks + kb) * FL_UNIT_BYTES));
+                    // B = hi block of X_J:  hi.hi + lo.hi
                     mbar_wait(&bars->full[stage], phase);
                     tcgen05_fence_after();
-                    const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(sA + (size_t)kb * FL_UNIT_BYTES));
-                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sRing + (size_t)stage * FL_UNIT_BYTES));
+                    uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sRing + (size_t)stage * FL_UNIT_BYTES));
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4)
-                        umma_tf32_ss(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0);
+                        umma_f16_ss(d_tmem, ah + 2 * k4, bdesc + 2 * k4, idesc1, (kb | k4) != 0);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) umma_f16_ss(d_tmem, al + 2 * k4, bdesc + 2 * k4, idesc1, 1u);
+                    tcgen05_commit(&bars->empty[stage]);
+                    if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
+                    // B = lo block of X_J:  hi.lo
+                    mbar_wait(&bars->full[stage], phase);
+                    tcgen05_fence_after();
+                    bdesc = make_kmajor_sw128_desc(smem_u32(sRing + (size_t)stage * FL_UNIT_BYTES));
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) umma_f16_ss(d_tmem, ah + 2 * k4, bdesc + 2 * k4, idesc1, 1u);
                     tcgen05_commit(&bars->empty[stage]);
                     if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -285,16 +313,24 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 }
 
 // ---- operand preparation ------------------------------------------------------------
-// Xr = tf32_rn(X); nrm[j] = -r_j log2(e) / (2 h^2) (or -inf for j >= n)
+// BF16 two-term split of X (hi = bf16(x), lo = bf16(x - hi)); nrm[j] = -r_j log2(e)/(2 h^2)
+// (or -inf for j >= n)
 __global__ void prep_x_kernel(const float *__restrict__ X, const float *__restrict__ r, int64_t rows,
-                              int64_t n, int64_t ld, float half_l2e_over_h2, float *__restrict__ Xr,
-                              float *__restrict__ nrm) {
+                              int64_t n, int64_t ld, float half_l2e_over_h2, __nv_bfloat16 *__restrict__ Xh,
+                              __nv_bfloat16 *__restrict__ Xl, float *__restrict__ nrm) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t ld4 = ld / 4;
     if (e < rows * ld4) {
         const float4 x = reinterpret_cast<const float4 *>(X)[e];
-        reinterpret_cast<float4 *>(Xr)[e] =
-            make_float4(to_tf32_rn(x.x), to_tf32_rn(x.y), to_tf32_rn(x.z), to_tf32_rn(x.w));
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            h[k] = __float2bfloat16_rn(xs[k]);
+            l[k] = __float2bfloat16_rn(xs[k] - __bfloat162float(h[k]));
+        }
+        reinterpret_cast<uint2 *>(Xh)[e] = *reinterpret_cast<uint2 *>(h);
+        reinterpret_cast<uint2 *>(Xl)[e] = *reinterpret_cast<uint2 *>(l);
     }
     if (e < rows) nrm[e] = (e < n) ? -r[e] * half_l2e_over_h2 : -INFINITY;
 }
@@ -321,8 +357,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
-int make_tensor_map_2d(stein_ctx *ctx, CUtensorMap *map, const float *base, uint64_t inner, uint64_t outer,
-                       uint64_t row_stride_bytes, uint32_t box_rows) {
+int make_tensor_map_2d(stein_ctx *ctx, CUtensorMap *map, const void *base, int elem_bytes, uint64_t inner,
+                       uint64_t outer, uint64_t row_stride_bytes, uint32_t box_rows) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -334,9 +370,10 @@ int make_tensor_map_2d(stein_ctx *ctx, CUtensorMap *map, const float *base, uint
     }
     const cuuint64_t gdim[2] = {inner, outer};
     const cuuint64_t gstride[1] = {row_stride_bytes};
-    const cuuint32_t box[2] = {32, box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), box_rows};   // 128-byte rows
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstride, box, estr,
+    const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUresult rc = encode(map, dt, 2, (void *)base, gdim, gstride, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) return fail(ctx, STEIN_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)rc);
@@ -344,7 +381,7 @@ int make_tensor_map_2d(stein_ctx *ctx, CUtensorMap *map, const float *base, uint
 }
 
 static size_t flash_smem_bytes(int64_t DP) {
-    return 1024 + (size_t)(DP / 32) * FL_UNIT_BYTES + (size_t)FL_STAGES * FL_UNIT_BYTES + 256 + 1024 + 64;
+    return 1024 + (size_t)2 * (DP / 64) * FL_UNIT_BYTES + (size_t)FL_STAGES * FL_UNIT_BYTES + 256 + 1024 + 64;
 }
 
 bool flash_tc_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
@@ -381,7 +418,7 @@ static FlashPlan flash_plan(const stein_ctx *ctx, int64_t n_local, int64_t n_tot
     return pl;
 }
 
-// workspace: [Xr | YrT | nrm | Opart slots | ksum slots | partials | tile_nslots]
+// workspace: [Xh, Xl (bf16) | YrT | nrm | Opart slots | ksum slots | partials | tile_nslots]
 int64_t flash_tc_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
     const FlashPlan pl = flash_plan(ctx, n_local, n_total, d);
     int64_t b = 0;
@@ -458,7 +495,8 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     STEIN_REQUIRE(ctx, ws_bytes >= flash_tc_workspace_bytes(ctx, n_local, n_total, d), "phi workspace too small");
     STEIN_REQUIRE(ctx, row_begin % TILE == 0, "row_begin must be a multiple of %d", TILE);
     char *pws = (char *)ws;
-    float *Xr = (float *)pws;            pws += pl.cols * pl.DP * 4;
+    __nv_bfloat16 *Xh = (__nv_bfloat16 *)pws;   pws += pl.cols * pl.DP * 2;
+    __nv_bfloat16 *Xl = (__nv_bfloat16 *)pws;   pws += pl.cols * pl.DP * 2;
     float *YrT = (float *)pws;           pws += pl.cols * pl.DP * 4;
     float *nrm = (float *)pws;           pws += pl.cols * 4;
     float *Opart = (float *)pws;         pws += (int64_t)pl.maxslots * pl.rows * pl.DP * 4;
@@ -471,7 +509,7 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     {
         const int64_t tot = std::max<int64_t>(pl.cols * pl.DP / 4, pl.cols);
         prep_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(X_all, r_all, pl.cols, n_total, ld,
-                                                                             0.5f * l2e / h2, Xr, nrm);
+                                                                             0.5f * l2e / h2, Xh, Xl, nrm);
         STEIN_CHECK_LAUNCH(ctx);
         dim3 g((unsigned)(pl.cols / 32), (unsigned)(pl.DP / 32)), b(32, 8);
         prep_yt_kernel<<<g, b, 0, ctx->stream>>>(X_all, S_all, pl.cols, ld, 1.0f / h2, YrT);
@@ -481,13 +519,14 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(tile_nslots, pl.tile_nslots.data(), pl.nI * sizeof(int),
                                           cudaMemcpyHostToDevice, ctx->stream));
 
-    CUtensorMap mapX, mapY;
-    STEIN_TRY(make_tensor_map_2d(ctx, &mapX, Xr, (uint64_t)pl.DP, (uint64_t)pl.cols, (uint64_t)pl.DP * 4, 128));
-    STEIN_TRY(make_tensor_map_2d(ctx, &mapY, YrT, (uint64_t)pl.cols, (uint64_t)pl.DP, (uint64_t)pl.cols * 4, 128));
+    CUtensorMap mapXh, mapXl, mapY;
+    STEIN_TRY(make_tensor_map_2d(ctx, &mapXh, Xh, 2, (uint64_t)pl.DP, (uint64_t)pl.cols, (uint64_t)pl.DP * 2, 128));
+    STEIN_TRY(make_tensor_map_2d(ctx, &mapXl, Xl, 2, (uint64_t)pl.DP, (uint64_t)pl.cols, (uint64_t)pl.DP * 2, 128));
+    STEIN_TRY(make_tensor_map_2d(ctx, &mapY, YrT, 4, (uint64_t)pl.cols, (uint64_t)pl.DP, (uint64_t)pl.cols * 4, 128));
 
     FlashParams p{};
     p.nJ = (int)pl.nJ;
-    p.kblocks = (int)(pl.DP / 32);
+    p.kblocks = (int)(pl.DP / 64);
     p.nhalf = (int)(pl.DP / 128);
     p.DP = (int)pl.DP;
     p.U = pl.U;
@@ -508,7 +547,7 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     }
     {
         RegionTimer timer(ctx, STEIN_REGION_PHI);
-        flash_phi_kernel<<<pl.G, FL_THREADS, smem, ctx->stream>>>(mapX, mapY, p);
+        flash_phi_kernel<<<pl.G, FL_THREADS, smem, ctx->stream>>>(mapXh, mapXl, mapY, p);
         STEIN_CHECK_LAUNCH(ctx);
     }
     const int64_t rows_valid = std::max<int64_t>(0, std::min<int64_t>(n_local, n_total - row_begin));

@@ -184,8 +184,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 }  // namespace tc
 
-// host: 2-D row-major fp32 tensor map, box = {32 floats (128 B), box_rows}, 128-byte swizzle
-int make_tensor_map_2d(stein_ctx *ctx, CUtensorMap *map, const float *base, uint64_t inner, uint64_t outer,
-                       uint64_t row_stride_bytes, uint32_t box_rows);
+// host: 2-D row-major tensor map (fp32 or bf16), box = {128 bytes, box_rows}, 128-byte swizzle
+int make_tensor_map_2d(stein_ctx *ctx, CUtensorMap *map, const void *base, int elem_bytes, uint64_t inner,
+                       uint64_t outer, uint64_t row_stride_bytes, uint32_t box_rows);
 
 }  // namespace stein
