@@ -23,8 +23,10 @@
 // cut into gridDim.x equal contiguous ranges, partial O / ksum of a range go to a
 // per-(I tile) slot and are summed in fixed order by finalize_phi_kernel.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer,
-// warps 2..5 = exponential/epilogue warpgroup (warp w owns TMEM lanes 32*(w%4)..).
+// Warp roles (384 threads): warpgroup 0 = control (warp 0 TMA producer, warp 1 MMA issuer,
+// warps 2-3 idle; registers released with setmaxnreg), warpgroups 1-2 = exponential /
+// epilogue (warp w owns TMEM lanes 32*(w%4)..; warpgroup g owns half of the S and O columns
+// and keeps the fp32 running sum of its O half in registers).
 #include <algorithm>
 #include <vector>
 
@@ -37,10 +39,12 @@ namespace stein {
 
 using namespace tc;
 
-constexpr int FL_THREADS = 192;
+constexpr int FL_THREADS = 384;                 // control warpgroup + 2 exponential/epilogue warpgroups
+constexpr int FL_EPI_THREADS = 256;
 constexpr int FL_STAGES = 6;
 constexpr uint32_t FL_UNIT_BYTES = 128 * 128;   // one TMA box: 128 rows x 128 bytes
 constexpr int FL_MAX_DP = 256;
+constexpr int FL_OCHUNK = 4;                    // column tiles accumulated in TMEM between two drains
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TMEM_S0 = 256, TMEM_S1 = 384;
 
@@ -57,6 +61,8 @@ struct FlashParams {
     long long o_slot_stride;
     float *ksum_part;    // [slot][rows_local]
     long long k_slot_stride;
+    float *dumpS;        // debug: raw GEMM1 output, [rows_local][dump_ld] (NULL in production)
+    long long dump_ld;
 };
 
 struct FlashBarriers {
@@ -86,9 +92,16 @@ struct SegIter {
     }
 };
 
+// Layout of one 128-column S/P buffer after the exponential step: each 32-column chunk ch
+// (columns j = 32 ch .. 32 ch + 31 of S) is overwritten in place by 16 words of P_hi
+// (bf16 pairs, element j even in the low half) followed by 16 words of P_lo.  K-step s of
+// GEMM2 (16 columns) therefore reads P_hi at column 32 (s/2) + 8 (s%2) and P_lo 16 further.
+__device__ __forceinline__ uint32_t p_hi_col(int s) { return (uint32_t)(32 * (s >> 1) + 8 * (s & 1)); }
+
 __global__ void __launch_bounds__(FL_THREADS, 1)
 flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
-                 const __grid_constant__ CUtensorMap mapY, const FlashParams p) {
+                 const __grid_constant__ CUtensorMap mapYh, const __grid_constant__ CUtensorMap mapYl,
+                 const FlashParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B-swizzle atoms
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -96,8 +109,9 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
     uint8_t *sRing = sA + (size_t)2 * p.kblocks * FL_UNIT_BYTES;  // FL_STAGES x 16 KB
     uint8_t *tail = sRing + (size_t)FL_STAGES * FL_UNIT_BYTES;
     FlashBarriers *bars = reinterpret_cast<FlashBarriers *>(tail);
-    float *sB = reinterpret_cast<float *>(tail + 256);            // [2][128]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 256 + 1024);
+    float *sB = reinterpret_cast<float *>(tail + 256);            // [2][128] column terms of the exponent
+    float *sK = reinterpret_cast<float *>(tail + 256 + 1024);     // [128] row-sum exchange between warpgroups
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 256 + 1024 + 512);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -110,15 +124,16 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
         mbar_init(&bars->a_empty, 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->s_full[b], 1);
-            mbar_init(&bars->p_full[b], 128);
+            mbar_init(&bars->p_full[b], FL_EPI_THREADS);
         }
         mbar_init(&bars->o_full, 1);
-        mbar_init(&bars->o_empty, 128);
+        mbar_init(&bars->o_empty, FL_EPI_THREADS);
         fence_barrier_init();
         fence_proxy_async();
         tma_prefetch_desc(&mapXh);
         tma_prefetch_desc(&mapXl);
-        tma_prefetch_desc(&mapY);
+        tma_prefetch_desc(&mapYh);
+        tma_prefetch_desc(&mapYl);
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tcgen05_fence_before();
@@ -126,7 +141,9 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0;
@@ -144,8 +161,11 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
                 }
             };
             auto emit_g2 = [&](int j) {
-                for (int kb2 = 0; kb2 < 4; ++kb2)
-                    for (int h = 0; h < p.nhalf; ++h) emit(&mapY, j * 128 + kb2 * 32, h * 128);
+                for (int kb2 = 0; kb2 < 2; ++kb2)
+                    for (int h = 0; h < p.nhalf; ++h) {
+                        emit(&mapYh, j * 128 + kb2 * 64, h * 128);
+                        emit(&mapYl, j * 128 + kb2 * 64, h * 128);
+                    }
             };
             SegIter it(p);
             int t, j0, j1, seg = 0;
@@ -169,53 +189,59 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(FMT_TF32, 128, 128);       // GEMM2
-            const uint32_t idesc1 = make_idesc(FMT_BF16, 128, 128);      // GEMM1
+            const uint32_t idesc = make_idesc(FMT_BF16, 128, 128);
             int stage = 0;
             uint32_t phase = 0;
             long long jj = 0;   // running column-tile counter of this CTA (S/P buffer = jj & 1)
+            long long oc = 0;   // O chunks committed so far
+            auto next_unit = [&]() -> uint64_t {
+                mbar_wait(&bars->full[stage], phase);
+                tcgen05_fence_after();
+                return make_kmajor_sw128_desc(smem_u32(sRing + (size_t)stage * FL_UNIT_BYTES));
+            };
+            auto release_unit = [&]() {
+                tcgen05_commit(&bars->empty[stage]);
+                if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
+            };
             auto g1 = [&](long long jcount) {
                 const uint32_t d_tmem = tmem + ((jcount & 1) ? TMEM_S1 : TMEM_S0);
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     const uint64_t ah = make_kmajor_sw128_desc(smem_u32(sA + (size_t)kb * FL_UNIT_BYTES));
                     const uint64_t al =
                         make_kmajor_sw128_desc(smem_u32(sA + (size_t)(p.kblocks + kb) * FL_UNIT_BYTES));
-                    // B = hi block of X_J:  hi.hi + lo.hi
-                    mbar_wait(&bars->full[stage], phase);
-                    tcgen05_fence_after();
-                    uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sRing + (size_t)stage * FL_UNIT_BYTES));
+                    uint64_t bdesc = next_unit();          // hi block of X_J: hi.hi + lo.hi
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4)
-                        umma_f16_ss(d_tmem, ah + 2 * k4, bdesc + 2 * k4, idesc1, (kb | k4) != 0);
+                        umma_f16_ss(d_tmem, ah + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0);
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) umma_f16_ss(d_tmem, al + 2 * k4, bdesc + 2 * k4, idesc1, 1u);
-                    tcgen05_commit(&bars->empty[stage]);
-                    if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
-                    // B = lo block of X_J:  hi.lo
-                    mbar_wait(&bars->full[stage], phase);
-                    tcgen05_fence_after();
-                    bdesc = make_kmajor_sw128_desc(smem_u32(sRing + (size_t)stage * FL_UNIT_BYTES));
+                    for (int k4 = 0; k4 < 4; ++k4) umma_f16_ss(d_tmem, al + 2 * k4, bdesc + 2 * k4, idesc, 1u);
+                    release_unit();
+                    bdesc = next_unit();                   // lo block of X_J: hi.lo
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) umma_f16_ss(d_tmem, ah + 2 * k4, bdesc + 2 * k4, idesc1, 1u);
-                    tcgen05_commit(&bars->empty[stage]);
-                    if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
+                    for (int k4 = 0; k4 < 4; ++k4) umma_f16_ss(d_tmem, ah + 2 * k4, bdesc + 2 * k4, idesc, 1u);
+                    release_unit();
                 }
                 tcgen05_commit(&bars->s_full[jcount & 1]);
             };
-            auto g2 = [&](long long jcount, bool first_of_segment) {
-                const uint32_t a_tmem = tmem + ((jcount & 1) ? TMEM_S1 : TMEM_S0);
-                for (int kb2 = 0; kb2 < 4; ++kb2) {
+            auto g2 = [&](long long jcount, bool first_of_chunk) {
+                const uint32_t a_base = tmem + ((jcount & 1) ? TMEM_S1 : TMEM_S0);
+                for (int kb2 = 0; kb2 < 2; ++kb2) {
                     for (int h = 0; h < p.nhalf; ++h) {
-                        mbar_wait(&bars->full[stage], phase);
-                        tcgen05_fence_after();
-                        const uint64_t bdesc =
-                            make_kmajor_sw128_desc(smem_u32(sRing + (size_t)stage * FL_UNIT_BYTES));
+                        const uint32_t d_tmem = tmem + h * 128;
+                        uint64_t bdesc = next_unit();      // hi block of Y_J: Phi.Yhi + Plo.Yhi
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const uint32_t ph = a_base + p_hi_col(kb2 * 4 + k4);
+                            umma_f16_ts(d_tmem, ph, bdesc + 2 * k4, idesc,
+                                        !(first_of_chunk && kb2 == 0 && k4 == 0));
+                            umma_f16_ts(d_tmem, ph + 16, bdesc + 2 * k4, idesc, 1u);
+                        }
+                        release_unit();
+                        bdesc = next_unit();               // lo block of Y_J: Phi.Ylo
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4)
-                            umma_tf32_ts(tmem + h * 128, a_tmem + kb2 * 32 + k4 * 8, bdesc + 2 * k4, idesc,
-                                         !(first_of_segment && kb2 == 0 && k4 == 0));
-                        tcgen05_commit(&bars->empty[stage]);
-                        if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
+                            umma_f16_ts(d_tmem, a_base + p_hi_col(kb2 * 4 + k4), bdesc + 2 * k4, idesc, 1u);
+                        release_unit();
                     }
                 }
             };
@@ -229,78 +255,122 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
                     if (j + 1 < j1) g1(jj + 1);
                     mbar_wait(&bars->p_full[jj & 1], (uint32_t)((jj >> 1) & 1));
                     tcgen05_fence_after();
-                    if (j == j0 && seg > 0) {
-                        mbar_wait(&bars->o_empty, (uint32_t)((seg - 1) & 1));
+                    const int ti = j - j0;
+                    const bool first_of_chunk = (ti % FL_OCHUNK) == 0;
+                    if (first_of_chunk && oc > 0) {
+                        // the previous chunk of O must have been drained by the epilogue warps
+                        mbar_wait(&bars->o_empty, (uint32_t)((oc - 1) & 1));
                         tcgen05_fence_after();
                     }
-                    g2(jj, j == j0);
+                    g2(jj, first_of_chunk);
+                    if (((ti + 1) % FL_OCHUNK) == 0 || j == j1 - 1) {
+                        tcgen05_commit(&bars->o_full);
+                        ++oc;
+                    }
                 }
-                tcgen05_commit(&bars->o_full);
                 tcgen05_commit(&bars->a_empty);
                 ++seg;
             }
         }
+    }
     } else {
-        // ===================== exponential / epilogue warpgroup =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        // ============ exponential / epilogue warpgroups (warps 4..7 and 8..11) ============
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int wg = (warp - 4) >> 2;               // 0 / 1: which half of the columns
         const int row = q * 32 + lane;                // row within the 128-row tile
-        const int tid128 = (warp - 2) * 32 + lane;    // 0..127 within the warpgroup
+        const int tid256 = (warp - 4) * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const int ocols = p.DP / 2;                   // O columns owned by this warpgroup
+        const int och = ocols / 32;                   // in 32-column chunks (2 or 4)
         SegIter it(p);
-        int t, j0, j1, seg = 0;
-        long long jj = 0;
-        // slot of this CTA's partial for tile t: index among the CTAs that cover t
+        int t, j0, j1;
+        long long jj = 0, oc = 0;
         const long long G = gridDim.x;
+        float acc[FL_MAX_DP / 2];                     // fp32 round-to-nearest running sum of O chunks
         while (it.next(t, j0, j1)) {
+            // slot of this CTA's partial for tile t: index among the CTAs that cover t
             const long long T0 = (long long)t * p.nJ;
             const long long c_first = ((T0 + 1) * G + p.U - 1) / p.U - 1;
             const int slot = (int)((long long)blockIdx.x - c_first);
             const float a_i = p.nrm[(size_t)(p.row_tile0 + t) * 128 + row];
             float ksum = 0.0f;
+#pragma unroll
+            for (int c = 0; c < FL_MAX_DP / 2; ++c) acc[c] = 0.0f;
             for (int j = j0; j < j1; ++j, ++jj) {
                 const int b = (int)(jj & 1);
-                sB[b * 128 + tid128] = p.nrm[(size_t)j * 128 + tid128];
-                named_bar_sync(1, 128);
+                if (tid256 < 128) sB[b * 128 + tid256] = p.nrm[(size_t)j * 128 + tid256];
+                named_bar_sync(1, FL_EPI_THREADS);
                 mbar_wait(&bars->s_full[b], (uint32_t)((jj >> 1) & 1));
                 tcgen05_fence_after();
                 const uint32_t s_addr = tmem + (b ? TMEM_S1 : TMEM_S0) + lane_addr;
 #pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int ch = wg * 2 + cc;       // 32-column chunk of the S tile
                     uint32_t v[32];
                     tmem_ld32(s_addr + ch * 32, v);
                     tmem_wait_ld();
+                    if (p.dumpS) {
+                        float *dst = p.dumpS + ((size_t)t * 128 + row) * p.dump_ld + (size_t)j * 128 + ch * 32;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float arg = fmaf(__uint_as_float(v[c]), p.c1, a_i + sB[b * 128 + ch * 32 + c]);
-                        const float pv = to_tf32_rn(ex2_approx(arg));
-                        ksum += pv;
-                        v[c] = __float_as_uint(pv);
+                        for (int c = 0; c < 32; ++c) dst[c] = __uint_as_float(v[c]);
                     }
-                    tmem_st32(s_addr + ch * 32, v);
+                    uint32_t w[32];
+#pragma unroll
+                    for (int c2 = 0; c2 < 16; ++c2) {
+                        const float e0 = ex2_approx(
+                            fmaf(__uint_as_float(v[2 * c2]), p.c1, a_i + sB[b * 128 + ch * 32 + 2 * c2]));
+                        const float e1 = ex2_approx(
+                            fmaf(__uint_as_float(v[2 * c2 + 1]), p.c1, a_i + sB[b * 128 + ch * 32 + 2 * c2 + 1]));
+                        ksum += e0 + e1;
+                        const uint32_t wh = pack_bf16x2(e0, e1);
+                        const float h0 = __uint_as_float(wh << 16), h1 = __uint_as_float(wh & 0xffff0000u);
+                        w[c2] = wh;
+                        w[16 + c2] = pack_bf16x2(e0 - h0, e1 - h1);
+                    }
+                    tmem_st32(s_addr + ch * 32, w);
                 }
                 tmem_wait_st();
                 tcgen05_fence_before();
                 mbar_arrive(&bars->p_full[b]);
-            }
-            // drain the O accumulator of this segment
-            mbar_wait(&bars->o_full, (uint32_t)(seg & 1));
-            tcgen05_fence_after();
-            float *orow = p.Opart + (size_t)slot * p.o_slot_stride + ((size_t)t * 128 + row) * p.DP;
-#pragma unroll 1
-            for (int ch = 0; ch < p.DP / 32; ++ch) {
-                uint32_t v[32];
-                tmem_ld32(tmem + lane_addr + ch * 32, v);
-                tmem_wait_ld();
+
+                const int ti = j - j0;
+                if (((ti + 1) % FL_OCHUNK) == 0 || j == j1 - 1) {
+                    // drain this chunk of the O accumulator into the fp32 registers (round to
+                    // nearest: the tensor core accumulates with truncation, so the chain of
+                    // accumulations inside TMEM is kept short)
+                    mbar_wait(&bars->o_full, (uint32_t)(oc & 1));
+                    tcgen05_fence_after();
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4)
-                    *reinterpret_cast<float4 *>(orow + ch * 32 + c4 * 4) =
-                        make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]),
-                                    __uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3]));
+                    for (int ch = 0; ch < FL_MAX_DP / 64; ++ch) {
+                        if (ch < och) {
+                            uint32_t v[32];
+                            tmem_ld32(tmem + lane_addr + wg * ocols + ch * 32, v);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) acc[ch * 32 + c] += __uint_as_float(v[c]);
+                        }
+                    }
+                    tcgen05_fence_before();
+                    mbar_arrive(&bars->o_empty);
+                    ++oc;
+                }
             }
-            p.ksum_part[(size_t)slot * p.k_slot_stride + (size_t)t * 128 + row] = ksum;
-            tcgen05_fence_before();
-            mbar_arrive(&bars->o_empty);
-            ++seg;
+            // write this segment's partial O row and row sum
+            float *orow = p.Opart + (size_t)slot * p.o_slot_stride + ((size_t)t * 128 + row) * p.DP + wg * ocols;
+#pragma unroll
+            for (int ch = 0; ch < FL_MAX_DP / 64; ++ch) {
+                if (ch < och) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4)
+                        *reinterpret_cast<float4 *>(orow + ch * 32 + c4 * 4) =
+                            make_float4(acc[ch * 32 + c4 * 4], acc[ch * 32 + c4 * 4 + 1], acc[ch * 32 + c4 * 4 + 2],
+                                        acc[ch * 32 + c4 * 4 + 3]);
+                }
+            }
+            if (wg == 1) sK[row] = ksum;
+            named_bar_sync(2, FL_EPI_THREADS);
+            if (wg == 0) p.ksum_part[(size_t)slot * p.k_slot_stride + (size_t)t * 128 + row] = ksum + sK[row];
         }
     }
 
@@ -335,19 +405,23 @@ __global__ void prep_x_kernel(const float *__restrict__ X, const float *__restri
     if (e < rows) nrm[e] = (e < n) ? -r[e] * half_l2e_over_h2 : -INFINITY;
 }
 
-// YrT[c][j] = tf32_rn(S[j][c] - X[j][c] / h2)   (transpose through shared memory)
+// Y = S - X / h2, transposed (YT[c][j]) and split into BF16 hi / lo
 __global__ void prep_yt_kernel(const float *__restrict__ X, const float *__restrict__ S, int64_t rows,
-                               int64_t ld, float inv_h2, float *__restrict__ YrT) {
+                               int64_t ld, float inv_h2, __nv_bfloat16 *__restrict__ YTh,
+                               __nv_bfloat16 *__restrict__ YTl) {
     __shared__ float tile[32][33];
     const int64_t j0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
     for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
         const int64_t j = j0 + rr, c = c0 + threadIdx.x;
-        tile[rr][threadIdx.x] = to_tf32_rn(S[j * ld + c] - X[j * ld + c] * inv_h2);
+        tile[rr][threadIdx.x] = S[j * ld + c] - X[j * ld + c] * inv_h2;
     }
     __syncthreads();
     for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
         const int64_t c = c0 + rr, j = j0 + threadIdx.x;
-        YrT[c * rows + j] = tile[threadIdx.x][rr];
+        const float y = tile[threadIdx.x][rr];
+        const __nv_bfloat16 h = __float2bfloat16_rn(y);
+        YTh[c * rows + j] = h;
+        YTl[c * rows + j] = __float2bfloat16_rn(y - __bfloat162float(h));
     }
 }
 
@@ -381,7 +455,7 @@ int make_tensor_map_2d(stein_ctx *ctx, CUtensorMap *map, const void *base, int e
 }
 
 static size_t flash_smem_bytes(int64_t DP) {
-    return 1024 + (size_t)2 * (DP / 64) * FL_UNIT_BYTES + (size_t)FL_STAGES * FL_UNIT_BYTES + 256 + 1024 + 64;
+    return 1024 + (size_t)2 * (DP / 64) * FL_UNIT_BYTES + (size_t)FL_STAGES * FL_UNIT_BYTES + 256 + 1024 + 512 + 64;
 }
 
 bool flash_tc_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
@@ -418,11 +492,11 @@ static FlashPlan flash_plan(const stein_ctx *ctx, int64_t n_local, int64_t n_tot
     return pl;
 }
 
-// workspace: [Xh, Xl (bf16) | YrT | nrm | Opart slots | ksum slots | partials | tile_nslots]
+// workspace: [Xh, Xl, YTh, YTl (bf16) | nrm | Opart slots | ksum slots | partials | tile_nslots]
 int64_t flash_tc_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
     const FlashPlan pl = flash_plan(ctx, n_local, n_total, d);
     int64_t b = 0;
-    b += pl.cols * pl.DP * 4 * 2;                       // Xr, YrT
+    b += pl.cols * pl.DP * 2 * 4;                       // Xh, Xl, YTh, YTl (bf16)
     b += pl.cols * 4;                                   // nrm
     b += (int64_t)pl.maxslots * pl.rows * pl.DP * 4;    // Opart
     b += (int64_t)pl.maxslots * pl.rows * 4;            // ksum
@@ -487,6 +561,8 @@ reduce_partials2_kernel(const double *__restrict__ partials, int count, double *
     if (threadIdx.x == 0) *out = red[0];
 }
 
+static float *g_debug_dumpS = nullptr;   // set only by stein_debug_flash_gram (tests)
+
 int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all, int64_t n_total,
                  int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
                  int64_t ws_bytes, float *phi, double *sumsq) {
@@ -497,7 +573,8 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     char *pws = (char *)ws;
     __nv_bfloat16 *Xh = (__nv_bfloat16 *)pws;   pws += pl.cols * pl.DP * 2;
     __nv_bfloat16 *Xl = (__nv_bfloat16 *)pws;   pws += pl.cols * pl.DP * 2;
-    float *YrT = (float *)pws;           pws += pl.cols * pl.DP * 4;
+    __nv_bfloat16 *YTh = (__nv_bfloat16 *)pws;  pws += pl.cols * pl.DP * 2;
+    __nv_bfloat16 *YTl = (__nv_bfloat16 *)pws;  pws += pl.cols * pl.DP * 2;
     float *nrm = (float *)pws;           pws += pl.cols * 4;
     float *Opart = (float *)pws;         pws += (int64_t)pl.maxslots * pl.rows * pl.DP * 4;
     float *ksum = (float *)pws;          pws += (int64_t)pl.maxslots * pl.rows * 4;
@@ -512,17 +589,18 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
                                                                              0.5f * l2e / h2, Xh, Xl, nrm);
         STEIN_CHECK_LAUNCH(ctx);
         dim3 g((unsigned)(pl.cols / 32), (unsigned)(pl.DP / 32)), b(32, 8);
-        prep_yt_kernel<<<g, b, 0, ctx->stream>>>(X_all, S_all, pl.cols, ld, 1.0f / h2, YrT);
+        prep_yt_kernel<<<g, b, 0, ctx->stream>>>(X_all, S_all, pl.cols, ld, 1.0f / h2, YTh, YTl);
         STEIN_CHECK_LAUNCH(ctx);
     }
     // pageable source: the runtime stages the bytes before returning, so `pl` may go away
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(tile_nslots, pl.tile_nslots.data(), pl.nI * sizeof(int),
                                           cudaMemcpyHostToDevice, ctx->stream));
 
-    CUtensorMap mapXh, mapXl, mapY;
+    CUtensorMap mapXh, mapXl, mapYh, mapYl;
     STEIN_TRY(make_tensor_map_2d(ctx, &mapXh, Xh, 2, (uint64_t)pl.DP, (uint64_t)pl.cols, (uint64_t)pl.DP * 2, 128));
     STEIN_TRY(make_tensor_map_2d(ctx, &mapXl, Xl, 2, (uint64_t)pl.DP, (uint64_t)pl.cols, (uint64_t)pl.DP * 2, 128));
-    STEIN_TRY(make_tensor_map_2d(ctx, &mapY, YrT, 4, (uint64_t)pl.cols, (uint64_t)pl.DP, (uint64_t)pl.cols * 4, 128));
+    STEIN_TRY(make_tensor_map_2d(ctx, &mapYh, YTh, 2, (uint64_t)pl.cols, (uint64_t)pl.DP, (uint64_t)pl.cols * 2, 128));
+    STEIN_TRY(make_tensor_map_2d(ctx, &mapYl, YTl, 2, (uint64_t)pl.cols, (uint64_t)pl.DP, (uint64_t)pl.cols * 2, 128));
 
     FlashParams p{};
     p.nJ = (int)pl.nJ;
@@ -537,6 +615,8 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     p.o_slot_stride = pl.rows * pl.DP;
     p.ksum_part = ksum;
     p.k_slot_stride = pl.rows;
+    p.dumpS = g_debug_dumpS;
+    p.dump_ld = pl.cols;
 
     const size_t smem = flash_smem_bytes(pl.DP);
     static bool attr_set = false;
@@ -547,7 +627,7 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     }
     {
         RegionTimer timer(ctx, STEIN_REGION_PHI);
-        flash_phi_kernel<<<pl.G, FL_THREADS, smem, ctx->stream>>>(mapXh, mapXl, mapY, p);
+        flash_phi_kernel<<<pl.G, FL_THREADS, smem, ctx->stream>>>(mapXh, mapXl, mapYh, mapYl, p);
         STEIN_CHECK_LAUNCH(ctx);
     }
     const int64_t rows_valid = std::max<int64_t>(0, std::min<int64_t>(n_local, n_total - row_begin));
@@ -563,3 +643,18 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
 }
 
 }  // namespace stein
+
+// Test hook (not part of the public header): runs the flash kernel on (X, S = 0) and
+// returns the raw GEMM1 tile outputs G = X X^T as computed on the tensor cores
+// (rows_padded(n) x rows_padded(n), fp32) so the tests can bound its error.
+extern "C" int stein_debug_flash_gram(stein_ctx *ctx, const float *X_dev, const float *S_dev,
+                                      const float *r_dev, int64_t n, int64_t d, int64_t ld, float bandwidth,
+                                      void *ws, int64_t ws_bytes, float *phi_dev, double *sumsq_dev,
+                                      float *G_dev) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    stein::g_debug_dumpS = G_dev;
+    const int rc = stein::phi_flash_tc(ctx, X_dev, S_dev, r_dev, n, d, ld, 0, n, bandwidth * bandwidth, ws,
+                                       ws_bytes, phi_dev, sumsq_dev);
+    stein::g_debug_dumpS = nullptr;
+    return rc;
+}

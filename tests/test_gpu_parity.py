@@ -215,6 +215,34 @@ def test_phi_flash_tcgen05_matches_oracle(ctx, n, d, scale):
     assert abs(sumsq - (phi ** 2).sum()) <= 1e-6 * (phi ** 2).sum()
 
 
+@pytest.mark.parametrize("n,d", [(128, 256), (300, 128), (1000, 256)])
+def test_flash_gram_tiles_are_accurate(ctx, n, d):
+    """GEMM1 of the flash kernel (3-pass BF16 split on tcgen05) against float64 X X^T."""
+    import torch
+    X = _particles(n, d, n + 3 * d)
+    Xd, Sd = ctx.to_padded(X), ctx.to_padded(np.zeros_like(X))
+    rows, ld = Xd.shape
+    r = torch.empty(rows, dtype=torch.float32, device=Xd.device)
+    ctx.check(ctx.lib.stein_row_norms(ctx.handle, _ptr(Xd), n, d, ld, _ptr(r)))
+    nb = int(ctx.lib.stein_phi_workspace_bytes(ctx.handle, n, n, d))
+    ws = torch.empty(nb, dtype=torch.uint8, device=Xd.device)
+    phi = torch.empty_like(Xd)
+    sumsq = torch.zeros(1, dtype=torch.float64, device=Xd.device)
+    G = torch.zeros((rows, rows), dtype=torch.float32, device=Xd.device)
+    fn = ctx.lib.stein_debug_flash_gram
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64] * 3 + [ctypes.c_float, ctypes.c_void_p,
+                                                                  ctypes.c_int64] + [ctypes.c_void_p] * 3
+    ctx.check(fn(ctx.handle, _ptr(Xd), _ptr(Sd), _ptr(r), n, d, ld, 10.0, _ptr(ws), nb, _ptr(phi), _ptr(sumsq),
+                 _ptr(G)))
+    got = G.cpu().numpy()[:n, :n].astype(np.float64)
+    ref = X.astype(np.float64) @ X.astype(np.float64).T
+    scale = np.sqrt(np.outer((X.astype(np.float64) ** 2).sum(1), (X.astype(np.float64) ** 2).sum(1)))
+    err = np.abs(got - ref) / scale            # relative to |x_i| |x_j|
+    print("gram max rel err", err.max(), "rms", np.sqrt((err ** 2).mean()))
+    assert err.max() < 2.0 ** -15
+
+
 def test_compute_phi_api(ctx):
     """AbstractSteinSampler.compute_phi(theta_array, grads_array) on host arrays."""
     from stein_b200.log_p import LinearRegression
