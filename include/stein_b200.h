@@ -45,6 +45,11 @@ extern "C" {
 #define STEIN_PHI_DENSE_SIMT 1 /* materialises K for the local row block; FP32 FFMA */
 #define STEIN_PHI_FLASH_TC 2   /* tcgen05/TMEM/TMA fused kernel; never stores K   */
 
+/* median implementations (stein_ctx_set_median_impl) */
+#define STEIN_MEDIAN_AUTO 0
+#define STEIN_MEDIAN_FFMA 1 /* every sweep in contract arithmetic on the FP32 pipe          */
+#define STEIN_MEDIAN_TC 2   /* tcgen05 filter sweep + contract recomputation of candidates  */
+
 /* optimizer kinds (stein_engine_create) */
 #define STEIN_OPT_ADAM 0    /* stein/optimizers/adam_gradient_descent.py    */
 #define STEIN_OPT_ADAGRAD 1 /* stein/optimizers/adagrad_gradient_descent.py */
@@ -72,6 +77,7 @@ int stein_ctx_destroy(stein_ctx *ctx);
 int stein_ctx_set_stream(stein_ctx *ctx, void *cuda_stream);
 int stein_ctx_set_comm(stein_ctx *ctx, const stein_comm *comm /* NULL = single GPU */);
 int stein_ctx_set_phi_impl(stein_ctx *ctx, int impl);
+int stein_ctx_set_median_impl(stein_ctx *ctx, int impl);
 const char *stein_last_error(const stein_ctx *ctx /* NULL = last error of any ctx */);
 /* number of kernels of this library launched on ctx since creation */
 int64_t stein_ctx_launch_count(const stein_ctx *ctx);

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libstein_b200.so")
 STEIN_OK = 0
 PHI_AUTO, PHI_DENSE_SIMT, PHI_FLASH_TC = 0, 1, 2
 OPT_ADAM, OPT_ADAGRAD = 0, 1
+MEDIAN_AUTO, MEDIAN_FFMA, MEDIAN_TC = 0, 1, 2
 
 c_i64, c_i32, c_u32, c_u64 = ctypes.c_int64, ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint64
 c_f32, c_f64, c_vp = ctypes.c_float, ctypes.c_double, ctypes.c_void_p
@@ -38,6 +39,7 @@ SIGNATURES = {
     "stein_ctx_set_stream": (ctypes.c_int, [c_vp, c_vp]),
     "stein_ctx_set_comm": (ctypes.c_int, [c_vp, ctypes.POINTER(SteinComm)]),
     "stein_ctx_set_phi_impl": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "stein_ctx_set_median_impl": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "stein_last_error": (ctypes.c_char_p, [c_vp]),
     "stein_ctx_launch_count": (c_i64, [c_vp]),
     "stein_ctx_profile_enable": (ctypes.c_int, [c_vp, ctypes.c_int]),

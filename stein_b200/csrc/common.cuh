@@ -26,6 +26,7 @@ struct stein_ctx {
     bool has_comm = false;
     stein_comm comm{};
     int phi_impl = STEIN_PHI_AUTO;
+    int median_impl = STEIN_MEDIAN_AUTO;
     int64_t launches = 0;
     std::string error;
     // pinned host staging + device scratch for the median loop

@@ -107,6 +107,13 @@ int stein_ctx_set_phi_impl(stein_ctx *ctx, int impl) {
     return STEIN_OK;
 }
 
+int stein_ctx_set_median_impl(stein_ctx *ctx, int impl) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    STEIN_REQUIRE(ctx, impl >= STEIN_MEDIAN_AUTO && impl <= STEIN_MEDIAN_TC, "unknown median impl %d", impl);
+    ctx->median_impl = impl;
+    return STEIN_OK;
+}
+
 const char *stein_last_error(const stein_ctx *ctx) {
     return ctx ? ctx->error.c_str() : g_last_error.c_str();
 }

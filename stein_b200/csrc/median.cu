@@ -214,6 +214,12 @@ struct Window {
 };
 static const Window kFullWindow = {0u, 18u, (uint32_t)HIST_MAX_BINS};
 
+// median_tc.cu
+bool median_tc_supported(int64_t n, int64_t d);
+int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t d, int64_t ld,
+              const uint64_t ranks[2], uint32_t win_lo_key, uint32_t win_hi_key, uint32_t keys_out[2],
+              int *sweeps);
+
 }  // namespace stein
 
 using namespace stein;
@@ -345,6 +351,9 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
     STEIN_TRY(ensure_scratch(ctx, pilot_m));
 
     Window win[2] = {kFullWindow, kFullWindow};
+    bool done[2] = {false, false};
+    uint32_t key[2] = {0u, 0u};
+    int sweeps = 0;
     if (pilot_m) {
         // sample ranks m/2 -+ 3.5 sqrt(m): the true median lies between them with
         // probability ~1 - 1e-11; a miss is caught below and falls back to the
@@ -367,17 +376,24 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
             while (((span - 1) >> sh) >= (uint64_t)HIST_MAX_BINS) ++sh;
             Window w = {ka, sh, (uint32_t)(((span - 1) >> sh) + 1)};
             win[0] = win[1] = w;
+            // tensor-core route: one tcgen05 sweep + exact recomputation of the few pairs
+            // that can matter; falls through to the FFMA sweeps if it cannot bracket the rank
+            if (ctx->median_impl != STEIN_MEDIAN_FFMA && median_tc_supported(n, d) && ld == stein_ld(d)) {
+                const int rc = median_tc(ctx, X_dev, r_dev, n, d, ld, ranks, ka, kb, key, &sweeps);
+                if (rc < 0) return rc;
+                if (rc == STEIN_OK) done[0] = done[1] = true;
+            }
         }
     }
+    if (ctx->median_impl == STEIN_MEDIAN_TC && !(done[0] && done[1]))
+        return fail(ctx, STEIN_ERR_UNSUPPORTED, "tensor-core median route not applicable (n=%lld d=%lld)",
+                    (long long)n, (long long)d);
 
     const int world = ctx->has_comm ? ctx->comm.world : 1;
     const int rank = ctx->has_comm ? ctx->comm.rank : 0;
     const int64_t ntiles = stein_num_tiles(n);
     const int64_t t0 = ntiles * rank / world, t1 = ntiles * (rank + 1) / world;
 
-    bool done[2] = {false, false};
-    uint32_t key[2] = {0u, 0u};
-    int sweeps = 0;
     for (int iter = 0; iter < 16 && !(done[0] && done[1]); ++iter) {
         const int q0 = done[0] ? 1 : 0;
         const Window w = win[q0];

@@ -1,0 +1,628 @@
+// median_tc.cu -- kernel (2), tensor-core route: the exact median of the n x n
+// squared-distance matrix with ONE tcgen05 sweep over the upper-triangular tiles.
+//
+// Reference: stein/kernels/abstract_kernel.py:33-38, stein/utilities/compute_median.py:4-16.
+//
+// The answer must be the order statistic of the CONTRACT-arithmetic distances
+// (fp32 fma chain, see median.cu / oracle/svgd_oracle.c) -- tensor cores cannot
+// produce those bits.  They are used as a FILTER instead:
+//   1. the sweep computes D~ = r_i + r_j - 2 g~ with g~ from a 3-pass BF16-split GEMM
+//      (|D~ - D| <= eps_ij = c_half (r_i + r_j), a worst-case bound, see eps_coeff());
+//      pairs that are certainly below the pilot window [wlo, whi] are counted, pairs
+//      certainly above are dropped, the rest (~0.7 %) are appended to a list with D~;
+//   2. a radix select over the listed D~ gives t~, the D~ value at the target rank;
+//      the exact median lies within delta = max eps of it;
+//   3. entries certainly below t~ - delta are counted, entries that may lie within
+//      [t~ - delta, t~ + delta] (~0.07 %) get their distance recomputed in contract
+//      arithmetic (FFMA chain) and the exact rank is selected among those keys.
+// Every step checks that the target rank is bracketed; if not (pilot window missed,
+// list overflow) the caller falls back to the all-FFMA route of median.cu.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace stein {
+
+using namespace tc;
+
+constexpr int SW_THREADS = 384;
+constexpr int SW_EPI_THREADS = 256;
+constexpr int SW_STAGES = 4;
+constexpr uint32_t SW_UNIT_BYTES = 128 * 128;
+constexpr int SW_STAGE_CAP = 2048;          // entries staged in shared memory per flush
+constexpr uint32_t SW_TMEM_COLS = 256;
+
+struct PairEntry {
+    uint32_t i;
+    uint32_t jw;    // bit 31: weight 2 (off-diagonal tile), else weight 1
+    float dt;       // tensor-core distance D~
+};
+
+struct SweepParams {
+    int T;                        // tiles per side
+    long long t_begin, t_end;     // upper-triangular tile range of this launch
+    int kblocks;                  // DP / 64
+    long long n;
+    const float *r;
+    float wlo, whi, c_half;
+    unsigned long long *counters; // [0] certainly-below (weighted), [1] listed (weighted), [2] list length
+    int *overflow;
+    PairEntry *list;
+    unsigned long long list_cap;
+};
+
+struct SweepBarriers {
+    uint64_t full[SW_STAGES], empty[SW_STAGES];
+    uint64_t a_full, a_empty;
+    uint64_t s_full[2], s_empty[2];
+};
+
+__global__ void __launch_bounds__(SW_THREADS, 1)
+sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
+                const SweepParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;                                              // [hi | lo] x kblocks x 16 KB
+    uint8_t *sRing = sA + (size_t)2 * p.kblocks * SW_UNIT_BYTES;
+    uint8_t *tail = sRing + (size_t)SW_STAGES * SW_UNIT_BYTES;
+    SweepBarriers *bars = reinterpret_cast<SweepBarriers *>(tail);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 192);
+    unsigned int *sCount = reinterpret_cast<unsigned int *>(tail + 196);
+    unsigned int *sN = reinterpret_cast<unsigned int *>(tail + 200);
+    unsigned long long *sBase = reinterpret_cast<unsigned long long *>(tail + 208);
+    PairEntry *sBuf = reinterpret_cast<PairEntry *>(tail + 256);     // SW_STAGE_CAP entries
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long NT = p.t_end - p.t_begin;
+    const long long my0 = p.t_begin + NT * blockIdx.x / gridDim.x;
+    const long long my1 = p.t_begin + NT * (blockIdx.x + 1) / gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SW_STAGES; ++s) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], 1);
+        }
+        mbar_init(&bars->a_full, 1);
+        mbar_init(&bars->a_empty, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars->s_full[b], 1);
+            mbar_init(&bars->s_empty[b], SW_EPI_THREADS);
+        }
+        *sCount = 0u;
+        fence_barrier_init();
+        fence_proxy_async();
+        tma_prefetch_desc(&mapXh);
+        tma_prefetch_desc(&mapXl);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, SW_TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == 0 && lane == 0) {
+            // ===================== TMA producer =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            int prevI = -1, aseg = 0;
+            for (long long t = my0; t < my1; ++t) {
+                int I, J;
+                tri_tile(t, p.T, I, J);
+                if (I != prevI) {
+                    if (aseg > 0) mbar_wait(&bars->a_empty, (uint32_t)((aseg - 1) & 1));
+                    mbar_expect_tx(&bars->a_full, (uint32_t)(2 * p.kblocks) * SW_UNIT_BYTES);
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        tma_load_2d(sA + (size_t)kb * SW_UNIT_BYTES, &mapXh, &bars->a_full, kb * 64, I * 128);
+                        tma_load_2d(sA + (size_t)(p.kblocks + kb) * SW_UNIT_BYTES, &mapXl, &bars->a_full, kb * 64,
+                                    I * 128);
+                    }
+                    ++aseg;
+                    prevI = I;
+                }
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    for (int part = 0; part < 2; ++part) {
+                        mbar_wait(&bars->empty[stage], phase ^ 1);
+                        mbar_expect_tx(&bars->full[stage], SW_UNIT_BYTES);
+                        tma_load_2d(sRing + (size_t)stage * SW_UNIT_BYTES, part == 0 ? &mapXh : &mapXl,
+                                    &bars->full[stage], kb * 64, J * 128);
+                        if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ===================== MMA issuer =====================
+            const uint32_t idesc = make_idesc(FMT_BF16, 128, 128);
+            int stage = 0;
+            uint32_t phase = 0;
+            int prevI = -1, aseg = 0;
+            long long jj = 0;
+            for (long long t = my0; t < my1; ++t, ++jj) {
+                int I, J;
+                tri_tile(t, p.T, I, J);
+                if (I != prevI) {
+                    if (prevI != -1) tcgen05_commit(&bars->a_empty);   // all MMAs on the old A tile issued
+                    mbar_wait(&bars->a_full, (uint32_t)(aseg & 1));
+                    tcgen05_fence_after();
+                    ++aseg;
+                    prevI = I;
+                }
+                const int b = (int)(jj & 1);
+                if (jj >= 2) {
+                    mbar_wait(&bars->s_empty[b], (uint32_t)(((jj >> 1) - 1) & 1));
+                    tcgen05_fence_after();
+                }
+                const uint32_t d_tmem = tmem + b * 128;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    const uint64_t ah = make_kmajor_sw128_desc(smem_u32(sA + (size_t)kb * SW_UNIT_BYTES));
+                    const uint64_t al =
+                        make_kmajor_sw128_desc(smem_u32(sA + (size_t)(p.kblocks + kb) * SW_UNIT_BYTES));
+                    mbar_wait(&bars->full[stage], phase);
+                    tcgen05_fence_after();
+                    uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sRing + (size_t)stage * SW_UNIT_BYTES));
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        umma_f16_ss(d_tmem, ah + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) umma_f16_ss(d_tmem, al + 2 * k4, bdesc + 2 * k4, idesc, 1u);
+                    tcgen05_commit(&bars->empty[stage]);
+                    if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
+                    mbar_wait(&bars->full[stage], phase);
+                    tcgen05_fence_after();
+                    bdesc = make_kmajor_sw128_desc(smem_u32(sRing + (size_t)stage * SW_UNIT_BYTES));
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) umma_f16_ss(d_tmem, ah + 2 * k4, bdesc + 2 * k4, idesc, 1u);
+                    tcgen05_commit(&bars->empty[stage]);
+                    if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(&bars->s_full[b]);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        // ===================== classification warpgroups =====================
+        const int q = warp & 3;
+        const int wg = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        const int tid256 = (warp - 4) * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        unsigned int below = 0u, listed = 0u;
+        long long jj = 0;
+        for (long long t = my0; t < my1; ++t, ++jj) {
+            int I, J;
+            tri_tile(t, p.T, I, J);
+            const int b = (int)(jj & 1);
+            const unsigned int w = (I == J) ? 1u : 2u;
+            const long long i = (long long)I * 128 + row;
+            const float r_i = p.r[i];
+            const float *rj = p.r + (size_t)J * 128;
+            mbar_wait(&bars->s_full[b], (uint32_t)((jj >> 1) & 1));
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+                const int ch = wg * 2 + cc;
+                uint32_t v[32];
+                tmem_ld32(tmem + b * 128 + lane_addr + ch * 32, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const long long j = (long long)J * 128 + ch * 32 + c;
+                    const float tsum = r_i + __ldg(rj + ch * 32 + c);
+                    const float dt = fmaf(-2.0f, __uint_as_float(v[c]), tsum);
+                    const float eps = p.c_half * tsum;
+                    if (i < p.n && j < p.n) {
+                        if (dt + eps < p.wlo) {
+                            below += w;
+                        } else if (dt - eps <= p.whi) {
+                            listed += w;
+                            PairEntry e;
+                            e.i = (uint32_t)i;
+                            e.jw = (uint32_t)j | (w == 2u ? 0x80000000u : 0u);
+                            e.dt = dt;
+                            const unsigned int slot = atomicAdd(sCount, 1u);
+                            if (slot < (unsigned)SW_STAGE_CAP) {
+                                sBuf[slot] = e;
+                            } else {   // staging full (degenerate data): straight to global
+                                const unsigned long long g = atomicAdd(&p.counters[2], 1ull);
+                                if (g < p.list_cap) p.list[g] = e;
+                                else *p.overflow = 1;
+                            }
+                        }
+                    }
+                }
+            }
+            // S buffer b may be overwritten by the GEMM of tile jj + 2
+            tcgen05_fence_before();
+            mbar_arrive(&bars->s_empty[b]);
+            // flush the staged entries: one global reservation per tile
+            named_bar_sync(1, SW_EPI_THREADS);
+            if (tid256 == 0) {
+                const unsigned int cnt = min(*sCount, (unsigned)SW_STAGE_CAP);
+                *sN = cnt;
+                *sBase = cnt ? atomicAdd(&p.counters[2], (unsigned long long)cnt) : 0ull;
+                *sCount = 0u;
+            }
+            named_bar_sync(2, SW_EPI_THREADS);
+            const unsigned int cnt = *sN;
+            if (cnt) {
+                const unsigned long long base = *sBase;
+                for (unsigned int e = tid256; e < cnt; e += SW_EPI_THREADS) {
+                    if (base + e < p.list_cap) p.list[base + e] = sBuf[e];
+                    else *p.overflow = 1;
+                }
+            }
+            named_bar_sync(3, SW_EPI_THREADS);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            below += __shfl_xor_sync(0xffffffffu, below, o);
+            listed += __shfl_xor_sync(0xffffffffu, listed, o);
+        }
+        if (lane == 0) {
+            if (below) atomicAdd(&p.counters[0], (unsigned long long)below);
+            if (listed) atomicAdd(&p.counters[1], (unsigned long long)listed);
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem, SW_TMEM_COLS);
+    }
+}
+
+// ---- helpers ---------------------------------------------------------------------------
+__global__ void split_bf16_kernel(const float *__restrict__ X, int64_t count4, __nv_bfloat16 *__restrict__ Xh,
+                                  __nv_bfloat16 *__restrict__ Xl) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count4) return;
+    const float4 x = reinterpret_cast<const float4 *>(X)[e];
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        h[k] = __float2bfloat16_rn(xs[k]);
+        l[k] = __float2bfloat16_rn(xs[k] - __bfloat162float(h[k]));
+    }
+    reinterpret_cast<uint2 *>(Xh)[e] = *reinterpret_cast<uint2 *>(h);
+    reinterpret_cast<uint2 *>(Xl)[e] = *reinterpret_cast<uint2 *>(l);
+}
+
+__global__ void __launch_bounds__(1024)
+max_kernel(const float *__restrict__ r, int64_t n, float *__restrict__ out) {
+    __shared__ float red[32];
+    float m = 0.0f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, r[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = red[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) *out = m;
+    }
+}
+
+// weighted histogram of one radix digit over (SRC 0) the D~ of the pair list, (SRC 1) band keys
+template <int SRC>
+__global__ void __launch_bounds__(256)
+hist_pass_kernel(const void *__restrict__ src, unsigned long long m, uint32_t prefix, uint32_t mask, int shift,
+                 int bits, unsigned long long *__restrict__ bins) {
+    __shared__ unsigned int h[2048];
+    const int nb = 1 << bits;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) h[b] = 0u;
+    __syncthreads();
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < m;
+         e += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t key, w;
+        if (SRC == 0) {
+            const PairEntry pe = reinterpret_cast<const PairEntry *>(src)[e];
+            key = float_to_key(pe.dt);
+            w = (pe.jw >> 31) ? 2u : 1u;
+        } else {
+            const uint2 kw = reinterpret_cast<const uint2 *>(src)[e];
+            key = kw.x;
+            w = kw.y;
+        }
+        if ((key & mask) == prefix) atomicAdd(&h[(key >> shift) & (nb - 1)], w);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x)
+        if (h[b]) atomicAdd(&bins[b], (unsigned long long)h[b]);
+}
+
+// entries certainly below t~ - delta are counted; entries that may fall inside
+// [t~ - delta, t~ + delta] get the contract-arithmetic distance and go to the band
+__global__ void __launch_bounds__(256)
+band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, const float *__restrict__ X,
+                   const float *__restrict__ r, int64_t ld, float tlo, float thi, float c_half,
+                   unsigned long long *__restrict__ counters /* [3] below, [4] band weighted, [5] band len */,
+                   uint2 *__restrict__ band, unsigned long long band_cap, int *__restrict__ overflow) {
+    unsigned int below = 0u;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < m;
+         e += (unsigned long long)gridDim.x * blockDim.x) {
+        const PairEntry pe = list[e];
+        const uint32_t i = pe.i, j = pe.jw & 0x7fffffffu, w = (pe.jw >> 31) ? 2u : 1u;
+        const float tsum = r[i] + r[j];
+        const float eps = c_half * tsum;
+        if (pe.dt + eps < tlo) {
+            below += w;
+        } else if (pe.dt - eps <= thi) {
+            const float4 *a = reinterpret_cast<const float4 *>(X + (size_t)i * ld);
+            const float4 *b = reinterpret_cast<const float4 *>(X + (size_t)j * ld);
+            float acc = 0.0f;
+            for (int64_t k4 = 0; k4 < ld / 4; ++k4) {
+                const float4 u = a[k4], v = b[k4];
+                acc = __fmaf_rn(u.x, v.x, acc);
+                acc = __fmaf_rn(u.y, v.y, acc);
+                acc = __fmaf_rn(u.z, v.z, acc);
+                acc = __fmaf_rn(u.w, v.w, acc);
+            }
+            const uint32_t key = float_to_key(tsum - 2.0f * acc);
+            const unsigned long long g = atomicAdd(&counters[5], 1ull);
+            if (g < band_cap) band[g] = make_uint2(key, w);
+            else *overflow = 1;
+            atomicAdd(&counters[4], (unsigned long long)w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if ((threadIdx.x & 31) == 0 && below) atomicAdd(&counters[3], (unsigned long long)below);
+}
+
+// worst-case |D~ - D_contract| <= eps_coeff(d) * (r_i + r_j):
+//   BF16 2-term split: dropped lo.lo and the rounding of lo, <= 3 * 2^-18 |x_i||x_j|;
+//   tensor-core accumulation (truncating, 3 d/16 adds of magnitude <= |x_i||x_j|): 3d/16 * 2^-23;
+//   contract fma chain: d * 2^-24 |x_i||x_j|;  |x_i||x_j| <= (r_i + r_j)/2;  final roundings 2^-22.
+// All doubled once more as a safety margin.
+static float eps_coeff(int64_t d) {
+    const double per_xx = 3.0 * ldexp(1.0, -18) + (3.0 * d / 16.0) * ldexp(1.0, -23) + d * ldexp(1.0, -24);
+    return (float)(2.0 * (per_xx + ldexp(1.0, -22)));
+}
+
+struct MedianArena {
+    __nv_bfloat16 *Xh = nullptr, *Xl = nullptr;
+    PairEntry *list = nullptr;
+    uint2 *band = nullptr;
+    unsigned long long *counters = nullptr;   // 8 x u64 + overflow int + rmax float
+    unsigned long long *bins = nullptr;       // 2048
+    unsigned long long *h_pinned = nullptr;   // 2048 + 16
+    int64_t x_elems = 0;
+    unsigned long long list_cap = 0, band_cap = 0;
+};
+
+static MedianArena g_arena;   // one per process (one GPU per process)
+
+static int ensure_arena(stein_ctx *ctx, int64_t rows, int64_t DP, uint64_t pairs) {
+    MedianArena &A = g_arena;
+    if (!A.counters) {
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.counters, 128));
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.bins, 2048 * 8));
+        STEIN_CHECK_CUDA(ctx, cudaMallocHost(&A.h_pinned, (2048 + 16) * 8));
+    }
+    if (rows * DP > A.x_elems) {
+        if (A.Xh) cudaFree(A.Xh);
+        if (A.Xl) cudaFree(A.Xl);
+        A.Xh = A.Xl = nullptr;
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.Xh, rows * DP * 2));
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.Xl, rows * DP * 2));
+        A.x_elems = rows * DP;
+    }
+    // the pilot window holds ~0.7 % of the pairs; room for 2 % (upper-triangular count)
+    const unsigned long long want = std::max<unsigned long long>(1ull << 20, pairs / 50);
+    if (want > A.list_cap) {
+        if (A.list) cudaFree(A.list);
+        if (A.band) cudaFree(A.band);
+        A.list = nullptr;
+        A.band = nullptr;
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.list, want * sizeof(PairEntry)));
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.band, want * sizeof(uint2)));
+        A.list_cap = A.band_cap = want;
+    }
+    return STEIN_OK;
+}
+
+// distributed weighted radix select: value of 0-based rank `rank` among the keys; also
+// reports the next larger key present (valid when *has_next) and the weight at/below the key
+template <int SRC>
+static int radix_select(stein_ctx *ctx, const void *src, unsigned long long m_local, uint64_t rank,
+                        uint32_t *key_out, uint64_t *cum_through_key, bool *has_next, uint32_t *next_key) {
+    MedianArena &A = g_arena;
+    uint32_t prefix = 0, mask = 0;
+    int consumed = 0;
+    uint64_t offset = 0;   // weight strictly below the current prefix range
+    while (consumed < 32) {
+        const int bits = std::min(11, 32 - consumed);
+        const int shift = 32 - consumed - bits;
+        const int nb = 1 << bits;
+        STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(A.bins, 0, nb * 8, ctx->stream));
+        if (m_local) {
+            const unsigned grid = (unsigned)std::min<unsigned long long>((m_local + 255) / 256, 8ull * ctx->num_sms);
+            hist_pass_kernel<SRC><<<grid, 256, 0, ctx->stream>>>(src, m_local, prefix, mask, shift, bits, A.bins);
+            STEIN_CHECK_LAUNCH(ctx);
+        }
+        if (ctx->has_comm && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.bins, nb) != 0)
+            return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.h_pinned, A.bins, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        uint64_t cum = offset;
+        int b = 0;
+        for (; b < nb; ++b) {
+            if (cum + A.h_pinned[b] > rank) break;
+            cum += A.h_pinned[b];
+        }
+        if (b == nb) return 1;   // rank beyond the data: caller falls back
+        offset = cum;
+        prefix |= (uint32_t)b << shift;
+        mask |= (uint32_t)(nb - 1) << shift;
+        consumed += bits;
+        if (consumed == 32) {
+            *cum_through_key = cum + A.h_pinned[b];
+            *has_next = false;
+            for (int nbk = b + 1; nbk < nb; ++nbk)
+                if (A.h_pinned[nbk]) {
+                    *has_next = true;
+                    *next_key = (prefix & ~(uint32_t)(nb - 1)) | (uint32_t)nbk;
+                    break;
+                }
+        }
+    }
+    *key_out = prefix;
+    return STEIN_OK;
+}
+
+bool median_tc_supported(int64_t n, int64_t d) {
+    const int64_t DP = stein_ld(d);
+    return (DP == 128 || DP == 256) && (uint64_t)n * (uint64_t)n >= (1ull << 24) && n < (1ll << 31);
+}
+
+// returns STEIN_OK with keys filled, 1 = "not bracketed, use the FFMA route", <0 = error
+int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t d, int64_t ld,
+              const uint64_t ranks[2], uint32_t win_lo_key, uint32_t win_hi_key, uint32_t keys_out[2],
+              int *sweeps) {
+    const int64_t rows = stein_rows_padded(n), DP = ld;
+    const int64_t T = (n + TILE - 1) / TILE;
+    const uint64_t pairs = (uint64_t)T * (T + 1) / 2 * TILE * TILE;
+    STEIN_TRY(ensure_arena(ctx, rows, DP, pairs));
+    MedianArena &A = g_arena;
+    const int world = ctx->has_comm ? ctx->comm.world : 1, rank = ctx->has_comm ? ctx->comm.rank : 0;
+    const int64_t ntiles = T * (T + 1) / 2;
+    const int64_t t0 = ntiles * rank / world, t1 = ntiles * (rank + 1) / world;
+    const float c_half = eps_coeff(d);
+
+    STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(A.counters, 0, 128, ctx->stream));
+    const int64_t count4 = rows * DP / 4;
+    split_bf16_kernel<<<(unsigned)((count4 + 255) / 256), 256, 0, ctx->stream>>>(X, count4, A.Xh, A.Xl);
+    STEIN_CHECK_LAUNCH(ctx);
+    float *d_rmax = reinterpret_cast<float *>(A.counters + 9);
+    int *d_overflow = reinterpret_cast<int *>(A.counters + 8);
+    max_kernel<<<1, 1024, 0, ctx->stream>>>(r, n, d_rmax);
+    STEIN_CHECK_LAUNCH(ctx);
+
+    CUtensorMap mapXh, mapXl;
+    STEIN_TRY(make_tensor_map_2d(ctx, &mapXh, A.Xh, 2, (uint64_t)DP, (uint64_t)rows, (uint64_t)DP * 2, 128));
+    STEIN_TRY(make_tensor_map_2d(ctx, &mapXl, A.Xl, 2, (uint64_t)DP, (uint64_t)rows, (uint64_t)DP * 2, 128));
+    SweepParams p{};
+    p.T = (int)T;
+    p.t_begin = t0;
+    p.t_end = t1;
+    p.kblocks = (int)(DP / 64);
+    p.n = n;
+    p.r = r;
+    p.wlo = key_to_float(win_lo_key);
+    p.whi = key_to_float(win_hi_key);
+    p.c_half = c_half;
+    p.counters = A.counters;
+    p.overflow = d_overflow;
+    p.list = A.list;
+    p.list_cap = A.list_cap;
+    const size_t smem = 1024 + (size_t)2 * (DP / 64) * SW_UNIT_BYTES + (size_t)SW_STAGES * SW_UNIT_BYTES + 256 +
+                        (size_t)SW_STAGE_CAP * sizeof(PairEntry) + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(sweep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)(1024 + 8 * SW_UNIT_BYTES + SW_STAGES * SW_UNIT_BYTES + 256 +
+                                                         SW_STAGE_CAP * sizeof(PairEntry) + 64)));
+        attr_set = true;
+    }
+    if (t1 > t0) {
+        const int grid = (int)std::min<int64_t>(ctx->num_sms, t1 - t0);
+        RegionTimer timer(ctx, STEIN_REGION_SWEEP);
+        sweep_tc_kernel<<<grid, SW_THREADS, smem, ctx->stream>>>(mapXh, mapXl, p);
+        STEIN_CHECK_LAUNCH(ctx);
+    }
+    if (sweeps) *sweeps += 1;
+    // counters[0] below, [1] listed weight are global quantities; [2] list length stays local
+    unsigned long long *h = A.h_pinned + 2048;
+    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h, A.counters, 80, cudaMemcpyDeviceToHost, ctx->stream));
+    STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const unsigned long long list_len = std::min<unsigned long long>(h[2], A.list_cap);
+    int overflow_local = *reinterpret_cast<int *>(h + 8);
+    const float rmax = *reinterpret_cast<float *>(h + 9);
+    if (world > 1) {
+        // make the two weighted counts and the overflow flag global
+        unsigned long long *scratch = A.h_pinned + 2048 + 12;
+        scratch[0] = h[0];
+        scratch[1] = h[1];
+        scratch[2] = (unsigned long long)overflow_local;
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.bins, scratch, 24, cudaMemcpyHostToDevice, ctx->stream));
+        if (ctx->comm.allreduce_sum_u64(ctx->comm.user, A.bins, 3) != 0)
+            return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(scratch, A.bins, 24, cudaMemcpyDeviceToHost, ctx->stream));
+        STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        h[0] = scratch[0];
+        h[1] = scratch[1];
+        overflow_local = scratch[2] != 0;
+    }
+    const uint64_t below = h[0], listed = h[1];
+    if (overflow_local) return 1;
+    if (!(below <= ranks[0] && ranks[1] < below + listed)) return 1;   // pilot window missed
+
+    // D~ value at the lower target rank
+    uint32_t tkey = 0, nk = 0;
+    uint64_t cum = 0;
+    bool hn = false;
+    int rc = radix_select<0>(ctx, A.list, list_len, ranks[0] - below, &tkey, &cum, &hn, &nk);
+    if (rc != STEIN_OK) return rc;
+    const float tmid = key_to_float(tkey);
+    const float delta = c_half * 2.0f * rmax * 1.0001f + 2.0f * fabsf(tmid) * 1.2e-7f;
+    const float tlo = tmid - delta, thi = tmid + delta;
+
+    if (list_len) {
+        const unsigned grid = (unsigned)std::min<unsigned long long>((list_len + 255) / 256, 16ull * ctx->num_sms);
+        band_filter_kernel<<<grid, 256, 0, ctx->stream>>>(A.list, list_len, X, r, ld, tlo, thi, c_half, A.counters,
+                                                         A.band, A.band_cap, d_overflow);
+        STEIN_CHECK_LAUNCH(ctx);
+    }
+    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h, A.counters, 80, cudaMemcpyDeviceToHost, ctx->stream));
+    STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const unsigned long long band_len = std::min<unsigned long long>(h[5], A.band_cap);
+    uint64_t below2 = h[3], band_w = h[4];
+    int overflow2 = *reinterpret_cast<int *>(h + 8);
+    if (world > 1) {
+        unsigned long long *scratch = A.h_pinned + 2048 + 12;
+        scratch[0] = below2;
+        scratch[1] = band_w;
+        scratch[2] = (unsigned long long)overflow2;
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.bins, scratch, 24, cudaMemcpyHostToDevice, ctx->stream));
+        if (ctx->comm.allreduce_sum_u64(ctx->comm.user, A.bins, 3) != 0)
+            return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(scratch, A.bins, 24, cudaMemcpyDeviceToHost, ctx->stream));
+        STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        below2 = scratch[0];
+        band_w = scratch[1];
+        overflow2 = scratch[2] != 0;
+    }
+    if (overflow2) return 1;
+    const uint64_t c1 = below + below2;
+    if (!(c1 <= ranks[0] && ranks[1] < c1 + band_w)) return 1;
+
+    // exact keys of the two target ranks among the band
+    uint32_t k0 = 0, k1 = 0;
+    rc = radix_select<1>(ctx, A.band, band_len, ranks[0] - c1, &k0, &cum, &hn, &nk);
+    if (rc != STEIN_OK) return rc;
+    if (ranks[1] == ranks[0] || ranks[1] - c1 < cum) {
+        k1 = k0;
+    } else if (hn) {
+        k1 = nk;
+    } else {
+        uint64_t cum2;
+        rc = radix_select<1>(ctx, A.band, band_len, ranks[1] - c1, &k1, &cum2, &hn, &nk);
+        if (rc != STEIN_OK) return rc;
+    }
+    // the selected values must lie where the certainty argument holds
+    const float m0 = key_to_float(k0), m1 = key_to_float(k1);
+    if (!(m0 >= tlo && m1 <= thi && m0 >= p.wlo && m1 <= p.whi)) return 1;
+    keys_out[0] = k0;
+    keys_out[1] = k1;
+    return STEIN_OK;
+}
+
+}  // namespace stein

@@ -47,6 +47,9 @@ class Context:
     def set_phi_impl(self, impl):
         self.check(self.lib.stein_ctx_set_phi_impl(self.handle, int(impl)))
 
+    def set_median_impl(self, impl):
+        self.check(self.lib.stein_ctx_set_median_impl(self.handle, int(impl)))
+
     @property
     def launch_count(self):
         return int(self.lib.stein_ctx_launch_count(self.handle))

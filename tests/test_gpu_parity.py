@@ -101,6 +101,40 @@ def test_median_bit_exact_with_pilot_window(ctx, n, d):
     assert sweeps <= 3
 
 
+def _median_with(ctx, X, impl):
+    from stein_b200.utilities import median_sqdist
+    ctx.set_median_impl(impl)
+    try:
+        return median_sqdist(X, return_middle=True)
+    finally:
+        ctx.set_median_impl(0)
+
+
+@pytest.mark.parametrize("n,d,kind", [(4096, 256, "gauss"), (5000, 128, "gauss"), (4500, 250, "small"),
+                                      (6000, 256, "clusters"), (4100, 256, "dup")])
+def test_median_tensor_core_route_bit_exact(ctx, n, d, kind):
+    """tcgen05 filter sweep + contract recomputation of the candidates == the all-FFMA
+    route == the oracle (radix route), bit for bit."""
+    from stein_b200 import _lib
+    rng = np.random.default_rng(n + d)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    if kind == "small":
+        X *= 0.01
+    elif kind == "clusters":
+        X = (X * 0.05 + rng.integers(0, 3, size=(n, 1)) * 2.0).astype(np.float32)
+    elif kind == "dup":
+        X[n // 2:] = X[:n - n // 2]
+    tc = _median_with(ctx, X, _lib.MEDIAN_TC)
+    ff = _median_with(ctx, X, _lib.MEDIAN_FFMA)
+    assert tc[0].tobytes() == ff[0].tobytes()
+    assert (tc[1][0].tobytes(), tc[1][1].tobytes()) == (ff[1][0].tobytes(), ff[1][1].tobytes())
+    if n <= 4500:
+        m_ref, mid_ref = orc.median_chain(X, radix=True)
+        assert tc[0].tobytes() == m_ref.tobytes()
+        assert (tc[1][0].tobytes(), tc[1][1].tobytes()) == (mid_ref[0].tobytes(), mid_ref[1].tobytes())
+    assert tc[2] == 1          # one distance sweep
+
+
 def test_histogram_sweep_counts_are_exact(ctx):
     import torch
     n, d = 1000, 24
@@ -197,7 +231,7 @@ def test_phi_dense_matches_oracle(ctx, n, d, scale):
 
 
 FLASH_CASES = [(128, 256, 1.0), (130, 256, 1.0), (640, 256, 1.0), (1000, 128, 0.3), (3000, 256, 1.0),
-               (2500, 200, 0.01), (4096, 100, 1.0)]
+               (2500, 250, 0.01), (4096, 100, 1.0)]
 
 
 @pytest.mark.parametrize("n,d,scale", FLASH_CASES)
@@ -542,6 +576,13 @@ def test_full_size_properties(ctx):
     ctx.check(ctx.lib.stein_median_sqdist(ctx.handle, _ptr(Xd), _ptr(r), n, d, d, ctypes.byref(med), mid,
                                           ctypes.byref(sweeps)))
     assert mid[0] <= med.value <= mid[1] and sweeps.value <= 3
+    # the tensor-core route (AUTO at this shape) and the all-FFMA route agree bit for bit
+    from stein_b200 import _lib
+    ctx.set_median_impl(_lib.MEDIAN_FFMA)
+    med_f, mid_f = ctypes.c_float(), (ctypes.c_float * 2)()
+    ctx.check(ctx.lib.stein_median_sqdist(ctx.handle, _ptr(Xd), _ptr(r), n, d, d, ctypes.byref(med_f), mid_f, None))
+    ctx.set_median_impl(0)
+    assert (med_f.value, mid_f[0], mid_f[1]) == (med.value, mid[0], mid[1])
     sub = [float(orc.median_chain(X[rng.choice(n, 2048, replace=False)])[0]) for _ in range(3)]
     assert min(sub) * 0.995 < med.value < max(sub) * 1.005
     k0, k1 = ctx.lib.stein_float_to_key(mid[0]), ctx.lib.stein_float_to_key(mid[1])
