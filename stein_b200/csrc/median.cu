@@ -219,6 +219,8 @@ bool median_tc_supported(int64_t n, int64_t d);
 int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t d, int64_t ld,
               const uint64_t ranks[2], uint32_t win_lo_key, uint32_t win_hi_key, uint32_t keys_out[2],
               int *sweeps);
+int pilot_window(stein_ctx *ctx, const uint32_t *keys_dev, int64_t m, uint64_t rank_lo, uint64_t rank_hi,
+                 uint32_t *lo_key, uint32_t *hi_key);
 
 }  // namespace stein
 
@@ -362,14 +364,8 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
             X_dev, r_dev, n, ld, pilot_m, 0x5eedull, ctx->d_pilot_keys);
         STEIN_CHECK_LAUNCH(ctx);
         const uint64_t delta = (uint64_t)(3.5 * sqrt((double)pilot_m));
-        select_keys_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_pilot_keys, pilot_m,
-                                                        pilot_m / 2 - delta, pilot_m / 2 + delta,
-                                                        ctx->d_sel);
-        STEIN_CHECK_LAUNCH(ctx);
-        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_sel, ctx->d_sel, sizeof(uint32_t) * 2,
-                                              cudaMemcpyDeviceToHost, ctx->stream));
-        STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        const uint32_t ka = ctx->h_sel[0], kb = ctx->h_sel[1];
+        uint32_t ka = 0, kb = 0;
+        STEIN_TRY(pilot_window(ctx, ctx->d_pilot_keys, pilot_m, pilot_m / 2 - delta, pilot_m / 2 + delta, &ka, &kb));
         if (kb >= ka) {
             const uint64_t span = (uint64_t)kb - ka + 1;
             uint32_t sh = 0;

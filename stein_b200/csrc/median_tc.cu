@@ -30,9 +30,9 @@ using namespace tc;
 
 constexpr int SW_THREADS = 384;
 constexpr int SW_EPI_THREADS = 256;
-constexpr int SW_STAGES = 4;
+constexpr int SW_STAGES = 5;
 constexpr uint32_t SW_UNIT_BYTES = 128 * 128;
-constexpr int SW_STAGE_CAP = 2048;          // entries staged in shared memory per flush
+constexpr int SW_STAGE_CAP = 1024;          // entries staged in shared memory between flushes
 constexpr uint32_t SW_TMEM_COLS = 256;
 
 struct PairEntry {
@@ -238,13 +238,17 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
             // S buffer b may be overwritten by the GEMM of tile jj + 2
             tcgen05_fence_before();
             mbar_arrive(&bars->s_empty[b]);
-            // flush the staged entries: one global reservation per tile
+            // flush the staged entries when the buffer is half full (or at the last tile):
+            // one global reservation per flush, not per tile
             named_bar_sync(1, SW_EPI_THREADS);
             if (tid256 == 0) {
-                const unsigned int cnt = min(*sCount, (unsigned)SW_STAGE_CAP);
-                *sN = cnt;
-                *sBase = cnt ? atomicAdd(&p.counters[2], (unsigned long long)cnt) : 0ull;
-                *sCount = 0u;
+                const unsigned int have = min(*sCount, (unsigned)SW_STAGE_CAP);
+                const bool flush = have > (unsigned)SW_STAGE_CAP / 2 || (t + 1 == my1 && have > 0);
+                *sN = flush ? have : 0u;
+                if (flush) {
+                    *sBase = atomicAdd(&p.counters[2], (unsigned long long)have);
+                    *sCount = 0u;
+                }
             }
             named_bar_sync(2, SW_EPI_THREADS);
             const unsigned int cnt = *sN;
@@ -254,8 +258,8 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                     if (base + e < p.list_cap) p.list[base + e] = sBuf[e];
                     else *p.overflow = 1;
                 }
+                named_bar_sync(3, SW_EPI_THREADS);
             }
-            named_bar_sync(3, SW_EPI_THREADS);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -326,6 +330,9 @@ hist_pass_kernel(const void *__restrict__ src, unsigned long long m, uint32_t pr
             const PairEntry pe = reinterpret_cast<const PairEntry *>(src)[e];
             key = float_to_key(pe.dt);
             w = (pe.jw >> 31) ? 2u : 1u;
+        } else if (SRC == 2) {
+            key = reinterpret_cast<const uint32_t *>(src)[e];
+            w = 1u;
         } else {
             const uint2 kw = reinterpret_cast<const uint2 *>(src)[e];
             key = kw.x;
@@ -339,42 +346,68 @@ hist_pass_kernel(const void *__restrict__ src, unsigned long long m, uint32_t pr
 }
 
 // entries certainly below t~ - delta are counted; entries that may fall inside
-// [t~ - delta, t~ + delta] get the contract-arithmetic distance and go to the band
+// [t~ - delta, t~ + delta] are compacted into the band (key slot filled by band_exact_kernel)
 __global__ void __launch_bounds__(256)
-band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, const float *__restrict__ X,
-                   const float *__restrict__ r, int64_t ld, float tlo, float thi, float c_half,
+band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, const float *__restrict__ r,
+                   float tlo, float thi, float c_half,
                    unsigned long long *__restrict__ counters /* [3] below, [4] band weighted, [5] band len */,
-                   uint2 *__restrict__ band, unsigned long long band_cap, int *__restrict__ overflow) {
-    unsigned int below = 0u;
+                   uint2 *__restrict__ band_ij, unsigned long long band_cap, int *__restrict__ overflow) {
+    unsigned int below = 0u, bw = 0u;
     for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < m;
          e += (unsigned long long)gridDim.x * blockDim.x) {
         const PairEntry pe = list[e];
         const uint32_t i = pe.i, j = pe.jw & 0x7fffffffu, w = (pe.jw >> 31) ? 2u : 1u;
-        const float tsum = r[i] + r[j];
-        const float eps = c_half * tsum;
+        const float eps = c_half * (r[i] + r[j]);
         if (pe.dt + eps < tlo) {
             below += w;
         } else if (pe.dt - eps <= thi) {
-            const float4 *a = reinterpret_cast<const float4 *>(X + (size_t)i * ld);
-            const float4 *b = reinterpret_cast<const float4 *>(X + (size_t)j * ld);
-            float acc = 0.0f;
-            for (int64_t k4 = 0; k4 < ld / 4; ++k4) {
-                const float4 u = a[k4], v = b[k4];
-                acc = __fmaf_rn(u.x, v.x, acc);
-                acc = __fmaf_rn(u.y, v.y, acc);
-                acc = __fmaf_rn(u.z, v.z, acc);
-                acc = __fmaf_rn(u.w, v.w, acc);
-            }
-            const uint32_t key = float_to_key(tsum - 2.0f * acc);
+            bw += w;
             const unsigned long long g = atomicAdd(&counters[5], 1ull);
-            if (g < band_cap) band[g] = make_uint2(key, w);
+            if (g < band_cap) band_ij[g] = make_uint2(pe.i, pe.jw);
             else *overflow = 1;
-            atomicAdd(&counters[4], (unsigned long long)w);
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
-    if ((threadIdx.x & 31) == 0 && below) atomicAdd(&counters[3], (unsigned long long)below);
+    for (int o = 16; o > 0; o >>= 1) {
+        below += __shfl_xor_sync(0xffffffffu, below, o);
+        bw += __shfl_xor_sync(0xffffffffu, bw, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (below) atomicAdd(&counters[3], (unsigned long long)below);
+        if (bw) atomicAdd(&counters[4], (unsigned long long)bw);
+    }
+}
+
+// contract-arithmetic distance of every band pair: (i, jw) -> (key, weight), in place.
+// The fma chain is sequential in k, so the row loads are issued 8 float4 pairs ahead.
+__global__ void __launch_bounds__(128)
+band_exact_kernel(uint2 *__restrict__ band, unsigned long long m, const float *__restrict__ X,
+                  const float *__restrict__ r, int64_t ld) {
+    const unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    const uint2 ij = band[e];
+    const uint32_t i = ij.x, j = ij.y & 0x7fffffffu, w = (ij.y >> 31) ? 2u : 1u;
+    const float4 *a = reinterpret_cast<const float4 *>(X + (size_t)i * ld);
+    const float4 *b = reinterpret_cast<const float4 *>(X + (size_t)j * ld);
+    float acc = 0.0f;
+    const int64_t n4 = ld / 4;        // ld % 32 == 0  ->  n4 % 8 == 0
+    for (int64_t k4 = 0; k4 < n4; k4 += 8) {
+        float4 u[8], v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            u[q] = __ldg(a + k4 + q);
+            v[q] = __ldg(b + k4 + q);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            acc = __fmaf_rn(u[q].x, v[q].x, acc);
+            acc = __fmaf_rn(u[q].y, v[q].y, acc);
+            acc = __fmaf_rn(u[q].z, v[q].z, acc);
+            acc = __fmaf_rn(u[q].w, v[q].w, acc);
+        }
+    }
+    const float tsum = r[i] + r[j];
+    band[e] = make_uint2(float_to_key(tsum - 2.0f * acc), w);
 }
 
 // worst-case |D~ - D_contract| <= eps_coeff(d) * (r_i + r_j):
@@ -407,7 +440,7 @@ static int ensure_arena(stein_ctx *ctx, int64_t rows, int64_t DP, uint64_t pairs
         STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.bins, 2048 * 8));
         STEIN_CHECK_CUDA(ctx, cudaMallocHost(&A.h_pinned, (2048 + 16) * 8));
     }
-    if (rows * DP > A.x_elems) {
+    if (rows * DP > A.x_elems && rows * DP > 0) {
         if (A.Xh) cudaFree(A.Xh);
         if (A.Xl) cudaFree(A.Xl);
         A.Xh = A.Xl = nullptr;
@@ -416,7 +449,7 @@ static int ensure_arena(stein_ctx *ctx, int64_t rows, int64_t DP, uint64_t pairs
         A.x_elems = rows * DP;
     }
     // the pilot window holds ~0.7 % of the pairs; room for 2 % (upper-triangular count)
-    const unsigned long long want = std::max<unsigned long long>(1ull << 20, pairs / 50);
+    const unsigned long long want = pairs ? std::max<unsigned long long>(1ull << 20, pairs / 50) : 0ull;
     if (want > A.list_cap) {
         if (A.list) cudaFree(A.list);
         if (A.band) cudaFree(A.band);
@@ -433,12 +466,13 @@ static int ensure_arena(stein_ctx *ctx, int64_t rows, int64_t DP, uint64_t pairs
 // reports the next larger key present (valid when *has_next) and the weight at/below the key
 template <int SRC>
 static int radix_select(stein_ctx *ctx, const void *src, unsigned long long m_local, uint64_t rank,
-                        uint32_t *key_out, uint64_t *cum_through_key, bool *has_next, uint32_t *next_key) {
+                        uint32_t *key_out, uint64_t *cum_through_key, bool *has_next, uint32_t *next_key,
+                        int max_bits = 32, bool distributed = true) {
     MedianArena &A = g_arena;
     uint32_t prefix = 0, mask = 0;
     int consumed = 0;
     uint64_t offset = 0;   // weight strictly below the current prefix range
-    while (consumed < 32) {
+    while (consumed < max_bits) {
         const int bits = std::min(11, 32 - consumed);
         const int shift = 32 - consumed - bits;
         const int nb = 1 << bits;
@@ -448,7 +482,7 @@ static int radix_select(stein_ctx *ctx, const void *src, unsigned long long m_lo
             hist_pass_kernel<SRC><<<grid, 256, 0, ctx->stream>>>(src, m_local, prefix, mask, shift, bits, A.bins);
             STEIN_CHECK_LAUNCH(ctx);
         }
-        if (ctx->has_comm && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.bins, nb) != 0)
+        if (distributed && ctx->has_comm && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.bins, nb) != 0)
             return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
         STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.h_pinned, A.bins, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
         STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -475,6 +509,24 @@ static int radix_select(stein_ctx *ctx, const void *src, unsigned long long m_lo
         }
     }
     *key_out = prefix;
+    return STEIN_OK;
+}
+
+// Window keys from the pilot sample: [lo, hi] brackets the sample quantiles at rank_lo /
+// rank_hi to 22-bit resolution (two histogram passes each; every rank holds the same sample,
+// so nothing is all-reduced).
+int pilot_window(stein_ctx *ctx, const uint32_t *keys_dev, int64_t m, uint64_t rank_lo, uint64_t rank_hi,
+                 uint32_t *lo_key, uint32_t *hi_key) {
+    if (!g_arena.counters) STEIN_TRY(ensure_arena(ctx, 0, 0, 0));
+    uint64_t cum;
+    bool hn;
+    uint32_t nk, k;
+    int rc = radix_select<2>(ctx, keys_dev, (unsigned long long)m, rank_lo, &k, &cum, &hn, &nk, 22, false);
+    if (rc != STEIN_OK) return rc;
+    *lo_key = k;                       // low 10 bits zero: start of the bin
+    rc = radix_select<2>(ctx, keys_dev, (unsigned long long)m, rank_hi, &k, &cum, &hn, &nk, 22, false);
+    if (rc != STEIN_OK) return rc;
+    *hi_key = k | 0x3FFu;              // end of the bin
     return STEIN_OK;
 }
 
@@ -577,7 +629,7 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
 
     if (list_len) {
         const unsigned grid = (unsigned)std::min<unsigned long long>((list_len + 255) / 256, 16ull * ctx->num_sms);
-        band_filter_kernel<<<grid, 256, 0, ctx->stream>>>(A.list, list_len, X, r, ld, tlo, thi, c_half, A.counters,
+        band_filter_kernel<<<grid, 256, 0, ctx->stream>>>(A.list, list_len, r, tlo, thi, c_half, A.counters,
                                                          A.band, A.band_cap, d_overflow);
         STEIN_CHECK_LAUNCH(ctx);
     }
@@ -603,6 +655,10 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     if (overflow2) return 1;
     const uint64_t c1 = below + below2;
     if (!(c1 <= ranks[0] && ranks[1] < c1 + band_w)) return 1;
+    if (band_len) {
+        band_exact_kernel<<<(unsigned)((band_len + 127) / 128), 128, 0, ctx->stream>>>(A.band, band_len, X, r, ld);
+        STEIN_CHECK_LAUNCH(ctx);
+    }
 
     // exact keys of the two target ranks among the band
     uint32_t k0 = 0, k1 = 0;
