@@ -200,29 +200,45 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
             const long long i = (long long)I * 128 + row;
             const float r_i = p.r[i];
             const float *rj = p.r + (size_t)J * 128;
+            const bool row_ok = i < p.n;
             mbar_wait(&bars->s_full[b], (uint32_t)((jj >> 1) & 1));
             tcgen05_fence_after();
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
                 const int ch = wg * 2 + cc;
+                const long long jbase = (long long)J * 128 + ch * 32;
+                const float rj_lane = __ldg(rj + ch * 32 + lane);      // column norms, one per lane
                 uint32_t v[32];
                 tmem_ld32(tmem + b * 128 + lane_addr + ch * 32, v);
                 tmem_wait_ld();
+                // classify: bit c of bmask = certainly below the window, of hmask = may be inside
+                uint32_t bmask = 0u, hmask = 0u;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    const long long j = (long long)J * 128 + ch * 32 + c;
-                    const float tsum = r_i + __ldg(rj + ch * 32 + c);
+                    const float tsum = r_i + __shfl_sync(0xffffffffu, rj_lane, c);
                     const float dt = fmaf(-2.0f, __uint_as_float(v[c]), tsum);
-                    const float eps = p.c_half * tsum;
-                    if (i < p.n && j < p.n) {
-                        if (dt + eps < p.wlo) {
-                            below += w;
-                        } else if (dt - eps <= p.whi) {
-                            listed += w;
+                    const bool isb = fmaf(p.c_half, tsum, dt) < p.wlo;
+                    const bool ish = !isb && fmaf(-p.c_half, tsum, dt) <= p.whi;
+                    bmask |= (isb ? 1u : 0u) << c;
+                    hmask |= (ish ? 1u : 0u) << c;
+                }
+                // ragged edges: rows / columns beyond n do not exist
+                const long long ncol = p.n - jbase;
+                const uint32_t cmask = !row_ok || ncol <= 0 ? 0u : (ncol >= 32 ? 0xffffffffu : ((1u << ncol) - 1u));
+                bmask &= cmask;
+                hmask &= cmask;
+                below += w * (unsigned)__popc(bmask);
+                if (hmask) {
+                    listed += w * (unsigned)__popc(hmask);
+                    const float rj_all = 0.0f;
+                    (void)rj_all;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        if ((hmask >> c) & 1u) {
                             PairEntry e;
                             e.i = (uint32_t)i;
-                            e.jw = (uint32_t)j | (w == 2u ? 0x80000000u : 0u);
-                            e.dt = dt;
+                            e.jw = (uint32_t)(jbase + c) | (w == 2u ? 0x80000000u : 0u);
+                            e.dt = fmaf(-2.0f, __uint_as_float(v[c]), r_i + rj[ch * 32 + c]);
                             const unsigned int slot = atomicAdd(sCount, 1u);
                             if (slot < (unsigned)SW_STAGE_CAP) {
                                 sBuf[slot] = e;
