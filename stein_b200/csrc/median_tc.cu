@@ -30,10 +30,11 @@ using namespace tc;
 
 constexpr int SW_THREADS = 384;
 constexpr int SW_EPI_THREADS = 256;
-constexpr int SW_STAGES = 5;
+constexpr int SW_STAGES = 12;
 constexpr uint32_t SW_UNIT_BYTES = 128 * 128;
 constexpr int SW_STAGE_CAP = 1024;          // entries staged in shared memory between flushes
-constexpr uint32_t SW_TMEM_COLS = 256;
+constexpr uint32_t SW_TMEM_COLS = 512;
+constexpr uint32_t SW_TMEM_AH = 256, SW_TMEM_AL = 384;   // A operand (row tile, BF16 hi / lo) in TMEM
 
 struct PairEntry {
     uint32_t i;
@@ -47,6 +48,7 @@ struct SweepParams {
     int kblocks;                  // DP / 64
     long long n;
     const float *r;
+    const uint32_t *Xh, *Xl;      // BF16 split of X viewed as 32-bit words (DP / 2 per row)
     float wlo, whi, c_half;
     unsigned long long *counters; // [0] certainly-below (weighted), [1] listed (weighted), [2] list length
     int *overflow;
@@ -60,20 +62,24 @@ struct SweepBarriers {
     uint64_t s_full[2], s_empty[2];
 };
 
+// The row tile X_I (A operand) lives in TENSOR MEMORY (columns 256..511: BF16 hi and lo,
+// two elements per 32-bit column), written by the classification warps when I changes.
+// That leaves all of shared memory to a 12-stage ring of column-tile boxes, deep enough to
+// hide the L2 latency of the TMA loads; with A resident in shared memory (5 stages) the
+// sweep ran at 14 % tensor-pipe utilisation.
 __global__ void __launch_bounds__(SW_THREADS, 1)
 sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
                 const SweepParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *sA = smem;                                              // [hi | lo] x kblocks x 16 KB
-    uint8_t *sRing = sA + (size_t)2 * p.kblocks * SW_UNIT_BYTES;
+    uint8_t *sRing = smem;
     uint8_t *tail = sRing + (size_t)SW_STAGES * SW_UNIT_BYTES;
     SweepBarriers *bars = reinterpret_cast<SweepBarriers *>(tail);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 192);
-    unsigned int *sCount = reinterpret_cast<unsigned int *>(tail + 196);
-    unsigned int *sN = reinterpret_cast<unsigned int *>(tail + 200);
-    unsigned long long *sBase = reinterpret_cast<unsigned long long *>(tail + 208);
-    PairEntry *sBuf = reinterpret_cast<PairEntry *>(tail + 256);     // SW_STAGE_CAP entries
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 256);
+    unsigned int *sCount = reinterpret_cast<unsigned int *>(tail + 260);
+    unsigned int *sN = reinterpret_cast<unsigned int *>(tail + 264);
+    unsigned long long *sBase = reinterpret_cast<unsigned long long *>(tail + 272);
+    PairEntry *sBuf = reinterpret_cast<PairEntry *>(tail + 320);     // SW_STAGE_CAP entries
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long NT = p.t_end - p.t_begin;
@@ -85,7 +91,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
             mbar_init(&bars->full[s], 1);
             mbar_init(&bars->empty[s], 1);
         }
-        mbar_init(&bars->a_full, 1);
+        mbar_init(&bars->a_full, SW_EPI_THREADS);
         mbar_init(&bars->a_empty, 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->s_full[b], 1);
@@ -106,24 +112,12 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 0 && lane == 0) {
-            // ===================== TMA producer =====================
+            // ===================== TMA producer: column tiles only =====================
             int stage = 0;
             uint32_t phase = 0;
-            int prevI = -1, aseg = 0;
             for (long long t = my0; t < my1; ++t) {
                 int I, J;
                 tri_tile(t, p.T, I, J);
-                if (I != prevI) {
-                    if (aseg > 0) mbar_wait(&bars->a_empty, (uint32_t)((aseg - 1) & 1));
-                    mbar_expect_tx(&bars->a_full, (uint32_t)(2 * p.kblocks) * SW_UNIT_BYTES);
-                    for (int kb = 0; kb < p.kblocks; ++kb) {
-                        tma_load_2d(sA + (size_t)kb * SW_UNIT_BYTES, &mapXh, &bars->a_full, kb * 64, I * 128);
-                        tma_load_2d(sA + (size_t)(p.kblocks + kb) * SW_UNIT_BYTES, &mapXl, &bars->a_full, kb * 64,
-                                    I * 128);
-                    }
-                    ++aseg;
-                    prevI = I;
-                }
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     for (int part = 0; part < 2; ++part) {
                         mbar_wait(&bars->empty[stage], phase ^ 1);
@@ -145,7 +139,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                 int I, J;
                 tri_tile(t, p.T, I, J);
                 if (I != prevI) {
-                    if (prevI != -1) tcgen05_commit(&bars->a_empty);   // all MMAs on the old A tile issued
+                    if (prevI != -1) tcgen05_commit(&bars->a_empty);   // every MMA on the old A tile is issued
                     mbar_wait(&bars->a_full, (uint32_t)(aseg & 1));
                     tcgen05_fence_after();
                     ++aseg;
@@ -158,24 +152,22 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                 }
                 const uint32_t d_tmem = tmem + b * 128;
                 for (int kb = 0; kb < p.kblocks; ++kb) {
-                    const uint64_t ah = make_kmajor_sw128_desc(smem_u32(sA + (size_t)kb * SW_UNIT_BYTES));
-                    const uint64_t al =
-                        make_kmajor_sw128_desc(smem_u32(sA + (size_t)(p.kblocks + kb) * SW_UNIT_BYTES));
+                    const uint32_t ah = tmem + SW_TMEM_AH + kb * 32, al = tmem + SW_TMEM_AL + kb * 32;
                     mbar_wait(&bars->full[stage], phase);
                     tcgen05_fence_after();
                     uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sRing + (size_t)stage * SW_UNIT_BYTES));
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4)
-                        umma_f16_ss(d_tmem, ah + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0);
+                        umma_f16_ts(d_tmem, ah + 8 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0);   // hi.hi
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) umma_f16_ss(d_tmem, al + 2 * k4, bdesc + 2 * k4, idesc, 1u);
+                    for (int k4 = 0; k4 < 4; ++k4) umma_f16_ts(d_tmem, al + 8 * k4, bdesc + 2 * k4, idesc, 1u);   // lo.hi
                     tcgen05_commit(&bars->empty[stage]);
                     if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
                     mbar_wait(&bars->full[stage], phase);
                     tcgen05_fence_after();
                     bdesc = make_kmajor_sw128_desc(smem_u32(sRing + (size_t)stage * SW_UNIT_BYTES));
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) umma_f16_ss(d_tmem, ah + 2 * k4, bdesc + 2 * k4, idesc, 1u);
+                    for (int k4 = 0; k4 < 4; ++k4) umma_f16_ts(d_tmem, ah + 8 * k4, bdesc + 2 * k4, idesc, 1u);   // hi.lo
                     tcgen05_commit(&bars->empty[stage]);
                     if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -190,14 +182,40 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
         const int row = q * 32 + lane;
         const int tid256 = (warp - 4) * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const int wpr = p.kblocks * 32;             // 32-bit words per row of Xh / Xl
         unsigned int below = 0u, listed = 0u;
+        int prevI = -1, aseg = 0;
         long long jj = 0;
         for (long long t = my0; t < my1; ++t, ++jj) {
             int I, J;
             tri_tile(t, p.T, I, J);
+            const long long i = (long long)I * 128 + row;
+            if (I != prevI) {
+                // new row tile: (re)write the A operand in tensor memory.  Warpgroup 0 writes
+                // the hi words of row i, warpgroup 1 the lo words.
+                if (aseg > 0) {
+                    mbar_wait(&bars->a_empty, (uint32_t)((aseg - 1) & 1));
+                    tcgen05_fence_after();
+                }
+                const uint4 *src = reinterpret_cast<const uint4 *>((wg ? p.Xl : p.Xh) + (size_t)i * wpr);
+                const uint32_t dst = tmem + lane_addr + (wg ? SW_TMEM_AL : SW_TMEM_AH);
+                for (int ch = 0; ch < p.kblocks; ++ch) {
+                    uint32_t v[32];
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        const uint4 u = __ldg(src + ch * 8 + q4);
+                        v[4 * q4] = u.x; v[4 * q4 + 1] = u.y; v[4 * q4 + 2] = u.z; v[4 * q4 + 3] = u.w;
+                    }
+                    tmem_st32(dst + ch * 32, v);
+                }
+                tmem_wait_st();
+                tcgen05_fence_before();
+                mbar_arrive(&bars->a_full);
+                ++aseg;
+                prevI = I;
+            }
             const int b = (int)(jj & 1);
             const unsigned int w = (I == J) ? 1u : 2u;
-            const long long i = (long long)I * 128 + row;
             const float r_i = p.r[i];
             const float *rj = p.r + (size_t)J * 128;
             const bool row_ok = i < p.n;
@@ -208,8 +226,9 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                 const int ch = wg * 2 + cc;
                 const long long jbase = (long long)J * 128 + ch * 32;
                 const float rj_lane = __ldg(rj + ch * 32 + lane);      // column norms, one per lane
+                const uint32_t s_addr = tmem + b * 128 + lane_addr + ch * 32;
                 uint32_t v[32];
-                tmem_ld32(tmem + b * 128 + lane_addr + ch * 32, v);
+                tmem_ld32(s_addr, v);
                 tmem_wait_ld();
                 // classify: bit c of bmask = certainly below the window, of hmask = may be inside
                 uint32_t bmask = 0u, hmask = 0u;
@@ -228,25 +247,28 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                 bmask &= cmask;
                 hmask &= cmask;
                 below += w * (unsigned)__popc(bmask);
-                if (hmask) {
-                    listed += w * (unsigned)__popc(hmask);
-                    const float rj_all = 0.0f;
-                    (void)rj_all;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        if ((hmask >> c) & 1u) {
-                            PairEntry e;
-                            e.i = (uint32_t)i;
-                            e.jw = (uint32_t)(jbase + c) | (w == 2u ? 0x80000000u : 0u);
-                            e.dt = fmaf(-2.0f, __uint_as_float(v[c]), r_i + rj[ch * 32 + c]);
-                            const unsigned int slot = atomicAdd(sCount, 1u);
-                            if (slot < (unsigned)SW_STAGE_CAP) {
-                                sBuf[slot] = e;
-                            } else {   // staging full (degenerate data): straight to global
-                                const unsigned long long g = atomicAdd(&p.counters[2], 1ull);
-                                if (g < p.list_cap) p.list[g] = e;
-                                else *p.overflow = 1;
-                            }
+                listed += w * (unsigned)__popc(hmask);
+                // rare path (~0.7 % of the pairs): warp-uniform loop over the columns that have a hit
+                uint32_t um = __reduce_or_sync(0xffffffffu, hmask);
+                while (um) {
+                    const int c = __ffs(um) - 1;
+                    um &= um - 1u;
+                    uint32_t g;
+                    tmem_ld1(s_addr + c, g);
+                    const float rjc = __shfl_sync(0xffffffffu, rj_lane, c);
+                    tmem_wait_ld();
+                    if ((hmask >> c) & 1u) {
+                        PairEntry e;
+                        e.i = (uint32_t)i;
+                        e.jw = (uint32_t)(jbase + c) | (w == 2u ? 0x80000000u : 0u);
+                        e.dt = fmaf(-2.0f, __uint_as_float(g), r_i + rjc);
+                        const unsigned int slot = atomicAdd(sCount, 1u);
+                        if (slot < (unsigned)SW_STAGE_CAP) {
+                            sBuf[slot] = e;
+                        } else {   // staging full (degenerate data): straight to global
+                            const unsigned long long gi = atomicAdd(&p.counters[2], 1ull);
+                            if (gi < p.list_cap) p.list[gi] = e;
+                            else *p.overflow = 1;
                         }
                     }
                 }
@@ -584,6 +606,8 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     p.kblocks = (int)(DP / 64);
     p.n = n;
     p.r = r;
+    p.Xh = reinterpret_cast<const uint32_t *>(A.Xh);
+    p.Xl = reinterpret_cast<const uint32_t *>(A.Xl);
     p.wlo = key_to_float(win_lo_key);
     p.whi = key_to_float(win_hi_key);
     p.c_half = c_half;
@@ -591,13 +615,11 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     p.overflow = d_overflow;
     p.list = A.list;
     p.list_cap = A.list_cap;
-    const size_t smem = 1024 + (size_t)2 * (DP / 64) * SW_UNIT_BYTES + (size_t)SW_STAGES * SW_UNIT_BYTES + 256 +
-                        (size_t)SW_STAGE_CAP * sizeof(PairEntry) + 64;
+    const size_t smem = 1024 + (size_t)SW_STAGES * SW_UNIT_BYTES + 320 + (size_t)SW_STAGE_CAP * sizeof(PairEntry) + 64;
     static bool attr_set = false;
     if (!attr_set) {
         STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(sweep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)(1024 + 8 * SW_UNIT_BYTES + SW_STAGES * SW_UNIT_BYTES + 256 +
-                                                         SW_STAGE_CAP * sizeof(PairEntry) + 64)));
+                                                   (int)smem));
         attr_set = true;
     }
     if (t1 > t0) {
