@@ -71,7 +71,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
 sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
                 const SweepParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // (pointer arithmetic on the __shared__ array keeps the shared address space visible to the
+    //  compiler: LDS/STS/ATOMS instead of generic LD/ST/ATOM)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *sRing = smem;
     uint8_t *tail = sRing + (size_t)SW_STAGES * SW_UNIT_BYTES;
     SweepBarriers *bars = reinterpret_cast<SweepBarriers *>(tail);

@@ -120,7 +120,9 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
                  const FlashParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B-swizzle atoms
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // (pointer arithmetic on the __shared__ array keeps the shared address space visible to the
+    //  compiler: LDS/STS/ATOMS instead of generic LD/ST/ATOM)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *sA = smem;                                           // [hi | lo] x kblocks x 16 KB
     uint8_t *sRing = sA + (size_t)2 * p.kblocks * FL_UNIT_BYTES;  // FL_STAGES x 16 KB
     uint8_t *tail = sRing + (size_t)FL_STAGES * FL_UNIT_BYTES;
