@@ -62,6 +62,20 @@ struct SweepBarriers {
     uint64_t s_full[2], s_empty[2];
 };
 
+// v[c] for a run-time c without spilling the array to local memory: binary select tree
+__device__ __forceinline__ uint32_t select32(const uint32_t (&v)[32], int c) {
+    uint32_t a[16], b[8], d[4], e[2];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = (c & 1) ? v[2 * k + 1] : v[2 * k];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) b[k] = (c & 2) ? a[2 * k + 1] : a[2 * k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d[k] = (c & 4) ? b[2 * k + 1] : b[2 * k];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) e[k] = (c & 8) ? d[2 * k + 1] : d[2 * k];
+    return (c & 16) ? e[1] : e[0];
+}
+
 // The row tile X_I (A operand) lives in TENSOR MEMORY (columns 256..511: BF16 hi and lo,
 // two elements per 32-bit column), written by the classification warps when I changes.
 // That leaves all of shared memory to a 12-stage ring of column-tile boxes, deep enough to
@@ -250,21 +264,20 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                 hmask &= cmask;
                 below += w * (unsigned)__popc(bmask);
                 listed += w * (unsigned)__popc(hmask);
-                // rare path (~0.7 % of the pairs): warp-uniform loop over the columns that have a hit
-                uint32_t um = __reduce_or_sync(0xffffffffu, hmask);
-                while (um) {
-                    const int c = __ffs(um) - 1;
-                    um &= um - 1u;
-                    uint32_t g;
-                    tmem_ld1(s_addr + c, g);
-                    const float rjc = __shfl_sync(0xffffffffu, rj_lane, c);
-                    tmem_wait_ld();
-                    if ((hmask >> c) & 1u) {
+                // rare path (~0.7 % of the pairs, ~0.2 hits per thread and chunk): each thread with
+                // hits reserves its slots with one shared-memory atomic, then walks its set bits; the
+                // value of column c is picked out of the 32 registers with a 5-level select tree
+                if (hmask) {
+                    unsigned int slot = atomicAdd(sCount, (unsigned)__popc(hmask));
+                    uint32_t hm = hmask;
+                    while (hm) {
+                        const int c = __ffs(hm) - 1;
+                        hm &= hm - 1u;
+                        const float g = __uint_as_float(select32(v, c));
                         PairEntry e;
                         e.i = (uint32_t)i;
                         e.jw = (uint32_t)(jbase + c) | (w == 2u ? 0x80000000u : 0u);
-                        e.dt = fmaf(-2.0f, __uint_as_float(g), r_i + rjc);
-                        const unsigned int slot = atomicAdd(sCount, 1u);
+                        e.dt = fmaf(-2.0f, g, r_i + __ldg(rj + ch * 32 + c));
                         if (slot < (unsigned)SW_STAGE_CAP) {
                             sBuf[slot] = e;
                         } else {   // staging full (degenerate data): straight to global
@@ -272,6 +285,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                             if (gi < p.list_cap) p.list[gi] = e;
                             else *p.overflow = 1;
                         }
+                        ++slot;
                     }
                 }
             }
