@@ -102,7 +102,7 @@ int stein_ctx_set_comm(stein_ctx *ctx, const stein_comm *comm) {
 
 int stein_ctx_set_phi_impl(stein_ctx *ctx, int impl) {
     STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
-    STEIN_REQUIRE(ctx, impl >= STEIN_PHI_AUTO && impl <= STEIN_PHI_FLASH_TC, "unknown phi impl %d", impl);
+    STEIN_REQUIRE(ctx, impl >= STEIN_PHI_AUTO && impl <= STEIN_PHI_FLASH_TC2, "unknown phi impl %d", impl);
     ctx->phi_impl = impl;
     return STEIN_OK;
 }
@@ -170,6 +170,13 @@ int stein_phi(stein_ctx *ctx, const float *X_all_dev, const float *S_all_dev, co
     STEIN_REQUIRE(ctx, bandwidth > 0.0f && bandwidth == bandwidth, "bandwidth must be positive and finite");
     const float h2 = bandwidth * bandwidth;  // squared_exponential_kernel.py:22 tf.square(bandwidth)
     const int impl = pick_phi_impl(ctx, n_local, n_total, d);
+    if (impl == STEIN_PHI_FLASH_TC2) {
+        if (!flash_tc2_supported(ctx, n_local, n_total, d))
+            return fail(ctx, STEIN_ERR_UNSUPPORTED, "CTA-pair flash phi does not take n=%lld d=%lld",
+                        (long long)n_total, (long long)d);
+        return phi_flash_tc2(ctx, X_all_dev, S_all_dev, r_all_dev, n_total, d, ld, row_begin, n_local, h2,
+                             workspace_dev, workspace_bytes, phi_dev, sumsq_dev);
+    }
     if (impl == STEIN_PHI_FLASH_TC) {
         if (!flash_tc_supported(ctx, n_local, n_total, d))
             return fail(ctx, STEIN_ERR_UNSUPPORTED, "flash tcgen05 phi does not take n=%lld d=%lld",

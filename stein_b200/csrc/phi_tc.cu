@@ -395,12 +395,350 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
     }
 }
 
+// =====================================================================================
+// CTA-pair version (cta_group::2), DP = 256.  Two CTAs of a cluster own 256 particle rows
+// (128 each, each CTA's accumulators in its own TMEM); the LEADER (cluster rank 0) issues
+// every tcgen05.mma for both with M = 256.  The B operand of each MMA is split between the
+// two CTAs' shared memories, so every SM loads only HALF of each column tile:
+//   GEMM1  N = 128: each CTA stages 64 rows of X_J (hi and lo blocks share one 16 KB slot),
+//   GEMM2  N = 256: each CTA stages 128 of the 256 rows of Y^T (one slot for hi, one for lo).
+// Per column tile an SM now streams 128 KB instead of 256 KB and the leader issues 72 MMAs
+// for 256 rows instead of 96 per 128 rows; the 6-slot ring covers twice the latency.
+// Barriers that gate the leader's MMA thread (full, a_full, p_full, o_empty) live in the
+// leader CTA and receive remote arrivals / TMA bytes from the peer; barriers that release
+// work to both CTAs (empty, a_empty, s_full, o_full) are signalled by multicast commits.
+// =====================================================================================
+struct Flash2Params {
+    int nJ;               // column tiles (128 particles)
+    int nI2;              // row pair-tiles (256 particles)
+    int row_pair0;        // (unused)
+    long long row_begin;  // first global particle row of the local block (multiple of 128)
+    float c1;
+    const float *nrm;
+    float *Opart;
+    long long o_slot_stride;
+    float *ksum_part;
+    long long k_slot_stride;
+};
+
+struct Seg2Iter {   // same round-synchronous schedule as SegIter, over cluster pairs
+    int nI, nJ, G, c, k, rounds, rem, s;
+    __device__ Seg2Iter(const Flash2Params &p)
+        : nI(p.nI2), nJ(p.nJ), G((int)gridDim.x / 2), c((int)blockIdx.x / 2), k(0) {
+        rounds = nI / G;
+        rem = nI % G;
+        s = rem ? G / rem : 1;
+        if (s > nJ) s = nJ;
+    }
+    __device__ bool next(int &t, int &j0, int &j1, int &slot) {
+        if (k < rounds) {
+            t = k * G + c;
+            j0 = 0;
+            j1 = nJ;
+            slot = 0;
+            ++k;
+            return true;
+        }
+        if (k == rounds && rem && c < rem * s) {
+            t = rounds * G + c / s;
+            slot = c % s;
+            j0 = (int)((long long)nJ * slot / s);
+            j1 = (int)((long long)nJ * (slot + 1) / s);
+            ++k;
+            return j1 > j0;
+        }
+        return false;
+    }
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FL_THREADS, 1)
+flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
+                  const __grid_constant__ CUtensorMap mapXh64, const __grid_constant__ CUtensorMap mapXl64,
+                  const __grid_constant__ CUtensorMap mapYh, const __grid_constant__ CUtensorMap mapYl,
+                  const Flash2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int KB = FL_MAX_DP / 64;                            // 4 K-blocks of 64 bf16
+    uint8_t *sA = smem;                                           // [hi | lo] x 4 x 16 KB (this CTA's 128 rows)
+    uint8_t *sRing = sA + (size_t)2 * KB * FL_UNIT_BYTES;         // FL_STAGES x 16 KB
+    uint8_t *tail = sRing + (size_t)FL_STAGES * FL_UNIT_BYTES;
+    FlashBarriers *bars = reinterpret_cast<FlashBarriers *>(tail);
+    float *sB = reinterpret_cast<float *>(tail + 256);
+    float *sK = reinterpret_cast<float *>(tail + 256 + 1024);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 256 + 1024 + 512);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < FL_STAGES; ++s) {
+            mbar_init(&bars->full[s], 1);          // leader: one expect_tx arrival, bytes from both CTAs
+            mbar_init(&bars->empty[s], 1);         // multicast commit
+        }
+        mbar_init(&bars->a_full, 1);
+        mbar_init(&bars->a_empty, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars->s_full[b], 1);                        // multicast commit
+            mbar_init(&bars->p_full[b], 2 * FL_EPI_THREADS);       // leader: both CTAs' epilogue threads
+        }
+        mbar_init(&bars->o_full, 1);                               // multicast commit
+        mbar_init(&bars->o_empty, 2 * FL_EPI_THREADS);             // leader
+        fence_barrier_init();
+        fence_proxy_async();
+        tma_prefetch_desc(&mapXh);
+        tma_prefetch_desc(&mapXl);
+        tma_prefetch_desc(&mapXh64);
+        tma_prefetch_desc(&mapXl64);
+        tma_prefetch_desc(&mapYh);
+        tma_prefetch_desc(&mapYl);
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();            // peer barriers are initialised before anyone signals them
+    tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            auto acquire = [&](uint32_t bytes_both) {
+                mbar_wait(&bars->empty[stage], phase ^ 1);         // local: multicast commit of the leader
+                if (leader) mbar_expect_tx(&bars->full[stage], bytes_both);
+            };
+            auto advance = [&]() {
+                if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
+            };
+            Seg2Iter it(p);
+            int t, j0, j1, slot, seg = 0;
+            while (it.next(t, j0, j1, slot)) {
+                if (seg > 0) mbar_wait(&bars->a_empty, (uint32_t)((seg - 1) & 1));
+                if (leader) mbar_expect_tx(&bars->a_full, 2u * 2u * KB * FL_UNIT_BYTES);
+                const int arow = (int)p.row_begin + (t * 2 + (int)rank) * 128;
+                for (int kb = 0; kb < KB; ++kb) {
+                    tma_load_2d_pair(sA + (size_t)kb * FL_UNIT_BYTES, &mapXh, &bars->a_full, kb * 64, arow);
+                    tma_load_2d_pair(sA + (size_t)(KB + kb) * FL_UNIT_BYTES, &mapXl, &bars->a_full, kb * 64, arow);
+                }
+                auto emit_g1 = [&](int j) {       // slot = [64 rows of X_J hi | 64 rows of X_J lo]
+                    for (int kb = 0; kb < KB; ++kb) {
+                        acquire(2u * FL_UNIT_BYTES);
+                        uint8_t *dst = sRing + (size_t)stage * FL_UNIT_BYTES;
+                        tma_load_2d_pair(dst, &mapXh64, &bars->full[stage], kb * 64, j * 128 + (int)rank * 64);
+                        tma_load_2d_pair(dst + FL_UNIT_BYTES / 2, &mapXl64, &bars->full[stage], kb * 64,
+                                         j * 128 + (int)rank * 64);
+                        advance();
+                    }
+                };
+                auto emit_g2 = [&](int j) {       // slot = 128 of the 256 rows of Y^T (hi, then lo)
+                    for (int kb2 = 0; kb2 < 2; ++kb2) {
+                        acquire(2u * FL_UNIT_BYTES);
+                        tma_load_2d_pair(sRing + (size_t)stage * FL_UNIT_BYTES, &mapYh, &bars->full[stage],
+                                         j * 128 + kb2 * 64, (int)rank * 128);
+                        advance();
+                        acquire(2u * FL_UNIT_BYTES);
+                        tma_load_2d_pair(sRing + (size_t)stage * FL_UNIT_BYTES, &mapYl, &bars->full[stage],
+                                         j * 128 + kb2 * 64, (int)rank * 128);
+                        advance();
+                    }
+                };
+                emit_g1(j0);
+                for (int j = j0; j < j1; ++j) {
+                    if (j + 1 < j1) emit_g1(j + 1);
+                    emit_g2(j);
+                }
+                ++seg;
+            }
+        }
+        } else if (warp == 1 && leader) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0) {
+            const uint32_t idesc1 = make_idesc(FMT_BF16, 256, 128);   // GEMM1: M = 256 (pair), N = 128
+            const uint32_t idesc2 = make_idesc(FMT_BF16, 256, 256);   // GEMM2: N = 256
+            int stage = 0;
+            uint32_t phase = 0;
+            long long jj = 0, oc = 0;
+            auto next_unit = [&]() -> uint32_t {
+                mbar_wait(&bars->full[stage], phase);
+                tcgen05_fence_after();
+                return smem_u32(sRing + (size_t)stage * FL_UNIT_BYTES);
+            };
+            auto release_unit = [&]() {
+                tcgen05_commit_pair(&bars->empty[stage]);
+                if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
+            };
+            auto g1 = [&](long long jcount) {
+                const uint32_t d_tmem = tmem + ((jcount & 1) ? TMEM_S1 : TMEM_S0);
+#pragma unroll 1
+                for (int kb = 0; kb < KB; ++kb) {
+                    const uint64_t ah = make_kmajor_sw128_desc(smem_u32(sA + (size_t)kb * FL_UNIT_BYTES));
+                    const uint64_t al = make_kmajor_sw128_desc(smem_u32(sA + (size_t)(KB + kb) * FL_UNIT_BYTES));
+                    const uint32_t slot_addr = next_unit();
+                    const uint64_t bh = make_kmajor_sw128_desc(slot_addr);
+                    const uint64_t bl = make_kmajor_sw128_desc(slot_addr + FL_UNIT_BYTES / 2);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ss(d_tmem, ah + 2 * k4, bh + 2 * k4, idesc1, (kb | k4) != 0);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ss(d_tmem, al + 2 * k4, bh + 2 * k4, idesc1, 1u);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ss(d_tmem, ah + 2 * k4, bl + 2 * k4, idesc1, 1u);
+                    release_unit();
+                }
+                tcgen05_commit_pair(&bars->s_full[jcount & 1]);
+            };
+            auto g2 = [&](long long jcount, bool first_of_chunk) {
+                const uint32_t a_base = tmem + ((jcount & 1) ? TMEM_S1 : TMEM_S0);
+#pragma unroll 1
+                for (int kb2 = 0; kb2 < 2; ++kb2) {
+                    uint64_t bdesc = make_kmajor_sw128_desc(next_unit());      // Y hi: Phi.Yhi + Plo.Yhi
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const uint32_t ph = a_base + p_hi_col(kb2 * 4 + k4);
+                        umma2_f16_ts(tmem, ph, bdesc + 2 * k4, idesc2, !(first_of_chunk && kb2 == 0 && k4 == 0));
+                        umma2_f16_ts(tmem, ph + 16, bdesc + 2 * k4, idesc2, 1u);
+                    }
+                    release_unit();
+                    bdesc = make_kmajor_sw128_desc(next_unit());               // Y lo: Phi.Ylo
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        umma2_f16_ts(tmem, a_base + p_hi_col(kb2 * 4 + k4), bdesc + 2 * k4, idesc2, 1u);
+                    release_unit();
+                }
+            };
+            Seg2Iter it(p);
+            int t, j0, j1, slot, seg = 0;
+            while (it.next(t, j0, j1, slot)) {
+                mbar_wait(&bars->a_full, (uint32_t)(seg & 1));
+                tcgen05_fence_after();
+                g1(jj);
+                for (int j = j0; j < j1; ++j, ++jj) {
+                    if (j + 1 < j1) g1(jj + 1);
+                    mbar_wait(&bars->p_full[jj & 1], (uint32_t)((jj >> 1) & 1));
+                    tcgen05_fence_after();
+                    const int ti = j - j0;
+                    const bool first_of_chunk = (ti % FL_OCHUNK) == 0;
+                    if (first_of_chunk && oc > 0) {
+                        mbar_wait(&bars->o_empty, (uint32_t)((oc - 1) & 1));
+                        tcgen05_fence_after();
+                    }
+                    g2(jj, first_of_chunk);
+                    if (((ti + 1) % FL_OCHUNK) == 0 || j == j1 - 1) {
+                        tcgen05_commit_pair(&bars->o_full);
+                        ++oc;
+                    }
+                }
+                tcgen05_commit_pair(&bars->a_empty);
+                ++seg;
+            }
+        }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        // ============ exponential / epilogue warpgroups (both CTAs, own 128 rows) ============
+        const int q = warp & 3;
+        const int wg = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        const int tid256 = (warp - 4) * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        constexpr int ocols = FL_MAX_DP / 2, och = ocols / 32;
+        // leader-side barriers, as shared::cluster addresses
+        const uint32_t p_full_addr0 = mapa_shared(smem_u32(&bars->p_full[0]), 0);
+        const uint32_t p_full_addr1 = mapa_shared(smem_u32(&bars->p_full[1]), 0);
+        const uint32_t o_empty_addr = mapa_shared(smem_u32(&bars->o_empty), 0);
+        Seg2Iter it(p);
+        int t, j0, j1, slot;
+        long long jj = 0, oc = 0;
+        float acc[ocols];
+        while (it.next(t, j0, j1, slot)) {
+            const size_t grow = (size_t)p.row_begin + ((size_t)t * 2 + rank) * 128 + row;   // global particle row
+            const size_t lrow = ((size_t)t * 2 + rank) * 128 + row;                    // row in the local block
+            const float a_i = p.nrm[grow];
+            float ksum = 0.0f;
+#pragma unroll
+            for (int c = 0; c < ocols; ++c) acc[c] = 0.0f;
+            for (int j = j0; j < j1; ++j, ++jj) {
+                const int b = (int)(jj & 1);
+                if (tid256 < 128) sB[b * 128 + tid256] = p.nrm[(size_t)j * 128 + tid256];
+                named_bar_sync(1, FL_EPI_THREADS);
+                mbar_wait(&bars->s_full[b], (uint32_t)((jj >> 1) & 1));
+                tcgen05_fence_after();
+                const uint32_t s_addr = tmem + (b ? TMEM_S1 : TMEM_S0) + lane_addr;
+#pragma unroll 1
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int ch = wg * 2 + cc;
+                    uint32_t v[32];
+                    tmem_ld32(s_addr + ch * 32, v);
+                    tmem_wait_ld();
+                    uint32_t w[32];
+#pragma unroll
+                    for (int c2 = 0; c2 < 16; ++c2) {
+                        const float e0 = ex2_approx(
+                            fmaf(__uint_as_float(v[2 * c2]), p.c1, a_i + sB[b * 128 + ch * 32 + 2 * c2]));
+                        const float e1 = ex2_approx(
+                            fmaf(__uint_as_float(v[2 * c2 + 1]), p.c1, a_i + sB[b * 128 + ch * 32 + 2 * c2 + 1]));
+                        ksum += e0 + e1;
+                        const uint32_t wh = pack_bf16x2(e0, e1);
+                        const float h0 = __uint_as_float(wh << 16), h1 = __uint_as_float(wh & 0xffff0000u);
+                        w[c2] = wh;
+                        w[16 + c2] = pack_bf16x2(e0 - h0, e1 - h1);
+                    }
+                    tmem_st32(s_addr + ch * 32, w);
+                }
+                tmem_wait_st();
+                tcgen05_fence_before();
+                mbar_arrive_cluster(b ? p_full_addr1 : p_full_addr0);
+
+                const int ti = j - j0;
+                if (((ti + 1) % FL_OCHUNK) == 0 || j == j1 - 1) {
+                    mbar_wait(&bars->o_full, (uint32_t)(oc & 1));
+                    tcgen05_fence_after();
+#pragma unroll
+                    for (int ch = 0; ch < och; ++ch) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem + lane_addr + wg * ocols + ch * 32, v);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) acc[ch * 32 + c] += __uint_as_float(v[c]);
+                    }
+                    tcgen05_fence_before();
+                    mbar_arrive_cluster(o_empty_addr);
+                    ++oc;
+                }
+            }
+            float *orow = p.Opart + (size_t)slot * p.o_slot_stride + lrow * FL_MAX_DP + wg * ocols;
+#pragma unroll
+            for (int ch = 0; ch < och; ++ch) {
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4)
+                    *reinterpret_cast<float4 *>(orow + ch * 32 + c4 * 4) =
+                        make_float4(acc[ch * 32 + c4 * 4], acc[ch * 32 + c4 * 4 + 1], acc[ch * 32 + c4 * 4 + 2],
+                                    acc[ch * 32 + c4 * 4 + 3]);
+            }
+            if (wg == 1) sK[row] = ksum;
+            named_bar_sync(2, FL_EPI_THREADS);
+            if (wg == 0) p.ksum_part[(size_t)slot * p.k_slot_stride + lrow] = ksum + sK[row];
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();            // no CTA leaves while its partner may still signal / read it
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc_pair(tmem, TMEM_COLS);
+    }
+}
+
 // ---- operand preparation ------------------------------------------------------------
 // BF16 two-term split of X (hi = bf16(x), lo = bf16(x - hi)); nrm[j] = -r_j log2(e)/(2 h^2)
 // (or -inf for j >= n)
 __global__ void prep_x_kernel(const float *__restrict__ X, const float *__restrict__ r, int64_t rows,
                               int64_t n, int64_t ld, float half_l2e_over_h2, __nv_bfloat16 *__restrict__ Xh,
-                              __nv_bfloat16 *__restrict__ Xl, float *__restrict__ nrm) {
+                              __nv_bfloat16 *__restrict__ Xl, float *__restrict__ nrm, int64_t nrm_rows) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t ld4 = ld / 4;
     if (e < rows * ld4) {
@@ -415,7 +753,7 @@ __global__ void prep_x_kernel(const float *__restrict__ X, const float *__restri
         reinterpret_cast<uint2 *>(Xh)[e] = *reinterpret_cast<uint2 *>(h);
         reinterpret_cast<uint2 *>(Xl)[e] = *reinterpret_cast<uint2 *>(l);
     }
-    if (e < rows) nrm[e] = (e < n) ? -r[e] * half_l2e_over_h2 : -INFINITY;
+    if (e < nrm_rows) nrm[e] = (e < n) ? -r[e] * half_l2e_over_h2 : -INFINITY;
 }
 
 // Y = S - X / h2, transposed (YT[c][j]) and split into BF16 hi / lo
@@ -501,14 +839,22 @@ static FlashPlan flash_plan(const stein_ctx *ctx, int64_t n_local, int64_t n_tot
     return pl;
 }
 
+static int pair_maxslots(const stein_ctx *ctx, int64_t n_local, int64_t n_total) {
+    const int64_t nI2 = round_up(stein_rows_padded(n_local), 256) / 256, nJ = (n_total + TILE - 1) / TILE;
+    const int64_t G2 = std::max(1, ctx->num_sms / 2), rem = nI2 % G2;
+    return (int)(rem ? std::min<int64_t>(G2 / rem, nJ) : 1);
+}
+
 // workspace: [Xh, Xl, YTh, YTl (bf16) | nrm | Opart slots | ksum slots | partials | tile_nslots]
 int64_t flash_tc_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
     const FlashPlan pl = flash_plan(ctx, n_local, n_total, d);
     int64_t b = 0;
     b += pl.cols * pl.DP * 2 * 4;                       // Xh, Xl, YTh, YTl (bf16)
-    b += pl.cols * 4;                                   // nrm
-    b += (int64_t)pl.maxslots * pl.rows * pl.DP * 4;    // Opart
-    b += (int64_t)pl.maxslots * pl.rows * 4;            // ksum
+    const int64_t rows2 = round_up(pl.rows, 256);       // the CTA-pair kernel works on 256-row tiles
+    const int64_t slots = std::max(pl.maxslots, pair_maxslots(ctx, n_local, n_total));
+    b += (pl.cols + 256) * 4;                           // nrm
+    b += slots * rows2 * pl.DP * 4;                     // Opart
+    b += slots * rows2 * 4;                             // ksum
     b += FINALIZE_MAX_BLOCKS * 8;
     b += pl.nI * 4;
     return b + 4096;
@@ -595,7 +941,7 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     {
         const int64_t tot = std::max<int64_t>(pl.cols * pl.DP / 4, pl.cols);
         prep_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(X_all, r_all, pl.cols, n_total, ld,
-                                                                             0.5f * l2e / h2, Xh, Xl, nrm);
+                                                                             0.5f * l2e / h2, Xh, Xl, nrm, pl.cols);
         STEIN_CHECK_LAUNCH(ctx);
         dim3 g((unsigned)(pl.cols / 32), (unsigned)(pl.DP / 32)), b(32, 8);
         prep_yt_kernel<<<g, b, 0, ctx->stream>>>(X_all, S_all, pl.cols, ld, 1.0f / h2, YTh, YTl);
@@ -645,6 +991,98 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     finalize_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(Opart, pl.rows * pl.DP, tile_nslots, ksum, pl.rows,
                                                            X_all + row_begin * ld, rows_valid, pl.rows, ld,
                                                            1.0f / h2, 1.0f / (float)n_total, phi, partials);
+    STEIN_CHECK_LAUNCH(ctx);
+    reduce_partials2_kernel<<<1, 256, 0, ctx->stream>>>(partials, blocks, sumsq);
+    STEIN_CHECK_LAUNCH(ctx);
+    return STEIN_OK;
+}
+
+// ---- CTA-pair launcher -----------------------------------------------------------------
+bool flash_tc2_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
+    (void)n_local;
+    return stein_ld(d) == FL_MAX_DP && n_total >= 2 && ctx->num_sms >= 2;
+}
+
+int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all, int64_t n_total,
+                  int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
+                  int64_t ws_bytes, float *phi, double *sumsq) {
+    const int64_t rows = stein_rows_padded(n_local), cols = stein_rows_padded(n_total), DP = FL_MAX_DP;
+    STEIN_REQUIRE(ctx, ld == DP, "CTA-pair flash phi needs ld == 256");
+    STEIN_REQUIRE(ctx, ws_bytes >= flash_tc_workspace_bytes(ctx, n_local, n_total, d), "phi workspace too small");
+    STEIN_REQUIRE(ctx, row_begin % TILE == 0, "row_begin must be a multiple of %d", TILE);
+    const int64_t rows2 = round_up(rows, 256);
+    const int64_t nI2 = rows2 / 256, nJ = (n_total + TILE - 1) / TILE;
+    const int G2 = ctx->num_sms / 2;                     // clusters
+    const int64_t rounds = nI2 / G2, rem = nI2 % G2;
+    int64_t sl = rem ? G2 / rem : 1;
+    sl = std::min<int64_t>(sl, nJ);
+    const int maxslots = (int)(rem ? sl : 1);
+    std::vector<int> tile_nslots(rows / TILE, 1);
+    for (int64_t t = rounds * G2; t < nI2; ++t)
+        for (int h = 0; h < 2; ++h)
+            if (2 * t + h < (int64_t)tile_nslots.size()) tile_nslots[2 * t + h] = (int)sl;
+
+    char *pws = (char *)ws;
+    __nv_bfloat16 *Xh = (__nv_bfloat16 *)pws;   pws += cols * DP * 2;
+    __nv_bfloat16 *Xl = (__nv_bfloat16 *)pws;   pws += cols * DP * 2;
+    __nv_bfloat16 *YTh = (__nv_bfloat16 *)pws;  pws += cols * DP * 2;
+    __nv_bfloat16 *YTl = (__nv_bfloat16 *)pws;  pws += cols * DP * 2;
+    float *nrm = (float *)pws;           pws += (cols + 256) * 4;
+    float *Opart = (float *)pws;         pws += (int64_t)maxslots * rows2 * DP * 4;
+    float *ksum = (float *)pws;          pws += (int64_t)maxslots * rows2 * 4;
+    double *partials = (double *)(((uintptr_t)pws + 7) & ~(uintptr_t)7);
+    pws = (char *)partials + FINALIZE_MAX_BLOCKS * 8;
+    int *d_tile_nslots = (int *)pws;
+
+    const float l2e = 1.4426950408889634f;
+    {
+        const int64_t tot = std::max<int64_t>(cols * DP / 4, cols + 256);
+        prep_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(X_all, r_all, cols, n_total, ld,
+                                                                             0.5f * l2e / h2, Xh, Xl, nrm, cols + 256);
+        STEIN_CHECK_LAUNCH(ctx);
+        dim3 g((unsigned)(cols / 32), (unsigned)(DP / 32)), b(32, 8);
+        prep_yt_kernel<<<g, b, 0, ctx->stream>>>(X_all, S_all, cols, ld, 1.0f / h2, YTh, YTl);
+        STEIN_CHECK_LAUNCH(ctx);
+    }
+    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(d_tile_nslots, tile_nslots.data(), tile_nslots.size() * sizeof(int),
+                                          cudaMemcpyHostToDevice, ctx->stream));
+    CUtensorMap mXh, mXl, mXh64, mXl64, mYh, mYl;
+    STEIN_TRY(make_tensor_map_2d(ctx, &mXh, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
+    STEIN_TRY(make_tensor_map_2d(ctx, &mXl, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
+    STEIN_TRY(make_tensor_map_2d(ctx, &mXh64, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
+    STEIN_TRY(make_tensor_map_2d(ctx, &mXl64, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
+    STEIN_TRY(make_tensor_map_2d(ctx, &mYh, YTh, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
+    STEIN_TRY(make_tensor_map_2d(ctx, &mYl, YTl, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
+
+    Flash2Params p{};
+    p.nJ = (int)nJ;
+    p.nI2 = (int)nI2;
+    p.row_pair0 = 0;
+    p.c1 = l2e / h2;
+    p.nrm = nrm;
+    p.Opart = Opart;
+    p.o_slot_stride = rows2 * DP;
+    p.ksum_part = ksum;
+    p.k_slot_stride = rows2;
+    p.row_begin = row_begin;
+    const size_t smem = flash_smem_bytes(DP);
+    static bool attr_set = false;
+    if (!attr_set) {
+        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)smem));
+        attr_set = true;
+    }
+    {
+        RegionTimer timer(ctx, STEIN_REGION_PHI);
+        flash_phi2_kernel<<<2 * G2, FL_THREADS, smem, ctx->stream>>>(mXh, mXl, mXh64, mXl64, mYh, mYl, p);
+        STEIN_CHECK_LAUNCH(ctx);
+    }
+    const int64_t rows_valid = std::max<int64_t>(0, std::min<int64_t>(n_local, n_total - row_begin));
+    const int64_t total4 = rows * ld / 4;
+    const int blocks = (int)std::min<int64_t>((total4 + 255) / 256, FINALIZE_MAX_BLOCKS);
+    finalize_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(Opart, rows2 * DP, d_tile_nslots, ksum, rows2,
+                                                           X_all + row_begin * ld, rows_valid, rows, ld, 1.0f / h2,
+                                                           1.0f / (float)n_total, phi, partials);
     STEIN_CHECK_LAUNCH(ctx);
     reduce_partials2_kernel<<<1, 256, 0, ctx->stream>>>(partials, blocks, sumsq);
     STEIN_CHECK_LAUNCH(ctx);

@@ -249,6 +249,21 @@ def test_phi_flash_tcgen05_matches_oracle(ctx, n, d, scale):
     assert abs(sumsq - (phi ** 2).sum()) <= 1e-6 * (phi ** 2).sum()
 
 
+@pytest.mark.parametrize("n,d,scale", [(128, 256, 1.0), (130, 256, 1.0), (640, 256, 1.0), (3000, 256, 1.0),
+                                       (2500, 250, 0.01), (5000, 230, 1.0), (19000, 256, 1.0)])
+def test_phi_flash_cta_pair_matches_oracle(ctx, n, d, scale):
+    """cta_group::2 variant (CTA pairs, M = 256): same bar as the single-CTA kernel."""
+    from stein_b200 import _lib
+    X = _particles(n, d, 3 * n + d, scale)
+    S = _particles(n, d, 5 * n + d, 1.0) - X
+    phi, sumsq, bw = _phi_gpu(ctx, X, S, _lib.PHI_FLASH_TC2)
+    one, _, _ = _phi_gpu(ctx, X, S, _lib.PHI_FLASH_TC)
+    _assert_close(phi, one, 2e-5)
+    if n <= 5000:
+        _assert_close(phi, orc.compute_phi(X, S.astype(np.float64)))
+    assert abs(sumsq - (phi ** 2).sum()) <= 1e-6 * (phi ** 2).sum()
+
+
 @pytest.mark.parametrize("n,d", [(128, 256), (300, 128), (1000, 256)])
 def test_flash_gram_tiles_are_accurate(ctx, n, d):
     """GEMM1 of the flash kernel (3-pass BF16 split on tcgen05) against float64 X X^T."""
