@@ -514,6 +514,10 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
             auto advance = [&]() {
                 if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
             };
+            // the leader's barriers as shared::cluster addresses
+            const uint32_t full0_addr = mapa_shared(smem_u32(&bars->full[0]), 0);
+            const uint32_t a_full_addr = mapa_shared(smem_u32(&bars->a_full), 0);
+            auto full_addr = [&]() -> uint32_t { return full0_addr + 8u * (uint32_t)stage; };
             Seg2Iter it(p);
             int t, j0, j1, slot, seg = 0;
             while (it.next(t, j0, j1, slot)) {
@@ -521,15 +525,15 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                 if (leader) mbar_expect_tx(&bars->a_full, 2u * 2u * KB * FL_UNIT_BYTES);
                 const int arow = (int)p.row_begin + (t * 2 + (int)rank) * 128;
                 for (int kb = 0; kb < KB; ++kb) {
-                    tma_load_2d_pair(sA + (size_t)kb * FL_UNIT_BYTES, &mapXh, &bars->a_full, kb * 64, arow);
-                    tma_load_2d_pair(sA + (size_t)(KB + kb) * FL_UNIT_BYTES, &mapXl, &bars->a_full, kb * 64, arow);
+                    tma_load_2d_pair(sA + (size_t)kb * FL_UNIT_BYTES, &mapXh, a_full_addr, kb * 64, arow);
+                    tma_load_2d_pair(sA + (size_t)(KB + kb) * FL_UNIT_BYTES, &mapXl, a_full_addr, kb * 64, arow);
                 }
                 auto emit_g1 = [&](int j) {       // slot = [64 rows of X_J hi | 64 rows of X_J lo]
                     for (int kb = 0; kb < KB; ++kb) {
                         acquire(2u * FL_UNIT_BYTES);
                         uint8_t *dst = sRing + (size_t)stage * FL_UNIT_BYTES;
-                        tma_load_2d_pair(dst, &mapXh64, &bars->full[stage], kb * 64, j * 128 + (int)rank * 64);
-                        tma_load_2d_pair(dst + FL_UNIT_BYTES / 2, &mapXl64, &bars->full[stage], kb * 64,
+                        tma_load_2d_pair(dst, &mapXh64, full_addr(), kb * 64, j * 128 + (int)rank * 64);
+                        tma_load_2d_pair(dst + FL_UNIT_BYTES / 2, &mapXl64, full_addr(), kb * 64,
                                          j * 128 + (int)rank * 64);
                         advance();
                     }
@@ -537,11 +541,11 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                 auto emit_g2 = [&](int j) {       // slot = 128 of the 256 rows of Y^T (hi, then lo)
                     for (int kb2 = 0; kb2 < 2; ++kb2) {
                         acquire(2u * FL_UNIT_BYTES);
-                        tma_load_2d_pair(sRing + (size_t)stage * FL_UNIT_BYTES, &mapYh, &bars->full[stage],
+                        tma_load_2d_pair(sRing + (size_t)stage * FL_UNIT_BYTES, &mapYh, full_addr(),
                                          j * 128 + kb2 * 64, (int)rank * 128);
                         advance();
                         acquire(2u * FL_UNIT_BYTES);
-                        tma_load_2d_pair(sRing + (size_t)stage * FL_UNIT_BYTES, &mapYl, &bars->full[stage],
+                        tma_load_2d_pair(sRing + (size_t)stage * FL_UNIT_BYTES, &mapYl, full_addr(),
                                          j * 128 + kb2 * 64, (int)rank * 128);
                         advance();
                     }

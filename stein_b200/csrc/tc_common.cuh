@@ -180,16 +180,15 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// Both CTAs of the pair run this; the bytes are accounted on the LEADER's barrier (the
-// shared::cluster address of a CTA pair differs in bit 24 only: clear it -> CTA 0).
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
-__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *leader_bar,
+// Both CTAs of the pair run this; the bytes are accounted on the LEADER's barrier, given as a
+// shared::cluster address (mapa_shared(local_address, 0)).
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint32_t leader_bar_addr,
                                                  int32_t c_inner, int32_t c_outer) {
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
         " [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(leader_bar) & kPeerBitMask),
-          "r"(c_inner), "r"(c_outer)
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar_addr), "r"(c_inner),
+          "r"(c_outer)
         : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t *smem_slot, uint32_t ncols) {
