@@ -508,7 +508,7 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             auto acquire = [&](uint32_t bytes_both) {
-                mbar_wait(&bars->empty[stage], phase ^ 1);         // local: multicast commit of the leader
+                mbar_wait(&bars->empty[stage], phase ^ 1, 2);      // local: multicast commit of the leader
                 if (leader) mbar_expect_tx(&bars->full[stage], bytes_both);
             };
             auto advance = [&]() {
@@ -521,7 +521,7 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
             Seg2Iter it(p);
             int t, j0, j1, slot, seg = 0;
             while (it.next(t, j0, j1, slot)) {
-                if (seg > 0) mbar_wait(&bars->a_empty, (uint32_t)((seg - 1) & 1));
+                if (seg > 0) mbar_wait(&bars->a_empty, (uint32_t)((seg - 1) & 1), 1);
                 if (leader) mbar_expect_tx(&bars->a_full, 2u * 2u * KB * FL_UNIT_BYTES);
                 const int arow = (int)p.row_begin + (t * 2 + (int)rank) * 128;
                 for (int kb = 0; kb < KB; ++kb) {
@@ -567,7 +567,7 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
             uint32_t phase = 0;
             long long jj = 0, oc = 0;
             auto next_unit = [&]() -> uint32_t {
-                mbar_wait(&bars->full[stage], phase);
+                mbar_wait(&bars->full[stage], phase, 4);
                 tcgen05_fence_after();
                 return smem_u32(sRing + (size_t)stage * FL_UNIT_BYTES);
             };
@@ -616,17 +616,17 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
             Seg2Iter it(p);
             int t, j0, j1, slot, seg = 0;
             while (it.next(t, j0, j1, slot)) {
-                mbar_wait(&bars->a_full, (uint32_t)(seg & 1));
+                mbar_wait(&bars->a_full, (uint32_t)(seg & 1), 3);
                 tcgen05_fence_after();
                 g1(jj);
                 for (int j = j0; j < j1; ++j, ++jj) {
                     if (j + 1 < j1) g1(jj + 1);
-                    mbar_wait(&bars->p_full[jj & 1], (uint32_t)((jj >> 1) & 1));
+                    mbar_wait(&bars->p_full[jj & 1], (uint32_t)((jj >> 1) & 1), 6);
                     tcgen05_fence_after();
                     const int ti = j - j0;
                     const bool first_of_chunk = (ti % FL_OCHUNK) == 0;
                     if (first_of_chunk && oc > 0) {
-                        mbar_wait(&bars->o_empty, (uint32_t)((oc - 1) & 1));
+                        mbar_wait(&bars->o_empty, (uint32_t)((oc - 1) & 1), 7);
                         tcgen05_fence_after();
                     }
                     g2(jj, first_of_chunk);
@@ -668,7 +668,7 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                 const int b = (int)(jj & 1);
                 if (tid256 < 128) sB[b * 128 + tid256] = p.nrm[(size_t)j * 128 + tid256];
                 named_bar_sync(1, FL_EPI_THREADS);
-                mbar_wait(&bars->s_full[b], (uint32_t)((jj >> 1) & 1));
+                mbar_wait(&bars->s_full[b], (uint32_t)((jj >> 1) & 1), 8);
                 tcgen05_fence_after();
                 const uint32_t s_addr = tmem + (b ? TMEM_S1 : TMEM_S0) + lane_addr;
 #pragma unroll 1
@@ -698,7 +698,7 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
 
                 const int ti = j - j0;
                 if (((ti + 1) % FL_OCHUNK) == 0 || j == j1 - 1) {
-                    mbar_wait(&bars->o_full, (uint32_t)(oc & 1));
+                    mbar_wait(&bars->o_full, (uint32_t)(oc & 1), 9);
                     tcgen05_fence_after();
 #pragma unroll
                     for (int ch = 0; ch < och; ++ch) {
@@ -1108,4 +1108,10 @@ extern "C" int stein_debug_flash_gram(stein_ctx *ctx, const float *X_dev, const 
                                        ws_bytes, phi_dev, sumsq_dev);
     stein::g_debug_dumpS = nullptr;
     return rc;
+}
+
+// Test/debug hook: install a host-mapped buffer (>= 1 + 16 * grid words) that receives the
+// wait site of every warp that timed out in a tcgen05 kernel of this file.
+extern "C" int stein_debug_set_hang_report(unsigned int *mapped_dev_ptr) {
+    return cudaMemcpyToSymbol(stein::tc::g_hang_report, &mapped_dev_ptr, sizeof(mapped_dev_ptr)) == cudaSuccess ? 0 : -2;
 }

@@ -43,13 +43,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must abort the kernel (trap -> launch failure),
-// never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+// Bounded wait: a protocol bug must abort the kernel (trap -> launch failure), never hang
+// the GPU.  When a host-mapped report buffer is installed (tests / debugging), the site of
+// the wait that timed out is recorded per (CTA, warp) before the trap.
+static __device__ unsigned int *g_hang_report = nullptr;
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t site = 0) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s
+        if (clock64() - t0 > 4000000000ll) {   // ~2 s
+            if (g_hang_report) {
+                g_hang_report[1 + blockIdx.x * 16 + (threadIdx.x >> 5)] = 0x80000000u | (site << 8) | parity;
+                __threadfence_system();
+            }
+            __trap();
+        }
     }
 }
 
