@@ -641,7 +641,7 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
         }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
         // ============ exponential / epilogue warpgroups (both CTAs, own 128 rows) ============
         const int q = warp & 3;
         const int wg = (warp - 4) >> 2;

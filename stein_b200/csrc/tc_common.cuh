@@ -51,13 +51,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) {   // ~2 s
-            if (g_hang_report) {
-                g_hang_report[1 + blockIdx.x * 16 + (threadIdx.x >> 5)] = 0x80000000u | (site << 8) | parity;
-                __threadfence_system();
-            }
-            __trap();
+        const long long dt = clock64() - t0;
+        if (dt > 3000000000ll && g_hang_report) {   // ~1.5 s: report, keep waiting so that others report too
+            g_hang_report[1 + blockIdx.x * 16 + (threadIdx.x >> 5)] = 0x80000000u | (site << 8) | parity;
+            __threadfence_system();
         }
+        if (dt > 4000000000ll) __trap();            // ~2 s
     }
 }
 
