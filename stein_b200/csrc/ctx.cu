@@ -145,6 +145,7 @@ int64_t stein_ctx_launch_count(const stein_ctx *ctx) { return ctx ? ctx->launche
 
 static int pick_phi_impl(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
     if (ctx->phi_impl != STEIN_PHI_AUTO) return ctx->phi_impl;
+    if (flash_tc2_supported(ctx, n_local, n_total, d)) return STEIN_PHI_FLASH_TC2;   // d padded to 256: CTA pairs
     return flash_tc_supported(ctx, n_local, n_total, d) ? STEIN_PHI_FLASH_TC : STEIN_PHI_DENSE_SIMT;
 }
 
