@@ -20,6 +20,8 @@
 #include <cuda_bf16.h>
 #include <math.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "tc_common.cuh"
@@ -50,6 +52,8 @@ struct SweepParams {
     const float *r;
     const uint32_t *Xh, *Xl;      // BF16 split of X viewed as 32-bit words (DP / 2 per row)
     float wlo, whi, c_half;
+    const float *rmax;            // device: max_i r_i (bounds the column part of the error term)
+    int debug_skip;               // experiments only: skip the classification (results invalid)
     unsigned long long *counters; // [0] certainly-below (weighted), [1] listed (weighted), [2] list length
     int *overflow;
     PairEntry *list;
@@ -76,6 +80,14 @@ __device__ __forceinline__ uint32_t select32(const uint32_t (&v)[32], int c) {
     return (c & 16) ? e[1] : e[0];
 }
 
+// successor of tile (I, J) in the row-major order of the upper triangle
+__device__ __forceinline__ void next_tile(int &I, int &J, int T) {
+    if (++J == T) {
+        ++I;
+        J = I;
+    }
+}
+
 // The row tile X_I (A operand) lives in TENSOR MEMORY (columns 256..511: BF16 hi and lo,
 // two elements per 32-bit column), written by the classification warps when I changes.
 // That leaves all of shared memory to a 12-stage ring of column-tile boxes, deep enough to
@@ -96,8 +108,9 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
     unsigned int *sN = reinterpret_cast<unsigned int *>(tail + 264);
     unsigned long long *sBase = reinterpret_cast<unsigned long long *>(tail + 272);
     PairEntry *sBuf = reinterpret_cast<PairEntry *>(tail + 320);     // SW_STAGE_CAP entries
+    float *sCol = reinterpret_cast<float *>(tail + 320 + SW_STAGE_CAP * sizeof(PairEntry));   // [2][128]
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
     const long long NT = p.t_end - p.t_begin;
     const long long my0 = p.t_begin + NT * blockIdx.x / gridDim.x;
     const long long my1 = p.t_begin + NT * (blockIdx.x + 1) / gridDim.x;
@@ -131,31 +144,38 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
             // ===================== TMA producer: column tiles only =====================
             int stage = 0;
             uint32_t phase = 0;
-            for (long long t = my0; t < my1; ++t) {
-                int I, J;
-                tri_tile(t, p.T, I, J);
+            int I = 0, J = 0;
+            if (my0 < my1) tri_tile(my0, p.T, I, J);
+            for (long long t = my0; t < my1; ++t, next_tile(I, J, p.T)) {
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     for (int part = 0; part < 2; ++part) {
                         mbar_wait(&bars->empty[stage], phase ^ 1);
+                        if (p.debug_skip == 2) {
+                            mbar_arrive(&bars->full[stage]);
+                        } else {
                         mbar_expect_tx(&bars->full[stage], SW_UNIT_BYTES);
                         tma_load_2d(sRing + (size_t)stage * SW_UNIT_BYTES, part == 0 ? &mapXh : &mapXl,
                                     &bars->full[stage], kb * 64, J * 128);
+                        }
                         if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
-        } else if (warp == 1 && lane == 0) {
+        } else if (warp == 1) {
             // ===================== MMA issuer =====================
+            // The whole warp runs the loop (uniform control flow, descriptors in uniform
+            // registers); one elected lane issues the tcgen05 instructions.
             const uint32_t idesc = make_idesc(FMT_BF16, 128, 128);
             int stage = 0;
             uint32_t phase = 0;
             int prevI = -1, aseg = 0;
             long long jj = 0;
-            for (long long t = my0; t < my1; ++t, ++jj) {
-                int I, J;
-                tri_tile(t, p.T, I, J);
+            int I = 0, J = 0;
+            if (my0 < my1) tri_tile(my0, p.T, I, J);
+            for (long long t = my0; t < my1; ++t, ++jj, next_tile(I, J, p.T)) {
                 if (I != prevI) {
-                    if (prevI != -1) tcgen05_commit(&bars->a_empty);   // every MMA on the old A tile is issued
+                    if (prevI != -1 && elect_one_sync()) tcgen05_commit(&bars->a_empty);   // every MMA on the old A tile is issued
+                    __syncwarp();
                     mbar_wait(&bars->a_full, (uint32_t)(aseg & 1));
                     tcgen05_fence_after();
                     ++aseg;
@@ -172,39 +192,64 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                     mbar_wait(&bars->full[stage], phase);
                     tcgen05_fence_after();
                     uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sRing + (size_t)stage * SW_UNIT_BYTES));
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4)
-                        umma_f16_ts(d_tmem, ah + 8 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0);   // hi.hi
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            umma_f16_ts(d_tmem, ah + 8 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0);   // hi.hi
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) umma_f16_ts(d_tmem, al + 8 * k4, bdesc + 2 * k4, idesc, 1u);   // lo.hi
-                    tcgen05_commit(&bars->empty[stage]);
+                        for (int k4 = 0; k4 < 4; ++k4) umma_f16_ts(d_tmem, al + 8 * k4, bdesc + 2 * k4, idesc, 1u);   // lo.hi
+                        tcgen05_commit(&bars->empty[stage]);
+                    }
+                    __syncwarp();
                     if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
                     mbar_wait(&bars->full[stage], phase);
                     tcgen05_fence_after();
                     bdesc = make_kmajor_sw128_desc(smem_u32(sRing + (size_t)stage * SW_UNIT_BYTES));
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) umma_f16_ts(d_tmem, ah + 8 * k4, bdesc + 2 * k4, idesc, 1u);   // hi.lo
-                    tcgen05_commit(&bars->empty[stage]);
+                        for (int k4 = 0; k4 < 4; ++k4) umma_f16_ts(d_tmem, ah + 8 * k4, bdesc + 2 * k4, idesc, 1u);   // hi.lo
+                        tcgen05_commit(&bars->empty[stage]);
+                        if (kb == p.kblocks - 1) tcgen05_commit(&bars->s_full[b]);
+                    }
+                    __syncwarp();
                     if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
                 }
-                tcgen05_commit(&bars->s_full[b]);
             }
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         // ===================== classification warpgroups =====================
+        // With D~ = r_i + r_j - 2 g and |D~ - D| <= c (r_i + r_j):
+        //   certainly above the window  <=>  g < (1-c)/2 (r_i + r_j) - whi/2
+        //   certainly below the window  <=>  g > (1+c)/2 (r_i + r_j) - wlo/2
+        // Written with t = g - B_j, B_j = (1-c)/2 r_j (one shared-memory value per column):
+        //   above  <=>  t < lo_i,   lo_i = (1-c)/2 r_i - whi/2
+        //   below  <=>  t > hi_i,   hi_i = (1+c)/2 r_i + c rmax - wlo/2   (rmax >= r_j: conservative)
+        // and everything else is listed.  In the loop: d = t - mid_i; below <=> d > half_i, listed
+        // <=> |d| <= half_i.  lo_i / hi_i are moved outwards by `slack` (>> the fp32 rounding of
+        // these few operations); that only enlarges the listed set, whose members are resolved
+        // from their own D~ later, so the three classes stay an exact partition of the pairs.
         const int q = warp & 3;
         const int wg = (warp - 4) >> 2;
         const int row = q * 32 + lane;
         const int tid256 = (warp - 4) * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const int wpr = p.kblocks * 32;             // 32-bit words per row of Xh / Xl
+        const float cm = 0.5f * (1.0f - p.c_half), cp = 0.5f * (1.0f + p.c_half);
+        const float rmax = __ldg(p.rmax);
         unsigned int below = 0u, listed = 0u;
         int prevI = -1, aseg = 0;
         long long jj = 0;
+        int I = 0, J = 0;
+        if (my0 < my1) {
+            tri_tile(my0, p.T, I, J);
+            if (tid256 < 128) {
+                const long long j = (long long)J * 128 + tid256;
+                sCol[tid256] = j < p.n ? cm * p.r[j] : INFINITY;
+            }
+            named_bar_sync(1, SW_EPI_THREADS);
+        }
         for (long long t = my0; t < my1; ++t, ++jj) {
-            int I, J;
-            tri_tile(t, p.T, I, J);
             const long long i = (long long)I * 128 + row;
             if (I != prevI) {
                 // new row tile: (re)write the A operand in tensor memory.  Warpgroup 0 writes
@@ -235,34 +280,56 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
             const float r_i = p.r[i];
             const float *rj = p.r + (size_t)J * 128;
             const bool row_ok = i < p.n;
+            const float slack = (r_i + rmax) * 9.5367431640625e-07f;   // 2^-20
+            const float lo_i = cm * r_i - 0.5f * p.whi - slack;
+            const float hi_i = cp * r_i + p.c_half * rmax - 0.5f * p.wlo + slack;
+            // rows beyond n: nothing is below (d = -inf) and nothing is listed (|d| = inf > 0)
+            const float mid_i = row_ok ? 0.5f * (lo_i + hi_i) : INFINITY;
+            const float half_i = row_ok ? 0.5f * (hi_i - lo_i) + slack : 0.0f;
+            const float *colterm = sCol + b * 128;
             mbar_wait(&bars->s_full[b], (uint32_t)((jj >> 1) & 1));
             tcgen05_fence_after();
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
                 const int ch = wg * 2 + cc;
                 const long long jbase = (long long)J * 128 + ch * 32;
-                const float rj_lane = __ldg(rj + ch * 32 + lane);      // column norms, one per lane
                 const uint32_t s_addr = tmem + b * 128 + lane_addr + ch * 32;
                 uint32_t v[32];
                 tmem_ld32(s_addr, v);
                 tmem_wait_ld();
-                // classify: bit c of bmask = certainly below the window, of hmask = may be inside
-                uint32_t bmask = 0u, hmask = 0u;
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float tsum = r_i + __shfl_sync(0xffffffffu, rj_lane, c);
-                    const float dt = fmaf(-2.0f, __uint_as_float(v[c]), tsum);
-                    const bool isb = fmaf(p.c_half, tsum, dt) < p.wlo;
-                    const bool ish = !isb && fmaf(-p.c_half, tsum, dt) <= p.whi;
-                    bmask |= (isb ? 1u : 0u) << c;
-                    hmask |= (ish ? 1u : 0u) << c;
+                if (p.debug_skip) {
+                    if (v[0] == 0x7fc12345u) ++below;
+                    continue;
                 }
-                // ragged edges: rows / columns beyond n do not exist
-                const long long ncol = p.n - jbase;
-                const uint32_t cmask = !row_ok || ncol <= 0 ? 0u : (ncol >= 32 ? 0xffffffffu : ((1u << ncol) - 1u));
-                bmask &= cmask;
-                hmask &= cmask;
-                below += w * (unsigned)__popc(bmask);
+                // common case first: count the pairs below and find the distance of the closest
+                // value to the listing interval [lo_i, hi_i] = mid_i -+ half_i; the bit mask of
+                // listed columns is only built when some value falls inside (every ~5th chunk)
+                unsigned int nb0 = 0u, nb1 = 0u;
+                float near0 = INFINITY, near1 = INFINITY;
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 bj = *reinterpret_cast<const float4 *>(colterm + ch * 32 + 4 * c4);
+                    const float d0 = (__uint_as_float(v[4 * c4]) - bj.x) - mid_i;
+                    const float d1 = (__uint_as_float(v[4 * c4 + 1]) - bj.y) - mid_i;
+                    const float d2 = (__uint_as_float(v[4 * c4 + 2]) - bj.z) - mid_i;
+                    const float d3 = (__uint_as_float(v[4 * c4 + 3]) - bj.w) - mid_i;
+                    nb0 += d0 > half_i ? 1u : 0u;
+                    nb1 += d1 > half_i ? 1u : 0u;
+                    nb0 += d2 > half_i ? 1u : 0u;
+                    nb1 += d3 > half_i ? 1u : 0u;
+                    near0 = fminf(near0, fminf(fabsf(d0), fabsf(d2)));
+                    near1 = fminf(near1, fminf(fabsf(d1), fabsf(d3)));
+                }
+                const unsigned int nb = nb0 + nb1;
+                uint32_t hmask = 0u;
+                if (fminf(near0, near1) <= half_i) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float dd = (__uint_as_float(v[c]) - colterm[ch * 32 + c]) - mid_i;
+                        hmask |= (fabsf(dd) <= half_i ? 1u : 0u) << c;
+                    }
+                }
+                below += w * nb;
                 listed += w * (unsigned)__popc(hmask);
                 // rare path (~0.7 % of the pairs, ~0.2 hits per thread and chunk): each thread with
                 // hits reserves its slots with one shared-memory atomic, then walks its set bits; the
@@ -292,6 +359,12 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
             // S buffer b may be overwritten by the GEMM of tile jj + 2
             tcgen05_fence_before();
             mbar_arrive(&bars->s_empty[b]);
+            // column terms of the next tile (published by the barrier below)
+            next_tile(I, J, p.T);
+            if (t + 1 < my1 && tid256 < 128) {
+                const long long j = (long long)J * 128 + tid256;
+                sCol[(b ^ 1) * 128 + tid256] = j < p.n ? cm * p.r[j] : INFINITY;
+            }
             // flush the staged entries when the buffer is half full (or at the last tile):
             // one global reservation per flush, not per tile
             named_bar_sync(1, SW_EPI_THREADS);
@@ -407,18 +480,35 @@ band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, con
                    unsigned long long *__restrict__ counters /* [3] below, [4] band weighted, [5] band len */,
                    uint2 *__restrict__ band_ij, unsigned long long band_cap, int *__restrict__ overflow) {
     unsigned int below = 0u, bw = 0u;
-    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < m;
+    const int lane = threadIdx.x & 31;
+    // whole warps iterate together (the bound is rounded up to a multiple of 32) so that the
+    // band slots of a warp are reserved with ONE atomic
+    const unsigned long long m32 = (m + 31ull) & ~31ull;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < m32;
          e += (unsigned long long)gridDim.x * blockDim.x) {
-        const PairEntry pe = list[e];
-        const uint32_t i = pe.i, j = pe.jw & 0x7fffffffu, w = (pe.jw >> 31) ? 2u : 1u;
-        const float eps = c_half * (r[i] + r[j]);
-        if (pe.dt + eps < tlo) {
-            below += w;
-        } else if (pe.dt - eps <= thi) {
-            bw += w;
-            const unsigned long long g = atomicAdd(&counters[5], 1ull);
-            if (g < band_cap) band_ij[g] = make_uint2(pe.i, pe.jw);
-            else *overflow = 1;
+        bool in_band = false;
+        PairEntry pe{};
+        if (e < m) {
+            pe = list[e];
+            const uint32_t i = pe.i, j = pe.jw & 0x7fffffffu, w = (pe.jw >> 31) ? 2u : 1u;
+            const float eps = c_half * (r[i] + r[j]);
+            if (pe.dt + eps < tlo) {
+                below += w;
+            } else if (pe.dt - eps <= thi) {
+                bw += w;
+                in_band = true;
+            }
+        }
+        const unsigned int vote = __ballot_sync(0xffffffffu, in_band);
+        if (vote) {
+            unsigned long long base = 0ull;
+            if (lane == 0) base = atomicAdd(&counters[5], (unsigned long long)__popc(vote));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (in_band) {
+                const unsigned long long g = base + (unsigned)__popc(vote & ((1u << lane) - 1u));
+                if (g < band_cap) band_ij[g] = make_uint2(pe.i, pe.jw);
+                else *overflow = 1;
+            }
         }
     }
 #pragma unroll
@@ -627,11 +717,13 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     p.wlo = key_to_float(win_lo_key);
     p.whi = key_to_float(win_hi_key);
     p.c_half = c_half;
+    p.rmax = d_rmax;
+    p.debug_skip = getenv("STEIN_DEBUG_SWEEP_SKIP") ? atoi(getenv("STEIN_DEBUG_SWEEP_SKIP")) : 0;
     p.counters = A.counters;
     p.overflow = d_overflow;
     p.list = A.list;
     p.list_cap = A.list_cap;
-    const size_t smem = 1024 + (size_t)SW_STAGES * SW_UNIT_BYTES + 320 + (size_t)SW_STAGE_CAP * sizeof(PairEntry) + 64;
+    const size_t smem = 1024 + (size_t)SW_STAGES * SW_UNIT_BYTES + 320 + (size_t)SW_STAGE_CAP * sizeof(PairEntry) + 1024 + 64;
     static bool attr_set = false;
     if (!attr_set) {
         STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(sweep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -641,8 +733,23 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     if (t1 > t0) {
         const int grid = (int)std::min<int64_t>(ctx->num_sms, t1 - t0);
         RegionTimer timer(ctx, STEIN_REGION_SWEEP);
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (p.debug_skip) {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, ctx->stream);
+        }
         sweep_tc_kernel<<<grid, SW_THREADS, smem, ctx->stream>>>(mapXh, mapXl, p);
         STEIN_CHECK_LAUNCH(ctx);
+        if (p.debug_skip) {
+            cudaEventRecord(e1, ctx->stream);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            fprintf(stderr, "[debug] sweep_tc_kernel without classification: %.3f ms\n", ms);
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
     }
     if (sweeps) *sweeps += 1;
     // counters[0] below, [1] listed weight are global quantities; [2] list length stays local

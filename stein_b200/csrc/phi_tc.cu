@@ -131,7 +131,7 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
     float *sK = reinterpret_cast<float *>(tail + 256 + 1024);     // [128] row-sum exchange between warpgroups
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 256 + 1024 + 512);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < FL_STAGES; ++s) {
@@ -206,7 +206,8 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // whole warp in uniform control flow, one elected lane issues (see elect_one_sync)
+        {
             const uint32_t idesc = make_idesc(FMT_BF16, 128, 128);
             int stage = 0;
             uint32_t phase = 0;
@@ -217,8 +218,7 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
                 tcgen05_fence_after();
                 return make_kmajor_sw128_desc(smem_u32(sRing + (size_t)stage * FL_UNIT_BYTES));
             };
-            auto release_unit = [&]() {
-                tcgen05_commit(&bars->empty[stage]);
+            auto advance = [&]() {
                 if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
             };
             auto g1 = [&](long long jcount) {
@@ -228,38 +228,55 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
                     const uint64_t al =
                         make_kmajor_sw128_desc(smem_u32(sA + (size_t)(p.kblocks + kb) * FL_UNIT_BYTES));
                     uint64_t bdesc = next_unit();          // hi block of X_J: hi.hi + lo.hi
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4)
-                        umma_f16_ss(d_tmem, ah + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0);
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            umma_f16_ss(d_tmem, ah + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0);
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) umma_f16_ss(d_tmem, al + 2 * k4, bdesc + 2 * k4, idesc, 1u);
-                    release_unit();
+                        for (int k4 = 0; k4 < 4; ++k4) umma_f16_ss(d_tmem, al + 2 * k4, bdesc + 2 * k4, idesc, 1u);
+                        tcgen05_commit(&bars->empty[stage]);
+                    }
+                    __syncwarp();
+                    advance();
                     bdesc = next_unit();                   // lo block of X_J: hi.lo
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) umma_f16_ss(d_tmem, ah + 2 * k4, bdesc + 2 * k4, idesc, 1u);
-                    release_unit();
+                        for (int k4 = 0; k4 < 4; ++k4) umma_f16_ss(d_tmem, ah + 2 * k4, bdesc + 2 * k4, idesc, 1u);
+                        tcgen05_commit(&bars->empty[stage]);
+                        if (kb == p.kblocks - 1) tcgen05_commit(&bars->s_full[jcount & 1]);
+                    }
+                    __syncwarp();
+                    advance();
                 }
-                tcgen05_commit(&bars->s_full[jcount & 1]);
             };
-            auto g2 = [&](long long jcount, bool first_of_chunk) {
+            auto g2 = [&](long long jcount, bool first_of_chunk, bool last_of_chunk) {
                 const uint32_t a_base = tmem + ((jcount & 1) ? TMEM_S1 : TMEM_S0);
                 for (int kb2 = 0; kb2 < 2; ++kb2) {
                     for (int h = 0; h < p.nhalf; ++h) {
                         const uint32_t d_tmem = tmem + h * 128;
                         uint64_t bdesc = next_unit();      // hi block of Y_J: Phi.Yhi + Plo.Yhi
+                        if (elect_one_sync()) {
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            const uint32_t ph = a_base + p_hi_col(kb2 * 4 + k4);
-                            umma_f16_ts(d_tmem, ph, bdesc + 2 * k4, idesc,
-                                        !(first_of_chunk && kb2 == 0 && k4 == 0));
-                            umma_f16_ts(d_tmem, ph + 16, bdesc + 2 * k4, idesc, 1u);
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                const uint32_t ph = a_base + p_hi_col(kb2 * 4 + k4);
+                                umma_f16_ts(d_tmem, ph, bdesc + 2 * k4, idesc,
+                                            !(first_of_chunk && kb2 == 0 && k4 == 0));
+                                umma_f16_ts(d_tmem, ph + 16, bdesc + 2 * k4, idesc, 1u);
+                            }
+                            tcgen05_commit(&bars->empty[stage]);
                         }
-                        release_unit();
+                        __syncwarp();
+                        advance();
                         bdesc = next_unit();               // lo block of Y_J: Phi.Ylo
+                        if (elect_one_sync()) {
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4)
-                            umma_f16_ts(d_tmem, a_base + p_hi_col(kb2 * 4 + k4), bdesc + 2 * k4, idesc, 1u);
-                        release_unit();
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                umma_f16_ts(d_tmem, a_base + p_hi_col(kb2 * 4 + k4), bdesc + 2 * k4, idesc, 1u);
+                            tcgen05_commit(&bars->empty[stage]);
+                            if (last_of_chunk && kb2 == 1 && h == p.nhalf - 1) tcgen05_commit(&bars->o_full);
+                        }
+                        __syncwarp();
+                        advance();
                     }
                 }
             };
@@ -280,13 +297,12 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
                         mbar_wait(&bars->o_empty, (uint32_t)((oc - 1) & 1));
                         tcgen05_fence_after();
                     }
-                    g2(jj, first_of_chunk);
-                    if (((ti + 1) % FL_OCHUNK) == 0 || j == j1 - 1) {
-                        tcgen05_commit(&bars->o_full);
-                        ++oc;
-                    }
+                    const bool last_of_chunk = ((ti + 1) % FL_OCHUNK) == 0 || j == j1 - 1;
+                    g2(jj, first_of_chunk, last_of_chunk);
+                    if (last_of_chunk) ++oc;
                 }
-                tcgen05_commit(&bars->a_empty);
+                if (elect_one_sync()) tcgen05_commit(&bars->a_empty);
+                __syncwarp();
                 ++seg;
             }
         }
@@ -467,7 +483,7 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
     float *sK = reinterpret_cast<float *>(tail + 256 + 1024);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 256 + 1024 + 512);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
 
@@ -560,7 +576,9 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
         }
         } else if (warp == 1 && leader) {
         // ===================== MMA issuer (leader CTA only) =====================
-        if (lane == 0) {
+        // The whole warp runs the loop in uniform control flow (descriptors stay in uniform
+        // registers, every tcgen05.mma is one UTCHMMA); one elected lane issues.
+        {
             const uint32_t idesc1 = make_idesc(FMT_BF16, 256, 128);   // GEMM1: M = 256 (pair), N = 128
             const uint32_t idesc2 = make_idesc(FMT_BF16, 256, 256);   // GEMM2: N = 256
             int stage = 0;
@@ -571,8 +589,7 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                 tcgen05_fence_after();
                 return smem_u32(sRing + (size_t)stage * FL_UNIT_BYTES);
             };
-            auto release_unit = [&]() {
-                tcgen05_commit_pair(&bars->empty[stage]);
+            auto advance = [&]() {
                 if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
             };
             auto g1 = [&](long long jcount) {
@@ -584,33 +601,46 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                     const uint32_t slot_addr = next_unit();
                     const uint64_t bh = make_kmajor_sw128_desc(slot_addr);
                     const uint64_t bl = make_kmajor_sw128_desc(slot_addr + FL_UNIT_BYTES / 2);
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ss(d_tmem, ah + 2 * k4, bh + 2 * k4, idesc1, (kb | k4) != 0);
+                        for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ss(d_tmem, ah + 2 * k4, bh + 2 * k4, idesc1, (kb | k4) != 0);
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ss(d_tmem, al + 2 * k4, bh + 2 * k4, idesc1, 1u);
+                        for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ss(d_tmem, al + 2 * k4, bh + 2 * k4, idesc1, 1u);
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ss(d_tmem, ah + 2 * k4, bl + 2 * k4, idesc1, 1u);
-                    release_unit();
+                        for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ss(d_tmem, ah + 2 * k4, bl + 2 * k4, idesc1, 1u);
+                        tcgen05_commit_pair(&bars->empty[stage]);
+                        if (kb == KB - 1) tcgen05_commit_pair(&bars->s_full[jcount & 1]);
+                    }
+                    __syncwarp();
+                    advance();
                 }
-                tcgen05_commit_pair(&bars->s_full[jcount & 1]);
             };
-            auto g2 = [&](long long jcount, bool first_of_chunk) {
+            auto g2 = [&](long long jcount, bool first_of_chunk, bool last_of_chunk) {
                 const uint32_t a_base = tmem + ((jcount & 1) ? TMEM_S1 : TMEM_S0);
 #pragma unroll 1
                 for (int kb2 = 0; kb2 < 2; ++kb2) {
                     uint64_t bdesc = make_kmajor_sw128_desc(next_unit());      // Y hi: Phi.Yhi + Plo.Yhi
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        const uint32_t ph = a_base + p_hi_col(kb2 * 4 + k4);
-                        umma2_f16_ts(tmem, ph, bdesc + 2 * k4, idesc2, !(first_of_chunk && kb2 == 0 && k4 == 0));
-                        umma2_f16_ts(tmem, ph + 16, bdesc + 2 * k4, idesc2, 1u);
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const uint32_t ph = a_base + p_hi_col(kb2 * 4 + k4);
+                            umma2_f16_ts(tmem, ph, bdesc + 2 * k4, idesc2, !(first_of_chunk && kb2 == 0 && k4 == 0));
+                            umma2_f16_ts(tmem, ph + 16, bdesc + 2 * k4, idesc2, 1u);
+                        }
+                        tcgen05_commit_pair(&bars->empty[stage]);
                     }
-                    release_unit();
+                    __syncwarp();
+                    advance();
                     bdesc = make_kmajor_sw128_desc(next_unit());               // Y lo: Phi.Ylo
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4)
-                        umma2_f16_ts(tmem, a_base + p_hi_col(kb2 * 4 + k4), bdesc + 2 * k4, idesc2, 1u);
-                    release_unit();
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            umma2_f16_ts(tmem, a_base + p_hi_col(kb2 * 4 + k4), bdesc + 2 * k4, idesc2, 1u);
+                        tcgen05_commit_pair(&bars->empty[stage]);
+                        if (kb2 == 1 && last_of_chunk) tcgen05_commit_pair(&bars->o_full);
+                    }
+                    __syncwarp();
+                    advance();
                 }
             };
             Seg2Iter it(p);
@@ -629,13 +659,12 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                         mbar_wait(&bars->o_empty, (uint32_t)((oc - 1) & 1), 7);
                         tcgen05_fence_after();
                     }
-                    g2(jj, first_of_chunk);
-                    if (((ti + 1) % FL_OCHUNK) == 0 || j == j1 - 1) {
-                        tcgen05_commit_pair(&bars->o_full);
-                        ++oc;
-                    }
+                    const bool last_of_chunk = ((ti + 1) % FL_OCHUNK) == 0 || j == j1 - 1;
+                    g2(jj, first_of_chunk, last_of_chunk);
+                    if (last_of_chunk) ++oc;
                 }
-                tcgen05_commit_pair(&bars->a_empty);
+                if (elect_one_sync()) tcgen05_commit_pair(&bars->a_empty);
+                __syncwarp();
                 ++seg;
             }
         }

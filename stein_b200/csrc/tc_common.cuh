@@ -164,6 +164,23 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t &v) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// One lane of a converged warp (the same lane every time).  The warp-uniform values that the
+// elected lane hands to tcgen05.mma / commit / TMA must be computed OUTSIDE the elected branch,
+// in warp-uniform control flow: they then live in uniform registers and each UTCHMMA is a single
+// instruction.  Under `if (lane == 0)` the compiler wraps every one of them in an
+// ELECT / R2UR.BROADCAST "waterfall" loop (~100 cycles of issue latency per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// warp index as a provably warp-uniform value
+__device__ __forceinline__ int warp_idx_sync() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -1,0 +1,13 @@
+#!/bin/bash
+# One GPU box visit: parity tests, bench (both arms), ncu launch list, ncu --set full of the top kernels.
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest_rc=$?"
+python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke_rc=$?"
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench_rc=$?"
+python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "ref_rc=$?"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1; echo "ncu_list_rc=$?"
+ncu --set full --clock-control none --import-source on \
+    -k regex:'flash_phi2_kernel|sweep_tc_kernel|band_exact_kernel|band_filter_kernel|pilot_kernel|clip_adam_kernel' -c 6 \
+    -f -o gpurun_out/prof_full python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu_full_rc=$?"
+tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -2; cat gpurun_out/bench.log
