@@ -140,8 +140,9 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        if (warp == 0 && lane == 0) {
+        if (warp == 0) {
             // ===================== TMA producer: column tiles only =====================
+            // whole warp in uniform control flow; one elected lane issues the copies
             int stage = 0;
             uint32_t phase = 0;
             int I = 0, J = 0;
@@ -150,13 +151,16 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     for (int part = 0; part < 2; ++part) {
                         mbar_wait(&bars->empty[stage], phase ^ 1);
-                        if (p.debug_skip == 2) {
-                            mbar_arrive(&bars->full[stage]);
-                        } else {
-                        mbar_expect_tx(&bars->full[stage], SW_UNIT_BYTES);
-                        tma_load_2d(sRing + (size_t)stage * SW_UNIT_BYTES, part == 0 ? &mapXh : &mapXl,
-                                    &bars->full[stage], kb * 64, J * 128);
+                        if (elect_one_sync()) {
+                            if (p.debug_skip == 2) {
+                                mbar_arrive(&bars->full[stage]);
+                            } else {
+                                mbar_expect_tx(&bars->full[stage], SW_UNIT_BYTES);
+                                tma_load_2d(sRing + (size_t)stage * SW_UNIT_BYTES, part == 0 ? &mapXh : &mapXl,
+                                            &bars->full[stage], kb * 64, J * 128);
+                            }
                         }
+                        __syncwarp();
                         if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }

@@ -163,13 +163,17 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // whole warp in uniform control flow; one elected lane issues the copies
+        {
             int stage = 0;
             uint32_t phase = 0;
             auto emit = [&](const CUtensorMap *map, int c_inner, int c_outer) {
                 mbar_wait(&bars->empty[stage], phase ^ 1);
-                mbar_expect_tx(&bars->full[stage], FL_UNIT_BYTES);
-                tma_load_2d(sRing + (size_t)stage * FL_UNIT_BYTES, map, &bars->full[stage], c_inner, c_outer);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(&bars->full[stage], FL_UNIT_BYTES);
+                    tma_load_2d(sRing + (size_t)stage * FL_UNIT_BYTES, map, &bars->full[stage], c_inner, c_outer);
+                }
+                __syncwarp();
                 if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
             };
             auto emit_g1 = [&](int j) {
@@ -189,13 +193,16 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
             int t, j0, j1, slot, seg = 0;
             while (it.next(t, j0, j1, slot)) {
                 if (seg > 0) mbar_wait(&bars->a_empty, (uint32_t)((seg - 1) & 1));
-                mbar_expect_tx(&bars->a_full, (uint32_t)(2 * p.kblocks) * FL_UNIT_BYTES);
-                for (int kb = 0; kb < p.kblocks; ++kb) {
-                    tma_load_2d(sA + (size_t)kb * FL_UNIT_BYTES, &mapXh, &bars->a_full, kb * 64,
-                                (p.row_tile0 + t) * 128);
-                    tma_load_2d(sA + (size_t)(p.kblocks + kb) * FL_UNIT_BYTES, &mapXl, &bars->a_full, kb * 64,
-                                (p.row_tile0 + t) * 128);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(&bars->a_full, (uint32_t)(2 * p.kblocks) * FL_UNIT_BYTES);
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        tma_load_2d(sA + (size_t)kb * FL_UNIT_BYTES, &mapXh, &bars->a_full, kb * 64,
+                                    (p.row_tile0 + t) * 128);
+                        tma_load_2d(sA + (size_t)(p.kblocks + kb) * FL_UNIT_BYTES, &mapXl, &bars->a_full, kb * 64,
+                                    (p.row_tile0 + t) * 128);
+                    }
                 }
+                __syncwarp();
                 emit_g1(j0);
                 for (int j = j0; j < j1; ++j) {
                     if (j + 1 < j1) emit_g1(j + 1);
@@ -520,12 +527,12 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
-        if (lane == 0) {
+        // whole warp in uniform control flow; one elected lane issues the copies
+        {
             int stage = 0;
             uint32_t phase = 0;
-            auto acquire = [&](uint32_t bytes_both) {
+            auto acquire = [&]() {
                 mbar_wait(&bars->empty[stage], phase ^ 1, 2);      // local: multicast commit of the leader
-                if (leader) mbar_expect_tx(&bars->full[stage], bytes_both);
             };
             auto advance = [&]() {
                 if (++stage == FL_STAGES) { stage = 0; phase ^= 1; }
@@ -533,36 +540,50 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
             // the leader's barriers as shared::cluster addresses
             const uint32_t full0_addr = mapa_shared(smem_u32(&bars->full[0]), 0);
             const uint32_t a_full_addr = mapa_shared(smem_u32(&bars->a_full), 0);
-            auto full_addr = [&]() -> uint32_t { return full0_addr + 8u * (uint32_t)stage; };
             Seg2Iter it(p);
             int t, j0, j1, slot, seg = 0;
             while (it.next(t, j0, j1, slot)) {
                 if (seg > 0) mbar_wait(&bars->a_empty, (uint32_t)((seg - 1) & 1), 1);
-                if (leader) mbar_expect_tx(&bars->a_full, 2u * 2u * KB * FL_UNIT_BYTES);
                 const int arow = (int)p.row_begin + (t * 2 + (int)rank) * 128;
-                for (int kb = 0; kb < KB; ++kb) {
-                    tma_load_2d_pair(sA + (size_t)kb * FL_UNIT_BYTES, &mapXh, a_full_addr, kb * 64, arow);
-                    tma_load_2d_pair(sA + (size_t)(KB + kb) * FL_UNIT_BYTES, &mapXl, a_full_addr, kb * 64, arow);
+                if (elect_one_sync()) {
+                    if (leader) mbar_expect_tx(&bars->a_full, 2u * 2u * KB * FL_UNIT_BYTES);
+                    for (int kb = 0; kb < KB; ++kb) {
+                        tma_load_2d_pair(sA + (size_t)kb * FL_UNIT_BYTES, &mapXh, a_full_addr, kb * 64, arow);
+                        tma_load_2d_pair(sA + (size_t)(KB + kb) * FL_UNIT_BYTES, &mapXl, a_full_addr, kb * 64, arow);
+                    }
                 }
+                __syncwarp();
                 auto emit_g1 = [&](int j) {       // slot = [64 rows of X_J hi | 64 rows of X_J lo]
                     for (int kb = 0; kb < KB; ++kb) {
-                        acquire(2u * FL_UNIT_BYTES);
-                        uint8_t *dst = sRing + (size_t)stage * FL_UNIT_BYTES;
-                        tma_load_2d_pair(dst, &mapXh64, full_addr(), kb * 64, j * 128 + (int)rank * 64);
-                        tma_load_2d_pair(dst + FL_UNIT_BYTES / 2, &mapXl64, full_addr(), kb * 64,
-                                         j * 128 + (int)rank * 64);
+                        acquire();
+                        if (elect_one_sync()) {
+                            if (leader) mbar_expect_tx(&bars->full[stage], 2u * FL_UNIT_BYTES);
+                            uint8_t *dst = sRing + (size_t)stage * FL_UNIT_BYTES;
+                            const uint32_t fa = full0_addr + 8u * (uint32_t)stage;
+                            tma_load_2d_pair(dst, &mapXh64, fa, kb * 64, j * 128 + (int)rank * 64);
+                            tma_load_2d_pair(dst + FL_UNIT_BYTES / 2, &mapXl64, fa, kb * 64, j * 128 + (int)rank * 64);
+                        }
+                        __syncwarp();
                         advance();
                     }
                 };
                 auto emit_g2 = [&](int j) {       // slot = 128 of the 256 rows of Y^T (hi, then lo)
                     for (int kb2 = 0; kb2 < 2; ++kb2) {
-                        acquire(2u * FL_UNIT_BYTES);
-                        tma_load_2d_pair(sRing + (size_t)stage * FL_UNIT_BYTES, &mapYh, full_addr(),
-                                         j * 128 + kb2 * 64, (int)rank * 128);
+                        acquire();
+                        if (elect_one_sync()) {
+                            if (leader) mbar_expect_tx(&bars->full[stage], 2u * FL_UNIT_BYTES);
+                            tma_load_2d_pair(sRing + (size_t)stage * FL_UNIT_BYTES, &mapYh,
+                                             full0_addr + 8u * (uint32_t)stage, j * 128 + kb2 * 64, (int)rank * 128);
+                        }
+                        __syncwarp();
                         advance();
-                        acquire(2u * FL_UNIT_BYTES);
-                        tma_load_2d_pair(sRing + (size_t)stage * FL_UNIT_BYTES, &mapYl, full_addr(),
-                                         j * 128 + kb2 * 64, (int)rank * 128);
+                        acquire();
+                        if (elect_one_sync()) {
+                            if (leader) mbar_expect_tx(&bars->full[stage], 2u * FL_UNIT_BYTES);
+                            tma_load_2d_pair(sRing + (size_t)stage * FL_UNIT_BYTES, &mapYl,
+                                             full0_addr + 8u * (uint32_t)stage, j * 128 + kb2 * 64, (int)rank * 128);
+                        }
+                        __syncwarp();
                         advance();
                     }
                 };
