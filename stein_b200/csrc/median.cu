@@ -8,7 +8,7 @@
 // computed (off-diagonal tiles weigh 2).  Each sweep recomputes the tiles with
 // the FFMA mainloop in contract arithmetic and histograms the order-preserving
 // u32 keys that fall into a window [key_lo, key_lo + nbins << shift); keys
-// below the window are only counted.  A cheap pilot (2^20 sampled pairs) puts
+// below the window are only counted.  A cheap pilot (2^20 sampled pairs, pair_chain.cuh) puts
 // the window around the median so that one sweep usually resolves individual
 // fp32 values (shift == 0); otherwise the window is narrowed and swept again
 // (radix select).  Counts are u64 (n*n = 2^32 at n = 65 536).
@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "gemm_simt.cuh"
+#include "pair_chain.cuh"
 
 namespace stein {
 
@@ -96,35 +97,6 @@ sqdist_hist_kernel(const float *__restrict__ X, const float *__restrict__ r, int
         const unsigned int v = hist[b];
         if (v) atomicAdd(&counts[1 + b], (unsigned long long)v);
     }
-}
-
-// ---- pilot: keys of sampled pairs -----------------------------------------------
-__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
-    x += 0x9E3779B97F4A7C15ull;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
-}
-
-__global__ void pilot_kernel(const float *__restrict__ X, const float *__restrict__ r, int64_t n,
-                             int64_t ld, int64_t m, uint64_t seed, uint32_t *__restrict__ keys) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= m) return;
-    const uint64_t h = splitmix64(seed + (uint64_t)s);
-    const int64_t i = (int64_t)((h >> 32) % (uint64_t)n);
-    const int64_t j = (int64_t)((h & 0xffffffffull) % (uint64_t)n);
-    const float4 *a = reinterpret_cast<const float4 *>(X + i * ld);
-    const float4 *b = reinterpret_cast<const float4 *>(X + j * ld);
-    float acc = 0.0f;
-    for (int64_t k4 = 0; k4 < ld / 4; ++k4) {
-        const float4 u = a[k4], v = b[k4];
-        acc = __fmaf_rn(u.x, v.x, acc);
-        acc = __fmaf_rn(u.y, v.y, acc);
-        acc = __fmaf_rn(u.z, v.z, acc);
-        acc = __fmaf_rn(u.w, v.w, acc);
-    }
-    const float tsum = r[i] + r[j];
-    keys[s] = float_to_key(tsum - 2.0f * acc);
 }
 
 // single-block radix select of two ranks among m keys
@@ -360,9 +332,8 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
         // sample ranks m/2 -+ 3.5 sqrt(m): the true median lies between them with
         // probability ~1 - 1e-11; a miss is caught below and falls back to the
         // full-range radix select.
-        pilot_kernel<<<(unsigned)((pilot_m + 255) / 256), 256, 0, ctx->stream>>>(
-            X_dev, r_dev, n, ld, pilot_m, 0x5eedull, ctx->d_pilot_keys);
-        STEIN_CHECK_LAUNCH(ctx);
+        STEIN_TRY(launch_pair_chain<1>(ctx, ctx->d_pilot_keys, (unsigned long long)pilot_m, X_dev, r_dev, n, ld,
+                                       0x5eedull));
         const uint64_t delta = (uint64_t)(3.5 * sqrt((double)pilot_m));
         uint32_t ka = 0, kb = 0;
         STEIN_TRY(pilot_window(ctx, ctx->d_pilot_keys, pilot_m, pilot_m / 2 - delta, pilot_m / 2 + delta, &ka, &kb));

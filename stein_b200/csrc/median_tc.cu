@@ -14,7 +14,7 @@
 //      the exact median lies within delta = max eps of it;
 //   3. entries certainly below t~ - delta are counted, entries that may lie within
 //      [t~ - delta, t~ + delta] (~0.07 %) get their distance recomputed in contract
-//      arithmetic (FFMA chain) and the exact rank is selected among those keys.
+//      arithmetic (FFMA chain, pair_chain.cuh) and the exact rank is selected among those keys.
 // Every step checks that the target rank is bracketed; if not (pilot window missed,
 // list overflow) the caller falls back to the all-FFMA route of median.cu.
 #include <cuda_bf16.h>
@@ -24,6 +24,7 @@
 
 #include <algorithm>
 
+#include "pair_chain.cuh"
 #include "tc_common.cuh"
 
 namespace stein {
@@ -526,38 +527,6 @@ band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, con
     }
 }
 
-// contract-arithmetic distance of every band pair: (i, jw) -> (key, weight), in place.
-// The fma chain is sequential in k, so the row loads are issued 8 float4 pairs ahead.
-__global__ void __launch_bounds__(128)
-band_exact_kernel(uint2 *__restrict__ band, unsigned long long m, const float *__restrict__ X,
-                  const float *__restrict__ r, int64_t ld) {
-    const unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= m) return;
-    const uint2 ij = band[e];
-    const uint32_t i = ij.x, j = ij.y & 0x7fffffffu, w = (ij.y >> 31) ? 2u : 1u;
-    const float4 *a = reinterpret_cast<const float4 *>(X + (size_t)i * ld);
-    const float4 *b = reinterpret_cast<const float4 *>(X + (size_t)j * ld);
-    float acc = 0.0f;
-    const int64_t n4 = ld / 4;        // ld % 32 == 0  ->  n4 % 8 == 0
-    for (int64_t k4 = 0; k4 < n4; k4 += 8) {
-        float4 u[8], v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            u[q] = __ldg(a + k4 + q);
-            v[q] = __ldg(b + k4 + q);
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            acc = __fmaf_rn(u[q].x, v[q].x, acc);
-            acc = __fmaf_rn(u[q].y, v[q].y, acc);
-            acc = __fmaf_rn(u[q].z, v[q].z, acc);
-            acc = __fmaf_rn(u[q].w, v[q].w, acc);
-        }
-    }
-    const float tsum = r[i] + r[j];
-    band[e] = make_uint2(float_to_key(tsum - 2.0f * acc), w);
-}
-
 // worst-case |D~ - D_contract| <= eps_coeff(d) * (r_i + r_j):
 //   BF16 2-term split: dropped lo.lo and the rounding of lo, <= 3 * 2^-18 |x_i||x_j|;
 //   tensor-core accumulation (truncating, 3 d/16 adds of magnitude <= |x_i||x_j|): 3d/16 * 2^-23;
@@ -820,10 +789,8 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     if (overflow2) return 1;
     const uint64_t c1 = below + below2;
     if (!(c1 <= ranks[0] && ranks[1] < c1 + band_w)) return 1;
-    if (band_len) {
-        band_exact_kernel<<<(unsigned)((band_len + 127) / 128), 128, 0, ctx->stream>>>(A.band, band_len, X, r, ld);
-        STEIN_CHECK_LAUNCH(ctx);
-    }
+    // contract-arithmetic distance of every band pair: (i, jw) -> (key, weight), in place
+    STEIN_TRY(launch_pair_chain<0>(ctx, A.band, band_len, X, r, n, ld, 0));
 
     // exact keys of the two target ranks among the band
     uint32_t k0 = 0, k1 = 0;
