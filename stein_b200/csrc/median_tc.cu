@@ -478,22 +478,45 @@ hist_pass_kernel(const void *__restrict__ src, unsigned long long m, uint32_t pr
 }
 
 // entries certainly below t~ - delta are counted; entries that may fall inside
-// [t~ - delta, t~ + delta] are compacted into the band (key slot filled by band_exact_kernel)
-__global__ void __launch_bounds__(256)
+// [t~ - delta, t~ + delta] are compacted into the band (key slot filled by pair_chain_kernel).
+// A block walks a contiguous part of the list and stages its band entries in shared memory, so
+// the global cursor is advanced once per ~1000 band entries (one atomic per entry, and even one
+// per warp, serialised on that single address: 77 % of the kernel was spent waiting for it).
+constexpr int BF_THREADS = 256;
+constexpr int BF_STAGE = 1024;
+__global__ void __launch_bounds__(BF_THREADS)
 band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, const float *__restrict__ r,
                    float tlo, float thi, float c_half,
                    unsigned long long *__restrict__ counters /* [3] below, [4] band weighted, [5] band len */,
                    uint2 *__restrict__ band_ij, unsigned long long band_cap, int *__restrict__ overflow) {
-    unsigned int below = 0u, bw = 0u;
+    __shared__ uint2 stage[BF_STAGE];
+    __shared__ unsigned int s_count;
+    __shared__ unsigned long long s_base;
+    if (threadIdx.x == 0) s_count = 0u;
+    __syncthreads();
+    unsigned int below = 0u, bw = 0u, pending = 0u;
     const int lane = threadIdx.x & 31;
-    // whole warps iterate together (the bound is rounded up to a multiple of 32) so that the
-    // band slots of a warp are reserved with ONE atomic
-    const unsigned long long m32 = (m + 31ull) & ~31ull;
-    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < m32;
-         e += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long per = (m + gridDim.x - 1) / gridDim.x;
+    const unsigned long long b0 = per * blockIdx.x, b1 = b0 + per < m ? b0 + per : m;
+    auto flush = [&]() {     // whole block
+        __syncthreads();
+        const unsigned int cnt = s_count;
+        if (threadIdx.x == 0 && cnt) s_base = atomicAdd(&counters[5], (unsigned long long)cnt);
+        __syncthreads();
+        const unsigned long long base = s_base;
+        for (unsigned int e = threadIdx.x; e < cnt; e += BF_THREADS) {
+            if (base + e < band_cap) band_ij[base + e] = stage[e];
+            else *overflow = 1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_count = 0u;
+        __syncthreads();
+    };
+    for (unsigned long long e0 = b0; e0 < b1; e0 += BF_THREADS) {
+        const unsigned long long e = e0 + threadIdx.x;
         bool in_band = false;
         PairEntry pe{};
-        if (e < m) {
+        if (e < b1) {
             pe = list[e];
             const uint32_t i = pe.i, j = pe.jw & 0x7fffffffu, w = (pe.jw >> 31) ? 2u : 1u;
             const float eps = c_half * (r[i] + r[j]);
@@ -506,16 +529,20 @@ band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, con
         }
         const unsigned int vote = __ballot_sync(0xffffffffu, in_band);
         if (vote) {
-            unsigned long long base = 0ull;
-            if (lane == 0) base = atomicAdd(&counters[5], (unsigned long long)__popc(vote));
+            unsigned int base = 0u;
+            if (lane == 0) base = atomicAdd(&s_count, (unsigned)__popc(vote));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (in_band) {
-                const unsigned long long g = base + (unsigned)__popc(vote & ((1u << lane) - 1u));
-                if (g < band_cap) band_ij[g] = make_uint2(pe.i, pe.jw);
-                else *overflow = 1;
-            }
+            if (in_band) stage[base + (unsigned)__popc(vote & ((1u << lane) - 1u))] = make_uint2(pe.i, pe.jw);
+        }
+        // flush while one more round of at most BF_THREADS entries is still guaranteed to fit
+        // (decided on the round count, which is uniform without reading the shared counter)
+        pending += BF_THREADS;
+        if (pending > BF_STAGE - BF_THREADS) {
+            flush();
+            pending = 0;
         }
     }
+    flush();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         below += __shfl_xor_sync(0xffffffffu, below, o);

@@ -11,9 +11,10 @@
 // memory 32 columns at a time, every global load instruction covering four complete
 // 128-byte lines (8 lanes x 16 B per row).  The one-thread-one-row form this replaces touched
 // 32 different lines per load instruction and was bound by the L1 tag stage (99 % l1tex).
-// Shared layout per warp: A[k][p] / B[k][p] (k = column in the chunk, p = pair), stored at
-// p' = (p + 4 (k >> 2)) & 31 so that both the transposing stores and the per-thread reads
-// are bank-conflict free.
+// Shared layout per warp: A[p][k] / B[p][k] (p = pair, k = column in the chunk) with a row
+// stride of 36 floats: the 16-byte stores of a quarter warp (one row, 8 consecutive float4)
+// and the 16-byte reads of a quarter warp (8 rows, same float4 index) both cover all 32 banks
+// exactly once, so every shared-memory access is a conflict-free 128-bit one.
 #pragma once
 #include "common.cuh"
 
@@ -28,7 +29,8 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 
 constexpr int PC_WARPS = 4;                       // warps per block
 constexpr int PC_CHUNK = 32;                      // columns staged per step (one 128-byte line per row)
-constexpr int PC_SMEM_PER_WARP = 2 * PC_CHUNK * 32 * 4;
+constexpr int PC_ROW = PC_CHUNK + 4;              // padded row stride (floats)
+constexpr int PC_SMEM_PER_WARP = 2 * 32 * PC_ROW * 4;
 
 // SRC 0: io = uint2 (i, jw) list, rewritten in place as (key, weight)   [band of median_tc.cu]
 // SRC 1: pairs drawn from splitmix64(seed + s), io = u32 keys[s]         [pilot of median.cu]
@@ -39,7 +41,7 @@ pair_chain_kernel(void *__restrict__ io, unsigned long long m, const float *__re
     extern __shared__ __align__(16) unsigned char pc_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *sA = reinterpret_cast<float *>(pc_smem + (size_t)warp * PC_SMEM_PER_WARP);
-    float *sB = sA + PC_CHUNK * 32;
+    float *sB = sA + 32 * PC_ROW;
     const unsigned long long ngroups = (m + 31ull) / 32ull;
     // contiguous group range per block (neighbouring list entries share rows: L1 reuse)
     const unsigned long long g0 = ngroups * blockIdx.x / gridDim.x, g1 = ngroups * (blockIdx.x + 1) / gridDim.x;
@@ -76,11 +78,7 @@ pair_chain_kernel(void *__restrict__ io, unsigned long long m, const float *__re
             __syncwarp();                          // the previous chunk has been consumed
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
-                float *dst = (t < 8 ? sA : sB) + (4 * f) * 32 + (((4 * t + sub) + 4 * f) & 31);
-                dst[0] = buf[t].x;
-                dst[32] = buf[t].y;
-                dst[64] = buf[t].z;
-                dst[96] = buf[t].w;
+                *reinterpret_cast<float4 *>((t < 8 ? sA : sB) + ((4 * t + sub) & 31) * PC_ROW + 4 * f) = buf[t];
             }
             if (c + 1 < nchunks) {
 #pragma unroll
@@ -88,9 +86,13 @@ pair_chain_kernel(void *__restrict__ io, unsigned long long m, const float *__re
             }
             __syncwarp();
 #pragma unroll
-            for (int k = 0; k < PC_CHUNK; ++k) {
-                const int col = (lane + 4 * (k >> 2)) & 31;
-                acc = __fmaf_rn(sA[k * 32 + col], sB[k * 32 + col], acc);
+            for (int q = 0; q < PC_CHUNK / 4; ++q) {
+                const float4 a = *reinterpret_cast<const float4 *>(sA + lane * PC_ROW + 4 * q);
+                const float4 b = *reinterpret_cast<const float4 *>(sB + lane * PC_ROW + 4 * q);
+                acc = __fmaf_rn(a.x, b.x, acc);
+                acc = __fmaf_rn(a.y, b.y, acc);
+                acc = __fmaf_rn(a.z, b.z, acc);
+                acc = __fmaf_rn(a.w, b.w, acc);
             }
         }
         if (valid) {
@@ -108,7 +110,7 @@ static int launch_pair_chain(stein_ctx *ctx, void *io, unsigned long long m, con
     if (m == 0) return STEIN_OK;
     const size_t smem = (size_t)PC_WARPS * PC_SMEM_PER_WARP;
     const unsigned long long ngroups = (m + 31ull) / 32ull;
-    // 4 blocks of 4 warps per SM are resident (register-limited: 128 per thread)
+    // 4 blocks of 4 warps per SM are resident (register-limited: 128 per thread; 36 KB of shared memory each)
     const unsigned grid = (unsigned)std::min<unsigned long long>((ngroups + PC_WARPS - 1) / PC_WARPS,
                                                                  4ull * (unsigned long long)ctx->num_sms);
     pair_chain_kernel<SRC><<<grid, PC_WARPS * 32, smem, ctx->stream>>>(io, m, X, r, n, ld, seed);
