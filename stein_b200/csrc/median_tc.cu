@@ -36,6 +36,7 @@ constexpr int SW_EPI_THREADS = 256;
 constexpr int SW_STAGES = 12;
 constexpr uint32_t SW_UNIT_BYTES = 128 * 128;
 constexpr int SW_STAGE_CAP = 1024;          // entries staged in shared memory between flushes
+constexpr int SW_HIST_BINS = 4096;          // histogram of the listed D~ (locates t~ without extra passes)
 constexpr uint32_t SW_TMEM_COLS = 512;
 constexpr uint32_t SW_TMEM_AH = 256, SW_TMEM_AL = 384;   // A operand (row tile, BF16 hi / lo) in TMEM
 
@@ -55,7 +56,11 @@ struct SweepParams {
     float wlo, whi, c_half;
     const float *rmax;            // device: max_i r_i (bounds the column part of the error term)
     int debug_skip;               // experiments only: skip the classification (results invalid)
-    unsigned long long *counters; // [0] certainly-below (weighted), [1] listed (weighted), [2] list length
+    // listed D~ -> bin floor((D~ - hlo) * hscale), clamped to [0, SW_HIST_BINS); hlo / hscale are
+    // derived in the kernel from the window and rmax (a device value)
+    unsigned long long *hist;     // [SW_HIST_BINS] weighted counts of the listed D~ (accumulated)
+    unsigned long long *cnt_below, *cnt_listed, *cnt_len;   // weighted below / listed counts, list length
+    float *hparams_out;           // [2]: the (hlo, hscale) actually used, for the host
     int *overflow;
     PairEntry *list;
     unsigned long long list_cap;
@@ -79,6 +84,12 @@ __device__ __forceinline__ uint32_t select32(const uint32_t (&v)[32], int c) {
 #pragma unroll
     for (int k = 0; k < 2; ++k) e[k] = (c & 8) ? d[2 * k + 1] : d[2 * k];
     return (c & 16) ? e[1] : e[0];
+}
+
+// monotone (non-decreasing in dt) bin of a listed D~
+__device__ __forceinline__ int hist_bin(float dt, float hlo, float hscale) {
+    const float x = (dt - hlo) * hscale;
+    return x <= 0.0f ? 0 : (x >= (float)(SW_HIST_BINS - 1) ? SW_HIST_BINS - 1 : (int)x);
 }
 
 // successor of tile (I, J) in the row-major order of the upper triangle
@@ -110,6 +121,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
     unsigned long long *sBase = reinterpret_cast<unsigned long long *>(tail + 272);
     PairEntry *sBuf = reinterpret_cast<PairEntry *>(tail + 320);     // SW_STAGE_CAP entries
     float *sCol = reinterpret_cast<float *>(tail + 320 + SW_STAGE_CAP * sizeof(PairEntry));   // [2][128]
+    unsigned int *sHist = reinterpret_cast<unsigned int *>(sCol + 256);                        // [SW_HIST_BINS]
 
     const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
     const long long NT = p.t_end - p.t_begin;
@@ -133,6 +145,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
         tma_prefetch_desc(&mapXh);
         tma_prefetch_desc(&mapXl);
     }
+    for (int b = threadIdx.x; b < SW_HIST_BINS; b += SW_THREADS) sHist[b] = 0u;
     if (warp == 1) tmem_alloc(tmem_slot, SW_TMEM_COLS);
     tcgen05_fence_before();
     __syncthreads();
@@ -242,6 +255,14 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
         const int wpr = p.kblocks * 32;             // 32-bit words per row of Xh / Xl
         const float cm = 0.5f * (1.0f - p.c_half), cp = 0.5f * (1.0f + p.c_half);
         const float rmax = __ldg(p.rmax);
+        // histogram range of the listed D~: the window widened by the largest possible error term
+        const float hpad = 4.0f * p.c_half * rmax + 1e-5f * fmaxf(fabsf(p.wlo), fabsf(p.whi));
+        const float hlo = p.wlo - hpad;
+        const float hscale = (float)SW_HIST_BINS / fmaxf((p.whi + hpad) - hlo, 1e-30f);
+        if (blockIdx.x == 0 && tid256 == 0) {
+            p.hparams_out[0] = hlo;
+            p.hparams_out[1] = hscale;
+        }
         unsigned int below = 0u, listed = 0u;
         int prevI = -1, aseg = 0;
         long long jj = 0;
@@ -353,9 +374,10 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                         if (slot < (unsigned)SW_STAGE_CAP) {
                             sBuf[slot] = e;
                         } else {   // staging full (degenerate data): straight to global
-                            const unsigned long long gi = atomicAdd(&p.counters[2], 1ull);
+                            const unsigned long long gi = atomicAdd(p.cnt_len, 1ull);
                             if (gi < p.list_cap) p.list[gi] = e;
                             else *p.overflow = 1;
+                            atomicAdd(&sHist[hist_bin(e.dt, hlo, hscale)], w);
                         }
                         ++slot;
                     }
@@ -378,7 +400,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                 const bool flush = have > (unsigned)SW_STAGE_CAP / 2 || (t + 1 == my1 && have > 0);
                 *sN = flush ? have : 0u;
                 if (flush) {
-                    *sBase = atomicAdd(&p.counters[2], (unsigned long long)have);
+                    *sBase = atomicAdd(p.cnt_len, (unsigned long long)have);
                     *sCount = 0u;
                 }
             }
@@ -387,8 +409,10 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
             if (cnt) {
                 const unsigned long long base = *sBase;
                 for (unsigned int e = tid256; e < cnt; e += SW_EPI_THREADS) {
-                    if (base + e < p.list_cap) p.list[base + e] = sBuf[e];
+                    const PairEntry pe = sBuf[e];
+                    if (base + e < p.list_cap) p.list[base + e] = pe;
                     else *p.overflow = 1;
+                    atomicAdd(&sHist[hist_bin(pe.dt, hlo, hscale)], (pe.jw >> 31) ? 2u : 1u);
                 }
                 named_bar_sync(3, SW_EPI_THREADS);
             }
@@ -399,8 +423,13 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
             listed += __shfl_xor_sync(0xffffffffu, listed, o);
         }
         if (lane == 0) {
-            if (below) atomicAdd(&p.counters[0], (unsigned long long)below);
-            if (listed) atomicAdd(&p.counters[1], (unsigned long long)listed);
+            if (below) atomicAdd(p.cnt_below, (unsigned long long)below);
+            if (listed) atomicAdd(p.cnt_listed, (unsigned long long)listed);
+        }
+        named_bar_sync(3, SW_EPI_THREADS);
+        for (int b = tid256; b < SW_HIST_BINS; b += SW_EPI_THREADS) {
+            const unsigned int v = sHist[b];
+            if (v) atomicAdd(&p.hist[b], (unsigned long long)v);
         }
     }
 
@@ -446,23 +475,21 @@ max_kernel(const float *__restrict__ r, int64_t n, float *__restrict__ out) {
     }
 }
 
-// weighted histogram of one radix digit over (SRC 0) the D~ of the pair list, (SRC 1) band keys
+// weighted histogram of the keys that fall into the window [key_lo, key_lo + (nbins << shift)):
+// bins[0] += weight of the keys below the window, bins[1 + b] += weight of bin b; keys above the
+// window are ignored.  SRC 1: uint2 (key, weight) band entries, SRC 2: plain u32 keys (weight 1).
 template <int SRC>
 __global__ void __launch_bounds__(256)
-hist_pass_kernel(const void *__restrict__ src, unsigned long long m, uint32_t prefix, uint32_t mask, int shift,
-                 int bits, unsigned long long *__restrict__ bins) {
-    __shared__ unsigned int h[2048];
-    const int nb = 1 << bits;
-    for (int b = threadIdx.x; b < nb; b += blockDim.x) h[b] = 0u;
+window_hist_kernel(const void *__restrict__ src, unsigned long long m, uint32_t key_lo, uint32_t shift,
+                   uint32_t nbins, unsigned long long *__restrict__ bins) {
+    extern __shared__ unsigned int wh[];      // nbins + 1
+    for (uint32_t b = threadIdx.x; b <= nbins; b += blockDim.x) wh[b] = 0u;
     __syncthreads();
+    unsigned int below = 0u;
     for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < m;
          e += (unsigned long long)gridDim.x * blockDim.x) {
         uint32_t key, w;
-        if (SRC == 0) {
-            const PairEntry pe = reinterpret_cast<const PairEntry *>(src)[e];
-            key = float_to_key(pe.dt);
-            w = (pe.jw >> 31) ? 2u : 1u;
-        } else if (SRC == 2) {
+        if (SRC == 2) {
             key = reinterpret_cast<const uint32_t *>(src)[e];
             w = 1u;
         } else {
@@ -470,11 +497,19 @@ hist_pass_kernel(const void *__restrict__ src, unsigned long long m, uint32_t pr
             key = kw.x;
             w = kw.y;
         }
-        if ((key & mask) == prefix) atomicAdd(&h[(key >> shift) & (nb - 1)], w);
+        if (key < key_lo) {
+            below += w;
+        } else {
+            const uint32_t b = (key - key_lo) >> shift;
+            if (b < nbins) atomicAdd(&wh[1 + b], w);
+        }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if ((threadIdx.x & 31) == 0 && below) atomicAdd(&wh[0], below);
     __syncthreads();
-    for (int b = threadIdx.x; b < nb; b += blockDim.x)
-        if (h[b]) atomicAdd(&bins[b], (unsigned long long)h[b]);
+    for (uint32_t b = threadIdx.x; b <= nbins; b += blockDim.x)
+        if (wh[b]) atomicAdd(&bins[b], (unsigned long long)wh[b]);
 }
 
 // entries certainly below t~ - delta are counted; entries that may fall inside
@@ -486,8 +521,8 @@ constexpr int BF_THREADS = 256;
 constexpr int BF_STAGE = 1024;
 __global__ void __launch_bounds__(BF_THREADS)
 band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, const float *__restrict__ r,
-                   float tlo, float thi, float c_half,
-                   unsigned long long *__restrict__ counters /* [3] below, [4] band weighted, [5] band len */,
+                   float tlo, float thi, float c_half, unsigned long long *__restrict__ below_out,
+                   unsigned long long *__restrict__ bandw_out, unsigned long long *__restrict__ bandlen_out,
                    uint2 *__restrict__ band_ij, unsigned long long band_cap, int *__restrict__ overflow) {
     __shared__ uint2 stage[BF_STAGE];
     __shared__ unsigned int s_count;
@@ -501,7 +536,7 @@ band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, con
     auto flush = [&]() {     // whole block
         __syncthreads();
         const unsigned int cnt = s_count;
-        if (threadIdx.x == 0 && cnt) s_base = atomicAdd(&counters[5], (unsigned long long)cnt);
+        if (threadIdx.x == 0 && cnt) s_base = atomicAdd(bandlen_out, (unsigned long long)cnt);
         __syncthreads();
         const unsigned long long base = s_base;
         for (unsigned int e = threadIdx.x; e < cnt; e += BF_THREADS) {
@@ -549,8 +584,8 @@ band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, con
         bw += __shfl_xor_sync(0xffffffffu, bw, o);
     }
     if ((threadIdx.x & 31) == 0) {
-        if (below) atomicAdd(&counters[3], (unsigned long long)below);
-        if (bw) atomicAdd(&counters[4], (unsigned long long)bw);
+        if (below) atomicAdd(below_out, (unsigned long long)below);
+        if (bw) atomicAdd(bandw_out, (unsigned long long)bw);
     }
 }
 
@@ -568,21 +603,30 @@ struct MedianArena {
     __nv_bfloat16 *Xh = nullptr, *Xl = nullptr;
     PairEntry *list = nullptr;
     uint2 *band = nullptr;
-    unsigned long long *counters = nullptr;   // 8 x u64 + overflow int + rmax float
-    unsigned long long *bins = nullptr;       // 2048
-    unsigned long long *h_pinned = nullptr;   // 2048 + 16
+    unsigned long long *counters = nullptr;   // CNT_TOTAL u64, layout below
+    unsigned long long *bins = nullptr;       // HIST_MAX_BINS + 2
+    unsigned long long *h_pinned = nullptr;   // HIST_MAX_BINS + 2 window counts, then CNT_TOTAL counters
     int64_t x_elems = 0;
     unsigned long long list_cap = 0, band_cap = 0;
 };
+
+// counters block (u64 slots).  Slots [0, CNT_G1_END) are global quantities after the sweep (one
+// all-reduce), [CNT_BELOW2, CNT_BELOW2 + 3) after the band filter; the rest is rank-local.
+constexpr int CNT_BELOW = 0, CNT_LISTED = 1, CNT_OVERFLOW = 2, CNT_HIST = 3;
+constexpr int CNT_G1_END = CNT_HIST + SW_HIST_BINS;
+constexpr int CNT_LIST_LEN = CNT_G1_END;
+constexpr int CNT_BELOW2 = CNT_G1_END + 1, CNT_BANDW = CNT_G1_END + 2, CNT_OVERFLOW2 = CNT_G1_END + 3;
+constexpr int CNT_BAND_LEN = CNT_G1_END + 4, CNT_RMAX = CNT_G1_END + 5, CNT_HPARAMS = CNT_G1_END + 6;
+constexpr int CNT_TOTAL = CNT_G1_END + 8;
 
 static MedianArena g_arena;   // one per process (one GPU per process)
 
 static int ensure_arena(stein_ctx *ctx, int64_t rows, int64_t DP, uint64_t pairs) {
     MedianArena &A = g_arena;
     if (!A.counters) {
-        STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.counters, 128));
-        STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.bins, 2048 * 8));
-        STEIN_CHECK_CUDA(ctx, cudaMallocHost(&A.h_pinned, (2048 + 16) * 8));
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.counters, CNT_TOTAL * 8));
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.bins, (HIST_MAX_BINS + 2) * 8));
+        STEIN_CHECK_CUDA(ctx, cudaMallocHost(&A.h_pinned, (HIST_MAX_BINS + 2 + CNT_TOTAL) * 8));
     }
     if (rows * DP > A.x_elems && rows * DP > 0) {
         if (A.Xh) cudaFree(A.Xh);
@@ -606,71 +650,96 @@ static int ensure_arena(stein_ctx *ctx, int64_t rows, int64_t DP, uint64_t pairs
     return STEIN_OK;
 }
 
-// distributed weighted radix select: value of 0-based rank `rank` among the keys; also
-// reports the next larger key present (valid when *has_next) and the weight at/below the key
+// One histogram pass over a key window; the counts (nbins + 1 u64) end up in A.h_pinned.
 template <int SRC>
-static int radix_select(stein_ctx *ctx, const void *src, unsigned long long m_local, uint64_t rank,
-                        uint32_t *key_out, uint64_t *cum_through_key, bool *has_next, uint32_t *next_key,
-                        int max_bits = 32, bool distributed = true) {
+static int window_counts(stein_ctx *ctx, const void *src, unsigned long long m_local, uint32_t key_lo,
+                         uint32_t shift, uint32_t nbins, bool distributed) {
     MedianArena &A = g_arena;
-    uint32_t prefix = 0, mask = 0;
-    int consumed = 0;
-    uint64_t offset = 0;   // weight strictly below the current prefix range
-    while (consumed < max_bits) {
-        const int bits = std::min(11, 32 - consumed);
-        const int shift = 32 - consumed - bits;
-        const int nb = 1 << bits;
-        STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(A.bins, 0, nb * 8, ctx->stream));
-        if (m_local) {
-            const unsigned grid = (unsigned)std::min<unsigned long long>((m_local + 255) / 256, 8ull * ctx->num_sms);
-            hist_pass_kernel<SRC><<<grid, 256, 0, ctx->stream>>>(src, m_local, prefix, mask, shift, bits, A.bins);
-            STEIN_CHECK_LAUNCH(ctx);
-        }
-        if (distributed && ctx->has_comm && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.bins, nb) != 0)
-            return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
-        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.h_pinned, A.bins, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        uint64_t cum = offset;
-        int b = 0;
-        for (; b < nb; ++b) {
-            if (cum + A.h_pinned[b] > rank) break;
-            cum += A.h_pinned[b];
-        }
-        if (b == nb) return 1;   // rank beyond the data: caller falls back
-        offset = cum;
-        prefix |= (uint32_t)b << shift;
-        mask |= (uint32_t)(nb - 1) << shift;
-        consumed += bits;
-        if (consumed == 32) {
-            *cum_through_key = cum + A.h_pinned[b];
-            *has_next = false;
-            for (int nbk = b + 1; nbk < nb; ++nbk)
-                if (A.h_pinned[nbk]) {
-                    *has_next = true;
-                    *next_key = (prefix & ~(uint32_t)(nb - 1)) | (uint32_t)nbk;
-                    break;
-                }
-        }
+    static bool attr_set = false;
+    if (!attr_set) {
+        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(window_hist_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (HIST_MAX_BINS + 1) * 4));
+        attr_set = true;
     }
-    *key_out = prefix;
+    STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(A.bins, 0, (nbins + 1) * 8, ctx->stream));
+    if (m_local) {
+        const unsigned grid = (unsigned)std::min<unsigned long long>((m_local + 255) / 256, 4ull * ctx->num_sms);
+        window_hist_kernel<SRC><<<grid, 256, (nbins + 1) * 4, ctx->stream>>>(src, m_local, key_lo, shift, nbins, A.bins);
+        STEIN_CHECK_LAUNCH(ctx);
+    }
+    if (distributed && ctx->has_comm && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.bins, (int64_t)nbins + 1) != 0)
+        return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.h_pinned, A.bins, (nbins + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return STEIN_OK;
 }
 
-// Window keys from the pilot sample: [lo, hi] brackets the sample quantiles at rank_lo /
-// rank_hi to 22-bit resolution (two histogram passes each; every rank holds the same sample,
-// so nothing is all-reduced).
+struct KeyWindow {
+    uint32_t key_lo, shift, nbins;
+};
+// smallest shift for which [lo, hi] fits into HIST_MAX_BINS bins
+static KeyWindow window_over(uint32_t lo, uint32_t hi) {
+    const uint64_t span = (uint64_t)hi - lo + 1;
+    uint32_t sh = 0;
+    while (((span - 1) >> sh) >= (uint64_t)HIST_MAX_BINS) ++sh;
+    return {lo, sh, (uint32_t)(((span - 1) >> sh) + 1)};
+}
+
+// Exact keys at the 0-based ascending weighted ranks rank[0] <= rank[1] among keys known to lie
+// in [key_lo, key_hi] (keys outside: below counts, above is ignored).  One pass when the span is
+// at most HIST_MAX_BINS keys (the normal case for the band), otherwise the window is narrowed.
+// Returns 1 when a rank is not inside the window.
+template <int SRC>
+static int window_select2(stein_ctx *ctx, const void *src, unsigned long long m_local, uint32_t key_lo,
+                          uint32_t key_hi, const uint64_t rank[2], uint32_t key_out[2], bool distributed) {
+    MedianArena &A = g_arena;
+    KeyWindow win[2];
+    win[0] = win[1] = window_over(key_lo, key_hi);
+    bool done[2] = {false, false};
+    for (int iter = 0; iter < 8 && !(done[0] && done[1]); ++iter) {
+        const int q0 = done[0] ? 1 : 0;
+        const KeyWindow w = win[q0];
+        STEIN_TRY(window_counts<SRC>(ctx, src, m_local, w.key_lo, w.shift, w.nbins, distributed));
+        for (int q = q0; q < 2; ++q) {
+            if (done[q] || win[q].key_lo != w.key_lo || win[q].shift != w.shift || win[q].nbins != w.nbins) continue;
+            KeyWindow nw = w;
+            const int rc = stein_median_narrow(reinterpret_cast<const uint64_t *>(A.h_pinned), w.key_lo, w.shift, w.nbins, rank[q], &key_out[q],
+                                               &nw.key_lo, &nw.shift, &nw.nbins);
+            if (rc == 1) done[q] = true;
+            else if (rc == 0) win[q] = nw;
+            else return 1;
+        }
+    }
+    return (done[0] && done[1]) ? STEIN_OK : 1;
+}
+
+// Window keys from the pilot sample: [lo, hi] brackets the sample quantiles at rank_lo / rank_hi.
+// Two histogram passes (every rank holds the same sample, so nothing is all-reduced): 14 bits of
+// the full key range, then the bins of the two ranks split 16384 ways.
 int pilot_window(stein_ctx *ctx, const uint32_t *keys_dev, int64_t m, uint64_t rank_lo, uint64_t rank_hi,
                  uint32_t *lo_key, uint32_t *hi_key) {
     if (!g_arena.counters) STEIN_TRY(ensure_arena(ctx, 0, 0, 0));
-    uint64_t cum;
-    bool hn;
-    uint32_t nk, k;
-    int rc = radix_select<2>(ctx, keys_dev, (unsigned long long)m, rank_lo, &k, &cum, &hn, &nk, 22, false);
-    if (rc != STEIN_OK) return rc;
-    *lo_key = k;                       // low 10 bits zero: start of the bin
-    rc = radix_select<2>(ctx, keys_dev, (unsigned long long)m, rank_hi, &k, &cum, &hn, &nk, 22, false);
-    if (rc != STEIN_OK) return rc;
-    *hi_key = k | 0x3FFu;              // end of the bin
+    MedianArena &A = g_arena;
+    KeyWindow w = {0u, 18u, (uint32_t)HIST_MAX_BINS};
+    for (int pass = 0; pass < 2; ++pass) {
+        STEIN_TRY(window_counts<2>(ctx, keys_dev, (unsigned long long)m, w.key_lo, w.shift, w.nbins, false));
+        uint64_t cum = A.h_pinned[0];
+        if (rank_lo < cum) return 1;
+        int64_t blo = -1, bhi = -1;
+        for (uint32_t b = 0; b < w.nbins; ++b) {
+            const uint64_t c = A.h_pinned[1 + b];
+            if (blo < 0 && cum + c > rank_lo) blo = b;
+            if (bhi < 0 && cum + c > rank_hi) bhi = b;
+            cum += c;
+        }
+        if (blo < 0 || bhi < 0) return 1;
+        const uint64_t lo = (uint64_t)w.key_lo + ((uint64_t)blo << w.shift);
+        const uint64_t hi = std::min<uint64_t>((uint64_t)w.key_lo + (((uint64_t)bhi + 1) << w.shift) - 1, 0xffffffffull);
+        *lo_key = (uint32_t)lo;
+        *hi_key = (uint32_t)hi;
+        if (w.shift == 0) break;
+        w = window_over((uint32_t)lo, (uint32_t)hi);
+    }
     return STEIN_OK;
 }
 
@@ -693,12 +762,13 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     const int64_t t0 = ntiles * rank / world, t1 = ntiles * (rank + 1) / world;
     const float c_half = eps_coeff(d);
 
-    STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(A.counters, 0, 128, ctx->stream));
+    STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(A.counters, 0, CNT_TOTAL * 8, ctx->stream));
     const int64_t count4 = rows * DP / 4;
     split_bf16_kernel<<<(unsigned)((count4 + 255) / 256), 256, 0, ctx->stream>>>(X, count4, A.Xh, A.Xl);
     STEIN_CHECK_LAUNCH(ctx);
-    float *d_rmax = reinterpret_cast<float *>(A.counters + 9);
-    int *d_overflow = reinterpret_cast<int *>(A.counters + 8);
+    float *d_rmax = reinterpret_cast<float *>(A.counters + CNT_RMAX);
+    int *d_overflow = reinterpret_cast<int *>(A.counters + CNT_OVERFLOW);
+    int *d_overflow2 = reinterpret_cast<int *>(A.counters + CNT_OVERFLOW2);
     max_kernel<<<1, 1024, 0, ctx->stream>>>(r, n, d_rmax);
     STEIN_CHECK_LAUNCH(ctx);
 
@@ -719,11 +789,16 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     p.c_half = c_half;
     p.rmax = d_rmax;
     p.debug_skip = getenv("STEIN_DEBUG_SWEEP_SKIP") ? atoi(getenv("STEIN_DEBUG_SWEEP_SKIP")) : 0;
-    p.counters = A.counters;
+    p.hist = A.counters + CNT_HIST;
+    p.cnt_below = A.counters + CNT_BELOW;
+    p.cnt_listed = A.counters + CNT_LISTED;
+    p.cnt_len = A.counters + CNT_LIST_LEN;
+    p.hparams_out = reinterpret_cast<float *>(A.counters + CNT_HPARAMS);
     p.overflow = d_overflow;
     p.list = A.list;
     p.list_cap = A.list_cap;
-    const size_t smem = 1024 + (size_t)SW_STAGES * SW_UNIT_BYTES + 320 + (size_t)SW_STAGE_CAP * sizeof(PairEntry) + 1024 + 64;
+    const size_t smem = 1024 + (size_t)SW_STAGES * SW_UNIT_BYTES + 320 + (size_t)SW_STAGE_CAP * sizeof(PairEntry) + 1024 +
+                        (size_t)SW_HIST_BINS * 4 + 64;
     static bool attr_set = false;
     if (!attr_set) {
         STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(sweep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -752,91 +827,72 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
         }
     }
     if (sweeps) *sweeps += 1;
-    // counters[0] below, [1] listed weight are global quantities; [2] list length stays local
-    unsigned long long *h = A.h_pinned + 2048;
-    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h, A.counters, 80, cudaMemcpyDeviceToHost, ctx->stream));
+    // below / listed / overflow / histogram of the listed D~ become global quantities with ONE
+    // all-reduce; the list itself (and its length) stays rank-local
+    if (world > 1 && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.counters, CNT_G1_END) != 0)
+        return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+    unsigned long long *h = A.h_pinned + HIST_MAX_BINS + 2;
+    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h, A.counters, CNT_TOTAL * 8, cudaMemcpyDeviceToHost, ctx->stream));
     STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const unsigned long long list_len = std::min<unsigned long long>(h[2], A.list_cap);
-    int overflow_local = *reinterpret_cast<int *>(h + 8);
-    const float rmax = *reinterpret_cast<float *>(h + 9);
-    if (world > 1) {
-        // make the two weighted counts and the overflow flag global
-        unsigned long long *scratch = A.h_pinned + 2048 + 12;
-        scratch[0] = h[0];
-        scratch[1] = h[1];
-        scratch[2] = (unsigned long long)overflow_local;
-        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.bins, scratch, 24, cudaMemcpyHostToDevice, ctx->stream));
-        if (ctx->comm.allreduce_sum_u64(ctx->comm.user, A.bins, 3) != 0)
-            return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
-        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(scratch, A.bins, 24, cudaMemcpyDeviceToHost, ctx->stream));
-        STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        h[0] = scratch[0];
-        h[1] = scratch[1];
-        overflow_local = scratch[2] != 0;
-    }
-    const uint64_t below = h[0], listed = h[1];
-    if (overflow_local) return 1;
+    const unsigned long long list_len = std::min<unsigned long long>(h[CNT_LIST_LEN], A.list_cap);
+    const float rmax = *reinterpret_cast<float *>(h + CNT_RMAX);
+    const float hlo = reinterpret_cast<float *>(h + CNT_HPARAMS)[0], hscale = reinterpret_cast<float *>(h + CNT_HPARAMS)[1];
+    const uint64_t below = h[CNT_BELOW], listed = h[CNT_LISTED];
+    if (h[CNT_OVERFLOW]) return 1;
     if (!(below <= ranks[0] && ranks[1] < below + listed)) return 1;   // pilot window missed
 
-    // D~ value at the lower target rank
-    uint32_t tkey = 0, nk = 0;
-    uint64_t cum = 0;
-    bool hn = false;
-    int rc = radix_select<0>(ctx, A.list, list_len, ranks[0] - below, &tkey, &cum, &hn, &nk);
-    if (rc != STEIN_OK) return rc;
-    const float tmid = key_to_float(tkey);
-    const float delta = c_half * 2.0f * rmax * 1.0001f + 2.0f * fabsf(tmid) * 1.2e-7f;
-    const float tlo = tmid - delta, thi = tmid + delta;
+    // bin of the D~ value at the lower target rank (the bins are monotone in D~)
+    uint64_t cum = below;
+    int bstar = -1;
+    for (int b = 0; b < SW_HIST_BINS; ++b) {
+        if (cum + h[CNT_HIST + b] > ranks[0]) {
+            bstar = b;
+            break;
+        }
+        cum += h[CNT_HIST + b];
+    }
+    if (bstar <= 0 || bstar >= SW_HIST_BINS - 1) return 1;             // clamped end bins: not usable
+    // t~ lies in bin bstar; one extra bin on either side covers the rounding of the bin function
+    const float bin_w = 1.0f / hscale;
+    const float t_lo = hlo + (float)(bstar - 1) * bin_w, t_hi = hlo + (float)(bstar + 2) * bin_w;
+    // the exact value at a rank differs from the D~ value at that rank by at most max eps
+    const float delta = c_half * 2.0f * rmax * 1.0001f + 2.0f * fmaxf(fabsf(t_lo), fabsf(t_hi)) * 1.2e-7f;
+    const float tlo = t_lo - delta, thi = t_hi + delta;
 
     if (list_len) {
         const unsigned grid = (unsigned)std::min<unsigned long long>((list_len + 255) / 256, 16ull * ctx->num_sms);
-        band_filter_kernel<<<grid, 256, 0, ctx->stream>>>(A.list, list_len, r, tlo, thi, c_half, A.counters,
-                                                         A.band, A.band_cap, d_overflow);
+        band_filter_kernel<<<grid, BF_THREADS, 0, ctx->stream>>>(A.list, list_len, r, tlo, thi, c_half,
+                                                                A.counters + CNT_BELOW2, A.counters + CNT_BANDW,
+                                                                A.counters + CNT_BAND_LEN, A.band, A.band_cap,
+                                                                d_overflow2);
         STEIN_CHECK_LAUNCH(ctx);
     }
-    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h, A.counters, 80, cudaMemcpyDeviceToHost, ctx->stream));
+    if (world > 1 && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.counters + CNT_BELOW2, 3) != 0)
+        return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h + CNT_BELOW2, A.counters + CNT_BELOW2, 4 * 8, cudaMemcpyDeviceToHost,
+                                          ctx->stream));
     STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const unsigned long long band_len = std::min<unsigned long long>(h[5], A.band_cap);
-    uint64_t below2 = h[3], band_w = h[4];
-    int overflow2 = *reinterpret_cast<int *>(h + 8);
-    if (world > 1) {
-        unsigned long long *scratch = A.h_pinned + 2048 + 12;
-        scratch[0] = below2;
-        scratch[1] = band_w;
-        scratch[2] = (unsigned long long)overflow2;
-        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.bins, scratch, 24, cudaMemcpyHostToDevice, ctx->stream));
-        if (ctx->comm.allreduce_sum_u64(ctx->comm.user, A.bins, 3) != 0)
-            return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
-        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(scratch, A.bins, 24, cudaMemcpyDeviceToHost, ctx->stream));
-        STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        below2 = scratch[0];
-        band_w = scratch[1];
-        overflow2 = scratch[2] != 0;
-    }
-    if (overflow2) return 1;
+    const unsigned long long band_len = std::min<unsigned long long>(h[CNT_BAND_LEN], A.band_cap);
+    const uint64_t below2 = h[CNT_BELOW2], band_w = h[CNT_BANDW];
+    if (h[CNT_OVERFLOW2]) return 1;
     const uint64_t c1 = below + below2;
     if (!(c1 <= ranks[0] && ranks[1] < c1 + band_w)) return 1;
     // contract-arithmetic distance of every band pair: (i, jw) -> (key, weight), in place
     STEIN_TRY(launch_pair_chain<0>(ctx, A.band, band_len, X, r, n, ld, 0));
 
-    // exact keys of the two target ranks among the band
-    uint32_t k0 = 0, k1 = 0;
-    rc = radix_select<1>(ctx, A.band, band_len, ranks[0] - c1, &k0, &cum, &hn, &nk);
+    // exact keys of the two target ranks among the band.  A band pair has |D - D~| <= eps <= delta
+    // and D~ within eps of [tlo, thi], so its key lies in the window below (normally a few
+    // thousand keys wide: one histogram pass)
+    const uint32_t klo = float_to_key(tlo - 2.0f * delta), khi = float_to_key(thi + 2.0f * delta);
+    const uint64_t rk[2] = {ranks[0] - c1, ranks[1] - c1};
+    uint32_t k01[2] = {0u, 0u};
+    const int rc = window_select2<1>(ctx, A.band, band_len, klo, khi, rk, k01, true);
     if (rc != STEIN_OK) return rc;
-    if (ranks[1] == ranks[0] || ranks[1] - c1 < cum) {
-        k1 = k0;
-    } else if (hn) {
-        k1 = nk;
-    } else {
-        uint64_t cum2;
-        rc = radix_select<1>(ctx, A.band, band_len, ranks[1] - c1, &k1, &cum2, &hn, &nk);
-        if (rc != STEIN_OK) return rc;
-    }
     // the selected values must lie where the certainty argument holds
-    const float m0 = key_to_float(k0), m1 = key_to_float(k1);
+    const float m0 = key_to_float(k01[0]), m1 = key_to_float(k01[1]);
     if (!(m0 >= tlo && m1 <= thi && m0 >= p.wlo && m1 <= p.whi)) return 1;
-    keys_out[0] = k0;
-    keys_out[1] = k1;
+    keys_out[0] = k01[0];
+    keys_out[1] = k01[1];
     return STEIN_OK;
 }
 

@@ -972,6 +972,34 @@ reduce_partials2_kernel(const double *__restrict__ partials, int count, double *
 
 static float *g_debug_dumpS = nullptr;   // set only by stein_debug_flash_gram (tests)
 
+// The per-tile slot counts read by finalize_slots_kernel depend only on the shape.  They live in
+// a small library-owned device buffer (one per process = one per GPU) and are uploaded again
+// only when the shape or the kernel changes, so a steady-state iteration has no H2D copy.
+static int plan_upload(stein_ctx *ctx, int impl, const std::vector<int> &nslots, int64_t n_local, int64_t n_total,
+                       int64_t d, int **dev_out) {
+    static int *d_plan = nullptr;
+    static size_t cap = 0;
+    static int64_t c_key[4] = {-1, -1, -1, -1};
+    const int64_t key[4] = {impl, n_local, n_total, d};
+    const bool same = d_plan && c_key[0] == key[0] && c_key[1] == key[1] && c_key[2] == key[2] && c_key[3] == key[3];
+    if (!same) {
+        if (nslots.size() > cap) {
+            STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the old buffer may still be read
+            if (d_plan) cudaFree(d_plan);
+            d_plan = nullptr;
+            cap = 0;
+            STEIN_CHECK_CUDA(ctx, cudaMalloc(&d_plan, nslots.size() * sizeof(int)));
+            cap = nslots.size();
+        }
+        // pageable source: the runtime stages the bytes before returning
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(d_plan, nslots.data(), nslots.size() * sizeof(int),
+                                              cudaMemcpyHostToDevice, ctx->stream));
+        for (int k = 0; k < 4; ++k) c_key[k] = key[k];
+    }
+    *dev_out = d_plan;
+    return STEIN_OK;
+}
+
 int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all, int64_t n_total,
                  int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
                  int64_t ws_bytes, float *phi, double *sumsq) {
@@ -989,7 +1017,7 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     float *ksum = (float *)pws;          pws += (int64_t)pl.maxslots * pl.rows * 4;
     double *partials = (double *)(((uintptr_t)pws + 7) & ~(uintptr_t)7);
     pws = (char *)partials + FINALIZE_MAX_BLOCKS * 8;
-    int *tile_nslots = (int *)pws;
+    int *tile_nslots = nullptr;
 
     const float l2e = 1.4426950408889634f;
     {
@@ -1001,9 +1029,7 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
         prep_yt_kernel<<<g, b, 0, ctx->stream>>>(X_all, S_all, pl.cols, ld, 1.0f / h2, YTh, YTl);
         STEIN_CHECK_LAUNCH(ctx);
     }
-    // pageable source: the runtime stages the bytes before returning, so `pl` may go away
-    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(tile_nslots, pl.tile_nslots.data(), pl.nI * sizeof(int),
-                                          cudaMemcpyHostToDevice, ctx->stream));
+    STEIN_TRY(plan_upload(ctx, 0, pl.tile_nslots, n_local, n_total, d, &tile_nslots));
 
     CUtensorMap mapXh, mapXl, mapYh, mapYl;
     STEIN_TRY(make_tensor_map_2d(ctx, &mapXh, Xh, 2, (uint64_t)pl.DP, (uint64_t)pl.cols, (uint64_t)pl.DP * 2, 128));
@@ -1086,7 +1112,7 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
     float *ksum = (float *)pws;          pws += (int64_t)maxslots * rows2 * 4;
     double *partials = (double *)(((uintptr_t)pws + 7) & ~(uintptr_t)7);
     pws = (char *)partials + FINALIZE_MAX_BLOCKS * 8;
-    int *d_tile_nslots = (int *)pws;
+    int *d_tile_nslots = nullptr;
 
     const float l2e = 1.4426950408889634f;
     {
@@ -1098,8 +1124,7 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
         prep_yt_kernel<<<g, b, 0, ctx->stream>>>(X_all, S_all, cols, ld, 1.0f / h2, YTh, YTl);
         STEIN_CHECK_LAUNCH(ctx);
     }
-    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(d_tile_nslots, tile_nslots.data(), tile_nslots.size() * sizeof(int),
-                                          cudaMemcpyHostToDevice, ctx->stream));
+    STEIN_TRY(plan_upload(ctx, 1, tile_nslots, n_local, n_total, d, &d_tile_nslots));
     CUtensorMap mXh, mXl, mXh64, mXl64, mYh, mYl;
     STEIN_TRY(make_tensor_map_2d(ctx, &mXh, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
     STEIN_TRY(make_tensor_map_2d(ctx, &mXl, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
