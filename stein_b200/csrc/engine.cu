@@ -36,6 +36,8 @@ struct stein_engine {
     void *ws = nullptr;
     int64_t ws_bytes = 0;
     void *stage = nullptr;  // device staging for float64 host arrays
+    cudaStream_t copy_stream = nullptr;  // score upload overlapped with the median (update_particles_host)
+    cudaEvent_t ev_scores = nullptr, ev_ready = nullptr;
     float last_med = 0.f, last_bw = 0.f;
     int32_t last_sweeps = 0;
     float *X_local() const { return X_all + (int64_t)rank * q * ld; }
@@ -60,22 +62,29 @@ __global__ void padded_to_f64_kernel(const float *__restrict__ src, int64_t rows
     dst[e] = (double)src[r * ld + c];
 }
 
-static int upload(stein_engine *e, const void *host, int is_f64, float *dst) {
+static int upload(stein_engine *e, const void *host, int is_f64, float *dst, cudaStream_t stream) {
     stein_ctx *ctx = e->ctx;
     STEIN_REQUIRE(ctx, host != nullptr, "null host pointer");
     if (e->n_local == 0) return STEIN_OK;
     if (!is_f64) {
-        STEIN_CHECK_CUDA(ctx, cudaMemcpy2DAsync(dst, e->ld * 4, host, e->d * 4, e->d * 4, e->n_local,
-                                                cudaMemcpyHostToDevice, ctx->stream));
+        if (e->ld == e->d) {
+            STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(dst, host, e->n_local * e->d * 4, cudaMemcpyHostToDevice, stream));
+        } else {
+            STEIN_CHECK_CUDA(ctx, cudaMemcpy2DAsync(dst, e->ld * 4, host, e->d * 4, e->d * 4, e->n_local,
+                                                    cudaMemcpyHostToDevice, stream));
+        }
     } else {
         STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(e->stage, host, e->n_local * e->d * 8,
-                                              cudaMemcpyHostToDevice, ctx->stream));
+                                              cudaMemcpyHostToDevice, stream));
         const int64_t total = e->n_local * e->d;
-        f64_to_padded_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+        f64_to_padded_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
             (const double *)e->stage, e->n_local, e->d, e->ld, dst);
         STEIN_CHECK_LAUNCH(ctx);
     }
     return STEIN_OK;
+}
+static int upload(stein_engine *e, const void *host, int is_f64, float *dst) {
+    return upload(e, host, is_f64, dst, e->ctx->stream);
 }
 
 static int download(stein_engine *e, const float *src, void *host, int is_f64) {
@@ -83,8 +92,12 @@ static int download(stein_engine *e, const float *src, void *host, int is_f64) {
     STEIN_REQUIRE(ctx, host != nullptr, "null host pointer");
     if (e->n_local == 0) return STEIN_OK;
     if (!is_f64) {
-        STEIN_CHECK_CUDA(ctx, cudaMemcpy2DAsync(host, e->d * 4, src, e->ld * 4, e->d * 4, e->n_local,
-                                                cudaMemcpyDeviceToHost, ctx->stream));
+        if (e->ld == e->d) {
+            STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(host, src, e->n_local * e->d * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            STEIN_CHECK_CUDA(ctx, cudaMemcpy2DAsync(host, e->d * 4, src, e->ld * 4, e->d * 4, e->n_local,
+                                                    cudaMemcpyDeviceToHost, ctx->stream));
+        }
     } else {
         const int64_t total = e->n_local * e->d;
         padded_to_f64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
@@ -144,6 +157,9 @@ int stein_engine_create(stein_engine **out, stein_ctx *ctx, int64_t n_total, int
     alloc0(&e->ws, e->ws_bytes);
     alloc0(&e->stage, std::max<int64_t>(e->q * d * 8, 256));
     if (err == cudaSuccess) err = cudaMallocHost(&e->h_sumsq, 64);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_scores, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_ready, cudaEventDisableTiming);
     if (err != cudaSuccess) {
         stein_engine_destroy(e);
         return fail(ctx, err == cudaErrorMemoryAllocation ? STEIN_ERR_NOMEM : STEIN_ERR_CUDA,
@@ -161,6 +177,12 @@ int stein_engine_destroy(stein_engine *e) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->h_sumsq) cudaFreeHost(e->h_sumsq);
+    if (e->copy_stream) {
+        cudaStreamSynchronize(e->copy_stream);
+        cudaStreamDestroy(e->copy_stream);
+    }
+    if (e->ev_scores) cudaEventDestroy(e->ev_scores);
+    if (e->ev_ready) cudaEventDestroy(e->ev_ready);
     delete e;
     return STEIN_OK;
 }
@@ -205,15 +227,13 @@ int stein_engine_get_phi(stein_engine *e, void *phi_host, int is_f64) {
     return download(e, e->phi, phi_host, is_f64);
 }
 
-int stein_engine_step(stein_engine *e) {
-    if (!e) return STEIN_ERR_INVALID;
+// Phase 1 needs only the particles: all-gather X, row norms, exact median, bandwidth.
+static int step_bandwidth(stein_engine *e, float *bw_out) {
     stein_ctx *ctx = e->ctx;
-    STEIN_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t rows_all = e->q * e->world;
     if (e->world > 1) {
         const int64_t cnt = e->q * e->ld;
-        if (ctx->comm.allgather_f32(ctx->comm.user, e->X_local(), e->X_all, cnt) != 0 ||
-            ctx->comm.allgather_f32(ctx->comm.user, e->S_local(), e->S_all, cnt) != 0)
+        if (ctx->comm.allgather_f32(ctx->comm.user, e->X_local(), e->X_all, cnt) != 0)
             return fail(ctx, STEIN_ERR_COMM, "allgather_f32 hook failed");
     }
     // abstract_kernel.py:34 -- r = sum(T*T, 1), contract order
@@ -228,6 +248,18 @@ int stein_engine_step(stein_engine *e) {
     if (!(bw > 0.0f) || bw != bw)
         return fail(ctx, STEIN_ERR_INVALID,
                     "median squared distance is %g: bandwidth undefined (all particles equal?)", (double)med);
+    *bw_out = bw;
+    return STEIN_OK;
+}
+
+// Phase 2 needs the scores: (all-gather S,) phi, clip, optimizer step.
+static int step_update(stein_engine *e, float bw) {
+    stein_ctx *ctx = e->ctx;
+    if (e->world > 1) {
+        const int64_t cnt = e->q * e->ld;
+        if (ctx->comm.allgather_f32(ctx->comm.user, e->S_local(), e->S_all, cnt) != 0)
+            return fail(ctx, STEIN_ERR_COMM, "allgather_f32 hook failed");
+    }
     // abstract_stein_sampler.py:100-105
     STEIN_TRY(stein_phi(ctx, e->X_all, e->S_all, e->r_all, e->n_total, e->d, e->ld, e->row_begin,
                         std::max<int64_t>(e->n_local, 1), bw, e->ws, e->ws_bytes, e->phi, e->sumsq));
@@ -250,11 +282,30 @@ int stein_engine_step(stein_engine *e) {
     return STEIN_OK;
 }
 
+int stein_engine_step(stein_engine *e) {
+    if (!e) return STEIN_ERR_INVALID;
+    STEIN_CHECK_CUDA(e->ctx, cudaSetDevice(e->ctx->device));
+    float bw = 0.f;
+    STEIN_TRY(step_bandwidth(e, &bw));
+    return step_update(e, bw);
+}
+
 int stein_engine_update_particles_host(stein_engine *e, const void *S_host, void *X_host_out,
                                        int is_f64) {
     if (!e) return STEIN_ERR_INVALID;
-    STEIN_TRY(stein_engine_set_scores(e, S_host, is_f64));
-    STEIN_TRY(stein_engine_step(e));
+    stein_ctx *ctx = e->ctx;
+    STEIN_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    // The median needs the particles only: the scores travel on a second stream while it runs
+    // (the S buffer's last reader, the previous phi, is ordered before the copy by ev_ready).
+    STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_ready, ctx->stream));
+    STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(e->copy_stream, e->ev_ready, 0));
+    STEIN_TRY(upload(e, S_host, is_f64, e->S_local(), e->copy_stream));
+    STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_scores, e->copy_stream));
+    float bw = 0.f;
+    const int rc = step_bandwidth(e, &bw);
+    STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e->ev_scores, 0));
+    if (rc != STEIN_OK) return rc;
+    STEIN_TRY(step_update(e, bw));
     if (X_host_out) return stein_engine_get_particles(e, X_host_out, is_f64);
     return STEIN_OK;
 }

@@ -48,6 +48,21 @@ constexpr int FL_OCHUNK = 4;                    // column tiles accumulated in T
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TMEM_S0 = 256, TMEM_S1 = 384;
 
+// Partial results of a row are stored per slot: slot 0 covers every local row; slots >= 1 exist
+// only for the leftover row tiles of the schedule (rows >= row0), stored compactly.
+struct SlotLayout {
+    float *O0, *Ox;          // [rows][DP]  /  [slot - 1][rows - row0][DP]
+    float *k0, *kx;          // [rows]      /  [slot - 1][rows - row0]
+    long long row0, xrows;   // first leftover row, number of leftover rows
+    int DP;
+    __host__ __device__ float *orow(int slot, long long row) const {
+        return slot == 0 ? O0 + row * DP : Ox + ((long long)(slot - 1) * xrows + (row - row0)) * DP;
+    }
+    __host__ __device__ float *krow(int slot, long long row) const {
+        return slot == 0 ? k0 + row : kx + (long long)(slot - 1) * xrows + (row - row0);
+    }
+};
+
 struct FlashParams {
     int nJ;              // column tiles
     int kblocks;         // DP / 64: 128-byte K blocks per row of the BF16 hi / lo arrays
@@ -57,10 +72,7 @@ struct FlashParams {
     int row_tile0;       // first global tile of the local row block
     float c1;            // log2(e) / h^2
     const float *nrm;    // -r_j log2(e) / (2 h^2); -inf for j >= n
-    float *Opart;        // [slot][rows_local][DP]
-    long long o_slot_stride;
-    float *ksum_part;    // [slot][rows_local]
-    long long k_slot_stride;
+    SlotLayout out;      // partial O / row sums per (slot, row)
     float *dumpS;        // debug: raw GEMM1 output, [rows_local][dump_ld] (NULL in production)
     long long dump_ld;
 };
@@ -72,40 +84,64 @@ struct FlashBarriers {
     uint64_t o_full, o_empty;
 };
 
-// Work schedule shared by the three roles.  Every CTA sweeps the column tiles in the SAME
-// order at the same pace, so a column tile is fetched from HBM once and then served to the
-// other CTAs by L2 (a stream-K split measured 38 % L2 misses = 20 GB of DRAM reads per
-// launch at n = 65 536).  Round r < nI/G: CTA c owns row tile r*G + c and all nJ column
-// tiles.  The nI % G leftover row tiles are each cut into s = G / rem equal column ranges
-// ("slots"), one CTA per range; partial results of a row tile are summed by finalize.
-struct SegIter {
-    int nI, nJ, G, c, k, rounds, rem, s;
-    __device__ SegIter(const FlashParams &p)
-        : nI(p.nI), nJ(p.nJ), G((int)gridDim.x), c((int)blockIdx.x), k(0) {
+// Work schedule shared by the three roles.  Every CTA (cluster) sweeps the column tiles in the
+// SAME order at the same pace, so a column tile is fetched from HBM once and then served to the
+// others by L2 (a stream-K split measured 38 % L2 misses = 20 GB of DRAM reads per launch at
+// n = 65 536).  Round r < nI / G: unit c owns row tile r G + c and all nJ column tiles.  The
+// rem = nI % G leftover row tiles are laid end to end (rem nJ column tiles) and cut into equal
+// chunks, one per unit, so every unit stays busy whatever nI is (particle-sharded runs have
+// nI < G).  A chunk may straddle two row tiles; the partial results of a row tile go to
+// consecutive "slots" and are summed in fixed order by finalize.  chunk >= nJ / 7 bounds the
+// number of slots of a tile by 8.
+struct TileSchedule {
+    int nI, nJ, G, rounds, rem;
+    long long W, chunk;
+    __host__ __device__ TileSchedule(int nI_, int nJ_, int G_) : nI(nI_), nJ(nJ_), G(G_) {
         rounds = nI / G;
         rem = nI % G;
-        s = rem ? G / rem : 1;
-        if (s > nJ) s = nJ;
+        W = (long long)rem * nJ;
+        const long long a = (W + G - 1) / G, b = (nJ + 6) / 7;
+        chunk = a > b ? a : b;
+        if (chunk < 1) chunk = 1;
+    }
+    // first / last unit working on leftover tile tr (0 <= tr < rem)
+    __host__ __device__ int first_unit(int tr) const { return (int)(((long long)tr * nJ) / chunk); }
+    __host__ __device__ int last_unit(int tr) const { return (int)((((long long)tr + 1) * nJ - 1) / chunk); }
+    __host__ __device__ int nslots(int t) const { return t < rounds * G ? 1 : last_unit(t - rounds * G) - first_unit(t - rounds * G) + 1; }
+};
+
+struct SegWalk {
+    TileSchedule sc;
+    int c, k;
+    long long pos, end;
+    __device__ SegWalk(int nI, int nJ, int G, int c_) : sc(nI, nJ, G), c(c_), k(0) {
+        pos = (long long)c * sc.chunk;
+        end = pos + sc.chunk;
+        if (end > sc.W) end = sc.W;
     }
     __device__ bool next(int &t, int &j0, int &j1, int &slot) {
-        if (k < rounds) {
-            t = k * G + c;
+        if (k < sc.rounds) {
+            t = k * sc.G + c;
             j0 = 0;
-            j1 = nJ;
+            j1 = sc.nJ;
             slot = 0;
             ++k;
             return true;
         }
-        if (k == rounds && rem && c < rem * s) {
-            t = rounds * G + c / s;
-            slot = c % s;
-            j0 = (int)((long long)nJ * slot / s);
-            j1 = (int)((long long)nJ * (slot + 1) / s);
-            ++k;
-            return j1 > j0;
-        }
-        return false;
+        if (pos >= end) return false;
+        const int tr = (int)(pos / sc.nJ);
+        j0 = (int)(pos - (long long)tr * sc.nJ);
+        const long long left = end - pos;
+        j1 = (long long)j0 + left < (long long)sc.nJ ? (int)(j0 + left) : sc.nJ;
+        t = sc.rounds * sc.G + tr;
+        slot = c - sc.first_unit(tr);
+        pos += j1 - j0;
+        return true;
     }
+};
+
+struct SegIter : SegWalk {
+    __device__ SegIter(const FlashParams &p) : SegWalk(p.nI, p.nJ, (int)gridDim.x, (int)blockIdx.x) {}
 };
 
 // Layout of one 128-column S/P buffer after the exponential step: each 32-column chunk ch
@@ -393,7 +429,7 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
                 }
             }
             // write this segment's partial O row and row sum
-            float *orow = p.Opart + (size_t)slot * p.o_slot_stride + ((size_t)t * 128 + row) * p.DP + wg * ocols;
+            float *orow = p.out.orow(slot, (long long)t * 128 + row) + wg * ocols;
 #pragma unroll
             for (int ch = 0; ch < FL_MAX_DP / 64; ++ch) {
                 if (ch < och) {
@@ -406,7 +442,7 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
             }
             if (wg == 1) sK[row] = ksum;
             named_bar_sync(2, FL_EPI_THREADS);
-            if (wg == 0) p.ksum_part[(size_t)slot * p.k_slot_stride + (size_t)t * 128 + row] = ksum + sK[row];
+            if (wg == 0) *p.out.krow(slot, (long long)t * 128 + row) = ksum + sK[row];
         }
     }
 
@@ -438,40 +474,12 @@ struct Flash2Params {
     long long row_begin;  // first global particle row of the local block (multiple of 128)
     float c1;
     const float *nrm;
-    float *Opart;
-    long long o_slot_stride;
-    float *ksum_part;
-    long long k_slot_stride;
+    SlotLayout out;
 };
 
-struct Seg2Iter {   // same round-synchronous schedule as SegIter, over cluster pairs
-    int nI, nJ, G, c, k, rounds, rem, s;
+struct Seg2Iter : SegWalk {   // same schedule as SegIter, over cluster pairs and 256-row tiles
     __device__ Seg2Iter(const Flash2Params &p)
-        : nI(p.nI2), nJ(p.nJ), G((int)gridDim.x / 2), c((int)blockIdx.x / 2), k(0) {
-        rounds = nI / G;
-        rem = nI % G;
-        s = rem ? G / rem : 1;
-        if (s > nJ) s = nJ;
-    }
-    __device__ bool next(int &t, int &j0, int &j1, int &slot) {
-        if (k < rounds) {
-            t = k * G + c;
-            j0 = 0;
-            j1 = nJ;
-            slot = 0;
-            ++k;
-            return true;
-        }
-        if (k == rounds && rem && c < rem * s) {
-            t = rounds * G + c / s;
-            slot = c % s;
-            j0 = (int)((long long)nJ * slot / s);
-            j1 = (int)((long long)nJ * (slot + 1) / s);
-            ++k;
-            return j1 > j0;
-        }
-        return false;
-    }
+        : SegWalk(p.nI2, p.nJ, (int)gridDim.x / 2, (int)blockIdx.x / 2) {}
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FL_THREADS, 1)
@@ -763,7 +771,7 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                     ++oc;
                 }
             }
-            float *orow = p.Opart + (size_t)slot * p.o_slot_stride + lrow * FL_MAX_DP + wg * ocols;
+            float *orow = p.out.orow(slot, (long long)lrow) + wg * ocols;
 #pragma unroll
             for (int ch = 0; ch < och; ++ch) {
 #pragma unroll
@@ -774,7 +782,7 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
             }
             if (wg == 1) sK[row] = ksum;
             named_bar_sync(2, FL_EPI_THREADS);
-            if (wg == 0) p.ksum_part[(size_t)slot * p.k_slot_stride + lrow] = ksum + sK[row];
+            if (wg == 0) *p.out.krow(slot, (long long)lrow) = ksum + sK[row];
         }
     }
 
@@ -870,54 +878,68 @@ bool flash_tc_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total, 
 }
 
 struct FlashPlan {
-    int64_t rows, cols, DP, nI, nJ;
+    int64_t rows, cols, DP, nI, nJ;     // nI row tiles of tile_rows rows each
+    int64_t tile_rows, rows_alloc;      // rows_alloc = nI * tile_rows
     int G, maxslots;
-    std::vector<int> tile_nslots;
+    int64_t row0, xrows;                // leftover rows of the schedule (SlotLayout)
+    std::vector<int> tile_nslots;       // per 128-row tile
 };
 
-static FlashPlan flash_plan(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
+// pair = false: 128-row tiles over num_sms CTAs; pair = true: 256-row tiles over num_sms / 2 clusters
+static FlashPlan flash_plan(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d, bool pair) {
     FlashPlan pl;
     pl.rows = stein_rows_padded(n_local);
     pl.cols = stein_rows_padded(n_total);
     pl.DP = stein_ld(d);
-    pl.nI = pl.rows / TILE;
+    pl.tile_rows = pair ? 256 : TILE;
+    pl.rows_alloc = round_up(pl.rows, pl.tile_rows);
+    pl.nI = pl.rows_alloc / pl.tile_rows;
     pl.nJ = (n_total + TILE - 1) / TILE;
-    pl.G = ctx->num_sms;
-    // mirrors SegIter
-    const int64_t rounds = pl.nI / pl.G, rem = pl.nI % pl.G;
-    int64_t s = rem ? pl.G / rem : 1;
-    s = std::min<int64_t>(s, pl.nJ);
-    pl.tile_nslots.assign(pl.nI, 1);
-    for (int64_t t = rounds * pl.G; t < pl.nI; ++t) pl.tile_nslots[t] = (int)s;
-    pl.maxslots = (int)(rem ? s : 1);
+    pl.G = pair ? std::max(1, ctx->num_sms / 2) : ctx->num_sms;
+    const TileSchedule sc((int)pl.nI, (int)pl.nJ, pl.G);
+    pl.row0 = (int64_t)sc.rounds * sc.G * pl.tile_rows;
+    pl.xrows = (int64_t)sc.rem * pl.tile_rows;
+    pl.maxslots = 1;
+    pl.tile_nslots.assign(pl.rows_alloc / TILE, 1);
+    for (int64_t t = 0; t < pl.nI; ++t) {
+        const int ns = sc.nslots((int)t);
+        pl.maxslots = std::max(pl.maxslots, ns);
+        for (int64_t h = 0; h < pl.tile_rows / TILE; ++h) pl.tile_nslots[t * (pl.tile_rows / TILE) + h] = ns;
+    }
     return pl;
 }
 
-static int pair_maxslots(const stein_ctx *ctx, int64_t n_local, int64_t n_total) {
-    const int64_t nI2 = round_up(stein_rows_padded(n_local), 256) / 256, nJ = (n_total + TILE - 1) / TILE;
-    const int64_t G2 = std::max(1, ctx->num_sms / 2), rem = nI2 % G2;
-    return (int)(rem ? std::min<int64_t>(G2 / rem, nJ) : 1);
+static int64_t slot_bytes(const FlashPlan &pl) {
+    return (pl.rows_alloc + (int64_t)(pl.maxslots - 1) * pl.xrows) * (pl.DP + 1) * 4;
 }
 
-// workspace: [Xh, Xl, YTh, YTl (bf16) | nrm | Opart slots | ksum slots | partials | tile_nslots]
+// carve the slot buffers out of the workspace
+static SlotLayout slot_layout(const FlashPlan &pl, char *&pws) {
+    SlotLayout L;
+    L.O0 = (float *)pws;  pws += pl.rows_alloc * pl.DP * 4;
+    L.Ox = (float *)pws;  pws += (int64_t)(pl.maxslots - 1) * pl.xrows * pl.DP * 4;
+    L.k0 = (float *)pws;  pws += pl.rows_alloc * 4;
+    L.kx = (float *)pws;  pws += (int64_t)(pl.maxslots - 1) * pl.xrows * 4;
+    L.row0 = pl.row0;
+    L.xrows = pl.xrows;
+    L.DP = (int)pl.DP;
+    return L;
+}
+
+// workspace: [Xh, Xl, YTh, YTl (bf16) | nrm | slot buffers | partials]
 int64_t flash_tc_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
-    const FlashPlan pl = flash_plan(ctx, n_local, n_total, d);
+    const FlashPlan p1 = flash_plan(ctx, n_local, n_total, d, false), p2 = flash_plan(ctx, n_local, n_total, d, true);
     int64_t b = 0;
-    b += pl.cols * pl.DP * 2 * 4;                       // Xh, Xl, YTh, YTl (bf16)
-    const int64_t rows2 = round_up(pl.rows, 256);       // the CTA-pair kernel works on 256-row tiles
-    const int64_t slots = std::max(pl.maxslots, pair_maxslots(ctx, n_local, n_total));
-    b += (pl.cols + 256) * 4;                           // nrm
-    b += slots * rows2 * pl.DP * 4;                     // Opart
-    b += slots * rows2 * 4;                             // ksum
+    b += p1.cols * p1.DP * 2 * 4;                       // Xh, Xl, YTh, YTl (bf16)
+    b += (p1.cols + 256) * 4;                           // nrm
+    b += std::max(slot_bytes(p1), slot_bytes(p2));
     b += FINALIZE_MAX_BLOCKS * 8;
-    b += pl.nI * 4;
     return b + 4096;
 }
 
 // finalize with a per-tile slot count (unused slots are never read)
 __global__ void __launch_bounds__(256)
-finalize_slots_kernel(const float *__restrict__ O, int64_t slot_stride, const int *__restrict__ tile_nslots,
-                      const float *__restrict__ ksum, int64_t ksum_slot_stride,
+finalize_slots_kernel(const SlotLayout L, const int *__restrict__ tile_nslots,
                       const float *__restrict__ X_local, int64_t rows_valid, int64_t rows, int64_t ld,
                       float inv_h2, float inv_n, float *__restrict__ phi, double *__restrict__ partials) {
     const int64_t ld4 = ld / 4;
@@ -925,14 +947,14 @@ finalize_slots_kernel(const float *__restrict__ O, int64_t slot_stride, const in
     double local = 0.0;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total4;
          e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = e / ld4;
+        const int64_t row = e / ld4, c4 = e - row * ld4;
         const int ns = tile_nslots[row / TILE];
-        float4 o = reinterpret_cast<const float4 *>(O)[e];
-        float ks = ksum[row];
+        float4 o = reinterpret_cast<const float4 *>(L.orow(0, row))[c4];
+        float ks = *L.krow(0, row);
         for (int s = 1; s < ns; ++s) {
-            const float4 o2 = reinterpret_cast<const float4 *>(O + s * slot_stride)[e];
+            const float4 o2 = reinterpret_cast<const float4 *>(L.orow(s, row))[c4];
             o.x += o2.x; o.y += o2.y; o.z += o2.z; o.w += o2.w;
-            ks += ksum[row + s * ksum_slot_stride];
+            ks += *L.krow(s, row);
         }
         float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < rows_valid) {
@@ -1003,7 +1025,7 @@ static int plan_upload(stein_ctx *ctx, int impl, const std::vector<int> &nslots,
 int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all, int64_t n_total,
                  int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
                  int64_t ws_bytes, float *phi, double *sumsq) {
-    const FlashPlan pl = flash_plan(ctx, n_local, n_total, d);
+    const FlashPlan pl = flash_plan(ctx, n_local, n_total, d, false);
     STEIN_REQUIRE(ctx, ld == pl.DP, "flash phi needs ld == stein_ld(d)");
     STEIN_REQUIRE(ctx, ws_bytes >= flash_tc_workspace_bytes(ctx, n_local, n_total, d), "phi workspace too small");
     STEIN_REQUIRE(ctx, row_begin % TILE == 0, "row_begin must be a multiple of %d", TILE);
@@ -1012,11 +1034,9 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     __nv_bfloat16 *Xl = (__nv_bfloat16 *)pws;   pws += pl.cols * pl.DP * 2;
     __nv_bfloat16 *YTh = (__nv_bfloat16 *)pws;  pws += pl.cols * pl.DP * 2;
     __nv_bfloat16 *YTl = (__nv_bfloat16 *)pws;  pws += pl.cols * pl.DP * 2;
-    float *nrm = (float *)pws;           pws += pl.cols * 4;
-    float *Opart = (float *)pws;         pws += (int64_t)pl.maxslots * pl.rows * pl.DP * 4;
-    float *ksum = (float *)pws;          pws += (int64_t)pl.maxslots * pl.rows * 4;
+    float *nrm = (float *)pws;           pws += (pl.cols + 256) * 4;
+    const SlotLayout L = slot_layout(pl, pws);
     double *partials = (double *)(((uintptr_t)pws + 7) & ~(uintptr_t)7);
-    pws = (char *)partials + FINALIZE_MAX_BLOCKS * 8;
     int *tile_nslots = nullptr;
 
     const float l2e = 1.4426950408889634f;
@@ -1046,10 +1066,7 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     p.row_tile0 = (int)(row_begin / TILE);
     p.c1 = l2e / h2;
     p.nrm = nrm;
-    p.Opart = Opart;
-    p.o_slot_stride = pl.rows * pl.DP;
-    p.ksum_part = ksum;
-    p.k_slot_stride = pl.rows;
+    p.out = L;
     p.dumpS = g_debug_dumpS;
     p.dump_ld = pl.cols;
 
@@ -1068,9 +1085,8 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     const int64_t rows_valid = std::max<int64_t>(0, std::min<int64_t>(n_local, n_total - row_begin));
     const int64_t total4 = pl.rows * ld / 4;
     const int blocks = (int)std::min<int64_t>((total4 + 255) / 256, FINALIZE_MAX_BLOCKS);
-    finalize_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(Opart, pl.rows * pl.DP, tile_nslots, ksum, pl.rows,
-                                                           X_all + row_begin * ld, rows_valid, pl.rows, ld,
-                                                           1.0f / h2, 1.0f / (float)n_total, phi, partials);
+    finalize_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(L, tile_nslots, X_all + row_begin * ld, rows_valid, pl.rows,
+                                                           ld, 1.0f / h2, 1.0f / (float)n_total, phi, partials);
     STEIN_CHECK_LAUNCH(ctx);
     reduce_partials2_kernel<<<1, 256, 0, ctx->stream>>>(partials, blocks, sumsq);
     STEIN_CHECK_LAUNCH(ctx);
@@ -1086,21 +1102,14 @@ bool flash_tc2_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total,
 int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all, int64_t n_total,
                   int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
                   int64_t ws_bytes, float *phi, double *sumsq) {
-    const int64_t rows = stein_rows_padded(n_local), cols = stein_rows_padded(n_total), DP = FL_MAX_DP;
+    const FlashPlan pl = flash_plan(ctx, n_local, n_total, d, true);
+    const int64_t rows = pl.rows, cols = pl.cols, DP = FL_MAX_DP;
     STEIN_REQUIRE(ctx, ld == DP, "CTA-pair flash phi needs ld == 256");
     STEIN_REQUIRE(ctx, ws_bytes >= flash_tc_workspace_bytes(ctx, n_local, n_total, d), "phi workspace too small");
     STEIN_REQUIRE(ctx, row_begin % TILE == 0, "row_begin must be a multiple of %d", TILE);
-    const int64_t rows2 = round_up(rows, 256);
-    const int64_t nI2 = rows2 / 256, nJ = (n_total + TILE - 1) / TILE;
-    const int G2 = ctx->num_sms / 2;                     // clusters
-    const int64_t rounds = nI2 / G2, rem = nI2 % G2;
-    int64_t sl = rem ? G2 / rem : 1;
-    sl = std::min<int64_t>(sl, nJ);
-    const int maxslots = (int)(rem ? sl : 1);
-    std::vector<int> tile_nslots(rows / TILE, 1);
-    for (int64_t t = rounds * G2; t < nI2; ++t)
-        for (int h = 0; h < 2; ++h)
-            if (2 * t + h < (int64_t)tile_nslots.size()) tile_nslots[2 * t + h] = (int)sl;
+    const int64_t nI2 = pl.nI, nJ = pl.nJ;
+    const int G2 = pl.G;                                 // clusters
+    const std::vector<int> &tile_nslots = pl.tile_nslots;
 
     char *pws = (char *)ws;
     __nv_bfloat16 *Xh = (__nv_bfloat16 *)pws;   pws += cols * DP * 2;
@@ -1108,10 +1117,8 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
     __nv_bfloat16 *YTh = (__nv_bfloat16 *)pws;  pws += cols * DP * 2;
     __nv_bfloat16 *YTl = (__nv_bfloat16 *)pws;  pws += cols * DP * 2;
     float *nrm = (float *)pws;           pws += (cols + 256) * 4;
-    float *Opart = (float *)pws;         pws += (int64_t)maxslots * rows2 * DP * 4;
-    float *ksum = (float *)pws;          pws += (int64_t)maxslots * rows2 * 4;
+    const SlotLayout L = slot_layout(pl, pws);
     double *partials = (double *)(((uintptr_t)pws + 7) & ~(uintptr_t)7);
-    pws = (char *)partials + FINALIZE_MAX_BLOCKS * 8;
     int *d_tile_nslots = nullptr;
 
     const float l2e = 1.4426950408889634f;
@@ -1139,10 +1146,7 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
     p.row_pair0 = 0;
     p.c1 = l2e / h2;
     p.nrm = nrm;
-    p.Opart = Opart;
-    p.o_slot_stride = rows2 * DP;
-    p.ksum_part = ksum;
-    p.k_slot_stride = rows2;
+    p.out = L;
     p.row_begin = row_begin;
     const size_t smem = flash_smem_bytes(DP);
     static bool attr_set = false;
@@ -1159,9 +1163,8 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
     const int64_t rows_valid = std::max<int64_t>(0, std::min<int64_t>(n_local, n_total - row_begin));
     const int64_t total4 = rows * ld / 4;
     const int blocks = (int)std::min<int64_t>((total4 + 255) / 256, FINALIZE_MAX_BLOCKS);
-    finalize_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(Opart, rows2 * DP, d_tile_nslots, ksum, rows2,
-                                                           X_all + row_begin * ld, rows_valid, rows, ld, 1.0f / h2,
-                                                           1.0f / (float)n_total, phi, partials);
+    finalize_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(L, d_tile_nslots, X_all + row_begin * ld, rows_valid, rows, ld,
+                                                           1.0f / h2, 1.0f / (float)n_total, phi, partials);
     STEIN_CHECK_LAUNCH(ctx);
     reduce_partials2_kernel<<<1, 256, 0, ctx->stream>>>(partials, blocks, sumsq);
     STEIN_CHECK_LAUNCH(ctx);
