@@ -50,6 +50,7 @@ extern "C" {
 #define STEIN_MEDIAN_AUTO 0
 #define STEIN_MEDIAN_FFMA 1 /* every sweep in contract arithmetic on the FP32 pipe          */
 #define STEIN_MEDIAN_TC 2   /* tcgen05 filter sweep + contract recomputation of candidates  */
+#define STEIN_MEDIAN_TC1 3  /* same, single-CTA sweep kernel (the default sweeps with CTA pairs) */
 
 /* optimizer kinds (stein_engine_create) */
 #define STEIN_OPT_ADAM 0    /* stein/optimizers/adam_gradient_descent.py    */

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libstein_b200.so")
 STEIN_OK = 0
 PHI_AUTO, PHI_DENSE_SIMT, PHI_FLASH_TC, PHI_FLASH_TC2 = 0, 1, 2, 3
 OPT_ADAM, OPT_ADAGRAD = 0, 1
-MEDIAN_AUTO, MEDIAN_FFMA, MEDIAN_TC = 0, 1, 2
+MEDIAN_AUTO, MEDIAN_FFMA, MEDIAN_TC, MEDIAN_TC1 = 0, 1, 2, 3
 
 c_i64, c_i32, c_u32, c_u64 = ctypes.c_int64, ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint64
 c_f32, c_f64, c_vp = ctypes.c_float, ctypes.c_double, ctypes.c_void_p

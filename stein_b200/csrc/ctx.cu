@@ -109,7 +109,7 @@ int stein_ctx_set_phi_impl(stein_ctx *ctx, int impl) {
 
 int stein_ctx_set_median_impl(stein_ctx *ctx, int impl) {
     STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
-    STEIN_REQUIRE(ctx, impl >= STEIN_MEDIAN_AUTO && impl <= STEIN_MEDIAN_TC, "unknown median impl %d", impl);
+    STEIN_REQUIRE(ctx, impl >= STEIN_MEDIAN_AUTO && impl <= STEIN_MEDIAN_TC1, "unknown median impl %d", impl);
     ctx->median_impl = impl;
     return STEIN_OK;
 }

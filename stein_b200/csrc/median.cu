@@ -332,11 +332,23 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
         // sample ranks m/2 -+ 3.5 sqrt(m): the true median lies between them with
         // probability ~1 - 1e-11; a miss is caught below and falls back to the
         // full-range radix select.
-        STEIN_TRY(launch_pair_chain<1>(ctx, ctx->d_pilot_keys, (unsigned long long)pilot_m, X_dev, r_dev, n, ld,
-                                       0x5eedull));
+        // every rank draws the same sample; with collective hooks each rank evaluates its slice
+        // of it and the window histograms are all-reduced
+        const int pw = ctx->has_comm ? ctx->comm.world : 1, pr = ctx->has_comm ? ctx->comm.rank : 0;
+        const int64_t s0 = pilot_m * pr / pw, s1 = pilot_m * (pr + 1) / pw;
+        STEIN_TRY(launch_pair_chain<1>(ctx, ctx->d_pilot_keys + s0, (unsigned long long)(s1 - s0), X_dev, r_dev, n, ld,
+                                       0x5eedull + (uint64_t)s0));
         const uint64_t delta = (uint64_t)(3.5 * sqrt((double)pilot_m));
         uint32_t ka = 0, kb = 0;
-        STEIN_TRY(pilot_window(ctx, ctx->d_pilot_keys, pilot_m, pilot_m / 2 - delta, pilot_m / 2 + delta, &ka, &kb));
+        {
+            const int prc = pilot_window(ctx, ctx->d_pilot_keys + s0, s1 - s0, pilot_m / 2 - delta,
+                                         pilot_m / 2 + delta, &ka, &kb);
+            if (prc < 0) return prc;
+            if (prc != STEIN_OK) {   // degenerate sample: no window, full-range FFMA select below
+                ka = 1u;
+                kb = 0u;
+            }
+        }
         if (kb >= ka) {
             const uint64_t span = (uint64_t)kb - ka + 1;
             uint32_t sh = 0;
@@ -352,7 +364,7 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
             }
         }
     }
-    if (ctx->median_impl == STEIN_MEDIAN_TC && !(done[0] && done[1]))
+    if ((ctx->median_impl == STEIN_MEDIAN_TC || ctx->median_impl == STEIN_MEDIAN_TC1) && !(done[0] && done[1]))
         return fail(ctx, STEIN_ERR_UNSUPPORTED, "tensor-core median route not applicable (n=%lld d=%lld)",
                     (long long)n, (long long)d);
 

@@ -100,6 +100,174 @@ __device__ __forceinline__ void next_tile(int &I, int &J, int T) {
     }
 }
 
+// ---- classification of one 128 x 128 tile of g = x_i . x_j (shared by both sweep kernels) ----
+// With D~ = r_i + r_j - 2 g and |D~ - D| <= c (r_i + r_j):
+//   certainly above the window  <=>  g < (1-c)/2 (r_i + r_j) - whi/2
+//   certainly below the window  <=>  g > (1+c)/2 (r_i + r_j) - wlo/2
+// Written with t = g - B_j, B_j = (1-c)/2 r_j (one shared-memory value per column):
+//   above  <=>  t < lo_i,   lo_i = (1-c)/2 r_i - whi/2
+//   below  <=>  t > hi_i,   hi_i = (1+c)/2 r_i + c rmax - wlo/2   (rmax >= r_j: conservative)
+// and everything else is listed.  lo_i / hi_i are moved outwards by `slack` (>> the fp32 rounding
+// of these few operations); that only enlarges the listed set, whose members are resolved from
+// their own D~ later.  "below" and "above" are decided by the sign of one subtraction each, so
+// the three classes are an exact partition of the pairs (t = -0.0 cannot occur with lo_i > 0;
+// a zero difference has a clear sign bit and counts as listed).
+struct TileClassifier {
+    const SweepParams &p;
+    PairEntry *sBuf;
+    float *sCol;                 // [2][128] column terms B_j of the current / next tile
+    unsigned int *sHist, *sCount, *sN;
+    unsigned long long *sBase;
+    int wg, row, tid256, lane;
+    uint32_t lane_addr;
+    float cm, cp, rmax, hlo, hscale;
+    unsigned int below, listed;
+
+    __device__ TileClassifier(const SweepParams &p_, uint8_t *tail, int warp, int lane_)
+        : p(p_), lane(lane_), below(0u), listed(0u) {
+        sCount = reinterpret_cast<unsigned int *>(tail + 260);
+        sN = reinterpret_cast<unsigned int *>(tail + 264);
+        sBase = reinterpret_cast<unsigned long long *>(tail + 272);
+        sBuf = reinterpret_cast<PairEntry *>(tail + 320);
+        sCol = reinterpret_cast<float *>(tail + 320 + SW_STAGE_CAP * sizeof(PairEntry));
+        sHist = reinterpret_cast<unsigned int *>(sCol + 256);
+        const int q = warp & 3;
+        wg = (warp - 4) >> 2;
+        row = q * 32 + lane;
+        tid256 = (warp - 4) * 32 + lane;
+        lane_addr = (uint32_t)(q * 32) << 16;
+        cm = 0.5f * (1.0f - p.c_half);
+        cp = 0.5f * (1.0f + p.c_half);
+        rmax = __ldg(p.rmax);
+        // histogram range of the listed D~: the window widened by the largest possible error term
+        const float hpad = 4.0f * p.c_half * rmax + 1e-5f * fmaxf(fabsf(p.wlo), fabsf(p.whi));
+        hlo = p.wlo - hpad;
+        hscale = (float)SW_HIST_BINS / fmaxf((p.whi + hpad) - hlo, 1e-30f);
+        if (blockIdx.x == 0 && tid256 == 0) {
+            p.hparams_out[0] = hlo;
+            p.hparams_out[1] = hscale;
+        }
+    }
+    // column terms of column tile J into buffer b (visible after the next named barrier)
+    __device__ void publish_cols(int J, int b) {
+        if (tid256 < 128) {
+            const long long j = (long long)J * 128 + tid256;
+            sCol[b * 128 + tid256] = j < p.n ? cm * p.r[j] : INFINITY;
+        }
+    }
+    // this thread's row i against the 128 columns of tile J; the g tile sits in TMEM at `s_tmem`
+    // (column 0 of the buffer, lane field 0); w = weight of the tile (0: nothing to do)
+    __device__ void classify(uint32_t s_tmem, long long i, int J, unsigned int w, int b) {
+        if (w == 0u) return;
+        const bool row_ok = i < p.n;
+        const float r_i = row_ok ? p.r[i] : 0.0f;
+        const float *rj = p.r + (size_t)J * 128;
+        const float slack = (r_i + rmax) * 9.5367431640625e-07f;   // 2^-20
+        // rows beyond n: lo_i = hi_i = +inf, so every pair is "above" (neither counted nor listed)
+        const float lo_i = row_ok ? cm * r_i - 0.5f * p.whi - 2.0f * slack : INFINITY;
+        const float hi_i = row_ok ? cp * r_i + p.c_half * rmax - 0.5f * p.wlo + 2.0f * slack : INFINITY;
+        const float *colterm = sCol + b * 128;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+            const int ch = wg * 2 + cc;
+            const long long jbase = (long long)J * 128 + ch * 32;
+            uint32_t v[32];
+            tmem_ld32(s_tmem + lane_addr + ch * 32, v);
+            tmem_wait_ld();
+            if (p.debug_skip) {
+                if (v[0] == 0x7fc12345u) ++below;
+                continue;
+            }
+            // per element: t = g - B_j, then the SIGN BITS of (hi_i - t) [set: below the window] and
+            // of (t - lo_i) [set: above] are shifted into two masks -- 5 instructions, no
+            // predicates.  Element c ends up at bit 31 - c.
+            uint32_t mb = 0u, ma = 0u;
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 bj = *reinterpret_cast<const float4 *>(colterm + ch * 32 + 4 * c4);
+                const float bjs[4] = {bj.x, bj.y, bj.z, bj.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float tt = __uint_as_float(v[4 * c4 + k]) - bjs[k];
+                    mb = __funnelshift_l(__float_as_uint(hi_i - tt), mb, 1);
+                    ma = __funnelshift_l(__float_as_uint(tt - lo_i), ma, 1);
+                }
+            }
+            const unsigned int nb = (unsigned)__popc(mb);
+            const uint32_t hmask = __brev(~(mb | ma));        // bit c <=> column c is listed
+            below += w * nb;
+            listed += w * (unsigned)__popc(hmask);
+            // rare path (~0.7 % of the pairs, ~0.2 hits per thread and chunk): each thread with
+            // hits reserves its slots with one shared-memory atomic, then walks its set bits; the
+            // value of column c is picked out of the 32 registers with a 5-level select tree
+            if (hmask) {
+                unsigned int slot = atomicAdd(sCount, (unsigned)__popc(hmask));
+                uint32_t hm = hmask;
+                while (hm) {
+                    const int c = __ffs(hm) - 1;
+                    hm &= hm - 1u;
+                    const float g = __uint_as_float(select32(v, c));
+                    PairEntry e;
+                    e.i = (uint32_t)i;
+                    e.jw = (uint32_t)(jbase + c) | (w == 2u ? 0x80000000u : 0u);
+                    e.dt = fmaf(-2.0f, g, r_i + __ldg(rj + ch * 32 + c));
+                    if (slot < (unsigned)SW_STAGE_CAP) {
+                        sBuf[slot] = e;
+                    } else {   // staging full (degenerate data): straight to global
+                        const unsigned long long gi = atomicAdd(p.cnt_len, 1ull);
+                        if (gi < p.list_cap) p.list[gi] = e;
+                        else *p.overflow = 1;
+                        atomicAdd(&sHist[hist_bin(e.dt, hlo, hscale)], w);
+                    }
+                    ++slot;
+                }
+            }
+        }
+    }
+    // all 256 classification threads, once per tile: flush the staged entries when the buffer is
+    // half full (or at the last tile) with one global reservation per flush
+    __device__ void flush(bool last) {
+        named_bar_sync(1, SW_EPI_THREADS);
+        if (tid256 == 0) {
+            const unsigned int have = min(*sCount, (unsigned)SW_STAGE_CAP);
+            const bool fl = have > (unsigned)SW_STAGE_CAP / 2 || (last && have > 0);
+            *sN = fl ? have : 0u;
+            if (fl) {
+                *sBase = atomicAdd(p.cnt_len, (unsigned long long)have);
+                *sCount = 0u;
+            }
+        }
+        named_bar_sync(2, SW_EPI_THREADS);
+        const unsigned int cnt = *sN;
+        if (cnt) {
+            const unsigned long long base = *sBase;
+            for (unsigned int e = tid256; e < cnt; e += SW_EPI_THREADS) {
+                const PairEntry pe = sBuf[e];
+                if (base + e < p.list_cap) p.list[base + e] = pe;
+                else *p.overflow = 1;
+                atomicAdd(&sHist[hist_bin(pe.dt, hlo, hscale)], (pe.jw >> 31) ? 2u : 1u);
+            }
+            named_bar_sync(3, SW_EPI_THREADS);
+        }
+    }
+    __device__ void finish() {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            below += __shfl_xor_sync(0xffffffffu, below, o);
+            listed += __shfl_xor_sync(0xffffffffu, listed, o);
+        }
+        if (lane == 0) {
+            if (below) atomicAdd(p.cnt_below, (unsigned long long)below);
+            if (listed) atomicAdd(p.cnt_listed, (unsigned long long)listed);
+        }
+        named_bar_sync(3, SW_EPI_THREADS);
+        for (int b = tid256; b < SW_HIST_BINS; b += SW_EPI_THREADS) {
+            const unsigned int v = sHist[b];
+            if (v) atomicAdd(&p.hist[b], (unsigned long long)v);
+        }
+    }
+};
+
 // The row tile X_I (A operand) lives in TENSOR MEMORY (columns 256..511: BF16 hi and lo,
 // two elements per 32-bit column), written by the classification warps when I changes.
 // That leaves all of shared memory to a 12-stage ring of column-tile boxes, deep enough to
@@ -116,12 +284,10 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
     uint8_t *tail = sRing + (size_t)SW_STAGES * SW_UNIT_BYTES;
     SweepBarriers *bars = reinterpret_cast<SweepBarriers *>(tail);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 256);
+    // tail + 260.. : staging counters, SW_STAGE_CAP staged entries, column terms, histogram
+    // (laid out by TileClassifier)
     unsigned int *sCount = reinterpret_cast<unsigned int *>(tail + 260);
-    unsigned int *sN = reinterpret_cast<unsigned int *>(tail + 264);
-    unsigned long long *sBase = reinterpret_cast<unsigned long long *>(tail + 272);
-    PairEntry *sBuf = reinterpret_cast<PairEntry *>(tail + 320);     // SW_STAGE_CAP entries
-    float *sCol = reinterpret_cast<float *>(tail + 320 + SW_STAGE_CAP * sizeof(PairEntry));   // [2][128]
-    unsigned int *sHist = reinterpret_cast<unsigned int *>(sCol + 256);                        // [SW_HIST_BINS]
+    unsigned int *sHist = reinterpret_cast<unsigned int *>(tail + 320 + SW_STAGE_CAP * sizeof(PairEntry) + 1024);
 
     const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
     const long long NT = p.t_end - p.t_begin;
@@ -237,42 +403,16 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         // ===================== classification warpgroups =====================
-        // With D~ = r_i + r_j - 2 g and |D~ - D| <= c (r_i + r_j):
-        //   certainly above the window  <=>  g < (1-c)/2 (r_i + r_j) - whi/2
-        //   certainly below the window  <=>  g > (1+c)/2 (r_i + r_j) - wlo/2
-        // Written with t = g - B_j, B_j = (1-c)/2 r_j (one shared-memory value per column):
-        //   above  <=>  t < lo_i,   lo_i = (1-c)/2 r_i - whi/2
-        //   below  <=>  t > hi_i,   hi_i = (1+c)/2 r_i + c rmax - wlo/2   (rmax >= r_j: conservative)
-        // and everything else is listed.  In the loop: d = t - mid_i; below <=> d > half_i, listed
-        // <=> |d| <= half_i.  lo_i / hi_i are moved outwards by `slack` (>> the fp32 rounding of
-        // these few operations); that only enlarges the listed set, whose members are resolved
-        // from their own D~ later, so the three classes stay an exact partition of the pairs.
-        const int q = warp & 3;
-        const int wg = (warp - 4) >> 2;
-        const int row = q * 32 + lane;
-        const int tid256 = (warp - 4) * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        TileClassifier tc(p, tail, warp, lane);
+        const int wg = tc.wg, row = tc.row;
+        const uint32_t lane_addr = tc.lane_addr;
         const int wpr = p.kblocks * 32;             // 32-bit words per row of Xh / Xl
-        const float cm = 0.5f * (1.0f - p.c_half), cp = 0.5f * (1.0f + p.c_half);
-        const float rmax = __ldg(p.rmax);
-        // histogram range of the listed D~: the window widened by the largest possible error term
-        const float hpad = 4.0f * p.c_half * rmax + 1e-5f * fmaxf(fabsf(p.wlo), fabsf(p.whi));
-        const float hlo = p.wlo - hpad;
-        const float hscale = (float)SW_HIST_BINS / fmaxf((p.whi + hpad) - hlo, 1e-30f);
-        if (blockIdx.x == 0 && tid256 == 0) {
-            p.hparams_out[0] = hlo;
-            p.hparams_out[1] = hscale;
-        }
-        unsigned int below = 0u, listed = 0u;
         int prevI = -1, aseg = 0;
         long long jj = 0;
         int I = 0, J = 0;
         if (my0 < my1) {
             tri_tile(my0, p.T, I, J);
-            if (tid256 < 128) {
-                const long long j = (long long)J * 128 + tid256;
-                sCol[tid256] = j < p.n ? cm * p.r[j] : INFINITY;
-            }
+            tc.publish_cols(J, 0);
             named_bar_sync(1, SW_EPI_THREADS);
         }
         for (long long t = my0; t < my1; ++t, ++jj) {
@@ -302,135 +442,18 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                 prevI = I;
             }
             const int b = (int)(jj & 1);
-            const unsigned int w = (I == J) ? 1u : 2u;
-            const float r_i = p.r[i];
-            const float *rj = p.r + (size_t)J * 128;
-            const bool row_ok = i < p.n;
-            const float slack = (r_i + rmax) * 9.5367431640625e-07f;   // 2^-20
-            const float lo_i = cm * r_i - 0.5f * p.whi - slack;
-            const float hi_i = cp * r_i + p.c_half * rmax - 0.5f * p.wlo + slack;
-            // rows beyond n: nothing is below (d = -inf) and nothing is listed (|d| = inf > 0)
-            const float mid_i = row_ok ? 0.5f * (lo_i + hi_i) : INFINITY;
-            const float half_i = row_ok ? 0.5f * (hi_i - lo_i) + slack : 0.0f;
-            const float *colterm = sCol + b * 128;
             mbar_wait(&bars->s_full[b], (uint32_t)((jj >> 1) & 1));
             tcgen05_fence_after();
-#pragma unroll 1
-            for (int cc = 0; cc < 2; ++cc) {
-                const int ch = wg * 2 + cc;
-                const long long jbase = (long long)J * 128 + ch * 32;
-                const uint32_t s_addr = tmem + b * 128 + lane_addr + ch * 32;
-                uint32_t v[32];
-                tmem_ld32(s_addr, v);
-                tmem_wait_ld();
-                if (p.debug_skip) {
-                    if (v[0] == 0x7fc12345u) ++below;
-                    continue;
-                }
-                // common case first: count the pairs below and find the distance of the closest
-                // value to the listing interval [lo_i, hi_i] = mid_i -+ half_i; the bit mask of
-                // listed columns is only built when some value falls inside (every ~5th chunk)
-                unsigned int nb0 = 0u, nb1 = 0u;
-                float near0 = INFINITY, near1 = INFINITY;
-#pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 bj = *reinterpret_cast<const float4 *>(colterm + ch * 32 + 4 * c4);
-                    const float d0 = (__uint_as_float(v[4 * c4]) - bj.x) - mid_i;
-                    const float d1 = (__uint_as_float(v[4 * c4 + 1]) - bj.y) - mid_i;
-                    const float d2 = (__uint_as_float(v[4 * c4 + 2]) - bj.z) - mid_i;
-                    const float d3 = (__uint_as_float(v[4 * c4 + 3]) - bj.w) - mid_i;
-                    nb0 += d0 > half_i ? 1u : 0u;
-                    nb1 += d1 > half_i ? 1u : 0u;
-                    nb0 += d2 > half_i ? 1u : 0u;
-                    nb1 += d3 > half_i ? 1u : 0u;
-                    near0 = fminf(near0, fminf(fabsf(d0), fabsf(d2)));
-                    near1 = fminf(near1, fminf(fabsf(d1), fabsf(d3)));
-                }
-                const unsigned int nb = nb0 + nb1;
-                uint32_t hmask = 0u;
-                if (fminf(near0, near1) <= half_i) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float dd = (__uint_as_float(v[c]) - colterm[ch * 32 + c]) - mid_i;
-                        hmask |= (fabsf(dd) <= half_i ? 1u : 0u) << c;
-                    }
-                }
-                below += w * nb;
-                listed += w * (unsigned)__popc(hmask);
-                // rare path (~0.7 % of the pairs, ~0.2 hits per thread and chunk): each thread with
-                // hits reserves its slots with one shared-memory atomic, then walks its set bits; the
-                // value of column c is picked out of the 32 registers with a 5-level select tree
-                if (hmask) {
-                    unsigned int slot = atomicAdd(sCount, (unsigned)__popc(hmask));
-                    uint32_t hm = hmask;
-                    while (hm) {
-                        const int c = __ffs(hm) - 1;
-                        hm &= hm - 1u;
-                        const float g = __uint_as_float(select32(v, c));
-                        PairEntry e;
-                        e.i = (uint32_t)i;
-                        e.jw = (uint32_t)(jbase + c) | (w == 2u ? 0x80000000u : 0u);
-                        e.dt = fmaf(-2.0f, g, r_i + __ldg(rj + ch * 32 + c));
-                        if (slot < (unsigned)SW_STAGE_CAP) {
-                            sBuf[slot] = e;
-                        } else {   // staging full (degenerate data): straight to global
-                            const unsigned long long gi = atomicAdd(p.cnt_len, 1ull);
-                            if (gi < p.list_cap) p.list[gi] = e;
-                            else *p.overflow = 1;
-                            atomicAdd(&sHist[hist_bin(e.dt, hlo, hscale)], w);
-                        }
-                        ++slot;
-                    }
-                }
-            }
+            tc.classify(tmem + b * 128, i, J, (I == J) ? 1u : 2u, b);
             // S buffer b may be overwritten by the GEMM of tile jj + 2
             tcgen05_fence_before();
             mbar_arrive(&bars->s_empty[b]);
-            // column terms of the next tile (published by the barrier below)
+            // column terms of the next tile (published by the barrier in flush)
             next_tile(I, J, p.T);
-            if (t + 1 < my1 && tid256 < 128) {
-                const long long j = (long long)J * 128 + tid256;
-                sCol[(b ^ 1) * 128 + tid256] = j < p.n ? cm * p.r[j] : INFINITY;
-            }
-            // flush the staged entries when the buffer is half full (or at the last tile):
-            // one global reservation per flush, not per tile
-            named_bar_sync(1, SW_EPI_THREADS);
-            if (tid256 == 0) {
-                const unsigned int have = min(*sCount, (unsigned)SW_STAGE_CAP);
-                const bool flush = have > (unsigned)SW_STAGE_CAP / 2 || (t + 1 == my1 && have > 0);
-                *sN = flush ? have : 0u;
-                if (flush) {
-                    *sBase = atomicAdd(p.cnt_len, (unsigned long long)have);
-                    *sCount = 0u;
-                }
-            }
-            named_bar_sync(2, SW_EPI_THREADS);
-            const unsigned int cnt = *sN;
-            if (cnt) {
-                const unsigned long long base = *sBase;
-                for (unsigned int e = tid256; e < cnt; e += SW_EPI_THREADS) {
-                    const PairEntry pe = sBuf[e];
-                    if (base + e < p.list_cap) p.list[base + e] = pe;
-                    else *p.overflow = 1;
-                    atomicAdd(&sHist[hist_bin(pe.dt, hlo, hscale)], (pe.jw >> 31) ? 2u : 1u);
-                }
-                named_bar_sync(3, SW_EPI_THREADS);
-            }
+            if (t + 1 < my1) tc.publish_cols(J, b ^ 1);
+            tc.flush(t + 1 == my1);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            below += __shfl_xor_sync(0xffffffffu, below, o);
-            listed += __shfl_xor_sync(0xffffffffu, listed, o);
-        }
-        if (lane == 0) {
-            if (below) atomicAdd(p.cnt_below, (unsigned long long)below);
-            if (listed) atomicAdd(p.cnt_listed, (unsigned long long)listed);
-        }
-        named_bar_sync(3, SW_EPI_THREADS);
-        for (int b = tid256; b < SW_HIST_BINS; b += SW_EPI_THREADS) {
-            const unsigned int v = sHist[b];
-            if (v) atomicAdd(&p.hist[b], (unsigned long long)v);
-        }
+        tc.finish();
     }
 
     tcgen05_fence_before();
@@ -438,6 +461,225 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc(tmem, SW_TMEM_COLS);
+    }
+}
+
+// =====================================================================================
+// CTA-pair sweep (cta_group::2).  The single-CTA kernel above is bound by tensor-memory reads:
+// its A operand comes from TMEM (4 KB per 128x128x16 MMA at 64 B/cycle = the whole MMA time)
+// next to the 64 KB per tile the classification reads.  Here two CTAs of a cluster own 256
+// rows (row tiles 2 I2 and 2 I2 + 1), each keeps its 128-row A tile (BF16 hi and lo) in
+// SHARED memory, the leader issues M = 256 MMAs whose B operand is split between the two
+// CTAs (each stages 64 of the 128 rows of X_J), and tensor memory is only read by the
+// classification.  Shared-memory traffic per SM and MMA: 4 KB of A + 2 KB of B.
+// Tiles: pair rows I2 = 0 .. ceil(T/2)-1, columns J = 2 I2 .. T-1; the half tile below the
+// diagonal (row tile 2 I2 + 1 against column tile 2 I2) is computed but not classified.
+// =====================================================================================
+constexpr int SW2_STAGES = 4;
+constexpr int SW2_KB = 4;                       // K blocks of 64 BF16 staged for A (DP <= 256)
+constexpr uint32_t SW2_TMEM_COLS = 256;         // two 128-column g buffers
+
+struct Sweep2Barriers {
+    uint64_t full[SW2_STAGES], empty[SW2_STAGES];
+    uint64_t a_full, a_empty;
+    uint64_t s_full[2], s_empty[2];
+};
+
+// pair tile t (row-major over I2, J >= 2 I2) -> (I2, J)
+__host__ __device__ inline void pair_tile(long long t, int T, int &I2, int &J) {
+    int i2 = 0;
+    while (t >= (long long)(T - 2 * i2)) {
+        t -= T - 2 * i2;
+        ++i2;
+    }
+    I2 = i2;
+    J = 2 * i2 + (int)t;
+}
+__device__ __forceinline__ void next_pair_tile(int &I2, int &J, int T) {
+    if (++J == T) {
+        ++I2;
+        J = 2 * I2;
+    }
+}
+static int64_t num_pair_tiles(int64_t T) {
+    int64_t nt = 0;
+    for (int64_t i2 = 0; 2 * i2 < T; ++i2) nt += T - 2 * i2;
+    return nt;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SW_THREADS, 1)
+sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
+                 const __grid_constant__ CUtensorMap mapXh64, const __grid_constant__ CUtensorMap mapXl64,
+                 const SweepParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *sA = smem;                                              // [hi | lo] x SW2_KB x 16 KB
+    uint8_t *sRing = sA + (size_t)2 * SW2_KB * SW_UNIT_BYTES;        // SW2_STAGES x [64 rows hi | 64 rows lo]
+    uint8_t *tail = sRing + (size_t)SW2_STAGES * SW_UNIT_BYTES;
+    Sweep2Barriers *bars = reinterpret_cast<Sweep2Barriers *>(tail);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 256);
+    unsigned int *sCount = reinterpret_cast<unsigned int *>(tail + 260);
+    unsigned int *sHist = reinterpret_cast<unsigned int *>(tail + 320 + SW_STAGE_CAP * sizeof(PairEntry) + 1024);
+
+    const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const long long NT = p.t_end - p.t_begin;
+    const int ncl = (int)gridDim.x / 2, cl = (int)blockIdx.x / 2;
+    const long long my0 = p.t_begin + NT * cl / ncl;
+    const long long my1 = p.t_begin + NT * (cl + 1) / ncl;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SW2_STAGES; ++s) {
+            mbar_init(&bars->full[s], 1);            // leader: one expect_tx arrival, bytes from both CTAs
+            mbar_init(&bars->empty[s], 1);           // multicast commit
+        }
+        mbar_init(&bars->a_full, 1);                 // leader
+        mbar_init(&bars->a_empty, 1);                // multicast commit
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars->s_full[b], 1);                        // multicast commit
+            mbar_init(&bars->s_empty[b], 2 * SW_EPI_THREADS);      // leader: both CTAs' classification threads
+        }
+        *sCount = 0u;
+        fence_barrier_init();
+        fence_proxy_async();
+        tma_prefetch_desc(&mapXh);
+        tma_prefetch_desc(&mapXl);
+        tma_prefetch_desc(&mapXh64);
+        tma_prefetch_desc(&mapXl64);
+    }
+    for (int b = threadIdx.x; b < SW_HIST_BINS; b += SW_THREADS) sHist[b] = 0u;
+    if (warp == 1) tmem_alloc_pair(tmem_slot, SW2_TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();            // peer barriers are initialised before anyone signals them
+    tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == 0) {
+            // ===================== TMA producer (both CTAs) =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t full0_addr = mapa_shared(smem_u32(&bars->full[0]), 0);
+            const uint32_t a_full_addr = mapa_shared(smem_u32(&bars->a_full), 0);
+            int prevI2 = -1, aseg = 0;
+            int I2 = 0, J = 0;
+            if (my0 < my1) pair_tile(my0, p.T, I2, J);
+            for (long long t = my0; t < my1; ++t, next_pair_tile(I2, J, p.T)) {
+                if (I2 != prevI2) {
+                    // this CTA's 128 rows of the pair row, hi and lo
+                    if (aseg > 0) mbar_wait(&bars->a_empty, (uint32_t)((aseg - 1) & 1));
+                    const int arow = (2 * I2 + (int)rank) * 128;
+                    if (elect_one_sync()) {
+                        if (leader) mbar_expect_tx(&bars->a_full, 2u * 2u * (uint32_t)p.kblocks * SW_UNIT_BYTES);
+                        for (int kb = 0; kb < p.kblocks; ++kb) {
+                            tma_load_2d_pair(sA + (size_t)kb * SW_UNIT_BYTES, &mapXh, a_full_addr, kb * 64, arow);
+                            tma_load_2d_pair(sA + (size_t)(SW2_KB + kb) * SW_UNIT_BYTES, &mapXl, a_full_addr, kb * 64, arow);
+                        }
+                    }
+                    __syncwarp();
+                    ++aseg;
+                    prevI2 = I2;
+                }
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(&bars->empty[stage], phase ^ 1);      // local: multicast commit of the leader
+                    if (elect_one_sync()) {
+                        if (leader) mbar_expect_tx(&bars->full[stage], 2u * SW_UNIT_BYTES);
+                        uint8_t *dst = sRing + (size_t)stage * SW_UNIT_BYTES;
+                        const uint32_t fa = full0_addr + 8u * (uint32_t)stage;
+                        tma_load_2d_pair(dst, &mapXh64, fa, kb * 64, J * 128 + (int)rank * 64);
+                        tma_load_2d_pair(dst + SW_UNIT_BYTES / 2, &mapXl64, fa, kb * 64, J * 128 + (int)rank * 64);
+                    }
+                    __syncwarp();
+                    if (++stage == SW2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1 && leader) {
+            // ===================== MMA issuer (leader CTA only) =====================
+            const uint32_t idesc = make_idesc(FMT_BF16, 256, 128);
+            int stage = 0;
+            uint32_t phase = 0;
+            int prevI2 = -1, aseg = 0;
+            long long jj = 0;
+            int I2 = 0, J = 0;
+            if (my0 < my1) pair_tile(my0, p.T, I2, J);
+            for (long long t = my0; t < my1; ++t, ++jj, next_pair_tile(I2, J, p.T)) {
+                if (I2 != prevI2) {
+                    if (prevI2 != -1 && elect_one_sync()) tcgen05_commit_pair(&bars->a_empty);   // old A tiles are free
+                    __syncwarp();
+                    mbar_wait(&bars->a_full, (uint32_t)(aseg & 1));
+                    tcgen05_fence_after();
+                    ++aseg;
+                    prevI2 = I2;
+                }
+                const int b = (int)(jj & 1);
+                if (jj >= 2) {
+                    mbar_wait(&bars->s_empty[b], (uint32_t)(((jj >> 1) - 1) & 1));
+                    tcgen05_fence_after();
+                }
+                const uint32_t d_tmem = tmem + b * 128;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    const uint64_t ah = make_kmajor_sw128_desc(smem_u32(sA + (size_t)kb * SW_UNIT_BYTES));
+                    const uint64_t al = make_kmajor_sw128_desc(smem_u32(sA + (size_t)(SW2_KB + kb) * SW_UNIT_BYTES));
+                    mbar_wait(&bars->full[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t slot_addr = smem_u32(sRing + (size_t)stage * SW_UNIT_BYTES);
+                    const uint64_t bh = make_kmajor_sw128_desc(slot_addr);
+                    const uint64_t bl = make_kmajor_sw128_desc(slot_addr + SW_UNIT_BYTES / 2);
+                    if (elect_one_sync()) {
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ss(d_tmem, ah + 2 * k4, bh + 2 * k4, idesc, (kb | k4) != 0);   // hi.hi
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ss(d_tmem, al + 2 * k4, bh + 2 * k4, idesc, 1u);             // lo.hi
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ss(d_tmem, ah + 2 * k4, bl + 2 * k4, idesc, 1u);             // hi.lo
+                        tcgen05_commit_pair(&bars->empty[stage]);
+                        if (kb == p.kblocks - 1) tcgen05_commit_pair(&bars->s_full[b]);
+                    }
+                    __syncwarp();
+                    if (++stage == SW2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        // ===================== classification warpgroups (both CTAs, own 128 rows) =====================
+        TileClassifier tc(p, tail, warp, lane);
+        const uint32_t s_empty_addr0 = mapa_shared(smem_u32(&bars->s_empty[0]), 0);
+        const uint32_t s_empty_addr1 = mapa_shared(smem_u32(&bars->s_empty[1]), 0);
+        long long jj = 0;
+        int I2 = 0, J = 0;
+        if (my0 < my1) {
+            pair_tile(my0, p.T, I2, J);
+            tc.publish_cols(J, 0);
+            named_bar_sync(1, SW_EPI_THREADS);
+        }
+        for (long long t = my0; t < my1; ++t, ++jj) {
+            const int I = 2 * I2 + (int)rank;
+            const long long i = (long long)I * 128 + tc.row;
+            const int b = (int)(jj & 1);
+            const unsigned int w = J > I ? 2u : (J == I ? 1u : 0u);
+            mbar_wait(&bars->s_full[b], (uint32_t)((jj >> 1) & 1));
+            tcgen05_fence_after();
+            tc.classify(tmem + b * 128, i, J, w, b);
+            // g buffer b may be overwritten by the GEMM of tile jj + 2
+            tcgen05_fence_before();
+            mbar_arrive_cluster(b ? s_empty_addr1 : s_empty_addr0);
+            next_pair_tile(I2, J, p.T);
+            if (t + 1 < my1) tc.publish_cols(J, b ^ 1);
+            tc.flush(t + 1 == my1);
+        }
+        tc.finish();
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();            // no CTA leaves while its partner may still signal / read it
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc_pair(tmem, SW2_TMEM_COLS);
     }
 }
 
@@ -714,15 +956,15 @@ static int window_select2(stein_ctx *ctx, const void *src, unsigned long long m_
 }
 
 // Window keys from the pilot sample: [lo, hi] brackets the sample quantiles at rank_lo / rank_hi.
-// Two histogram passes (every rank holds the same sample, so nothing is all-reduced): 14 bits of
-// the full key range, then the bins of the two ranks split 16384 ways.
+// Two histogram passes: 14 bits of the full key range, then the bins of the two ranks split
+// 16384 ways.  keys_dev / m are this rank's slice of the sample; the counts are all-reduced.
 int pilot_window(stein_ctx *ctx, const uint32_t *keys_dev, int64_t m, uint64_t rank_lo, uint64_t rank_hi,
                  uint32_t *lo_key, uint32_t *hi_key) {
     if (!g_arena.counters) STEIN_TRY(ensure_arena(ctx, 0, 0, 0));
     MedianArena &A = g_arena;
     KeyWindow w = {0u, 18u, (uint32_t)HIST_MAX_BINS};
     for (int pass = 0; pass < 2; ++pass) {
-        STEIN_TRY(window_counts<2>(ctx, keys_dev, (unsigned long long)m, w.key_lo, w.shift, w.nbins, false));
+        STEIN_TRY(window_counts<2>(ctx, keys_dev, (unsigned long long)m, w.key_lo, w.shift, w.nbins, true));
         uint64_t cum = A.h_pinned[0];
         if (rank_lo < cum) return 1;
         int64_t blo = -1, bhi = -1;
@@ -758,7 +1000,9 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     STEIN_TRY(ensure_arena(ctx, rows, DP, pairs));
     MedianArena &A = g_arena;
     const int world = ctx->has_comm ? ctx->comm.world : 1, rank = ctx->has_comm ? ctx->comm.rank : 0;
-    const int64_t ntiles = T * (T + 1) / 2;
+    // CTA-pair sweep unless the single-CTA kernel is asked for (STEIN_MEDIAN_TC1, tests / comparison)
+    const bool pair = ctx->median_impl != STEIN_MEDIAN_TC1 && ctx->num_sms >= 2 && DP <= 64 * SW2_KB;
+    const int64_t ntiles = pair ? num_pair_tiles(T) : T * (T + 1) / 2;
     const int64_t t0 = ntiles * rank / world, t1 = ntiles * (rank + 1) / world;
     const float c_half = eps_coeff(d);
 
@@ -797,16 +1041,18 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     p.overflow = d_overflow;
     p.list = A.list;
     p.list_cap = A.list_cap;
-    const size_t smem = 1024 + (size_t)SW_STAGES * SW_UNIT_BYTES + 320 + (size_t)SW_STAGE_CAP * sizeof(PairEntry) + 1024 +
-                        (size_t)SW_HIST_BINS * 4 + 64;
+    const size_t tail_bytes = 320 + (size_t)SW_STAGE_CAP * sizeof(PairEntry) + 1024 + (size_t)SW_HIST_BINS * 4 + 64;
+    const size_t smem1 = 1024 + (size_t)SW_STAGES * SW_UNIT_BYTES + tail_bytes;
+    const size_t smem2 = 1024 + (size_t)(2 * SW2_KB + SW2_STAGES) * SW_UNIT_BYTES + tail_bytes;
     static bool attr_set = false;
     if (!attr_set) {
         STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(sweep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)smem));
+                                                   (int)smem1));
+        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(sweep2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)smem2));
         attr_set = true;
     }
     if (t1 > t0) {
-        const int grid = (int)std::min<int64_t>(ctx->num_sms, t1 - t0);
         RegionTimer timer(ctx, STEIN_REGION_SWEEP);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (p.debug_skip) {
@@ -814,14 +1060,23 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
             cudaEventCreate(&e1);
             cudaEventRecord(e0, ctx->stream);
         }
-        sweep_tc_kernel<<<grid, SW_THREADS, smem, ctx->stream>>>(mapXh, mapXl, p);
+        if (pair) {
+            CUtensorMap mapXh64, mapXl64;
+            STEIN_TRY(make_tensor_map_2d(ctx, &mapXh64, A.Xh, 2, (uint64_t)DP, (uint64_t)rows, (uint64_t)DP * 2, 64));
+            STEIN_TRY(make_tensor_map_2d(ctx, &mapXl64, A.Xl, 2, (uint64_t)DP, (uint64_t)rows, (uint64_t)DP * 2, 64));
+            const int clusters = (int)std::min<int64_t>(ctx->num_sms / 2, t1 - t0);
+            sweep2_tc_kernel<<<2 * clusters, SW_THREADS, smem2, ctx->stream>>>(mapXh, mapXl, mapXh64, mapXl64, p);
+        } else {
+            const int grid = (int)std::min<int64_t>(ctx->num_sms, t1 - t0);
+            sweep_tc_kernel<<<grid, SW_THREADS, smem1, ctx->stream>>>(mapXh, mapXl, p);
+        }
         STEIN_CHECK_LAUNCH(ctx);
         if (p.debug_skip) {
             cudaEventRecord(e1, ctx->stream);
             cudaEventSynchronize(e1);
             float ms = 0.f;
             cudaEventElapsedTime(&ms, e0, e1);
-            fprintf(stderr, "[debug] sweep_tc_kernel without classification: %.3f ms\n", ms);
+            fprintf(stderr, "[debug] tcgen05 sweep without classification: %.3f ms\n", ms);
             cudaEventDestroy(e0);
             cudaEventDestroy(e1);
         }

@@ -34,6 +34,7 @@ constexpr int PC_SMEM_PER_WARP = 2 * 32 * PC_ROW * 4;
 
 // SRC 0: io = uint2 (i, jw) list, rewritten in place as (key, weight)   [band of median_tc.cu]
 // SRC 1: pairs drawn from splitmix64(seed + s), io = u32 keys[s]         [pilot of median.cu]
+//        (seed already includes the index of the first sample of this launch)
 template <int SRC>
 __global__ void __launch_bounds__(PC_WARPS * 32, 4)
 pair_chain_kernel(void *__restrict__ io, unsigned long long m, const float *__restrict__ X,

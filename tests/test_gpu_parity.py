@@ -111,10 +111,11 @@ def _median_with(ctx, X, impl):
 
 
 @pytest.mark.parametrize("n,d,kind", [(4096, 256, "gauss"), (5000, 128, "gauss"), (4500, 250, "small"),
-                                      (6000, 256, "clusters"), (4100, 256, "dup")])
+                                      (6000, 256, "clusters"), (4100, 256, "dup"), (4225, 250, "gauss")])
 def test_median_tensor_core_route_bit_exact(ctx, n, d, kind):
-    """tcgen05 filter sweep + contract recomputation of the candidates == the all-FFMA
-    route == the oracle (radix route), bit for bit."""
+    """tcgen05 filter sweep (CTA-pair kernel and single-CTA kernel) + contract recomputation
+    of the candidates == the all-FFMA route == the oracle (radix route), bit for bit.
+    n = 4225 has an odd number of 128-row tiles (the last pair row is half empty)."""
     from stein_b200 import _lib
     rng = np.random.default_rng(n + d)
     X = rng.standard_normal((n, d)).astype(np.float32)
@@ -125,8 +126,11 @@ def test_median_tensor_core_route_bit_exact(ctx, n, d, kind):
     elif kind == "dup":
         X[n // 2:] = X[:n - n // 2]
     tc = _median_with(ctx, X, _lib.MEDIAN_TC)
+    tc1 = _median_with(ctx, X, _lib.MEDIAN_TC1)
     ff = _median_with(ctx, X, _lib.MEDIAN_FFMA)
-    assert tc[0].tobytes() == ff[0].tobytes()
+    assert tc[0].tobytes() == ff[0].tobytes() == tc1[0].tobytes()
+    assert (tc1[1][0].tobytes(), tc1[1][1].tobytes()) == (ff[1][0].tobytes(), ff[1][1].tobytes())
+    assert tc1[2] == 1
     assert (tc[1][0].tobytes(), tc[1][1].tobytes()) == (ff[1][0].tobytes(), ff[1][1].tobytes())
     if n <= 4500:
         m_ref, mid_ref = orc.median_chain(X, radix=True)
