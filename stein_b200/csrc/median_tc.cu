@@ -35,8 +35,16 @@ constexpr int SW_THREADS = 384;
 constexpr int SW_EPI_THREADS = 256;
 constexpr int SW_STAGES = 12;
 constexpr uint32_t SW_UNIT_BYTES = 128 * 128;
-constexpr int SW_STAGE_CAP = 1024;          // entries staged in shared memory between flushes
+constexpr int SW_EPI_WARPS = SW_EPI_THREADS / 32;
+constexpr int SW_WARP_CAP = 128;            // entries a classification warp stages between two flushes
+// shared-memory tail after the operand buffers (both sweep kernels): barriers at +0 (256 B),
+// tensor-memory base at +256, per-warp staging counters at +288, then the arrays below
+constexpr size_t SW_TAIL_COUNTS = 288;
+constexpr size_t SW_TAIL_BUF = 320;                                             // PairEntry [warps][SW_WARP_CAP]
+constexpr size_t SW_TAIL_COL = SW_TAIL_BUF + (size_t)SW_EPI_WARPS * SW_WARP_CAP * 12;   // float [warps][64]
+constexpr size_t SW_TAIL_HIST = SW_TAIL_COL + (size_t)SW_EPI_WARPS * 64 * 4;    // u32 [SW_HIST_BINS]
 constexpr int SW_HIST_BINS = 4096;          // histogram of the listed D~ (locates t~ without extra passes)
+constexpr size_t SW_TAIL_BYTES = SW_TAIL_HIST + (size_t)SW_HIST_BINS * 4 + 64;
 constexpr uint32_t SW_TMEM_COLS = 512;
 constexpr uint32_t SW_TMEM_AH = 256, SW_TMEM_AL = 384;   // A operand (row tile, BF16 hi / lo) in TMEM
 
@@ -112,29 +120,29 @@ __device__ __forceinline__ void next_tile(int &I, int &J, int T) {
 // their own D~ later.  "below" and "above" are decided by the sign of one subtraction each, so
 // the three classes are an exact partition of the pairs (t = -0.0 cannot occur with lo_i > 0;
 // a zero difference has a clear sign bit and counts as listed).
+// Each classification warp is self-contained: it derives the column terms of its own 64 columns
+// and stages its listed pairs in its own shared-memory buffer, so the warps of a CTA never wait
+// for each other (the block-wide named barriers of the first version cost 10 % of the sweep).
 struct TileClassifier {
     const SweepParams &p;
-    PairEntry *sBuf;
-    float *sCol;                 // [2][128] column terms B_j of the current / next tile
-    unsigned int *sHist, *sCount, *sN;
-    unsigned long long *sBase;
-    int wg, row, tid256, lane;
+    PairEntry *wBuf;             // [SW_WARP_CAP] staging of this warp
+    float *wCol;                 // [64] column terms B_j of this warp's two 32-column chunks
+    unsigned int *sHist, *wCount;
+    int wg, row, lane;
     uint32_t lane_addr;
     float cm, cp, rmax, hlo, hscale;
     unsigned int below, listed;
 
     __device__ TileClassifier(const SweepParams &p_, uint8_t *tail, int warp, int lane_)
         : p(p_), lane(lane_), below(0u), listed(0u) {
-        sCount = reinterpret_cast<unsigned int *>(tail + 260);
-        sN = reinterpret_cast<unsigned int *>(tail + 264);
-        sBase = reinterpret_cast<unsigned long long *>(tail + 272);
-        sBuf = reinterpret_cast<PairEntry *>(tail + 320);
-        sCol = reinterpret_cast<float *>(tail + 320 + SW_STAGE_CAP * sizeof(PairEntry));
-        sHist = reinterpret_cast<unsigned int *>(sCol + 256);
+        const int ew = warp - 4;                     // classification warp index 0..7
+        wCount = reinterpret_cast<unsigned int *>(tail + SW_TAIL_COUNTS) + ew;
+        wBuf = reinterpret_cast<PairEntry *>(tail + SW_TAIL_BUF) + (size_t)ew * SW_WARP_CAP;
+        wCol = reinterpret_cast<float *>(tail + SW_TAIL_COL) + ew * 64;
+        sHist = reinterpret_cast<unsigned int *>(tail + SW_TAIL_HIST);
         const int q = warp & 3;
-        wg = (warp - 4) >> 2;
+        wg = ew >> 2;
         row = q * 32 + lane;
-        tid256 = (warp - 4) * 32 + lane;
         lane_addr = (uint32_t)(q * 32) << 16;
         cm = 0.5f * (1.0f - p.c_half);
         cp = 0.5f * (1.0f + p.c_half);
@@ -143,30 +151,31 @@ struct TileClassifier {
         const float hpad = 4.0f * p.c_half * rmax + 1e-5f * fmaxf(fabsf(p.wlo), fabsf(p.whi));
         hlo = p.wlo - hpad;
         hscale = (float)SW_HIST_BINS / fmaxf((p.whi + hpad) - hlo, 1e-30f);
-        if (blockIdx.x == 0 && tid256 == 0) {
+        if (blockIdx.x == 0 && ew == 0 && lane == 0) {
             p.hparams_out[0] = hlo;
             p.hparams_out[1] = hscale;
         }
-    }
-    // column terms of column tile J into buffer b (visible after the next named barrier)
-    __device__ void publish_cols(int J, int b) {
-        if (tid256 < 128) {
-            const long long j = (long long)J * 128 + tid256;
-            sCol[b * 128 + tid256] = j < p.n ? cm * p.r[j] : INFINITY;
-        }
+        if (lane == 0) *wCount = 0u;
+        __syncwarp();
     }
     // this thread's row i against the 128 columns of tile J; the g tile sits in TMEM at `s_tmem`
     // (column 0 of the buffer, lane field 0); w = weight of the tile (0: nothing to do)
-    __device__ void classify(uint32_t s_tmem, long long i, int J, unsigned int w, int b) {
+    __device__ void classify(uint32_t s_tmem, long long i, int J, unsigned int w) {
         if (w == 0u) return;
         const bool row_ok = i < p.n;
         const float r_i = row_ok ? p.r[i] : 0.0f;
-        const float *rj = p.r + (size_t)J * 128;
+        const float *rj = p.r + (size_t)J * 128 + wg * 64;       // this warp's 64 columns
+        // column terms (the previous tile's are no longer read: same warp, program order)
+        {
+            const long long j0 = (long long)J * 128 + wg * 64 + lane;
+            wCol[lane] = j0 < p.n ? cm * __ldg(rj + lane) : INFINITY;
+            wCol[32 + lane] = j0 + 32 < p.n ? cm * __ldg(rj + 32 + lane) : INFINITY;
+            __syncwarp();
+        }
         const float slack = (r_i + rmax) * 9.5367431640625e-07f;   // 2^-20
         // rows beyond n: lo_i = hi_i = +inf, so every pair is "above" (neither counted nor listed)
         const float lo_i = row_ok ? cm * r_i - 0.5f * p.whi - 2.0f * slack : INFINITY;
         const float hi_i = row_ok ? cp * r_i + p.c_half * rmax - 0.5f * p.wlo + 2.0f * slack : INFINITY;
-        const float *colterm = sCol + b * 128;
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
             const int ch = wg * 2 + cc;
@@ -184,7 +193,7 @@ struct TileClassifier {
             uint32_t mb = 0u, ma = 0u;
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
-                const float4 bj = *reinterpret_cast<const float4 *>(colterm + ch * 32 + 4 * c4);
+                const float4 bj = *reinterpret_cast<const float4 *>(wCol + cc * 32 + 4 * c4);
                 const float bjs[4] = {bj.x, bj.y, bj.z, bj.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -193,15 +202,14 @@ struct TileClassifier {
                     ma = __funnelshift_l(__float_as_uint(tt - lo_i), ma, 1);
                 }
             }
-            const unsigned int nb = (unsigned)__popc(mb);
             const uint32_t hmask = __brev(~(mb | ma));        // bit c <=> column c is listed
-            below += w * nb;
+            below += w * (unsigned)__popc(mb);
             listed += w * (unsigned)__popc(hmask);
             // rare path (~0.7 % of the pairs, ~0.2 hits per thread and chunk): each thread with
             // hits reserves its slots with one shared-memory atomic, then walks its set bits; the
             // value of column c is picked out of the 32 registers with a 5-level select tree
             if (hmask) {
-                unsigned int slot = atomicAdd(sCount, (unsigned)__popc(hmask));
+                unsigned int slot = atomicAdd(wCount, (unsigned)__popc(hmask));
                 uint32_t hm = hmask;
                 while (hm) {
                     const int c = __ffs(hm) - 1;
@@ -210,9 +218,9 @@ struct TileClassifier {
                     PairEntry e;
                     e.i = (uint32_t)i;
                     e.jw = (uint32_t)(jbase + c) | (w == 2u ? 0x80000000u : 0u);
-                    e.dt = fmaf(-2.0f, g, r_i + __ldg(rj + ch * 32 + c));
-                    if (slot < (unsigned)SW_STAGE_CAP) {
-                        sBuf[slot] = e;
+                    e.dt = fmaf(-2.0f, g, r_i + __ldg(rj + cc * 32 + c));
+                    if (slot < (unsigned)SW_WARP_CAP) {
+                        wBuf[slot] = e;
                     } else {   // staging full (degenerate data): straight to global
                         const unsigned long long gi = atomicAdd(p.cnt_len, 1ull);
                         if (gi < p.list_cap) p.list[gi] = e;
@@ -224,33 +232,27 @@ struct TileClassifier {
             }
         }
     }
-    // all 256 classification threads, once per tile: flush the staged entries when the buffer is
-    // half full (or at the last tile) with one global reservation per flush
+    // once per tile, whole warp: move the staged entries to the global list when the buffer is
+    // half full (or at the last tile) -- one global reservation per flush
     __device__ void flush(bool last) {
-        named_bar_sync(1, SW_EPI_THREADS);
-        if (tid256 == 0) {
-            const unsigned int have = min(*sCount, (unsigned)SW_STAGE_CAP);
-            const bool fl = have > (unsigned)SW_STAGE_CAP / 2 || (last && have > 0);
-            *sN = fl ? have : 0u;
-            if (fl) {
-                *sBase = atomicAdd(p.cnt_len, (unsigned long long)have);
-                *sCount = 0u;
-            }
+        __syncwarp();
+        const unsigned int have = min(*wCount, (unsigned)SW_WARP_CAP);
+        if (!(have > (unsigned)SW_WARP_CAP / 2 || (last && have > 0))) return;
+        unsigned long long base = 0ull;
+        if (lane == 0) base = atomicAdd(p.cnt_len, (unsigned long long)have);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (unsigned int e = lane; e < have; e += 32) {
+            const PairEntry pe = wBuf[e];
+            if (base + e < p.list_cap) p.list[base + e] = pe;
+            else *p.overflow = 1;
+            atomicAdd(&sHist[hist_bin(pe.dt, hlo, hscale)], (pe.jw >> 31) ? 2u : 1u);
         }
-        named_bar_sync(2, SW_EPI_THREADS);
-        const unsigned int cnt = *sN;
-        if (cnt) {
-            const unsigned long long base = *sBase;
-            for (unsigned int e = tid256; e < cnt; e += SW_EPI_THREADS) {
-                const PairEntry pe = sBuf[e];
-                if (base + e < p.list_cap) p.list[base + e] = pe;
-                else *p.overflow = 1;
-                atomicAdd(&sHist[hist_bin(pe.dt, hlo, hscale)], (pe.jw >> 31) ? 2u : 1u);
-            }
-            named_bar_sync(3, SW_EPI_THREADS);
-        }
+        __syncwarp();
+        if (lane == 0) *wCount = 0u;
+        __syncwarp();
     }
-    __device__ void finish() {
+    // after the last tile: counts, then (all classification warps together) the histogram
+    __device__ void finish(int ew_tid) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             below += __shfl_xor_sync(0xffffffffu, below, o);
@@ -261,7 +263,7 @@ struct TileClassifier {
             if (listed) atomicAdd(p.cnt_listed, (unsigned long long)listed);
         }
         named_bar_sync(3, SW_EPI_THREADS);
-        for (int b = tid256; b < SW_HIST_BINS; b += SW_EPI_THREADS) {
+        for (int b = ew_tid; b < SW_HIST_BINS; b += SW_EPI_THREADS) {
             const unsigned int v = sHist[b];
             if (v) atomicAdd(&p.hist[b], (unsigned long long)v);
         }
@@ -284,10 +286,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
     uint8_t *tail = sRing + (size_t)SW_STAGES * SW_UNIT_BYTES;
     SweepBarriers *bars = reinterpret_cast<SweepBarriers *>(tail);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 256);
-    // tail + 260.. : staging counters, SW_STAGE_CAP staged entries, column terms, histogram
-    // (laid out by TileClassifier)
-    unsigned int *sCount = reinterpret_cast<unsigned int *>(tail + 260);
-    unsigned int *sHist = reinterpret_cast<unsigned int *>(tail + 320 + SW_STAGE_CAP * sizeof(PairEntry) + 1024);
+    unsigned int *sHist = reinterpret_cast<unsigned int *>(tail + SW_TAIL_HIST);
 
     const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
     const long long NT = p.t_end - p.t_begin;
@@ -303,9 +302,8 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
         mbar_init(&bars->a_empty, 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->s_full[b], 1);
-            mbar_init(&bars->s_empty[b], SW_EPI_THREADS);
+            mbar_init(&bars->s_empty[b], SW_EPI_WARPS);
         }
-        *sCount = 0u;
         fence_barrier_init();
         fence_proxy_async();
         tma_prefetch_desc(&mapXh);
@@ -410,11 +408,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
         int prevI = -1, aseg = 0;
         long long jj = 0;
         int I = 0, J = 0;
-        if (my0 < my1) {
-            tri_tile(my0, p.T, I, J);
-            tc.publish_cols(J, 0);
-            named_bar_sync(1, SW_EPI_THREADS);
-        }
+        if (my0 < my1) tri_tile(my0, p.T, I, J);
         for (long long t = my0; t < my1; ++t, ++jj) {
             const long long i = (long long)I * 128 + row;
             if (I != prevI) {
@@ -444,16 +438,15 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
             const int b = (int)(jj & 1);
             mbar_wait(&bars->s_full[b], (uint32_t)((jj >> 1) & 1));
             tcgen05_fence_after();
-            tc.classify(tmem + b * 128, i, J, (I == J) ? 1u : 2u, b);
-            // S buffer b may be overwritten by the GEMM of tile jj + 2
+            tc.classify(tmem + b * 128, i, J, (I == J) ? 1u : 2u);
+            // S buffer b may be overwritten by the GEMM of tile jj + 2 (one arrival per warp)
             tcgen05_fence_before();
-            mbar_arrive(&bars->s_empty[b]);
-            // column terms of the next tile (published by the barrier in flush)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->s_empty[b]);
             next_tile(I, J, p.T);
-            if (t + 1 < my1) tc.publish_cols(J, b ^ 1);
             tc.flush(t + 1 == my1);
         }
-        tc.finish();
+        tc.finish((warp - 4) * 32 + lane);
     }
 
     tcgen05_fence_before();
@@ -518,8 +511,7 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
     uint8_t *tail = sRing + (size_t)SW2_STAGES * SW_UNIT_BYTES;
     Sweep2Barriers *bars = reinterpret_cast<Sweep2Barriers *>(tail);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 256);
-    unsigned int *sCount = reinterpret_cast<unsigned int *>(tail + 260);
-    unsigned int *sHist = reinterpret_cast<unsigned int *>(tail + 320 + SW_STAGE_CAP * sizeof(PairEntry) + 1024);
+    unsigned int *sHist = reinterpret_cast<unsigned int *>(tail + SW_TAIL_HIST);
 
     const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -538,9 +530,8 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
         mbar_init(&bars->a_empty, 1);                // multicast commit
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->s_full[b], 1);                        // multicast commit
-            mbar_init(&bars->s_empty[b], 2 * SW_EPI_THREADS);      // leader: both CTAs' classification threads
+            mbar_init(&bars->s_empty[b], 2 * SW_EPI_WARPS);        // leader: both CTAs' classification warps
         }
-        *sCount = 0u;
         fence_barrier_init();
         fence_proxy_async();
         tma_prefetch_desc(&mapXh);
@@ -651,11 +642,7 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
         const uint32_t s_empty_addr1 = mapa_shared(smem_u32(&bars->s_empty[1]), 0);
         long long jj = 0;
         int I2 = 0, J = 0;
-        if (my0 < my1) {
-            pair_tile(my0, p.T, I2, J);
-            tc.publish_cols(J, 0);
-            named_bar_sync(1, SW_EPI_THREADS);
-        }
+        if (my0 < my1) pair_tile(my0, p.T, I2, J);
         for (long long t = my0; t < my1; ++t, ++jj) {
             const int I = 2 * I2 + (int)rank;
             const long long i = (long long)I * 128 + tc.row;
@@ -663,15 +650,15 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
             const unsigned int w = J > I ? 2u : (J == I ? 1u : 0u);
             mbar_wait(&bars->s_full[b], (uint32_t)((jj >> 1) & 1));
             tcgen05_fence_after();
-            tc.classify(tmem + b * 128, i, J, w, b);
-            // g buffer b may be overwritten by the GEMM of tile jj + 2
+            tc.classify(tmem + b * 128, i, J, w);
+            // g buffer b may be overwritten by the GEMM of tile jj + 2 (one arrival per warp)
             tcgen05_fence_before();
-            mbar_arrive_cluster(b ? s_empty_addr1 : s_empty_addr0);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(b ? s_empty_addr1 : s_empty_addr0);
             next_pair_tile(I2, J, p.T);
-            if (t + 1 < my1) tc.publish_cols(J, b ^ 1);
             tc.flush(t + 1 == my1);
         }
-        tc.finish();
+        tc.finish((warp - 4) * 32 + lane);
     }
 
     tcgen05_fence_before();
@@ -1041,7 +1028,7 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     p.overflow = d_overflow;
     p.list = A.list;
     p.list_cap = A.list_cap;
-    const size_t tail_bytes = 320 + (size_t)SW_STAGE_CAP * sizeof(PairEntry) + 1024 + (size_t)SW_HIST_BINS * 4 + 64;
+    const size_t tail_bytes = SW_TAIL_BYTES;
     const size_t smem1 = 1024 + (size_t)SW_STAGES * SW_UNIT_BYTES + tail_bytes;
     const size_t smem2 = 1024 + (size_t)(2 * SW2_KB + SW2_STAGES) * SW_UNIT_BYTES + tail_bytes;
     static bool attr_set = false;

@@ -178,10 +178,10 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
         mbar_init(&bars->a_empty, 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->s_full[b], 1);
-            mbar_init(&bars->p_full[b], FL_EPI_THREADS);
+            mbar_init(&bars->p_full[b], FL_EPI_THREADS / 32);      // one arrival per epilogue warp
         }
         mbar_init(&bars->o_full, 1);
-        mbar_init(&bars->o_empty, FL_EPI_THREADS);
+        mbar_init(&bars->o_empty, FL_EPI_THREADS / 32);
         fence_barrier_init();
         fence_proxy_async();
         tma_prefetch_desc(&mapXh);
@@ -404,7 +404,8 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
                 }
                 tmem_wait_st();
                 tcgen05_fence_before();
-                mbar_arrive(&bars->p_full[b]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->p_full[b]);
 
                 const int ti = j - j0;
                 if (((ti + 1) % FL_OCHUNK) == 0 || j == j1 - 1) {
@@ -424,7 +425,8 @@ flash_phi_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
                         }
                     }
                     tcgen05_fence_before();
-                    mbar_arrive(&bars->o_empty);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->o_empty);
                     ++oc;
                 }
             }
@@ -511,10 +513,10 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
         mbar_init(&bars->a_empty, 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->s_full[b], 1);                        // multicast commit
-            mbar_init(&bars->p_full[b], 2 * FL_EPI_THREADS);       // leader: both CTAs' epilogue threads
+            mbar_init(&bars->p_full[b], 2 * FL_EPI_THREADS / 32);  // leader: one arrival per epilogue warp of both CTAs
         }
         mbar_init(&bars->o_full, 1);                               // multicast commit
-        mbar_init(&bars->o_empty, 2 * FL_EPI_THREADS);             // leader
+        mbar_init(&bars->o_empty, 2 * FL_EPI_THREADS / 32);        // leader
         fence_barrier_init();
         fence_proxy_async();
         tma_prefetch_desc(&mapXh);
@@ -752,7 +754,8 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                 }
                 tmem_wait_st();
                 tcgen05_fence_before();
-                mbar_arrive_cluster(b ? p_full_addr1 : p_full_addr0);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(b ? p_full_addr1 : p_full_addr0);
 
                 const int ti = j - j0;
                 if (((ti + 1) % FL_OCHUNK) == 0 || j == j1 - 1) {
@@ -767,7 +770,8 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                         for (int c = 0; c < 32; ++c) acc[ch * 32 + c] += __uint_as_float(v[c]);
                     }
                     tcgen05_fence_before();
-                    mbar_arrive_cluster(o_empty_addr);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(o_empty_addr);
                     ++oc;
                 }
             }

@@ -201,8 +201,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
     return r;
 }
+// Arrival on a barrier of another CTA of the cluster.  No `.release.cluster`: that form is compiled
+// to MEMBAR.ALL.GPU + ERRBAR in every arriving thread (18 % of the pair sweep's samples).  What
+// the consumer (the MMA issuer) must observe are completed tcgen05.ld/st, which the callers
+// order with tcgen05.wait + tcgen05.fence::before_thread_sync; no generic-proxy data is published.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // Both CTAs of the pair run this; the bytes are accounted on the LEADER's barrier, given as a
 // shared::cluster address (mapa_shared(local_address, 0)).
