@@ -78,6 +78,13 @@ int stein_ctx_create(stein_ctx **out, int device, void *cuda_stream /* may be NU
 int stein_ctx_destroy(stein_ctx *ctx);
 int stein_ctx_set_stream(stein_ctx *ctx, void *cuda_stream);
 int stein_ctx_set_comm(stein_ctx *ctx, const stein_comm *comm /* NULL = single GPU */);
+/* Built-in hooks on NCCL (resolved at run time from the libnccl.so.2 loaded in the process):
+ * rank 0 calls stein_nccl_unique_id and hands the 128 bytes to every rank by any means; every
+ * rank then calls stein_ctx_init_nccl, which creates the communicator (collective) and installs
+ * hooks that enqueue ncclAllGather / ncclAllReduce on the ctx stream.  world == 1 clears them. */
+#define STEIN_NCCL_ID_BYTES 128
+int stein_nccl_unique_id(void *id_out);
+int stein_ctx_init_nccl(stein_ctx *ctx, int rank, int world, const void *id);
 int stein_ctx_set_phi_impl(stein_ctx *ctx, int impl);
 int stein_ctx_set_median_impl(stein_ctx *ctx, int impl);
 const char *stein_last_error(const stein_ctx *ctx /* NULL = last error of any ctx */);

@@ -38,6 +38,8 @@ SIGNATURES = {
     "stein_ctx_destroy": (ctypes.c_int, [c_vp]),
     "stein_ctx_set_stream": (ctypes.c_int, [c_vp, c_vp]),
     "stein_ctx_set_comm": (ctypes.c_int, [c_vp, ctypes.POINTER(SteinComm)]),
+    "stein_nccl_unique_id": (ctypes.c_int, [c_vp]),
+    "stein_ctx_init_nccl": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp]),
     "stein_ctx_set_phi_impl": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "stein_ctx_set_median_impl": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "stein_last_error": (ctypes.c_char_p, [c_vp]),

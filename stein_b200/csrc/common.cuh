@@ -25,6 +25,7 @@ struct stein_ctx {
     cudaStream_t stream = nullptr;
     bool has_comm = false;
     stein_comm comm{};
+    void *nccl_state = nullptr;     // built-in NCCL transport (comm_nccl.cu), if initialised
     int phi_impl = STEIN_PHI_AUTO;
     int median_impl = STEIN_MEDIAN_AUTO;
     int64_t launches = 0;
@@ -47,6 +48,7 @@ namespace stein {
 extern thread_local std::string g_last_error;
 
 int fail(stein_ctx *ctx, int code, const char *fmt, ...);
+void nccl_release(stein_ctx *ctx);   // comm_nccl.cu
 
 #define STEIN_CHECK_CUDA(ctx, expr)                                                        \
     do {                                                                                   \

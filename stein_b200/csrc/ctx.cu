@@ -64,6 +64,7 @@ int stein_ctx_create(stein_ctx **out, int device, void *cuda_stream) {
 int stein_ctx_destroy(stein_ctx *ctx) {
     if (!ctx) return STEIN_OK;
     cudaSetDevice(ctx->device);
+    nccl_release(ctx);
     if (ctx->d_counts) cudaFree(ctx->d_counts);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->d_pilot_keys) cudaFree(ctx->d_pilot_keys);

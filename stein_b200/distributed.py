@@ -18,13 +18,37 @@ class _DevMem:
             "shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
-def make_comm(ctx, group=None):
-    """Build a `stein_comm` for `ctx` from the default (or given) process group
-    and install it.  Returns the struct (kept alive on the context)."""
+def make_nccl_comm(ctx, group=None):
+    """Collectives driven by the library itself: an NCCL communicator created from a unique
+    id that rank 0 generates and torch.distributed broadcasts once.  Afterwards no Python runs
+    inside an iteration (a Python-backed hook costs more than the collective at these sizes)."""
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [None]
+    if rank == 0:
+        buf = ctypes.create_string_buffer(128)
+        ctx.check(ctx.lib.stein_nccl_unique_id(buf))
+        box[0] = buf.raw
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ctx.check(ctx.lib.stein_ctx_init_nccl(ctx.handle, rank, world, ctypes.c_char_p(box[0])))
+    return rank, world
+
+
+def make_comm(ctx, group=None, native=None):
+    """Install collective hooks on `ctx` for the default (or given) process group.
+    native=True (default on an NCCL group): the library's own NCCL transport
+    (`make_nccl_comm`); native=False: hooks backed by torch.distributed calls (any backend
+    that works on device tensors).  Returns what was installed."""
     import torch
     import torch.distributed as dist
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
+    if native is None:
+        native = dist.get_backend(group) == "nccl"
+    if native:
+        return make_nccl_comm(ctx, group)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = "cuda:%d" % ctx.device
 
