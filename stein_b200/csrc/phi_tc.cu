@@ -799,6 +799,48 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
     }
 }
 
+// ---- centring ------------------------------------------------------------------------
+// D_ij only depends on differences, but the Gram form r_i + r_j - 2 x_i.x_j loses
+// |x|^2 / D_ij of its relative precision.  The tensor-core GEMM1 is good to ~2^-17 |x_i||x_j|,
+// which is ample for a cloud around the origin and useless for one that sits away from it
+// (posterior mass at |mean| >> spread).  The flash kernels therefore work on X - mean(X):
+// K, sum_j K_ij and sum_j K_ij (x_i - x_j) are translation invariant.
+constexpr int CM_BLOCKS = 256;
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const float *__restrict__ X, int64_t n, int64_t ld, double *__restrict__ part /* [CM_BLOCKS][ld] */) {
+    // block b sums rows b, b + CM_BLOCKS, ...; thread c owns column c (coalesced row reads)
+    for (int64_t c = threadIdx.x; c < ld; c += blockDim.x) {
+        double acc = 0.0;
+        for (int64_t i = blockIdx.x; i < n; i += CM_BLOCKS) acc += (double)X[i * ld + c];
+        part[(int64_t)blockIdx.x * ld + c] = acc;
+    }
+}
+__global__ void colmean_kernel(const double *__restrict__ part, int64_t n, int64_t ld, float *__restrict__ mean) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ld) return;
+    double acc = 0.0;
+    for (int b = 0; b < CM_BLOCKS; ++b) acc += part[(int64_t)b * ld + c];      // fixed order
+    mean[c] = (float)(acc / (double)n);
+}
+// Xc = X - mean for the n valid rows (pad rows and pad columns stay zero); rc_i = |Xc_i|^2.
+// One warp per row.
+__global__ void __launch_bounds__(256)
+center_kernel(const float *__restrict__ X, const float *__restrict__ mean, int64_t n, int64_t rows, int64_t d,
+              int64_t ld, float *__restrict__ Xc, float *__restrict__ rc) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float acc = 0.0f;
+    for (int64_t c = lane; c < ld; c += 32) {
+        const float v = (row < n && c < d) ? X[row * ld + c] - mean[c] : 0.0f;
+        Xc[row * ld + c] = v;
+        acc = fmaf(v, v, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) rc[row] = acc;
+}
+
 // ---- operand preparation ------------------------------------------------------------
 // BF16 two-term split of X (hi = bf16(x), lo = bf16(x - hi)); nrm[j] = -r_j log2(e)/(2 h^2)
 // (or -inf for j >= n)
@@ -881,6 +923,32 @@ bool flash_tc_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total, 
     return (DP == 128 || DP == 256) && n_total >= 2;
 }
 
+// Centred copy of the particles and its row norms, carved from the workspace.
+struct Centred {
+    float *Xc, *rc;
+};
+static int64_t centred_bytes(int64_t cols, int64_t DP) {
+    return cols * DP * 4 + cols * 4 + (int64_t)CM_BLOCKS * DP * 8 + DP * 4 + 64;
+}
+static int make_centred(stein_ctx *ctx, const float *X_all, int64_t n_total, int64_t d, int64_t cols, int64_t ld,
+                        char *&pws, Centred *out) {
+    pws = (char *)(((uintptr_t)pws + 15) & ~(uintptr_t)15);
+    float *Xc = (float *)pws;        pws += cols * ld * 4;
+    float *rc = (float *)pws;        pws += cols * 4;
+    pws = (char *)(((uintptr_t)pws + 7) & ~(uintptr_t)7);
+    double *part = (double *)pws;    pws += (int64_t)CM_BLOCKS * ld * 8;
+    float *mean = (float *)pws;      pws += ld * 4;
+    colsum_partial_kernel<<<CM_BLOCKS, 256, 0, ctx->stream>>>(X_all, n_total, ld, part);
+    STEIN_CHECK_LAUNCH(ctx);
+    colmean_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, ctx->stream>>>(part, n_total, ld, mean);
+    STEIN_CHECK_LAUNCH(ctx);
+    center_kernel<<<(unsigned)((cols * 32 + 255) / 256), 256, 0, ctx->stream>>>(X_all, mean, n_total, cols, d, ld, Xc, rc);
+    STEIN_CHECK_LAUNCH(ctx);
+    out->Xc = Xc;
+    out->rc = rc;
+    return STEIN_OK;
+}
+
 struct FlashPlan {
     int64_t rows, cols, DP, nI, nJ;     // nI row tiles of tile_rows rows each
     int64_t tile_rows, rows_alloc;      // rows_alloc = nI * tile_rows
@@ -936,6 +1004,7 @@ int64_t flash_tc_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t 
     int64_t b = 0;
     b += p1.cols * p1.DP * 2 * 4;                       // Xh, Xl, YTh, YTl (bf16)
     b += (p1.cols + 256) * 4;                           // nrm
+    b += centred_bytes(p1.cols, p1.DP);                 // centred particles, their norms, column means
     b += std::max(slot_bytes(p1), slot_bytes(p2));
     b += FINALIZE_MAX_BLOCKS * 8;
     return b + 4096;
@@ -1041,16 +1110,21 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     float *nrm = (float *)pws;           pws += (pl.cols + 256) * 4;
     const SlotLayout L = slot_layout(pl, pws);
     double *partials = (double *)(((uintptr_t)pws + 7) & ~(uintptr_t)7);
+    pws = (char *)partials + FINALIZE_MAX_BLOCKS * 8;
     int *tile_nslots = nullptr;
+    // the debug hook compares the raw GEMM1 tiles with X X^T: no centring there
+    Centred cen{const_cast<float *>(X_all), const_cast<float *>(r_all)};
+    if (!g_debug_dumpS) STEIN_TRY(make_centred(ctx, X_all, n_total, d, pl.cols, ld, pws, &cen));
+    const float *Xc = cen.Xc, *rc = cen.rc;
 
     const float l2e = 1.4426950408889634f;
     {
         const int64_t tot = std::max<int64_t>(pl.cols * pl.DP / 4, pl.cols);
-        prep_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(X_all, r_all, pl.cols, n_total, ld,
+        prep_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(Xc, rc, pl.cols, n_total, ld,
                                                                              0.5f * l2e / h2, Xh, Xl, nrm, pl.cols);
         STEIN_CHECK_LAUNCH(ctx);
         dim3 g((unsigned)(pl.cols / 32), (unsigned)(pl.DP / 32)), b(32, 8);
-        prep_yt_kernel<<<g, b, 0, ctx->stream>>>(X_all, S_all, pl.cols, ld, 1.0f / h2, YTh, YTl);
+        prep_yt_kernel<<<g, b, 0, ctx->stream>>>(Xc, S_all, pl.cols, ld, 1.0f / h2, YTh, YTl);
         STEIN_CHECK_LAUNCH(ctx);
     }
     STEIN_TRY(plan_upload(ctx, 0, pl.tile_nslots, n_local, n_total, d, &tile_nslots));
@@ -1089,7 +1163,7 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     const int64_t rows_valid = std::max<int64_t>(0, std::min<int64_t>(n_local, n_total - row_begin));
     const int64_t total4 = pl.rows * ld / 4;
     const int blocks = (int)std::min<int64_t>((total4 + 255) / 256, FINALIZE_MAX_BLOCKS);
-    finalize_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(L, tile_nslots, X_all + row_begin * ld, rows_valid, pl.rows,
+    finalize_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(L, tile_nslots, Xc + row_begin * ld, rows_valid, pl.rows,
                                                            ld, 1.0f / h2, 1.0f / (float)n_total, phi, partials);
     STEIN_CHECK_LAUNCH(ctx);
     reduce_partials2_kernel<<<1, 256, 0, ctx->stream>>>(partials, blocks, sumsq);
@@ -1123,16 +1197,20 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
     float *nrm = (float *)pws;           pws += (cols + 256) * 4;
     const SlotLayout L = slot_layout(pl, pws);
     double *partials = (double *)(((uintptr_t)pws + 7) & ~(uintptr_t)7);
+    pws = (char *)partials + FINALIZE_MAX_BLOCKS * 8;
     int *d_tile_nslots = nullptr;
+    Centred cen{};
+    STEIN_TRY(make_centred(ctx, X_all, n_total, d, cols, ld, pws, &cen));
+    const float *Xc = cen.Xc, *rc = cen.rc;
 
     const float l2e = 1.4426950408889634f;
     {
         const int64_t tot = std::max<int64_t>(cols * DP / 4, cols + 256);
-        prep_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(X_all, r_all, cols, n_total, ld,
+        prep_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(Xc, rc, cols, n_total, ld,
                                                                              0.5f * l2e / h2, Xh, Xl, nrm, cols + 256);
         STEIN_CHECK_LAUNCH(ctx);
         dim3 g((unsigned)(cols / 32), (unsigned)(DP / 32)), b(32, 8);
-        prep_yt_kernel<<<g, b, 0, ctx->stream>>>(X_all, S_all, cols, ld, 1.0f / h2, YTh, YTl);
+        prep_yt_kernel<<<g, b, 0, ctx->stream>>>(Xc, S_all, cols, ld, 1.0f / h2, YTh, YTl);
         STEIN_CHECK_LAUNCH(ctx);
     }
     STEIN_TRY(plan_upload(ctx, 1, tile_nslots, n_local, n_total, d, &d_tile_nslots));
@@ -1167,7 +1245,7 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
     const int64_t rows_valid = std::max<int64_t>(0, std::min<int64_t>(n_local, n_total - row_begin));
     const int64_t total4 = rows * ld / 4;
     const int blocks = (int)std::min<int64_t>((total4 + 255) / 256, FINALIZE_MAX_BLOCKS);
-    finalize_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(L, d_tile_nslots, X_all + row_begin * ld, rows_valid, rows, ld,
+    finalize_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(L, d_tile_nslots, Xc + row_begin * ld, rows_valid, rows, ld,
                                                            1.0f / h2, 1.0f / (float)n_total, phi, partials);
     STEIN_CHECK_LAUNCH(ctx);
     reduce_partials2_kernel<<<1, 256, 0, ctx->stream>>>(partials, blocks, sumsq);

@@ -268,6 +268,38 @@ def test_phi_flash_cta_pair_matches_oracle(ctx, n, d, scale):
     assert abs(sumsq - (phi ** 2).sum()) <= 1e-6 * (phi ** 2).sum()
 
 
+def _phi_float64(X, S, bw):
+    """The reference formula (squared_exponential_kernel.py:22-35, abstract_stein_sampler.py:105)
+    evaluated in float64 throughout, with the given bandwidth."""
+    X64, S64 = X.astype(np.float64), S.astype(np.float64)
+    r = (X64 ** 2).sum(1)
+    D = r[:, None] + r[None, :] - 2 * X64 @ X64.T
+    h2 = float(bw) ** 2
+    K = np.exp(-D / h2 / 2)
+    dK = (X64 * K.sum(1)[:, None] - K @ X64) / h2
+    return (K @ S64 + dK) / X.shape[0]
+
+
+@pytest.mark.parametrize("impl", ["flash", "pair"])
+@pytest.mark.parametrize("offset", [1.0, 10.0])
+def test_phi_flash_offset_cloud(ctx, impl, offset):
+    """A particle cloud away from the origin (|mean|^2 >> spread^2).  The Gram form of the
+    distances loses |x|^2 / D of its precision; the reference (and the oracle, and the FFMA
+    dense path) form D in fp32 and are themselves 1e-4 .. 1e-2 away from the exact value of the
+    formula here (tools/offset_study.py).  The flash kernels work on centred particles: the
+    bandwidth is still the reference's bit for bit, and phi matches the float64 evaluation of
+    the reference formula to 1e-4 at any offset."""
+    from stein_b200 import _lib
+    n, d = 2000, 256
+    rng = np.random.default_rng(99)
+    Z = rng.standard_normal((n, d))
+    X = (offset + 0.1 * Z).astype(np.float32)
+    S = (rng.standard_normal((n, d)) - 10.0 * Z).astype(np.float32)
+    phi, sumsq, bw = _phi_gpu(ctx, X, S, _lib.PHI_FLASH_TC2 if impl == "pair" else _lib.PHI_FLASH_TC)
+    assert bw.tobytes() == orc.kernel_and_grad(X)[2].tobytes()
+    _assert_close(phi, _phi_float64(X, S, bw))
+
+
 @pytest.mark.parametrize("n,d", [(128, 256), (300, 128), (1000, 256)])
 def test_flash_gram_tiles_are_accurate(ctx, n, d):
     """GEMM1 of the flash kernel (3-pass BF16 split on tcgen05) against float64 X X^T."""

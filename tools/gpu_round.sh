@@ -8,6 +8,6 @@ python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1; echo "ncu_list_rc=$?"
 ncu --set full --clock-control none --import-source on \
-    -k regex:'flash_phi2_kernel|sweep_tc_kernel|band_exact_kernel|band_filter_kernel|pilot_kernel|clip_adam_kernel' -c 6 \
+    -k regex:'flash_phi2_kernel|sweep2_tc_kernel|pair_chain_kernel|band_filter_kernel|clip_adam_kernel' -c 7 \
     -f -o gpurun_out/prof_full python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu_full_rc=$?"
 tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -2; cat gpurun_out/bench.log
