@@ -31,6 +31,7 @@
 #include <vector>
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "phi_common.cuh"
 #include "tc_common.cuh"
@@ -484,10 +485,14 @@ struct Seg2Iter : SegWalk {   // same schedule as SegIter, over cluster pairs an
         : SegWalk(p.nI2, p.nJ, (int)gridDim.x / 2, (int)blockIdx.x / 2) {}
 };
 
+// G2F8 = true: GEMM2 as one FP16 pass plus two FP8 passes (see "mixed-precision GEMM2" below);
+// mapYh then is the FP16 array of Y^T and mapY8h / mapY8l the two FP8 arrays (mapYl unused).
+template <bool G2F8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FL_THREADS, 1)
 flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
                   const __grid_constant__ CUtensorMap mapXh64, const __grid_constant__ CUtensorMap mapXl64,
                   const __grid_constant__ CUtensorMap mapYh, const __grid_constant__ CUtensorMap mapYl,
+                  const __grid_constant__ CUtensorMap mapY8h, const __grid_constant__ CUtensorMap mapY8l,
                   const Flash2Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -524,7 +529,12 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
         tma_prefetch_desc(&mapXh64);
         tma_prefetch_desc(&mapXl64);
         tma_prefetch_desc(&mapYh);
-        tma_prefetch_desc(&mapYl);
+        if (G2F8) {
+            tma_prefetch_desc(&mapY8h);
+            tma_prefetch_desc(&mapY8l);
+        } else {
+            tma_prefetch_desc(&mapYl);
+        }
     }
     if (warp == 1) tmem_alloc_pair(tmem_slot, TMEM_COLS);
     tcgen05_fence_before();
@@ -577,24 +587,28 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                         advance();
                     }
                 };
-                auto emit_g2 = [&](int j) {       // slot = 128 of the 256 rows of Y^T (hi, then lo)
-                    for (int kb2 = 0; kb2 < 2; ++kb2) {
-                        acquire();
-                        if (elect_one_sync()) {
-                            if (leader) mbar_expect_tx(&bars->full[stage], 2u * FL_UNIT_BYTES);
-                            tma_load_2d_pair(sRing + (size_t)stage * FL_UNIT_BYTES, &mapYh,
-                                             full0_addr + 8u * (uint32_t)stage, j * 128 + kb2 * 64, (int)rank * 128);
+                // one ring slot = this CTA's 128 of the 256 rows of a Y^T operand block
+                auto emit_y = [&](const CUtensorMap *map, int c_inner) {
+                    acquire();
+                    if (elect_one_sync()) {
+                        if (leader) mbar_expect_tx(&bars->full[stage], 2u * FL_UNIT_BYTES);
+                        tma_load_2d_pair(sRing + (size_t)stage * FL_UNIT_BYTES, map, full0_addr + 8u * (uint32_t)stage,
+                                         c_inner, (int)rank * 128);
+                    }
+                    __syncwarp();
+                    advance();
+                };
+                auto emit_g2 = [&](int j) {
+                    if (G2F8) {       // FP16 Y (two 64-particle blocks), then the two FP8 arrays (128 particles each)
+                        emit_y(&mapYh, j * 128);
+                        emit_y(&mapYh, j * 128 + 64);
+                        emit_y(&mapY8h, j * 128);
+                        emit_y(&mapY8l, j * 128);
+                    } else {          // per 64-particle block: BF16 hi, then lo
+                        for (int kb2 = 0; kb2 < 2; ++kb2) {
+                            emit_y(&mapYh, j * 128 + kb2 * 64);
+                            emit_y(&mapYl, j * 128 + kb2 * 64);
                         }
-                        __syncwarp();
-                        advance();
-                        acquire();
-                        if (elect_one_sync()) {
-                            if (leader) mbar_expect_tx(&bars->full[stage], 2u * FL_UNIT_BYTES);
-                            tma_load_2d_pair(sRing + (size_t)stage * FL_UNIT_BYTES, &mapYl,
-                                             full0_addr + 8u * (uint32_t)stage, j * 128 + kb2 * 64, (int)rank * 128);
-                        }
-                        __syncwarp();
-                        advance();
                     }
                 };
                 emit_g1(j0);
@@ -648,6 +662,37 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
             };
             auto g2 = [&](long long jcount, bool first_of_chunk, bool last_of_chunk) {
                 const uint32_t a_base = tmem + ((jcount & 1) ? TMEM_S1 : TMEM_S0);
+                if (G2F8) {
+                    // mixed-precision GEMM2: P16.Y16 (8 K steps of 16) + Pl8.Yh8 + Ph8.Yl8 (4 K steps of 32 each)
+                    const uint32_t idesc16 = make_idesc(FMT_F16, 256, 256);
+                    const uint32_t idesc8 = make_idesc_ab(FMT8_E4M3, FMT8_E5M2, 256, 256);
+#pragma unroll 1
+                    for (int kb2 = 0; kb2 < 2; ++kb2) {
+                        const uint64_t bdesc = make_kmajor_sw128_desc(next_unit());
+                        if (elect_one_sync()) {
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                umma2_f16_ts(tmem, a_base + p_hi_col(kb2 * 4 + k4), bdesc + 2 * k4, idesc16,
+                                             !(first_of_chunk && kb2 == 0 && k4 == 0));
+                            tcgen05_commit_pair(&bars->empty[stage]);
+                        }
+                        __syncwarp();
+                        advance();
+                    }
+#pragma unroll 1
+                    for (int part = 0; part < 2; ++part) {     // 0: Pl8 . Yh8, 1: Ph8 . Yl8
+                        const uint64_t bdesc = make_kmajor_sw128_desc(next_unit());
+                        if (elect_one_sync()) {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                umma2_f8_ts(tmem, a_base + 32 * c + 16 + 8 * part, bdesc + 2 * c, idesc8, 1u);
+                            tcgen05_commit_pair(&bars->empty[stage]);
+                            if (part == 1 && last_of_chunk) tcgen05_commit_pair(&bars->o_full);
+                        }
+                        __syncwarp();
+                        advance();
+                    }
+                } else {
 #pragma unroll 1
                 for (int kb2 = 0; kb2 < 2; ++kb2) {
                     uint64_t bdesc = make_kmajor_sw128_desc(next_unit());      // Y hi: Phi.Yhi + Plo.Yhi
@@ -672,6 +717,7 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                     }
                     __syncwarp();
                     advance();
+                }
                 }
             };
             Seg2Iter it(p);
@@ -745,10 +791,26 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                         const float e1 = ex2_approx(
                             fmaf(__uint_as_float(v[2 * c2 + 1]), p.c1, a_i + sB[b * 128 + ch * 32 + 2 * c2 + 1]));
                         ksum += e0 + e1;
-                        const uint32_t wh = pack_bf16x2(e0, e1);
-                        const float h0 = __uint_as_float(wh << 16), h1 = __uint_as_float(wh & 0xffff0000u);
-                        w[c2] = wh;
-                        w[16 + c2] = pack_bf16x2(e0 - h0, e1 - h1);
+                        if (G2F8) {
+                            // words 0..15: P as FP16 pairs; 16..23: E4M3 of (P - P16) 2^12, four per
+                            // word; 24..31: E4M3 of P, four per word
+                            const uint32_t wh = pack_f16x2(e0, e1);
+                            const float l0 = (e0 - f16_lo_to_f32(wh)) * 4096.0f, l1 = (e1 - f16_hi_to_f32(wh)) * 4096.0f;
+                            const uint32_t pl = pack_e4m3x2(l0, l1), ph = pack_e4m3x2(e0, e1);
+                            w[c2] = wh;
+                            if (c2 & 1) {
+                                w[16 + (c2 >> 1)] |= pl << 16;
+                                w[24 + (c2 >> 1)] |= ph << 16;
+                            } else {
+                                w[16 + (c2 >> 1)] = pl;
+                                w[24 + (c2 >> 1)] = ph;
+                            }
+                        } else {
+                            const uint32_t wh = pack_bf16x2(e0, e1);
+                            const float h0 = __uint_as_float(wh << 16), h1 = __uint_as_float(wh & 0xffff0000u);
+                            w[c2] = wh;
+                            w[16 + c2] = pack_bf16x2(e0 - h0, e1 - h1);
+                        }
                     }
                     tmem_st32(s_addr + ch * 32, w);
                 }
@@ -884,6 +946,54 @@ __global__ void prep_yt_kernel(const float *__restrict__ X, const float *__restr
     }
 }
 
+// ---- operands of the mixed-precision GEMM2 (flash_phi2_kernel<true>) -----------------------
+// Y = S - Xc / h2 is scaled per column by a power of two so that its largest entry lies in
+// [128, 256) (FP16 has the precision of BF16x1.4 but 5 exponent bits), then split as
+//   Y16 = fp16(Y'),  Y8h = e5m2(Y16 2^-12),  Y8l = e5m2(Y' - Y16)
+// so that  P.Y' ~ P16.Y16 + (P - P16) 2^12 . Y8h + P8 . Y8l  with all three products on the same
+// scale (the 2^12 of the E4M3 residual of P is undone by the 2^-12 inside Y8h).
+__global__ void __launch_bounds__(256)
+colmax_partial_kernel(const float *__restrict__ X, const float *__restrict__ S, int64_t n, int64_t ld, float inv_h2,
+                      float *__restrict__ part /* [CM_BLOCKS][ld] */) {
+    for (int64_t c = threadIdx.x; c < ld; c += blockDim.x) {
+        float m = 0.0f;
+        for (int64_t i = blockIdx.x; i < n; i += CM_BLOCKS) m = fmaxf(m, fabsf(S[i * ld + c] - X[i * ld + c] * inv_h2));
+        part[(int64_t)blockIdx.x * ld + c] = m;
+    }
+}
+__global__ void colscale_kernel(const float *__restrict__ part, int64_t ld, float *__restrict__ down,
+                                float *__restrict__ up) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ld) return;
+    float m = 0.0f;
+    for (int b = 0; b < CM_BLOCKS; ++b) m = fmaxf(m, part[(int64_t)b * ld + c]);
+    int e = 0;
+    if (m > 0.0f && m < INFINITY) e = ilogbf(m) - 7;        // m 2^-e in [128, 256)
+    e = max(-100, min(100, e));
+    down[c] = ldexpf(1.0f, -e);
+    up[c] = ldexpf(1.0f, e);
+}
+__global__ void prep_yt8_kernel(const float *__restrict__ X, const float *__restrict__ S, int64_t rows, int64_t ld,
+                                float inv_h2, const float *__restrict__ down, __half *__restrict__ YT16,
+                                uint8_t *__restrict__ YT8h, uint8_t *__restrict__ YT8l) {
+    __shared__ float tile[32][33];
+    const int64_t j0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int64_t j = j0 + rr, c = c0 + threadIdx.x;
+        tile[rr][threadIdx.x] = (S[j * ld + c] - X[j * ld + c] * inv_h2) * down[c];
+    }
+    __syncthreads();
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int64_t c = c0 + rr, j = j0 + threadIdx.x;
+        const float y = tile[threadIdx.x][rr];
+        const __half h = __float2half_rn(y);
+        const float hf = __half2float(h);
+        YT16[c * rows + j] = h;
+        YT8h[c * rows + j] = (uint8_t)(tc::pack_e5m2x2(hf * 0.000244140625f, 0.0f) & 0xffu);
+        YT8l[c * rows + j] = (uint8_t)(tc::pack_e5m2x2(y - hf, 0.0f) & 0xffu);
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -905,7 +1015,10 @@ int make_tensor_map_2d(stein_ctx *ctx, CUtensorMap *map, const void *base, int e
     const cuuint64_t gstride[1] = {row_stride_bytes};
     const cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), box_rows};   // 128-byte rows
     const cuuint32_t estr[2] = {1, 1};
-    const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    // (16-bit data is only moved, never converted: the BF16 type also serves FP16 arrays)
+    const CUtensorMapDataType dt = elem_bytes == 1   ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                   : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                     : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     const CUresult rc = encode(map, dt, 2, (void *)base, gdim, gstride, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1005,6 +1118,7 @@ int64_t flash_tc_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t 
     b += p1.cols * p1.DP * 2 * 4;                       // Xh, Xl, YTh, YTl (bf16)
     b += (p1.cols + 256) * 4;                           // nrm
     b += centred_bytes(p1.cols, p1.DP);                 // centred particles, their norms, column means
+    b += ((int64_t)CM_BLOCKS + 2) * p1.DP * 4 + 64;     // column maxima / scales of Y (mixed-precision GEMM2)
     b += std::max(slot_bytes(p1), slot_bytes(p2));
     b += FINALIZE_MAX_BLOCKS * 8;
     return b + 4096;
@@ -1014,7 +1128,8 @@ int64_t flash_tc_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t 
 __global__ void __launch_bounds__(256)
 finalize_slots_kernel(const SlotLayout L, const int *__restrict__ tile_nslots,
                       const float *__restrict__ X_local, int64_t rows_valid, int64_t rows, int64_t ld,
-                      float inv_h2, float inv_n, float *__restrict__ phi, double *__restrict__ partials) {
+                      float inv_h2, float inv_n, const float *__restrict__ colscale /* or NULL */,
+                      float *__restrict__ phi, double *__restrict__ partials) {
     const int64_t ld4 = ld / 4;
     const int64_t total4 = rows * ld4;
     double local = 0.0;
@@ -1028,6 +1143,10 @@ finalize_slots_kernel(const SlotLayout L, const int *__restrict__ tile_nslots,
             const float4 o2 = reinterpret_cast<const float4 *>(L.orow(s, row))[c4];
             o.x += o2.x; o.y += o2.y; o.z += o2.z; o.w += o2.w;
             ks += *L.krow(s, row);
+        }
+        if (colscale) {      // O was accumulated against column-scaled Y
+            const float4 cs = reinterpret_cast<const float4 *>(colscale)[c4];
+            o.x *= cs.x; o.y *= cs.y; o.z *= cs.z; o.w *= cs.w;
         }
         float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < rows_valid) {
@@ -1164,7 +1283,7 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     const int64_t total4 = pl.rows * ld / 4;
     const int blocks = (int)std::min<int64_t>((total4 + 255) / 256, FINALIZE_MAX_BLOCKS);
     finalize_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(L, tile_nslots, Xc + row_begin * ld, rows_valid, pl.rows,
-                                                           ld, 1.0f / h2, 1.0f / (float)n_total, phi, partials);
+                                                           ld, 1.0f / h2, 1.0f / (float)n_total, nullptr, phi, partials);
     STEIN_CHECK_LAUNCH(ctx);
     reduce_partials2_kernel<<<1, 256, 0, ctx->stream>>>(partials, blocks, sumsq);
     STEIN_CHECK_LAUNCH(ctx);
@@ -1179,7 +1298,7 @@ bool flash_tc2_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total,
 
 int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all, int64_t n_total,
                   int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
-                  int64_t ws_bytes, float *phi, double *sumsq) {
+                  int64_t ws_bytes, float *phi, double *sumsq, bool g2f8) {
     const FlashPlan pl = flash_plan(ctx, n_local, n_total, d, true);
     const int64_t rows = pl.rows, cols = pl.cols, DP = FL_MAX_DP;
     STEIN_REQUIRE(ctx, ld == DP, "CTA-pair flash phi needs ld == 256");
@@ -1202,6 +1321,10 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
     Centred cen{};
     STEIN_TRY(make_centred(ctx, X_all, n_total, d, cols, ld, pws, &cen));
     const float *Xc = cen.Xc, *rc = cen.rc;
+    pws = (char *)(((uintptr_t)pws + 15) & ~(uintptr_t)15);
+    float *cmax_part = (float *)pws;     pws += (int64_t)CM_BLOCKS * DP * 4;
+    float *cs_down = (float *)pws;       pws += DP * 4;
+    float *cs_up = (float *)pws;         pws += DP * 4;
 
     const float l2e = 1.4426950408889634f;
     {
@@ -1210,17 +1333,30 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
                                                                              0.5f * l2e / h2, Xh, Xl, nrm, cols + 256);
         STEIN_CHECK_LAUNCH(ctx);
         dim3 g((unsigned)(cols / 32), (unsigned)(DP / 32)), b(32, 8);
-        prep_yt_kernel<<<g, b, 0, ctx->stream>>>(Xc, S_all, cols, ld, 1.0f / h2, YTh, YTl);
+        if (g2f8) {
+            // the FP16 array takes the place of YTh, the two FP8 arrays share the place of YTl
+            colmax_partial_kernel<<<CM_BLOCKS, 256, 0, ctx->stream>>>(Xc, S_all, n_total, ld, 1.0f / h2, cmax_part);
+            STEIN_CHECK_LAUNCH(ctx);
+            colscale_kernel<<<(unsigned)((DP + 255) / 256), 256, 0, ctx->stream>>>(cmax_part, DP, cs_down, cs_up);
+            STEIN_CHECK_LAUNCH(ctx);
+            prep_yt8_kernel<<<g, b, 0, ctx->stream>>>(Xc, S_all, cols, ld, 1.0f / h2, cs_down, (__half *)YTh,
+                                                     (uint8_t *)YTl, (uint8_t *)YTl + cols * DP);
+        } else {
+            prep_yt_kernel<<<g, b, 0, ctx->stream>>>(Xc, S_all, cols, ld, 1.0f / h2, YTh, YTl);
+        }
         STEIN_CHECK_LAUNCH(ctx);
     }
     STEIN_TRY(plan_upload(ctx, 1, tile_nslots, n_local, n_total, d, &d_tile_nslots));
-    CUtensorMap mXh, mXl, mXh64, mXl64, mYh, mYl;
+    CUtensorMap mXh, mXl, mXh64, mXl64, mYh, mYl, mY8h, mY8l;
     STEIN_TRY(make_tensor_map_2d(ctx, &mXh, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
     STEIN_TRY(make_tensor_map_2d(ctx, &mXl, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
     STEIN_TRY(make_tensor_map_2d(ctx, &mXh64, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
     STEIN_TRY(make_tensor_map_2d(ctx, &mXl64, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
     STEIN_TRY(make_tensor_map_2d(ctx, &mYh, YTh, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
     STEIN_TRY(make_tensor_map_2d(ctx, &mYl, YTl, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
+    // FP8 arrays: [DP][cols] bytes, box = 128 particles x 128 rows
+    STEIN_TRY(make_tensor_map_2d(ctx, &mY8h, YTl, 1, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols, 128));
+    STEIN_TRY(make_tensor_map_2d(ctx, &mY8l, (uint8_t *)YTl + cols * DP, 1, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols, 128));
 
     Flash2Params p{};
     p.nJ = (int)nJ;
@@ -1233,20 +1369,26 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
     const size_t smem = flash_smem_bytes(DP);
     static bool attr_set = false;
     if (!attr_set) {
-        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)smem));
+        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)smem));
         attr_set = true;
     }
     {
         RegionTimer timer(ctx, STEIN_REGION_PHI);
-        flash_phi2_kernel<<<2 * G2, FL_THREADS, smem, ctx->stream>>>(mXh, mXl, mXh64, mXl64, mYh, mYl, p);
+        if (g2f8)
+            flash_phi2_kernel<true><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(mXh, mXl, mXh64, mXl64, mYh, mYl, mY8h, mY8l, p);
+        else
+            flash_phi2_kernel<false><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(mXh, mXl, mXh64, mXl64, mYh, mYl, mY8h, mY8l, p);
         STEIN_CHECK_LAUNCH(ctx);
     }
     const int64_t rows_valid = std::max<int64_t>(0, std::min<int64_t>(n_local, n_total - row_begin));
     const int64_t total4 = rows * ld / 4;
     const int blocks = (int)std::min<int64_t>((total4 + 255) / 256, FINALIZE_MAX_BLOCKS);
     finalize_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(L, d_tile_nslots, Xc + row_begin * ld, rows_valid, rows, ld,
-                                                           1.0f / h2, 1.0f / (float)n_total, phi, partials);
+                                                           1.0f / h2, 1.0f / (float)n_total, g2f8 ? cs_up : nullptr, phi,
+                                                           partials);
     STEIN_CHECK_LAUNCH(ctx);
     reduce_partials2_kernel<<<1, 256, 0, ctx->stream>>>(partials, blocks, sumsq);
     STEIN_CHECK_LAUNCH(ctx);

@@ -252,6 +252,17 @@ __device__ __forceinline__ void umma2_f16_ts(uint32_t d_tmem, uint32_t a_tmem, u
         : "memory");
 }
 
+// FP8 operands (kind::f8f6f4, K = 32 per instruction), A from tensor memory (four 8-bit elements
+// per 32-bit column), CTA pair
+__device__ __forceinline__ void umma2_f8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // ---- descriptors -------------------------------------------------------------------------
 // K-major operand tile in shared memory written by TMA with CU_TENSOR_MAP_SWIZZLE_128B:
 // rows of 128 bytes, 8-row swizzle atoms of 1024 bytes stacked densely (SBO = 1024 B).
@@ -274,7 +285,11 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 __host__ __device__ inline uint32_t make_idesc(uint32_t ab_format, uint32_t M, uint32_t N) {
     return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
-constexpr uint32_t FMT_BF16 = 1, FMT_TF32 = 2;
+constexpr uint32_t FMT_F16 = 0, FMT_BF16 = 1, FMT_TF32 = 2;
+constexpr uint32_t FMT8_E4M3 = 0, FMT8_E5M2 = 1;       // kind::f8f6f4 operand formats
+__host__ __device__ inline uint32_t make_idesc_ab(uint32_t a_format, uint32_t b_format, uint32_t M, uint32_t N) {
+    return (1u << 4) | (a_format << 7) | (b_format << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 
 __device__ __forceinline__ float to_tf32_rn(float x) {
     uint32_t r;
@@ -287,6 +302,33 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// {low 16 bits: f16(lo), high 16 bits: f16(hi)}, round to nearest even
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float f16_lo_to_f32(uint32_t packed) {
+    float f;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}" : "=f"(f) : "r"(packed));
+    return f;
+}
+__device__ __forceinline__ float f16_hi_to_f32(uint32_t packed) {
+    float f;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}" : "=f"(f) : "r"(packed));
+    return f;
+}
+// two FP8 values in the low 16 bits: {bits 0-7: e4m3(lo), bits 8-15: e4m3(hi)}, saturating
+__device__ __forceinline__ uint32_t pack_e4m3x2(float lo, float hi) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+    return (uint32_t)r;
+}
+__device__ __forceinline__ uint32_t pack_e5m2x2(float lo, float hi) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+    return (uint32_t)r;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -295,7 +337,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 }  // namespace tc
 
-// host: 2-D row-major tensor map (fp32 or bf16), box = {128 bytes, box_rows}, 128-byte swizzle
+// host: 2-D row-major tensor map (4-, 2- or 1-byte elements), box = {128 bytes, box_rows}, 128-byte swizzle
 int make_tensor_map_2d(stein_ctx *ctx, CUtensorMap *map, const void *base, int elem_bytes, uint64_t inner,
                        uint64_t outer, uint64_t row_stride_bytes, uint32_t box_rows);
 
