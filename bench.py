@@ -176,7 +176,7 @@ def run_ours(args):
         from stein_b200.distributed import make_comm
         make_comm(ctx)
     if args.phi_impl:
-        ctx.set_phi_impl({"auto": 0, "dense": 1, "flash": 2, "flash2": 3, "flash3": 4}[args.phi_impl])
+        ctx.set_phi_impl({"auto": 0, "dense": 1, "flash": 2, "flash2": 3, "flash3": 4, "flash4": 5}[args.phi_impl])
 
     n, d = args.n, args.d
     eng = SvgdEngine(n, d, "adam", learning_rate=1e-2, ctx=ctx)
@@ -266,7 +266,7 @@ def run_ours(args):
     achieved = f_phi / (phi_avg_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     impl = {0: "auto", 1: "dense_simt_fp32", 2: "flash_tcgen05", 3: "flash_tcgen05_cta_pair",
-            4: "flash_tcgen05_cta_pair_fp8_gemm2"}[args_phi_impl_code(ctx, args)]
+            4: "flash_tcgen05_cta_pair_fp8_gemm2", 5: "flash_tcgen05_cta_pair_fp8_gemm1_gemm2"}[args_phi_impl_code(ctx, args)]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -303,7 +303,7 @@ def run_ours(args):
 
 def args_phi_impl_code(ctx, args):
     if args.phi_impl:
-        return {"auto": 0, "dense": 1, "flash": 2, "flash2": 3, "flash3": 4}[args.phi_impl]
+        return {"auto": 0, "dense": 1, "flash": 2, "flash2": 3, "flash3": 4, "flash4": 5}[args.phi_impl]
     return 0
 
 
@@ -315,7 +315,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=N_PARTICLES)
     ap.add_argument("--d", type=int, default=DIM)
-    ap.add_argument("--phi-impl", default=None, choices=[None, "auto", "dense", "flash", "flash2", "flash3"])
+    ap.add_argument("--phi-impl", default=None, choices=[None, "auto", "dense", "flash", "flash2", "flash3", "flash4"])
     ap.add_argument("--ref-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -46,6 +46,7 @@ extern "C" {
 #define STEIN_PHI_FLASH_TC 2   /* tcgen05/TMEM/TMA fused kernel; never stores K   */
 #define STEIN_PHI_FLASH_TC2 3  /* same, CTA pairs (cta_group::2, M = 256); d <= 256 padded to 256 */
 #define STEIN_PHI_FLASH_TC3 4  /* CTA pairs, GEMM2 as one FP16 pass + two FP8 passes instead of 3 BF16 */
+#define STEIN_PHI_FLASH_TC4 5  /* CTA pairs, both GEMMs as FP16 + 2 x FP8 */
 
 /* median implementations (stein_ctx_set_median_impl) */
 #define STEIN_MEDIAN_AUTO 0

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstein_b200.so")
 
 STEIN_OK = 0
-PHI_AUTO, PHI_DENSE_SIMT, PHI_FLASH_TC, PHI_FLASH_TC2, PHI_FLASH_TC3 = 0, 1, 2, 3, 4
+PHI_AUTO, PHI_DENSE_SIMT, PHI_FLASH_TC, PHI_FLASH_TC2, PHI_FLASH_TC3, PHI_FLASH_TC4 = 0, 1, 2, 3, 4, 5
 OPT_ADAM, OPT_ADAGRAD = 0, 1
 MEDIAN_AUTO, MEDIAN_FFMA, MEDIAN_TC, MEDIAN_TC1 = 0, 1, 2, 3
 

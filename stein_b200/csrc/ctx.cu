@@ -103,7 +103,7 @@ int stein_ctx_set_comm(stein_ctx *ctx, const stein_comm *comm) {
 
 int stein_ctx_set_phi_impl(stein_ctx *ctx, int impl) {
     STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
-    STEIN_REQUIRE(ctx, impl >= STEIN_PHI_AUTO && impl <= STEIN_PHI_FLASH_TC3, "unknown phi impl %d", impl);
+    STEIN_REQUIRE(ctx, impl >= STEIN_PHI_AUTO && impl <= STEIN_PHI_FLASH_TC4, "unknown phi impl %d", impl);
     ctx->phi_impl = impl;
     return STEIN_OK;
 }
@@ -146,7 +146,7 @@ int64_t stein_ctx_launch_count(const stein_ctx *ctx) { return ctx ? ctx->launche
 
 static int pick_phi_impl(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
     if (ctx->phi_impl != STEIN_PHI_AUTO) return ctx->phi_impl;
-    if (flash_tc2_supported(ctx, n_local, n_total, d)) return STEIN_PHI_FLASH_TC3;   // d padded to 256: CTA pairs, FP16+FP8 GEMM2
+    if (flash_tc2_supported(ctx, n_local, n_total, d)) return STEIN_PHI_FLASH_TC4;   // d padded to 256: CTA pairs, FP16 + 2 x FP8 passes per GEMM
     return flash_tc_supported(ctx, n_local, n_total, d) ? STEIN_PHI_FLASH_TC : STEIN_PHI_DENSE_SIMT;
 }
 
@@ -172,12 +172,12 @@ int stein_phi(stein_ctx *ctx, const float *X_all_dev, const float *S_all_dev, co
     STEIN_REQUIRE(ctx, bandwidth > 0.0f && bandwidth == bandwidth, "bandwidth must be positive and finite");
     const float h2 = bandwidth * bandwidth;  // squared_exponential_kernel.py:22 tf.square(bandwidth)
     const int impl = pick_phi_impl(ctx, n_local, n_total, d);
-    if (impl == STEIN_PHI_FLASH_TC2 || impl == STEIN_PHI_FLASH_TC3) {
+    if (impl == STEIN_PHI_FLASH_TC2 || impl == STEIN_PHI_FLASH_TC3 || impl == STEIN_PHI_FLASH_TC4) {
         if (!flash_tc2_supported(ctx, n_local, n_total, d))
             return fail(ctx, STEIN_ERR_UNSUPPORTED, "CTA-pair flash phi does not take n=%lld d=%lld",
                         (long long)n_total, (long long)d);
         return phi_flash_tc2(ctx, X_all_dev, S_all_dev, r_all_dev, n_total, d, ld, row_begin, n_local, h2,
-                             workspace_dev, workspace_bytes, phi_dev, sumsq_dev, impl == STEIN_PHI_FLASH_TC3);
+                             workspace_dev, workspace_bytes, phi_dev, sumsq_dev, impl - STEIN_PHI_FLASH_TC2);
     }
     if (impl == STEIN_PHI_FLASH_TC) {
         if (!flash_tc_supported(ctx, n_local, n_total, d))

@@ -31,6 +31,6 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
 bool flash_tc2_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d);
 int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all,
                   int64_t n_total, int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2,
-                  void *ws, int64_t ws_bytes, float *phi, double *sumsq, bool g2f8);
+                  void *ws, int64_t ws_bytes, float *phi, double *sumsq, int mode);
 
 }  // namespace stein

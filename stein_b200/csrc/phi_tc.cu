@@ -475,6 +475,7 @@ struct Flash2Params {
     int nI2;              // row pair-tiles (256 particles)
     int row_pair0;        // (unused)
     long long row_begin;  // first global particle row of the local block (multiple of 128)
+    const float *c1mul;   // device: factor on c1 that undoes the power-of-two scaling of X (G1F8), or NULL
     float c1;
     const float *nrm;
     SlotLayout out;
@@ -485,15 +486,23 @@ struct Seg2Iter : SegWalk {   // same schedule as SegIter, over cluster pairs an
         : SegWalk(p.nI2, p.nJ, (int)gridDim.x / 2, (int)blockIdx.x / 2) {}
 };
 
-// G2F8 = true: GEMM2 as one FP16 pass plus two FP8 passes (see "mixed-precision GEMM2" below);
-// mapYh then is the FP16 array of Y^T and mapY8h / mapY8l the two FP8 arrays (mapYl unused).
-template <bool G2F8>
+// Tensor maps of the pair kernel.  BF16 mode: xa_* / xb_* are the hi / lo arrays of X (boxes of
+// 128 rows for the A tile, 64 rows for a CTA's half of the B tile), yh / yl those of Y^T.
+// Mixed-precision modes: xa_hi / xb_hi and yh are the FP16 arrays and the *8* maps the FP8 arrays
+// (a8l = e4m3((x - x16) 2^12), a8h = e4m3(x16), b8h = e5m2(x16 2^-12), b8l = e5m2(x - x16);
+// y8h = e5m2(y16 2^-12), y8l = e5m2(y - y16)).
+struct Phi2Maps {
+    CUtensorMap xa_hi, xa_lo, xb_hi, xb_lo, a8l, a8h, b8h, b8l, yh, yl, y8h, y8l;
+};
+
+// G1F8 / G2F8 = true: that GEMM runs as one FP16 pass plus two FP8 passes ("mixed precision")
+// instead of three BF16 passes: the FP16 product carries 11 bits of each factor, the two cross
+// terms are 2^-12 relative and only need the 3-4 bits FP8 gives them.
+template <bool G1F8, bool G2F8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FL_THREADS, 1)
-flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
-                  const __grid_constant__ CUtensorMap mapXh64, const __grid_constant__ CUtensorMap mapXl64,
-                  const __grid_constant__ CUtensorMap mapYh, const __grid_constant__ CUtensorMap mapYl,
-                  const __grid_constant__ CUtensorMap mapY8h, const __grid_constant__ CUtensorMap mapY8l,
-                  const Flash2Params p) {
+flash_phi2_kernel(const __grid_constant__ Phi2Maps maps, const Flash2Params p) {
+    const CUtensorMap &mapXh = maps.xa_hi, &mapXl = maps.xa_lo, &mapXh64 = maps.xb_hi, &mapXl64 = maps.xb_lo;
+    const CUtensorMap &mapYh = maps.yh, &mapYl = maps.yl, &mapY8h = maps.y8h, &mapY8l = maps.y8l;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int KB = FL_MAX_DP / 64;                            // 4 K-blocks of 64 bf16
@@ -528,6 +537,12 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
         tma_prefetch_desc(&mapXl);
         tma_prefetch_desc(&mapXh64);
         tma_prefetch_desc(&mapXl64);
+        if (G1F8) {
+            tma_prefetch_desc(&maps.a8l);
+            tma_prefetch_desc(&maps.a8h);
+            tma_prefetch_desc(&maps.b8h);
+            tma_prefetch_desc(&maps.b8l);
+        }
         tma_prefetch_desc(&mapYh);
         if (G2F8) {
             tma_prefetch_desc(&mapY8h);
@@ -567,24 +582,42 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                 const int arow = (int)p.row_begin + (t * 2 + (int)rank) * 128;
                 if (elect_one_sync()) {
                     if (leader) mbar_expect_tx(&bars->a_full, 2u * 2u * KB * FL_UNIT_BYTES);
-                    for (int kb = 0; kb < KB; ++kb) {
-                        tma_load_2d_pair(sA + (size_t)kb * FL_UNIT_BYTES, &mapXh, a_full_addr, kb * 64, arow);
-                        tma_load_2d_pair(sA + (size_t)(KB + kb) * FL_UNIT_BYTES, &mapXl, a_full_addr, kb * 64, arow);
+                    if (G1F8) {   // boxes 0-3: X16 K blocks of 64; 4-5: a8l K blocks of 128; 6-7: a8h
+                        for (int kb = 0; kb < KB; ++kb)
+                            tma_load_2d_pair(sA + (size_t)kb * FL_UNIT_BYTES, &mapXh, a_full_addr, kb * 64, arow);
+                        for (int q = 0; q < 2; ++q) {
+                            tma_load_2d_pair(sA + (size_t)(4 + q) * FL_UNIT_BYTES, &maps.a8l, a_full_addr, q * 128, arow);
+                            tma_load_2d_pair(sA + (size_t)(6 + q) * FL_UNIT_BYTES, &maps.a8h, a_full_addr, q * 128, arow);
+                        }
+                    } else {
+                        for (int kb = 0; kb < KB; ++kb) {
+                            tma_load_2d_pair(sA + (size_t)kb * FL_UNIT_BYTES, &mapXh, a_full_addr, kb * 64, arow);
+                            tma_load_2d_pair(sA + (size_t)(KB + kb) * FL_UNIT_BYTES, &mapXl, a_full_addr, kb * 64, arow);
+                        }
                     }
                 }
                 __syncwarp();
-                auto emit_g1 = [&](int j) {       // slot = [64 rows of X_J hi | 64 rows of X_J lo]
-                    for (int kb = 0; kb < KB; ++kb) {
-                        acquire();
-                        if (elect_one_sync()) {
-                            if (leader) mbar_expect_tx(&bars->full[stage], 2u * FL_UNIT_BYTES);
-                            uint8_t *dst = sRing + (size_t)stage * FL_UNIT_BYTES;
-                            const uint32_t fa = full0_addr + 8u * (uint32_t)stage;
-                            tma_load_2d_pair(dst, &mapXh64, fa, kb * 64, j * 128 + (int)rank * 64);
-                            tma_load_2d_pair(dst + FL_UNIT_BYTES / 2, &mapXl64, fa, kb * 64, j * 128 + (int)rank * 64);
-                        }
-                        __syncwarp();
-                        advance();
+                // one ring slot = two half boxes (64 rows of X_J each): [first | second]
+                auto emit_x2 = [&](const CUtensorMap *m0, int c0, const CUtensorMap *m1, int c1, int j) {
+                    acquire();
+                    if (elect_one_sync()) {
+                        if (leader) mbar_expect_tx(&bars->full[stage], 2u * FL_UNIT_BYTES);
+                        uint8_t *dst = sRing + (size_t)stage * FL_UNIT_BYTES;
+                        const uint32_t fa = full0_addr + 8u * (uint32_t)stage;
+                        tma_load_2d_pair(dst, m0, fa, c0, j * 128 + (int)rank * 64);
+                        tma_load_2d_pair(dst + FL_UNIT_BYTES / 2, m1, fa, c1, j * 128 + (int)rank * 64);
+                    }
+                    __syncwarp();
+                    advance();
+                };
+                auto emit_g1 = [&](int j) {
+                    if (G1F8) {   // [X16 kb 0 | kb 1], [kb 2 | kb 3], [b8h q | b8l q] for q = 0, 1
+                        emit_x2(&mapXh64, 0, &mapXh64, 64, j);
+                        emit_x2(&mapXh64, 128, &mapXh64, 192, j);
+                        emit_x2(&maps.b8h, 0, &maps.b8l, 0, j);
+                        emit_x2(&maps.b8h, 128, &maps.b8l, 128, j);
+                    } else {      // per K block: [hi | lo]
+                        for (int kb = 0; kb < KB; ++kb) emit_x2(&mapXh64, kb * 64, &mapXl64, kb * 64, j);
                     }
                 };
                 // one ring slot = this CTA's 128 of the 256 rows of a Y^T operand block
@@ -639,6 +672,46 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
             };
             auto g1 = [&](long long jcount) {
                 const uint32_t d_tmem = tmem + ((jcount & 1) ? TMEM_S1 : TMEM_S0);
+                if (G1F8) {
+                    // mixed-precision GEMM1: X16.X16 (16 K steps of 16) + a8l.b8h + a8h.b8l (8 K steps of 32 each)
+                    const uint32_t idesc16 = make_idesc(FMT_F16, 256, 128);
+                    const uint32_t idesc8 = make_idesc_ab(FMT8_E4M3, FMT8_E5M2, 256, 128);
+#pragma unroll 1
+                    for (int u = 0; u < 2; ++u) {          // ring slot = [kb 2u | kb 2u + 1]
+                        const uint32_t slot_addr = next_unit();
+                        if (elect_one_sync()) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint64_t a = make_kmajor_sw128_desc(smem_u32(sA + (size_t)(2 * u + h) * FL_UNIT_BYTES));
+                                const uint64_t b = make_kmajor_sw128_desc(slot_addr + h * (FL_UNIT_BYTES / 2));
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; ++k4)
+                                    umma2_f16_ss(d_tmem, a + 2 * k4, b + 2 * k4, idesc16, (u | h | k4) != 0);
+                            }
+                            tcgen05_commit_pair(&bars->empty[stage]);
+                        }
+                        __syncwarp();
+                        advance();
+                    }
+#pragma unroll 1
+                    for (int q = 0; q < 2; ++q) {          // ring slot = [b8h q | b8l q], K block of 128
+                        const uint32_t slot_addr = next_unit();
+                        if (elect_one_sync()) {
+                            const uint64_t al = make_kmajor_sw128_desc(smem_u32(sA + (size_t)(4 + q) * FL_UNIT_BYTES));
+                            const uint64_t ah = make_kmajor_sw128_desc(smem_u32(sA + (size_t)(6 + q) * FL_UNIT_BYTES));
+                            const uint64_t bh = make_kmajor_sw128_desc(slot_addr);
+                            const uint64_t bl = make_kmajor_sw128_desc(slot_addr + FL_UNIT_BYTES / 2);
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) umma2_f8_ss(d_tmem, al + 2 * k4, bh + 2 * k4, idesc8, 1u);
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) umma2_f8_ss(d_tmem, ah + 2 * k4, bl + 2 * k4, idesc8, 1u);
+                            tcgen05_commit_pair(&bars->empty[stage]);
+                            if (q == 1) tcgen05_commit_pair(&bars->s_full[jcount & 1]);
+                        }
+                        __syncwarp();
+                        advance();
+                    }
+                } else {
 #pragma unroll 1
                 for (int kb = 0; kb < KB; ++kb) {
                     const uint64_t ah = make_kmajor_sw128_desc(smem_u32(sA + (size_t)kb * FL_UNIT_BYTES));
@@ -658,6 +731,7 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                     }
                     __syncwarp();
                     advance();
+                }
                 }
             };
             auto g2 = [&](long long jcount, bool first_of_chunk, bool last_of_chunk) {
@@ -762,6 +836,8 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
         Seg2Iter it(p);
         int t, j0, j1, slot;
         long long jj = 0, oc = 0;
+        // GEMM1 of the mixed-precision mode works on X 2^-e: S carries 2^-2e, undone here (exact)
+        const float c1 = G1F8 ? p.c1 * __ldg(p.c1mul) : p.c1;
         float acc[ocols];
         while (it.next(t, j0, j1, slot)) {
             const size_t grow = (size_t)p.row_begin + ((size_t)t * 2 + rank) * 128 + row;   // global particle row
@@ -787,9 +863,9 @@ flash_phi2_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
 #pragma unroll
                     for (int c2 = 0; c2 < 16; ++c2) {
                         const float e0 = ex2_approx(
-                            fmaf(__uint_as_float(v[2 * c2]), p.c1, a_i + sB[b * 128 + ch * 32 + 2 * c2]));
+                            fmaf(__uint_as_float(v[2 * c2]), c1, a_i + sB[b * 128 + ch * 32 + 2 * c2]));
                         const float e1 = ex2_approx(
-                            fmaf(__uint_as_float(v[2 * c2 + 1]), p.c1, a_i + sB[b * 128 + ch * 32 + 2 * c2 + 1]));
+                            fmaf(__uint_as_float(v[2 * c2 + 1]), c1, a_i + sB[b * 128 + ch * 32 + 2 * c2 + 1]));
                         ksum += e0 + e1;
                         if (G2F8) {
                             // words 0..15: P as FP16 pairs; 16..23: E4M3 of (P - P16) 2^12, four per
@@ -994,6 +1070,73 @@ __global__ void prep_yt8_kernel(const float *__restrict__ X, const float *__rest
     }
 }
 
+// ---- operands of the mixed-precision GEMM1 ------------------------------------------------
+// The centred particles are scaled by one power of two so that the largest |entry| lies in
+// [128, 256), then split as  x16 = fp16(x'),  a8l = e4m3((x' - x16) 2^12),  a8h = e4m3(x16),
+// b8h = e5m2(x16 2^-12),  b8l = e5m2(x' - x16):
+//   x_i . x_j ~ x16_i . x16_j + a8l_i . b8h_j + a8h_i . b8l_j        (all on the scale 2^-2e)
+__global__ void __launch_bounds__(256)
+absmax_partial_kernel(const float *__restrict__ X, int64_t n, int64_t ld, float *__restrict__ part /* [CM_BLOCKS][ld] */) {
+    for (int64_t c = threadIdx.x; c < ld; c += blockDim.x) {
+        float m = 0.0f;
+        for (int64_t i = blockIdx.x; i < n; i += CM_BLOCKS) m = fmaxf(m, fabsf(X[i * ld + c]));
+        part[(int64_t)blockIdx.x * ld + c] = m;
+    }
+}
+// out[0] = 2^-e (applied to X), out[1] = 2^(2e) (applied to c1)
+__global__ void __launch_bounds__(1024)
+xscale_kernel(const float *__restrict__ part, int64_t count, float *__restrict__ out) {
+    __shared__ float red[32];
+    float m = 0.0f;
+    for (int64_t i = threadIdx.x; i < count; i += blockDim.x) m = fmaxf(m, part[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = red[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) {
+            int e = 0;
+            if (m > 0.0f && m < INFINITY) e = ilogbf(m) - 7;
+            e = max(-60, min(60, e));
+            out[0] = ldexpf(1.0f, -e);
+            out[1] = ldexpf(1.0f, 2 * e);
+        }
+    }
+}
+__global__ void prep_x8_kernel(const float *__restrict__ X, const float *__restrict__ r, int64_t rows, int64_t n,
+                               int64_t ld, float half_l2e_over_h2, const float *__restrict__ xscale,
+                               __half *__restrict__ X16, uint8_t *__restrict__ A8l, uint8_t *__restrict__ A8h,
+                               uint8_t *__restrict__ B8h, uint8_t *__restrict__ B8l, float *__restrict__ nrm,
+                               int64_t nrm_rows) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t ld4 = ld / 4;
+    if (e < rows * ld4) {
+        const float sc = __ldg(xscale);
+        const float4 x = reinterpret_cast<const float4 *>(X)[e];
+        const float xs[4] = {x.x * sc, x.y * sc, x.z * sc, x.w * sc};
+        __half h[4];
+        float hf[4], lo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            h[k] = __float2half_rn(xs[k]);
+            hf[k] = __half2float(h[k]);
+            lo[k] = xs[k] - hf[k];
+        }
+        reinterpret_cast<uint2 *>(X16)[e] = *reinterpret_cast<uint2 *>(h);
+        reinterpret_cast<uint32_t *>(A8l)[e] = tc::pack_e4m3x2(lo[0] * 4096.0f, lo[1] * 4096.0f) |
+                                               (tc::pack_e4m3x2(lo[2] * 4096.0f, lo[3] * 4096.0f) << 16);
+        reinterpret_cast<uint32_t *>(A8h)[e] = tc::pack_e4m3x2(hf[0], hf[1]) | (tc::pack_e4m3x2(hf[2], hf[3]) << 16);
+        const float dn = 0.000244140625f;   // 2^-12
+        reinterpret_cast<uint32_t *>(B8h)[e] = tc::pack_e5m2x2(hf[0] * dn, hf[1] * dn) |
+                                               (tc::pack_e5m2x2(hf[2] * dn, hf[3] * dn) << 16);
+        reinterpret_cast<uint32_t *>(B8l)[e] = tc::pack_e5m2x2(lo[0], lo[1]) | (tc::pack_e5m2x2(lo[2], lo[3]) << 16);
+    }
+    if (e < nrm_rows) nrm[e] = (e < n) ? -r[e] * half_l2e_over_h2 : -INFINITY;
+}
+
 // ---- host side -----------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -1119,6 +1262,7 @@ int64_t flash_tc_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t 
     b += (p1.cols + 256) * 4;                           // nrm
     b += centred_bytes(p1.cols, p1.DP);                 // centred particles, their norms, column means
     b += ((int64_t)CM_BLOCKS + 2) * p1.DP * 4 + 64;     // column maxima / scales of Y (mixed-precision GEMM2)
+    b += p1.cols * p1.DP * 2 + 64;                      // b8h, b8l of X (mixed-precision GEMM1)
     b += std::max(slot_bytes(p1), slot_bytes(p2));
     b += FINALIZE_MAX_BLOCKS * 8;
     return b + 4096;
@@ -1298,7 +1442,9 @@ bool flash_tc2_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total,
 
 int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all, int64_t n_total,
                   int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
-                  int64_t ws_bytes, float *phi, double *sumsq, bool g2f8) {
+                  int64_t ws_bytes, float *phi, double *sumsq, int mode) {
+    // mode 0: BF16x3 for both GEMMs; 1: mixed-precision GEMM2; 2: mixed precision for both
+    const bool g2f8 = mode >= 1, g1f8 = mode >= 2;
     const FlashPlan pl = flash_plan(ctx, n_local, n_total, d, true);
     const int64_t rows = pl.rows, cols = pl.cols, DP = FL_MAX_DP;
     STEIN_REQUIRE(ctx, ld == DP, "CTA-pair flash phi needs ld == 256");
@@ -1325,12 +1471,26 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
     float *cmax_part = (float *)pws;     pws += (int64_t)CM_BLOCKS * DP * 4;
     float *cs_down = (float *)pws;       pws += DP * 4;
     float *cs_up = (float *)pws;         pws += DP * 4;
+    float *xscale = (float *)pws;        pws += 16;       // [0] = 2^-e on X, [1] = 2^(2e) on c1
+    uint8_t *B8h = (uint8_t *)pws;       pws += cols * DP;
+    uint8_t *B8l = (uint8_t *)pws;       pws += cols * DP;
 
     const float l2e = 1.4426950408889634f;
     {
         const int64_t tot = std::max<int64_t>(cols * DP / 4, cols + 256);
-        prep_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(Xc, rc, cols, n_total, ld,
-                                                                             0.5f * l2e / h2, Xh, Xl, nrm, cols + 256);
+        if (g1f8) {
+            // FP16 array in the place of Xh; a8l, a8h share the place of Xl; b8h, b8l have their own
+            absmax_partial_kernel<<<CM_BLOCKS, 256, 0, ctx->stream>>>(Xc, n_total, ld, cmax_part);
+            STEIN_CHECK_LAUNCH(ctx);
+            xscale_kernel<<<1, 1024, 0, ctx->stream>>>(cmax_part, (int64_t)CM_BLOCKS * DP, xscale);
+            STEIN_CHECK_LAUNCH(ctx);
+            prep_x8_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(
+                Xc, rc, cols, n_total, ld, 0.5f * l2e / h2, xscale, (__half *)Xh, (uint8_t *)Xl, (uint8_t *)Xl + cols * DP,
+                B8h, B8l, nrm, cols + 256);
+        } else {
+            prep_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(Xc, rc, cols, n_total, ld,
+                                                                                 0.5f * l2e / h2, Xh, Xl, nrm, cols + 256);
+        }
         STEIN_CHECK_LAUNCH(ctx);
         dim3 g((unsigned)(cols / 32), (unsigned)(DP / 32)), b(32, 8);
         if (g2f8) {
@@ -1347,16 +1507,28 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
         STEIN_CHECK_LAUNCH(ctx);
     }
     STEIN_TRY(plan_upload(ctx, 1, tile_nslots, n_local, n_total, d, &d_tile_nslots));
-    CUtensorMap mXh, mXl, mXh64, mXl64, mYh, mYl, mY8h, mY8l;
-    STEIN_TRY(make_tensor_map_2d(ctx, &mXh, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
-    STEIN_TRY(make_tensor_map_2d(ctx, &mXl, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
-    STEIN_TRY(make_tensor_map_2d(ctx, &mXh64, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
-    STEIN_TRY(make_tensor_map_2d(ctx, &mXl64, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
-    STEIN_TRY(make_tensor_map_2d(ctx, &mYh, YTh, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
-    STEIN_TRY(make_tensor_map_2d(ctx, &mYl, YTl, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
-    // FP8 arrays: [DP][cols] bytes, box = 128 particles x 128 rows
-    STEIN_TRY(make_tensor_map_2d(ctx, &mY8h, YTl, 1, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols, 128));
-    STEIN_TRY(make_tensor_map_2d(ctx, &mY8l, (uint8_t *)YTl + cols * DP, 1, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols, 128));
+    Phi2Maps maps;
+    memset(&maps, 0, sizeof(maps));
+    STEIN_TRY(make_tensor_map_2d(ctx, &maps.xa_hi, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
+    STEIN_TRY(make_tensor_map_2d(ctx, &maps.xb_hi, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
+    if (g1f8) {   // FP8 arrays of X: [cols][DP] bytes
+        uint8_t *A8l = (uint8_t *)Xl, *A8h = (uint8_t *)Xl + cols * DP;
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.a8l, A8l, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 128));
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.a8h, A8h, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 128));
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.b8h, B8h, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 64));
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.b8l, B8l, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 64));
+    } else {
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.xa_lo, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.xb_lo, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
+    }
+    STEIN_TRY(make_tensor_map_2d(ctx, &maps.yh, YTh, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
+    if (g2f8) {   // FP8 arrays of Y^T: [DP][cols] bytes, box = 128 particles x 128 rows
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.y8h, YTl, 1, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols, 128));
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.y8l, (uint8_t *)YTl + cols * DP, 1, (uint64_t)cols, (uint64_t)DP,
+                                     (uint64_t)cols, 128));
+    } else {
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.yl, YTl, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
+    }
 
     Flash2Params p{};
     p.nJ = (int)nJ;
@@ -1366,21 +1538,26 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
     p.nrm = nrm;
     p.out = L;
     p.row_begin = row_begin;
+    p.c1mul = g1f8 ? xscale + 1 : nullptr;
     const size_t smem = flash_smem_bytes(DP);
     static bool attr_set = false;
     if (!attr_set) {
-        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)smem));
-        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)smem));
+        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi2_kernel<false, false>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi2_kernel<false, true>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi2_kernel<true, true>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     {
         RegionTimer timer(ctx, STEIN_REGION_PHI);
-        if (g2f8)
-            flash_phi2_kernel<true><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(mXh, mXl, mXh64, mXl64, mYh, mYl, mY8h, mY8l, p);
+        if (g1f8)
+            flash_phi2_kernel<true, true><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(maps, p);
+        else if (g2f8)
+            flash_phi2_kernel<false, true><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(maps, p);
         else
-            flash_phi2_kernel<false><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(mXh, mXl, mXh64, mXl64, mYh, mYl, mY8h, mY8l, p);
+            flash_phi2_kernel<false, false><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(maps, p);
         STEIN_CHECK_LAUNCH(ctx);
     }
     const int64_t rows_valid = std::max<int64_t>(0, std::min<int64_t>(n_local, n_total - row_begin));

@@ -252,6 +252,15 @@ __device__ __forceinline__ void umma2_f16_ts(uint32_t d_tmem, uint32_t a_tmem, u
         : "memory");
 }
 
+// FP8 operands (kind::f8f6f4, K = 32 per instruction), both from shared memory, CTA pair
+__device__ __forceinline__ void umma2_f8_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // FP8 operands (kind::f8f6f4, K = 32 per instruction), A from tensor memory (four 8-bit elements
 // per 32-bit column), CTA pair
 __device__ __forceinline__ void umma2_f8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,

@@ -268,20 +268,21 @@ def test_phi_flash_cta_pair_matches_oracle(ctx, n, d, scale):
     assert abs(sumsq - (phi ** 2).sum()) <= 1e-6 * (phi ** 2).sum()
 
 
+@pytest.mark.parametrize("mode", ["gemm2", "both"])
 @pytest.mark.parametrize("n,d,scale", [(128, 256, 1.0), (640, 256, 1.0), (3000, 256, 1.0), (2500, 250, 0.01),
-                                       (5000, 230, 1.0)])
-def test_phi_flash_mixed_precision_gemm2_matches_oracle(ctx, n, d, scale):
-    """CTA-pair kernel with GEMM2 as one FP16 pass + two FP8 passes (instead of three BF16
-    passes): same 1e-4 bar against the oracle; also with scores of very different column scales
-    (the FP16 / FP8 operands are column-scaled by powers of two)."""
+                                       (5000, 230, 1.0), (2000, 256, 1e-4), (2000, 256, 300.0)])
+def test_phi_flash_mixed_precision_matches_oracle(ctx, n, d, scale, mode):
+    """CTA-pair kernel with GEMM2 (and GEMM1) as one FP16 pass + two FP8 passes instead of three
+    BF16 passes: same 1e-4 bar against the oracle; with scores of very different column scales and
+    particles of very different overall scales (the FP16 / FP8 operands are scaled by powers of two)."""
     from stein_b200 import _lib
     X = _particles(n, d, 3 * n + d, scale)
     S = _particles(n, d, 5 * n + d, 1.0) - X
     S *= np.logspace(-3, 4, d, dtype=np.float32)[None, :]
-    phi, sumsq, bw = _phi_gpu(ctx, X, S, _lib.PHI_FLASH_TC3)
+    phi, sumsq, bw = _phi_gpu(ctx, X, S, _lib.PHI_FLASH_TC3 if mode == "gemm2" else _lib.PHI_FLASH_TC4)
     ref = orc.compute_phi(X, S.astype(np.float64))
     fro, mx = _rel(phi, ref)
-    print("mixed GEMM2: fro %.2e max %.2e" % (fro, mx))
+    print("mixed %s: fro %.2e max %.2e" % (mode, fro, mx))
     # column-wise: every column must be right relative to its own scale
     col = np.abs(phi - ref).max(axis=0) / np.abs(ref).max(axis=0)
     assert col.max() <= RTOL_PHI, col.max()
@@ -300,7 +301,7 @@ def _phi_float64(X, S, bw):
     return (K @ S64 + dK) / X.shape[0]
 
 
-@pytest.mark.parametrize("impl", ["flash", "pair", "pair_f8"])
+@pytest.mark.parametrize("impl", ["flash", "pair", "pair_f8", "pair_f8x2"])
 @pytest.mark.parametrize("offset", [1.0, 10.0])
 def test_phi_flash_offset_cloud(ctx, impl, offset):
     """A particle cloud away from the origin (|mean|^2 >> spread^2).  The Gram form of the
@@ -315,7 +316,8 @@ def test_phi_flash_offset_cloud(ctx, impl, offset):
     Z = rng.standard_normal((n, d))
     X = (offset + 0.1 * Z).astype(np.float32)
     S = (rng.standard_normal((n, d)) - 10.0 * Z).astype(np.float32)
-    code = {"flash": _lib.PHI_FLASH_TC, "pair": _lib.PHI_FLASH_TC2, "pair_f8": _lib.PHI_FLASH_TC3}[impl]
+    code = {"flash": _lib.PHI_FLASH_TC, "pair": _lib.PHI_FLASH_TC2, "pair_f8": _lib.PHI_FLASH_TC3,
+            "pair_f8x2": _lib.PHI_FLASH_TC4}[impl]
     phi, sumsq, bw = _phi_gpu(ctx, X, S, code)
     assert bw.tobytes() == orc.kernel_and_grad(X)[2].tobytes()
     _assert_close(phi, _phi_float64(X, S, bw))
