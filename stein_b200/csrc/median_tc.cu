@@ -36,11 +36,14 @@ constexpr int SW_EPI_THREADS = 256;
 constexpr int SW_STAGES = 12;
 constexpr uint32_t SW_UNIT_BYTES = 128 * 128;
 constexpr int SW_EPI_WARPS = SW_EPI_THREADS / 32;
-constexpr int SW_WARP_CAP = 128;            // entries a classification warp stages between two flushes
+constexpr int SW2_EPI_WG = 4;               // pair kernel: four classification warpgroups, one 32-column chunk per warp
+constexpr int SW2_THREADS = 128 + 128 * SW2_EPI_WG;
+constexpr int SW_WARP_CAP = 128;            // entries a classification warp of the 8-warp layout stages between flushes
+// (the tail below is sized for 8 warps x 128 entries x 64 columns = 16 warps x 64 entries x 32 columns)
 // shared-memory tail after the operand buffers (both sweep kernels): barriers at +0 (256 B),
 // tensor-memory base at +256, per-warp staging counters at +288, then the arrays below
 constexpr size_t SW_TAIL_COUNTS = 288;
-constexpr size_t SW_TAIL_BUF = 320;                                             // PairEntry [warps][SW_WARP_CAP]
+constexpr size_t SW_TAIL_BUF = 384;                                             // PairEntry [warps][entries] (counts: up to 16 warps x 4 B from +288)
 constexpr size_t SW_TAIL_COL = SW_TAIL_BUF + (size_t)SW_EPI_WARPS * SW_WARP_CAP * 12;   // float [warps][64]
 constexpr size_t SW_TAIL_HIST = SW_TAIL_COL + (size_t)SW_EPI_WARPS * 64 * 4;    // u32 [SW_HIST_BINS]
 constexpr int SW_HIST_BINS = 4096;          // histogram of the listed D~ (locates t~ without extra passes)
@@ -123,10 +126,15 @@ __device__ __forceinline__ void next_tile(int &I, int &J, int T) {
 // Each classification warp is self-contained: it derives the column terms of its own 64 columns
 // and stages its listed pairs in its own shared-memory buffer, so the warps of a CTA never wait
 // for each other (the block-wide named barriers of the first version cost 10 % of the sweep).
+template <int NWG>   // classification warpgroups: 2 (each warp two 32-column chunks) or 4 (one chunk)
 struct TileClassifier {
+    static constexpr int CHUNKS = 4 / NWG;           // 32-column chunks per warp
+    static constexpr int WCOLS = 32 * CHUNKS;        // columns per warp
+    static constexpr int WCAP = SW_WARP_CAP * 2 / NWG;   // staged entries per warp
+    static constexpr int ETHREADS = 128 * NWG;
     const SweepParams &p;
-    PairEntry *wBuf;             // [SW_WARP_CAP] staging of this warp
-    float *wCol;                 // [64] column terms B_j of this warp's two 32-column chunks
+    PairEntry *wBuf;             // [WCAP] staging of this warp
+    float *wCol;                 // [WCOLS] column terms B_j of this warp's chunk(s)
     unsigned int *sHist, *wCount;
     int wg, row, lane;
     uint32_t lane_addr;
@@ -135,10 +143,10 @@ struct TileClassifier {
 
     __device__ TileClassifier(const SweepParams &p_, uint8_t *tail, int warp, int lane_)
         : p(p_), lane(lane_), below(0u), listed(0u) {
-        const int ew = warp - 4;                     // classification warp index 0..7
+        const int ew = warp - 4;                     // classification warp index
         wCount = reinterpret_cast<unsigned int *>(tail + SW_TAIL_COUNTS) + ew;
-        wBuf = reinterpret_cast<PairEntry *>(tail + SW_TAIL_BUF) + (size_t)ew * SW_WARP_CAP;
-        wCol = reinterpret_cast<float *>(tail + SW_TAIL_COL) + ew * 64;
+        wBuf = reinterpret_cast<PairEntry *>(tail + SW_TAIL_BUF) + (size_t)ew * WCAP;
+        wCol = reinterpret_cast<float *>(tail + SW_TAIL_COL) + ew * WCOLS;
         sHist = reinterpret_cast<unsigned int *>(tail + SW_TAIL_HIST);
         const int q = warp & 3;
         wg = ew >> 2;
@@ -164,12 +172,13 @@ struct TileClassifier {
         if (w == 0u) return;
         const bool row_ok = i < p.n;
         const float r_i = row_ok ? p.r[i] : 0.0f;
-        const float *rj = p.r + (size_t)J * 128 + wg * 64;       // this warp's 64 columns
+        const float *rj = p.r + (size_t)J * 128 + wg * WCOLS;    // this warp's columns
         // column terms (the previous tile's are no longer read: same warp, program order)
         {
-            const long long j0 = (long long)J * 128 + wg * 64 + lane;
-            wCol[lane] = j0 < p.n ? cm * __ldg(rj + lane) : INFINITY;
-            wCol[32 + lane] = j0 + 32 < p.n ? cm * __ldg(rj + 32 + lane) : INFINITY;
+            const long long j0 = (long long)J * 128 + wg * WCOLS + lane;
+#pragma unroll
+            for (int cc = 0; cc < CHUNKS; ++cc)
+                wCol[32 * cc + lane] = j0 + 32 * cc < p.n ? cm * __ldg(rj + 32 * cc + lane) : INFINITY;
             __syncwarp();
         }
         const float slack = (r_i + rmax) * 9.5367431640625e-07f;   // 2^-20
@@ -177,8 +186,8 @@ struct TileClassifier {
         const float lo_i = row_ok ? cm * r_i - 0.5f * p.whi - 2.0f * slack : INFINITY;
         const float hi_i = row_ok ? cp * r_i + p.c_half * rmax - 0.5f * p.wlo + 2.0f * slack : INFINITY;
 #pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-            const int ch = wg * 2 + cc;
+        for (int cc = 0; cc < CHUNKS; ++cc) {
+            const int ch = wg * CHUNKS + cc;
             const long long jbase = (long long)J * 128 + ch * 32;
             uint32_t v[32];
             tmem_ld32(s_tmem + lane_addr + ch * 32, v);
@@ -219,7 +228,7 @@ struct TileClassifier {
                     e.i = (uint32_t)i;
                     e.jw = (uint32_t)(jbase + c) | (w == 2u ? 0x80000000u : 0u);
                     e.dt = fmaf(-2.0f, g, r_i + __ldg(rj + cc * 32 + c));
-                    if (slot < (unsigned)SW_WARP_CAP) {
+                    if (slot < (unsigned)WCAP) {
                         wBuf[slot] = e;
                     } else {   // staging full (degenerate data): straight to global
                         const unsigned long long gi = atomicAdd(p.cnt_len, 1ull);
@@ -236,8 +245,8 @@ struct TileClassifier {
     // half full (or at the last tile) -- one global reservation per flush
     __device__ void flush(bool last) {
         __syncwarp();
-        const unsigned int have = min(*wCount, (unsigned)SW_WARP_CAP);
-        if (!(have > (unsigned)SW_WARP_CAP / 2 || (last && have > 0))) return;
+        const unsigned int have = min(*wCount, (unsigned)WCAP);
+        if (!(have > (unsigned)WCAP / 2 || (last && have > 0))) return;
         unsigned long long base = 0ull;
         if (lane == 0) base = atomicAdd(p.cnt_len, (unsigned long long)have);
         base = __shfl_sync(0xffffffffu, base, 0);
@@ -262,8 +271,8 @@ struct TileClassifier {
             if (below) atomicAdd(p.cnt_below, (unsigned long long)below);
             if (listed) atomicAdd(p.cnt_listed, (unsigned long long)listed);
         }
-        named_bar_sync(3, SW_EPI_THREADS);
-        for (int b = ew_tid; b < SW_HIST_BINS; b += SW_EPI_THREADS) {
+        named_bar_sync(3, ETHREADS);
+        for (int b = ew_tid; b < SW_HIST_BINS; b += ETHREADS) {
             const unsigned int v = sHist[b];
             if (v) atomicAdd(&p.hist[b], (unsigned long long)v);
         }
@@ -401,7 +410,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         // ===================== classification warpgroups =====================
-        TileClassifier tc(p, tail, warp, lane);
+        TileClassifier<2> tc(p, tail, warp, lane);
         const int wg = tc.wg, row = tc.row;
         const uint32_t lane_addr = tc.lane_addr;
         const int wpr = p.kblocks * 32;             // 32-bit words per row of Xh / Xl
@@ -500,7 +509,7 @@ static int64_t num_pair_tiles(int64_t T) {
     return nt;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SW_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SW2_THREADS, 1)
 sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
                  const __grid_constant__ CUtensorMap mapXh64, const __grid_constant__ CUtensorMap mapXl64,
                  const SweepParams p) {
@@ -530,7 +539,7 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
         mbar_init(&bars->a_empty, 1);                // multicast commit
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->s_full[b], 1);                        // multicast commit
-            mbar_init(&bars->s_empty[b], 2 * SW_EPI_WARPS);        // leader: both CTAs' classification warps
+            mbar_init(&bars->s_empty[b], 2 * 4 * SW2_EPI_WG);      // leader: both CTAs' classification warps
         }
         fence_barrier_init();
         fence_proxy_async();
@@ -539,7 +548,7 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
         tma_prefetch_desc(&mapXh64);
         tma_prefetch_desc(&mapXl64);
     }
-    for (int b = threadIdx.x; b < SW_HIST_BINS; b += SW_THREADS) sHist[b] = 0u;
+    for (int b = threadIdx.x; b < SW_HIST_BINS; b += SW2_THREADS) sHist[b] = 0u;
     if (warp == 1) tmem_alloc_pair(tmem_slot, SW2_TMEM_COLS);
     tcgen05_fence_before();
     __syncthreads();
@@ -548,7 +557,9 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
     const uint32_t tmem = *tmem_slot;
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // 640 threads: 96 registers each at launch; the two control warps give theirs to nobody
+        // (128 x 48 + 512 x 104 = 59 392 <= 65 536)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         if (warp == 0) {
             // ===================== TMA producer (both CTAs) =====================
             int stage = 0;
@@ -635,9 +646,9 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ===================== classification warpgroups (both CTAs, own 128 rows) =====================
-        TileClassifier tc(p, tail, warp, lane);
+        TileClassifier<SW2_EPI_WG> tc(p, tail, warp, lane);
         const uint32_t s_empty_addr0 = mapa_shared(smem_u32(&bars->s_empty[0]), 0);
         const uint32_t s_empty_addr1 = mapa_shared(smem_u32(&bars->s_empty[1]), 0);
         long long jj = 0;
@@ -1052,7 +1063,7 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
             STEIN_TRY(make_tensor_map_2d(ctx, &mapXh64, A.Xh, 2, (uint64_t)DP, (uint64_t)rows, (uint64_t)DP * 2, 64));
             STEIN_TRY(make_tensor_map_2d(ctx, &mapXl64, A.Xl, 2, (uint64_t)DP, (uint64_t)rows, (uint64_t)DP * 2, 64));
             const int clusters = (int)std::min<int64_t>(ctx->num_sms / 2, t1 - t0);
-            sweep2_tc_kernel<<<2 * clusters, SW_THREADS, smem2, ctx->stream>>>(mapXh, mapXl, mapXh64, mapXl64, p);
+            sweep2_tc_kernel<<<2 * clusters, SW2_THREADS, smem2, ctx->stream>>>(mapXh, mapXl, mapXh64, mapXl64, p);
         } else {
             const int grid = (int)std::min<int64_t>(ctx->num_sms, t1 - t0);
             sweep_tc_kernel<<<grid, SW_THREADS, smem1, ctx->stream>>>(mapXh, mapXl, p);
