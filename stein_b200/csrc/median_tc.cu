@@ -1150,3 +1150,7 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
 }
 
 }  // namespace stein
+
+// Test hooks (pure host functions): enumeration of the CTA-pair sweep's tiles.
+extern "C" long long stein_debug_num_pair_tiles(long long T) { return stein::num_pair_tiles(T); }
+extern "C" void stein_debug_pair_tile(long long t, int T, int *I2, int *J) { stein::pair_tile(t, T, *I2, *J); }

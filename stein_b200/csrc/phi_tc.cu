@@ -115,12 +115,12 @@ struct SegWalk {
     TileSchedule sc;
     int c, k;
     long long pos, end;
-    __device__ SegWalk(int nI, int nJ, int G, int c_) : sc(nI, nJ, G), c(c_), k(0) {
+    __host__ __device__ SegWalk(int nI, int nJ, int G, int c_) : sc(nI, nJ, G), c(c_), k(0) {
         pos = (long long)c * sc.chunk;
         end = pos + sc.chunk;
         if (end > sc.W) end = sc.W;
     }
-    __device__ bool next(int &t, int &j0, int &j1, int &slot) {
+    __host__ __device__ bool next(int &t, int &j0, int &j1, int &slot) {
         if (k < sc.rounds) {
             t = k * sc.G + c;
             j0 = 0;
@@ -1587,6 +1587,29 @@ extern "C" int stein_debug_flash_gram(stein_ctx *ctx, const float *X_dev, const 
                                        ws_bytes, phi_dev, sumsq_dev);
     stein::g_debug_dumpS = nullptr;
     return rc;
+}
+
+// Test hook (pure host function): the segments (row tile, column range, slot) that unit `unit` of
+// `G` walks for nI row tiles x nJ column tiles, and the slot count of every row tile -- the
+// schedule both flash kernels and their launchers share.  Returns the number of segments.
+extern "C" int stein_debug_tile_schedule(int nI, int nJ, int G, int unit, int max_segs, int *t, int *j0, int *j1,
+                                         int *slot, int *tile_nslots /* [nI] or NULL */) {
+    stein::SegWalk w(nI, nJ, G, unit);
+    int n = 0, a, b, c, d;
+    while (w.next(a, b, c, d)) {
+        if (n < max_segs) {
+            t[n] = a;
+            j0[n] = b;
+            j1[n] = c;
+            slot[n] = d;
+        }
+        ++n;
+    }
+    if (tile_nslots) {
+        const stein::TileSchedule sc(nI, nJ, G);
+        for (int i = 0; i < nI; ++i) tile_nslots[i] = sc.nslots(i);
+    }
+    return n;
 }
 
 // Test/debug hook: install a host-mapped buffer (>= 1 + 16 * grid words) that receives the

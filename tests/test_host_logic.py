@@ -194,3 +194,71 @@ def test_shard_plans_cover_everything_once(n, world):
     assert all(tiles[r][1] == tiles[r + 1][0] for r in range(world - 1))
     sizes = [b - a for a, b in tiles]
     assert max(sizes) - min(sizes) <= 1
+
+
+# --------------------------------------------------------------------------- #
+# work schedules of the tensor-core kernels (pure host functions of the .so)   #
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("nI,nJ,G", [(256, 512, 74), (512, 512, 148), (128, 512, 74), (64, 512, 74), (32, 512, 74),
+                                     (1, 1, 74), (1, 40, 74), (75, 3, 74), (3, 1000, 148), (147, 17, 148),
+                                     (149, 17, 148), (10, 5, 1)])
+def test_phi_tile_schedule_covers_every_tile_pair_once(lib, nI, nJ, G):
+    """TileSchedule / SegWalk (csrc/phi_tc.cu): over all units, every (row tile, column tile) pair
+    is visited exactly once; the partial results of a row tile land in distinct slots
+    0..nslots-1 with nslots <= 8; and the units' loads differ by at most one chunk."""
+    fn = lib.stein_debug_tile_schedule
+    fn.restype = ctypes.c_int
+    IntP = ctypes.POINTER(ctypes.c_int)
+    fn.argtypes = [ctypes.c_int] * 5 + [IntP] * 5
+    cover = np.zeros((nI, nJ), np.int32)
+    slots = [set() for _ in range(nI)]
+    nslots = (ctypes.c_int * nI)()
+    loads = []
+    cap = nI // G + 4
+    for c in range(G):
+        t, j0, j1, sl = ((ctypes.c_int * cap)() for _ in range(4))
+        n = fn(nI, nJ, G, c, cap, t, j0, j1, sl, nslots)
+        assert n <= cap
+        load = 0
+        for k in range(n):
+            assert 0 <= t[k] < nI and 0 <= j0[k] < j1[k] <= nJ
+            cover[t[k], j0[k]:j1[k]] += 1
+            assert sl[k] not in slots[t[k]]
+            slots[t[k]].add(sl[k])
+            load += j1[k] - j0[k]
+        loads.append(load)
+    assert (cover == 1).all()
+    for i in range(nI):
+        assert slots[i] == set(range(nslots[i])) and 1 <= nslots[i] <= 8
+    rem = nI % G
+    chunk = max(-(-rem * nJ // G), -(-nJ // 7), 1)
+    assert max(loads) - min(l for l in loads if l > 0 or rem == 0) <= chunk
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 4, 33, 40, 512])
+def test_pair_sweep_tile_enumeration(lib, T):
+    """The CTA-pair median sweep walks pair rows I2 and column tiles J >= 2 I2 in row-major order
+    (csrc/median_tc.cu pair_tile): together with the weights J > I -> 2, J == I -> 1, J < I -> 0
+    every unordered tile pair {I, J} of the T x T tile grid is weighted as in the full matrix."""
+    num = lib.stein_debug_num_pair_tiles
+    num.restype, num.argtypes = ctypes.c_longlong, [ctypes.c_longlong]
+    pt = lib.stein_debug_pair_tile
+    pt.restype, pt.argtypes = None, [ctypes.c_longlong, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                      ctypes.POINTER(ctypes.c_int)]
+    nt = num(T)
+    assert nt == sum(T - 2 * i2 for i2 in range((T + 1) // 2))
+    weight = np.zeros((T + 1, T), np.int64)
+    I2, J = ctypes.c_int(), ctypes.c_int()
+    prev = (-1, -1)
+    for t in range(nt):
+        pt(t, T, ctypes.byref(I2), ctypes.byref(J))
+        assert (I2.value, J.value) > prev and 2 * I2.value <= J.value < T
+        prev = (I2.value, J.value)
+        for rank in (0, 1):
+            I = 2 * I2.value + rank
+            weight[I, J.value] += 2 if J.value > I else (1 if J.value == I else 0)
+    assert weight[T].sum() == 0                            # the phantom row tile of an odd T weighs nothing
+    full = weight[:T]
+    assert full.sum() == T * T                             # = all entries of the full (symmetric) matrix
+    iu, il = np.triu_indices(T, 1), np.tril_indices(T, -1)
+    assert (np.diag(full) == 1).all() and (full[iu] == 2).all() and (full[il] == 0).all()
