@@ -36,6 +36,26 @@ def algorithmic_flops_phi(n, d):
     return 2.0 * n * n * (3 * d + 1)
 
 
+def ncu_traffic(kernel_substr):
+    """DRAM bytes per launch (read + write) of the dominant kernel from the committed ncu
+    --set full summary (profiles/, written by tools/ncu_summary.py), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
+    try:
+        data = json.load(open(path))
+    except (OSError, ValueError):
+        return None, None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for rec in data.get("launches", []):
+        if kernel_substr in rec.get("kernel", ""):
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                if key not in rec:
+                    return None, None
+                tot += float(rec[key]) * scale.get(rec.get("_units", {}).get(key, "byte"), 1.0)
+            return tot, os.path.relpath(path, ROOT)
+    return None, None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -265,8 +285,17 @@ def run_ours(args):
     phi_avg_ms = phi_ms.value / max(phi_n.value, 1)
     achieved = f_phi / (phi_avg_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
-    impl = {0: "auto", 1: "dense_simt_fp32", 2: "flash_tcgen05", 3: "flash_tcgen05_cta_pair",
-            4: "flash_tcgen05_cta_pair_fp8_gemm2", 5: "flash_tcgen05_cta_pair_fp8_gemm1_gemm2"}[args_phi_impl_code(ctx, args)]
+    code = args_phi_impl_code(ctx, args)
+    if code == 0:       # what AUTO resolves to (stein_b200/csrc/ctx.cu pick_phi_impl)
+        ldp = (d + 31) // 32 * 32
+        code = 5 if ldp == 256 else (2 if ldp == 128 else 1)
+    impl = {1: "dense_simt_fp32", 2: "flash_tcgen05", 3: "flash_tcgen05_cta_pair",
+            4: "flash_tcgen05_cta_pair_fp8_gemm2", 5: "flash_tcgen05_cta_pair_fp16_fp8"}[code]
+    executed = {1: "FP32 FFMA", 2: "3 BF16 passes per GEMM", 3: "3 BF16 passes per GEMM",
+                4: "GEMM1 3 BF16 passes; GEMM2 1 FP16 + 2 FP8 passes",
+                5: "1 FP16 + 2 FP8 passes per GEMM (= 2 BF16-pass equivalents of tensor time each)"}[code]
+    traffic, traffic_src = ncu_traffic("flash_phi2_kernel") if (code >= 3 and world == 1 and (n, d) == (N_PARTICLES, DIM)) \
+        else (None, None)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -281,8 +310,9 @@ def run_ours(args):
         "wall_s_timed_region": wall,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "phi (%s)" % impl, "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peaks["source"] + ", bf16 dense sustained",
+                     "executed_arithmetic": executed,
                      "algorithmic_flops_per_launch": f_phi, "avg_launch_ms": phi_avg_ms,
                      "launches_timed": int(phi_n.value),
                      "share_of_step": phi_ms.value / total_ms if world == 1 else None,

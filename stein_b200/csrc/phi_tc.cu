@@ -943,14 +943,22 @@ flash_phi2_kernel(const __grid_constant__ Phi2Maps maps, const Flash2Params p) {
 // which is ample for a cloud around the origin and useless for one that sits away from it
 // (posterior mass at |mean| >> spread).  The flash kernels therefore work on X - mean(X):
 // K, sum_j K_ij and sum_j K_ij (x_i - x_j) are translation invariant.
-constexpr int CM_BLOCKS = 256;
+constexpr int CM_BLOCKS = 1024;
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const float *__restrict__ X, int64_t n, int64_t ld, double *__restrict__ part /* [CM_BLOCKS][ld] */) {
-    // block b sums rows b, b + CM_BLOCKS, ...; thread c owns column c (coalesced row reads)
+    // block b sums rows b, b + CM_BLOCKS, ...; thread c owns column c (coalesced row reads);
+    // four rows in flight per thread, combined in a fixed order
     for (int64_t c = threadIdx.x; c < ld; c += blockDim.x) {
-        double acc = 0.0;
-        for (int64_t i = blockIdx.x; i < n; i += CM_BLOCKS) acc += (double)X[i * ld + c];
-        part[(int64_t)blockIdx.x * ld + c] = acc;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int64_t i = blockIdx.x;
+        for (; i + 3 * CM_BLOCKS < n; i += 4 * CM_BLOCKS) {
+            a0 += (double)X[i * ld + c];
+            a1 += (double)X[(i + CM_BLOCKS) * ld + c];
+            a2 += (double)X[(i + 2 * CM_BLOCKS) * ld + c];
+            a3 += (double)X[(i + 3 * CM_BLOCKS) * ld + c];
+        }
+        for (; i < n; i += CM_BLOCKS) a0 += (double)X[i * ld + c];
+        part[(int64_t)blockIdx.x * ld + c] = (a0 + a1) + (a2 + a3);
     }
 }
 __global__ void colmean_kernel(const double *__restrict__ part, int64_t n, int64_t ld, float *__restrict__ mean) {
@@ -960,23 +968,39 @@ __global__ void colmean_kernel(const double *__restrict__ part, int64_t n, int64
     for (int b = 0; b < CM_BLOCKS; ++b) acc += part[(int64_t)b * ld + c];      // fixed order
     mean[c] = (float)(acc / (double)n);
 }
-// Xc = X - mean for the n valid rows (pad rows and pad columns stay zero); rc_i = |Xc_i|^2.
-// One warp per row.
+// Xc = X - mean for the n valid rows (pad rows and pad columns stay zero); rc_i = |Xc_i|^2;
+// blockmax[b] = largest |entry| of the block's 8 rows (for the power-of-two scale of the
+// mixed-precision operands).  One warp per row.
 __global__ void __launch_bounds__(256)
 center_kernel(const float *__restrict__ X, const float *__restrict__ mean, int64_t n, int64_t rows, int64_t d,
-              int64_t ld, float *__restrict__ Xc, float *__restrict__ rc) {
+              int64_t ld, float *__restrict__ Xc, float *__restrict__ rc, float *__restrict__ blockmax) {
+    __shared__ float wmax[8];
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    float acc = 0.0f;
-    for (int64_t c = lane; c < ld; c += 32) {
-        const float v = (row < n && c < d) ? X[row * ld + c] - mean[c] : 0.0f;
-        Xc[row * ld + c] = v;
-        acc = fmaf(v, v, acc);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc = 0.0f, m = 0.0f;
+    if (row < rows) {
+        for (int64_t c = lane; c < ld; c += 32) {
+            const float v = (row < n && c < d) ? X[row * ld + c] - mean[c] : 0.0f;
+            Xc[row * ld + c] = v;
+            acc = fmaf(v, v, acc);
+            m = fmaxf(m, fabsf(v));
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) rc[row] = acc;
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    if (lane == 0) {
+        if (row < rows) rc[row] = acc;
+        wmax[warp] = m;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float bm = wmax[0];
+        for (int w = 1; w < 8; ++w) bm = fmaxf(bm, wmax[w]);
+        blockmax[blockIdx.x] = bm;
+    }
 }
 
 // ---- operand preparation ------------------------------------------------------------
@@ -1032,9 +1056,14 @@ __global__ void __launch_bounds__(256)
 colmax_partial_kernel(const float *__restrict__ X, const float *__restrict__ S, int64_t n, int64_t ld, float inv_h2,
                       float *__restrict__ part /* [CM_BLOCKS][ld] */) {
     for (int64_t c = threadIdx.x; c < ld; c += blockDim.x) {
-        float m = 0.0f;
-        for (int64_t i = blockIdx.x; i < n; i += CM_BLOCKS) m = fmaxf(m, fabsf(S[i * ld + c] - X[i * ld + c] * inv_h2));
-        part[(int64_t)blockIdx.x * ld + c] = m;
+        float m0 = 0.0f, m1 = 0.0f;
+        int64_t i = blockIdx.x;
+        for (; i + CM_BLOCKS < n; i += 2 * CM_BLOCKS) {
+            m0 = fmaxf(m0, fabsf(S[i * ld + c] - X[i * ld + c] * inv_h2));
+            m1 = fmaxf(m1, fabsf(S[(i + CM_BLOCKS) * ld + c] - X[(i + CM_BLOCKS) * ld + c] * inv_h2));
+        }
+        if (i < n) m0 = fmaxf(m0, fabsf(S[i * ld + c] - X[i * ld + c] * inv_h2));
+        part[(int64_t)blockIdx.x * ld + c] = fmaxf(m0, m1);
     }
 }
 __global__ void colscale_kernel(const float *__restrict__ part, int64_t ld, float *__restrict__ down,
@@ -1075,14 +1104,6 @@ __global__ void prep_yt8_kernel(const float *__restrict__ X, const float *__rest
 // [128, 256), then split as  x16 = fp16(x'),  a8l = e4m3((x' - x16) 2^12),  a8h = e4m3(x16),
 // b8h = e5m2(x16 2^-12),  b8l = e5m2(x' - x16):
 //   x_i . x_j ~ x16_i . x16_j + a8l_i . b8h_j + a8h_i . b8l_j        (all on the scale 2^-2e)
-__global__ void __launch_bounds__(256)
-absmax_partial_kernel(const float *__restrict__ X, int64_t n, int64_t ld, float *__restrict__ part /* [CM_BLOCKS][ld] */) {
-    for (int64_t c = threadIdx.x; c < ld; c += blockDim.x) {
-        float m = 0.0f;
-        for (int64_t i = blockIdx.x; i < n; i += CM_BLOCKS) m = fmaxf(m, fabsf(X[i * ld + c]));
-        part[(int64_t)blockIdx.x * ld + c] = m;
-    }
-}
 // out[0] = 2^-e (applied to X), out[1] = 2^(2e) (applied to c1)
 __global__ void __launch_bounds__(1024)
 xscale_kernel(const float *__restrict__ part, int64_t count, float *__restrict__ out) {
@@ -1182,9 +1203,11 @@ bool flash_tc_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total, 
 // Centred copy of the particles and its row norms, carved from the workspace.
 struct Centred {
     float *Xc, *rc;
+    float *blockmax;        // largest |entry| of Xc per 8 rows
+    int64_t nblockmax;
 };
 static int64_t centred_bytes(int64_t cols, int64_t DP) {
-    return cols * DP * 4 + cols * 4 + (int64_t)CM_BLOCKS * DP * 8 + DP * 4 + 64;
+    return cols * DP * 4 + cols * 4 + (int64_t)CM_BLOCKS * DP * 8 + DP * 4 + (cols / 8 + 1) * 4 + 64;
 }
 static int make_centred(stein_ctx *ctx, const float *X_all, int64_t n_total, int64_t d, int64_t cols, int64_t ld,
                         char *&pws, Centred *out) {
@@ -1194,14 +1217,18 @@ static int make_centred(stein_ctx *ctx, const float *X_all, int64_t n_total, int
     pws = (char *)(((uintptr_t)pws + 7) & ~(uintptr_t)7);
     double *part = (double *)pws;    pws += (int64_t)CM_BLOCKS * ld * 8;
     float *mean = (float *)pws;      pws += ld * 4;
+    const int64_t nblk = (cols * 32 + 255) / 256;
+    float *blockmax = (float *)pws;  pws += nblk * 4;
     colsum_partial_kernel<<<CM_BLOCKS, 256, 0, ctx->stream>>>(X_all, n_total, ld, part);
     STEIN_CHECK_LAUNCH(ctx);
     colmean_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, ctx->stream>>>(part, n_total, ld, mean);
     STEIN_CHECK_LAUNCH(ctx);
-    center_kernel<<<(unsigned)((cols * 32 + 255) / 256), 256, 0, ctx->stream>>>(X_all, mean, n_total, cols, d, ld, Xc, rc);
+    center_kernel<<<(unsigned)nblk, 256, 0, ctx->stream>>>(X_all, mean, n_total, cols, d, ld, Xc, rc, blockmax);
     STEIN_CHECK_LAUNCH(ctx);
     out->Xc = Xc;
     out->rc = rc;
+    out->blockmax = blockmax;
+    out->nblockmax = nblk;
     return STEIN_OK;
 }
 
@@ -1376,7 +1403,7 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     pws = (char *)partials + FINALIZE_MAX_BLOCKS * 8;
     int *tile_nslots = nullptr;
     // the debug hook compares the raw GEMM1 tiles with X X^T: no centring there
-    Centred cen{const_cast<float *>(X_all), const_cast<float *>(r_all)};
+    Centred cen{const_cast<float *>(X_all), const_cast<float *>(r_all), nullptr, 0};
     if (!g_debug_dumpS) STEIN_TRY(make_centred(ctx, X_all, n_total, d, pl.cols, ld, pws, &cen));
     const float *Xc = cen.Xc, *rc = cen.rc;
 
@@ -1480,9 +1507,7 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
         const int64_t tot = std::max<int64_t>(cols * DP / 4, cols + 256);
         if (g1f8) {
             // FP16 array in the place of Xh; a8l, a8h share the place of Xl; b8h, b8l have their own
-            absmax_partial_kernel<<<CM_BLOCKS, 256, 0, ctx->stream>>>(Xc, n_total, ld, cmax_part);
-            STEIN_CHECK_LAUNCH(ctx);
-            xscale_kernel<<<1, 1024, 0, ctx->stream>>>(cmax_part, (int64_t)CM_BLOCKS * DP, xscale);
+            xscale_kernel<<<1, 1024, 0, ctx->stream>>>(cen.blockmax, cen.nblockmax, xscale);
             STEIN_CHECK_LAUNCH(ctx);
             prep_x8_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(
                 Xc, rc, cols, n_total, ld, 0.5f * l2e / h2, xscale, (__half *)Xh, (uint8_t *)Xl, (uint8_t *)Xl + cols * DP,
