@@ -302,6 +302,9 @@ def run_ours(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "gaussian_target_n%d_d%d" % (n, d), "n_particles": n, "dim": d,
                    "optimizer": "adam", "parallelism": "particle_rows_x%d" % world,
+                   "collectives": ("none" if world == 1 else
+                                   "NCCL (library-driven); particles pushed to peers by the optimizer kernel"
+                                   if eng.peer_push else "NCCL (library-driven)"),
                    "phi_impl": impl, "median_sweeps_last_step": info["sweeps"],
                    "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set "
                          "is also > 126 MB"},

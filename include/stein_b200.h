@@ -72,6 +72,10 @@ typedef struct stein_comm {
     int (*allreduce_sum_f64)(void *user, void *buf_dev, int64_t count);
     /* gathers `count` floats from every rank into recv_dev[rank*count ...] */
     int (*allgather_f32)(void *user, const void *send_dev, void *recv_dev, int64_t count);
+    /* OPTIONAL (may be NULL): the same gather enqueued on the given CUDA stream instead of the ctx
+     * stream, through resources that may run concurrently with the other hooks (the built-in NCCL
+     * transport uses a second communicator).  Lets the score shards travel while the median runs. */
+    int (*allgather_f32_on)(void *user, const void *send_dev, void *recv_dev, int64_t count, void *cuda_stream);
 } stein_comm;
 
 /* ---- context ------------------------------------------------------------- */
@@ -83,10 +87,11 @@ int stein_ctx_set_comm(stein_ctx *ctx, const stein_comm *comm /* NULL = single G
 /* Built-in hooks on NCCL (resolved at run time from the libnccl.so.2 loaded in the process):
  * rank 0 calls stein_nccl_unique_id and hands the 128 bytes to every rank by any means; every
  * rank then calls stein_ctx_init_nccl, which creates the communicator (collective) and installs
- * hooks that enqueue ncclAllGather / ncclAllReduce on the ctx stream.  world == 1 clears them. */
+ * hooks that enqueue ncclAllGather / ncclAllReduce on the ctx stream.  A second id (optional,
+ * id_side) creates a second communicator for the allgather_f32_on hook.  world == 1 clears them. */
 #define STEIN_NCCL_ID_BYTES 128
 int stein_nccl_unique_id(void *id_out);
-int stein_ctx_init_nccl(stein_ctx *ctx, int rank, int world, const void *id);
+int stein_ctx_init_nccl(stein_ctx *ctx, int rank, int world, const void *id, const void *id_side /* or NULL */);
 int stein_ctx_set_phi_impl(stein_ctx *ctx, int impl);
 int stein_ctx_set_median_impl(stein_ctx *ctx, int impl);
 const char *stein_last_error(const stein_ctx *ctx /* NULL = last error of any ctx */);
@@ -255,6 +260,16 @@ int stein_engine_step(stein_engine *eng);
  * be NULL to leave the particles on the device)                               */
 int stein_engine_update_particles_host(stein_engine *eng, const void *S_host, void *X_host_out,
                                        int is_f64);
+/* Peer push (optional, ranks on one node): each rank exports the CUDA-IPC handle of its particle
+ * buffer (STEIN_IPC_HANDLE_BYTES), the handles of all ranks are concatenated in rank order by any
+ * means, and every rank imports them.  From then on the optimizer kernel stores the updated rows
+ * straight into the other ranks' buffers over NVLink and the all-gather of the particles is replaced
+ * by a one-word all-reduce.  Returns STEIN_ERR_UNSUPPORTED when a handle cannot be opened (the
+ * engine then keeps using the all-gather hook).  handles == NULL closes the peers again.  Either
+ * every rank pushes or none: the caller must agree on the outcome across ranks. */
+#define STEIN_IPC_HANDLE_BYTES 64
+int stein_engine_ipc_handle(stein_engine *eng, void *handle_out);
+int stein_engine_set_peer_handles(stein_engine *eng, const void *handles /* world x 64 bytes */);
 /* diagnostics of the last step */
 int stein_engine_last(const stein_engine *eng, float *median, float *bandwidth,
                       double *phi_norm, int32_t *sweeps);

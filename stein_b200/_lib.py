@@ -19,12 +19,13 @@ c_f32, c_f64, c_vp = ctypes.c_float, ctypes.c_double, ctypes.c_void_p
 
 HOOK = ctypes.CFUNCTYPE(ctypes.c_int, c_vp, c_vp, c_i64)
 HOOK_GATHER = ctypes.CFUNCTYPE(ctypes.c_int, c_vp, c_vp, c_vp, c_i64)
+HOOK_GATHER_ON = ctypes.CFUNCTYPE(ctypes.c_int, c_vp, c_vp, c_vp, c_i64, c_vp)
 
 
 class SteinComm(ctypes.Structure):
     _fields_ = [("rank", c_i32), ("world", c_i32), ("user", c_vp),
                 ("allreduce_sum_u64", HOOK), ("allreduce_sum_f64", HOOK),
-                ("allgather_f32", HOOK_GATHER)]
+                ("allgather_f32", HOOK_GATHER), ("allgather_f32_on", HOOK_GATHER_ON)]
 
 
 class SteinLibraryError(RuntimeError):
@@ -39,7 +40,7 @@ SIGNATURES = {
     "stein_ctx_set_stream": (ctypes.c_int, [c_vp, c_vp]),
     "stein_ctx_set_comm": (ctypes.c_int, [c_vp, ctypes.POINTER(SteinComm)]),
     "stein_nccl_unique_id": (ctypes.c_int, [c_vp]),
-    "stein_ctx_init_nccl": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp]),
+    "stein_ctx_init_nccl": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "stein_ctx_set_phi_impl": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "stein_ctx_set_median_impl": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "stein_last_error": (ctypes.c_char_p, [c_vp]),
@@ -93,6 +94,8 @@ SIGNATURES = {
     "stein_engine_get_phi": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int]),
     "stein_engine_step": (ctypes.c_int, [c_vp]),
     "stein_engine_update_particles_host": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int]),
+    "stein_engine_ipc_handle": (ctypes.c_int, [c_vp, c_vp]),
+    "stein_engine_set_peer_handles": (ctypes.c_int, [c_vp, c_vp]),
     "stein_engine_last": (ctypes.c_int, [c_vp, ctypes.POINTER(c_f32), ctypes.POINTER(c_f32),
                                          ctypes.POINTER(c_f64), ctypes.POINTER(c_i32)]),
     "stein_engine_get_state": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_f64),

@@ -55,7 +55,8 @@ static NcclApi &nccl_api() {
 
 struct NcclState {
     stein_ctx *ctx;
-    nccl_comm_t comm;
+    nccl_comm_t comm;       // collectives on the ctx stream
+    nccl_comm_t comm_side;  // all-gathers on a caller-given stream, concurrent with the first one
 };
 
 static int hook_allreduce_u64(void *user, void *buf, int64_t count) {
@@ -71,9 +72,15 @@ static int hook_allgather_f32(void *user, const void *send, void *recv, int64_t 
     return nccl_api().AllGather(send, recv, (size_t)count, NCCL_FLOAT32, st->comm, st->ctx->stream);
 }
 
+static int hook_allgather_f32_on(void *user, const void *send, void *recv, int64_t count, void *stream) {
+    NcclState *st = (NcclState *)user;
+    return nccl_api().AllGather(send, recv, (size_t)count, NCCL_FLOAT32, st->comm_side, (cudaStream_t)stream);
+}
+
 void nccl_release(stein_ctx *ctx) {
     NcclState *st = (NcclState *)ctx->nccl_state;
     if (!st) return;
+    if (st->comm_side) nccl_api().CommDestroy(st->comm_side);
     if (st->comm) nccl_api().CommDestroy(st->comm);
     delete st;
     ctx->nccl_state = nullptr;
@@ -97,7 +104,7 @@ int stein_nccl_unique_id(void *id_out) {
     return STEIN_OK;
 }
 
-int stein_ctx_init_nccl(stein_ctx *ctx, int rank, int world, const void *id) {
+int stein_ctx_init_nccl(stein_ctx *ctx, int rank, int world, const void *id, const void *id_side) {
     STEIN_REQUIRE(ctx, ctx != nullptr && id != nullptr, "null ctx / id");
     STEIN_REQUIRE(ctx, world >= 1 && rank >= 0 && rank < world, "rank %d outside world %d", rank, world);
     NcclApi &api = nccl_api();
@@ -105,11 +112,16 @@ int stein_ctx_init_nccl(stein_ctx *ctx, int rank, int world, const void *id) {
     STEIN_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
     nccl_release(ctx);
     if (world == 1) return stein_ctx_set_comm(ctx, nullptr);
-    NcclState *st = new NcclState{ctx, nullptr};
+    NcclState *st = new NcclState{ctx, nullptr, nullptr};
     nccl_unique_id uid;
     memcpy(&uid, id, sizeof(uid));
-    const int rc = api.CommInitRank(&st->comm, world, uid, rank);
+    int rc = api.CommInitRank(&st->comm, world, uid, rank);
+    if (rc == NCCL_SUCCESS && id_side) {
+        memcpy(&uid, id_side, sizeof(uid));
+        rc = api.CommInitRank(&st->comm_side, world, uid, rank);
+    }
     if (rc != NCCL_SUCCESS) {
+        if (st->comm) api.CommDestroy(st->comm);
         delete st;
         return fail(ctx, STEIN_ERR_COMM, "ncclCommInitRank: %s", api.GetErrorString ? api.GetErrorString(rc) : "?");
     }
@@ -121,6 +133,7 @@ int stein_ctx_init_nccl(stein_ctx *ctx, int rank, int world, const void *id) {
     c.allreduce_sum_u64 = hook_allreduce_u64;
     c.allreduce_sum_f64 = hook_allreduce_f64;
     c.allgather_f32 = hook_allgather_f32;
+    c.allgather_f32_on = st->comm_side ? hook_allgather_f32_on : nullptr;
     return stein_ctx_set_comm(ctx, &c);
 }
 

@@ -106,6 +106,21 @@ struct RegionTimer {
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// Where the optimizer kernel additionally stores the updated rows: the same row range in the
+// particle buffers of the other ranks of the node (opened through CUDA IPC, engine.cu).
+constexpr int MAX_PEERS = 15;
+struct PeerTargets {
+    float4 *dst[MAX_PEERS];
+    int n = 0;
+};
+// optimizer.cu
+int clip_adam_step(stein_ctx *ctx, float *X_dev, const float *phi_dev, float *mu_dev, float *nu_dev,
+                   int64_t count, const double *sumsq_dev, double learning_rate, double beta_1, double beta_2,
+                   int64_t n_iters, const PeerTargets &peers);
+int clip_adagrad_step(stein_ctx *ctx, float *X_dev, const float *phi_dev, float *hist_dev, int64_t count,
+                      const double *sumsq_dev, double learning_rate, double alpha, int64_t n_iters,
+                      const PeerTargets &peers);
+
 // order-preserving fp32 -> u32 (ascending); -0 folded onto +0
 __host__ __device__ inline uint32_t float_to_key(float f) {
     f = f + 0.0f;

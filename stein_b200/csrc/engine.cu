@@ -38,6 +38,11 @@ struct stein_engine {
     void *stage = nullptr;  // device staging for float64 host arrays
     cudaStream_t copy_stream = nullptr;  // score upload overlapped with the median (update_particles_host)
     cudaEvent_t ev_scores = nullptr, ev_ready = nullptr;
+    // peer push of the updated particles (CUDA IPC views of the other ranks' X_all)
+    float *peer_X[stein::MAX_PEERS + 1] = {nullptr};   // indexed by rank; own entry unused
+    bool peers_open = false;
+    bool x_all_current = false;     // every rank's X_all holds everybody's current rows
+    unsigned long long *barrier_word = nullptr;   // 1 u64 all-reduced as the cross-rank barrier after a push
     float last_med = 0.f, last_bw = 0.f;
     int32_t last_sweeps = 0;
     float *X_local() const { return X_all + (int64_t)rank * q * ld; }
@@ -173,6 +178,10 @@ int stein_engine_destroy(stein_engine *e) {
     if (!e) return STEIN_OK;
     cudaSetDevice(e->ctx->device);
     cudaStreamSynchronize(e->ctx->stream);
+    if (e->peers_open)
+        for (int r = 0; r < e->world; ++r)
+            if (r != e->rank && e->peer_X[r]) cudaIpcCloseMemHandle(e->peer_X[r]);
+    if (e->barrier_word) cudaFree(e->barrier_word);
     void *ptrs[] = {e->X_all, e->S_all, e->phi, e->m1, e->m2, e->r_all, e->sumsq, e->ws, e->stage};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -207,6 +216,7 @@ int stein_engine_buffers(stein_engine *e, float **X_local_dev, float **S_local_d
 
 int stein_engine_set_particles(stein_engine *e, const void *X_host, int is_f64) {
     if (!e) return STEIN_ERR_INVALID;
+    e->x_all_current = false;      // the other ranks' copies of these rows are stale now
     STEIN_TRY(upload(e, X_host, is_f64, e->X_local()));
     STEIN_CHECK_CUDA(e->ctx, cudaStreamSynchronize(e->ctx->stream));
     return STEIN_OK;
@@ -232,9 +242,17 @@ static int step_bandwidth(stein_engine *e, float *bw_out) {
     stein_ctx *ctx = e->ctx;
     const int64_t rows_all = e->q * e->world;
     if (e->world > 1) {
-        const int64_t cnt = e->q * e->ld;
-        if (ctx->comm.allgather_f32(ctx->comm.user, e->X_local(), e->X_all, cnt) != 0)
-            return fail(ctx, STEIN_ERR_COMM, "allgather_f32 hook failed");
+        if (e->peers_open && e->x_all_current) {
+            // every rank pushed its updated rows into this buffer during its last optimizer
+            // step; a 1-word all-reduce is the barrier that orders those stores (it completes
+            // only after every rank has enqueued it, i.e. after its step kernel)
+            if (ctx->comm.allreduce_sum_u64(ctx->comm.user, e->barrier_word, 1) != 0)
+                return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+        } else {
+            const int64_t cnt = e->q * e->ld;
+            if (ctx->comm.allgather_f32(ctx->comm.user, e->X_local(), e->X_all, cnt) != 0)
+                return fail(ctx, STEIN_ERR_COMM, "allgather_f32 hook failed");
+        }
     }
     // abstract_kernel.py:34 -- r = sum(T*T, 1), contract order
     STEIN_TRY(stein_row_norms(ctx, e->X_all, rows_all, e->d, e->ld, e->r_all));
@@ -253,9 +271,9 @@ static int step_bandwidth(stein_engine *e, float *bw_out) {
 }
 
 // Phase 2 needs the scores: (all-gather S,) phi, clip, optimizer step.
-static int step_update(stein_engine *e, float bw) {
+static int step_update(stein_engine *e, float bw, bool scores_gathered) {
     stein_ctx *ctx = e->ctx;
-    if (e->world > 1) {
+    if (e->world > 1 && !scores_gathered) {
         const int64_t cnt = e->q * e->ld;
         if (ctx->comm.allgather_f32(ctx->comm.user, e->S_local(), e->S_all, cnt) != 0)
             return fail(ctx, STEIN_ERR_COMM, "allgather_f32 hook failed");
@@ -269,25 +287,58 @@ static int step_update(stein_engine *e, float bw) {
     }
     // abstract_stein_sampler.py:125-126
     const int64_t count = e->q * e->ld;
+    // peers: the same rows inside the other ranks' X_all.  Safe to overwrite now: the all-reduce
+    // of sum(phi^2) above means every rank is past its phi kernel, and nothing after it reads
+    // the uncentred X_all of other ranks' rows.
+    PeerTargets peers{};
+    if (e->world > 1 && e->peers_open) {
+        for (int r = 0; r < e->world; ++r)
+            if (r != e->rank) peers.dst[peers.n++] = reinterpret_cast<float4 *>(e->peer_X[r] + (int64_t)e->rank * e->q * e->ld);
+    }
     if (e->opt == STEIN_OPT_ADAM) {
-        STEIN_TRY(stein_clip_adam_step(ctx, e->X_local(), e->phi, e->m1, e->m2, count, e->sumsq, e->lr,
-                                       e->p1, e->p2, e->n_iters));
+        STEIN_TRY(clip_adam_step(ctx, e->X_local(), e->phi, e->m1, e->m2, count, e->sumsq, e->lr, e->p1, e->p2,
+                                 e->n_iters, peers));
         e->lr *= e->decay;  // adam_gradient_descent.py:56
     } else {
         // adagrad_gradient_descent.py never applies `decay`
-        STEIN_TRY(stein_clip_adagrad_step(ctx, e->X_local(), e->phi, e->m1, count, e->sumsq, e->lr,
-                                          e->p1, e->n_iters));
+        STEIN_TRY(clip_adagrad_step(ctx, e->X_local(), e->phi, e->m1, count, e->sumsq, e->lr, e->p1, e->n_iters,
+                                    peers));
     }
+    if (peers.n) e->x_all_current = true;
     e->n_iters += 1;
+    return STEIN_OK;
+}
+
+// Sharded runs with a side-stream all-gather hook: the score shards travel on the copy stream
+// (own communicator) while the median runs; `after` = event the gather must wait for.
+static int gather_scores_async(stein_engine *e, bool *done) {
+    stein_ctx *ctx = e->ctx;
+    *done = false;
+    if (e->world <= 1 || !ctx->comm.allgather_f32_on) return STEIN_OK;
+    const int64_t cnt = e->q * e->ld;
+    if (ctx->comm.allgather_f32_on(ctx->comm.user, e->S_local(), e->S_all, cnt, (void *)e->copy_stream) != 0)
+        return fail(ctx, STEIN_ERR_COMM, "allgather_f32_on hook failed");
+    *done = true;
     return STEIN_OK;
 }
 
 int stein_engine_step(stein_engine *e) {
     if (!e) return STEIN_ERR_INVALID;
-    STEIN_CHECK_CUDA(e->ctx, cudaSetDevice(e->ctx->device));
+    stein_ctx *ctx = e->ctx;
+    STEIN_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    // the scores were written on the ctx stream; their all-gather may overlap the median
+    bool gathered = false;
+    if (e->world > 1 && ctx->comm.allgather_f32_on) {
+        STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_ready, ctx->stream));
+        STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(e->copy_stream, e->ev_ready, 0));
+        STEIN_TRY(gather_scores_async(e, &gathered));
+        STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_scores, e->copy_stream));
+    }
     float bw = 0.f;
-    STEIN_TRY(step_bandwidth(e, &bw));
-    return step_update(e, bw);
+    const int rc = step_bandwidth(e, &bw);
+    if (gathered) STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e->ev_scores, 0));
+    if (rc != STEIN_OK) return rc;
+    return step_update(e, bw, gathered);
 }
 
 int stein_engine_update_particles_host(stein_engine *e, const void *S_host, void *X_host_out,
@@ -300,13 +351,68 @@ int stein_engine_update_particles_host(stein_engine *e, const void *S_host, void
     STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_ready, ctx->stream));
     STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(e->copy_stream, e->ev_ready, 0));
     STEIN_TRY(upload(e, S_host, is_f64, e->S_local(), e->copy_stream));
+    bool gathered = false;
+    STEIN_TRY(gather_scores_async(e, &gathered));
     STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_scores, e->copy_stream));
     float bw = 0.f;
     const int rc = step_bandwidth(e, &bw);
     STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e->ev_scores, 0));
     if (rc != STEIN_OK) return rc;
-    STEIN_TRY(step_update(e, bw));
+    STEIN_TRY(step_update(e, bw, gathered));
     if (X_host_out) return stein_engine_get_particles(e, X_host_out, is_f64);
+    return STEIN_OK;
+}
+
+int stein_engine_ipc_handle(stein_engine *e, void *handle_out) {
+    if (!e || !handle_out) return STEIN_ERR_INVALID;
+    stein_ctx *ctx = e->ctx;
+    STEIN_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    STEIN_CHECK_CUDA(ctx, cudaIpcGetMemHandle(&h, e->X_all));
+    static_assert(sizeof(h) == STEIN_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    memcpy(handle_out, &h, sizeof(h));
+    return STEIN_OK;
+}
+
+int stein_engine_set_peer_handles(stein_engine *e, const void *handles) {
+    if (!e) return STEIN_ERR_INVALID;
+    stein_ctx *ctx = e->ctx;
+    if (!handles) {     // back to the all-gather hook
+        STEIN_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+        STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int r = 0; r < e->world && r <= MAX_PEERS; ++r)
+            if (r != e->rank && e->peer_X[r]) {
+                cudaIpcCloseMemHandle(e->peer_X[r]);
+                e->peer_X[r] = nullptr;
+            }
+        e->peers_open = false;
+        e->x_all_current = false;
+        return STEIN_OK;
+    }
+    STEIN_REQUIRE(ctx, e->world > 1 && e->world <= MAX_PEERS + 1, "peer push needs 2..%d ranks", MAX_PEERS + 1);
+    STEIN_REQUIRE(ctx, !e->peers_open, "peer handles already set");
+    STEIN_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int r = 0; r < e->world; ++r) {
+        if (r == e->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + (size_t)r * STEIN_IPC_HANDLE_BYTES, sizeof(h));
+        void *p = nullptr;
+        const cudaError_t err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (err != cudaSuccess) {
+            for (int q = 0; q < r; ++q)
+                if (q != e->rank && e->peer_X[q]) {
+                    cudaIpcCloseMemHandle(e->peer_X[q]);
+                    e->peer_X[q] = nullptr;
+                }
+            cudaGetLastError();
+            return fail(ctx, STEIN_ERR_UNSUPPORTED, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(err));
+        }
+        e->peer_X[r] = (float *)p;
+    }
+    STEIN_CHECK_CUDA(ctx, cudaMalloc(&e->barrier_word, 8));
+    STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(e->barrier_word, 0, 8, ctx->stream));
+    e->peers_open = true;
+    e->x_all_current = false;
     return STEIN_OK;
 }
 

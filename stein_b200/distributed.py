@@ -26,14 +26,42 @@ def make_nccl_comm(ctx, group=None):
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    box = [None]
+    box = [None, None]      # ids of the main and of the side communicator
     if rank == 0:
-        buf = ctypes.create_string_buffer(128)
-        ctx.check(ctx.lib.stein_nccl_unique_id(buf))
-        box[0] = buf.raw
+        for k in range(2):
+            buf = ctypes.create_string_buffer(128)
+            ctx.check(ctx.lib.stein_nccl_unique_id(buf))
+            box[k] = buf.raw
     dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-    ctx.check(ctx.lib.stein_ctx_init_nccl(ctx.handle, rank, world, ctypes.c_char_p(box[0])))
+    ctx.check(ctx.lib.stein_ctx_init_nccl(ctx.handle, rank, world, ctypes.c_char_p(box[0]),
+                                          ctypes.c_char_p(box[1])))
+    ctx._native_comm_group = (group, rank, world)      # engines exchange their IPC handles over it
     return rank, world
+
+
+def connect_peers(engine):
+    """Exchange the CUDA-IPC handles of the engines' particle buffers (all ranks, one node) so that
+    the optimizer kernel pushes updated rows straight into the peers' buffers.  Collective.
+    Returns True when every rank could open every handle; otherwise the engines keep using the
+    all-gather hook."""
+    import torch.distributed as dist
+    ctx = engine.ctx
+    info = getattr(ctx, "_native_comm_group", None)
+    if info is None:
+        return False
+    group, rank, world = info
+    buf = ctypes.create_string_buffer(64)
+    ctx.check(ctx.lib.stein_engine_ipc_handle(engine.handle, buf))
+    handles = [None] * world
+    dist.all_gather_object(handles, buf.raw, group=group)
+    rc = ctx.lib.stein_engine_set_peer_handles(engine.handle, ctypes.c_char_p(b"".join(handles)))
+    # all or nothing: a rank that could not open its peers must not skip the all-gather alone
+    ok = [None] * world
+    dist.all_gather_object(ok, rc == 0, group=group)
+    if not all(ok):
+        ctx.check(ctx.lib.stein_engine_set_peer_handles(engine.handle, None))
+        return False
+    return True
 
 
 def make_comm(ctx, group=None, native=None):
@@ -88,7 +116,7 @@ def make_comm(ctx, group=None, native=None):
             return 1
 
     comm = _lib.SteinComm(rank, world, None, _lib.HOOK(allreduce_u64), _lib.HOOK(allreduce_f64),
-                          _lib.HOOK_GATHER(allgather_f32))
+                          _lib.HOOK_GATHER(allgather_f32), _lib.HOOK_GATHER_ON())
     ctx.check(ctx.lib.stein_ctx_set_comm(ctx.handle, ctypes.byref(comm)))
     ctx._comm_keepalive = comm      # the C side copied the struct; keep the callbacks alive
     return comm

@@ -15,7 +15,7 @@ from .runtime import context, _torch
 
 class SvgdEngine:
     def __init__(self, n_particles, n_params, optimizer="adam", learning_rate=1e-3, decay=1.0,
-                 p1=0.9, p2=0.999, ctx=None):
+                 p1=0.9, p2=0.999, ctx=None, peer_push=True):
         self.ctx = ctx or context()
         self.lib = self.ctx.lib
         self.n_particles, self.n_params = int(n_particles), int(n_params)
@@ -33,6 +33,12 @@ class SvgdEngine:
                                                      ctypes.byref(p), ctypes.byref(ld), ctypes.byref(rows)))
         self.ld, self.rows_padded = ld.value, rows.value
         self.x_ptr, self.s_ptr, self.phi_ptr = x.value, s.value, p.value
+        # sharded run on the library's NCCL transport: let the optimizer kernel push the updated
+        # rows into the peers' buffers (replaces the all-gather of the particles)
+        self.peer_push = False
+        if peer_push and getattr(self.ctx, "_native_comm_group", None) is not None:
+            from .distributed import connect_peers
+            self.peer_push = connect_peers(self)
 
     def close(self):
         if self.handle:

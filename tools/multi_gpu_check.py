@@ -24,16 +24,16 @@ def main():
     ctx = context(local)
     make_comm(ctx)
     ok = True
-    for n, d in [(1000, 33), (5000, 256), (4097, 128)]:
+    for n, d, push in [(1000, 33, True), (5000, 256, True), (5000, 256, False), (4097, 128, True)]:
         rng = np.random.default_rng(n)
         X = rng.standard_normal((n, d)).astype(np.float32).astype(np.float64)
         mean = rng.standard_normal(d)
-        eng = SvgdEngine(n, d, "adam", learning_rate=0.1, decay=0.999, ctx=ctx)
+        eng = SvgdEngine(n, d, "adam", learning_rate=0.1, decay=0.999, ctx=ctx, peer_push=push)
         b, nl = eng.row_begin, eng.n_local
         eng.set_particles(np.ascontiguousarray(X[b:b + nl]))
         gd = orc.AdamGradientDescent(0.1, 0.999)
         Xref = X.copy()
-        for it in range(2):
+        for it in range(3):
             S = (mean - Xref) * 2.0
             bw_ref = orc.kernel_and_grad(Xref)[2] if n <= 1500 else None
             out = np.empty((nl, d))
@@ -63,8 +63,9 @@ def main():
                 full = [None] * world
                 dist.all_gather_object(full, out)
                 Xref = np.concatenate(full, axis=0)
-            print("rank %d n=%d d=%d iter %d: bandwidth %.9g sweeps %d err %.2e %s"
-                  % (rank, n, d, it, info["bandwidth"], info["sweeps"], err, "ok" if good else "FAIL"), flush=True)
+            print("rank %d n=%d d=%d push=%s iter %d: bandwidth %.9g sweeps %d err %.2e %s"
+                  % (rank, n, d, eng.peer_push, it, info["bandwidth"], info["sweeps"], err, "ok" if good else "FAIL"),
+                  flush=True)
             ok = ok and good
         eng.close()
     flag = torch.tensor([0 if ok else 1], device="cuda")
