@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <functional>
 
 #include "pair_chain.cuh"
 #include "tc_common.cuh"
@@ -720,9 +721,10 @@ max_kernel(const float *__restrict__ r, int64_t n, float *__restrict__ out) {
 // window are ignored.  SRC 1: uint2 (key, weight) band entries, SRC 2: plain u32 keys (weight 1).
 template <int SRC>
 __global__ void __launch_bounds__(256)
-window_hist_kernel(const void *__restrict__ src, unsigned long long m, uint32_t key_lo, uint32_t shift,
-                   uint32_t nbins, unsigned long long *__restrict__ bins) {
+window_hist_kernel(const void *__restrict__ src, unsigned long long m, const unsigned long long *__restrict__ m_dev,
+                   uint32_t key_lo, uint32_t shift, uint32_t nbins, unsigned long long *__restrict__ bins) {
     extern __shared__ unsigned int wh[];      // nbins + 1
+    if (m_dev) m = min(m, *m_dev);            // length only known on the device (m = upper bound)
     for (uint32_t b = threadIdx.x; b <= nbins; b += blockDim.x) wh[b] = 0u;
     __syncthreads();
     unsigned int below = 0u;
@@ -893,7 +895,9 @@ static int ensure_arena(stein_ctx *ctx, int64_t rows, int64_t DP, uint64_t pairs
 // One histogram pass over a key window; the counts (nbins + 1 u64) end up in A.h_pinned.
 template <int SRC>
 static int window_counts(stein_ctx *ctx, const void *src, unsigned long long m_local, uint32_t key_lo,
-                         uint32_t shift, uint32_t nbins, bool distributed) {
+                         uint32_t shift, uint32_t nbins, bool distributed,
+                         const unsigned long long *m_dev = nullptr, const unsigned long long *extra_dev = nullptr,
+                         int extra_words = 0, unsigned long long *extra_host = nullptr) {
     MedianArena &A = g_arena;
     static bool attr_set = false;
     if (!attr_set) {
@@ -904,12 +908,17 @@ static int window_counts(stein_ctx *ctx, const void *src, unsigned long long m_l
     STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(A.bins, 0, (nbins + 1) * 8, ctx->stream));
     if (m_local) {
         const unsigned grid = (unsigned)std::min<unsigned long long>((m_local + 255) / 256, 4ull * ctx->num_sms);
-        window_hist_kernel<SRC><<<grid, 256, (nbins + 1) * 4, ctx->stream>>>(src, m_local, key_lo, shift, nbins, A.bins);
+        window_hist_kernel<SRC><<<grid, 256, (nbins + 1) * 4, ctx->stream>>>(src, m_local, m_dev, key_lo, shift, nbins,
+                                                                             A.bins);
         STEIN_CHECK_LAUNCH(ctx);
     }
     if (distributed && ctx->has_comm && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.bins, (int64_t)nbins + 1) != 0)
         return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.h_pinned, A.bins, (nbins + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    // a few more device words can ride on the same round trip
+    if (extra_words)
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(extra_host, extra_dev, (size_t)extra_words * 8, cudaMemcpyDeviceToHost,
+                                              ctx->stream));
     STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return STEIN_OK;
 }
@@ -929,22 +938,40 @@ static KeyWindow window_over(uint32_t lo, uint32_t hi) {
 // in [key_lo, key_hi] (keys outside: below counts, above is ignored).  One pass when the span is
 // at most HIST_MAX_BINS keys (the normal case for the band), otherwise the window is narrowed.
 // Returns 1 when a rank is not inside the window.
+// `first_sync` (optional) describes device words to fetch with the first pass and a function
+// that turns them into the ranks (the band's rank offsets are only known on the device until then).
+struct FirstSync {
+    const unsigned long long *m_dev = nullptr;       // device-side length of src (m_local = bound)
+    const unsigned long long *extra_dev = nullptr;   // words copied to extra_host with the first pass
+    unsigned long long *extra_host = nullptr;
+    int extra_words = 0;
+    std::function<int(uint64_t rank[2])> ranks;      // 0 = ok; anything else aborts with that code
+};
 template <int SRC>
 static int window_select2(stein_ctx *ctx, const void *src, unsigned long long m_local, uint32_t key_lo,
-                          uint32_t key_hi, const uint64_t rank[2], uint32_t key_out[2], bool distributed) {
+                          uint32_t key_hi, uint64_t rank[2], uint32_t key_out[2], bool distributed,
+                          const FirstSync *first_sync = nullptr) {
     MedianArena &A = g_arena;
     KeyWindow win[2];
     win[0] = win[1] = window_over(key_lo, key_hi);
     bool done[2] = {false, false};
+    const unsigned long long *m_dev = first_sync ? first_sync->m_dev : nullptr;
     for (int iter = 0; iter < 8 && !(done[0] && done[1]); ++iter) {
         const int q0 = done[0] ? 1 : 0;
         const KeyWindow w = win[q0];
-        STEIN_TRY(window_counts<SRC>(ctx, src, m_local, w.key_lo, w.shift, w.nbins, distributed));
+        if (iter == 0 && first_sync) {
+            STEIN_TRY(window_counts<SRC>(ctx, src, m_local, w.key_lo, w.shift, w.nbins, distributed, m_dev,
+                                         first_sync->extra_dev, first_sync->extra_words, first_sync->extra_host));
+            const int frc = first_sync->ranks(rank);
+            if (frc != 0) return frc;
+        } else {
+            STEIN_TRY(window_counts<SRC>(ctx, src, m_local, w.key_lo, w.shift, w.nbins, distributed, m_dev));
+        }
         for (int q = q0; q < 2; ++q) {
             if (done[q] || win[q].key_lo != w.key_lo || win[q].shift != w.shift || win[q].nbins != w.nbins) continue;
             KeyWindow nw = w;
-            const int rc = stein_median_narrow(reinterpret_cast<const uint64_t *>(A.h_pinned), w.key_lo, w.shift, w.nbins, rank[q], &key_out[q],
-                                               &nw.key_lo, &nw.shift, &nw.nbins);
+            const int rc = stein_median_narrow(reinterpret_cast<const uint64_t *>(A.h_pinned), w.key_lo, w.shift, w.nbins,
+                                               rank[q], &key_out[q], &nw.key_lo, &nw.shift, &nw.nbins);
             if (rc == 1) done[q] = true;
             else if (rc == 0) win[q] = nw;
             else return 1;
@@ -954,32 +981,59 @@ static int window_select2(stein_ctx *ctx, const void *src, unsigned long long m_
 }
 
 // Window keys from the pilot sample: [lo, hi] brackets the sample quantiles at rank_lo / rank_hi.
-// Two histogram passes: 14 bits of the full key range, then the bins of the two ranks split
-// 16384 ways.  keys_dev / m are this rank's slice of the sample; the counts are all-reduced.
+// Generic route: two histogram passes (14 bits of the full key range, then the bins of the two
+// ranks split 16384 ways).  keys_dev / m are this rank's slice of the sample; the counts are
+// all-reduced, so every rank takes the same decisions.
+// bins of the two ranks in the counts of the last window_counts call; false when a rank lies outside
+static bool locate_two(const KeyWindow &w, uint64_t rank_lo, uint64_t rank_hi, uint64_t *lo, uint64_t *hi) {
+    MedianArena &A = g_arena;
+    uint64_t cum = A.h_pinned[0];
+    if (rank_lo < cum) return false;
+    int64_t blo = -1, bhi = -1;
+    for (uint32_t b = 0; b < w.nbins; ++b) {
+        const uint64_t c = A.h_pinned[1 + b];
+        if (blo < 0 && cum + c > rank_lo) blo = b;
+        if (bhi < 0 && cum + c > rank_hi) bhi = b;
+        cum += c;
+    }
+    if (blo < 0 || bhi < 0) return false;
+    *lo = (uint64_t)w.key_lo + ((uint64_t)blo << w.shift);
+    *hi = std::min<uint64_t>((uint64_t)w.key_lo + (((uint64_t)bhi + 1) << w.shift) - 1, 0xffffffffull);
+    return true;
+}
+
 int pilot_window(stein_ctx *ctx, const uint32_t *keys_dev, int64_t m, uint64_t rank_lo, uint64_t rank_hi,
                  uint32_t *lo_key, uint32_t *hi_key) {
     if (!g_arena.counters) STEIN_TRY(ensure_arena(ctx, 0, 0, 0));
-    MedianArena &A = g_arena;
-    KeyWindow w = {0u, 18u, (uint32_t)HIST_MAX_BINS};
-    for (int pass = 0; pass < 2; ++pass) {
+    // Successive SVGD iterations move the median by a fraction of a percent: first try ONE pass
+    // over +-2^20 keys (about +-9 % in value, 128 keys per bin) around the last window.  The
+    // result is only used when both ranks fall inside; otherwise the two generic passes run.
+    static uint32_t last_center = 0u;
+    static bool have_last = false;
+    uint64_t lo = 0, hi = 0;
+    bool found = false;
+    if (have_last) {
+        const uint32_t c = last_center, half = 1u << 20;
+        const KeyWindow w = window_over(c > half ? c - half : 0u, c < 0xffffffffu - half ? c + half : 0xffffffffu);
         STEIN_TRY(window_counts<2>(ctx, keys_dev, (unsigned long long)m, w.key_lo, w.shift, w.nbins, true));
-        uint64_t cum = A.h_pinned[0];
-        if (rank_lo < cum) return 1;
-        int64_t blo = -1, bhi = -1;
-        for (uint32_t b = 0; b < w.nbins; ++b) {
-            const uint64_t c = A.h_pinned[1 + b];
-            if (blo < 0 && cum + c > rank_lo) blo = b;
-            if (bhi < 0 && cum + c > rank_hi) bhi = b;
-            cum += c;
-        }
-        if (blo < 0 || bhi < 0) return 1;
-        const uint64_t lo = (uint64_t)w.key_lo + ((uint64_t)blo << w.shift);
-        const uint64_t hi = std::min<uint64_t>((uint64_t)w.key_lo + (((uint64_t)bhi + 1) << w.shift) - 1, 0xffffffffull);
-        *lo_key = (uint32_t)lo;
-        *hi_key = (uint32_t)hi;
-        if (w.shift == 0) break;
-        w = window_over((uint32_t)lo, (uint32_t)hi);
+        found = locate_two(w, rank_lo, rank_hi, &lo, &hi);
     }
+    if (!found) {
+        KeyWindow w = {0u, 18u, (uint32_t)HIST_MAX_BINS};
+        for (int pass = 0; pass < 2; ++pass) {
+            STEIN_TRY(window_counts<2>(ctx, keys_dev, (unsigned long long)m, w.key_lo, w.shift, w.nbins, true));
+            if (!locate_two(w, rank_lo, rank_hi, &lo, &hi)) {
+                have_last = false;
+                return 1;
+            }
+            if (w.shift == 0) break;
+            w = window_over((uint32_t)lo, (uint32_t)hi);
+        }
+    }
+    *lo_key = (uint32_t)lo;
+    *hi_key = (uint32_t)hi;
+    last_center = (uint32_t)((lo + hi) / 2);
+    have_last = true;
     return STEIN_OK;
 }
 
@@ -1122,24 +1176,32 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     }
     if (world > 1 && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.counters + CNT_BELOW2, 3) != 0)
         return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
-    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h + CNT_BELOW2, A.counters + CNT_BELOW2, 4 * 8, cudaMemcpyDeviceToHost,
-                                          ctx->stream));
-    STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const unsigned long long band_len = std::min<unsigned long long>(h[CNT_BAND_LEN], A.band_cap);
-    const uint64_t below2 = h[CNT_BELOW2], band_w = h[CNT_BANDW];
-    if (h[CNT_OVERFLOW2]) return 1;
-    const uint64_t c1 = below + below2;
-    if (!(c1 <= ranks[0] && ranks[1] < c1 + band_w)) return 1;
+    // No host round trip here: the band length stays on the device (list_len bounds it), the
+    // counts of the filter are fetched together with the first histogram of the select below.
+    const unsigned long long band_bound = std::min<unsigned long long>(list_len, A.band_cap);
     // contract-arithmetic distance of every band pair: (i, jw) -> (key, weight), in place
-    STEIN_TRY(launch_pair_chain<0>(ctx, A.band, band_len, X, r, n, ld, 0));
+    STEIN_TRY(launch_pair_chain<0>(ctx, A.band, band_bound, X, r, n, ld, 0, A.counters + CNT_BAND_LEN));
 
     // exact keys of the two target ranks among the band.  A band pair has |D - D~| <= eps <= delta
     // and D~ within eps of [tlo, thi], so its key lies in the window below (normally a few
     // thousand keys wide: one histogram pass)
     const uint32_t klo = float_to_key(tlo - 2.0f * delta), khi = float_to_key(thi + 2.0f * delta);
-    const uint64_t rk[2] = {ranks[0] - c1, ranks[1] - c1};
+    uint64_t rk[2] = {0, 0};
     uint32_t k01[2] = {0u, 0u};
-    const int rc = window_select2<1>(ctx, A.band, band_len, klo, khi, rk, k01, true);
+    FirstSync fs;
+    fs.m_dev = A.counters + CNT_BAND_LEN;
+    fs.extra_dev = A.counters + CNT_BELOW2;
+    fs.extra_host = h + CNT_BELOW2;
+    fs.extra_words = 4;                     // below2, band weight, overflow flag, band length
+    fs.ranks = [&](uint64_t out[2]) -> int {
+        if (h[CNT_OVERFLOW2] || h[CNT_BAND_LEN] > A.band_cap) return 1;
+        const uint64_t c1 = below + h[CNT_BELOW2], band_w = h[CNT_BANDW];
+        if (!(c1 <= ranks[0] && ranks[1] < c1 + band_w)) return 1;
+        out[0] = ranks[0] - c1;
+        out[1] = ranks[1] - c1;
+        return 0;
+    };
+    const int rc = window_select2<1>(ctx, A.band, band_bound, klo, khi, rk, k01, true, &fs);
     if (rc != STEIN_OK) return rc;
     // the selected values must lie where the certainty argument holds
     const float m0 = key_to_float(k01[0]), m1 = key_to_float(k01[1]);

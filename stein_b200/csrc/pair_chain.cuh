@@ -37,8 +37,10 @@ constexpr int PC_SMEM_PER_WARP = 2 * 32 * PC_ROW * 4;
 //        (seed already includes the index of the first sample of this launch)
 template <int SRC>
 __global__ void __launch_bounds__(PC_WARPS * 32, 4)
-pair_chain_kernel(void *__restrict__ io, unsigned long long m, const float *__restrict__ X,
-                  const float *__restrict__ r, int64_t n, int64_t ld, uint64_t seed) {
+pair_chain_kernel(void *__restrict__ io, unsigned long long m, const unsigned long long *__restrict__ m_dev,
+                  const float *__restrict__ X, const float *__restrict__ r, int64_t n, int64_t ld, uint64_t seed) {
+    // the list length may only be known on the device (m is then its upper bound)
+    if (m_dev) m = min(m, *m_dev);
     extern __shared__ __align__(16) unsigned char pc_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *sA = reinterpret_cast<float *>(pc_smem + (size_t)warp * PC_SMEM_PER_WARP);
@@ -107,14 +109,14 @@ pair_chain_kernel(void *__restrict__ io, unsigned long long m, const float *__re
 
 template <int SRC>
 static int launch_pair_chain(stein_ctx *ctx, void *io, unsigned long long m, const float *X, const float *r,
-                             int64_t n, int64_t ld, uint64_t seed) {
+                             int64_t n, int64_t ld, uint64_t seed, const unsigned long long *m_dev = nullptr) {
     if (m == 0) return STEIN_OK;
     const size_t smem = (size_t)PC_WARPS * PC_SMEM_PER_WARP;
     const unsigned long long ngroups = (m + 31ull) / 32ull;
     // 4 blocks of 4 warps per SM are resident (register-limited: 128 per thread; 36 KB of shared memory each)
     const unsigned grid = (unsigned)std::min<unsigned long long>((ngroups + PC_WARPS - 1) / PC_WARPS,
                                                                  4ull * (unsigned long long)ctx->num_sms);
-    pair_chain_kernel<SRC><<<grid, PC_WARPS * 32, smem, ctx->stream>>>(io, m, X, r, n, ld, seed);
+    pair_chain_kernel<SRC><<<grid, PC_WARPS * 32, smem, ctx->stream>>>(io, m, m_dev, X, r, n, ld, seed);
     STEIN_CHECK_LAUNCH(ctx);
     return STEIN_OK;
 }
