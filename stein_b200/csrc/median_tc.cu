@@ -20,8 +20,6 @@
 #include <cuda_bf16.h>
 #include <math.h>
 
-#include <stdlib.h>
-
 #include <algorithm>
 #include <functional>
 
@@ -67,7 +65,6 @@ struct SweepParams {
     const uint32_t *Xh, *Xl;      // BF16 split of X viewed as 32-bit words (DP / 2 per row)
     float wlo, whi, c_half;
     const float *rmax;            // device: max_i r_i (bounds the column part of the error term)
-    int debug_skip;               // experiments only: skip the classification (results invalid)
     // listed D~ -> bin floor((D~ - hlo) * hscale), clamped to [0, SW_HIST_BINS); hlo / hscale are
     // derived in the kernel from the window and rmax (a device value)
     unsigned long long *hist;     // [SW_HIST_BINS] weighted counts of the listed D~ (accumulated)
@@ -193,10 +190,6 @@ struct TileClassifier {
             uint32_t v[32];
             tmem_ld32(s_tmem + lane_addr + ch * 32, v);
             tmem_wait_ld();
-            if (p.debug_skip) {
-                if (v[0] == 0x7fc12345u) ++below;
-                continue;
-            }
             // per element: t = g - B_j, then the SIGN BITS of (hi_i - t) [set: below the window] and
             // of (t - lo_i) [set: above] are shifted into two masks -- 5 instructions, no
             // predicates.  Element c ends up at bit 31 - c.
@@ -340,13 +333,9 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
                     for (int part = 0; part < 2; ++part) {
                         mbar_wait(&bars->empty[stage], phase ^ 1);
                         if (elect_one_sync()) {
-                            if (p.debug_skip == 2) {
-                                mbar_arrive(&bars->full[stage]);
-                            } else {
-                                mbar_expect_tx(&bars->full[stage], SW_UNIT_BYTES);
-                                tma_load_2d(sRing + (size_t)stage * SW_UNIT_BYTES, part == 0 ? &mapXh : &mapXl,
-                                            &bars->full[stage], kb * 64, J * 128);
-                            }
+                            mbar_expect_tx(&bars->full[stage], SW_UNIT_BYTES);
+                            tma_load_2d(sRing + (size_t)stage * SW_UNIT_BYTES, part == 0 ? &mapXh : &mapXl,
+                                        &bars->full[stage], kb * 64, J * 128);
                         }
                         __syncwarp();
                         if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
@@ -1084,7 +1073,6 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     p.whi = key_to_float(win_hi_key);
     p.c_half = c_half;
     p.rmax = d_rmax;
-    p.debug_skip = getenv("STEIN_DEBUG_SWEEP_SKIP") ? atoi(getenv("STEIN_DEBUG_SWEEP_SKIP")) : 0;
     p.hist = A.counters + CNT_HIST;
     p.cnt_below = A.counters + CNT_BELOW;
     p.cnt_listed = A.counters + CNT_LISTED;
@@ -1106,12 +1094,6 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     }
     if (t1 > t0) {
         RegionTimer timer(ctx, STEIN_REGION_SWEEP);
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if (p.debug_skip) {
-            cudaEventCreate(&e0);
-            cudaEventCreate(&e1);
-            cudaEventRecord(e0, ctx->stream);
-        }
         if (pair) {
             CUtensorMap mapXh64, mapXl64;
             STEIN_TRY(make_tensor_map_2d(ctx, &mapXh64, A.Xh, 2, (uint64_t)DP, (uint64_t)rows, (uint64_t)DP * 2, 64));
@@ -1123,15 +1105,6 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
             sweep_tc_kernel<<<grid, SW_THREADS, smem1, ctx->stream>>>(mapXh, mapXl, p);
         }
         STEIN_CHECK_LAUNCH(ctx);
-        if (p.debug_skip) {
-            cudaEventRecord(e1, ctx->stream);
-            cudaEventSynchronize(e1);
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, e0, e1);
-            fprintf(stderr, "[debug] tcgen05 sweep without classification: %.3f ms\n", ms);
-            cudaEventDestroy(e0);
-            cudaEventDestroy(e1);
-        }
     }
     if (sweeps) *sweeps += 1;
     // below / listed / overflow / histogram of the listed D~ become global quantities with ONE
