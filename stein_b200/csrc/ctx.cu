@@ -171,6 +171,9 @@ int stein_phi(stein_ctx *ctx, const float *X_all_dev, const float *S_all_dev, co
                   "row_begin=%lld must be a non-negative multiple of %d", (long long)row_begin, TILE);
     STEIN_REQUIRE(ctx, bandwidth > 0.0f && bandwidth == bandwidth, "bandwidth must be positive and finite");
     const float h2 = bandwidth * bandwidth;  // squared_exponential_kernel.py:22 tf.square(bandwidth)
+    // A leading dimension of 128 / 256 makes the matrix eligible for the tensor-core kernels
+    // whatever d is: the zero pad columns are then simply treated as coordinates.
+    if ((ld == 128 || ld == 256) && d < ld) d = ld;
     const int impl = pick_phi_impl(ctx, n_local, n_total, d);
     if (impl == STEIN_PHI_FLASH_TC2 || impl == STEIN_PHI_FLASH_TC3 || impl == STEIN_PHI_FLASH_TC4) {
         if (!flash_tc2_supported(ctx, n_local, n_total, d))

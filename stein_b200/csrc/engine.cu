@@ -133,7 +133,10 @@ int stein_engine_create(stein_engine **out, stein_ctx *ctx, int64_t n_total, int
     e->ctx = ctx;
     e->n_total = n_total;
     e->d = d;
+    // Many particles of up to 256 coordinates: pad the rows to 128 / 256 floats so that the
+    // tensor-core median and phi kernels apply (pad columns are zero and stay zero).
     e->ld = stein_ld(d);
+    if (n_total >= 2048 && d <= 256) e->ld = d <= 128 ? 128 : 256;
     e->world = ctx->has_comm ? ctx->comm.world : 1;
     e->rank = ctx->has_comm ? ctx->comm.rank : 0;
     e->q = stein_rows_padded((n_total + e->world - 1) / e->world);
@@ -145,7 +148,7 @@ int stein_engine_create(stein_engine **out, stein_ctx *ctx, int64_t n_total, int
     e->p1 = p1;
     e->p2 = p2;
     const int64_t all = e->q * e->world * e->ld * 4, loc = e->q * e->ld * 4;
-    e->ws_bytes = stein_phi_workspace_bytes(ctx, std::max<int64_t>(e->n_local, 1), n_total, d);
+    e->ws_bytes = stein_phi_workspace_bytes(ctx, std::max<int64_t>(e->n_local, 1), n_total, e->ld);
     cudaError_t err = cudaSuccess;
     auto alloc0 = [&](void **p, int64_t bytes) {
         if (err != cudaSuccess) return;

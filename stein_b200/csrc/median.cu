@@ -187,7 +187,7 @@ struct Window {
 static const Window kFullWindow = {0u, 18u, (uint32_t)HIST_MAX_BINS};
 
 // median_tc.cu
-bool median_tc_supported(int64_t n, int64_t d);
+bool median_tc_supported(int64_t n, int64_t ld);
 int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t d, int64_t ld,
               const uint64_t ranks[2], uint32_t win_lo_key, uint32_t win_hi_key, uint32_t keys_out[2],
               int *sweeps);
@@ -357,7 +357,7 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
             win[0] = win[1] = w;
             // tensor-core route: one tcgen05 sweep + exact recomputation of the few pairs
             // that can matter; falls through to the FFMA sweeps if it cannot bracket the rank
-            if (ctx->median_impl != STEIN_MEDIAN_FFMA && median_tc_supported(n, d) && ld == stein_ld(d)) {
+            if (ctx->median_impl != STEIN_MEDIAN_FFMA && median_tc_supported(n, ld)) {
                 const int rc = median_tc(ctx, X_dev, r_dev, n, d, ld, ranks, ka, kb, key, &sweeps);
                 if (rc < 0) return rc;
                 if (rc == STEIN_OK) done[0] = done[1] = true;

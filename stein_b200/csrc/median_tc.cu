@@ -1026,9 +1026,9 @@ int pilot_window(stein_ctx *ctx, const uint32_t *keys_dev, int64_t m, uint64_t r
     return STEIN_OK;
 }
 
-bool median_tc_supported(int64_t n, int64_t d) {
-    const int64_t DP = stein_ld(d);
-    return (DP == 128 || DP == 256) && (uint64_t)n * (uint64_t)n >= (1ull << 24) && n < (1ll << 31);
+// ld: leading dimension of the particle matrix (its zero pad columns count as coordinates)
+bool median_tc_supported(int64_t n, int64_t ld) {
+    return (ld == 128 || ld == 256) && (uint64_t)n * (uint64_t)n >= (1ull << 24) && n < (1ll << 31);
 }
 
 // returns STEIN_OK with keys filled, 1 = "not bracketed, use the FFMA route", <0 = error

@@ -517,6 +517,39 @@ def test_engine_steps_match_oracle(ctx, opt, n, d):
     eng.close()
 
 
+@pytest.mark.parametrize("n,d,ld", [(3000, 55, 128), (4500, 200, 256), (2048, 130, 256)])
+def test_engine_pads_rows_for_the_tensor_core_kernels(ctx, n, d, ld):
+    """With >= 2048 particles of up to 256 coordinates the engine pads the rows to 128 / 256
+    floats, so the tcgen05 kernels (phi; the median too when n*n >= 2^24) run for any such d.
+    Two update_particles(): bandwidth bit-exact, particles within 1e-4 of the oracle."""
+    from stein_b200.engine import SvgdEngine
+    X0 = _particles(n, d, 11, 0.7).astype(np.float64)
+    mean = np.random.default_rng(12).standard_normal(d)
+    eng = SvgdEngine(n, d, "adam", learning_rate=0.1)
+    assert eng.ld == ld
+    gd = orc.AdamGradientDescent(0.1)
+    eng.set_particles(X0)
+    X_gpu = np.empty_like(X0)
+    for it in range(2):
+        X_in = eng.get_particles(np.float64)
+        S = (mean - X_in) * 2.0
+        bw_ref = orc.kernel_and_grad(X_in)[2]
+        X_ref, _ = orc.update_particles(X_in, S, gd)
+        eng.update_particles_host(np.ascontiguousarray(S), X_gpu)
+        last = eng.last()
+        assert np.float32(last["bandwidth"]).tobytes() == bw_ref.tobytes()
+        phi_ref = orc.compute_phi(X_in, S)
+        _assert_close(eng.get_phi(), phi_ref)
+        # Adam's first steps are close to lr * sign(phi): where phi is within the kernels' error
+        # of zero the step is ill-conditioned in ANY arithmetic, so those few entries are left out
+        ok = np.abs(phi_ref) > 1e-4 * np.abs(phi_ref).max()
+        assert ok.mean() > 0.98
+        assert np.abs(X_gpu - X_ref)[ok].max() <= RTOL_PHI * np.abs(X_ref).max()
+        if n * n >= 1 << 24:
+            assert last["sweeps"] == 1          # tensor-core median route
+    eng.close()
+
+
 def test_sampler_linear_regression_known_answer(ctx, golden_dir):
     """examples/linear_regression/main.py on the reference's shipped data: 50
     particles, Adam lr 0.1, 500 iterations -> analytic posterior."""
