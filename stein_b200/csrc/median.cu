@@ -99,58 +99,166 @@ sqdist_hist_kernel(const float *__restrict__ X, const float *__restrict__ r, int
     }
 }
 
-// single-block radix select of two ranks among m keys
-__global__ void __launch_bounds__(1024, 1)
-select_keys_kernel(const uint32_t *__restrict__ keys, int64_t m, uint64_t rank0, uint64_t rank1,
-                   uint32_t *__restrict__ out) {
-    __shared__ unsigned int hist[256];
-    __shared__ uint32_t s_prefix, s_mask;
-    __shared__ unsigned long long s_rank;
+// ---- small n: every key of D, once ----------------------------------------------------------
+// keys[i * n + j] for all i, j < n from the upper-triangular tiles (the mirror image is written
+// too: D is symmetric bit for bit in contract arithmetic).  With n <= 2048 the n*n keys fit
+// 16 MB and the device-side radix select below finds both ranks with one host round trip.
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+sqdist_keys_kernel(const float *__restrict__ X, const float *__restrict__ r, int64_t n, int64_t ld, int64_t T,
+                   uint32_t *__restrict__ keys) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GemmSmem &gs = *reinterpret_cast<GemmSmem *>(smem_raw);
+    float acc[8][8];
+    const int64_t ntiles = T * (T + 1) / 2;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int I, J;
+        tri_tile(t, T, I, J);
+        const int64_t m0 = (int64_t)I * TILE, n0 = (int64_t)J * TILE;
+        gemm_tile<true>(X, ld, m0, X, ld, n0, 0, (int)ld, gs, acc);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int64_t i = m0 + acc_row(a);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int64_t j = n0 + acc_col(c);
+                if (i < n && j < n) {
+                    const uint32_t key = float_to_key((r[i] + r[j]) - 2.0f * acc[a][c]);
+                    keys[i * n + j] = key;
+                    if (I != J) keys[j * n + i] = key;
+                }
+            }
+        }
+    }
+}
+
+// ---- device-side radix select of two ranks among m unweighted keys ---------------------------
+// Three digit passes (11 + 11 + 10 bits).  Each pass is a multi-block histogram of the keys that
+// still match the prefix of rank q (q = 0, 1) followed by a one-block kernel that picks the digit
+// and narrows the prefix -- the host only reads the two final keys.
+struct SelectState {
+    uint32_t prefix[2], mask[2];
+    unsigned long long rank[2];
+    unsigned int bins[2][2048];
+};
+
+__global__ void select_init_kernel(SelectState *st, unsigned long long rank0, unsigned long long rank1) {
+    for (int b = threadIdx.x; b < 2 * 2048; b += blockDim.x) (&st->bins[0][0])[b] = 0u;
+    if (threadIdx.x == 0) {
+        st->prefix[0] = st->prefix[1] = 0u;
+        st->mask[0] = st->mask[1] = 0u;
+        st->rank[0] = rank0;
+        st->rank[1] = rank1;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+select_hist_kernel(const uint32_t *__restrict__ keys, int64_t m, SelectState *st, int shift, int bits) {
+    __shared__ unsigned int h[2][2048];
+    const int nb = 1 << bits;
+    for (int b = threadIdx.x; b < 2 * 2048; b += blockDim.x) (&h[0][0])[b] = 0u;
+    __syncthreads();
+    const uint32_t p0 = st->prefix[0], p1 = st->prefix[1], m0 = st->mask[0], m1 = st->mask[1];
+    const bool same = p0 == p1;          // both ranks still in the same bucket: one histogram serves both
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = keys[i];
+        const unsigned dg = (k >> shift) & (nb - 1);
+        if ((k & m0) == p0) atomicAdd(&h[0][dg], 1u);
+        if (!same && (k & m1) == p1) atomicAdd(&h[1][dg], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        if (h[0][b]) atomicAdd(&st->bins[0][b], h[0][b]);
+        if (!same && h[1][b]) atomicAdd(&st->bins[1][b], h[1][b]);
+    }
+}
+
+// one block of 1024 threads: thread t owns bins 2t and 2t+1; a block-wide scan locates the digit
+__global__ void __launch_bounds__(1024)
+select_pick_kernel(SelectState *st, int shift, int bits, uint32_t *out /* [2] after the last pass */) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ int s_dg[2];
+    __shared__ unsigned long long s_cum[2];
+    const int nb = 1 << bits, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const bool same = st->prefix[0] == st->prefix[1];
+    if (t < 2) s_dg[t] = -1;
+    __syncthreads();
     for (int q = 0; q < 2; ++q) {
-        if (threadIdx.x == 0) {
-            s_prefix = 0u;
-            s_mask = 0u;
-            s_rank = q == 0 ? rank0 : rank1;
+        const unsigned int *bins = st->bins[(q == 1 && same) ? 0 : q];
+        const unsigned long long rk = st->rank[q];
+        const unsigned long long a = 2 * t < nb ? bins[2 * t] : 0ull, b = 2 * t + 1 < nb ? bins[2 * t + 1] : 0ull;
+        unsigned long long incl = a + b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = wsum[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long v = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += v;
+            }
+            wsum[lane] = wi - w;        // exclusive prefix of the warp totals
         }
         __syncthreads();
-        for (int pass = 0; pass < 4; ++pass) {
-            const int sh = 24 - 8 * pass;
-            if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
-            __syncthreads();
-            const uint32_t prefix = s_prefix, mask = s_mask;
-            // keys cluster in very few digits: aggregate equal digits within the warp
-            for (int64_t base = 0; base < m; base += blockDim.x) {
-                const int64_t idx = base + threadIdx.x;
-                bool ok = idx < m;
-                const uint32_t k = ok ? keys[idx] : 0u;
-                ok = ok && ((k & mask) == prefix);
-                const unsigned dg = ok ? ((k >> sh) & 255u) : 256u;
-                const unsigned peers = __match_any_sync(0xffffffffu, dg);
-                if (ok && (int)(threadIdx.x & 31) == __ffs(peers) - 1)
-                    atomicAdd(&hist[dg], (unsigned)__popc(peers));
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                unsigned long long cum = 0, rk = s_rank;
-                int dgt = 0;
-                for (; dgt < 255; ++dgt) {
-                    if (cum + hist[dgt] > rk) break;
-                    cum += hist[dgt];
-                }
-                s_rank = rk - cum;
-                s_prefix = prefix | ((uint32_t)dgt << sh);
-                s_mask = mask | (255u << sh);
-            }
-            __syncthreads();
+        const unsigned long long excl = wsum[warp] + incl - (a + b);
+        if (rk >= excl && rk < excl + a) {
+            s_dg[q] = 2 * t;
+            s_cum[q] = excl;
+        } else if (rk >= excl + a && rk < excl + a + b) {
+            s_dg[q] = 2 * t + 1;
+            s_cum[q] = excl + a;
         }
-        if (threadIdx.x == 0) out[q] = s_prefix;
         __syncthreads();
     }
+    if (t == 0) {
+        for (int q = 0; q < 2; ++q) {
+            int dg = s_dg[q];
+            unsigned long long cum = s_cum[q];
+            if (dg < 0) {            // rank beyond the data (cannot happen for valid ranks): last digit
+                dg = nb - 1;
+                cum = 0;
+            }
+            st->rank[q] -= cum;
+            st->prefix[q] |= (uint32_t)dg << shift;
+            st->mask[q] |= (uint32_t)(nb - 1) << shift;
+        }
+        if (shift == 0) {
+            out[0] = st->prefix[0];
+            out[1] = st->prefix[1];
+        }
+    }
+    __syncthreads();
+    for (int b2 = t; b2 < 2 * 2048; b2 += blockDim.x) (&st->bins[0][0])[b2] = 0u;
 }
 
 __global__ void values_to_keys_kernel(const float *__restrict__ v, int64_t m, uint32_t *__restrict__ keys) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < m) keys[i] = float_to_key(v[i]);
+}
+
+static int ensure_scratch(stein_ctx *ctx, int64_t pilot_m);
+
+// keys at ranks rank0 <= rank1 among m device keys -> ctx->d_sel[0..1] (no host round trip)
+static int select_two_keys(stein_ctx *ctx, const uint32_t *keys_dev, int64_t m, uint64_t rank0, uint64_t rank1) {
+    static SelectState *st = nullptr;       // one per process (one GPU per process)
+    if (!st) STEIN_CHECK_CUDA(ctx, cudaMalloc(&st, sizeof(SelectState)));
+    select_init_kernel<<<1, 1024, 0, ctx->stream>>>(st, rank0, rank1);
+    STEIN_CHECK_LAUNCH(ctx);
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((m + 255) / 256, 2 * (int64_t)ctx->num_sms));
+    const int bits[3] = {11, 11, 10};
+    int shift = 32;
+    for (int pass = 0; pass < 3; ++pass) {
+        shift -= bits[pass];
+        select_hist_kernel<<<grid, 256, 0, ctx->stream>>>(keys_dev, m, st, shift, bits[pass]);
+        STEIN_CHECK_LAUNCH(ctx);
+        select_pick_kernel<<<1, 1024, 0, ctx->stream>>>(st, shift, bits[pass], ctx->d_sel);
+        STEIN_CHECK_LAUNCH(ctx);
+    }
+    return STEIN_OK;
 }
 
 static int ensure_scratch(stein_ctx *ctx, int64_t pilot_m) {
@@ -303,8 +411,7 @@ int stein_median_values(stein_ctx *ctx, const float *V_dev, int64_t m, float *me
     STEIN_CHECK_LAUNCH(ctx);
     // compute_median.py:9-15
     const uint64_t r0 = (m % 2 == 0) ? (uint64_t)m / 2 - 1 : (uint64_t)m / 2, r1 = (uint64_t)m / 2;
-    select_keys_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_pilot_keys, m, r0, r1, ctx->d_sel);
-    STEIN_CHECK_LAUNCH(ctx);
+    STEIN_TRY(select_two_keys(ctx, ctx->d_pilot_keys, m, r0, r1));
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_sel, ctx->d_sel, sizeof(uint32_t) * 2,
                                           cudaMemcpyDeviceToHost, ctx->stream));
     STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -323,6 +430,37 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
     const uint64_t ranks[2] = {dim % 2 == 0 ? dim / 2 - 1 : dim / 2, dim / 2};
     const int64_t pilot_m = (dim >= (1ull << 24)) ? (1ll << 20) : 0;
     STEIN_TRY(ensure_scratch(ctx, pilot_m));
+
+    // Small problems (the reference's own example sizes): all n*n keys once, both ranks selected
+    // on the device, one host round trip.  Not used on sharded runs or when a route is forced.
+    if (n <= 2048 && !ctx->has_comm && ctx->median_impl == STEIN_MEDIAN_AUTO) {
+        STEIN_TRY(ensure_scratch(ctx, (int64_t)dim));
+        const int64_t T = (n + TILE - 1) / TILE;
+        static bool attr_set = false;
+        if (!attr_set) {
+            STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(sqdist_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                       (int)sizeof(GemmSmem)));
+            attr_set = true;
+        }
+        {
+            RegionTimer timer(ctx, STEIN_REGION_SWEEP);
+            sqdist_keys_kernel<<<(unsigned)std::min<int64_t>(T * (T + 1) / 2, 2 * (int64_t)ctx->num_sms), GEMM_THREADS,
+                                 sizeof(GemmSmem), ctx->stream>>>(X_dev, r_dev, n, ld, T, ctx->d_pilot_keys);
+            STEIN_CHECK_LAUNCH(ctx);
+        }
+        STEIN_TRY(select_two_keys(ctx, ctx->d_pilot_keys, (int64_t)dim, ranks[0], ranks[1]));
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_sel, ctx->d_sel, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost,
+                                              ctx->stream));
+        STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const float lo = key_to_float(ctx->h_sel[0]), hi = key_to_float(ctx->h_sel[1]);
+        *median_host = (dim % 2 == 0) ? (lo + hi) / 2.0f : lo;
+        if (mid_host) {
+            mid_host[0] = lo;
+            mid_host[1] = hi;
+        }
+        if (sweeps_host) *sweeps_host = 1;
+        return STEIN_OK;
+    }
 
     Window win[2] = {kFullWindow, kFullWindow};
     bool done[2] = {false, false};
