@@ -59,7 +59,7 @@ def test_row_norms_bit_exact(ctx, n, d):
 
 MEDIAN_CASES = [(2, 1, 1.0), (3, 2, 1.0), (7, 3, 1.0), (50, 1, 0.01), (100, 10, 0.01), (127, 5, 1.0),
                 (128, 32, 1.0), (129, 33, 1.0), (257, 17, 3.0), (512, 64, 1.0), (1000, 55, 0.5),
-                (1024, 256, 1.0), (2049, 20, 1.0)]
+                (1024, 256, 1.0), (1500, 9, 2.0), (2048, 30, 1.0), (2049, 20, 1.0)]
 
 
 @pytest.mark.parametrize("n,d,scale", MEDIAN_CASES)
