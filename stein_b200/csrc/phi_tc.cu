@@ -961,12 +961,18 @@ colsum_partial_kernel(const float *__restrict__ X, int64_t n, int64_t ld, double
         part[(int64_t)blockIdx.x * ld + c] = (a0 + a1) + (a2 + a3);
     }
 }
-__global__ void colmean_kernel(const double *__restrict__ part, int64_t n, int64_t ld, float *__restrict__ mean) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per column: lane l adds partials l, l + 32, ... and the lanes are combined by a
+// butterfly -- a fixed order, so every rank of a sharded run gets the same bits
+__global__ void __launch_bounds__(256)
+colmean_kernel(const double *__restrict__ part, int64_t n, int64_t ld, float *__restrict__ mean) {
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (c >= ld) return;
     double acc = 0.0;
-    for (int b = 0; b < CM_BLOCKS; ++b) acc += part[(int64_t)b * ld + c];      // fixed order
-    mean[c] = (float)(acc / (double)n);
+    for (int b = lane; b < CM_BLOCKS; b += 32) acc += part[(int64_t)b * ld + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) mean[c] = (float)(acc / (double)n);
 }
 // Xc = X - mean for the n valid rows (pad rows and pad columns stay zero); rc_i = |Xc_i|^2;
 // blockmax[b] = largest |entry| of the block's 8 rows (for the power-of-two scale of the
@@ -1066,12 +1072,16 @@ colmax_partial_kernel(const float *__restrict__ X, const float *__restrict__ S, 
         part[(int64_t)blockIdx.x * ld + c] = fmaxf(m0, m1);
     }
 }
-__global__ void colscale_kernel(const float *__restrict__ part, int64_t ld, float *__restrict__ down,
-                                float *__restrict__ up) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+colscale_kernel(const float *__restrict__ part, int64_t ld, float *__restrict__ down, float *__restrict__ up) {
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per column
+    const int lane = threadIdx.x & 31;
     if (c >= ld) return;
     float m = 0.0f;
-    for (int b = 0; b < CM_BLOCKS; ++b) m = fmaxf(m, part[(int64_t)b * ld + c]);
+    for (int b = lane; b < CM_BLOCKS; b += 32) m = fmaxf(m, part[(int64_t)b * ld + c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane != 0) return;
     int e = 0;
     if (m > 0.0f && m < INFINITY) e = ilogbf(m) - 7;        // m 2^-e in [128, 256)
     e = max(-100, min(100, e));
@@ -1221,7 +1231,7 @@ static int make_centred(stein_ctx *ctx, const float *X_all, int64_t n_total, int
     float *blockmax = (float *)pws;  pws += nblk * 4;
     colsum_partial_kernel<<<CM_BLOCKS, 256, 0, ctx->stream>>>(X_all, n_total, ld, part);
     STEIN_CHECK_LAUNCH(ctx);
-    colmean_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, ctx->stream>>>(part, n_total, ld, mean);
+    colmean_kernel<<<(unsigned)((ld * 32 + 255) / 256), 256, 0, ctx->stream>>>(part, n_total, ld, mean);
     STEIN_CHECK_LAUNCH(ctx);
     center_kernel<<<(unsigned)nblk, 256, 0, ctx->stream>>>(X_all, mean, n_total, cols, d, ld, Xc, rc, blockmax);
     STEIN_CHECK_LAUNCH(ctx);
@@ -1522,7 +1532,7 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
             // the FP16 array takes the place of YTh, the two FP8 arrays share the place of YTl
             colmax_partial_kernel<<<CM_BLOCKS, 256, 0, ctx->stream>>>(Xc, S_all, n_total, ld, 1.0f / h2, cmax_part);
             STEIN_CHECK_LAUNCH(ctx);
-            colscale_kernel<<<(unsigned)((DP + 255) / 256), 256, 0, ctx->stream>>>(cmax_part, DP, cs_down, cs_up);
+            colscale_kernel<<<(unsigned)((DP * 32 + 255) / 256), 256, 0, ctx->stream>>>(cmax_part, DP, cs_down, cs_up);
             STEIN_CHECK_LAUNCH(ctx);
             prep_yt8_kernel<<<g, b, 0, ctx->stream>>>(Xc, S_all, cols, ld, 1.0f / h2, cs_down, (__half *)YTh,
                                                      (uint8_t *)YTl, (uint8_t *)YTl + cols * DP);
