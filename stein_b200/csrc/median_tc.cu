@@ -6,7 +6,7 @@
 // The answer must be the order statistic of the CONTRACT-arithmetic distances
 // (fp32 fma chain, see median.cu / oracle/svgd_oracle.c) -- tensor cores cannot
 // produce those bits.  They are used as a FILTER instead:
-//   1. the sweep computes D~ = r_i + r_j - 2 g~ with g~ from a 3-pass BF16-split GEMM
+//   1. the sweep computes D~ = r_i + r_j - 2 g~ with g~ from a 3-pass FP16-split GEMM
 //      (|D~ - D| <= eps_ij = c_half (r_i + r_j), a worst-case bound, see eps_coeff());
 //      pairs that are certainly below the pilot window [wlo, whi] are counted, pairs
 //      certainly above are dropped, the rest (~0.7 %) are appended to a list with D~;
@@ -17,7 +17,7 @@
 //      arithmetic (FFMA chain, pair_chain.cuh) and the exact rank is selected among those keys.
 // Every step checks that the target rank is bracketed; if not (pilot window missed,
 // list overflow) the caller falls back to the all-FFMA route of median.cu.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include <algorithm>
@@ -62,9 +62,10 @@ struct SweepParams {
     int kblocks;                  // DP / 64
     long long n;
     const float *r;
-    const uint32_t *Xh, *Xl;      // BF16 split of X viewed as 32-bit words (DP / 2 per row)
+    const uint32_t *Xh, *Xl;      // FP16 split of s X viewed as 32-bit words (DP / 2 per row)
     float wlo, whi, c_half;
     const float *rmax;            // device: max_i r_i (bounds the column part of the error term)
+    const float *scale;           // device: [s, s^2, 1/s^2], s = power of two applied to X before the FP16 split
     // listed D~ -> bin floor((D~ - hlo) * hscale), clamped to [0, SW_HIST_BINS); hlo / hscale are
     // derived in the kernel from the window and rmax (a device value)
     unsigned long long *hist;     // [SW_HIST_BINS] weighted counts of the listed D~ (accumulated)
@@ -136,7 +137,7 @@ struct TileClassifier {
     unsigned int *sHist, *wCount;
     int wg, row, lane;
     uint32_t lane_addr;
-    float cm, cp, rmax, hlo, hscale;
+    float cm, cp, rmax, hlo, hscale, s2, inv_s2;
     unsigned int below, listed;
 
     __device__ TileClassifier(const SweepParams &p_, uint8_t *tail, int warp, int lane_)
@@ -153,6 +154,10 @@ struct TileClassifier {
         cm = 0.5f * (1.0f - p.c_half);
         cp = 0.5f * (1.0f + p.c_half);
         rmax = __ldg(p.rmax);
+        // g arrives scaled by s^2 (the operands are s X): the thresholds are scaled instead of g --
+        // exact, s is a power of two
+        s2 = __ldg(p.scale + 1);
+        inv_s2 = __ldg(p.scale + 2);
         // histogram range of the listed D~: the window widened by the largest possible error term
         const float hpad = 4.0f * p.c_half * rmax + 1e-5f * fmaxf(fabsf(p.wlo), fabsf(p.whi));
         hlo = p.wlo - hpad;
@@ -176,13 +181,13 @@ struct TileClassifier {
             const long long j0 = (long long)J * 128 + wg * WCOLS + lane;
 #pragma unroll
             for (int cc = 0; cc < CHUNKS; ++cc)
-                wCol[32 * cc + lane] = j0 + 32 * cc < p.n ? cm * __ldg(rj + 32 * cc + lane) : INFINITY;
+                wCol[32 * cc + lane] = j0 + 32 * cc < p.n ? cm * __ldg(rj + 32 * cc + lane) * s2 : INFINITY;
             __syncwarp();
         }
         const float slack = (r_i + rmax) * 9.5367431640625e-07f;   // 2^-20
         // rows beyond n: lo_i = hi_i = +inf, so every pair is "above" (neither counted nor listed)
-        const float lo_i = row_ok ? cm * r_i - 0.5f * p.whi - 2.0f * slack : INFINITY;
-        const float hi_i = row_ok ? cp * r_i + p.c_half * rmax - 0.5f * p.wlo + 2.0f * slack : INFINITY;
+        const float lo_i = row_ok ? (cm * r_i - 0.5f * p.whi - 2.0f * slack) * s2 : INFINITY;
+        const float hi_i = row_ok ? (cp * r_i + p.c_half * rmax - 0.5f * p.wlo + 2.0f * slack) * s2 : INFINITY;
 #pragma unroll 1
         for (int cc = 0; cc < CHUNKS; ++cc) {
             const int ch = wg * CHUNKS + cc;
@@ -221,7 +226,7 @@ struct TileClassifier {
                     PairEntry e;
                     e.i = (uint32_t)i;
                     e.jw = (uint32_t)(jbase + c) | (w == 2u ? 0x80000000u : 0u);
-                    e.dt = fmaf(-2.0f, g, r_i + __ldg(rj + cc * 32 + c));
+                    e.dt = fmaf(-2.0f * inv_s2, g, r_i + __ldg(rj + cc * 32 + c));
                     if (slot < (unsigned)WCAP) {
                         wBuf[slot] = e;
                     } else {   // staging full (degenerate data): straight to global
@@ -346,7 +351,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
             // ===================== MMA issuer =====================
             // The whole warp runs the loop (uniform control flow, descriptors in uniform
             // registers); one elected lane issues the tcgen05 instructions.
-            const uint32_t idesc = make_idesc(FMT_BF16, 128, 128);
+            const uint32_t idesc = make_idesc(FMT_F16, 128, 128);
             int stage = 0;
             uint32_t phase = 0;
             int prevI = -1, aseg = 0;
@@ -590,7 +595,7 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
             }
         } else if (warp == 1 && leader) {
             // ===================== MMA issuer (leader CTA only) =====================
-            const uint32_t idesc = make_idesc(FMT_BF16, 256, 128);
+            const uint32_t idesc = make_idesc(FMT_F16, 256, 128);
             int stage = 0;
             uint32_t phase = 0;
             int prevI2 = -1, aseg = 0;
@@ -672,24 +677,27 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
 }
 
 // ---- helpers ---------------------------------------------------------------------------
-__global__ void split_bf16_kernel(const float *__restrict__ X, int64_t count4, __nv_bfloat16 *__restrict__ Xh,
-                                  __nv_bfloat16 *__restrict__ Xl) {
+// hi = fp16(s x), lo = fp16(s x - hi): 22 bits of s x (entries far below the largest one end in
+// the FP16 subnormals; that absolute error is covered by the slack terms, see eps_coeff)
+__global__ void split_f16_kernel(const float *__restrict__ X, int64_t count4, const float *__restrict__ scale,
+                                 __half *__restrict__ Xh, __half *__restrict__ Xl) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= count4) return;
+    const float sc = __ldg(scale);
     const float4 x = reinterpret_cast<const float4 *>(X)[e];
-    const float xs[4] = {x.x, x.y, x.z, x.w};
-    __nv_bfloat16 h[4], l[4];
+    const float xs[4] = {x.x * sc, x.y * sc, x.z * sc, x.w * sc};
+    __half h[4], l[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        h[k] = __float2bfloat16_rn(xs[k]);
-        l[k] = __float2bfloat16_rn(xs[k] - __bfloat162float(h[k]));
+        h[k] = __float2half_rn(xs[k]);
+        l[k] = __float2half_rn(xs[k] - __half2float(h[k]));
     }
     reinterpret_cast<uint2 *>(Xh)[e] = *reinterpret_cast<uint2 *>(h);
     reinterpret_cast<uint2 *>(Xl)[e] = *reinterpret_cast<uint2 *>(l);
 }
 
 __global__ void __launch_bounds__(1024)
-max_kernel(const float *__restrict__ r, int64_t n, float *__restrict__ out) {
+max_kernel(const float *__restrict__ r, int64_t n, float *__restrict__ out, float *__restrict__ scale_out) {
     __shared__ float red[32];
     float m = 0.0f;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, r[i]);
@@ -701,7 +709,16 @@ max_kernel(const float *__restrict__ r, int64_t n, float *__restrict__ out) {
         m = red[threadIdx.x];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (threadIdx.x == 0) *out = m;
+        if (threadIdx.x == 0) {
+            *out = m;
+            // s = 2^-e with sqrt(rmax) s in [128, 256): no entry of s X exceeds 256
+            int e = 0;
+            if (m > 0.0f && m < INFINITY) e = ilogbf(sqrtf(m)) - 7;
+            e = max(-60, min(60, e));
+            scale_out[0] = ldexpf(1.0f, -e);
+            scale_out[1] = ldexpf(1.0f, -2 * e);
+            scale_out[2] = ldexpf(1.0f, 2 * e);
+        }
     }
 }
 
@@ -752,7 +769,7 @@ constexpr int BF_THREADS = 256;
 constexpr int BF_STAGE = 1024;
 __global__ void __launch_bounds__(BF_THREADS)
 band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, const float *__restrict__ r,
-                   float tlo, float thi, float c_half, unsigned long long *__restrict__ below_out,
+                   float tlo, float thi, float c_half, float eps_abs, unsigned long long *__restrict__ below_out,
                    unsigned long long *__restrict__ bandw_out, unsigned long long *__restrict__ bandlen_out,
                    uint2 *__restrict__ band_ij, unsigned long long band_cap, int *__restrict__ overflow) {
     __shared__ uint2 stage[BF_STAGE];
@@ -785,7 +802,7 @@ band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, con
         if (e < b1) {
             pe = list[e];
             const uint32_t i = pe.i, j = pe.jw & 0x7fffffffu, w = (pe.jw >> 31) ? 2u : 1u;
-            const float eps = c_half * (r[i] + r[j]);
+            const float eps = c_half * (r[i] + r[j]) + eps_abs;
             if (pe.dt + eps < tlo) {
                 below += w;
             } else if (pe.dt - eps <= thi) {
@@ -820,18 +837,21 @@ band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, con
     }
 }
 
-// worst-case |D~ - D_contract| <= eps_coeff(d) * (r_i + r_j):
-//   BF16 2-term split: dropped lo.lo and the rounding of lo, <= 3 * 2^-18 |x_i||x_j|;
+// worst-case |D~ - D_contract| <= eps_coeff(d) * (r_i + r_j) + EPS_ABS * rmax:
+//   FP16 2-term split of s X: dropped lo.lo and the rounding of lo, <= 3 * 2^-22 |x_i||x_j|
+//     (plus, for entries that end in the FP16 subnormals, <= 2^-25 absolute per entry of s X,
+//      i.e. <= 2^-23 sqrt(d) sqrt(rmax) / s <= 2^-26 d^(1/2) rmax / 16 in D: the EPS_ABS term);
 //   tensor-core accumulation (truncating, 3 d/16 adds of magnitude <= |x_i||x_j|): 3d/16 * 2^-23;
 //   contract fma chain: d * 2^-24 |x_i||x_j|;  |x_i||x_j| <= (r_i + r_j)/2;  final roundings 2^-22.
 // All doubled once more as a safety margin.
 static float eps_coeff(int64_t d) {
-    const double per_xx = 3.0 * ldexp(1.0, -18) + (3.0 * d / 16.0) * ldexp(1.0, -23) + d * ldexp(1.0, -24);
+    const double per_xx = 3.0 * ldexp(1.0, -22) + (3.0 * d / 16.0) * ldexp(1.0, -23) + d * ldexp(1.0, -24);
     return (float)(2.0 * (per_xx + ldexp(1.0, -22)));
 }
+constexpr float EPS_ABS = 2.384185791015625e-07f;    // 2^-22 (d <= 256: 2^-26 * 16 / 16 = 2^-26, x16 margin)
 
 struct MedianArena {
-    __nv_bfloat16 *Xh = nullptr, *Xl = nullptr;
+    __half *Xh = nullptr, *Xl = nullptr;
     PairEntry *list = nullptr;
     uint2 *band = nullptr;
     unsigned long long *counters = nullptr;   // CNT_TOTAL u64, layout below
@@ -848,7 +868,8 @@ constexpr int CNT_G1_END = CNT_HIST + SW_HIST_BINS;
 constexpr int CNT_LIST_LEN = CNT_G1_END;
 constexpr int CNT_BELOW2 = CNT_G1_END + 1, CNT_BANDW = CNT_G1_END + 2, CNT_OVERFLOW2 = CNT_G1_END + 3;
 constexpr int CNT_BAND_LEN = CNT_G1_END + 4, CNT_RMAX = CNT_G1_END + 5, CNT_HPARAMS = CNT_G1_END + 6;
-constexpr int CNT_TOTAL = CNT_G1_END + 8;
+constexpr int CNT_SCALE = CNT_G1_END + 7;      // 3 floats: s, s^2, 1/s^2
+constexpr int CNT_TOTAL = CNT_G1_END + 10;
 
 static MedianArena g_arena;   // one per process (one GPU per process)
 
@@ -1048,13 +1069,14 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     const float c_half = eps_coeff(d);
 
     STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(A.counters, 0, CNT_TOTAL * 8, ctx->stream));
-    const int64_t count4 = rows * DP / 4;
-    split_bf16_kernel<<<(unsigned)((count4 + 255) / 256), 256, 0, ctx->stream>>>(X, count4, A.Xh, A.Xl);
-    STEIN_CHECK_LAUNCH(ctx);
     float *d_rmax = reinterpret_cast<float *>(A.counters + CNT_RMAX);
+    float *d_scale = reinterpret_cast<float *>(A.counters + CNT_SCALE);
     int *d_overflow = reinterpret_cast<int *>(A.counters + CNT_OVERFLOW);
     int *d_overflow2 = reinterpret_cast<int *>(A.counters + CNT_OVERFLOW2);
-    max_kernel<<<1, 1024, 0, ctx->stream>>>(r, n, d_rmax);
+    max_kernel<<<1, 1024, 0, ctx->stream>>>(r, n, d_rmax, d_scale);
+    STEIN_CHECK_LAUNCH(ctx);
+    const int64_t count4 = rows * DP / 4;
+    split_f16_kernel<<<(unsigned)((count4 + 255) / 256), 256, 0, ctx->stream>>>(X, count4, d_scale, A.Xh, A.Xl);
     STEIN_CHECK_LAUNCH(ctx);
 
     CUtensorMap mapXh, mapXl;
@@ -1073,6 +1095,7 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     p.whi = key_to_float(win_hi_key);
     p.c_half = c_half;
     p.rmax = d_rmax;
+    p.scale = d_scale;
     p.hist = A.counters + CNT_HIST;
     p.cnt_below = A.counters + CNT_BELOW;
     p.cnt_listed = A.counters + CNT_LISTED;
@@ -1136,12 +1159,13 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     const float bin_w = 1.0f / hscale;
     const float t_lo = hlo + (float)(bstar - 1) * bin_w, t_hi = hlo + (float)(bstar + 2) * bin_w;
     // the exact value at a rank differs from the D~ value at that rank by at most max eps
-    const float delta = c_half * 2.0f * rmax * 1.0001f + 2.0f * fmaxf(fabsf(t_lo), fabsf(t_hi)) * 1.2e-7f;
+    const float eps_abs = EPS_ABS * rmax;
+    const float delta = c_half * 2.0f * rmax * 1.0001f + eps_abs + 2.0f * fmaxf(fabsf(t_lo), fabsf(t_hi)) * 1.2e-7f;
     const float tlo = t_lo - delta, thi = t_hi + delta;
 
     if (list_len) {
         const unsigned grid = (unsigned)std::min<unsigned long long>((list_len + 255) / 256, 16ull * ctx->num_sms);
-        band_filter_kernel<<<grid, BF_THREADS, 0, ctx->stream>>>(A.list, list_len, r, tlo, thi, c_half,
+        band_filter_kernel<<<grid, BF_THREADS, 0, ctx->stream>>>(A.list, list_len, r, tlo, thi, c_half, eps_abs,
                                                                 A.counters + CNT_BELOW2, A.counters + CNT_BANDW,
                                                                 A.counters + CNT_BAND_LEN, A.band, A.band_cap,
                                                                 d_overflow2);
