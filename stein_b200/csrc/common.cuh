@@ -28,6 +28,9 @@ struct stein_ctx {
     void *nccl_state = nullptr;     // built-in NCCL transport (comm_nccl.cu), if initialised
     int phi_impl = STEIN_PHI_AUTO;
     int median_impl = STEIN_MEDIAN_AUTO;
+    // set by an engine around its median call: identifies the sequence of calls whose medians move
+    // slowly, so that the previous window may be used as a hint (NULL: independent call, no hint)
+    const void *median_owner = nullptr;
     int64_t launches = 0;
     std::string error;
     // pinned host staging + device scratch for the median loop

@@ -43,6 +43,7 @@ struct stein_engine {
     bool peers_open = false;
     bool x_all_current = false;     // every rank's X_all holds everybody's current rows
     unsigned long long *barrier_word = nullptr;   // 1 u64 all-reduced as the cross-rank barrier after a push
+    uintptr_t uid = 0;      // unique per engine ever created in the process (median window hint owner)
     float last_med = 0.f, last_bw = 0.f;
     int32_t last_sweeps = 0;
     float *X_local() const { return X_all + (int64_t)rank * q * ld; }
@@ -129,7 +130,9 @@ int stein_engine_create(stein_engine **out, stein_ctx *ctx, int64_t n_total, int
     STEIN_REQUIRE(ctx, d >= 1, "d must be positive");
     STEIN_REQUIRE(ctx, optimizer == STEIN_OPT_ADAM || optimizer == STEIN_OPT_ADAGRAD, "unknown optimizer");
     STEIN_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    static uintptr_t next_uid = 1;
     stein_engine *e = new stein_engine();
+    e->uid = next_uid++;
     e->ctx = ctx;
     e->n_total = n_total;
     e->d = d;
@@ -261,8 +264,12 @@ static int step_bandwidth(stein_engine *e, float *bw_out) {
     STEIN_TRY(stein_row_norms(ctx, e->X_all, rows_all, e->d, e->ld, e->r_all));
     // compute_median.py + abstract_kernel.py:40
     float med = 0.f;
-    STEIN_TRY(stein_median_sqdist(ctx, e->X_all, e->r_all, e->n_total, e->d, e->ld, &med, nullptr,
-                                  &e->last_sweeps));
+    // successive medians of one engine move slowly: window hint allowed (owner = the engine's uid)
+    ctx->median_owner = reinterpret_cast<const void *>(e->uid);
+    const int mrc = stein_median_sqdist(ctx, e->X_all, e->r_all, e->n_total, e->d, e->ld, &med, nullptr,
+                                        &e->last_sweeps);
+    ctx->median_owner = nullptr;
+    if (mrc != STEIN_OK) return mrc;
     const float bw = stein_bandwidth(med, e->n_total);
     e->last_med = med;
     e->last_bw = bw;

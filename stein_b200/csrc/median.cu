@@ -296,9 +296,15 @@ static const Window kFullWindow = {0u, 18u, (uint32_t)HIST_MAX_BINS};
 
 // median_tc.cu
 bool median_tc_supported(int64_t n, int64_t ld);
+struct PilotSpec {
+    const uint32_t *keys_dev;
+    unsigned long long m_local;
+    unsigned long long rank_lo, rank_hi;
+};
+bool median_tc_has_hint(const stein_ctx *ctx);
 int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t d, int64_t ld,
               const uint64_t ranks[2], uint32_t win_lo_key, uint32_t win_hi_key, uint32_t keys_out[2],
-              int *sweeps);
+              int *sweeps, const PilotSpec *spec);
 int pilot_window(stein_ctx *ctx, const uint32_t *keys_dev, int64_t m, uint64_t rank_lo, uint64_t rank_hi,
                  uint32_t *lo_key, uint32_t *hi_key);
 
@@ -477,8 +483,17 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
         STEIN_TRY(launch_pair_chain<1>(ctx, ctx->d_pilot_keys + s0, (unsigned long long)(s1 - s0), X_dev, r_dev, n, ld,
                                        0x5eedull + (uint64_t)s0));
         const uint64_t delta = (uint64_t)(3.5 * sqrt((double)pilot_m));
-        uint32_t ka = 0, kb = 0;
-        {
+        const bool tc_ok = ctx->median_impl != STEIN_MEDIAN_FFMA && median_tc_supported(n, ld);
+        // steady state: pilot histogram, window pick and sweep chained on the device
+        if (tc_ok && median_tc_has_hint(ctx)) {
+            const PilotSpec spec = {ctx->d_pilot_keys + s0, (unsigned long long)(s1 - s0), pilot_m / 2 - delta,
+                                    pilot_m / 2 + delta};
+            const int rc = median_tc(ctx, X_dev, r_dev, n, d, ld, ranks, 0u, 0u, key, &sweeps, &spec);
+            if (rc < 0) return rc;
+            if (rc == STEIN_OK) done[0] = done[1] = true;
+        }
+        uint32_t ka = 1u, kb = 0u;
+        if (!(done[0] && done[1])) {
             const int prc = pilot_window(ctx, ctx->d_pilot_keys + s0, s1 - s0, pilot_m / 2 - delta,
                                          pilot_m / 2 + delta, &ka, &kb);
             if (prc < 0) return prc;
@@ -495,8 +510,8 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
             win[0] = win[1] = w;
             // tensor-core route: one tcgen05 sweep + exact recomputation of the few pairs
             // that can matter; falls through to the FFMA sweeps if it cannot bracket the rank
-            if (ctx->median_impl != STEIN_MEDIAN_FFMA && median_tc_supported(n, ld)) {
-                const int rc = median_tc(ctx, X_dev, r_dev, n, d, ld, ranks, ka, kb, key, &sweeps);
+            if (tc_ok) {
+                const int rc = median_tc(ctx, X_dev, r_dev, n, d, ld, ranks, ka, kb, key, &sweeps, nullptr);
                 if (rc < 0) return rc;
                 if (rc == STEIN_OK) done[0] = done[1] = true;
             }

@@ -64,6 +64,8 @@ struct SweepParams {
     const float *r;
     const uint32_t *Xh, *Xl;      // FP16 split of s X viewed as 32-bit words (DP / 2 per row)
     float wlo, whi, c_half;
+    const float *window;          // device [wlo, whi] replacing the two fields above when non-NULL (set by
+                                  // pilot_pick_kernel without a host round trip)
     const float *rmax;            // device: max_i r_i (bounds the column part of the error term)
     const float *scale;           // device: [s, s^2, 1/s^2], s = power of two applied to X before the FP16 split
     // listed D~ -> bin floor((D~ - hlo) * hscale), clamped to [0, SW_HIST_BINS); hlo / hscale are
@@ -137,7 +139,7 @@ struct TileClassifier {
     unsigned int *sHist, *wCount;
     int wg, row, lane;
     uint32_t lane_addr;
-    float cm, cp, rmax, hlo, hscale, s2, inv_s2;
+    float cm, cp, rmax, hlo, hscale, s2, inv_s2, wlo, whi;
     unsigned int below, listed;
 
     __device__ TileClassifier(const SweepParams &p_, uint8_t *tail, int warp, int lane_)
@@ -154,14 +156,16 @@ struct TileClassifier {
         cm = 0.5f * (1.0f - p.c_half);
         cp = 0.5f * (1.0f + p.c_half);
         rmax = __ldg(p.rmax);
+        wlo = p.window ? __ldg(p.window) : p.wlo;
+        whi = p.window ? __ldg(p.window + 1) : p.whi;
         // g arrives scaled by s^2 (the operands are s X): the thresholds are scaled instead of g --
         // exact, s is a power of two
         s2 = __ldg(p.scale + 1);
         inv_s2 = __ldg(p.scale + 2);
         // histogram range of the listed D~: the window widened by the largest possible error term
-        const float hpad = 4.0f * p.c_half * rmax + 1e-5f * fmaxf(fabsf(p.wlo), fabsf(p.whi));
-        hlo = p.wlo - hpad;
-        hscale = (float)SW_HIST_BINS / fmaxf((p.whi + hpad) - hlo, 1e-30f);
+        const float hpad = 4.0f * p.c_half * rmax + 1e-5f * fmaxf(fabsf(wlo), fabsf(whi));
+        hlo = wlo - hpad;
+        hscale = (float)SW_HIST_BINS / fmaxf((whi + hpad) - hlo, 1e-30f);
         if (blockIdx.x == 0 && ew == 0 && lane == 0) {
             p.hparams_out[0] = hlo;
             p.hparams_out[1] = hscale;
@@ -186,8 +190,8 @@ struct TileClassifier {
         }
         const float slack = (r_i + rmax) * 9.5367431640625e-07f;   // 2^-20
         // rows beyond n: lo_i = hi_i = +inf, so every pair is "above" (neither counted nor listed)
-        const float lo_i = row_ok ? (cm * r_i - 0.5f * p.whi - 2.0f * slack) * s2 : INFINITY;
-        const float hi_i = row_ok ? (cp * r_i + p.c_half * rmax - 0.5f * p.wlo + 2.0f * slack) * s2 : INFINITY;
+        const float lo_i = row_ok ? (cm * r_i - 0.5f * whi - 2.0f * slack) * s2 : INFINITY;
+        const float hi_i = row_ok ? (cp * r_i + p.c_half * rmax - 0.5f * wlo + 2.0f * slack) * s2 : INFINITY;
 #pragma unroll 1
         for (int cc = 0; cc < CHUNKS; ++cc) {
             const int ch = wg * CHUNKS + cc;
@@ -760,6 +764,63 @@ window_hist_kernel(const void *__restrict__ src, unsigned long long m, const uns
         if (wh[b]) atomicAdd(&bins[b], (unsigned long long)wh[b]);
 }
 
+// Device-side pick of the pilot window: bins (1 + nbins u64, counts of a window histogram of the
+// pilot keys) -> the keys that bracket rank_lo / rank_hi at bin resolution.  out: [0],[1] =
+// window as floats, [2],[3] = as keys, [4] = 1 when both ranks lie inside the histogram window.
+__global__ void __launch_bounds__(1024)
+pilot_pick_kernel(const unsigned long long *__restrict__ bins, uint32_t key_lo, uint32_t shift, uint32_t nbins,
+                  unsigned long long rank_lo, unsigned long long rank_hi, uint32_t *__restrict__ out) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ long long s_bin[2];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t < 2) s_bin[t] = -1;
+    // thread t owns bins [16 t, 16 t + 16) (nbins <= 16384)
+    unsigned long long loc[16], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t b = 16u * t + k;
+        loc[k] = b < nbins ? bins[1 + b] : 0ull;
+        tot += loc[k];
+    }
+    unsigned long long incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = wsum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    unsigned long long cum = bins[0] + wsum[warp] + incl - tot;     // weight before this thread's bins
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        if (rank_lo >= cum && rank_lo < cum + loc[k]) s_bin[0] = 16 * t + k;
+        if (rank_hi >= cum && rank_hi < cum + loc[k]) s_bin[1] = 16 * t + k;
+        cum += loc[k];
+    }
+    __syncthreads();
+    if (t == 0) {
+        const bool ok = s_bin[0] >= 0 && s_bin[1] >= 0 && rank_lo >= bins[0];
+        unsigned long long lo = (unsigned long long)key_lo + ((unsigned long long)(ok ? s_bin[0] : 0) << shift);
+        unsigned long long hi = (unsigned long long)key_lo + (((unsigned long long)(ok ? s_bin[1] : 0) + 1) << shift) - 1;
+        if (hi > 0xffffffffull) hi = 0xffffffffull;
+        out[0] = __float_as_uint(key_to_float((uint32_t)lo));
+        out[1] = __float_as_uint(key_to_float((uint32_t)hi));
+        out[2] = (uint32_t)lo;
+        out[3] = (uint32_t)hi;
+        out[4] = ok ? 1u : 0u;
+    }
+}
+
 // entries certainly below t~ - delta are counted; entries that may fall inside
 // [t~ - delta, t~ + delta] are compacted into the band (key slot filled by pair_chain_kernel).
 // A block walks a contiguous part of the list and stages its band entries in shared memory, so
@@ -850,6 +911,12 @@ static float eps_coeff(int64_t d) {
 }
 constexpr float EPS_ABS = 2.384185791015625e-07f;    // 2^-22 (d <= 256: 2^-26 * 16 / 16 = 2^-26, x16 margin)
 
+struct PilotSpec {
+    const uint32_t *keys_dev;       // this rank's slice of the pilot keys
+    unsigned long long m_local;
+    unsigned long long rank_lo, rank_hi;   // ranks in the WHOLE sample that bracket the median
+};
+
 struct MedianArena {
     __half *Xh = nullptr, *Xl = nullptr;
     PairEntry *list = nullptr;
@@ -859,6 +926,10 @@ struct MedianArena {
     unsigned long long *h_pinned = nullptr;   // HIST_MAX_BINS + 2 window counts, then CNT_TOTAL counters
     int64_t x_elems = 0;
     unsigned long long list_cap = 0, band_cap = 0;
+    // centre of the last pilot window (keys): successive iterations move the median only slightly
+    uint32_t last_center = 0u;
+    bool have_last = false;
+    const void *hint_owner = nullptr;     // the engine (stein_ctx::median_owner) the hint belongs to
 };
 
 // counters block (u64 slots).  Slots [0, CNT_G1_END) are global quantities after the sweep (one
@@ -869,9 +940,15 @@ constexpr int CNT_LIST_LEN = CNT_G1_END;
 constexpr int CNT_BELOW2 = CNT_G1_END + 1, CNT_BANDW = CNT_G1_END + 2, CNT_OVERFLOW2 = CNT_G1_END + 3;
 constexpr int CNT_BAND_LEN = CNT_G1_END + 4, CNT_RMAX = CNT_G1_END + 5, CNT_HPARAMS = CNT_G1_END + 6;
 constexpr int CNT_SCALE = CNT_G1_END + 7;      // 3 floats: s, s^2, 1/s^2
-constexpr int CNT_TOTAL = CNT_G1_END + 10;
+constexpr int CNT_WINDOW = CNT_G1_END + 9;     // device-picked pilot window: 2 floats, 2 keys, status word
+constexpr int CNT_TOTAL = CNT_G1_END + 12;
 
 static MedianArena g_arena;   // one per process (one GPU per process)
+
+// the hint is only used within one engine's sequence of iterations
+static bool hint_usable(const stein_ctx *ctx) {
+    return g_arena.have_last && ctx->median_owner != nullptr && g_arena.hint_owner == ctx->median_owner;
+}
 
 static int ensure_arena(stein_ctx *ctx, int64_t rows, int64_t DP, uint64_t pairs) {
     MedianArena &A = g_arena;
@@ -1018,11 +1095,11 @@ int pilot_window(stein_ctx *ctx, const uint32_t *keys_dev, int64_t m, uint64_t r
     // Successive SVGD iterations move the median by a fraction of a percent: first try ONE pass
     // over +-2^20 keys (about +-9 % in value, 128 keys per bin) around the last window.  The
     // result is only used when both ranks fall inside; otherwise the two generic passes run.
-    static uint32_t last_center = 0u;
-    static bool have_last = false;
+    uint32_t &last_center = g_arena.last_center;
+    bool &have_last = g_arena.have_last;
     uint64_t lo = 0, hi = 0;
     bool found = false;
-    if (have_last) {
+    if (hint_usable(ctx)) {
         const uint32_t c = last_center, half = 1u << 20;
         const KeyWindow w = window_over(c > half ? c - half : 0u, c < 0xffffffffu - half ? c + half : 0xffffffffu);
         STEIN_TRY(window_counts<2>(ctx, keys_dev, (unsigned long long)m, w.key_lo, w.shift, w.nbins, true));
@@ -1044,6 +1121,7 @@ int pilot_window(stein_ctx *ctx, const uint32_t *keys_dev, int64_t m, uint64_t r
     *hi_key = (uint32_t)hi;
     last_center = (uint32_t)((lo + hi) / 2);
     have_last = true;
+    g_arena.hint_owner = ctx->median_owner;
     return STEIN_OK;
 }
 
@@ -1053,9 +1131,14 @@ bool median_tc_supported(int64_t n, int64_t ld) {
 }
 
 // returns STEIN_OK with keys filled, 1 = "not bracketed, use the FFMA route", <0 = error
+bool median_tc_has_hint(const stein_ctx *ctx) { return hint_usable(ctx); }
+
+// spec != NULL: the window is not given but derived ON THE DEVICE from one histogram pass over the
+// pilot keys around the previous window (no host round trip between pilot and sweep).  Returns 2
+// when the pilot ranks fell outside that histogram (the caller then takes the generic route).
 int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t d, int64_t ld,
               const uint64_t ranks[2], uint32_t win_lo_key, uint32_t win_hi_key, uint32_t keys_out[2],
-              int *sweeps) {
+              int *sweeps, const PilotSpec *spec) {
     const int64_t rows = stein_rows_padded(n), DP = ld;
     const int64_t T = (n + TILE - 1) / TILE;
     const uint64_t pairs = (uint64_t)T * (T + 1) / 2 * TILE * TILE;
@@ -1079,6 +1162,30 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     split_f16_kernel<<<(unsigned)((count4 + 255) / 256), 256, 0, ctx->stream>>>(X, count4, d_scale, A.Xh, A.Xl);
     STEIN_CHECK_LAUNCH(ctx);
 
+    if (spec) {
+        // one histogram pass over +-2^20 keys around the last window, then the device picks the bins
+        const uint32_t c = A.last_center, half = 1u << 20;
+        const KeyWindow w = window_over(c > half ? c - half : 0u, c < 0xffffffffu - half ? c + half : 0xffffffffu);
+        static bool attr2 = false;
+        if (!attr2) {
+            STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(window_hist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                       (HIST_MAX_BINS + 1) * 4));
+            attr2 = true;
+        }
+        STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(A.bins, 0, (w.nbins + 1) * 8, ctx->stream));
+        if (spec->m_local) {
+            const unsigned grid = (unsigned)std::min<unsigned long long>((spec->m_local + 255) / 256, 4ull * ctx->num_sms);
+            window_hist_kernel<2><<<grid, 256, (w.nbins + 1) * 4, ctx->stream>>>(spec->keys_dev, spec->m_local, nullptr,
+                                                                               w.key_lo, w.shift, w.nbins, A.bins);
+            STEIN_CHECK_LAUNCH(ctx);
+        }
+        if (world > 1 && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.bins, (int64_t)w.nbins + 1) != 0)
+            return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+        pilot_pick_kernel<<<1, 1024, 0, ctx->stream>>>(A.bins, w.key_lo, w.shift, w.nbins, spec->rank_lo, spec->rank_hi,
+                                                      reinterpret_cast<uint32_t *>(A.counters + CNT_WINDOW));
+        STEIN_CHECK_LAUNCH(ctx);
+    }
+
     CUtensorMap mapXh, mapXl;
     STEIN_TRY(make_tensor_map_2d(ctx, &mapXh, A.Xh, 2, (uint64_t)DP, (uint64_t)rows, (uint64_t)DP * 2, 128));
     STEIN_TRY(make_tensor_map_2d(ctx, &mapXl, A.Xl, 2, (uint64_t)DP, (uint64_t)rows, (uint64_t)DP * 2, 128));
@@ -1093,6 +1200,7 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     p.Xl = reinterpret_cast<const uint32_t *>(A.Xl);
     p.wlo = key_to_float(win_lo_key);
     p.whi = key_to_float(win_hi_key);
+    p.window = spec ? reinterpret_cast<const float *>(A.counters + CNT_WINDOW) : nullptr;
     p.c_half = c_half;
     p.rmax = d_rmax;
     p.scale = d_scale;
@@ -1141,6 +1249,16 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     const float rmax = *reinterpret_cast<float *>(h + CNT_RMAX);
     const float hlo = reinterpret_cast<float *>(h + CNT_HPARAMS)[0], hscale = reinterpret_cast<float *>(h + CNT_HPARAMS)[1];
     const uint64_t below = h[CNT_BELOW], listed = h[CNT_LISTED];
+    if (spec) {
+        const uint32_t *wv = reinterpret_cast<const uint32_t *>(h + CNT_WINDOW);
+        if (!wv[4]) {            // the pilot ranks were not inside the histogram around the old window
+            A.have_last = false;
+            return 2;
+        }
+        memcpy(&p.wlo, &wv[0], 4);
+        memcpy(&p.whi, &wv[1], 4);
+        A.last_center = (uint32_t)(((uint64_t)wv[2] + wv[3]) / 2);
+    }
     if (h[CNT_OVERFLOW]) return 1;
     if (!(below <= ranks[0] && ranks[1] < below + listed)) return 1;   // pilot window missed
 
