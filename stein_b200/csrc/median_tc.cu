@@ -47,6 +47,9 @@ constexpr size_t SW_TAIL_COL = SW_TAIL_BUF + (size_t)SW_EPI_WARPS * SW_WARP_CAP 
 constexpr size_t SW_TAIL_HIST = SW_TAIL_COL + (size_t)SW_EPI_WARPS * 64 * 4;    // u32 [SW_HIST_BINS]
 constexpr int SW_HIST_BINS = 4096;          // histogram of the listed D~ (locates t~ without extra passes)
 constexpr size_t SW_TAIL_BYTES = SW_TAIL_HIST + (size_t)SW_HIST_BINS * 4 + 64;
+// 32-bit words of the device-picked band parameters (pick_band_kernel)
+constexpr int BP_TLO = 0, BP_THI = 1, BP_DELTA = 2, BP_EPS_ABS = 3, BP_KLO = 4, BP_SHIFT = 5, BP_NBINS = 6,
+              BP_STATUS = 7;   // 0 = usable
 constexpr uint32_t SW_TMEM_COLS = 512;
 constexpr uint32_t SW_TMEM_AH = 256, SW_TMEM_AL = 384;   // A operand (row tile, BF16 hi / lo) in TMEM
 
@@ -732,9 +735,16 @@ max_kernel(const float *__restrict__ r, int64_t n, float *__restrict__ out, floa
 template <int SRC>
 __global__ void __launch_bounds__(256)
 window_hist_kernel(const void *__restrict__ src, unsigned long long m, const unsigned long long *__restrict__ m_dev,
-                   uint32_t key_lo, uint32_t shift, uint32_t nbins, unsigned long long *__restrict__ bins) {
+                   uint32_t key_lo, uint32_t shift, uint32_t nbins, unsigned long long *__restrict__ bins,
+                   const uint32_t *__restrict__ bp = nullptr) {
     extern __shared__ unsigned int wh[];      // nbins + 1
     if (m_dev) m = min(m, *m_dev);            // length only known on the device (m = upper bound)
+    if (bp) {                                 // window picked on the device (pick_band_kernel)
+        if (bp[BP_STATUS] != 0u) return;
+        key_lo = bp[BP_KLO];
+        shift = bp[BP_SHIFT];
+        nbins = bp[BP_NBINS];
+    }
     for (uint32_t b = threadIdx.x; b <= nbins; b += blockDim.x) wh[b] = 0u;
     __syncthreads();
     unsigned int below = 0u;
@@ -821,6 +831,76 @@ pilot_pick_kernel(const unsigned long long *__restrict__ bins, uint32_t key_lo, 
     }
 }
 
+// Device-side counterpart of the host logic after the sweep: from the (all-reduced) counters and
+// the histogram of the listed D~, locate the bin of the target rank and derive the band
+// thresholds and the key window of the final select.  cnt = counters block (u64 slots).
+__global__ void __launch_bounds__(1024)
+pick_band_kernel(const unsigned long long *__restrict__ cnt, int slot_below, int slot_listed, int slot_overflow,
+                 int slot_hist, int slot_rmax, int slot_hparams, unsigned long long rank0, unsigned long long rank1,
+                 float c_half, float eps_abs_coeff, uint32_t max_bins, uint32_t *__restrict__ bp) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ int s_bin;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) s_bin = -1;
+    unsigned long long loc[4], tot = 0;          // thread t owns bins [4 t, 4 t + 4) of SW_HIST_BINS = 4096
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        loc[k] = cnt[slot_hist + 4 * t + k];
+        tot += loc[k];
+    }
+    unsigned long long incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = wsum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    const unsigned long long below = cnt[slot_below], listed = cnt[slot_listed];
+    unsigned long long cum = below + wsum[warp] + incl - tot;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (rank0 >= cum && rank0 < cum + loc[k]) s_bin = 4 * t + k;
+        cum += loc[k];
+    }
+    __syncthreads();
+    if (t != 0) return;
+    const int bstar = s_bin;
+    const bool ok = cnt[slot_overflow] == 0 && below <= rank0 && rank1 < below + listed && bstar > 0 &&
+                    bstar < SW_HIST_BINS - 1;
+    const float rmax = __uint_as_float((uint32_t)cnt[slot_rmax]);
+    const uint32_t hp0 = (uint32_t)cnt[slot_hparams], hp1 = (uint32_t)(cnt[slot_hparams] >> 32);
+    const float hlo = __uint_as_float(hp0), hscale = __uint_as_float(hp1);
+    // t~ lies in bin bstar; one extra bin on either side covers the rounding of the bin function
+    const float bin_w = 1.0f / hscale;
+    const float t_lo = hlo + (float)(bstar - 1) * bin_w, t_hi = hlo + (float)(bstar + 2) * bin_w;
+    const float eps_abs = eps_abs_coeff * rmax;
+    const float delta = c_half * 2.0f * rmax * 1.0001f + eps_abs + 2.0f * fmaxf(fabsf(t_lo), fabsf(t_hi)) * 1.2e-7f;
+    const float tlo = t_lo - delta, thi = t_hi + delta;
+    const uint32_t klo = float_to_key(tlo - 2.0f * delta), khi = float_to_key(thi + 2.0f * delta);
+    const unsigned long long span = (unsigned long long)khi - klo + 1;
+    uint32_t sh = 0;
+    while (((span - 1) >> sh) >= (unsigned long long)max_bins) ++sh;
+    bp[BP_TLO] = __float_as_uint(tlo);
+    bp[BP_THI] = __float_as_uint(thi);
+    bp[BP_DELTA] = __float_as_uint(delta);
+    bp[BP_EPS_ABS] = __float_as_uint(eps_abs);
+    bp[BP_KLO] = klo;
+    bp[BP_SHIFT] = sh;
+    bp[BP_NBINS] = (uint32_t)(((span - 1) >> sh) + 1);
+    bp[BP_STATUS] = (ok && khi >= klo) ? 0u : 1u;
+}
+
 // entries certainly below t~ - delta are counted; entries that may fall inside
 // [t~ - delta, t~ + delta] are compacted into the band (key slot filled by pair_chain_kernel).
 // A block walks a contiguous part of the list and stages its band entries in shared memory, so
@@ -832,8 +912,16 @@ __global__ void __launch_bounds__(BF_THREADS)
 band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, const float *__restrict__ r,
                    float tlo, float thi, float c_half, float eps_abs, unsigned long long *__restrict__ below_out,
                    unsigned long long *__restrict__ bandw_out, unsigned long long *__restrict__ bandlen_out,
-                   uint2 *__restrict__ band_ij, unsigned long long band_cap, int *__restrict__ overflow) {
+                   uint2 *__restrict__ band_ij, unsigned long long band_cap, int *__restrict__ overflow,
+                   const unsigned long long *__restrict__ m_dev = nullptr, const uint32_t *__restrict__ bp = nullptr) {
     __shared__ uint2 stage[BF_STAGE];
+    if (m_dev) m = min(m, *m_dev);            // list length / thresholds that only exist on the device
+    if (bp) {
+        if (bp[BP_STATUS] != 0u) return;
+        tlo = __uint_as_float(bp[BP_TLO]);
+        thi = __uint_as_float(bp[BP_THI]);
+        eps_abs = __uint_as_float(bp[BP_EPS_ABS]);
+    }
     __shared__ unsigned int s_count;
     __shared__ unsigned long long s_base;
     if (threadIdx.x == 0) s_count = 0u;
@@ -941,7 +1029,9 @@ constexpr int CNT_BELOW2 = CNT_G1_END + 1, CNT_BANDW = CNT_G1_END + 2, CNT_OVERF
 constexpr int CNT_BAND_LEN = CNT_G1_END + 4, CNT_RMAX = CNT_G1_END + 5, CNT_HPARAMS = CNT_G1_END + 6;
 constexpr int CNT_SCALE = CNT_G1_END + 7;      // 3 floats: s, s^2, 1/s^2
 constexpr int CNT_WINDOW = CNT_G1_END + 9;     // device-picked pilot window: 2 floats, 2 keys, status word
-constexpr int CNT_TOTAL = CNT_G1_END + 12;
+constexpr int CNT_BANDP = CNT_G1_END + 12;     // device-picked band parameters (BP_* words below)
+constexpr int CNT_TOTAL = CNT_G1_END + 18;
+
 
 static MedianArena g_arena;   // one per process (one GPU per process)
 
@@ -1133,6 +1223,87 @@ bool median_tc_supported(int64_t n, int64_t ld) {
 // returns STEIN_OK with keys filled, 1 = "not bracketed, use the FFMA route", <0 = error
 bool median_tc_has_hint(const stein_ctx *ctx) { return hint_usable(ctx); }
 
+// Steady-state tail of the tensor-core route (spec != NULL in median_tc): everything after the
+// sweep is chained on the device -- band thresholds (pick_band_kernel), band filter, exact
+// distances, histogram of the exact keys over a device-picked window -- and the host reads the
+// counters and that histogram in ONE round trip.  Same formulas as the host-driven path below.
+// Returns like median_tc.
+static int median_tc_device_tail(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t d, int64_t ld,
+                                 const uint64_t ranks[2], float c_half, SweepParams *p, uint32_t keys_out[2]) {
+    (void)d;
+    MedianArena &A = g_arena;
+    const int world = ctx->has_comm ? ctx->comm.world : 1;
+    uint32_t *bp = reinterpret_cast<uint32_t *>(A.counters + CNT_BANDP);
+    int *d_overflow2 = reinterpret_cast<int *>(A.counters + CNT_OVERFLOW2);
+    pick_band_kernel<<<1, 1024, 0, ctx->stream>>>(A.counters, CNT_BELOW, CNT_LISTED, CNT_OVERFLOW, CNT_HIST, CNT_RMAX,
+                                                 CNT_HPARAMS, ranks[0], ranks[1], c_half, EPS_ABS,
+                                                 (uint32_t)HIST_MAX_BINS, bp);
+    STEIN_CHECK_LAUNCH(ctx);
+    band_filter_kernel<<<16 * ctx->num_sms, BF_THREADS, 0, ctx->stream>>>(
+        A.list, A.list_cap, r, 0.f, 0.f, c_half, 0.f, A.counters + CNT_BELOW2, A.counters + CNT_BANDW,
+        A.counters + CNT_BAND_LEN, A.band, A.band_cap, d_overflow2, A.counters + CNT_LIST_LEN, bp);
+    STEIN_CHECK_LAUNCH(ctx);
+    if (world > 1 && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.counters + CNT_BELOW2, 3) != 0)
+        return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+    STEIN_TRY(launch_pair_chain<0>(ctx, A.band, A.band_cap, X, r, n, ld, 0, A.counters + CNT_BAND_LEN));
+    static bool attr_set = false;
+    if (!attr_set) {
+        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(window_hist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (HIST_MAX_BINS + 1) * 4));
+        attr_set = true;
+    }
+    STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(A.bins, 0, (HIST_MAX_BINS + 1) * 8, ctx->stream));
+    window_hist_kernel<1><<<4 * ctx->num_sms, 256, (HIST_MAX_BINS + 1) * 4, ctx->stream>>>(
+        A.band, A.band_cap, A.counters + CNT_BAND_LEN, 0u, 0u, (uint32_t)HIST_MAX_BINS, A.bins, bp);
+    STEIN_CHECK_LAUNCH(ctx);
+    if (world > 1 && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.bins, HIST_MAX_BINS + 1) != 0)
+        return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+    unsigned long long *h = A.h_pinned + HIST_MAX_BINS + 2;
+    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.h_pinned, A.bins, (HIST_MAX_BINS + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h, A.counters, CNT_TOTAL * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+
+    const uint32_t *wv = reinterpret_cast<const uint32_t *>(h + CNT_WINDOW);
+    if (!wv[4]) {                // the pilot ranks were not inside the histogram around the old window
+        A.have_last = false;
+        return 2;
+    }
+    memcpy(&p->wlo, &wv[0], 4);
+    memcpy(&p->whi, &wv[1], 4);
+    A.last_center = (uint32_t)(((uint64_t)wv[2] + wv[3]) / 2);
+    const uint32_t *hbp = reinterpret_cast<const uint32_t *>(h + CNT_BANDP);
+    if (hbp[BP_STATUS] != 0u || h[CNT_OVERFLOW2] || h[CNT_BAND_LEN] > A.band_cap) return 1;
+    float tlo, thi;
+    memcpy(&tlo, &hbp[BP_TLO], 4);
+    memcpy(&thi, &hbp[BP_THI], 4);
+    const uint64_t c1 = h[CNT_BELOW] + h[CNT_BELOW2], band_w = h[CNT_BANDW];
+    if (!(c1 <= ranks[0] && ranks[1] < c1 + band_w)) return 1;
+    uint64_t rk[2] = {ranks[0] - c1, ranks[1] - c1};
+    uint32_t k01[2] = {0u, 0u};
+    bool done = true;
+    for (int q = 0; q < 2; ++q) {
+        uint32_t lo2, sh2, nb2;
+        const int rc = stein_median_narrow(reinterpret_cast<const uint64_t *>(A.h_pinned), hbp[BP_KLO], hbp[BP_SHIFT],
+                                           hbp[BP_NBINS], rk[q], &k01[q], &lo2, &sh2, &nb2);
+        if (rc < 0) return 1;
+        if (rc == 0) done = false;       // window wider than HIST_MAX_BINS keys: refine below
+    }
+    if (!done) {                 // rare: host-driven passes over the same band
+        const uint64_t khi = (uint64_t)hbp[BP_KLO] + ((uint64_t)hbp[BP_NBINS] << hbp[BP_SHIFT]) - 1;
+        const int rc = window_select2<1>(ctx, A.band, std::min<unsigned long long>(h[CNT_BAND_LEN], A.band_cap),
+                                         hbp[BP_KLO], (uint32_t)std::min<uint64_t>(khi, 0xffffffffull), rk, k01, true);
+        if (rc != STEIN_OK) return rc;
+    }
+    // the selected values must lie where the certainty argument holds
+    const float m0 = key_to_float(k01[0]), m1 = key_to_float(k01[1]);
+    if (!(m0 >= tlo && m1 <= thi && m0 >= p->wlo && m1 <= p->whi)) return 1;
+    keys_out[0] = k01[0];
+    keys_out[1] = k01[1];
+    return STEIN_OK;
+}
+
+
+
 // spec != NULL: the window is not given but derived ON THE DEVICE from one histogram pass over the
 // pilot keys around the previous window (no host round trip between pilot and sweep).  Returns 2
 // when the pilot ranks fell outside that histogram (the caller then takes the generic route).
@@ -1242,6 +1413,7 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     // all-reduce; the list itself (and its length) stays rank-local
     if (world > 1 && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.counters, CNT_G1_END) != 0)
         return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+    if (spec) return median_tc_device_tail(ctx, X, r, n, d, ld, ranks, c_half, &p, keys_out);
     unsigned long long *h = A.h_pinned + HIST_MAX_BINS + 2;
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h, A.counters, CNT_TOTAL * 8, cudaMemcpyDeviceToHost, ctx->stream));
     STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1249,16 +1421,6 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     const float rmax = *reinterpret_cast<float *>(h + CNT_RMAX);
     const float hlo = reinterpret_cast<float *>(h + CNT_HPARAMS)[0], hscale = reinterpret_cast<float *>(h + CNT_HPARAMS)[1];
     const uint64_t below = h[CNT_BELOW], listed = h[CNT_LISTED];
-    if (spec) {
-        const uint32_t *wv = reinterpret_cast<const uint32_t *>(h + CNT_WINDOW);
-        if (!wv[4]) {            // the pilot ranks were not inside the histogram around the old window
-            A.have_last = false;
-            return 2;
-        }
-        memcpy(&p.wlo, &wv[0], 4);
-        memcpy(&p.whi, &wv[1], 4);
-        A.last_center = (uint32_t)(((uint64_t)wv[2] + wv[3]) / 2);
-    }
     if (h[CNT_OVERFLOW]) return 1;
     if (!(below <= ranks[0] && ranks[1] < below + listed)) return 1;   // pilot window missed
 
