@@ -8,6 +8,8 @@
  * stub a maintainer of the reference would add.
  *
  * Conventions
+ *   - one process drives one GPU: the library keeps per-process scratch (median arena, slot plan,
+ *     window hint), so contexts of different devices must live in different processes;
  *   - every function returns 0 (STEIN_OK) or a negative STEIN_ERR_* code;
  *     stein_last_error() returns the text of the last failure on that context;
  *   - pointers named *_dev are DEVICE pointers, *_host are HOST pointers;
@@ -40,7 +42,9 @@ extern "C" {
 
 #define STEIN_ABI_VERSION 1
 
-/* phi-kernel implementations (stein_ctx_set_phi_impl) */
+/* phi-kernel implementations (stein_ctx_set_phi_impl).  AUTO: leading dimension 256 -> FLASH_TC4,
+ * 128 -> FLASH_TC, anything else -> DENSE_SIMT (the engine pads the rows of >= 2048 particles of up
+ * to 256 coordinates to 128 / 256 floats). */
 #define STEIN_PHI_AUTO 0
 #define STEIN_PHI_DENSE_SIMT 1 /* materialises K for the local row block; FP32 FFMA */
 #define STEIN_PHI_FLASH_TC 2   /* tcgen05/TMEM/TMA fused kernel; never stores K   */
@@ -48,7 +52,8 @@ extern "C" {
 #define STEIN_PHI_FLASH_TC3 4  /* CTA pairs, GEMM2 as one FP16 pass + two FP8 passes instead of 3 BF16 */
 #define STEIN_PHI_FLASH_TC4 5  /* CTA pairs, both GEMMs as FP16 + 2 x FP8 */
 
-/* median implementations (stein_ctx_set_median_impl) */
+/* median implementations (stein_ctx_set_median_impl).  AUTO: n <= 2048 -> all n*n keys once and a
+ * device-side select; leading dimension 128 / 256 and n*n >= 2^24 -> TC; otherwise FFMA. */
 #define STEIN_MEDIAN_AUTO 0
 #define STEIN_MEDIAN_FFMA 1 /* every sweep in contract arithmetic on the FP32 pipe          */
 #define STEIN_MEDIAN_TC 2   /* tcgen05 filter sweep + contract recomputation of candidates  */
@@ -249,7 +254,10 @@ int stein_engine_local_rows(const stein_engine *eng, int64_t *row_begin, int64_t
 /* device views (padded layout) for callers that fill scores on the device     */
 int stein_engine_buffers(stein_engine *eng, float **X_local_dev, float **S_local_dev,
                          float **phi_local_dev, int64_t *ld, int64_t *rows_padded_local);
-/* host <-> device: plain row-major n_local x d arrays (float32 or float64)    */
+/* host <-> device: plain row-major n_local x d arrays (float32 or float64).  On a sharded engine
+ * set_particles is COLLECTIVE (every rank replaces its rows): it also tells the engine that the
+ * other ranks' copies of these rows are stale, so the next step all-gathers instead of relying on
+ * the peer push.                                                                                   */
 int stein_engine_set_particles(stein_engine *eng, const void *X_host, int is_f64);
 int stein_engine_get_particles(stein_engine *eng, void *X_host, int is_f64);
 int stein_engine_set_scores(stein_engine *eng, const void *S_host, int is_f64);

@@ -6,27 +6,33 @@
 // phi_dense.cu:   O_i = sum_j K_ij y_j,  y_j = s_j - x_j/h^2,  ksum_i = sum_j K_ij,
 //                 phi_i = (O_i + x_i ksum_i / h^2) / n.
 //
-// One CTA owns a 128-row particle tile I (A operand, resident in shared memory)
-// and streams column tiles J of 128 particles:
-//   GEMM1  S   = X_I X_J^T                (tcgen05.mma kind::f16 on a 2-term BF16 split of X:
-//                                          hi.hi + lo.hi + hi.lo, ~2^-17 relative; D in TMEM)
-//   exp    P   = exp2(S c1 + a_i + b_j)   (4 warps: tcgen05.ld -> FFMA/MUFU -> tcgen05.st, in place)
-//   GEMM2  O  += P Y_J                    (tcgen05.mma kind::tf32, A = P from TMEM, D = O in TMEM)
+// All of it on centred particles x - mean(x) (see "centring" below): K, ksum and
+// sum_j K_ij (x_i - x_j) are translation invariant, the Gram form of D is not well conditioned.
+//
+// A CTA (flash_phi_kernel) or a pair of CTAs (flash_phi2_kernel, cta_group::2, M = 256) owns a
+// row tile I (A operand, resident in shared memory) and streams column tiles J of 128 particles:
+//   GEMM1  S   = X_I X_J^T                D in TMEM
+//   exp    P   = exp2(S c1 + a_i + b_j)   (epilogue warps: tcgen05.ld -> FFMA/MUFU -> tcgen05.st, in place)
+//   GEMM2  O  += P Y_J                    A = P from TMEM (.ts), D = O in TMEM
 // TMEM columns: [0, DP) = O accumulator, [256,384) and [384,512) = two S/P buffers, so
 // GEMM1 of tile j+1 overlaps the exponentials of tile j (FlashAttention-4 style pipeline).
-// Why the split: with plain TF32 inputs the error of S has a part that is constant along
-// a row of K (x_i . (x_i - tf32(x_i))), which does not average out in the sums over j and
-// cost 2.6e-4 relative on phi; the 3-pass BF16 form costs 1.5x the TF32 GEMM1 and is exact
-// to ~1e-6.  P and Y are TF32 (round-to-nearest); their errors are independent per term.
-// Operands arrive through a 6-stage ring of 16 KB TMA boxes (128 rows x 128 B,
-// SWIZZLE_128B, K-major).  Work is split stream-K style: the nI*nJ tile pairs are
-// cut into gridDim.x equal contiguous ranges, partial O / ksum of a range go to a
-// per-(I tile) slot and are summed in fixed order by finalize_phi_kernel.
+// Arithmetic of the GEMMs -- every product of two fp32-accurate operands u, v is split:
+//   BF16 modes   u.v ~ hi.hi + lo.hi + hi.lo   (2-term BF16 split, three kind::f16 passes, ~2^-17).
+//                Plain TF32 inputs left an error of S that is constant along a row of K
+//                (x_i . (x_i - tf32(x_i))), does not average out over j and cost 2.6e-4 on phi.
+//   mixed modes  u.v ~ u16.v16 + (u - u16).v16 + u16.(v - v16)  with u16 = fp16(u): one kind::f16
+//                pass and two kind::f8f6f4 passes at twice the rate (the cross terms are 2^-12
+//                relative and only need FP8's 3-4 bits).  Default of the pair kernel.
+// Operands arrive through a 6-stage ring of 16 KB TMA boxes (128 B rows, SWIZZLE_128B, K-major).
+// Work is scheduled by TileSchedule (round-synchronous sweeps of the column tiles, leftover row
+// tiles cut into equal column chunks); partial O / ksum of a row tile go to slots that
+// finalize_slots_kernel sums in fixed order.
 //
 // Warp roles (384 threads): warpgroup 0 = control (warp 0 TMA producer, warp 1 MMA issuer,
 // warps 2-3 idle; registers released with setmaxnreg), warpgroups 1-2 = exponential /
 // epilogue (warp w owns TMEM lanes 32*(w%4)..; warpgroup g owns half of the S and O columns
-// and keeps the fp32 running sum of its O half in registers).
+// and keeps the fp32 running sum of its O half in registers).  Producer and issuer loops run in
+// warp-uniform control flow with one elected lane per instruction (tc_common.cuh elect_one_sync).
 #include <algorithm>
 #include <vector>
 
