@@ -51,7 +51,7 @@ constexpr size_t SW_TAIL_BYTES = SW_TAIL_HIST + (size_t)SW_HIST_BINS * 4 + 64;
 constexpr int BP_TLO = 0, BP_THI = 1, BP_DELTA = 2, BP_EPS_ABS = 3, BP_KLO = 4, BP_SHIFT = 5, BP_NBINS = 6,
               BP_STATUS = 7;   // 0 = usable
 constexpr uint32_t SW_TMEM_COLS = 512;
-constexpr uint32_t SW_TMEM_AH = 256, SW_TMEM_AL = 384;   // A operand (row tile, BF16 hi / lo) in TMEM
+constexpr uint32_t SW_TMEM_AH = 256, SW_TMEM_AL = 384;   // A operand (row tile, FP16 hi / lo) in TMEM
 
 struct PairEntry {
     uint32_t i;
@@ -285,7 +285,7 @@ struct TileClassifier {
     }
 };
 
-// The row tile X_I (A operand) lives in TENSOR MEMORY (columns 256..511: BF16 hi and lo,
+// The row tile X_I (A operand) lives in TENSOR MEMORY (columns 256..511: FP16 hi and lo,
 // two elements per 32-bit column), written by the classification warps when I changes.
 // That leaves all of shared memory to a 12-stage ring of column-tile boxes, deep enough to
 // hide the L2 latency of the TMA loads; with A resident in shared memory (5 stages) the
@@ -472,7 +472,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
 // CTA-pair sweep (cta_group::2).  The single-CTA kernel above is bound by tensor-memory reads:
 // its A operand comes from TMEM (4 KB per 128x128x16 MMA at 64 B/cycle = the whole MMA time)
 // next to the 64 KB per tile the classification reads.  Here two CTAs of a cluster own 256
-// rows (row tiles 2 I2 and 2 I2 + 1), each keeps its 128-row A tile (BF16 hi and lo) in
+// rows (row tiles 2 I2 and 2 I2 + 1), each keeps its 128-row A tile (FP16 hi and lo) in
 // SHARED memory, the leader issues M = 256 MMAs whose B operand is split between the two
 // CTAs (each stages 64 of the 128 rows of X_J), and tensor memory is only read by the
 // classification.  Shared-memory traffic per SM and MMA: 4 KB of A + 2 KB of B.
@@ -480,7 +480,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
 // diagonal (row tile 2 I2 + 1 against column tile 2 I2) is computed but not classified.
 // =====================================================================================
 constexpr int SW2_STAGES = 4;
-constexpr int SW2_KB = 4;                       // K blocks of 64 BF16 staged for A (DP <= 256)
+constexpr int SW2_KB = 4;                       // K blocks of 64 FP16 staged for A (DP <= 256)
 constexpr uint32_t SW2_TMEM_COLS = 256;         // two 128-column g buffers
 
 struct Sweep2Barriers {

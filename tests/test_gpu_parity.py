@@ -240,7 +240,7 @@ FLASH_CASES = [(128, 256, 1.0), (130, 256, 1.0), (640, 256, 1.0), (1000, 128, 0.
 
 @pytest.mark.parametrize("n,d,scale", FLASH_CASES)
 def test_phi_flash_tcgen05_matches_oracle(ctx, n, d, scale):
-    """The tcgen05/TMEM/TMA fused kernel (TF32 tensor-core GEMMs, FP32 accumulate):
+    """The tcgen05/TMEM/TMA fused kernel (single-CTA variant: three BF16 passes per GEMM, FP32 accumulate):
     1e-4 relative to the oracle, and to the FFMA dense path on the same device."""
     from stein_b200 import _lib
     X = _particles(n, d, 3 * n + d, scale)
