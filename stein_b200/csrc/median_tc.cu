@@ -472,20 +472,24 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant
 // CTA-pair sweep (cta_group::2).  The single-CTA kernel above is bound by tensor-memory reads:
 // its A operand comes from TMEM (4 KB per 128x128x16 MMA at 64 B/cycle = the whole MMA time)
 // next to the 64 KB per tile the classification reads.  Here two CTAs of a cluster own 256
-// rows (row tiles 2 I2 and 2 I2 + 1), each keeps its 128-row A tile (FP16 hi and lo) in
-// SHARED memory, the leader issues M = 256 MMAs whose B operand is split between the two
-// CTAs (each stages 64 of the 128 rows of X_J), and tensor memory is only read by the
-// classification.  Shared-memory traffic per SM and MMA: 4 KB of A + 2 KB of B.
+// rows (row tiles 2 I2 and 2 I2 + 1), the leader issues M = 256 MMAs whose B operand is split
+// between the two CTAs (each stages 64 of the 128 rows of X_J).  The hi half of a CTA's A tile
+// lives in SHARED memory (used by two of the three passes), the lo half in TENSOR memory (used
+// by one): per tile that is 288 KB of shared-memory traffic (75 % of the port) and 128 KB of
+// tensor-memory reads (67 %) -- with both halves in shared memory the port was the limit
+// (117 of 128 B/cycle), with both in tensor memory its read port.
 // Tiles: pair rows I2 = 0 .. ceil(T/2)-1, columns J = 2 I2 .. T-1; the half tile below the
 // diagonal (row tile 2 I2 + 1 against column tile 2 I2) is computed but not classified.
 // =====================================================================================
-constexpr int SW2_STAGES = 4;
+constexpr int SW2_STAGES = 8;
 constexpr int SW2_KB = 4;                       // K blocks of 64 FP16 staged for A (DP <= 256)
-constexpr uint32_t SW2_TMEM_COLS = 256;         // two 128-column g buffers
+constexpr uint32_t SW2_TMEM_COLS = 512;         // two 128-column g buffers + the lo half of the A tile
+constexpr uint32_t SW2_TMEM_AL = 256;           // A lo (FP16 pairs, 32 columns per K block of 64)
 
 struct Sweep2Barriers {
     uint64_t full[SW2_STAGES], empty[SW2_STAGES];
     uint64_t a_full, a_empty;
+    uint64_t al_full;                // leader: A lo written to tensor memory by both CTAs' classification warps
     uint64_t s_full[2], s_empty[2];
 };
 
@@ -517,8 +521,8 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
                  const SweepParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t *sA = smem;                                              // [hi | lo] x SW2_KB x 16 KB
-    uint8_t *sRing = sA + (size_t)2 * SW2_KB * SW_UNIT_BYTES;        // SW2_STAGES x [64 rows hi | 64 rows lo]
+    uint8_t *sA = smem;                                              // A hi: SW2_KB x 16 KB
+    uint8_t *sRing = sA + (size_t)SW2_KB * SW_UNIT_BYTES;            // SW2_STAGES x [64 rows hi | 64 rows lo]
     uint8_t *tail = sRing + (size_t)SW2_STAGES * SW_UNIT_BYTES;
     Sweep2Barriers *bars = reinterpret_cast<Sweep2Barriers *>(tail);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 256);
@@ -539,6 +543,7 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
         }
         mbar_init(&bars->a_full, 1);                 // leader
         mbar_init(&bars->a_empty, 1);                // multicast commit
+        mbar_init(&bars->al_full, 2 * 4 * SW2_EPI_WG);   // leader: one arrival per classification warp of both CTAs
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->s_full[b], 1);                        // multicast commit
             mbar_init(&bars->s_empty[b], 2 * 4 * SW2_EPI_WG);      // leader: both CTAs' classification warps
@@ -577,11 +582,9 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
                     if (aseg > 0) mbar_wait(&bars->a_empty, (uint32_t)((aseg - 1) & 1));
                     const int arow = (2 * I2 + (int)rank) * 128;
                     if (elect_one_sync()) {
-                        if (leader) mbar_expect_tx(&bars->a_full, 2u * 2u * (uint32_t)p.kblocks * SW_UNIT_BYTES);
-                        for (int kb = 0; kb < p.kblocks; ++kb) {
+                        if (leader) mbar_expect_tx(&bars->a_full, 2u * (uint32_t)p.kblocks * SW_UNIT_BYTES);
+                        for (int kb = 0; kb < p.kblocks; ++kb)
                             tma_load_2d_pair(sA + (size_t)kb * SW_UNIT_BYTES, &mapXh, a_full_addr, kb * 64, arow);
-                            tma_load_2d_pair(sA + (size_t)(SW2_KB + kb) * SW_UNIT_BYTES, &mapXl, a_full_addr, kb * 64, arow);
-                        }
                     }
                     __syncwarp();
                     ++aseg;
@@ -614,6 +617,7 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
                     if (prevI2 != -1 && elect_one_sync()) tcgen05_commit_pair(&bars->a_empty);   // old A tiles are free
                     __syncwarp();
                     mbar_wait(&bars->a_full, (uint32_t)(aseg & 1));
+                    mbar_wait(&bars->al_full, (uint32_t)(aseg & 1));
                     tcgen05_fence_after();
                     ++aseg;
                     prevI2 = I2;
@@ -626,7 +630,7 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
                 const uint32_t d_tmem = tmem + b * 128;
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     const uint64_t ah = make_kmajor_sw128_desc(smem_u32(sA + (size_t)kb * SW_UNIT_BYTES));
-                    const uint64_t al = make_kmajor_sw128_desc(smem_u32(sA + (size_t)(SW2_KB + kb) * SW_UNIT_BYTES));
+                    const uint32_t al = tmem + SW2_TMEM_AL + kb * 32;
                     mbar_wait(&bars->full[stage], phase);
                     tcgen05_fence_after();
                     const uint32_t slot_addr = smem_u32(sRing + (size_t)stage * SW_UNIT_BYTES);
@@ -636,7 +640,7 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ss(d_tmem, ah + 2 * k4, bh + 2 * k4, idesc, (kb | k4) != 0);   // hi.hi
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ss(d_tmem, al + 2 * k4, bh + 2 * k4, idesc, 1u);             // lo.hi
+                        for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ts(d_tmem, al + 8 * k4, bh + 2 * k4, idesc, 1u);             // lo.hi (A from TMEM)
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ss(d_tmem, ah + 2 * k4, bl + 2 * k4, idesc, 1u);             // hi.lo
                         tcgen05_commit_pair(&bars->empty[stage]);
@@ -653,12 +657,39 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
         TileClassifier<SW2_EPI_WG> tc(p, tail, warp, lane);
         const uint32_t s_empty_addr0 = mapa_shared(smem_u32(&bars->s_empty[0]), 0);
         const uint32_t s_empty_addr1 = mapa_shared(smem_u32(&bars->s_empty[1]), 0);
+        const uint32_t al_full_addr = mapa_shared(smem_u32(&bars->al_full), 0);
+        const int wpr = p.kblocks * 32;             // 32-bit words per row of Xl
         long long jj = 0;
-        int I2 = 0, J = 0;
+        int I2 = 0, J = 0, prevI2 = -1, aseg = 0;
         if (my0 < my1) pair_tile(my0, p.T, I2, J);
         for (long long t = my0; t < my1; ++t, ++jj) {
             const int I = 2 * I2 + (int)rank;
             const long long i = (long long)I * 128 + tc.row;
+            if (I2 != prevI2) {
+                // new pair row: this CTA's A lo tile goes to tensor memory; warp (lane quarter q,
+                // chunk c) writes K block c of its 32 rows (rows beyond the matrix are zero)
+                if (aseg > 0) {
+                    mbar_wait(&bars->a_empty, (uint32_t)((aseg - 1) & 1));
+                    tcgen05_fence_after();
+                }
+                if (tc.wg < p.kblocks) {
+                    const bool in = i < (long long)p.T * 128;
+                    const uint4 *src = reinterpret_cast<const uint4 *>(p.Xl + (size_t)(in ? i : 0) * wpr) + tc.wg * 8;
+                    uint32_t v[32];
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        const uint4 u = in ? __ldg(src + q4) : make_uint4(0u, 0u, 0u, 0u);
+                        v[4 * q4] = u.x; v[4 * q4 + 1] = u.y; v[4 * q4 + 2] = u.z; v[4 * q4 + 3] = u.w;
+                    }
+                    tmem_st32(tmem + tc.lane_addr + SW2_TMEM_AL + tc.wg * 32, v);
+                    tmem_wait_st();
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(al_full_addr);
+                ++aseg;
+                prevI2 = I2;
+            }
             const int b = (int)(jj & 1);
             const unsigned int w = J > I ? 2u : (J == I ? 1u : 0u);
             mbar_wait(&bars->s_full[b], (uint32_t)((jj >> 1) & 1));
@@ -1385,7 +1416,7 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     p.list_cap = A.list_cap;
     const size_t tail_bytes = SW_TAIL_BYTES;
     const size_t smem1 = 1024 + (size_t)SW_STAGES * SW_UNIT_BYTES + tail_bytes;
-    const size_t smem2 = 1024 + (size_t)(2 * SW2_KB + SW2_STAGES) * SW_UNIT_BYTES + tail_bytes;
+    const size_t smem2 = 1024 + (size_t)(SW2_KB + SW2_STAGES) * SW_UNIT_BYTES + tail_bytes;
     static bool attr_set = false;
     if (!attr_set) {
         STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(sweep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
