@@ -761,3 +761,28 @@ def test_trajectory_is_deterministic_and_stable(ctx):
     c, _, bws_c = _run_engine(n, d, steps, _lib.PHI_FLASH_TC2)
     assert np.abs(a - c).max() <= 1e-3 * np.abs(c).max()
     assert np.allclose(bws, bws_c, rtol=1e-4)
+
+
+def test_median_window_hint_miss_falls_back(ctx):
+    """Within an engine the pilot histogram and the sweep window of iteration t are taken around
+    the window of iteration t-1 without a host round trip.  When the particles jump (here: the same
+    cloud blown up 10x between two steps) the pilot ranks fall outside that histogram; the
+    iteration must notice, take the generic route and still return the exact median."""
+    from stein_b200.engine import SvgdEngine
+    n, d = 4096, 256
+    X = _particles(n, d, 21)
+    eng = SvgdEngine(n, d, "adam", learning_rate=1e-3)
+    sweeps = []
+    for scale in (1.0, 1.0, 10.0, 10.0, 0.05):
+        Xs = (X * scale).astype(np.float32)
+        eng.set_particles(Xs)
+        eng.set_scores(-Xs)
+        Xin = eng.get_particles(np.float32)
+        eng.step()
+        info = eng.last()
+        m_ref, _ = orc.median_chain(Xin, radix=True)
+        assert np.float32(info["median"]).tobytes() == m_ref.tobytes(), scale
+        sweeps.append(info["sweeps"])
+    eng.close()
+    # first step: no hint; second: hint hits; after each jump the speculative sweep is wasted once
+    assert sweeps[0] == 1 and sweeps[1] == 1 and sweeps[2] == 2 and sweeps[3] == 1 and sweeps[4] == 2, sweeps
