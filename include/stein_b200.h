@@ -278,7 +278,13 @@ int stein_engine_update_particles_host(stein_engine *eng, const void *S_host, vo
 #define STEIN_IPC_HANDLE_BYTES 64
 int stein_engine_ipc_handle(stein_engine *eng, void *handle_out);
 int stein_engine_set_peer_handles(stein_engine *eng, const void *handles /* world x 64 bytes */);
-/* diagnostics of the last step */
+/* Fixed-bandwidth squared-exponential kernel (the plugin point is
+ * stein/kernels/abstract_kernel.py:40, where the reference defines `bandwidth` by the median
+ * heuristic).  bandwidth > 0: every following step uses exactly this h and skips the median;
+ * 0 (the default): the median heuristic of the reference.  Collective state: sharded engines must
+ * be given the same value on every rank. */
+int stein_engine_set_bandwidth(stein_engine *eng, float bandwidth);
+/* diagnostics of the last step (median is NaN for a step with a fixed bandwidth) */
 int stein_engine_last(const stein_engine *eng, float *median, float *bandwidth,
                       double *phi_norm, int32_t *sweeps);
 /* optimizer state access (checkpoint-lite)               */

@@ -96,6 +96,7 @@ SIGNATURES = {
     "stein_engine_update_particles_host": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int]),
     "stein_engine_ipc_handle": (ctypes.c_int, [c_vp, c_vp]),
     "stein_engine_set_peer_handles": (ctypes.c_int, [c_vp, c_vp]),
+    "stein_engine_set_bandwidth": (ctypes.c_int, [c_vp, c_f32]),
     "stein_engine_last": (ctypes.c_int, [c_vp, ctypes.POINTER(c_f32), ctypes.POINTER(c_f32),
                                          ctypes.POINTER(c_f64), ctypes.POINTER(c_i32)]),
     "stein_engine_get_state": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_f64),

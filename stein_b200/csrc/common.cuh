@@ -31,6 +31,16 @@ struct stein_ctx {
     // set by an engine around its median call: identifies the sequence of calls whose medians move
     // slowly, so that the previous window may be used as a hint (NULL: independent call, no hint)
     const void *median_owner = nullptr;
+    // Work that does not depend on the bandwidth: the median calls this hook right before its
+    // host round trip, so the GPU has kernels queued while the host reads the counters.
+    int (*presync_fn)(void *) = nullptr;
+    void *presync_arg = nullptr;
+    // set by flash_tc2_prepare_x, consumed by the next phi call on the same problem (phi_tc.cu)
+    struct XPrep {
+        const void *X, *ws;
+        int64_t n_total, n_local, d;
+        int mode;
+    } xprep{nullptr, nullptr, 0, 0, 0, 0};
     int64_t launches = 0;
     std::string error;
     // pinned host staging + device scratch for the median loop

@@ -194,3 +194,16 @@ int stein_phi(stein_ctx *ctx, const float *X_all_dev, const float *S_all_dev, co
 }
 
 }  // extern "C"
+
+namespace stein {
+// Same dispatch as stein_phi; a no-op for the kernels that have nothing to hoist.
+int phi_prepare_x(stein_ctx *ctx, const float *X_all, int64_t n_total, int64_t d, int64_t ld, int64_t n_local,
+                  void *ws, int64_t ws_bytes) {
+    if ((ld == 128 || ld == 256) && d < ld) d = ld;
+    const int impl = pick_phi_impl(ctx, n_local, n_total, d);
+    if ((impl == STEIN_PHI_FLASH_TC2 || impl == STEIN_PHI_FLASH_TC3 || impl == STEIN_PHI_FLASH_TC4) &&
+        flash_tc2_supported(ctx, n_local, n_total, d))
+        return flash_tc2_prepare_x(ctx, X_all, n_total, d, ld, n_local, ws, ws_bytes, impl - STEIN_PHI_FLASH_TC2);
+    return STEIN_OK;
+}
+}  // namespace stein

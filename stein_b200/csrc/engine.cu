@@ -45,6 +45,7 @@ struct stein_engine {
     unsigned long long *barrier_word = nullptr;   // 1 u64 all-reduced as the cross-rank barrier after a push
     uintptr_t uid = 0;      // unique per engine ever created in the process (median window hint owner)
     float last_med = 0.f, last_bw = 0.f;
+    float fixed_bw = 0.f;   // > 0: use this bandwidth instead of the median heuristic
     int32_t last_sweeps = 0;
     float *X_local() const { return X_all + (int64_t)rank * q * ld; }
     float *S_local() const { return S_all + (int64_t)rank * q * ld; }
@@ -243,10 +244,19 @@ int stein_engine_get_phi(stein_engine *e, void *phi_host, int is_f64) {
     return download(e, e->phi, phi_host, is_f64);
 }
 
+// Called by the median right before its host round trip (stein_ctx::presync_fn): the part of the
+// phi preparation that needs neither the bandwidth nor the scores (centring, scale of X).
+static int engine_presync(void *arg) {
+    stein_engine *e = static_cast<stein_engine *>(arg);
+    return phi_prepare_x(e->ctx, e->X_all, e->n_total, e->d, e->ld, std::max<int64_t>(e->n_local, 1), e->ws,
+                         e->ws_bytes);
+}
+
 // Phase 1 needs only the particles: all-gather X, row norms, exact median, bandwidth.
 static int step_bandwidth(stein_engine *e, float *bw_out) {
     stein_ctx *ctx = e->ctx;
     const int64_t rows_all = e->q * e->world;
+    ctx->xprep.X = nullptr;
     if (e->world > 1) {
         if (e->peers_open && e->x_all_current) {
             // every rank pushed its updated rows into this buffer during its last optimizer
@@ -262,13 +272,24 @@ static int step_bandwidth(stein_engine *e, float *bw_out) {
     }
     // abstract_kernel.py:34 -- r = sum(T*T, 1), contract order
     STEIN_TRY(stein_row_norms(ctx, e->X_all, rows_all, e->d, e->ld, e->r_all));
+    if (e->fixed_bw > 0.0f) {
+        e->last_med = nanf("");
+        e->last_bw = e->fixed_bw;
+        e->last_sweeps = 0;
+        *bw_out = e->fixed_bw;
+        return STEIN_OK;
+    }
     // compute_median.py + abstract_kernel.py:40
     float med = 0.f;
     // successive medians of one engine move slowly: window hint allowed (owner = the engine's uid)
     ctx->median_owner = reinterpret_cast<const void *>(e->uid);
+    ctx->presync_fn = engine_presync;
+    ctx->presync_arg = e;
     const int mrc = stein_median_sqdist(ctx, e->X_all, e->r_all, e->n_total, e->d, e->ld, &med, nullptr,
                                         &e->last_sweeps);
     ctx->median_owner = nullptr;
+    ctx->presync_fn = nullptr;
+    ctx->presync_arg = nullptr;
     if (mrc != STEIN_OK) return mrc;
     const float bw = stein_bandwidth(med, e->n_total);
     e->last_med = med;
@@ -370,6 +391,14 @@ int stein_engine_update_particles_host(stein_engine *e, const void *S_host, void
     if (rc != STEIN_OK) return rc;
     STEIN_TRY(step_update(e, bw, gathered));
     if (X_host_out) return stein_engine_get_particles(e, X_host_out, is_f64);
+    return STEIN_OK;
+}
+
+int stein_engine_set_bandwidth(stein_engine *e, float bandwidth) {
+    if (!e) return STEIN_ERR_INVALID;
+    if (!(bandwidth >= 0.0f) || bandwidth > 3.0e38f)
+        return fail(e->ctx, STEIN_ERR_INVALID, "bandwidth must be finite and >= 0 (0 = median heuristic)");
+    e->fixed_bw = bandwidth;
     return STEIN_OK;
 }
 

@@ -302,6 +302,10 @@ struct PilotSpec {
     unsigned long long rank_lo, rank_hi;
 };
 bool median_tc_has_hint(const stein_ctx *ctx);
+int median_tc_begin(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t ld);
+void median_tc_reset(void);
+int median_tc_pilot(stein_ctx *ctx, uint32_t *keys_dev, unsigned long long m, const float *r, int64_t n, int64_t ld,
+                    uint64_t seed);
 int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t d, int64_t ld,
               const uint64_t ranks[2], uint32_t win_lo_key, uint32_t win_hi_key, uint32_t keys_out[2],
               int *sweeps, const PilotSpec *spec);
@@ -480,10 +484,19 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
         // of it and the window histograms are all-reduced
         const int pw = ctx->has_comm ? ctx->comm.world : 1, pr = ctx->has_comm ? ctx->comm.rank : 0;
         const int64_t s0 = pilot_m * pr / pw, s1 = pilot_m * (pr + 1) / pw;
-        STEIN_TRY(launch_pair_chain<1>(ctx, ctx->d_pilot_keys + s0, (unsigned long long)(s1 - s0), X_dev, r_dev, n, ld,
-                                       0x5eedull + (uint64_t)s0));
-        const uint64_t delta = (uint64_t)(3.5 * sqrt((double)pilot_m));
         const bool tc_ok = ctx->median_impl != STEIN_MEDIAN_FFMA && median_tc_supported(n, ld);
+        median_tc_reset();
+        if (tc_ok) {
+            // the tensor-core route splits s X into FP16 hi + lo anyway: the pilot only has to
+            // PLACE the window (every use of it is checked), so it reads the hi half alone
+            STEIN_TRY(median_tc_begin(ctx, X_dev, r_dev, n, ld));
+            STEIN_TRY(median_tc_pilot(ctx, ctx->d_pilot_keys + s0, (unsigned long long)(s1 - s0), r_dev, n, ld,
+                                      0x5eedull + (uint64_t)s0));
+        } else {
+            STEIN_TRY(launch_pair_chain<1>(ctx, ctx->d_pilot_keys + s0, (unsigned long long)(s1 - s0), X_dev, r_dev, n,
+                                           ld, 0x5eedull + (uint64_t)s0));
+        }
+        const uint64_t delta = (uint64_t)(3.5 * sqrt((double)pilot_m));
         // steady state: pilot histogram, window pick and sweep chained on the device
         if (tc_ok && median_tc_has_hint(ctx)) {
             const PilotSpec spec = {ctx->d_pilot_keys + s0, (unsigned long long)(s1 - s0), pilot_m / 2 - delta,
@@ -502,12 +515,14 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
                 kb = 0u;
             }
         }
-        if (kb >= ka) {
-            const uint64_t span = (uint64_t)kb - ka + 1;
+        auto window_of = [](uint32_t a, uint32_t b) {
+            const uint64_t span = (uint64_t)b - a + 1;
             uint32_t sh = 0;
             while (((span - 1) >> sh) >= (uint64_t)HIST_MAX_BINS) ++sh;
-            Window w = {ka, sh, (uint32_t)(((span - 1) >> sh) + 1)};
-            win[0] = win[1] = w;
+            return Window{a, sh, (uint32_t)(((span - 1) >> sh) + 1)};
+        };
+        if (kb >= ka) {
+            win[0] = win[1] = window_of(ka, kb);
             // tensor-core route: one tcgen05 sweep + exact recomputation of the few pairs
             // that can matter; falls through to the FFMA sweeps if it cannot bracket the rank
             if (tc_ok) {
@@ -515,6 +530,18 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
                 if (rc < 0) return rc;
                 if (rc == STEIN_OK) done[0] = done[1] = true;
             }
+        }
+        if (tc_ok && !(done[0] && done[1])) {
+            // The tensor-core route could not decide (particles far from the origin relative to
+            // their spread: the FP16 split is too coarse, and so was the FP16 pilot).  The FFMA
+            // sweeps below get a window from the exact pilot, as on the routes without tensor cores.
+            STEIN_TRY(launch_pair_chain<1>(ctx, ctx->d_pilot_keys + s0, (unsigned long long)(s1 - s0), X_dev, r_dev, n,
+                                           ld, 0x5eedull + (uint64_t)s0));
+            win[0] = win[1] = kFullWindow;
+            const int prc = pilot_window(ctx, ctx->d_pilot_keys + s0, s1 - s0, pilot_m / 2 - delta,
+                                         pilot_m / 2 + delta, &ka, &kb);
+            if (prc < 0) return prc;
+            if (prc == STEIN_OK && kb >= ka) win[0] = win[1] = window_of(ka, kb);
         }
     }
     if ((ctx->median_impl == STEIN_MEDIAN_TC || ctx->median_impl == STEIN_MEDIAN_TC1) && !(done[0] && done[1]))

@@ -760,6 +760,68 @@ max_kernel(const float *__restrict__ r, int64_t n, float *__restrict__ out, floa
     }
 }
 
+// Pilot sample from the FP16 hi array: APPROXIMATE distances (|error| ~ 2^-11 |x_i||x_j|, about
+// 1e-2 at config D against a window of 0.8) are all the pilot needs -- it only places the window,
+// and every consumer of the window checks that the target rank is bracketed.  Half the bytes of
+// the fp32 chain of pair_chain.cuh and no shared-memory staging: a row of ld halfs is one 16-byte
+// load per lane, the 32 per-lane partial sums of 32 pairs are reduced with a 31-shuffle butterfly.
+// Same sample as pair_chain_kernel<1>: pair e = splitmix64(seed + e).
+__global__ void __launch_bounds__(256)
+pilot_h16_kernel(uint32_t *__restrict__ keys, unsigned long long m, const uint4 *__restrict__ Xh,
+                 const float *__restrict__ r, const float *__restrict__ scale, int64_t n, int chunks, uint64_t seed) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long ngroups = (m + 31ull) / 32ull;
+    const float inv_s2 = __ldg(scale + 2);
+    const bool active = lane < chunks;
+    for (unsigned long long g = warp; g < ngroups; g += nwarps) {
+        const unsigned long long e = g * 32ull + lane;
+        const uint64_t h = splitmix64(seed + (uint64_t)e);
+        const uint32_t i = (uint32_t)((h >> 32) % (uint64_t)n), j = (uint32_t)((h & 0xffffffffull) % (uint64_t)n);
+        float v[32];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            uint4 A[8], B[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const uint32_t it = __shfl_sync(0xffffffffu, i, 8 * b + t), jt = __shfl_sync(0xffffffffu, j, 8 * b + t);
+                A[t] = B[t] = make_uint4(0u, 0u, 0u, 0u);
+                if (active) {
+                    A[t] = __ldg(Xh + (size_t)it * chunks + lane);
+                    B[t] = __ldg(Xh + (size_t)jt * chunks + lane);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const uint32_t a[4] = {A[t].x, A[t].y, A[t].z, A[t].w}, c[4] = {B[t].x, B[t].y, B[t].z, B[t].w};
+                float acc = 0.0f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&a[q]));
+                    const float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&c[q]));
+                    acc = fmaf(fa.x, fb.x, acc);
+                    acc = fmaf(fa.y, fb.y, acc);
+                }
+                v[8 * b + t] = acc;
+            }
+        }
+        // butterfly: after the step with stride s, a lane keeps the half of the pairs whose index
+        // bit s equals its own lane bit; at the end v[0] on lane L is the full sum of pair L
+#pragma unroll
+        for (int st = 16; st >= 1; st >>= 1) {
+            const bool up = (lane & st) != 0;
+#pragma unroll
+            for (int k = 0; k < st; ++k) {
+                const float send = up ? v[k] : v[k + st];
+                const float keep = up ? v[k + st] : v[k];
+                v[k] = keep + __shfl_xor_sync(0xffffffffu, send, st);
+            }
+        }
+        if (e < m) keys[e] = float_to_key((r[i] + r[j]) - 2.0f * v[0] * inv_s2);
+    }
+}
+
 // weighted histogram of the keys that fall into the window [key_lo, key_lo + (nbins << shift)):
 // bins[0] += weight of the keys below the window, bins[1 + b] += weight of bin b; keys above the
 // window are ignored.  SRC 1: uint2 (key, weight) band entries, SRC 2: plain u32 keys (weight 1).
@@ -1049,6 +1111,8 @@ struct MedianArena {
     uint32_t last_center = 0u;
     bool have_last = false;
     const void *hint_owner = nullptr;     // the engine (stein_ctx::median_owner) the hint belongs to
+    cudaEvent_t ev_tail = nullptr;        // marks the D2H copies of the device-driven tail
+    bool fresh = false;                   // median_tc_begin ran and no sweep has used its counters yet
 };
 
 // counters block (u64 slots).  Slots [0, CNT_G1_END) are global quantities after the sweep (one
@@ -1292,7 +1356,17 @@ static int median_tc_device_tail(stein_ctx *ctx, const float *X, const float *r,
     unsigned long long *h = A.h_pinned + HIST_MAX_BINS + 2;
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.h_pinned, A.bins, (HIST_MAX_BINS + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h, A.counters, CNT_TOTAL * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->presync_fn) {
+        // the caller has bandwidth-independent work for this stream: queue it behind the copies and
+        // wait for the copies only, so the GPU is busy during the host's part of the round trip
+        if (!A.ev_tail) STEIN_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&A.ev_tail, cudaEventDisableTiming));
+        STEIN_CHECK_CUDA(ctx, cudaEventRecord(A.ev_tail, ctx->stream));
+        const int hrc = ctx->presync_fn(ctx->presync_arg);
+        STEIN_CHECK_CUDA(ctx, cudaEventSynchronize(A.ev_tail));
+        if (hrc != STEIN_OK) return hrc < 0 ? hrc : STEIN_ERR_INVALID;
+    } else {
+        STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
 
     const uint32_t *wv = reinterpret_cast<const uint32_t *>(h + CNT_WINDOW);
     if (!wv[4]) {                // the pilot ranks were not inside the histogram around the old window
@@ -1335,6 +1409,40 @@ static int median_tc_device_tail(stein_ctx *ctx, const float *X, const float *r,
 
 
 
+// First stage of the route: zero the counters, largest row norm and scale, FP16 split of s X.
+int median_tc_begin(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t ld) {
+    const int64_t rows = stein_rows_padded(n), T = (n + TILE - 1) / TILE;
+    const uint64_t pairs = (uint64_t)T * (T + 1) / 2 * TILE * TILE;
+    STEIN_TRY(ensure_arena(ctx, rows, ld, pairs));
+    MedianArena &A = g_arena;
+    A.fresh = false;
+    STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(A.counters, 0, CNT_TOTAL * 8, ctx->stream));
+    float *d_scale = reinterpret_cast<float *>(A.counters + CNT_SCALE);
+    max_kernel<<<1, 1024, 0, ctx->stream>>>(r, n, reinterpret_cast<float *>(A.counters + CNT_RMAX), d_scale);
+    STEIN_CHECK_LAUNCH(ctx);
+    const int64_t count4 = rows * ld / 4;
+    split_f16_kernel<<<(unsigned)((count4 + 255) / 256), 256, 0, ctx->stream>>>(X, count4, d_scale, A.Xh, A.Xl);
+    STEIN_CHECK_LAUNCH(ctx);
+    A.fresh = true;
+    return STEIN_OK;
+}
+void median_tc_reset(void) { g_arena.fresh = false; }
+
+// Pilot keys of samples [s0, s0 + m) from the FP16 hi array (needs median_tc_begin on this X).
+int median_tc_pilot(stein_ctx *ctx, uint32_t *keys_dev, unsigned long long m, const float *r, int64_t n, int64_t ld,
+                    uint64_t seed) {
+    MedianArena &A = g_arena;
+    if (!A.fresh) return fail(ctx, STEIN_ERR_INTERNAL, "median_tc_pilot without median_tc_begin");
+    if (m == 0) return STEIN_OK;
+    const unsigned long long ngroups = (m + 31ull) / 32ull;
+    const unsigned grid = (unsigned)std::min<unsigned long long>((ngroups + 7) / 8, 8ull * ctx->num_sms);
+    pilot_h16_kernel<<<grid, 256, 0, ctx->stream>>>(keys_dev, m, reinterpret_cast<const uint4 *>(A.Xh), r,
+                                                   reinterpret_cast<const float *>(A.counters + CNT_SCALE), n,
+                                                   (int)(ld / 8), seed);
+    STEIN_CHECK_LAUNCH(ctx);
+    return STEIN_OK;
+}
+
 // spec != NULL: the window is not given but derived ON THE DEVICE from one histogram pass over the
 // pilot keys around the previous window (no host round trip between pilot and sweep).  Returns 2
 // when the pilot ranks fell outside that histogram (the caller then takes the generic route).
@@ -1353,16 +1461,14 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     const int64_t t0 = ntiles * rank / world, t1 = ntiles * (rank + 1) / world;
     const float c_half = eps_coeff(d);
 
-    STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(A.counters, 0, CNT_TOTAL * 8, ctx->stream));
+    // counters zeroed, largest row norm, scale, FP16 split: already there when the caller ran
+    // median_tc_begin for its pilot and this is the first sweep since
+    if (!A.fresh) STEIN_TRY(median_tc_begin(ctx, X, r, n, ld));
+    A.fresh = false;
     float *d_rmax = reinterpret_cast<float *>(A.counters + CNT_RMAX);
     float *d_scale = reinterpret_cast<float *>(A.counters + CNT_SCALE);
     int *d_overflow = reinterpret_cast<int *>(A.counters + CNT_OVERFLOW);
     int *d_overflow2 = reinterpret_cast<int *>(A.counters + CNT_OVERFLOW2);
-    max_kernel<<<1, 1024, 0, ctx->stream>>>(r, n, d_rmax, d_scale);
-    STEIN_CHECK_LAUNCH(ctx);
-    const int64_t count4 = rows * DP / 4;
-    split_f16_kernel<<<(unsigned)((count4 + 255) / 256), 256, 0, ctx->stream>>>(X, count4, d_scale, A.Xh, A.Xl);
-    STEIN_CHECK_LAUNCH(ctx);
 
     if (spec) {
         // one histogram pass over +-2^20 keys around the last window, then the device picks the bins

@@ -32,5 +32,11 @@ bool flash_tc2_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total,
 int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all,
                   int64_t n_total, int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2,
                   void *ws, int64_t ws_bytes, float *phi, double *sumsq, int mode);
+// the bandwidth-independent kernels of phi_flash_tc2, enqueued ahead of the call (ctx->xprep)
+int flash_tc2_prepare_x(stein_ctx *ctx, const float *X_all, int64_t n_total, int64_t d, int64_t ld,
+                        int64_t n_local, void *ws, int64_t ws_bytes, int mode);
+// what stein_phi would run for this problem: prepares its X side if that kernel supports it (ctx.cu)
+int phi_prepare_x(stein_ctx *ctx, const float *X_all, int64_t n_total, int64_t d, int64_t ld, int64_t n_local,
+                  void *ws, int64_t ws_bytes);
 
 }  // namespace stein

@@ -1216,6 +1216,16 @@ bool flash_tc_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total, 
     return (DP == 128 || DP == 256) && n_total >= 2;
 }
 
+// True (once) when flash_tc2_prepare_x already ran for exactly this problem.
+static bool xprep_consume(stein_ctx *ctx, const float *X_all, const void *ws, int64_t n_total, int64_t n_local,
+                          int64_t d, int mode) {
+    const stein_ctx::XPrep &x = ctx->xprep;
+    const bool hit = x.X != nullptr && x.X == X_all && x.ws == ws && x.n_total == n_total && x.n_local == n_local &&
+                     x.d == d && x.mode == mode;
+    ctx->xprep.X = nullptr;
+    return hit;
+}
+
 // Centred copy of the particles and its row norms, carved from the workspace.
 struct Centred {
     float *Xc, *rc;
@@ -1225,8 +1235,9 @@ struct Centred {
 static int64_t centred_bytes(int64_t cols, int64_t DP) {
     return cols * DP * 4 + cols * 4 + (int64_t)CM_BLOCKS * DP * 8 + DP * 4 + (cols / 8 + 1) * 4 + 64;
 }
+// launch = false: only carve the buffers (the kernels already ran for this X, see flash_prepare_x)
 static int make_centred(stein_ctx *ctx, const float *X_all, int64_t n_total, int64_t d, int64_t cols, int64_t ld,
-                        char *&pws, Centred *out) {
+                        char *&pws, Centred *out, bool launch = true) {
     pws = (char *)(((uintptr_t)pws + 15) & ~(uintptr_t)15);
     float *Xc = (float *)pws;        pws += cols * ld * 4;
     float *rc = (float *)pws;        pws += cols * 4;
@@ -1235,12 +1246,14 @@ static int make_centred(stein_ctx *ctx, const float *X_all, int64_t n_total, int
     float *mean = (float *)pws;      pws += ld * 4;
     const int64_t nblk = (cols * 32 + 255) / 256;
     float *blockmax = (float *)pws;  pws += nblk * 4;
-    colsum_partial_kernel<<<CM_BLOCKS, 256, 0, ctx->stream>>>(X_all, n_total, ld, part);
-    STEIN_CHECK_LAUNCH(ctx);
-    colmean_kernel<<<(unsigned)((ld * 32 + 255) / 256), 256, 0, ctx->stream>>>(part, n_total, ld, mean);
-    STEIN_CHECK_LAUNCH(ctx);
-    center_kernel<<<(unsigned)nblk, 256, 0, ctx->stream>>>(X_all, mean, n_total, cols, d, ld, Xc, rc, blockmax);
-    STEIN_CHECK_LAUNCH(ctx);
+    if (launch) {
+        colsum_partial_kernel<<<CM_BLOCKS, 256, 0, ctx->stream>>>(X_all, n_total, ld, part);
+        STEIN_CHECK_LAUNCH(ctx);
+        colmean_kernel<<<(unsigned)((ld * 32 + 255) / 256), 256, 0, ctx->stream>>>(part, n_total, ld, mean);
+        STEIN_CHECK_LAUNCH(ctx);
+        center_kernel<<<(unsigned)nblk, 256, 0, ctx->stream>>>(X_all, mean, n_total, cols, d, ld, Xc, rc, blockmax);
+        STEIN_CHECK_LAUNCH(ctx);
+    }
     out->Xc = Xc;
     out->rc = rc;
     out->blockmax = blockmax;
@@ -1420,7 +1433,8 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     int *tile_nslots = nullptr;
     // the debug hook compares the raw GEMM1 tiles with X X^T: no centring there
     Centred cen{const_cast<float *>(X_all), const_cast<float *>(r_all), nullptr, 0};
-    if (!g_debug_dumpS) STEIN_TRY(make_centred(ctx, X_all, n_total, d, pl.cols, ld, pws, &cen));
+    const bool prepared = xprep_consume(ctx, X_all, ws, n_total, n_local, d, -1);
+    if (!g_debug_dumpS) STEIN_TRY(make_centred(ctx, X_all, n_total, d, pl.cols, ld, pws, &cen, !prepared));
     const float *Xc = cen.Xc, *rc = cen.rc;
 
     const float l2e = 1.4426950408889634f;
@@ -1483,9 +1497,11 @@ bool flash_tc2_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total,
     return stein_ld(d) == FL_MAX_DP && n_total >= 2 && ctx->num_sms >= 2;
 }
 
-int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all, int64_t n_total,
-                  int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
-                  int64_t ws_bytes, float *phi, double *sumsq, int mode) {
+// only_prepare: enqueue the kernels that do not depend on the bandwidth (nor on S) and remember
+// that in ctx->xprep; the next full call on the same (X, workspace, shape, mode) skips them.
+static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all, int64_t n_total,
+                         int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
+                         int64_t ws_bytes, float *phi, double *sumsq, int mode, bool only_prepare) {
     // mode 0: BF16x3 for both GEMMs; 1: mixed-precision GEMM2; 2: mixed precision for both
     const bool g2f8 = mode >= 1, g1f8 = mode >= 2;
     const FlashPlan pl = flash_plan(ctx, n_local, n_total, d, true);
@@ -1507,8 +1523,11 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
     double *partials = (double *)(((uintptr_t)pws + 7) & ~(uintptr_t)7);
     pws = (char *)partials + FINALIZE_MAX_BLOCKS * 8;
     int *d_tile_nslots = nullptr;
+    // the bandwidth-independent part (centring, global scale of X) may already have been enqueued
+    // by flash_prepare_x while the host waited for the median
+    const bool prepared = !only_prepare && xprep_consume(ctx, X_all, ws, n_total, n_local, d, mode);
     Centred cen{};
-    STEIN_TRY(make_centred(ctx, X_all, n_total, d, cols, ld, pws, &cen));
+    STEIN_TRY(make_centred(ctx, X_all, n_total, d, cols, ld, pws, &cen, !prepared));
     const float *Xc = cen.Xc, *rc = cen.rc;
     pws = (char *)(((uintptr_t)pws + 15) & ~(uintptr_t)15);
     float *cmax_part = (float *)pws;     pws += (int64_t)CM_BLOCKS * DP * 4;
@@ -1517,14 +1536,20 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
     float *xscale = (float *)pws;        pws += 16;       // [0] = 2^-e on X, [1] = 2^(2e) on c1
     uint8_t *B8h = (uint8_t *)pws;       pws += cols * DP;
     uint8_t *B8l = (uint8_t *)pws;       pws += cols * DP;
+    if (g1f8 && !prepared) {
+        xscale_kernel<<<1, 1024, 0, ctx->stream>>>(cen.blockmax, cen.nblockmax, xscale);
+        STEIN_CHECK_LAUNCH(ctx);
+    }
+    if (only_prepare) {
+        ctx->xprep = {X_all, ws, n_total, n_local, d, mode};
+        return STEIN_OK;
+    }
 
     const float l2e = 1.4426950408889634f;
     {
         const int64_t tot = std::max<int64_t>(cols * DP / 4, cols + 256);
         if (g1f8) {
             // FP16 array in the place of Xh; a8l, a8h share the place of Xl; b8h, b8l have their own
-            xscale_kernel<<<1, 1024, 0, ctx->stream>>>(cen.blockmax, cen.nblockmax, xscale);
-            STEIN_CHECK_LAUNCH(ctx);
             prep_x8_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(
                 Xc, rc, cols, n_total, ld, 0.5f * l2e / h2, xscale, (__half *)Xh, (uint8_t *)Xl, (uint8_t *)Xl + cols * DP,
                 B8h, B8l, nrm, cols + 256);
@@ -1611,6 +1636,19 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
     reduce_partials2_kernel<<<1, 256, 0, ctx->stream>>>(partials, blocks, sumsq);
     STEIN_CHECK_LAUNCH(ctx);
     return STEIN_OK;
+}
+
+int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all, int64_t n_total,
+                  int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
+                  int64_t ws_bytes, float *phi, double *sumsq, int mode) {
+    return flash_tc2_run(ctx, X_all, S_all, r_all, n_total, d, ld, row_begin, n_local, h2, ws, ws_bytes, phi, sumsq,
+                         mode, false);
+}
+
+int flash_tc2_prepare_x(stein_ctx *ctx, const float *X_all, int64_t n_total, int64_t d, int64_t ld,
+                        int64_t n_local, void *ws, int64_t ws_bytes, int mode) {
+    return flash_tc2_run(ctx, X_all, nullptr, nullptr, n_total, d, ld, 0, n_local, 1.0f, ws, ws_bytes, nullptr,
+                         nullptr, mode, true);
 }
 
 }  // namespace stein

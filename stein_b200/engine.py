@@ -124,6 +124,11 @@ class SvgdEngine:
             X_out.ctypes.data_as(ctypes.c_void_p) if X_out is not None else None, f64))
         return X_out
 
+    def set_bandwidth(self, bandwidth=None):
+        """Fixed bandwidth h for the following steps; None / 0 = the reference's
+        median heuristic (abstract_kernel.py:40)."""
+        self.ctx.check(self.lib.stein_engine_set_bandwidth(self.handle, float(bandwidth or 0.0)))
+
     def last(self):
         med, bw, nrm, sw = ctypes.c_float(), ctypes.c_float(), ctypes.c_double(), ctypes.c_int32()
         self.ctx.check(self.lib.stein_engine_last(self.handle, ctypes.byref(med), ctypes.byref(bw),

@@ -20,10 +20,15 @@ class AbstractKernel:
     tf.Session); it is unused -- the CUDA context plays that role.
     """
 
-    def __init__(self, n_particles, sess=None):
+    def __init__(self, n_particles, sess=None, bandwidth=None):
+        """`bandwidth` (not in the reference): a fixed h > 0 instead of the median
+        heuristic; the samplers then skip the median (stein_engine_set_bandwidth)."""
         self.n_particles = n_particles
         self.sess = sess
-        self.bandwidth = None       # fp32, set by kernel_and_grad / compute_bandwidth
+        if bandwidth is not None and not (float(bandwidth) > 0.0 and np.isfinite(bandwidth)):
+            raise ValueError("bandwidth must be positive and finite")
+        self.fixed_bandwidth = None if bandwidth is None else np.float32(bandwidth)
+        self.bandwidth = self.fixed_bandwidth   # fp32, set by kernel_and_grad / compute_bandwidth
         self.median = None
 
     def _device_particles(self, theta):
@@ -45,6 +50,9 @@ class AbstractKernel:
         return self._bandwidth_dev(ctx, X, r, n, d)
 
     def _bandwidth_dev(self, ctx, X, r, n, d):
+        if self.fixed_bandwidth is not None:
+            self.bandwidth = self.fixed_bandwidth
+            return self.bandwidth
         med = ctypes.c_float()
         ctx.check(ctx.lib.stein_median_sqdist(ctx.handle, ptr(X), ptr(r), n, d, X.shape[1],
                                               ctypes.byref(med), None, None))

@@ -108,6 +108,7 @@ class AbstractSteinSampler:
         e = self._engine
         grads_array = np.ascontiguousarray(grads_array)
         if isinstance(self.gd, FusedGradientDescent):
+            self._sync_kernel_bandwidth()
             e.update_particles_host(grads_array)
             self.gd._after_engine_step()
         else:
@@ -118,6 +119,14 @@ class AbstractSteinSampler:
             phi *= 10. / max(10., np.linalg.norm(phi))
             e.set_particles(e.get_particles(np.float64) + self.gd.update(phi))
         self._theta_cache = None
+
+    def _sync_kernel_bandwidth(self):
+        """The engine follows `self.kernel`: a kernel built with `bandwidth=h` makes it
+        skip the median (the kernel object may be replaced after construction)."""
+        want = getattr(self.kernel, "fixed_bandwidth", None)
+        if want != getattr(self, "_engine_bandwidth", None):
+            self._engine.set_bandwidth(want)
+            self._engine_bandwidth = want
 
     def _device_phi_only(self):
         """phi for the scores in the engine, without the optimizer step."""

@@ -25,6 +25,7 @@ class SteinSampler(AbstractSteinSampler):
         e.ctx.sync_stream()
         self.log_p.scores(e, batch_feed)                 # S stays on the device
         if isinstance(self.gd, FusedGradientDescent):
+            self._sync_kernel_bandwidth()
             e.step()
             self.gd._after_engine_step()
         else:

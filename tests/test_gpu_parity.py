@@ -517,6 +517,40 @@ def test_engine_steps_match_oracle(ctx, opt, n, d):
     eng.close()
 
 
+@pytest.mark.parametrize("n,d", [(300, 20), (2500, 256)])
+def test_engine_fixed_bandwidth(ctx, n, d):
+    """stein_engine_set_bandwidth: the step uses exactly the given h (no median), phi and the
+    particles match the oracle evaluated with that h; 0 switches back to the median heuristic."""
+    from stein_b200.engine import SvgdEngine
+    X0 = _particles(n, d, 21, 0.6).astype(np.float64)
+    mean = np.random.default_rng(22).standard_normal(d)
+    eng = SvgdEngine(n, d, "adam", learning_rate=0.05)
+    gd = orc.AdamGradientDescent(0.05)
+    eng.set_particles(X0)
+    h = np.float32(0.8 * np.sqrt(d))
+    eng.set_bandwidth(h)
+    X_gpu = np.empty_like(X0)
+    for it in range(2):
+        X_in = eng.get_particles(np.float64)
+        S = (mean - X_in) * 1.5
+        phi_ref, _ = orc.phi_rows_c(X_in, S, h, 0, n)
+        eng.update_particles_host(np.ascontiguousarray(S), X_gpu)
+        last = eng.last()
+        assert np.float32(last["bandwidth"]).tobytes() == h.tobytes()
+        assert np.isnan(last["median"]) and last["sweeps"] == 0
+        _assert_close(eng.get_phi(), phi_ref)
+        X_ref = X_in + gd.update(orc.clip(phi_ref))
+        ok = np.abs(phi_ref) > 1e-4 * np.abs(phi_ref).max()
+        assert np.abs(X_gpu - X_ref)[ok].max() <= RTOL_PHI * np.abs(X_ref).max()
+    eng.set_bandwidth(None)
+    X_in = eng.get_particles(np.float64)
+    eng.update_particles_host(np.ascontiguousarray((mean - X_in) * 1.5), X_gpu)
+    assert np.float32(eng.last()["bandwidth"]).tobytes() == orc.kernel_and_grad(X_in)[2].tobytes()
+    with pytest.raises(Exception):
+        eng.set_bandwidth(-1.0)
+    eng.close()
+
+
 @pytest.mark.parametrize("n,d,ld", [(3000, 55, 128), (4500, 200, 256), (2048, 130, 256)])
 def test_engine_pads_rows_for_the_tensor_core_kernels(ctx, n, d, ld):
     """With >= 2048 particles of up to 256 coordinates the engine pads the rows to 128 / 256
@@ -577,6 +611,36 @@ def test_sampler_linear_regression_known_answer(ctx, golden_dir):
     assert 0.5 * sd < sampler.samples.std() < 1.5 * sd
     pred = sampler.function_posterior(model.y_hat, {model.X: X[:7]}, axis=0)
     np.testing.assert_allclose(pred, X[:7, 0] * sampler.samples.mean(), rtol=1e-4, atol=1e-6)
+
+
+def test_sampler_follows_a_fixed_bandwidth_kernel(ctx, golden_dir):
+    """The kernel object is the plugin point (abstract_kernel.py:45-62): a squared-exponential
+    kernel built with `bandwidth=h` makes the sampler's engine skip the median; putting the
+    default kernel back restores the heuristic."""
+    from stein_b200.kernels import SquaredExponentialKernel
+    from stein_b200.log_p import LinearRegression
+    from stein_b200.optimizers import AdamGradientDescent
+    from stein_b200.samplers import SteinSampler
+    g = np.load(os.path.join(golden_dir, "linear_regression.npz"))
+    X, y = g["X"], g["y"].reshape(-1, 1)
+    model = LinearRegression(X.shape[1])
+    np.random.seed(3)
+    sampler = SteinSampler(40, model.log_p, AdamGradientDescent(learning_rate=1e-2))
+    sampler.kernel = SquaredExponentialKernel(40, bandwidth=0.25)
+    th = sampler.samples
+    S = orc.score_linear(th, X.astype(np.float32), y.astype(np.float32))
+    phi_ref, _ = orc.phi_rows_c(th, S, np.float32(0.25), 0, 40)
+    ref = th + orc.AdamGradientDescent(learning_rate=1e-2).update(orc.clip(phi_ref))
+    sampler.train_on_batch({model.X: X, model.y: y})
+    assert sampler.engine.last()["bandwidth"] == 0.25 and sampler.engine.last()["sweeps"] == 0
+    _assert_close(sampler.samples, ref, 2e-4)
+    assert sampler.kernel.compute_bandwidth(sampler.samples) == np.float32(0.25)
+    sampler.kernel = SquaredExponentialKernel(40)
+    th = sampler.samples
+    sampler.train_on_batch({model.X: X, model.y: y})
+    assert np.float32(sampler.engine.last()["bandwidth"]).tobytes() == orc.kernel_and_grad(th)[2].tobytes()
+    with pytest.raises(ValueError):
+        SquaredExponentialKernel(40, bandwidth=0.0)
 
 
 def test_sampler_logistic_and_bnn_trajectories(ctx):

@@ -262,3 +262,18 @@ def test_pair_sweep_tile_enumeration(lib, T):
     assert full.sum() == T * T                             # = all entries of the full (symmetric) matrix
     iu, il = np.triu_indices(T, 1), np.tril_indices(T, -1)
     assert (np.diag(full) == 1).all() and (full[iu] == 2).all() and (full[il] == 0).all()
+
+
+def test_kernel_plugin_bandwidth_argument():
+    """abstract_kernel.py:17 takes (n_particles, sess); the optional `bandwidth` selects the
+    fixed-bandwidth kernel and is validated on the host."""
+    from stein_b200.kernels import AbstractKernel, SquaredExponentialKernel
+    k = SquaredExponentialKernel(16, None)
+    assert k.fixed_bandwidth is None and k.bandwidth is None and k.n_particles == 16
+    k = SquaredExponentialKernel(16, bandwidth=0.5)
+    assert k.fixed_bandwidth == np.float32(0.5) and k.bandwidth == np.float32(0.5)
+    for bad in (0.0, -1.0, float("nan"), float("inf")):
+        with pytest.raises(ValueError):
+            SquaredExponentialKernel(16, bandwidth=bad)
+    with pytest.raises(NotImplementedError):
+        AbstractKernel.kernel_and_grad(k, np.zeros((16, 2)))
