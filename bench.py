@@ -270,6 +270,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
+    n_local, peer_push = eng.n_local, eng.peer_push
+    eng.close()          # collective when the peers are connected (every rank is idle here)
 
     if rank != 0:
         if world > 1:
@@ -280,7 +282,6 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = 1000.0 / ms_per_step
     # roofline of the dominant kernel (phi): algorithmic FLOPs of the LOCAL row block
-    n_local = eng.n_local
     f_phi = algorithmic_flops_phi(n, d) * (n_local / float(n))
     phi_avg_ms = phi_ms.value / max(phi_n.value, 1)
     achieved = f_phi / (phi_avg_ms * 1e-3) / 1e12
@@ -303,8 +304,11 @@ def run_ours(args):
         "config": {"workload": "gaussian_target_n%d_d%d" % (n, d), "n_particles": n, "dim": d,
                    "optimizer": "adam", "parallelism": "particle_rows_x%d" % world,
                    "collectives": ("none" if world == 1 else
-                                   "NCCL (library-driven); particles pushed to peers by the optimizer kernel"
-                                   if eng.peer_push else "NCCL (library-driven)"),
+                                   "scores: NCCL all-gather on a side stream; particles: pushed to the peers by "
+                                   "the optimizer kernel; small all-reduces: %s"
+                                   % ("one kernel each over NVLink peer memory"
+                                      if os.environ.get("STEIN_PEER_REDUCE", "1") != "0" else "NCCL")
+                                   if peer_push else "NCCL (library-driven)"),
                    "phi_impl": impl, "median_sweeps_last_step": info["sweeps"],
                    "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set "
                          "is also > 126 MB"},

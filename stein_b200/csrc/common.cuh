@@ -19,6 +19,10 @@ constexpr int NUM_SMS_B200 = 148;
 
 }  // namespace stein
 
+namespace stein {
+struct PeerReduce;   // peer_reduce.cu
+}
+
 struct stein_ctx {
     int device = 0;
     int num_sms = stein::NUM_SMS_B200;
@@ -26,6 +30,9 @@ struct stein_ctx {
     bool has_comm = false;
     stein_comm comm{};
     void *nccl_state = nullptr;     // built-in NCCL transport (comm_nccl.cu), if initialised
+    // installed by an engine whose peers are open: the small all-reduces then run over NVLink peer
+    // memory (peer_reduce.cu) instead of the hooks above
+    stein::PeerReduce *peer_reduce = nullptr;
     int phi_impl = STEIN_PHI_AUTO;
     int median_impl = STEIN_MEDIAN_AUTO;
     // set by an engine around its median call: identifies the sequence of calls whose medians move
@@ -62,6 +69,9 @@ extern thread_local std::string g_last_error;
 
 int fail(stein_ctx *ctx, int code, const char *fmt, ...);
 void nccl_release(stein_ctx *ctx);   // comm_nccl.cu
+// in-place sums across the ranks, ordered on the ctx stream (peer_reduce.cu)
+int allreduce_u64(stein_ctx *ctx, void *buf_dev, int64_t count);
+int allreduce_f64(stein_ctx *ctx, void *buf_dev, int64_t count);
 
 #define STEIN_CHECK_CUDA(ctx, expr)                                                        \
     do {                                                                                   \

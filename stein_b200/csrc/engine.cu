@@ -18,6 +18,7 @@
 #include <algorithm>
 
 #include "phi_common.cuh"
+#include "peer_reduce.cuh"
 
 struct stein_engine {
     stein_ctx *ctx = nullptr;
@@ -43,6 +44,10 @@ struct stein_engine {
     bool peers_open = false;
     bool x_all_current = false;     // every rank's X_all holds everybody's current rows
     unsigned long long *barrier_word = nullptr;   // 1 u64 all-reduced as the cross-rank barrier after a push
+    // sharded engines: the particle buffer is followed by a mailbox (peer_reduce.cuh) so that one
+    // IPC handle exports both; peer_reduce is what the context uses while the peers are open
+    int64_t mbox_offset = 0;
+    stein::PeerReduce *peer_reduce = nullptr;
     uintptr_t uid = 0;      // unique per engine ever created in the process (median window hint owner)
     float last_med = 0.f, last_bw = 0.f;
     float fixed_bw = 0.f;   // > 0: use this bandwidth instead of the median heuristic
@@ -159,7 +164,8 @@ int stein_engine_create(stein_engine **out, stein_ctx *ctx, int64_t n_total, int
         err = cudaMalloc(p, bytes);
         if (err == cudaSuccess) err = cudaMemsetAsync(*p, 0, bytes, ctx->stream);
     };
-    alloc0((void **)&e->X_all, all);
+    e->mbox_offset = all;
+    alloc0((void **)&e->X_all, all + (e->world > 1 ? (int64_t)MBOX_BYTES : 0));
     alloc0((void **)&e->S_all, all);
     alloc0((void **)&e->phi, loc);
     alloc0((void **)&e->m1, loc);
@@ -181,10 +187,18 @@ int stein_engine_create(stein_engine **out, stein_ctx *ctx, int64_t n_total, int
     return STEIN_OK;
 }
 
+static void release_peer_reduce(stein_engine *e) {
+    if (!e->peer_reduce) return;
+    if (e->ctx->peer_reduce == e->peer_reduce) e->ctx->peer_reduce = nullptr;
+    peer_reduce_destroy(e->peer_reduce);
+    e->peer_reduce = nullptr;
+}
+
 int stein_engine_destroy(stein_engine *e) {
     if (!e) return STEIN_OK;
     cudaSetDevice(e->ctx->device);
     cudaStreamSynchronize(e->ctx->stream);
+    release_peer_reduce(e);
     if (e->peers_open)
         for (int r = 0; r < e->world; ++r)
             if (r != e->rank && e->peer_X[r]) cudaIpcCloseMemHandle(e->peer_X[r]);
@@ -262,8 +276,7 @@ static int step_bandwidth(stein_engine *e, float *bw_out) {
             // every rank pushed its updated rows into this buffer during its last optimizer
             // step; a 1-word all-reduce is the barrier that orders those stores (it completes
             // only after every rank has enqueued it, i.e. after its step kernel)
-            if (ctx->comm.allreduce_sum_u64(ctx->comm.user, e->barrier_word, 1) != 0)
-                return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+            STEIN_TRY(allreduce_u64(ctx, e->barrier_word, 1));
         } else {
             const int64_t cnt = e->q * e->ld;
             if (ctx->comm.allgather_f32(ctx->comm.user, e->X_local(), e->X_all, cnt) != 0)
@@ -312,10 +325,7 @@ static int step_update(stein_engine *e, float bw, bool scores_gathered) {
     // abstract_stein_sampler.py:100-105
     STEIN_TRY(stein_phi(ctx, e->X_all, e->S_all, e->r_all, e->n_total, e->d, e->ld, e->row_begin,
                         std::max<int64_t>(e->n_local, 1), bw, e->ws, e->ws_bytes, e->phi, e->sumsq));
-    if (e->world > 1) {
-        if (ctx->comm.allreduce_sum_f64(ctx->comm.user, e->sumsq, 1) != 0)
-            return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_f64 hook failed");
-    }
+    if (e->world > 1) STEIN_TRY(allreduce_f64(ctx, e->sumsq, 1));
     // abstract_stein_sampler.py:125-126
     const int64_t count = e->q * e->ld;
     // peers: the same rows inside the other ranks' X_all.  Safe to overwrite now: the all-reduce
@@ -424,6 +434,7 @@ int stein_engine_set_peer_handles(stein_engine *e, const void *handles) {
                 cudaIpcCloseMemHandle(e->peer_X[r]);
                 e->peer_X[r] = nullptr;
             }
+        release_peer_reduce(e);
         e->peers_open = false;
         e->x_all_current = false;
         return STEIN_OK;
@@ -448,8 +459,21 @@ int stein_engine_set_peer_handles(stein_engine *e, const void *handles) {
         }
         e->peer_X[r] = (float *)p;
     }
-    STEIN_CHECK_CUDA(ctx, cudaMalloc(&e->barrier_word, 8));
+    if (!e->barrier_word) STEIN_CHECK_CUDA(ctx, cudaMalloc(&e->barrier_word, 8));
     STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(e->barrier_word, 0, 8, ctx->stream));
+    // The small all-reduces of the iteration go through the mailboxes behind the particle buffers
+    // from now on (STEIN_PEER_REDUCE=0 keeps them on the stein_comm hooks; same value on every rank).
+    const char *env = getenv("STEIN_PEER_REDUCE");
+    if (!(env && env[0] == '0')) {
+        void *boxes[MAX_PEERS + 1];
+        for (int r = 0; r < e->world; ++r)
+            boxes[r] = reinterpret_cast<char *>(r == e->rank ? e->X_all : e->peer_X[r]) + e->mbox_offset;
+        STEIN_TRY(peer_reduce_create(ctx, e->rank, e->world, boxes, &e->peer_reduce));
+        ctx->peer_reduce = e->peer_reduce;
+    }
+    // the zero-fill of this rank's mailbox (engine creation) must be over before a peer writes
+    // into it; the caller's exchange of the outcome is the barrier between the ranks
+    STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     e->peers_open = true;
     e->x_all_current = false;
     return STEIN_OK;

@@ -560,10 +560,7 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
         STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->d_counts, 0, bytes, ctx->stream));
         STEIN_TRY(stein_sqdist_hist(ctx, X_dev, r_dev, n, d, ld, t0, t1, w.key_lo, w.shift, w.nbins,
                                     ctx->d_counts));
-        if (world > 1) {
-            if (ctx->comm.allreduce_sum_u64(ctx->comm.user, ctx->d_counts, (int64_t)w.nbins + 1) != 0)
-                return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
-        }
+        if (world > 1) STEIN_TRY(allreduce_u64(ctx, ctx->d_counts, (int64_t)w.nbins + 1));
         STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, bytes,
                                               cudaMemcpyDeviceToHost, ctx->stream));
         STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

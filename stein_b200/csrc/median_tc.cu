@@ -1184,8 +1184,7 @@ static int window_counts(stein_ctx *ctx, const void *src, unsigned long long m_l
                                                                              A.bins);
         STEIN_CHECK_LAUNCH(ctx);
     }
-    if (distributed && ctx->has_comm && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.bins, (int64_t)nbins + 1) != 0)
-        return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+    if (distributed && ctx->has_comm) STEIN_TRY(allreduce_u64(ctx, A.bins, (int64_t)nbins + 1));
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.h_pinned, A.bins, (nbins + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     // a few more device words can ride on the same round trip
     if (extra_words)
@@ -1338,8 +1337,7 @@ static int median_tc_device_tail(stein_ctx *ctx, const float *X, const float *r,
         A.list, A.list_cap, r, 0.f, 0.f, c_half, 0.f, A.counters + CNT_BELOW2, A.counters + CNT_BANDW,
         A.counters + CNT_BAND_LEN, A.band, A.band_cap, d_overflow2, A.counters + CNT_LIST_LEN, bp);
     STEIN_CHECK_LAUNCH(ctx);
-    if (world > 1 && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.counters + CNT_BELOW2, 3) != 0)
-        return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+    if (world > 1) STEIN_TRY(allreduce_u64(ctx, A.counters + CNT_BELOW2, 3));
     STEIN_TRY(launch_pair_chain<0>(ctx, A.band, A.band_cap, X, r, n, ld, 0, A.counters + CNT_BAND_LEN));
     static bool attr_set = false;
     if (!attr_set) {
@@ -1351,8 +1349,7 @@ static int median_tc_device_tail(stein_ctx *ctx, const float *X, const float *r,
     window_hist_kernel<1><<<4 * ctx->num_sms, 256, (HIST_MAX_BINS + 1) * 4, ctx->stream>>>(
         A.band, A.band_cap, A.counters + CNT_BAND_LEN, 0u, 0u, (uint32_t)HIST_MAX_BINS, A.bins, bp);
     STEIN_CHECK_LAUNCH(ctx);
-    if (world > 1 && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.bins, HIST_MAX_BINS + 1) != 0)
-        return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+    if (world > 1) STEIN_TRY(allreduce_u64(ctx, A.bins, HIST_MAX_BINS + 1));
     unsigned long long *h = A.h_pinned + HIST_MAX_BINS + 2;
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.h_pinned, A.bins, (HIST_MAX_BINS + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h, A.counters, CNT_TOTAL * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1487,8 +1484,7 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
                                                                                w.key_lo, w.shift, w.nbins, A.bins);
             STEIN_CHECK_LAUNCH(ctx);
         }
-        if (world > 1 && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.bins, (int64_t)w.nbins + 1) != 0)
-            return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+        if (world > 1) STEIN_TRY(allreduce_u64(ctx, A.bins, (int64_t)w.nbins + 1));
         pilot_pick_kernel<<<1, 1024, 0, ctx->stream>>>(A.bins, w.key_lo, w.shift, w.nbins, spec->rank_lo, spec->rank_hi,
                                                       reinterpret_cast<uint32_t *>(A.counters + CNT_WINDOW));
         STEIN_CHECK_LAUNCH(ctx);
@@ -1548,8 +1544,7 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     if (sweeps) *sweeps += 1;
     // below / listed / overflow / histogram of the listed D~ become global quantities with ONE
     // all-reduce; the list itself (and its length) stays rank-local
-    if (world > 1 && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.counters, CNT_G1_END) != 0)
-        return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+    if (world > 1) STEIN_TRY(allreduce_u64(ctx, A.counters, CNT_G1_END));
     if (spec) return median_tc_device_tail(ctx, X, r, n, d, ld, ranks, c_half, &p, keys_out);
     unsigned long long *h = A.h_pinned + HIST_MAX_BINS + 2;
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h, A.counters, CNT_TOTAL * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1588,8 +1583,7 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
                                                                 d_overflow2);
         STEIN_CHECK_LAUNCH(ctx);
     }
-    if (world > 1 && ctx->comm.allreduce_sum_u64(ctx->comm.user, A.counters + CNT_BELOW2, 3) != 0)
-        return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
+    if (world > 1) STEIN_TRY(allreduce_u64(ctx, A.counters + CNT_BELOW2, 3));
     // No host round trip here: the band length stays on the device (list_len bounds it), the
     // counts of the filter are fetched together with the first histogram of the select below.
     const unsigned long long band_bound = std::min<unsigned long long>(list_len, A.band_cap);

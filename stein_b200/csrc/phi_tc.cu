@@ -135,14 +135,30 @@ struct SegWalk {
             ++k;
             return true;
         }
-        if (pos >= end) return false;
+        // Leftover chunk [pos, end): chunk <= nJ, so it touches at most two row tiles.  The part in
+        // the second tile starts at column 0 and goes FIRST: every unit then walks its columns in
+        // ascending order, and at any time all units are within nJ - chunk columns of each other
+        // -- a column tile is fetched from HBM once and the later readers find it in L2.  (In
+        // tile order the units would start at ~G different columns and each would stream its
+        // operands from HBM: measured 12 % on the phi kernel of a 4-way sharded run.)
+        const int step = k - sc.rounds;
+        ++k;
+        if (pos >= end || step > 1) return false;
         const int tr = (int)(pos / sc.nJ);
-        j0 = (int)(pos - (long long)tr * sc.nJ);
-        const long long left = end - pos;
-        j1 = (long long)j0 + left < (long long)sc.nJ ? (int)(j0 + left) : sc.nJ;
+        const long long split = ((long long)tr + 1) * sc.nJ;      // first position of the next row tile
+        const bool two = end > split;
+        if (step == 0 && two) {
+            t = sc.rounds * sc.G + tr + 1;
+            j0 = 0;
+            j1 = (int)(end - split);
+            slot = c - sc.first_unit(tr + 1);
+            return true;
+        }
+        if (step == 1 && !two) return false;
         t = sc.rounds * sc.G + tr;
+        j0 = (int)(pos - (long long)tr * sc.nJ);
+        j1 = two ? sc.nJ : (int)(end - (long long)tr * sc.nJ);
         slot = c - sc.first_unit(tr);
-        pos += j1 - j0;
         return true;
     }
 };

@@ -64,6 +64,21 @@ def connect_peers(engine):
     return True
 
 
+def quiesce_peers(engine):
+    """Before an engine with connected peers is freed: drain this rank's stream, then wait for
+    every rank (their kernels write into this engine's particle buffer and mailbox).  Best
+    effort at interpreter shutdown, when the process group may already be gone."""
+    import torch
+    import torch.distributed as dist
+    info = getattr(engine.ctx, "_native_comm_group", None)
+    try:
+        torch.cuda.synchronize(engine.ctx.device)
+        if info is not None and dist.is_initialized():
+            dist.barrier(group=info[0])
+    except Exception:
+        pass
+
+
 def make_comm(ctx, group=None, native=None):
     """Install collective hooks on `ctx` for the default (or given) process group.
     native=True (default on an NCCL group): the library's own NCCL transport

@@ -40,14 +40,20 @@ class SvgdEngine:
             from .distributed import connect_peers
             self.peer_push = connect_peers(self)
 
-    def close(self):
+    def close(self, collective=True):
+        """Frees the engine.  With peers connected this is COLLECTIVE: the other ranks' kernels
+        store into this engine's buffers, so every rank first finishes its queued work and meets
+        the others at a barrier."""
         if self.handle:
+            if self.peer_push and collective:
+                from .distributed import quiesce_peers
+                quiesce_peers(self)
             self.lib.stein_engine_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
         try:
-            self.close()
+            self.close(collective=False)     # garbage collection is not a collective moment
         except Exception:
             pass
 

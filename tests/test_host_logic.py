@@ -235,6 +235,34 @@ def test_phi_tile_schedule_covers_every_tile_pair_once(lib, nI, nJ, G):
     assert max(loads) - min(l for l in loads if l > 0 or rem == 0) <= chunk
 
 
+@pytest.mark.parametrize("nI,nJ,G", [(256, 512, 74), (128, 512, 74), (64, 512, 74), (32, 512, 74), (16, 512, 74)])
+def test_phi_leftover_chunks_walk_the_columns_together(lib, nI, nJ, G):
+    """The leftover row tiles (all of them on a sharded run) are cut into one chunk per unit.  A
+    unit walks the columns of its chunk in ASCENDING order, so at every step all units are within
+    nJ - chunk columns of each other and a column tile is served from L2 after its first fetch."""
+    fn = lib.stein_debug_tile_schedule
+    fn.restype = ctypes.c_int
+    IntP = ctypes.POINTER(ctypes.c_int)
+    fn.argtypes = [ctypes.c_int] * 5 + [IntP] * 5
+    rounds, rem = nI // G, nI % G
+    chunk = max(-(-rem * nJ // G), -(-nJ // 7), 1)
+    cap = rounds + 4
+    walks = []
+    for c in range(G):
+        t, j0, j1, sl = ((ctypes.c_int * cap)() for _ in range(4))
+        n = fn(nI, nJ, G, c, cap, t, j0, j1, sl, None)
+        cols = [j for k in range(rounds, n) for j in range(j0[k], j1[k])]
+        assert cols == sorted(cols) and len(set(cols)) == len(cols)
+        if cols:
+            walks.append(cols)
+    assert all(len(w) == chunk for w in walks[:-1])        # only the last chunk may be shorter
+    steps = max(len(w) for w in walks)
+    for s in range(steps):
+        at = [w[s] for w in walks if s < len(w)]
+        assert max(at) - min(at) <= nJ - len(walks[-1]) + 1
+        assert max(at[:-1] or [0]) - min(at[:-1] or [0]) <= nJ - chunk + 1
+
+
 @pytest.mark.parametrize("T", [1, 2, 3, 4, 33, 40, 512])
 def test_pair_sweep_tile_enumeration(lib, T):
     """The CTA-pair median sweep walks pair rows I2 and column tiles J >= 2 I2 in row-major order

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1"
+timeout 300 $TR --master-port 29511 tools/multi_gpu_check.py > gpurun_out/mgc4.log 2>&1; echo "mgc_rc=$?"
+grep -c " ok" gpurun_out/mgc4.log; grep -i "fail\|error\|timed out" gpurun_out/mgc4.log | head -5
+timeout 300 $TR --master-port 29512 bench.py --gpus 4 --steps 20 --warmup 3 > gpurun_out/bench_n4.log 2> gpurun_out/bench_n4.err; echo "bench_rc=$?"
+tail -1 gpurun_out/bench_n4.log | cut -c1-200
