@@ -274,7 +274,13 @@ int stein_engine_update_particles_host(stein_engine *eng, const void *S_host, vo
  * straight into the other ranks' buffers over NVLink and the all-gather of the particles is replaced
  * by a one-word all-reduce.  Returns STEIN_ERR_UNSUPPORTED when a handle cannot be opened (the
  * engine then keeps using the all-gather hook).  handles == NULL closes the peers again.  Either
- * every rank pushes or none: the caller must agree on the outcome across ranks. */
+ * every rank pushes or none: the caller must agree on the outcome across ranks, and that exchange
+ * is also the barrier after which a rank may be written to by its peers.
+ * The exported buffer carries a mailbox behind the particles; while the peers are open the small
+ * all-reduces of an iteration (histograms, counters, sum(phi^2), the barrier word) run as one
+ * kernel each over those mappings instead of the allreduce hooks (environment STEIN_PEER_REDUCE=0,
+ * same on every rank, keeps them on the hooks).  Destroying an engine with open peers is
+ * collective: every rank must have drained its stream and met the others first. */
 #define STEIN_IPC_HANDLE_BYTES 64
 int stein_engine_ipc_handle(stein_engine *eng, void *handle_out);
 int stein_engine_set_peer_handles(stein_engine *eng, const void *handles /* world x 64 bytes */);
