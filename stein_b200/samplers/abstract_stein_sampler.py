@@ -6,6 +6,7 @@ import numpy as np
 from ..engine import SvgdEngine
 from ..kernels import SquaredExponentialKernel
 from ..log_p.base import LogPosterior, Output
+from ..log_p.graph_log_p import GraphLogPosterior, is_graph_tensor
 from ..optimizers._fused import FusedGradientDescent
 from ..runtime import context, ptr
 from ..utilities import convert_array_to_dictionary, convert_dictionary_to_array
@@ -25,11 +26,15 @@ class AbstractSteinSampler:
     """
 
     def __init__(self, n_particles, log_p, theta=None):
+        if is_graph_tensor(log_p):
+            # a `log_p` tensor recorded by the TF1 stand-in of compat/ (the reference's own scripts)
+            log_p = GraphLogPosterior(log_p)
         if not isinstance(log_p, LogPosterior):
             raise TypeError(
                 "log_p must be a stein_b200.log_p.LogPosterior (LinearRegression, "
-                "LogisticRegression, RegressionNeuralNetwork or TorchLogPosterior); "
-                "TensorFlow graphs are not supported")
+                "LogisticRegression, RegressionNeuralNetwork, TorchLogPosterior) or a graph "
+                "tensor built with the `tensorflow` stand-in of compat/; real TensorFlow graphs "
+                "are not supported")
         self.n_particles = n_particles
         self.sess = None
         self.log_p = log_p
@@ -148,9 +153,12 @@ class AbstractSteinSampler:
         """abstract_stein_sampler.py:129-168: `func` evaluated for every particle,
         one row per particle; `axis` averages.  `func` is an Output handle of the
         model (e.g. model.logits, model.pred): all particles in one kernel."""
-        if not isinstance(func, Output):
+        if is_graph_tensor(func) and isinstance(self.log_p, GraphLogPosterior):
+            dist = self.log_p.evaluate(func, self._engine, feed_dict)     # any tensor of the graph
+        elif isinstance(func, Output):
+            dist = func.model.evaluate(func, self._engine, feed_dict)
+        else:
             raise TypeError("func must be an Output handle of the model (e.g. model.logits)")
-        dist = func.model.evaluate(func, self._engine, feed_dict)
         dist = dist.reshape(dist.shape[0], -1)
         if axis is not None:
             return dist.double().mean(dim=axis).cpu().numpy()

@@ -850,3 +850,45 @@ def test_median_window_hint_miss_falls_back(ctx):
     eng.close()
     # first step: no hint; second: hint hits; after each jump the speculative sweep is wasted once
     assert sweeps[0] == 1 and sweeps[1] == 1 and sweeps[2] == 2 and sweeps[3] == 1 and sweeps[4] == 2, sweeps
+
+
+def test_sampler_takes_a_tf1_graph_like_the_reference(ctx, golden_dir):
+    """SteinSampler(n_particles, log_p, gd) with `log_p` a graph tensor recorded by the
+    TensorFlow-1 stand-in of compat/ (what the reference's scripts pass): same trajectory as the
+    built-in model class from the same start, `theta` keyed by the graph's variables,
+    function_posterior on any tensor of the graph."""
+    import sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "compat")
+    if compat not in sys.path:
+        sys.path.insert(0, compat)
+    import tensorflow as tf
+    from tensorflow.contrib.distributions import Normal
+    from stein_b200.log_p import LinearRegression
+    from stein_b200.optimizers import AdamGradientDescent
+    from stein_b200.samplers import SteinSampler
+    g = np.load(os.path.join(golden_dir, "linear_regression.npz"))
+    X, y = g["X"], g["y"].reshape(-1, 1)
+    tf.reset_default_graph()
+    with tf.variable_scope("model"):
+        model_X = tf.placeholder(tf.float32, shape=[None, X.shape[1]])
+        model_y = tf.placeholder(tf.float32, shape=[None, 1])
+        model_w = tf.Variable(tf.zeros([X.shape[1], 1]))
+        y_hat = tf.matmul(model_X, model_w)
+        log_p = (-0.5 * tf.reduce_sum(tf.square(y_hat - model_y)) +
+                 tf.reduce_sum(Normal(tf.zeros([X.shape[1], 1]), 1.).log_prob(model_w)))
+    np.random.seed(4)
+    sampler = SteinSampler(50, log_p, AdamGradientDescent(learning_rate=1e-1))
+    assert sampler.model_vars == [model_w] and sampler.theta[model_w].shape == (50, 1, 1)
+    builtin = LinearRegression(X.shape[1])
+    np.random.seed(4)
+    twin = SteinSampler(50, builtin.log_p, AdamGradientDescent(learning_rate=1e-1))
+    np.testing.assert_array_equal(sampler.samples, twin.samples)
+    for it in range(5):
+        sampler.train_on_batch({model_X: X, model_y: y})
+        twin.train_on_batch({builtin.X: X, builtin.y: y})
+        _assert_close(sampler.samples, twin.samples, 2e-4)
+    pred = sampler.function_posterior(y_hat, {model_X: X[:7]}, axis=0)
+    np.testing.assert_allclose(pred, twin.function_posterior(builtin.y_hat, {builtin.X: X[:7]}, axis=0),
+                               rtol=1e-3, atol=1e-6)
+    full = sampler.function_posterior(y_hat, {model_X: X[:7]})
+    assert full.shape == (50, 7)
