@@ -1326,7 +1326,10 @@ static SlotLayout slot_layout(const FlashPlan &pl, char *&pws) {
     return L;
 }
 
-// workspace: [Xh, Xl, YTh, YTl (bf16) | nrm | slot buffers | partials]
+// workspace: [four 16-bit operand arrays of cols x DP (BF16 hi/lo of X and Y^T, or, in the
+// mixed-precision modes, the FP16 arrays with the FP8 arrays sharing the lo places) | nrm |
+// slot buffers | partials | centred particles, their norms, column means | column scales of Y,
+// scale of X | b8h, b8l]
 int64_t flash_tc_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
     const FlashPlan p1 = flash_plan(ctx, n_local, n_total, d, false), p2 = flash_plan(ctx, n_local, n_total, d, true);
     int64_t b = 0;
