@@ -14,6 +14,7 @@ Put the directory that holds this package (`compat/`) on PYTHONPATH to run the r
 example scripts unchanged; it is deliberately not importable otherwise, so that it can never
 shadow a real TensorFlow by accident.
 """
+import collections
 import contextlib
 
 import numpy as np
@@ -207,6 +208,18 @@ class Tensor:
     def __pow__(self, o): return pow(self, o)
     def __matmul__(self, o): return matmul(self, o)
 
+    def __getitem__(self, key):
+        keys = key if isinstance(key, tuple) else (key,)
+        shape = None
+        if self._shape is not None and len(keys) <= len(self._shape) and all(
+                isinstance(k, (int, slice)) for k in keys):
+            shape = []
+            for k, dim in zip(keys, self._shape):
+                if isinstance(k, slice):
+                    shape.append(None if dim is None else len(range(*k.indices(dim))))
+            shape += self._shape[len(keys):]
+        return Tensor("StridedSlice", (self,), {"key": keys}, shape=shape)
+
     def eval(self, feed_dict=None, session=None):
         return (session or Session()).run(self, feed_dict)
 
@@ -337,8 +350,16 @@ def transpose(x, perm=None, name=None):
 
 
 def reshape(x, shape, name=None):
+    x = _const(x)
     shape = [int(s) for s in shape]
-    return Tensor("Reshape", (_const(x),), {"shape": shape}, shape=[None if s < 0 else s for s in shape])
+    static = [None if s < 0 else s for s in shape]
+    # like TensorFlow: a single -1 is inferred when the element count of the input is known
+    if static.count(None) == 1 and x._shape is not None and all(d is not None for d in x._shape):
+        total = int(np.prod(x._shape, dtype=np.int64)) if x._shape else 1
+        rest = int(np.prod([s for s in static if s is not None], dtype=np.int64)) if len(static) > 1 else 1
+        if rest > 0 and total % rest == 0:
+            static[static.index(None)] = total // rest
+    return Tensor("Reshape", (x,), {"shape": shape}, shape=static)
 
 
 def squeeze(x, axis=None, name=None):
@@ -398,6 +419,9 @@ def gradients(ys, xs, name=None, stop_gradients=None):
     return [Tensor("Gradient", [_const(y) for y in ys] + [x], {"n_ys": len(ys)}, shape=x._shape) for x in xs]
 
 
+TopKV2 = collections.namedtuple("TopKV2", ["values", "indices"])
+
+
 class _NN:
     @staticmethod
     def relu(x, name=None): return _unary("Relu", x)
@@ -420,9 +444,10 @@ class _NN:
     @staticmethod
     def top_k(x, k=1, sorted=True, name=None):  # noqa: A002
         x = _const(x)
-        values = Tensor("TopKValues", (x,), {"k": int(k)})
-        indices = Tensor("TopKIndices", (x,), {"k": int(k)})
-        return values, indices
+        shape = None if x._shape is None else list(x._shape[:-1]) + [int(k)]
+        values = Tensor("TopKValues", (x,), {"k": int(k)}, shape=shape)
+        indices = Tensor("TopKIndices", (x,), {"k": int(k)}, shape=shape)
+        return TopKV2(values, indices)
 
 
 nn = _NN()
@@ -437,6 +462,8 @@ def evaluate(fetches, values, device=None):
     import torch
     single = isinstance(fetches, Tensor)
     cache = {}
+    grad_nodes = [f for f in ([fetches] if single else fetches)
+                  if isinstance(f, Tensor) and f.op_type == "Gradient"]
 
     def const(arr):
         dt = torch.float32 if arr.dtype.kind == "f" else torch.int64
@@ -517,24 +544,34 @@ def evaluate(fetches, values, device=None):
             if op == "Sum": return x[0].sum(dim=ax, keepdim=kd)
             if op == "Mean": return x[0].mean(dim=ax, keepdim=kd)
             return torch.amax(x[0], dim=ax, keepdim=kd)
+        if op == "StridedSlice": return x[0][a["key"]]
         if op == "TopKValues": return torch.topk(x[0], a["k"]).values
         if op == "TopKIndices": return torch.topk(x[0], a["k"]).indices
         raise NotImplementedError("tensorflow shim: op %r" % op)
 
     def grad_op(t):
-        # independent evaluation with the differentiated input as a leaf
+        # Independent evaluation of the ys with the differentiated inputs as leaves.  All
+        # gradient nodes of this call that share their ys (tf.gradients(y, [x1, ..., xn])) are
+        # served by ONE backward pass.
         n_ys = t.attrs["n_ys"]
-        ys, x = t.inputs[:n_ys], t.inputs[n_ys]
-        leaf = ev(x).detach().clone().requires_grad_(True)
+        ys = t.inputs[:n_ys]
+        group = [g for g in grad_nodes if g.inputs[:g.attrs["n_ys"]] == ys] or [t]
+        if t not in group:
+            group.append(t)
+        xs = [g.inputs[g.attrs["n_ys"]] for g in group]
+        leaves = [ev(x).detach().clone().requires_grad_(True) for x in xs]
         sub = dict(values)
-        sub[x] = leaf
+        sub.update(zip(xs, leaves))
         with torch.enable_grad():
             outs = evaluate(list(ys), sub, device=device)
             total = sum(o.sum() for o in outs)
-            if not total.requires_grad:
-                return torch.zeros_like(leaf)
-            (g,) = torch.autograd.grad(total, leaf, allow_unused=True)
-        return torch.zeros_like(leaf) if g is None else g
+            if total.requires_grad:
+                grads = torch.autograd.grad(total, leaves, allow_unused=True)
+            else:
+                grads = [None] * len(leaves)
+        for g, leaf, val in zip(group, leaves, grads):
+            cache[id(g)] = torch.zeros_like(leaf) if val is None else val
+        return cache[id(t)]
 
     out = [ev(_const(f)) for f in ([fetches] if single else fetches)]
     return out[0] if single else out
@@ -554,13 +591,27 @@ class Session:
         values = {}
         for k, v in (feed_dict or {}).items():
             values[k] = np.asarray(v, dtype=np.float32)
-        if isinstance(fetches, (list, tuple)):
-            flat = [f for f in fetches if f is not None]
-            outs = iter(evaluate(flat, values)) if flat else iter(())
-            return [None if f is None else next(outs).detach().cpu().numpy() for f in fetches]
-        if fetches is None:
-            return None
-        return evaluate(fetches, values).detach().cpu().numpy()
+        flat = []
+
+        def collect(f):
+            if isinstance(f, (list, tuple)):
+                for g in f:
+                    collect(g)
+            elif f is not None:
+                flat.append(_const(f))
+
+        collect(fetches)
+        outs = iter(evaluate(flat, values)) if flat else iter(())
+
+        def rebuild(f):
+            if isinstance(f, (list, tuple)):
+                out = [rebuild(g) for g in f]
+                return out if isinstance(f, list) else (type(f)(*out) if hasattr(f, "_fields") else tuple(out))
+            if f is None:
+                return None
+            return next(outs).detach().cpu().numpy()
+
+        return rebuild(fetches)
 
     def close(self):
         pass

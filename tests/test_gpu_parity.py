@@ -892,3 +892,63 @@ def test_sampler_takes_a_tf1_graph_like_the_reference(ctx, golden_dir):
                                rtol=1e-3, atol=1e-6)
     full = sampler.function_posterior(y_hat, {model_X: X[:7]})
     assert full.shape == (50, 7)
+
+
+# --------------------------------------------------------------------------- #
+# against tests/golden/reference_run.npz: the reference's own library code,     #
+# executed on the TF1 stand-in (tests/golden/make_golden_reference_run.py)      #
+# --------------------------------------------------------------------------- #
+def test_kernel_and_grad_matches_the_reference_run(ctx, golden_dir):
+    """stein/kernels/squared_exponential_kernel.py:25-35 run by the reference's own class."""
+    from stein_b200.kernels import SquaredExponentialKernel
+    ref = np.load(os.path.join(golden_dir, "reference_run.npz"))
+    for i, (n, d) in enumerate(ref["kernel_shapes"]):
+        theta = ref["kernel%d_theta" % i]
+        kern = SquaredExponentialKernel(int(n), None)
+        K, dK = kern.kernel_and_grad(theta)
+        assert abs(float(kern.bandwidth) - float(ref["kernel%d_bandwidth" % i])) <= 2e-6 * float(kern.bandwidth)
+        np.testing.assert_allclose(K, ref["kernel%d_K" % i], atol=4e-6, rtol=2e-5)
+        _assert_close(dK, ref["kernel%d_dK" % i], 3e-5)
+
+
+@pytest.mark.parametrize("tag", ["linear", "logistic", "bnn_adam", "bnn_adagrad"])
+def test_first_iteration_matches_the_reference_run(ctx, golden_dir, tag):
+    """One SteinSampler.train_on_batch from the particles the reference run started from: scores
+    (the reference's per-particle tf.gradients loop), phi (its compute_phi) and the particles
+    after its clip + optimizer step.  Entries whose phi is within the kernels' error of zero are
+    left out of the particle comparison (the first Adam / Adagrad step is lr * c * sign(phi))."""
+    from stein_b200.log_p import LinearRegression, LogisticRegression, RegressionNeuralNetwork
+    from stein_b200.optimizers import AdagradGradientDescent, AdamGradientDescent
+    from stein_b200.samplers import SteinSampler
+    from stein_b200.utilities import convert_array_to_dictionary
+    ref = np.load(os.path.join(golden_dir, "reference_run.npz"))
+    traj = ref[tag + "_traj"]
+    n, d = traj[0].shape
+    if tag == "linear":
+        g = np.load(os.path.join(golden_dir, "linear_regression.npz"))
+        model = LinearRegression(g["X"].shape[1])
+        feed = {model.X: g["X"], model.y: g["y"].reshape(-1, 1)}
+        gd = AdamGradientDescent(learning_rate=1e-1)
+    elif tag == "logistic":
+        X, y, idx = ref["logistic_X"], ref["logistic_y"], ref["logistic_batches"][0]
+        model = LogisticRegression(X.shape[1], X.shape[0])
+        feed = {model.X: X[idx], model.y: y[idx]}
+        gd = AdamGradientDescent(learning_rate=1e-1)
+    else:
+        X, y, idx = ref["bnn_X"], ref["bnn_y"], ref["bnn_batches"][0]
+        model = RegressionNeuralNetwork(X.shape[1], 5, X.shape[0])
+        feed = {model.X: X[idx], model.y: y[idx]}
+        gd = (AdamGradientDescent(learning_rate=1e-1, decay=0.999) if tag == "bnn_adam"
+              else AdagradGradientDescent(learning_rate=5e-2, decay=0.5, alpha=0.9))
+    assert model.n_params == d
+    theta0 = convert_array_to_dictionary(traj[0], model.column_slices())
+    sampler = SteinSampler(int(n), model.log_p, gd, theta=theta0)
+    _assert_close(sampler.samples, traj[0], 1e-6)
+    sampler.train_on_batch(feed)
+    eng = sampler.engine
+    _assert_close(eng.scores_dev[:n, :d].cpu().numpy(), ref[tag + "_scores0"], 1e-4)
+    phi_ref = ref[tag + "_phi0"]
+    _assert_close(eng.get_phi(), phi_ref)
+    ok = np.abs(phi_ref) > 1e-4 * np.abs(phi_ref).max()
+    assert ok.mean() > 0.9
+    assert np.abs(sampler.samples - traj[1])[ok].max() <= RTOL_PHI * np.abs(traj[1]).max()
