@@ -6,10 +6,14 @@
  * cpu_baseline / --impl reference legs may load this file's shared object.
  * The product (stein_b200/) never links, imports or calls it.
  *
- * PARITY UNPINNED: the reference ships no tests and no golden vectors for the
- * TensorFlow-side arithmetic (distance matrix, top_k median, exp, gradients);
- * TensorFlow 1.12 cannot be installed here.  This file therefore restates the
- * published algorithm, following the reference line by line:
+ * Pinning: the reference ships no tests and no golden vectors, and TensorFlow
+ * 1.12 cannot be installed here.  The formulas below are checked (through
+ * oracle/svgd_oracle.py, tests/test_reference_run.py) against the reference's own
+ * library code executed on the TF1 graph-API stand-in of compat/
+ * (tests/golden/make_golden_reference_run.py) to float32 rounding.  PARITY UNPINNED
+ * at the bit level: TensorFlow's own SGEMM / exp kernels cannot be run, so the bits
+ * of D -- and with them "bit-exact median" -- are defined by the contract
+ * arithmetic stated below.  The restated algorithm, reference line by line:
  *
  *   D   = r + r^T - 2 T T^T            stein/kernels/abstract_kernel.py:33-35
  *   med = median of all n*n entries    stein/utilities/compute_median.py:4-16

@@ -6,14 +6,23 @@ function per reference function, each citing the file:line it follows.  Only
 ``--impl reference`` legs may import this module; nothing under ``stein_b200/``
 does.
 
-PARITY UNPINNED for everything that lived inside TensorFlow 1.12 in the
-reference (distance matrix, top_k median, exp, tf.gradients, tf.contrib
-distributions): the reference has no tests or golden vectors and TF 1.12 cannot
-run here.  What *is* pinned against the reference itself: the two optimizers and
-the dict<->array converters, which are pure NumPy in the reference and are
-imported from /root/reference by ``tests/golden/make_golden.py`` to generate
-``tests/golden/*.npz``; and the linear-regression example's shipped data, whose
-analytic posterior is the known answer.
+Pinning.  The reference ships no tests and no golden vectors, and TensorFlow
+1.12 cannot run here.  Pinned against THE REFERENCE'S OWN CODE, run in this
+container with the scripts under ``tests/golden/`` (outputs committed there):
+  * the two optimizers and the dict<->array converters (pure NumPy in the
+    reference): ``make_golden.py`` -> ``optimizers.npz``, ``converters.npz``;
+  * the whole library -- kernels (D, top_k median, bandwidth, K, the
+    tf.gradients-based dK and its -0.5 post-scale), compute_phi, the clip, the
+    per-particle score loop, trajectories, function_posterior -- imported
+    unmodified from /root/reference/stein and executed on the TF1 graph-API
+    stand-in of ``compat/`` (graph recorded, ops evaluated by PyTorch in fp32):
+    ``make_golden_reference_run.py`` -> ``reference_run.npz``, checked by
+    ``tests/test_reference_run.py`` to 1e-5..5e-5 (median rule: same bits);
+  * the linear-regression example's shipped data, whose analytic posterior is
+    the known answer.
+STILL UNPINNED: the float32 rounding of TensorFlow's own op kernels (SGEMM
+accumulation order, exp) -- the stand-in is not TensorFlow -- so "bit-exact
+median" is defined on the contract arithmetic below, not on a TF 1.12 run.
 
 Two flavours of the distance matrix are offered:
   * ``sqdist``        -- the literal NumPy line (BLAS sgemm; summation order is

@@ -2,10 +2,11 @@
 
 Pins: reference-generated golden vectors for the pure-NumPy parts of the
 reference (optimizers, converters; tests/golden/make_golden.py) and the analytic
-posterior of the reference's shipped linear-regression data.  Everything that
-lived inside TensorFlow in the reference is "parity unpinned" (no reference
-fixtures exist); for those the oracle is cross-checked against an independent
-autograd restatement and between its two implementations (NumPy / C).
+posterior of the reference's shipped linear-regression data.  What lived inside
+TensorFlow in the reference is pinned separately, against a run of the reference's
+own library on the TF1 stand-in (tests/test_reference_run.py); here the oracle is
+additionally cross-checked against an independent autograd restatement and between
+its two implementations (NumPy / C).
 """
 import os
 import types
