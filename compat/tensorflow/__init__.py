@@ -257,11 +257,17 @@ def placeholder(dtype=float32, shape=None, name=None):
 
 
 def _const(value, dtype=None):
+    """Python / NumPy value -> Const node: floating values become float32 (the graphs of the
+    reference are float32 throughout), integers stay integers; Tensors pass through."""
     if isinstance(value, Tensor):
         return value
-    arr = np.asarray(value, dtype=_NP_DTYPES.get(dtype, np.float32) if dtype else None)
-    if arr.dtype.kind == "f" or arr.dtype.kind in "iub" and dtype is None:
-        arr = arr.astype(np.float32) if arr.dtype.kind == "f" else arr
+    arr = np.asarray(value)
+    if dtype is not None:
+        arr = arr.astype(_NP_DTYPES.get(dtype, np.float32))
+    elif arr.dtype.kind == "f":
+        arr = arr.astype(np.float32)
+    elif arr.dtype.kind not in "iub":
+        raise TypeError("cannot convert %r to a tensor" % (value,))
     return Tensor("Const", attrs={"value": arr}, shape=arr.shape)
 
 
