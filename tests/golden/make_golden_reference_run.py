@@ -62,6 +62,22 @@ def main():
         out["kernel%d_theta" % i], out["kernel%d_K" % i], out["kernel%d_dK" % i] = theta, K, dK
         out["kernel%d_bandwidth" % i], out["kernel%d_D" % i] = bw, D
 
+    # ---- ties and dynamic range (read by the CPU oracle test only) ------------------------------
+    base = rng.standard_normal((10, 4))
+    ties = [np.repeat(base, 2, axis=0),                                        # duplicated particles
+            np.concatenate([np.zeros((5, 3)), np.ones((5, 3))]),               # two tight clusters: middle values 0 and 3
+            np.concatenate([np.zeros((5, 3)), np.ones((6, 3))]),               # degenerate: median 0 -> bandwidth 0 -> NaN
+            rng.standard_normal((21, 6)) * np.logspace(-2, 2, 21)[:, None]]    # wide range of norms, odd n*n
+    out["n_ties"] = np.array(len(ties))
+    for i, theta in enumerate(ties):
+        n = theta.shape[0]
+        tf.reset_default_graph()
+        sess = tf.Session()
+        k = ref["kernels"].SquaredExponentialKernel(n, sess)
+        K, dK = k.kernel_and_grad(theta)
+        bw = sess.run(k.bandwidth, {k.theta[j]: theta[j] for j in range(n)})
+        out["tie%d_theta" % i], out["tie%d_K" % i], out["tie%d_dK" % i], out["tie%d_bandwidth" % i] = theta, K, dK, bw
+
     # ---- compute_median on explicit inputs (even / odd length, ties) ----------------------------
     meds = [np.array([[3., 1.], [2., 5.]]), np.arange(9, dtype=np.float64).reshape(3, 3)[::-1] * 0.5,
             np.array([[0., 0., 1., 1.]]), rng.standard_normal((5, 5)), rng.standard_normal((6, 6))]

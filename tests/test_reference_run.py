@@ -35,6 +35,29 @@ def test_kernel_operator_matches_the_reference_run(ref):
         assert _rel(dK, ref["kernel%d_dK" % i]) < 1e-5
 
 
+def test_kernel_operator_with_ties_and_wide_norm_range(ref):
+    """Duplicated particles (D = 0 off the diagonal), two tight clusters (the two middle values
+    differ), norms over four decades with an odd n*n: same bandwidth, K and dK as the reference."""
+    for i in range(int(ref["n_ties"])):
+        theta = ref["tie%d_theta" % i]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            K, dK, bw = orc.kernel_and_grad(theta)
+        if float(ref["tie%d_bandwidth" % i]) == 0.0:
+            # more than half of the distances are zero: the reference divides by a zero bandwidth
+            # and returns NaN wherever D = 0 (the product refuses this input instead, engine.cu)
+            assert float(bw) == 0.0
+            assert (np.isnan(K) == np.isnan(ref["tie%d_K" % i])).all() and np.isnan(K).any()
+            assert np.array_equal(K[~np.isnan(K)], ref["tie%d_K" % i][~np.isnan(K)])
+            continue
+        assert abs(float(bw) - float(ref["tie%d_bandwidth" % i])) <= 4e-6 * float(bw), i
+        # r_i + r_j - 2 x_i.x_j in float32 carries an absolute error of a few ulp(max r) whatever
+        # the summation order; it reaches K through exp(-D / 2h^2)
+        rmax = float((theta.astype(np.float32) ** 2).sum(axis=1).max())
+        atol = 5e-6 + 8.0 * 2.0 ** -24 * rmax / float(bw) ** 2
+        assert np.abs(K - ref["tie%d_K" % i]).max() < atol, i
+        assert _rel(dK, ref["tie%d_dK" % i]) < 2e-5, i
+
+
 def test_median_rule_matches_the_reference_run(ref):
     """stein/utilities/compute_median.py:4-16 (top_k with k = n*n/2 + 1; mean of the two middle
     values for an even count): identical values in, identical bits out."""
