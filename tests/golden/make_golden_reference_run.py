@@ -63,11 +63,12 @@ def main():
         out["kernel%d_bandwidth" % i], out["kernel%d_D" % i] = bw, D
 
     # ---- ties and dynamic range (read by the CPU oracle test only) ------------------------------
-    base = rng.standard_normal((10, 4))
+    rng_t = np.random.default_rng(77)        # own stream: the draws of the other cases do not move
+    base = rng_t.standard_normal((10, 4))
     ties = [np.repeat(base, 2, axis=0),                                        # duplicated particles
             np.concatenate([np.zeros((5, 3)), np.ones((5, 3))]),               # two tight clusters: middle values 0 and 3
             np.concatenate([np.zeros((5, 3)), np.ones((6, 3))]),               # degenerate: median 0 -> bandwidth 0 -> NaN
-            rng.standard_normal((21, 6)) * np.logspace(-2, 2, 21)[:, None]]    # wide range of norms, odd n*n
+            rng_t.standard_normal((21, 6)) * np.logspace(-2, 2, 21)[:, None]]    # wide range of norms, odd n*n
     out["n_ties"] = np.array(len(ties))
     for i, theta in enumerate(ties):
         n = theta.shape[0]
