@@ -1,5 +1,5 @@
 #!/bin/bash
-# 2-GPU visit: oracle check, bench with the peer-memory all-reduces, bench with NCCL all-reduces
+# 4-GPU visit: oracle check, bench with the peer-memory all-reduces, bench with NCCL all-reduces
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1"
 timeout 300 $TR --master-port 29511 tools/multi_gpu_check.py > gpurun_out/mgc4.log 2>&1; echo "mgc_rc=$?"
