@@ -40,17 +40,20 @@ extern "C" {
 #define STEIN_ERR_COMM (-5)        /* a collective hook failed                    */
 #define STEIN_ERR_INTERNAL (-6)
 
-#define STEIN_ABI_VERSION 1
+#define STEIN_ABI_VERSION 2
 
-/* phi-kernel implementations (stein_ctx_set_phi_impl).  AUTO: leading dimension 256 -> FLASH_TC4,
- * 128 -> FLASH_TC, anything else -> DENSE_SIMT (the engine pads the rows of >= 2048 particles of up
+/* phi-kernel implementations (stein_ctx_set_phi_impl).  AUTO: leading dimension 256 -> the CTA-pair
+ * kernel, FLASH_TC4 (fast) or FLASH_TC5 (precise) picked per call ON THE DEVICE from the conditioning
+ * of the cloud (stein_ctx_phi_route); 128 -> FLASH_TC; 512 / 768 / 1024 -> the panel kernels
+ * (FLASH_PANEL); anything else -> DENSE_SIMT (the engine pads the rows of >= 2048 particles of up
  * to 256 coordinates to 128 / 256 floats). */
 #define STEIN_PHI_AUTO 0
 #define STEIN_PHI_DENSE_SIMT 1 /* materialises K for the local row block; FP32 FFMA */
 #define STEIN_PHI_FLASH_TC 2   /* tcgen05/TMEM/TMA fused kernel; never stores K   */
 #define STEIN_PHI_FLASH_TC2 3  /* same, CTA pairs (cta_group::2, M = 256); d <= 256 padded to 256 */
 #define STEIN_PHI_FLASH_TC3 4  /* CTA pairs, GEMM2 as one FP16 pass + two FP8 passes instead of 3 BF16 */
-#define STEIN_PHI_FLASH_TC4 5  /* CTA pairs, both GEMMs as FP16 + 2 x FP8 */
+#define STEIN_PHI_FLASH_TC4 5  /* CTA pairs, both GEMMs as FP16 + 2 x FP8 ("fast" route) */
+#define STEIN_PHI_FLASH_TC5 6  /* CTA pairs, both GEMMs as 3 x FP16 on a 2-term split ("precise" route, fp32-Gram accuracy) */
 
 /* median implementations (stein_ctx_set_median_impl).  AUTO: n <= 2048 -> all n*n keys once and a
  * device-side select; leading dimension 128 / 256 and n*n >= 2^24 -> TC; otherwise FFMA. */
@@ -102,6 +105,15 @@ int stein_ctx_set_median_impl(stein_ctx *ctx, int impl);
 const char *stein_last_error(const stein_ctx *ctx /* NULL = last error of any ctx */);
 /* number of kernels of this library launched on ctx since creation */
 int64_t stein_ctx_launch_count(const stein_ctx *ctx);
+
+/* Which route the last guarded phi call took on this context (synchronises the stream):
+ * *route = 0 fast (FLASH_TC4), 1 precise (FLASH_TC5), -1 no guarded call yet;
+ * *kappa = max_i |x_i - mean|^2 / h^2 of that call's cloud; *predicted_fast_error = the guard's
+ * estimate of the relative error of phi on the fast route (the precise route is taken when it
+ * exceeds the tolerance, default 5e-5, stein_ctx_set_phi_guard_tol / env STEIN_PHI_GUARD_TOL).
+ * No reference counterpart: the reference evaluates stein/kernels/abstract_kernel.py:33-35 in fp32. */
+int stein_ctx_phi_route(stein_ctx *ctx, int32_t *route, float *kappa, float *predicted_fast_error);
+int stein_ctx_set_phi_guard_tol(stein_ctx *ctx, float tol);
 
 /* Optional per-region device timing (CUDA events on the ctx stream), used by
  * bench.py for the live roofline figure.  Regions: 0 = phi main kernel(s),
@@ -264,6 +276,14 @@ int stein_engine_set_scores(stein_engine *eng, const void *S_host, int is_f64);
 int stein_engine_get_phi(stein_engine *eng, void *phi_host, int is_f64);
 /* one update_particles() on the scores currently in the engine's S buffer     */
 int stein_engine_step(stein_engine *eng);
+/* compute_phi() only (abstract_stein_sampler.py:100-105) on the scores in the S buffer: all-gathers,
+ * median / bandwidth, phi into the engine's phi buffer (stein_engine_get_phi), sum(phi^2) all-reduced
+ * -- no clip, no optimizer step.  For callers that bring their own AbstractGradientDescent
+ * (stein/optimizers/abstract_gradient_descent.py:32-52). */
+int stein_engine_phi_only(stein_engine *eng);
+/* optimizer hyper-parameters for the following steps (the reference reads learning_rate / decay /
+ * betas from the gd object at every update(), adam_gradient_descent.py:41-58) */
+int stein_engine_set_hyper(stein_engine *eng, double learning_rate, double decay, double p1, double p2);
 /* the host-buffer drop-in: H2D scores -> step -> D2H particles (X_host_out may
  * be NULL to leave the particles on the device)                               */
 int stein_engine_update_particles_host(stein_engine *eng, const void *S_host, void *X_host_out,

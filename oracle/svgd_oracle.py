@@ -289,6 +289,25 @@ def score_logistic(theta, X, y, n_train, a=1.0, b=0.01):
     return np.concatenate([gw, gla[:, None]], axis=1)
 
 
+def score_gmm(theta, means=None, sigma2=1.0):
+    """Score of the synthetic targets of BASELINE.json configs D / E: an
+    equal-weight mixture of isotropic Gaussians N(mu_k, sigma2 I),
+        S_i = sum_k r_ik (mu_k - x_i) / sigma2,   r_ik = softmax_k(-|x_i - mu_k|^2 / (2 sigma2)).
+    means=None: the standard normal target, S = -X / sigma2.  float64 throughout (a closed form,
+    not a reference function: the reference has no such model; the role is that of the per-particle
+    tf.gradients(log_p) loop of stein/samplers/stein_sampler.py:59-68)."""
+    X = np.asarray(theta, np.float64)
+    if means is None:
+        return -X / sigma2
+    M = np.asarray(means, np.float64)
+    d2 = ((X[:, None, :] - M[None, :, :]) ** 2).sum(-1)
+    logit = -d2 / (2.0 * sigma2)
+    logit -= logit.max(axis=1, keepdims=True)
+    R = np.exp(logit)
+    R /= R.sum(axis=1, keepdims=True)
+    return (R @ M - X) / sigma2
+
+
 def bnn_unpack(theta, F, H):
     """Flat layout of examples/regression_neural_network/main.py:35-42 under the
     name sort of converters.py:40: [log_lambda, log_gamma, w1 (F*H), b1 (H),

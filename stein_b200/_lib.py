@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstein_b200.so")
 
 STEIN_OK = 0
-PHI_AUTO, PHI_DENSE_SIMT, PHI_FLASH_TC, PHI_FLASH_TC2, PHI_FLASH_TC3, PHI_FLASH_TC4 = 0, 1, 2, 3, 4, 5
+PHI_AUTO, PHI_DENSE_SIMT, PHI_FLASH_TC, PHI_FLASH_TC2, PHI_FLASH_TC3, PHI_FLASH_TC4, PHI_FLASH_TC5 = 0, 1, 2, 3, 4, 5, 6
 OPT_ADAM, OPT_ADAGRAD = 0, 1
 MEDIAN_AUTO, MEDIAN_FFMA, MEDIAN_TC, MEDIAN_TC1 = 0, 1, 2, 3
 
@@ -45,6 +45,8 @@ SIGNATURES = {
     "stein_ctx_set_median_impl": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "stein_last_error": (ctypes.c_char_p, [c_vp]),
     "stein_ctx_launch_count": (c_i64, [c_vp]),
+    "stein_ctx_phi_route": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_f32), ctypes.POINTER(c_f32)]),
+    "stein_ctx_set_phi_guard_tol": (ctypes.c_int, [c_vp, c_f32]),
     "stein_ctx_profile_enable": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "stein_ctx_profile_read": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64)]),
     "stein_ld": (c_i64, [c_i64]),
@@ -93,6 +95,8 @@ SIGNATURES = {
     "stein_engine_set_scores": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int]),
     "stein_engine_get_phi": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int]),
     "stein_engine_step": (ctypes.c_int, [c_vp]),
+    "stein_engine_phi_only": (ctypes.c_int, [c_vp]),
+    "stein_engine_set_hyper": (ctypes.c_int, [c_vp, c_f64, c_f64, c_f64, c_f64]),
     "stein_engine_update_particles_host": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int]),
     "stein_engine_ipc_handle": (ctypes.c_int, [c_vp, c_vp]),
     "stein_engine_set_peer_handles": (ctypes.c_int, [c_vp, c_vp]),
@@ -120,7 +124,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError = header/library mismatch
         fn.restype, fn.argtypes = res, args
-    if lib.stein_abi_version() != 1:
+    if lib.stein_abi_version() != 2:
         raise SteinLibraryError("libstein_b200.so ABI version mismatch")
     _lib = lib
     return lib

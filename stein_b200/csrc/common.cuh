@@ -48,6 +48,10 @@ struct stein_ctx {
         int64_t n_total, n_local, d;
         int mode;
     } xprep{nullptr, nullptr, 0, 0, 0, 0};
+    // phi route guard (phi_tc.cu): device words [route, kappa, predicted error of the fast route]
+    // of the last guarded phi call, and the predicted error up to which the fast route is taken
+    int *d_route = nullptr;
+    float phi_guard_tol = 5.0e-5f;
     int64_t launches = 0;
     std::string error;
     // pinned host staging + device scratch for the median loop

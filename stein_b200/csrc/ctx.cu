@@ -1,5 +1,6 @@
 // ctx.cu -- context lifetime, error text, collective hooks, phi dispatch.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "phi_common.cuh"
 
@@ -40,6 +41,15 @@ int stein_ctx_create(stein_ctx **out, int device, void *cuda_stream) {
                     cudaGetErrorString(e));
     if (device < 0 || device >= count)
         return fail(nullptr, STEIN_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+    // One process drives ONE GPU: the library keeps per-process device scratch (median arena, select
+    // state, slot plan) and per-device function attributes.  A context on a second device of the
+    // same process would use buffers that live on the first one -- refuse it loudly.
+    static int process_device = -1;
+    if (process_device >= 0 && process_device != device)
+        return fail(nullptr, STEIN_ERR_UNSUPPORTED,
+                    "this process already drives CUDA device %d: libstein_b200 supports one GPU per process "
+                    "(launch one process per GPU, e.g. torchrun); device %d refused", process_device, device);
+    process_device = device;
     stein_ctx *ctx = new stein_ctx();
     ctx->device = device;
     e = cudaSetDevice(device);
@@ -57,6 +67,10 @@ int stein_ctx_create(stein_ctx **out, int device, void *cuda_stream) {
     }
     ctx->num_sms = prop.multiProcessorCount;
     ctx->stream = (cudaStream_t)cuda_stream;
+    if (const char *tol = getenv("STEIN_PHI_GUARD_TOL")) {
+        const float v = (float)atof(tol);
+        if (v >= 0.0f) ctx->phi_guard_tol = v;
+    }
     *out = ctx;
     return STEIN_OK;
 }
@@ -70,6 +84,7 @@ int stein_ctx_destroy(stein_ctx *ctx) {
     if (ctx->d_pilot_keys) cudaFree(ctx->d_pilot_keys);
     if (ctx->d_sel) cudaFree(ctx->d_sel);
     if (ctx->h_sel) cudaFreeHost(ctx->h_sel);
+    if (ctx->d_route) cudaFree(ctx->d_route);
     for (int r = 0; r < 2; ++r)
         for (auto &ev : ctx->prof_events[r]) ctx->prof_pool.push_back(ev);
     for (auto &ev : ctx->prof_pool) {
@@ -103,7 +118,7 @@ int stein_ctx_set_comm(stein_ctx *ctx, const stein_comm *comm) {
 
 int stein_ctx_set_phi_impl(stein_ctx *ctx, int impl) {
     STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
-    STEIN_REQUIRE(ctx, impl >= STEIN_PHI_AUTO && impl <= STEIN_PHI_FLASH_TC4, "unknown phi impl %d", impl);
+    STEIN_REQUIRE(ctx, impl >= STEIN_PHI_AUTO && impl <= STEIN_PHI_FLASH_TC5, "unknown phi impl %d", impl);
     ctx->phi_impl = impl;
     return STEIN_OK;
 }
@@ -144,9 +159,34 @@ int stein_ctx_profile_read(stein_ctx *ctx, int region, double *ms_total, int64_t
 
 int64_t stein_ctx_launch_count(const stein_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int stein_ctx_phi_route(stein_ctx *ctx, int32_t *route, float *kappa, float *predicted_fast_error) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    int32_t words[4] = {-1, 0, 0, 0};
+    if (ctx->d_route) {
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(words, ctx->d_route, 12, cudaMemcpyDeviceToHost, ctx->stream));
+        STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (route) *route = words[0];
+    if (kappa) memcpy(kappa, &words[1], 4);
+    if (predicted_fast_error) memcpy(predicted_fast_error, &words[2], 4);
+    return STEIN_OK;
+}
+
+int stein_ctx_set_phi_guard_tol(stein_ctx *ctx, float tol) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    STEIN_REQUIRE(ctx, tol >= 0.0f, "tolerance must be >= 0");
+    ctx->phi_guard_tol = tol;
+    return STEIN_OK;
+}
+
+// internal: CTA-pair kernel, fast (FLASH_TC4) or precise (FLASH_TC5) route picked on the device by the
+// conditioning guard -- what STEIN_PHI_AUTO resolves to for a leading dimension of 256
+constexpr int PHI_FLASH_GUARDED = STEIN_PHI_FLASH_TC5 + 1;
+static bool is_pair_impl(int impl) { return impl >= STEIN_PHI_FLASH_TC2 && impl <= PHI_FLASH_GUARDED; }
+
 static int pick_phi_impl(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
     if (ctx->phi_impl != STEIN_PHI_AUTO) return ctx->phi_impl;
-    if (flash_tc2_supported(ctx, n_local, n_total, d)) return STEIN_PHI_FLASH_TC4;   // d padded to 256: CTA pairs, FP16 + 2 x FP8 passes per GEMM
+    if (flash_tc2_supported(ctx, n_local, n_total, d)) return PHI_FLASH_GUARDED;
     return flash_tc_supported(ctx, n_local, n_total, d) ? STEIN_PHI_FLASH_TC : STEIN_PHI_DENSE_SIMT;
 }
 
@@ -173,13 +213,14 @@ int stein_phi(stein_ctx *ctx, const float *X_all_dev, const float *S_all_dev, co
     const float h2 = bandwidth * bandwidth;  // squared_exponential_kernel.py:22 tf.square(bandwidth)
     // A leading dimension of 128 / 256 makes the matrix eligible for the tensor-core kernels
     // whatever d is: the zero pad columns are then simply treated as coordinates.
+    const int64_t d_true = d;
     if ((ld == 128 || ld == 256) && d < ld) d = ld;
     const int impl = pick_phi_impl(ctx, n_local, n_total, d);
-    if (impl == STEIN_PHI_FLASH_TC2 || impl == STEIN_PHI_FLASH_TC3 || impl == STEIN_PHI_FLASH_TC4) {
+    if (is_pair_impl(impl)) {
         if (!flash_tc2_supported(ctx, n_local, n_total, d))
             return fail(ctx, STEIN_ERR_UNSUPPORTED, "CTA-pair flash phi does not take n=%lld d=%lld",
                         (long long)n_total, (long long)d);
-        return phi_flash_tc2(ctx, X_all_dev, S_all_dev, r_all_dev, n_total, d, ld, row_begin, n_local, h2,
+        return phi_flash_tc2(ctx, X_all_dev, S_all_dev, r_all_dev, n_total, d, d_true, ld, row_begin, n_local, h2,
                              workspace_dev, workspace_bytes, phi_dev, sumsq_dev, impl - STEIN_PHI_FLASH_TC2);
     }
     if (impl == STEIN_PHI_FLASH_TC) {
@@ -201,8 +242,7 @@ int phi_prepare_x(stein_ctx *ctx, const float *X_all, int64_t n_total, int64_t d
                   void *ws, int64_t ws_bytes) {
     if ((ld == 128 || ld == 256) && d < ld) d = ld;
     const int impl = pick_phi_impl(ctx, n_local, n_total, d);
-    if ((impl == STEIN_PHI_FLASH_TC2 || impl == STEIN_PHI_FLASH_TC3 || impl == STEIN_PHI_FLASH_TC4) &&
-        flash_tc2_supported(ctx, n_local, n_total, d))
+    if (is_pair_impl(impl) && flash_tc2_supported(ctx, n_local, n_total, d))
         return flash_tc2_prepare_x(ctx, X_all, n_total, d, ld, n_local, ws, ws_bytes, impl - STEIN_PHI_FLASH_TC2);
     return STEIN_OK;
 }

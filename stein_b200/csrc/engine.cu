@@ -48,6 +48,8 @@ struct stein_engine {
     // IPC handle exports both; peer_reduce is what the context uses while the peers are open
     int64_t mbox_offset = 0;
     stein::PeerReduce *peer_reduce = nullptr;
+    unsigned long long mbox_epoch = 0;   // all-reduces issued through the mailbox so far: survives a close / re-open
+                                         // of the peers (the flags in the mailboxes keep the old epochs)
     uintptr_t uid = 0;      // unique per engine ever created in the process (median window hint owner)
     float last_med = 0.f, last_bw = 0.f;
     float fixed_bw = 0.f;   // > 0: use this bandwidth instead of the median heuristic
@@ -190,6 +192,7 @@ int stein_engine_create(stein_engine **out, stein_ctx *ctx, int64_t n_total, int
 static void release_peer_reduce(stein_engine *e) {
     if (!e->peer_reduce) return;
     if (e->ctx->peer_reduce == e->peer_reduce) e->ctx->peer_reduce = nullptr;
+    e->mbox_epoch = peer_reduce_epoch(e->peer_reduce);
     peer_reduce_destroy(e->peer_reduce);
     e->peer_reduce = nullptr;
 }
@@ -314,8 +317,8 @@ static int step_bandwidth(stein_engine *e, float *bw_out) {
     return STEIN_OK;
 }
 
-// Phase 2 needs the scores: (all-gather S,) phi, clip, optimizer step.
-static int step_update(stein_engine *e, float bw, bool scores_gathered) {
+// Phase 2a needs the scores: (all-gather S,) phi for the local rows and the global sum(phi^2).
+static int step_phi(stein_engine *e, float bw, bool scores_gathered) {
     stein_ctx *ctx = e->ctx;
     if (e->world > 1 && !scores_gathered) {
         const int64_t cnt = e->q * e->ld;
@@ -326,6 +329,13 @@ static int step_update(stein_engine *e, float bw, bool scores_gathered) {
     STEIN_TRY(stein_phi(ctx, e->X_all, e->S_all, e->r_all, e->n_total, e->d, e->ld, e->row_begin,
                         std::max<int64_t>(e->n_local, 1), bw, e->ws, e->ws_bytes, e->phi, e->sumsq));
     if (e->world > 1) STEIN_TRY(allreduce_f64(ctx, e->sumsq, 1));
+    return STEIN_OK;
+}
+
+// Phase 2: phi, clip, optimizer step.
+static int step_update(stein_engine *e, float bw, bool scores_gathered) {
+    stein_ctx *ctx = e->ctx;
+    STEIN_TRY(step_phi(e, bw, scores_gathered));
     // abstract_stein_sampler.py:125-126
     const int64_t count = e->q * e->ld;
     // peers: the same rows inside the other ranks' X_all.  Safe to overwrite now: the all-reduce
@@ -404,6 +414,24 @@ int stein_engine_update_particles_host(stein_engine *e, const void *S_host, void
     return STEIN_OK;
 }
 
+int stein_engine_phi_only(stein_engine *e) {
+    if (!e) return STEIN_ERR_INVALID;
+    stein_ctx *ctx = e->ctx;
+    STEIN_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    float bw = 0.f;
+    STEIN_TRY(step_bandwidth(e, &bw));
+    return step_phi(e, bw, false);
+}
+
+int stein_engine_set_hyper(stein_engine *e, double learning_rate, double decay, double p1, double p2) {
+    if (!e) return STEIN_ERR_INVALID;
+    e->lr = learning_rate;
+    e->decay = decay;
+    e->p1 = p1;
+    e->p2 = p2;
+    return STEIN_OK;
+}
+
 int stein_engine_set_bandwidth(stein_engine *e, float bandwidth) {
     if (!e) return STEIN_ERR_INVALID;
     if (!(bandwidth >= 0.0f) || bandwidth > 3.0e38f)
@@ -468,7 +496,7 @@ int stein_engine_set_peer_handles(stein_engine *e, const void *handles) {
         void *boxes[MAX_PEERS + 1];
         for (int r = 0; r < e->world; ++r)
             boxes[r] = reinterpret_cast<char *>(r == e->rank ? e->X_all : e->peer_X[r]) + e->mbox_offset;
-        STEIN_TRY(peer_reduce_create(ctx, e->rank, e->world, boxes, &e->peer_reduce));
+        STEIN_TRY(peer_reduce_create(ctx, e->rank, e->world, boxes, e->mbox_epoch, &e->peer_reduce));
         ctx->peer_reduce = e->peer_reduce;
     }
     // the zero-fill of this rank's mailbox (engine creation) must be over before a peer writes

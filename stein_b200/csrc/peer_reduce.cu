@@ -80,20 +80,28 @@ mbox_allreduce_kernel(T *__restrict__ buf, int count, const MboxPtrs mb, int ran
         }
     }
     __syncthreads();
-    // 4. the slots in rank order (L2 loads: the lines were written by other GPUs)
+    // 4. the slots in rank order (L2 loads: the lines were written by other GPUs).  After a timeout
+    // the slots are not trustworthy: the result is poisoned (all bits set: NaN / a count no bracket
+    // check accepts) and the host reports the error word at its next look.
+    const bool dead = *reinterpret_cast<volatile int *>(err) != 0;
     const T *src = reinterpret_cast<const T *>(mb.base[rank] + pbase + MB_FLAGS);
     for (int i = i0 + (int)threadIdx.x; i < i1; i += (int)blockDim.x) {
         T s = __ldcg(src + i);
         for (int r = 1; r < world; ++r) s += __ldcg(src + (size_t)r * MB_CAP + i);
+        if (dead) memset(&s, 0xff, sizeof(T));
         buf[i] = s;
     }
 }
 
-int peer_reduce_create(stein_ctx *ctx, int rank, int world, void *const *mailboxes, PeerReduce **out) {
+unsigned long long peer_reduce_epoch(const PeerReduce *pr) { return pr ? pr->epoch : 0ull; }
+
+int peer_reduce_create(stein_ctx *ctx, int rank, int world, void *const *mailboxes, unsigned long long epoch0,
+                       PeerReduce **out) {
     STEIN_REQUIRE(ctx, world >= 2 && world <= MB_RANKS && rank >= 0 && rank < world, "peer reduce: bad rank/world");
     PeerReduce *pr = new PeerReduce();
     pr->rank = rank;
     pr->world = world;
+    pr->epoch = epoch0;
     for (int r = 0; r < world; ++r) pr->mb.base[r] = static_cast<unsigned long long *>(mailboxes[r]);
     cudaError_t err = cudaHostAlloc((void **)&pr->h_error, sizeof(int), cudaHostAllocMapped);
     if (err == cudaSuccess) {

@@ -14,7 +14,11 @@ constexpr size_t MBOX_BYTES = 2 * MB_PARITY_WORDS * 8;
 
 struct PeerReduce;
 // mailboxes[r]: rank r's mailbox as mapped on this GPU (own one included)
-int peer_reduce_create(stein_ctx *ctx, int rank, int world, void *const *mailboxes, PeerReduce **out);
+// epoch0: all-reduces already issued through these mailboxes (0 for fresh, zeroed mailboxes): the flags
+// hold epoch numbers, so a re-opened connection must keep counting where the last one stopped
+int peer_reduce_create(stein_ctx *ctx, int rank, int world, void *const *mailboxes, unsigned long long epoch0,
+                       PeerReduce **out);
+unsigned long long peer_reduce_epoch(const PeerReduce *pr);
 void peer_reduce_destroy(PeerReduce *pr);
 
 }  // namespace stein

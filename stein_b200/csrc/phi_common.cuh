@@ -29,9 +29,12 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
 
 // CTA-pair (cta_group::2) variant, d padded to 256 only
 bool flash_tc2_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d);
+// mode 0: BF16x3; 1: mixed-precision GEMM2; 2: mixed precision for both GEMMs (fast); 3: FP16x3 for both
+// (precise); 4: fast or precise, picked on the device from the conditioning of the cloud.  d_true = number
+// of real coordinates (d may have been promoted to the leading dimension).
 int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all,
-                  int64_t n_total, int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2,
-                  void *ws, int64_t ws_bytes, float *phi, double *sumsq, int mode);
+                  int64_t n_total, int64_t d, int64_t d_true, int64_t ld, int64_t row_begin, int64_t n_local,
+                  float h2, void *ws, int64_t ws_bytes, float *phi, double *sumsq, int mode);
 // the bandwidth-independent kernels of phi_flash_tc2, enqueued ahead of the call (ctx->xprep)
 int flash_tc2_prepare_x(stein_ctx *ctx, const float *X_all, int64_t n_total, int64_t d, int64_t ld,
                         int64_t n_local, void *ws, int64_t ws_bytes, int mode);

@@ -497,7 +497,8 @@ struct Flash2Params {
     int nI2;              // row pair-tiles (256 particles)
     int row_pair0;        // (unused)
     long long row_begin;  // first global particle row of the local block (multiple of 128)
-    const float *c1mul;   // device: factor on c1 that undoes the power-of-two scaling of X (G1F8), or NULL
+    const float *c1mul;   // device: factor on c1 that undoes the power-of-two scaling of X (scaled modes), or NULL
+    const int *route;     // device: route picked by phi_guard_kernel (0 fast / 1 precise), or NULL = run unconditionally
     float c1;
     const float *nrm;
     SlotLayout out;
@@ -514,15 +515,25 @@ struct Seg2Iter : SegWalk {   // same schedule as SegIter, over cluster pairs an
 // (a8l = e4m3((x - x16) 2^12), a8h = e4m3(x16), b8h = e5m2(x16 2^-12), b8l = e5m2(x - x16);
 // y8h = e5m2(y16 2^-12), y8l = e5m2(y - y16)).
 struct Phi2Maps {
-    CUtensorMap xa_hi, xa_lo, xb_hi, xb_lo, a8l, a8h, b8h, b8l, yh, yl, y8h, y8l;
+    CUtensorMap xa_hi, xa_lo, xb_hi, xb_lo, a8l, a8h, b8h, b8l, yh, yl, y8h, y8l, yx;
 };
 
-// G1F8 / G2F8 = true: that GEMM runs as one FP16 pass plus two FP8 passes ("mixed precision")
-// instead of three BF16 passes: the FP16 product carries 11 bits of each factor, the two cross
-// terms are 2^-12 relative and only need the 3-4 bits FP8 gives them.
-template <bool G1F8, bool G2F8>
+// Arithmetic of GEMM1 (G1) / GEMM2 (G2):
+//   0  three BF16 passes (hi.hi + lo.hi + hi.lo, ~2^-17);
+//   1  "mixed precision": one FP16 pass plus two FP8 passes -- the FP16 product carries 11 bits of
+//      each factor, the two cross terms are 2^-12 relative and only need the 3-4 bits FP8 gives them
+//      (~2^-16, two BF16-pass equivalents of tensor time: the fast route);
+//   2  "precise": three FP16 passes on a 2-term FP16 split (hi.hi + lo.hi + hi.lo, ~2^-22 -- the
+//      accuracy of an fp32 Gram matrix; the route for badly conditioned clouds, see phi_guard_kernel).
+//      GEMM2: the residual of P is scaled by 2^12 (FP16 has 5 exponent bits) and meets a copy of
+//      Y16 scaled by 2^-12, so all three products land on the same scale in the accumulator.
+template <int G1, int G2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FL_THREADS, 1)
 flash_phi2_kernel(const __grid_constant__ Phi2Maps maps, const Flash2Params p) {
+    constexpr bool G1F8 = G1 == 1, G2F8 = G2 == 1, G1H = G1 == 2, G2H = G2 == 2;
+    // device-side route selection: both candidate kernels are enqueued, the one that was not
+    // picked leaves at once (uniformly: no barrier, TMEM or cluster state has been touched)
+    if (p.route != nullptr && *p.route != (G1H ? 1 : 0)) return;
     const CUtensorMap &mapXh = maps.xa_hi, &mapXl = maps.xa_lo, &mapXh64 = maps.xb_hi, &mapXl64 = maps.xb_lo;
     const CUtensorMap &mapYh = maps.yh, &mapYl = maps.yl, &mapY8h = maps.y8h, &mapY8l = maps.y8l;
     extern __shared__ uint8_t smem_raw[];
@@ -571,6 +582,7 @@ flash_phi2_kernel(const __grid_constant__ Phi2Maps maps, const Flash2Params p) {
             tma_prefetch_desc(&mapY8l);
         } else {
             tma_prefetch_desc(&mapYl);
+            if (G2H) tma_prefetch_desc(&maps.yx);
         }
     }
     if (warp == 1) tmem_alloc_pair(tmem_slot, TMEM_COLS);
@@ -659,9 +671,10 @@ flash_phi2_kernel(const __grid_constant__ Phi2Maps maps, const Flash2Params p) {
                         emit_y(&mapYh, j * 128 + 64);
                         emit_y(&mapY8h, j * 128);
                         emit_y(&mapY8l, j * 128);
-                    } else {          // per 64-particle block: BF16 hi, then lo
+                    } else {          // per 64-particle block: hi, (precise: hi 2^-12,) then lo
                         for (int kb2 = 0; kb2 < 2; ++kb2) {
                             emit_y(&mapYh, j * 128 + kb2 * 64);
+                            if (G2H) emit_y(&maps.yx, j * 128 + kb2 * 64);
                             emit_y(&mapYl, j * 128 + kb2 * 64);
                         }
                     }
@@ -679,8 +692,8 @@ flash_phi2_kernel(const __grid_constant__ Phi2Maps maps, const Flash2Params p) {
         // The whole warp runs the loop in uniform control flow (descriptors stay in uniform
         // registers, every tcgen05.mma is one UTCHMMA); one elected lane issues.
         {
-            const uint32_t idesc1 = make_idesc(FMT_BF16, 256, 128);   // GEMM1: M = 256 (pair), N = 128
-            const uint32_t idesc2 = make_idesc(FMT_BF16, 256, 256);   // GEMM2: N = 256
+            const uint32_t idesc1 = make_idesc(G1H ? FMT_F16 : FMT_BF16, 256, 128);   // GEMM1: M = 256 (pair), N = 128
+            const uint32_t idesc2 = make_idesc(G2H ? FMT_F16 : FMT_BF16, 256, 256);   // GEMM2: N = 256
             int stage = 0;
             uint32_t phase = 0;
             long long jj = 0, oc = 0;
@@ -788,6 +801,25 @@ flash_phi2_kernel(const __grid_constant__ Phi2Maps maps, const Flash2Params p) {
                         __syncwarp();
                         advance();
                     }
+                } else if (G2H) {
+                    // precise GEMM2: P16.Y16 + (P - P16) 2^12 . Y16 2^-12 + P16.(Y - Y16), all FP16
+#pragma unroll 1
+                    for (int kb2 = 0; kb2 < 2; ++kb2) {
+#pragma unroll 1
+                        for (int part = 0; part < 3; ++part) {   // ring slots: Y16, Y16 2^-12, Y - Y16
+                            const uint64_t bdesc = make_kmajor_sw128_desc(next_unit());
+                            if (elect_one_sync()) {
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; ++k4)
+                                    umma2_f16_ts(tmem, a_base + p_hi_col(kb2 * 4 + k4) + (part == 1 ? 16 : 0), bdesc + 2 * k4,
+                                                 idesc2, !(first_of_chunk && kb2 == 0 && part == 0 && k4 == 0));
+                                tcgen05_commit_pair(&bars->empty[stage]);
+                                if (kb2 == 1 && part == 2 && last_of_chunk) tcgen05_commit_pair(&bars->o_full);
+                            }
+                            __syncwarp();
+                            advance();
+                        }
+                    }
                 } else {
 #pragma unroll 1
                 for (int kb2 = 0; kb2 < 2; ++kb2) {
@@ -859,7 +891,7 @@ flash_phi2_kernel(const __grid_constant__ Phi2Maps maps, const Flash2Params p) {
         int t, j0, j1, slot;
         long long jj = 0, oc = 0;
         // GEMM1 of the mixed-precision mode works on X 2^-e: S carries 2^-2e, undone here (exact)
-        const float c1 = G1F8 ? p.c1 * __ldg(p.c1mul) : p.c1;
+        const float c1 = (G1F8 || G1H) ? p.c1 * __ldg(p.c1mul) : p.c1;
         float acc[ocols];
         while (it.next(t, j0, j1, slot)) {
             const size_t grow = (size_t)p.row_begin + ((size_t)t * 2 + rank) * 128 + row;   // global particle row
@@ -903,6 +935,11 @@ flash_phi2_kernel(const __grid_constant__ Phi2Maps maps, const Flash2Params p) {
                                 w[16 + (c2 >> 1)] = pl;
                                 w[24 + (c2 >> 1)] = ph;
                             }
+                        } else if (G2H) {
+                            // words 0..15: P as FP16 pairs; 16..31: FP16 pairs of (P - P16) 2^12
+                            const uint32_t wh = pack_f16x2(e0, e1);
+                            w[c2] = wh;
+                            w[16 + c2] = pack_f16x2((e0 - f16_lo_to_f32(wh)) * 4096.0f, (e1 - f16_hi_to_f32(wh)) * 4096.0f);
                         } else {
                             const uint32_t wh = pack_bf16x2(e0, e1);
                             const float h0 = __uint_as_float(wh << 16), h1 = __uint_as_float(wh & 0xffff0000u);
@@ -1188,6 +1225,114 @@ __global__ void prep_x8_kernel(const float *__restrict__ X, const float *__restr
         reinterpret_cast<uint32_t *>(B8l)[e] = tc::pack_e5m2x2(lo[0], lo[1]) | (tc::pack_e5m2x2(lo[2], lo[3]) << 16);
     }
     if (e < nrm_rows) nrm[e] = (e < n) ? -r[e] * half_l2e_over_h2 : -INFINITY;
+}
+
+
+// ---- conditioning guard ---------------------------------------------------------------------
+// What limits the tensor-core routes is not the size of the cloud but its CONDITIONING: the error
+// of GEMM1 is relative to |x_i||x_j| (centred), the quantity that matters is D_ij / h^2, and the
+// repulsive term sum_j K_ij (x_i - x_j) is formed as a difference of two sums of size |x_i|.
+// With kappa = max_i |x_i - mean|^2 / h^2 the error of phi is about
+//     fast route     1.0e-5 kappa / sqrt(d)  (FP8 cross terms of GEMM1)  +  7.6e-6 sqrt(kappa)  (GEMM2)
+//     precise route  (the fp32 Gram form itself: ~2^-22 kappa)
+// (constants measured on the hardware, tools/phi_conditioning_study.py; a single Gaussian cloud has
+// kappa ~ 7, two tight clusters 10^2 .. 10^4).  The guard picks the fast route while its predicted
+// error stays below `tol` and the precise route otherwise, on the device, with no host round trip;
+// both candidate kernels are enqueued and the one not picked returns at once.
+// out: route[0] = 0 fast / 1 precise; diag[0] = kappa, diag[1] = predicted error of the fast route
+__global__ void __launch_bounds__(1024)
+phi_guard_kernel(const float *__restrict__ rc, int64_t n, float h2, float d_true, float tol, int *__restrict__ route,
+                 float *__restrict__ diag) {
+    __shared__ float red[32];
+    float m = 0.0f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, rc[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = red[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) {
+            const float kappa = m / h2;
+            const float pred = 1.0e-5f * kappa * rsqrtf(fmaxf(d_true, 1.0f)) + 7.6e-6f * sqrtf(kappa);
+            route[0] = (pred <= tol) ? 0 : 1;     // NaN / inf -> precise
+            diag[0] = kappa;
+            diag[1] = pred;
+        }
+    }
+}
+
+// X operands for the route that was picked (route == NULL: `forced`).  Fast: prep_x8_kernel's
+// arrays.  Precise: x16 = fp16(x'), xl16 = fp16(x' - x16) in the places of Xh / Xl.
+__global__ void prep_x_route_kernel(const float *__restrict__ X, const float *__restrict__ r, int64_t rows, int64_t n,
+                                    int64_t ld, float half_l2e_over_h2, const float *__restrict__ xscale,
+                                    const int *__restrict__ route, int forced, __half *__restrict__ X16,
+                                    uint8_t *__restrict__ A8l, uint8_t *__restrict__ A8h, uint8_t *__restrict__ B8h,
+                                    uint8_t *__restrict__ B8l, float *__restrict__ nrm, int64_t nrm_rows) {
+    const int precise = route ? *route : forced;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t ld4 = ld / 4;
+    if (e < rows * ld4) {
+        const float sc = __ldg(xscale);
+        const float4 x = reinterpret_cast<const float4 *>(X)[e];
+        const float xs[4] = {x.x * sc, x.y * sc, x.z * sc, x.w * sc};
+        __half h[4];
+        float hf[4], lo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            h[k] = __float2half_rn(xs[k]);
+            hf[k] = __half2float(h[k]);
+            lo[k] = xs[k] - hf[k];
+        }
+        reinterpret_cast<uint2 *>(X16)[e] = *reinterpret_cast<uint2 *>(h);
+        if (precise) {
+            __half l[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) l[k] = __float2half_rn(lo[k]);
+            reinterpret_cast<uint2 *>(A8l)[e] = *reinterpret_cast<uint2 *>(l);   // XL16 occupies the a8l + a8h place
+        } else {
+            reinterpret_cast<uint32_t *>(A8l)[e] = tc::pack_e4m3x2(lo[0] * 4096.0f, lo[1] * 4096.0f) |
+                                                   (tc::pack_e4m3x2(lo[2] * 4096.0f, lo[3] * 4096.0f) << 16);
+            reinterpret_cast<uint32_t *>(A8h)[e] = tc::pack_e4m3x2(hf[0], hf[1]) | (tc::pack_e4m3x2(hf[2], hf[3]) << 16);
+            const float dn = 0.000244140625f;   // 2^-12
+            reinterpret_cast<uint32_t *>(B8h)[e] = tc::pack_e5m2x2(hf[0] * dn, hf[1] * dn) |
+                                                   (tc::pack_e5m2x2(hf[2] * dn, hf[3] * dn) << 16);
+            reinterpret_cast<uint32_t *>(B8l)[e] = tc::pack_e5m2x2(lo[0], lo[1]) | (tc::pack_e5m2x2(lo[2], lo[3]) << 16);
+        }
+    }
+    if (e < nrm_rows) nrm[e] = (e < n) ? -r[e] * half_l2e_over_h2 : -INFINITY;
+}
+
+// Y^T operands for the route that was picked.  Fast: prep_yt8_kernel's arrays.  Precise:
+// Y16 = fp16(Y'), Yx = fp16(Y16 2^-12) (partner of the scaled residual of P), Yl = fp16(Y' - Y16).
+__global__ void prep_yt_route_kernel(const float *__restrict__ X, const float *__restrict__ S, int64_t rows, int64_t ld,
+                                     float inv_h2, const float *__restrict__ down, const int *__restrict__ route,
+                                     int forced, __half *__restrict__ YT16, uint8_t *__restrict__ YT8h,
+                                     uint8_t *__restrict__ YT8l, __half *__restrict__ YTx) {
+    const int precise = route ? *route : forced;
+    __shared__ float tile[32][33];
+    const int64_t j0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int64_t j = j0 + rr, c = c0 + threadIdx.x;
+        tile[rr][threadIdx.x] = (S[j * ld + c] - X[j * ld + c] * inv_h2) * down[c];
+    }
+    __syncthreads();
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int64_t c = c0 + rr, j = j0 + threadIdx.x;
+        const float y = tile[threadIdx.x][rr];
+        const __half h = __float2half_rn(y);
+        const float hf = __half2float(h);
+        YT16[c * rows + j] = h;
+        if (precise) {
+            reinterpret_cast<__half *>(YT8h)[c * rows + j] = __float2half_rn(y - hf);   // Yl occupies the y8h + y8l place
+            YTx[c * rows + j] = __float2half_rn(hf * 0.000244140625f);
+        } else {
+            YT8h[c * rows + j] = (uint8_t)(tc::pack_e5m2x2(hf * 0.000244140625f, 0.0f) & 0xffu);
+            YT8l[c * rows + j] = (uint8_t)(tc::pack_e5m2x2(y - hf, 0.0f) & 0xffu);
+        }
+    }
 }
 
 // ---- host side -----------------------------------------------------------------------------
@@ -1519,10 +1664,13 @@ bool flash_tc2_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total,
 // only_prepare: enqueue the kernels that do not depend on the bandwidth (nor on S) and remember
 // that in ctx->xprep; the next full call on the same (X, workspace, shape, mode) skips them.
 static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all, int64_t n_total,
-                         int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
+                         int64_t d, int64_t d_true, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
                          int64_t ws_bytes, float *phi, double *sumsq, int mode, bool only_prepare) {
-    // mode 0: BF16x3 for both GEMMs; 1: mixed-precision GEMM2; 2: mixed precision for both
-    const bool g2f8 = mode >= 1, g1f8 = mode >= 2;
+    // mode 0: BF16x3 for both GEMMs; 1: mixed-precision GEMM2; 2: mixed precision for both (fast);
+    // 3: three FP16 passes for both (precise); 4: fast or precise, picked on the device by phi_guard_kernel
+    const bool autoroute = mode == 4;
+    const bool scaled = mode >= 2;                       // GEMM1 works on X scaled by a power of two
+    const bool ycols = mode >= 1;                        // GEMM2 works on column-scaled Y
     const FlashPlan pl = flash_plan(ctx, n_local, n_total, d, true);
     const int64_t rows = pl.rows, cols = pl.cols, DP = FL_MAX_DP;
     STEIN_REQUIRE(ctx, ld == DP, "CTA-pair flash phi needs ld == 256");
@@ -1555,7 +1703,7 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
     float *xscale = (float *)pws;        pws += 16;       // [0] = 2^-e on X, [1] = 2^(2e) on c1
     uint8_t *B8h = (uint8_t *)pws;       pws += cols * DP;
     uint8_t *B8l = (uint8_t *)pws;       pws += cols * DP;
-    if (g1f8 && !prepared) {
+    if (scaled && !prepared) {
         xscale_kernel<<<1, 1024, 0, ctx->stream>>>(cen.blockmax, cen.nblockmax, xscale);
         STEIN_CHECK_LAUNCH(ctx);
     }
@@ -1564,55 +1712,89 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
         return STEIN_OK;
     }
 
+    // route of this call: forced by the mode, or picked on the device (route word + diagnostics in ctx)
+    if (!ctx->d_route) {
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_route, 16));
+        STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->d_route, 0, 16, ctx->stream));
+    }
+    int *d_route = ctx->d_route;
+    float *d_diag = reinterpret_cast<float *>(ctx->d_route) + 1;
+    {
+        // the diagnostics are written on every scaled-mode call; the route word only steers `autoroute`
+        const float tol = autoroute ? ctx->phi_guard_tol : (mode == 3 ? -1.0f : INFINITY);
+        phi_guard_kernel<<<1, 1024, 0, ctx->stream>>>(rc, n_total, h2, (float)d_true, tol, d_route, d_diag);
+        STEIN_CHECK_LAUNCH(ctx);
+    }
+    const int *route = autoroute ? d_route : nullptr;
+    const int forced_precise = mode == 3 ? 1 : 0;
+
     const float l2e = 1.4426950408889634f;
     {
         const int64_t tot = std::max<int64_t>(cols * DP / 4, cols + 256);
-        if (g1f8) {
-            // FP16 array in the place of Xh; a8l, a8h share the place of Xl; b8h, b8l have their own
-            prep_x8_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(
-                Xc, rc, cols, n_total, ld, 0.5f * l2e / h2, xscale, (__half *)Xh, (uint8_t *)Xl, (uint8_t *)Xl + cols * DP,
-                B8h, B8l, nrm, cols + 256);
+        if (scaled) {
+            // FP16 array in the place of Xh; fast: a8l, a8h share the place of Xl and b8h, b8l have their
+            // own; precise: the FP16 residual takes the place of Xl
+            prep_x_route_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(
+                Xc, rc, cols, n_total, ld, 0.5f * l2e / h2, xscale, route, forced_precise, (__half *)Xh, (uint8_t *)Xl,
+                (uint8_t *)Xl + cols * DP, B8h, B8l, nrm, cols + 256);
         } else {
             prep_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(Xc, rc, cols, n_total, ld,
                                                                                  0.5f * l2e / h2, Xh, Xl, nrm, cols + 256);
         }
         STEIN_CHECK_LAUNCH(ctx);
         dim3 g((unsigned)(cols / 32), (unsigned)(DP / 32)), b(32, 8);
-        if (g2f8) {
-            // the FP16 array takes the place of YTh, the two FP8 arrays share the place of YTl
+        if (ycols) {
+            // the FP16 array takes the place of YTh; fast: the two FP8 arrays share the place of YTl;
+            // precise: the FP16 residual takes the place of YTl, the 2^-12 copy that of b8h + b8l
             colmax_partial_kernel<<<CM_BLOCKS, 256, 0, ctx->stream>>>(Xc, S_all, n_total, ld, 1.0f / h2, cmax_part);
             STEIN_CHECK_LAUNCH(ctx);
             colscale_kernel<<<(unsigned)((DP * 32 + 255) / 256), 256, 0, ctx->stream>>>(cmax_part, DP, cs_down, cs_up);
             STEIN_CHECK_LAUNCH(ctx);
-            prep_yt8_kernel<<<g, b, 0, ctx->stream>>>(Xc, S_all, cols, ld, 1.0f / h2, cs_down, (__half *)YTh,
-                                                     (uint8_t *)YTl, (uint8_t *)YTl + cols * DP);
+            prep_yt_route_kernel<<<g, b, 0, ctx->stream>>>(Xc, S_all, cols, ld, 1.0f / h2, cs_down, scaled ? route : nullptr,
+                                                          forced_precise, (__half *)YTh, (uint8_t *)YTl,
+                                                          (uint8_t *)YTl + cols * DP, (__half *)B8h);
         } else {
             prep_yt_kernel<<<g, b, 0, ctx->stream>>>(Xc, S_all, cols, ld, 1.0f / h2, YTh, YTl);
         }
         STEIN_CHECK_LAUNCH(ctx);
     }
     STEIN_TRY(plan_upload(ctx, 1, tile_nslots, n_local, n_total, d, &d_tile_nslots));
-    Phi2Maps maps;
+    // tensor maps of the fast / BF16 layouts and of the precise layout
+    Phi2Maps maps, mapsP;
     memset(&maps, 0, sizeof(maps));
-    STEIN_TRY(make_tensor_map_2d(ctx, &maps.xa_hi, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
-    STEIN_TRY(make_tensor_map_2d(ctx, &maps.xb_hi, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
-    if (g1f8) {   // FP8 arrays of X: [cols][DP] bytes
-        uint8_t *A8l = (uint8_t *)Xl, *A8h = (uint8_t *)Xl + cols * DP;
-        STEIN_TRY(make_tensor_map_2d(ctx, &maps.a8l, A8l, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 128));
-        STEIN_TRY(make_tensor_map_2d(ctx, &maps.a8h, A8h, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 128));
-        STEIN_TRY(make_tensor_map_2d(ctx, &maps.b8h, B8h, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 64));
-        STEIN_TRY(make_tensor_map_2d(ctx, &maps.b8l, B8l, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 64));
-    } else {
-        STEIN_TRY(make_tensor_map_2d(ctx, &maps.xa_lo, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
-        STEIN_TRY(make_tensor_map_2d(ctx, &maps.xb_lo, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
+    memset(&mapsP, 0, sizeof(mapsP));
+    const bool g1f8 = mode == 2 || autoroute, g2f8 = mode == 1 || mode == 2 || autoroute;
+    const bool want_fast = mode != 3, want_precise = mode == 3 || autoroute;
+    if (want_fast) {
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.xa_hi, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.xb_hi, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
+        if (g1f8) {   // FP8 arrays of X: [cols][DP] bytes
+            uint8_t *A8l = (uint8_t *)Xl, *A8h = (uint8_t *)Xl + cols * DP;
+            STEIN_TRY(make_tensor_map_2d(ctx, &maps.a8l, A8l, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 128));
+            STEIN_TRY(make_tensor_map_2d(ctx, &maps.a8h, A8h, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 128));
+            STEIN_TRY(make_tensor_map_2d(ctx, &maps.b8h, B8h, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 64));
+            STEIN_TRY(make_tensor_map_2d(ctx, &maps.b8l, B8l, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 64));
+        } else {
+            STEIN_TRY(make_tensor_map_2d(ctx, &maps.xa_lo, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
+            STEIN_TRY(make_tensor_map_2d(ctx, &maps.xb_lo, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
+        }
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.yh, YTh, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
+        if (g2f8) {   // FP8 arrays of Y^T: [DP][cols] bytes, box = 128 particles x 128 rows
+            STEIN_TRY(make_tensor_map_2d(ctx, &maps.y8h, YTl, 1, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols, 128));
+            STEIN_TRY(make_tensor_map_2d(ctx, &maps.y8l, (uint8_t *)YTl + cols * DP, 1, (uint64_t)cols, (uint64_t)DP,
+                                         (uint64_t)cols, 128));
+        } else {
+            STEIN_TRY(make_tensor_map_2d(ctx, &maps.yl, YTl, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
+        }
     }
-    STEIN_TRY(make_tensor_map_2d(ctx, &maps.yh, YTh, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
-    if (g2f8) {   // FP8 arrays of Y^T: [DP][cols] bytes, box = 128 particles x 128 rows
-        STEIN_TRY(make_tensor_map_2d(ctx, &maps.y8h, YTl, 1, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols, 128));
-        STEIN_TRY(make_tensor_map_2d(ctx, &maps.y8l, (uint8_t *)YTl + cols * DP, 1, (uint64_t)cols, (uint64_t)DP,
-                                     (uint64_t)cols, 128));
-    } else {
-        STEIN_TRY(make_tensor_map_2d(ctx, &maps.yl, YTl, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
+    if (want_precise) {
+        STEIN_TRY(make_tensor_map_2d(ctx, &mapsP.xa_hi, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
+        STEIN_TRY(make_tensor_map_2d(ctx, &mapsP.xb_hi, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
+        STEIN_TRY(make_tensor_map_2d(ctx, &mapsP.xa_lo, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
+        STEIN_TRY(make_tensor_map_2d(ctx, &mapsP.xb_lo, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
+        STEIN_TRY(make_tensor_map_2d(ctx, &mapsP.yh, YTh, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
+        STEIN_TRY(make_tensor_map_2d(ctx, &mapsP.yl, YTl, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
+        STEIN_TRY(make_tensor_map_2d(ctx, &mapsP.yx, B8h, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
     }
 
     Flash2Params p{};
@@ -1623,33 +1805,41 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
     p.nrm = nrm;
     p.out = L;
     p.row_begin = row_begin;
-    p.c1mul = g1f8 ? xscale + 1 : nullptr;
+    p.c1mul = scaled ? xscale + 1 : nullptr;
+    p.route = route;
     const size_t smem = flash_smem_bytes(DP);
     static bool attr_set = false;
     if (!attr_set) {
-        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi2_kernel<false, false>,
+        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi2_kernel<0, 0>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi2_kernel<false, true>,
+        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi2_kernel<0, 1>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi2_kernel<true, true>,
+        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi2_kernel<1, 1>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(flash_phi2_kernel<2, 2>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     {
         RegionTimer timer(ctx, STEIN_REGION_PHI);
-        if (g1f8)
-            flash_phi2_kernel<true, true><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(maps, p);
-        else if (g2f8)
-            flash_phi2_kernel<false, true><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(maps, p);
-        else
-            flash_phi2_kernel<false, false><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(maps, p);
+        if (mode == 0) {
+            flash_phi2_kernel<0, 0><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(maps, p);
+        } else if (mode == 1) {
+            flash_phi2_kernel<0, 1><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(maps, p);
+        } else {
+            if (want_fast) {
+                flash_phi2_kernel<1, 1><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(maps, p);
+                STEIN_CHECK_LAUNCH(ctx);
+            }
+            if (want_precise) flash_phi2_kernel<2, 2><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(mapsP, p);
+        }
         STEIN_CHECK_LAUNCH(ctx);
     }
     const int64_t rows_valid = std::max<int64_t>(0, std::min<int64_t>(n_local, n_total - row_begin));
     const int64_t total4 = rows * ld / 4;
     const int blocks = (int)std::min<int64_t>((total4 + 255) / 256, FINALIZE_MAX_BLOCKS);
     finalize_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(L, d_tile_nslots, Xc + row_begin * ld, rows_valid, rows, ld,
-                                                           1.0f / h2, 1.0f / (float)n_total, g2f8 ? cs_up : nullptr, phi,
+                                                           1.0f / h2, 1.0f / (float)n_total, ycols ? cs_up : nullptr, phi,
                                                            partials);
     STEIN_CHECK_LAUNCH(ctx);
     reduce_partials2_kernel<<<1, 256, 0, ctx->stream>>>(partials, blocks, sumsq);
@@ -1658,15 +1848,15 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
 }
 
 int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all, int64_t n_total,
-                  int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
+                  int64_t d, int64_t d_true, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
                   int64_t ws_bytes, float *phi, double *sumsq, int mode) {
-    return flash_tc2_run(ctx, X_all, S_all, r_all, n_total, d, ld, row_begin, n_local, h2, ws, ws_bytes, phi, sumsq,
-                         mode, false);
+    return flash_tc2_run(ctx, X_all, S_all, r_all, n_total, d, d_true, ld, row_begin, n_local, h2, ws, ws_bytes, phi,
+                         sumsq, mode, false);
 }
 
 int flash_tc2_prepare_x(stein_ctx *ctx, const float *X_all, int64_t n_total, int64_t d, int64_t ld,
                         int64_t n_local, void *ws, int64_t ws_bytes, int mode) {
-    return flash_tc2_run(ctx, X_all, nullptr, nullptr, n_total, d, ld, 0, n_local, 1.0f, ws, ws_bytes, nullptr,
+    return flash_tc2_run(ctx, X_all, nullptr, nullptr, n_total, d, d, ld, 0, n_local, 1.0f, ws, ws_bytes, nullptr,
                          nullptr, mode, true);
 }
 

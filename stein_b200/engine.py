@@ -122,13 +122,25 @@ class SvgdEngine:
         step, (optionally) D2H particles.  Arrays must be C-contiguous float32 or
         float64 of shape (n_local, n_params)."""
         self.ctx.sync_stream()
-        f64 = int(S_host.dtype == np.float64)
-        if X_out is not None and X_out.dtype != S_host.dtype:
-            raise ValueError("S_host and X_out must share a dtype")
+        S_host, f64 = self._host(S_host)           # shape, dtype, contiguity
+        if X_out is not None:
+            if not isinstance(X_out, np.ndarray) or X_out.dtype != S_host.dtype:
+                raise ValueError("S_host and X_out must share a dtype (float32 or float64)")
+            if X_out.shape != (self.n_local, self.n_params) or not X_out.flags.c_contiguous:
+                raise ValueError("X_out must be a C-contiguous (%d, %d) array" % (self.n_local, self.n_params))
         self.ctx.check(self.lib.stein_engine_update_particles_host(
             self.handle, S_host.ctypes.data_as(ctypes.c_void_p),
             X_out.ctypes.data_as(ctypes.c_void_p) if X_out is not None else None, f64))
         return X_out
+
+    def phi_only(self):
+        """compute_phi() on the scores in the S buffer, into the phi buffer; no optimizer step."""
+        self.ctx.sync_stream()
+        self.ctx.check(self.lib.stein_engine_phi_only(self.handle))
+
+    def set_hyper(self, learning_rate, decay, p1, p2):
+        self.ctx.check(self.lib.stein_engine_set_hyper(self.handle, float(learning_rate), float(decay),
+                                                       float(p1), float(p2)))
 
     def set_bandwidth(self, bandwidth=None):
         """Fixed bandwidth h for the following steps; None / 0 = the reference's

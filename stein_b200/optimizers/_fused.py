@@ -32,11 +32,22 @@ class FusedGradientDescent(AbstractGradientDescent):
 
     def _bind(self, engine):
         self._engine = engine
+        self._pushed = self._hyper()
+
+    def _push_hyper(self):
+        """Forward hyper-parameters changed on this object since the last step (a learning-rate
+        schedule, `gd.learning_rate = x`) to the engine, which otherwise keeps its own copy."""
+        h = self._hyper()
+        if self._engine is not None and h != getattr(self, "_pushed", None):
+            self._engine.set_hyper(h["learning_rate"], h["decay"], h["p1"], h["p2"])
+        self._pushed = h
 
     def _after_engine_step(self):
         self.n_iters += 1
         if self._kind == "adam":
             self.learning_rate *= self.decay   # adam_gradient_descent.py:56
+        if getattr(self, "_pushed", None) is not None:
+            self._pushed = self._hyper()       # the engine applied the same decay to its copy
 
     def _moment(self, which):
         if self._engine is not None:

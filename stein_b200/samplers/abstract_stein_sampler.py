@@ -114,6 +114,7 @@ class AbstractSteinSampler:
         grads_array = np.ascontiguousarray(grads_array)
         if isinstance(self.gd, FusedGradientDescent):
             self._sync_kernel_bandwidth()
+            self.gd._push_hyper()          # the reference reads lr / decay / betas at every update()
             e.update_particles_host(grads_array)
             self.gd._after_engine_step()
         else:
@@ -134,19 +135,10 @@ class AbstractSteinSampler:
             self._engine_bandwidth = want
 
     def _device_phi_only(self):
-        """phi for the scores in the engine, without the optimizer step."""
-        import torch
-        e, ctx = self._engine, self._engine.ctx
-        X, S = e.particles_dev, e.scores_dev
-        r = torch.empty(e.rows_padded, dtype=torch.float32, device=X.device)
-        ctx.check(ctx.lib.stein_row_norms(ctx.handle, ptr(X), e.n_particles, e.n_params, e.ld, ptr(r)))
-        bw = self.kernel._bandwidth_dev(ctx, X, r, e.n_particles, e.n_params)
-        ws_bytes = int(ctx.lib.stein_phi_workspace_bytes(ctx.handle, e.n_particles, e.n_particles, e.n_params))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)
-        sumsq = torch.zeros(1, dtype=torch.float64, device=X.device)
-        ctx.check(ctx.lib.stein_phi(ctx.handle, ptr(X), ptr(S), ptr(r), e.n_particles, e.n_params, e.ld,
-                                    0, e.n_particles, float(bw), ptr(ws), ws_bytes, ptr(e.phi_dev),
-                                    ptr(sumsq)))
+        """phi for the scores in the engine, without the optimizer step (stein_engine_phi_only:
+        the engine's own workspace, leading dimension and row shard)."""
+        self._sync_kernel_bandwidth()
+        self._engine.phi_only()
 
     # -- posterior functionals --------------------------------------------------------------
     def function_posterior(self, func, feed_dict, axis=None):

@@ -26,6 +26,7 @@ class SteinSampler(AbstractSteinSampler):
         self.log_p.scores(e, batch_feed)                 # S stays on the device
         if isinstance(self.gd, FusedGradientDescent):
             self._sync_kernel_bandwidth()
+            self.gd._push_hyper()          # the reference reads lr / decay / betas at every update()
             e.step()
             self.gd._after_engine_step()
         else:

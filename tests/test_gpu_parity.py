@@ -952,3 +952,205 @@ def test_first_iteration_matches_the_reference_run(ctx, golden_dir, tag):
     ok = np.abs(phi_ref) > 1e-4 * np.abs(phi_ref).max()
     assert ok.mean() > 0.9
     assert np.abs(sampler.samples - traj[1])[ok].max() <= RTOL_PHI * np.abs(traj[1]).max()
+
+
+# --------------------------------------------------------------------------- #
+# round 2: conditioning guard, shard-shaped calls, mixture score               #
+# --------------------------------------------------------------------------- #
+def _cloud(kind, n, d, rng):
+    """The badly conditioned clouds of VERDICT round 1 ("what's weak" #1)."""
+    Z = rng.standard_normal((n, d))
+    half = (np.arange(n) % 2 == 0)[:, None]
+    if kind == "gauss":
+        return Z
+    if kind == "pm3":
+        return np.where(half, 3.0, -3.0) + 0.3 * Z
+    if kind == "pm10":
+        return np.where(half, 10.0, -10.0) + 0.1 * Z
+    if kind == "split6040":
+        return np.where((rng.random(n) < 0.6)[:, None], 1.0, -1.0) + 0.05 * Z
+    if kind == "gmm":
+        means = np.zeros((4, d))
+        means[0, 0], means[1, 0], means[2, 1], means[3, 1] = 2, -2, 2, -2
+        return means[rng.integers(0, 4, n)] + Z
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind,n", [("gauss", 2048), ("pm3", 2048), ("split6040", 2560), ("gmm", 3000), ("pm10", 2048)])
+def test_phi_auto_route_on_multimodal_clouds(ctx, kind, n):
+    """The AUTO route (device-side conditioning guard, fast FP16+FP8 or precise FP16x3 kernels) on
+    multi-modal clouds, d = 256, against the float64 evaluation of the reference formula
+    (squared_exponential_kernel.py:22-35, abstract_stein_sampler.py:105) and against the fp32 oracle.
+
+    Bar: 1e-4 relative wherever the reference's own fp32 arithmetic reaches it.  On the worst clouds
+    (kappa = max|x - mean|^2 / h^2 of 10^3 .. 10^4) the fp32 Gram form of abstract_kernel.py:33-35
+    itself is further than 1e-4 from float64 (the oracle's own error is measured here); there the
+    kernel must stay within twice the oracle's error -- no implementation in fp32 can do better
+    than the reference's arithmetic -- and the guard must have left the fast route."""
+    from stein_b200 import _lib
+    d = 256
+    rng = np.random.default_rng(5)
+    X = _cloud(kind, n, d, rng).astype(np.float32)
+    S = (rng.standard_normal((n, d)) - X).astype(np.float32)
+    phi, sumsq, bw = _phi_gpu(ctx, X, S, _lib.PHI_AUTO)
+    route = ctx.phi_route()
+    assert bw.tobytes() == orc.kernel_and_grad(X)[2].tobytes()
+    ref64 = _phi_float64(X, S, bw)
+    oracle = orc.compute_phi(X, S.astype(np.float64))
+    err = np.abs(phi - ref64).max() / np.abs(ref64).max()
+    err_oracle = np.abs(oracle - ref64).max() / np.abs(ref64).max()
+    print("%s: kappa %.3g route %s predicted(fast) %.2e | err vs float64 %.2e (oracle's own %.2e)"
+          % (kind, route["kappa"], route["route"], route["predicted_fast_error"], err, err_oracle))
+    assert route["route"] == ("fast" if kind in ("gauss", "gmm") else "precise"), route
+    assert err <= max(RTOL_PHI, 2.0 * err_oracle), (err, err_oracle, route)
+    if kind in ("gauss", "gmm", "pm3"):
+        assert err <= RTOL_PHI
+        _assert_close(phi, oracle)
+
+
+@pytest.mark.parametrize("n_local,row_begin", [(8192, 0), (8192, 16384), (8192, 57344), (128, 32768), (2944, 62592)])
+def test_phi_shard_shaped_calls_match_oracle_rows(ctx, n_local, row_begin):
+    """What a particle-sharded rank runs (emulated on one GPU): stein_phi for
+    the row block [row_begin, row_begin + n_local) of n = 65 536 particles against all columns --
+    every row tile is a "leftover" of the schedule (fewer row tiles than clusters) -- compared with
+    the C oracle on 256 random rows of the block, in the default (guarded FP16 + FP8) mode."""
+    import torch
+    from stein_b200 import _lib
+    n, d = 65536, 256
+    X = _particles(n, d, 11)
+    S = (-X + 0.1 * _particles(n, d, 12)).astype(np.float32)
+    Xd, Sd = ctx.to_padded(X), ctx.to_padded(S)
+    rows, ld = Xd.shape
+    r = torch.empty(rows, dtype=torch.float32, device=Xd.device)
+    ctx.check(ctx.lib.stein_row_norms(ctx.handle, _ptr(Xd), n, d, ld, _ptr(r)))
+    bw = np.float32(3.3971)          # any fixed bandwidth: phi is compared at the same h on both sides
+    n_loc = min(n_local, n - row_begin)
+    nb = int(ctx.lib.stein_phi_workspace_bytes(ctx.handle, n_loc, n, d))
+    ws = torch.empty(nb, dtype=torch.uint8, device=Xd.device)
+    prow = ctx.rows_padded(n_loc)
+    phi = torch.full((prow, ld), float("nan"), dtype=torch.float32, device=Xd.device)
+    sumsq = torch.zeros(1, dtype=torch.float64, device=Xd.device)
+    ctx.check(ctx.lib.stein_phi(ctx.handle, _ptr(Xd), _ptr(Sd), _ptr(r), n, d, ld, row_begin, n_loc, float(bw),
+                                _ptr(ws), nb, _ptr(phi), _ptr(sumsq)))
+    got = phi.cpu().numpy()
+    assert np.all(got[n_loc:] == 0), "pad rows must stay zero"
+    rng = np.random.default_rng(row_begin + n_local)
+    pick = np.sort(rng.choice(n_loc, size=min(256, n_loc), replace=False))
+    scale = 0.0
+    worst = 0.0
+    for i in pick:
+        ref, _ = orc.phi_rows_c(X, S, bw, row_begin + int(i), row_begin + int(i) + 1)
+        scale = max(scale, np.abs(ref).max())
+        worst = max(worst, np.abs(got[i, :d] - ref[0]).max())
+    assert worst <= RTOL_PHI * scale, (worst, scale)
+    assert abs(float(sumsq.item()) - (got.astype(np.float64) ** 2).sum()) <= 1e-6 * float(sumsq.item())
+
+
+def test_tile_range_histograms_sum_to_the_unsharded_one(ctx):
+    """The median's distributed sweep: contiguous tile ranges (one per rank, stein_b200.distributed
+    .shard_tiles) accumulate to exactly the counts of the single-range sweep (integer work: exact)."""
+    import torch
+    from stein_b200.distributed import shard_tiles
+    n, d = 3000, 64
+    X = _particles(n, d, 21)
+    Xd = ctx.to_padded(X)
+    rows, ld = Xd.shape
+    r = torch.empty(rows, dtype=torch.float32, device=Xd.device)
+    ctx.check(ctx.lib.stein_row_norms(ctx.handle, _ptr(Xd), n, d, ld, _ptr(r)))
+    nt = int(ctx.lib.stein_num_tiles(n))
+    klo, shift, nbins = 0, 18, 16384
+
+    def sweep(t0, t1, into):
+        ctx.check(ctx.lib.stein_sqdist_hist(ctx.handle, _ptr(Xd), _ptr(r), n, d, ld, t0, t1, klo, shift, nbins, _ptr(into)))
+
+    whole = torch.zeros(nbins + 1, dtype=torch.int64, device=Xd.device)
+    sweep(0, nt, whole)
+    for world in (2, 3, 8):
+        acc = torch.zeros_like(whole)
+        for rank in range(world):
+            t0, t1 = shard_tiles(n, world, rank)
+            part = torch.zeros_like(whole)
+            sweep(t0, t1, part)
+            acc += part
+        assert torch.equal(acc, whole), world
+    assert int(whole.sum().item()) == n * n
+
+
+@pytest.mark.parametrize("n,d,ncomp", [(1000, 256, 4), (300, 1024, 4), (129, 33, 3), (64, 8, 1)])
+def test_score_gaussian_mixture(ctx, n, d, ncomp):
+    """stein_score_gaussian_mixture (the score inside bench.py's timed region, configs D / E)
+    against the float64 closed form of the oracle."""
+    import torch
+    rng = np.random.default_rng(n + d)
+    X = (1.5 * rng.standard_normal((n, d))).astype(np.float32)
+    means = None
+    if ncomp > 1:
+        means = np.zeros((ncomp, d), np.float32)
+        for k in range(ncomp):
+            means[k, (k // 2) % d] = 2.0 if k % 2 == 0 else -2.0
+    Xd = ctx.to_padded(X)
+    Sd = torch.full_like(Xd, float("nan"))
+    md = ctx.dense(means) if means is not None else None
+    sigma2 = 1.3
+    ctx.check(ctx.lib.stein_score_gaussian_mixture(ctx.handle, _ptr(Xd), n, d, Xd.shape[1],
+                                                   _ptr(md) if md is not None else None, ncomp, sigma2, _ptr(Sd)))
+    got = Sd.cpu().numpy()[:n, :d]
+    ref = orc.score_gmm(X, means, sigma2)
+    assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
+def test_custom_gradient_descent_uses_the_engine_phi(ctx):
+    """A user-defined AbstractGradientDescent (abstract_gradient_descent.py:32-52) on >= 2 048 particles of
+    few coordinates: the engine pads the rows to 128 floats and stein_engine_phi_only must run on the
+    engine's own workspace / leading dimension (the old path sized the workspace for
+    stein_ld(d) and failed with "phi workspace too small")."""
+    from stein_b200.log_p import LinearRegression
+    from stein_b200.optimizers.abstract_gradient_descent import AbstractGradientDescent
+    from stein_b200.samplers import SteinSampler
+
+    class PlainAscent(AbstractGradientDescent):
+        def update(self, phi):
+            self.n_iters += 1
+            return self.learning_rate * phi
+
+    n, F, N = 2304, 10, 64
+    rng = np.random.default_rng(4)
+    Xd = rng.standard_normal((N, F)).astype(np.float32)
+    yd = rng.standard_normal((N, 1)).astype(np.float32)
+    model = LinearRegression(F)
+    np.random.seed(1)
+    sampler = SteinSampler(n, model.log_p, PlainAscent(0.05, 1.0))
+    theta0 = sampler.samples
+    sampler.train_on_batch({model.X: Xd, model.y: yd})
+    got = sampler.samples
+    S = orc.score_linear(theta0, Xd, yd)
+    phi = orc.compute_phi(theta0.astype(np.float32), S)
+    phi *= 10. / max(10., np.linalg.norm(phi))
+    ref = theta0 + 0.05 * phi
+    assert np.abs((got - theta0) - (ref - theta0)).max() <= RTOL_PHI * np.abs(ref - theta0).max()
+
+
+def test_learning_rate_schedule_reaches_the_engine(ctx):
+    """`gd.learning_rate = x` between iterations (the reference reads it at every update(),
+    adam_gradient_descent.py:55) must change the next engine step."""
+    from stein_b200.log_p import LinearRegression
+    from stein_b200.optimizers import AdamGradientDescent
+    from stein_b200.samplers import SteinSampler
+    n, F, N = 64, 5, 32
+    rng = np.random.default_rng(8)
+    Xd = rng.standard_normal((N, F)).astype(np.float32)
+    yd = rng.standard_normal((N, 1)).astype(np.float32)
+    model = LinearRegression(F)
+    np.random.seed(2)
+    gd = AdamGradientDescent(learning_rate=0.1, decay=0.9)
+    sampler = SteinSampler(n, model.log_p, gd)
+    ogd = orc.AdamGradientDescent(learning_rate=0.1, decay=0.9)
+    theta = sampler.samples
+    for it in range(4):
+        if it == 2:
+            gd.learning_rate = 0.5
+            ogd.learning_rate = 0.5
+        theta, _ = orc.update_particles(theta, orc.score_linear(theta, Xd, yd), ogd)
+        sampler.train_on_batch({model.X: Xd, model.y: yd})
+        assert abs(gd.learning_rate - ogd.learning_rate) <= 1e-15
+    assert np.abs(sampler.samples - theta).max() <= RTOL_PHI * np.abs(theta).max()
