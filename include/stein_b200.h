@@ -43,9 +43,9 @@ extern "C" {
 #define STEIN_ABI_VERSION 2
 
 /* phi-kernel implementations (stein_ctx_set_phi_impl).  AUTO: leading dimension 256 -> the CTA-pair
- * kernel, FLASH_TC4 (fast) or FLASH_TC5 (precise) picked per call ON THE DEVICE from the conditioning
- * of the cloud (stein_ctx_phi_route); 128 -> FLASH_TC; 512 / 768 / 1024 -> the panel kernels
- * (FLASH_PANEL); anything else -> DENSE_SIMT (the engine pads the rows of >= 2048 particles of up
+ * kernel, FLASH_TC4 (fast) or FLASH_TC5 (precise) or the FFMA path picked per call from the conditioning
+ * of the cloud (stein_ctx_phi_route); 128 -> FLASH_TC (same guard); 512 / 768 / 1024 -> the panel kernels
+ * (same guard); anything else -> DENSE_SIMT (the engine pads the rows of >= 2048 particles of up
  * to 256 coordinates to 128 / 256 floats). */
 #define STEIN_PHI_AUTO 0
 #define STEIN_PHI_DENSE_SIMT 1 /* materialises K for the local row block; FP32 FFMA */
@@ -106,11 +106,14 @@ const char *stein_last_error(const stein_ctx *ctx /* NULL = last error of any ct
 /* number of kernels of this library launched on ctx since creation */
 int64_t stein_ctx_launch_count(const stein_ctx *ctx);
 
-/* Which route the last guarded phi call took on this context (synchronises the stream):
- * *route = 0 fast (FLASH_TC4), 1 precise (FLASH_TC5), -1 no guarded call yet;
+/* Which route the last guarded (STEIN_PHI_AUTO) phi call took on this context:
+ * *route = 0 fast (FLASH_TC4 arithmetic), 1 precise (FLASH_TC5), 2 the FP32 FFMA path (DENSE_SIMT:
+ * the reference's own arithmetic, for clouds no tensor-core route serves to 1e-4), -1 no guarded call yet;
  * *kappa = max_i |x_i - mean|^2 / h^2 of that call's cloud; *predicted_fast_error = the guard's
- * estimate of the relative error of phi on the fast route (the precise route is taken when it
- * exceeds the tolerance, default 5e-5, stein_ctx_set_phi_guard_tol / env STEIN_PHI_GUARD_TOL).
+ * estimate of the relative error of phi on the fast route.  A faster route is taken while its
+ * predicted error stays below the tolerance (default 5e-5; stein_ctx_set_phi_guard_tol / environment
+ * STEIN_PHI_GUARD_TOL).  The decision is taken on the host from one 8-byte device value per call; every
+ * rank of a sharded run sees the same particles and takes the same route.
  * No reference counterpart: the reference evaluates stein/kernels/abstract_kernel.py:33-35 in fp32. */
 int stein_ctx_phi_route(stein_ctx *ctx, int32_t *route, float *kappa, float *predicted_fast_error);
 int stein_ctx_set_phi_guard_tol(stein_ctx *ctx, float tol);

@@ -48,9 +48,13 @@ struct stein_ctx {
         int64_t n_total, n_local, d;
         int mode;
     } xprep{nullptr, nullptr, 0, 0, 0, 0};
-    // phi route guard (phi_tc.cu): device words [route, kappa, predicted error of the fast route]
-    // of the last guarded phi call, and the predicted error up to which the fast route is taken
-    int *d_route = nullptr;
+    // phi route guard (phi_tc.cu): device / pinned words [kappa, max centred norm^2] of the last guarded
+    // phi call, the event that marks their copy, the route that call took (0 fast, 1 precise, 2 FP32
+    // FFMA; -1 none yet) and the predicted error up to which a faster route is taken
+    float *d_guard = nullptr, *h_guard = nullptr;
+    cudaEvent_t ev_guard = nullptr;
+    int last_route = -1;
+    float last_kappa = 0.0f, last_pred_fast = 0.0f;
     float phi_guard_tol = 5.0e-5f;
     int64_t launches = 0;
     std::string error;

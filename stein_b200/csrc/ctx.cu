@@ -84,7 +84,9 @@ int stein_ctx_destroy(stein_ctx *ctx) {
     if (ctx->d_pilot_keys) cudaFree(ctx->d_pilot_keys);
     if (ctx->d_sel) cudaFree(ctx->d_sel);
     if (ctx->h_sel) cudaFreeHost(ctx->h_sel);
-    if (ctx->d_route) cudaFree(ctx->d_route);
+    if (ctx->d_guard) cudaFree(ctx->d_guard);
+    if (ctx->h_guard) cudaFreeHost(ctx->h_guard);
+    if (ctx->ev_guard) cudaEventDestroy(ctx->ev_guard);
     for (int r = 0; r < 2; ++r)
         for (auto &ev : ctx->prof_events[r]) ctx->prof_pool.push_back(ev);
     for (auto &ev : ctx->prof_pool) {
@@ -161,14 +163,9 @@ int64_t stein_ctx_launch_count(const stein_ctx *ctx) { return ctx ? ctx->launche
 
 int stein_ctx_phi_route(stein_ctx *ctx, int32_t *route, float *kappa, float *predicted_fast_error) {
     STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
-    int32_t words[4] = {-1, 0, 0, 0};
-    if (ctx->d_route) {
-        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(words, ctx->d_route, 12, cudaMemcpyDeviceToHost, ctx->stream));
-        STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
-    if (route) *route = words[0];
-    if (kappa) memcpy(kappa, &words[1], 4);
-    if (predicted_fast_error) memcpy(predicted_fast_error, &words[2], 4);
+    if (route) *route = ctx->last_route;
+    if (kappa) *kappa = ctx->last_kappa;
+    if (predicted_fast_error) *predicted_fast_error = ctx->last_pred_fast;
     return STEIN_OK;
 }
 
@@ -228,7 +225,7 @@ int stein_phi(stein_ctx *ctx, const float *X_all_dev, const float *S_all_dev, co
             return fail(ctx, STEIN_ERR_UNSUPPORTED, "flash tcgen05 phi does not take n=%lld d=%lld",
                         (long long)n_total, (long long)d);
         return phi_flash_tc(ctx, X_all_dev, S_all_dev, r_all_dev, n_total, d, ld, row_begin, n_local, h2,
-                            workspace_dev, workspace_bytes, phi_dev, sumsq_dev);
+                            workspace_dev, workspace_bytes, phi_dev, sumsq_dev, ctx->phi_impl == STEIN_PHI_AUTO, d_true);
     }
     return phi_dense(ctx, X_all_dev, S_all_dev, r_all_dev, n_total, d, ld, row_begin, n_local, h2,
                      workspace_dev, workspace_bytes, phi_dev, sumsq_dev);

@@ -23,9 +23,11 @@ int phi_dense(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
 // tcgen05 flash path (phi_tc.cu)
 bool flash_tc_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d);
 int64_t flash_tc_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d);
+// guarded: conditioning guard on (STEIN_PHI_AUTO): clouds beyond the range of the kernel's three BF16
+// passes go to phi_dense; d_true = number of real coordinates
 int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all,
                  int64_t n_total, int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2,
-                 void *ws, int64_t ws_bytes, float *phi, double *sumsq);
+                 void *ws, int64_t ws_bytes, float *phi, double *sumsq, bool guarded, int64_t d_true);
 
 // CTA-pair (cta_group::2) variant, d padded to 256 only
 bool flash_tc2_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d);

@@ -1229,20 +1229,25 @@ __global__ void prep_x8_kernel(const float *__restrict__ X, const float *__restr
 
 
 // ---- conditioning guard ---------------------------------------------------------------------
-// What limits the tensor-core routes is not the size of the cloud but its CONDITIONING: the error
-// of GEMM1 is relative to |x_i||x_j| (centred), the quantity that matters is D_ij / h^2, and the
-// repulsive term sum_j K_ij (x_i - x_j) is formed as a difference of two sums of size |x_i|.
-// With kappa = max_i |x_i - mean|^2 / h^2 the error of phi is about
-//     fast route     1.0e-5 kappa / sqrt(d)  (FP8 cross terms of GEMM1)  +  7.6e-6 sqrt(kappa)  (GEMM2)
-//     precise route  (the fp32 Gram form itself: ~2^-22 kappa)
-// (constants measured on the hardware, tools/phi_conditioning_study.py; a single Gaussian cloud has
-// kappa ~ 7, two tight clusters 10^2 .. 10^4).  The guard picks the fast route while its predicted
-// error stays below `tol` and the precise route otherwise, on the device, with no host round trip;
-// both candidate kernels are enqueued and the one not picked returns at once.
-// out: route[0] = 0 fast / 1 precise; diag[0] = kappa, diag[1] = predicted error of the fast route
+// What limits the tensor-core routes is not the size of the cloud but its CONDITIONING.  The error
+// of GEMM1 is relative to |x_i||x_j| (centred) -- the products of the FP8 cross terms, and for every
+// route the fp32 accumulation inside the tensor core, which TRUNCATES (a bias of ~2^-24 per MMA and
+// unit of |g|) -- while what enters the exponent is D_ij / h^2; and the repulsive term
+// sum_j K_ij (x_i - x_j) is formed as a difference of two sums of size |x_i|.  With
+//     kappa = max_i |x_i - mean|^2 / h^2
+// (a single Gaussian cloud: ~5-8 whatever n and d; two tight clusters of unequal weight: 10^2 .. 10^4)
+// the relative error of phi measured on a B200 (tools/phi_conditioning_study.py) follows
+//     fast route (FP16 + 2 FP8)   1.0e-5 kappa / sqrt(d) + 1.2e-6 kappa + 7.6e-6 sqrt(kappa)
+//     precise route (3 FP16)                               1.2e-6 kappa + 3.0e-6 sqrt(kappa)
+//     three BF16 passes                                    1.0e-6 kappa + 7.6e-6 sqrt(kappa)
+// The guard computes kappa on the device; the host reads it (one 12-byte copy, overlapped with
+// bandwidth-dependent preparation that every route needs) and takes the fastest route whose predicted
+// error is below the tolerance (default 5e-5; the bar is 1e-4): fast -> precise -> the FP32 FFMA path
+// of phi_dense.cu, which is the reference's own arithmetic (fp32 Gram form, round to nearest) and
+// therefore as good as the reference itself on any cloud, at 1/25 of the speed.
+// diag[0] = kappa, diag[1] = max_i |x_i - mean|^2
 __global__ void __launch_bounds__(1024)
-phi_guard_kernel(const float *__restrict__ rc, int64_t n, float h2, float d_true, float tol, int *__restrict__ route,
-                 float *__restrict__ diag) {
+phi_guard_kernel(const float *__restrict__ rc, int64_t n, float h2, float *__restrict__ diag) {
     __shared__ float red[32];
     float m = 0.0f;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, rc[i]);
@@ -1255,11 +1260,8 @@ phi_guard_kernel(const float *__restrict__ rc, int64_t n, float h2, float d_true
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         if (threadIdx.x == 0) {
-            const float kappa = m / h2;
-            const float pred = 1.0e-5f * kappa * rsqrtf(fmaxf(d_true, 1.0f)) + 7.6e-6f * sqrtf(kappa);
-            route[0] = (pred <= tol) ? 0 : 1;     // NaN / inf -> precise
-            diag[0] = kappa;
-            diag[1] = pred;
+            diag[0] = m / h2;
+            diag[1] = m;
         }
     }
 }
@@ -1548,6 +1550,39 @@ reduce_partials2_kernel(const double *__restrict__ partials, int count, double *
     if (threadIdx.x == 0) *out = red[0];
 }
 
+// ---- guard: host side --------------------------------------------------------------------------
+// guard_begin enqueues the kappa kernel and the copy of its result; the caller then enqueues whatever
+// every route needs (so the GPU has work while the host waits) and calls guard_end, which returns the
+// route: 0 fast, 1 precise, 2 FP32 FFMA.  `have_fast` / `have_precise`: the routes this kernel family offers.
+static int guard_begin(stein_ctx *ctx, const float *rc, int64_t n_total, float h2) {
+    if (!ctx->d_guard) {
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_guard, 16));
+        STEIN_CHECK_CUDA(ctx, cudaMallocHost(&ctx->h_guard, 16));
+        STEIN_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_guard, cudaEventDisableTiming));
+    }
+    phi_guard_kernel<<<1, 1024, 0, ctx->stream>>>(rc, n_total, h2, ctx->d_guard);
+    STEIN_CHECK_LAUNCH(ctx);
+    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_guard, ctx->d_guard, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    STEIN_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_guard, ctx->stream));
+    return STEIN_OK;
+}
+static int guard_end(stein_ctx *ctx, int64_t d_true, bool have_fast, bool have_precise, bool bf16_only, int *route) {
+    STEIN_CHECK_CUDA(ctx, cudaEventSynchronize(ctx->ev_guard));
+    const float kappa = ctx->h_guard[0];
+    const float sk = sqrtf(fmaxf(kappa, 0.0f)), rd = 1.0f / sqrtf((float)std::max<int64_t>(d_true, 1));
+    const float pred_fast = 1.0e-5f * kappa * rd + 1.2e-6f * kappa + 7.6e-6f * sk;
+    const float pred_precise = bf16_only ? 1.0e-6f * kappa + 7.6e-6f * sk : 1.2e-6f * kappa + 3.0e-6f * sk;
+    const float tol = ctx->phi_guard_tol;
+    int r = 2;                                   // NaN / inf kappa end here as well
+    if (have_fast && pred_fast <= tol) r = 0;
+    else if (have_precise && pred_precise <= tol) r = 1;
+    ctx->last_route = r;
+    ctx->last_kappa = kappa;
+    ctx->last_pred_fast = pred_fast;
+    *route = r;
+    return STEIN_OK;
+}
+
 static float *g_debug_dumpS = nullptr;   // set only by stein_debug_flash_gram (tests)
 
 // The per-tile slot counts read by finalize_slots_kernel depend only on the shape.  They live in
@@ -1580,7 +1615,7 @@ static int plan_upload(stein_ctx *ctx, int impl, const std::vector<int> &nslots,
 
 int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all, int64_t n_total,
                  int64_t d, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
-                 int64_t ws_bytes, float *phi, double *sumsq) {
+                 int64_t ws_bytes, float *phi, double *sumsq, bool guarded, int64_t d_true) {
     const FlashPlan pl = flash_plan(ctx, n_local, n_total, d, false);
     STEIN_REQUIRE(ctx, ld == pl.DP, "flash phi needs ld == stein_ld(d)");
     STEIN_REQUIRE(ctx, ws_bytes >= flash_tc_workspace_bytes(ctx, n_local, n_total, d), "phi workspace too small");
@@ -1602,6 +1637,8 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
     const float *Xc = cen.Xc, *rc = cen.rc;
 
     const float l2e = 1.4426950408889634f;
+    guarded = guarded && !g_debug_dumpS;
+    if (guarded) STEIN_TRY(guard_begin(ctx, rc, n_total, h2));     // the preparation below overlaps the round trip
     {
         const int64_t tot = std::max<int64_t>(pl.cols * pl.DP / 4, pl.cols);
         prep_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(Xc, rc, pl.cols, n_total, ld,
@@ -1610,6 +1647,13 @@ int phi_flash_tc(stein_ctx *ctx, const float *X_all, const float *S_all, const f
         dim3 g((unsigned)(pl.cols / 32), (unsigned)(pl.DP / 32)), b(32, 8);
         prep_yt_kernel<<<g, b, 0, ctx->stream>>>(Xc, S_all, pl.cols, ld, 1.0f / h2, YTh, YTl);
         STEIN_CHECK_LAUNCH(ctx);
+    }
+    if (guarded) {
+        // this kernel's only arithmetic is three BF16 passes: beyond its range the FP32 FFMA path takes over
+        int route = 1;
+        STEIN_TRY(guard_end(ctx, d_true, false, true, true, &route));
+        if (route == 2)
+            return phi_dense(ctx, X_all, S_all, r_all, n_total, d, ld, row_begin, n_local, h2, ws, ws_bytes, phi, sumsq);
     }
     STEIN_TRY(plan_upload(ctx, 0, pl.tile_nslots, n_local, n_total, d, &tile_nslots));
 
@@ -1667,8 +1711,9 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
                          int64_t d, int64_t d_true, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
                          int64_t ws_bytes, float *phi, double *sumsq, int mode, bool only_prepare) {
     // mode 0: BF16x3 for both GEMMs; 1: mixed-precision GEMM2; 2: mixed precision for both (fast);
-    // 3: three FP16 passes for both (precise); 4: fast or precise, picked on the device by phi_guard_kernel
+    // 3: three FP16 passes for both (precise); 4: fast / precise / FP32 FFMA, picked by the conditioning guard
     const bool autoroute = mode == 4;
+    const int mode_in = mode;
     const bool scaled = mode >= 2;                       // GEMM1 works on X scaled by a power of two
     const bool ycols = mode >= 1;                        // GEMM2 works on column-scaled Y
     const FlashPlan pl = flash_plan(ctx, n_local, n_total, d, true);
@@ -1692,7 +1737,7 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
     int *d_tile_nslots = nullptr;
     // the bandwidth-independent part (centring, global scale of X) may already have been enqueued
     // by flash_prepare_x while the host waited for the median
-    const bool prepared = !only_prepare && xprep_consume(ctx, X_all, ws, n_total, n_local, d, mode);
+    const bool prepared = !only_prepare && xprep_consume(ctx, X_all, ws, n_total, n_local, d, mode_in);
     Centred cen{};
     STEIN_TRY(make_centred(ctx, X_all, n_total, d, cols, ld, pws, &cen, !prepared));
     const float *Xc = cen.Xc, *rc = cen.rc;
@@ -1708,93 +1753,84 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
         STEIN_CHECK_LAUNCH(ctx);
     }
     if (only_prepare) {
-        ctx->xprep = {X_all, ws, n_total, n_local, d, mode};
+        ctx->xprep = {X_all, ws, n_total, n_local, d, mode_in};
         return STEIN_OK;
     }
 
-    // route of this call: forced by the mode, or picked on the device (route word + diagnostics in ctx)
-    if (!ctx->d_route) {
-        STEIN_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_route, 16));
-        STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->d_route, 0, 16, ctx->stream));
-    }
-    int *d_route = ctx->d_route;
-    float *d_diag = reinterpret_cast<float *>(ctx->d_route) + 1;
-    {
-        // the diagnostics are written on every scaled-mode call; the route word only steers `autoroute`
-        const float tol = autoroute ? ctx->phi_guard_tol : (mode == 3 ? -1.0f : INFINITY);
-        phi_guard_kernel<<<1, 1024, 0, ctx->stream>>>(rc, n_total, h2, (float)d_true, tol, d_route, d_diag);
-        STEIN_CHECK_LAUNCH(ctx);
-    }
-    const int *route = autoroute ? d_route : nullptr;
-    const int forced_precise = mode == 3 ? 1 : 0;
-
     const float l2e = 1.4426950408889634f;
+    dim3 gy((unsigned)(cols / 32), (unsigned)(DP / 32)), by(32, 8);
+    // what every route of the column-scaled modes needs: the column maxima / scales of Y
+    auto enqueue_colscale = [&]() -> int {
+        colmax_partial_kernel<<<CM_BLOCKS, 256, 0, ctx->stream>>>(Xc, S_all, n_total, ld, 1.0f / h2, cmax_part);
+        STEIN_CHECK_LAUNCH(ctx);
+        colscale_kernel<<<(unsigned)((DP * 32 + 255) / 256), 256, 0, ctx->stream>>>(cmax_part, DP, cs_down, cs_up);
+        STEIN_CHECK_LAUNCH(ctx);
+        return STEIN_OK;
+    };
+    if (autoroute) {
+        // the route of this call: kappa from the device, decision on the host (guard_end); the column
+        // scales of Y keep the GPU busy during the round trip
+        STEIN_TRY(guard_begin(ctx, rc, n_total, h2));
+        STEIN_TRY(enqueue_colscale());
+        int route = 0;
+        STEIN_TRY(guard_end(ctx, d_true, true, true, false, &route));
+        if (route == 2)      // badly conditioned cloud: the reference's own fp32 arithmetic (raw particles, raw norms)
+            return phi_dense(ctx, X_all, S_all, r_all, n_total, d, ld, row_begin, n_local, h2, ws, ws_bytes, phi, sumsq);
+        mode = route == 0 ? 2 : 3;
+    } else if (ycols) {
+        STEIN_TRY(enqueue_colscale());
+    }
+    const int forced_precise = mode == 3 ? 1 : 0;
     {
         const int64_t tot = std::max<int64_t>(cols * DP / 4, cols + 256);
         if (scaled) {
             // FP16 array in the place of Xh; fast: a8l, a8h share the place of Xl and b8h, b8l have their
             // own; precise: the FP16 residual takes the place of Xl
             prep_x_route_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(
-                Xc, rc, cols, n_total, ld, 0.5f * l2e / h2, xscale, route, forced_precise, (__half *)Xh, (uint8_t *)Xl,
+                Xc, rc, cols, n_total, ld, 0.5f * l2e / h2, xscale, nullptr, forced_precise, (__half *)Xh, (uint8_t *)Xl,
                 (uint8_t *)Xl + cols * DP, B8h, B8l, nrm, cols + 256);
         } else {
             prep_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(Xc, rc, cols, n_total, ld,
                                                                                  0.5f * l2e / h2, Xh, Xl, nrm, cols + 256);
         }
         STEIN_CHECK_LAUNCH(ctx);
-        dim3 g((unsigned)(cols / 32), (unsigned)(DP / 32)), b(32, 8);
         if (ycols) {
             // the FP16 array takes the place of YTh; fast: the two FP8 arrays share the place of YTl;
             // precise: the FP16 residual takes the place of YTl, the 2^-12 copy that of b8h + b8l
-            colmax_partial_kernel<<<CM_BLOCKS, 256, 0, ctx->stream>>>(Xc, S_all, n_total, ld, 1.0f / h2, cmax_part);
-            STEIN_CHECK_LAUNCH(ctx);
-            colscale_kernel<<<(unsigned)((DP * 32 + 255) / 256), 256, 0, ctx->stream>>>(cmax_part, DP, cs_down, cs_up);
-            STEIN_CHECK_LAUNCH(ctx);
-            prep_yt_route_kernel<<<g, b, 0, ctx->stream>>>(Xc, S_all, cols, ld, 1.0f / h2, cs_down, scaled ? route : nullptr,
-                                                          forced_precise, (__half *)YTh, (uint8_t *)YTl,
-                                                          (uint8_t *)YTl + cols * DP, (__half *)B8h);
+            prep_yt_route_kernel<<<gy, by, 0, ctx->stream>>>(Xc, S_all, cols, ld, 1.0f / h2, cs_down, nullptr, forced_precise,
+                                                            (__half *)YTh, (uint8_t *)YTl, (uint8_t *)YTl + cols * DP,
+                                                            (__half *)B8h);
         } else {
-            prep_yt_kernel<<<g, b, 0, ctx->stream>>>(Xc, S_all, cols, ld, 1.0f / h2, YTh, YTl);
+            prep_yt_kernel<<<gy, by, 0, ctx->stream>>>(Xc, S_all, cols, ld, 1.0f / h2, YTh, YTl);
         }
         STEIN_CHECK_LAUNCH(ctx);
     }
     STEIN_TRY(plan_upload(ctx, 1, tile_nslots, n_local, n_total, d, &d_tile_nslots));
-    // tensor maps of the fast / BF16 layouts and of the precise layout
-    Phi2Maps maps, mapsP;
+    // tensor maps of the layout of this call's mode
+    Phi2Maps maps;
     memset(&maps, 0, sizeof(maps));
-    memset(&mapsP, 0, sizeof(mapsP));
-    const bool g1f8 = mode == 2 || autoroute, g2f8 = mode == 1 || mode == 2 || autoroute;
-    const bool want_fast = mode != 3, want_precise = mode == 3 || autoroute;
-    if (want_fast) {
-        STEIN_TRY(make_tensor_map_2d(ctx, &maps.xa_hi, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
-        STEIN_TRY(make_tensor_map_2d(ctx, &maps.xb_hi, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
-        if (g1f8) {   // FP8 arrays of X: [cols][DP] bytes
-            uint8_t *A8l = (uint8_t *)Xl, *A8h = (uint8_t *)Xl + cols * DP;
-            STEIN_TRY(make_tensor_map_2d(ctx, &maps.a8l, A8l, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 128));
-            STEIN_TRY(make_tensor_map_2d(ctx, &maps.a8h, A8h, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 128));
-            STEIN_TRY(make_tensor_map_2d(ctx, &maps.b8h, B8h, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 64));
-            STEIN_TRY(make_tensor_map_2d(ctx, &maps.b8l, B8l, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 64));
-        } else {
-            STEIN_TRY(make_tensor_map_2d(ctx, &maps.xa_lo, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
-            STEIN_TRY(make_tensor_map_2d(ctx, &maps.xb_lo, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
-        }
-        STEIN_TRY(make_tensor_map_2d(ctx, &maps.yh, YTh, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
-        if (g2f8) {   // FP8 arrays of Y^T: [DP][cols] bytes, box = 128 particles x 128 rows
-            STEIN_TRY(make_tensor_map_2d(ctx, &maps.y8h, YTl, 1, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols, 128));
-            STEIN_TRY(make_tensor_map_2d(ctx, &maps.y8l, (uint8_t *)YTl + cols * DP, 1, (uint64_t)cols, (uint64_t)DP,
-                                         (uint64_t)cols, 128));
-        } else {
-            STEIN_TRY(make_tensor_map_2d(ctx, &maps.yl, YTl, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
-        }
+    const bool g1f8 = mode == 2, g2f8 = mode == 1 || mode == 2;
+    STEIN_TRY(make_tensor_map_2d(ctx, &maps.xa_hi, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
+    STEIN_TRY(make_tensor_map_2d(ctx, &maps.xb_hi, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
+    if (g1f8) {   // FP8 arrays of X: [cols][DP] bytes
+        uint8_t *A8l = (uint8_t *)Xl, *A8h = (uint8_t *)Xl + cols * DP;
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.a8l, A8l, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 128));
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.a8h, A8h, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 128));
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.b8h, B8h, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 64));
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.b8l, B8l, 1, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP, 64));
+    } else {      // BF16 (mode 0, 1) or FP16 (precise) hi / lo arrays
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.xa_lo, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.xb_lo, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
     }
-    if (want_precise) {
-        STEIN_TRY(make_tensor_map_2d(ctx, &mapsP.xa_hi, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
-        STEIN_TRY(make_tensor_map_2d(ctx, &mapsP.xb_hi, Xh, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
-        STEIN_TRY(make_tensor_map_2d(ctx, &mapsP.xa_lo, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 128));
-        STEIN_TRY(make_tensor_map_2d(ctx, &mapsP.xb_lo, Xl, 2, (uint64_t)DP, (uint64_t)cols, (uint64_t)DP * 2, 64));
-        STEIN_TRY(make_tensor_map_2d(ctx, &mapsP.yh, YTh, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
-        STEIN_TRY(make_tensor_map_2d(ctx, &mapsP.yl, YTl, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
-        STEIN_TRY(make_tensor_map_2d(ctx, &mapsP.yx, B8h, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
+    STEIN_TRY(make_tensor_map_2d(ctx, &maps.yh, YTh, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
+    if (g2f8) {   // FP8 arrays of Y^T: [DP][cols] bytes, box = 128 particles x 128 rows
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.y8h, YTl, 1, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols, 128));
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.y8l, (uint8_t *)YTl + cols * DP, 1, (uint64_t)cols, (uint64_t)DP,
+                                     (uint64_t)cols, 128));
+    } else {
+        STEIN_TRY(make_tensor_map_2d(ctx, &maps.yl, YTl, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
+        if (mode == 3)
+            STEIN_TRY(make_tensor_map_2d(ctx, &maps.yx, B8h, 2, (uint64_t)cols, (uint64_t)DP, (uint64_t)cols * 2, 128));
     }
 
     Flash2Params p{};
@@ -1806,7 +1842,7 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
     p.out = L;
     p.row_begin = row_begin;
     p.c1mul = scaled ? xscale + 1 : nullptr;
-    p.route = route;
+    p.route = nullptr;
     const size_t smem = flash_smem_bytes(DP);
     static bool attr_set = false;
     if (!attr_set) {
@@ -1822,17 +1858,14 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
     }
     {
         RegionTimer timer(ctx, STEIN_REGION_PHI);
-        if (mode == 0) {
+        if (mode == 0)
             flash_phi2_kernel<0, 0><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(maps, p);
-        } else if (mode == 1) {
+        else if (mode == 1)
             flash_phi2_kernel<0, 1><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(maps, p);
-        } else {
-            if (want_fast) {
-                flash_phi2_kernel<1, 1><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(maps, p);
-                STEIN_CHECK_LAUNCH(ctx);
-            }
-            if (want_precise) flash_phi2_kernel<2, 2><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(mapsP, p);
-        }
+        else if (mode == 2)
+            flash_phi2_kernel<1, 1><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(maps, p);
+        else
+            flash_phi2_kernel<2, 2><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(maps, p);
         STEIN_CHECK_LAUNCH(ctx);
     }
     const int64_t rows_valid = std::max<int64_t>(0, std::min<int64_t>(n_local, n_total - row_begin));
@@ -1872,7 +1905,7 @@ extern "C" int stein_debug_flash_gram(stein_ctx *ctx, const float *X_dev, const 
     STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
     stein::g_debug_dumpS = G_dev;
     const int rc = stein::phi_flash_tc(ctx, X_dev, S_dev, r_dev, n, d, ld, 0, n, bandwidth * bandwidth, ws,
-                                       ws_bytes, phi_dev, sumsq_dev);
+                                       ws_bytes, phi_dev, sumsq_dev, false, d);
     stein::g_debug_dumpS = nullptr;
     return rc;
 }

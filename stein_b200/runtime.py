@@ -51,10 +51,11 @@ class Context:
         self.check(self.lib.stein_ctx_set_median_impl(self.handle, int(impl)))
 
     def phi_route(self):
-        """Route of the last guarded phi call: {"route": "fast" | "precise" | None, "kappa", "predicted_fast_error"}."""
+        """Route of the last guarded phi call: {"route": "fast" | "precise" | "ffma" | None, "kappa",
+        "predicted_fast_error"} (include/stein_b200.h stein_ctx_phi_route)."""
         r, k, e = ctypes.c_int32(), ctypes.c_float(), ctypes.c_float()
         self.check(self.lib.stein_ctx_phi_route(self.handle, ctypes.byref(r), ctypes.byref(k), ctypes.byref(e)))
-        return {"route": {0: "fast", 1: "precise"}.get(r.value), "kappa": k.value, "predicted_fast_error": e.value}
+        return {"route": {0: "fast", 1: "precise", 2: "ffma"}.get(r.value), "kappa": k.value, "predicted_fast_error": e.value}
 
     def set_phi_guard_tol(self, tol):
         self.check(self.lib.stein_ctx_set_phi_guard_tol(self.handle, float(tol)))

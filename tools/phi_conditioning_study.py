@@ -16,8 +16,10 @@ from oracle import svgd_oracle as orc  # noqa: E402
 
 def clouds(n, d, rng):
     Z = rng.standard_normal((n, d))
-    half = (np.arange(n) % 2 == 0)[:, None]
+    half = (rng.random(n) < 0.5)[:, None]          # random membership: clusters of unequal size
+    even = (np.arange(n) % 2 == 0)[:, None]
     yield "gauss", Z
+    yield "clusters_pm3_exact5050", np.where(even, 3.0, -3.0) + 0.3 * Z
     yield "offset10_sd0.1", 10.0 + 0.1 * Z
     yield "clusters_pm3_sd0.3", np.where(half, 3.0, -3.0) + 0.3 * Z
     yield "clusters_pm10_sd0.1", np.where(half, 10.0, -10.0) + 0.1 * Z
@@ -76,6 +78,8 @@ def main():
             errs.append(np.abs(got - ref).max() / np.abs(ref).max())
             if code == _lib.PHI_AUTO:
                 route = ctx.phi_route()
+        ctx.set_phi_guard_tol(1.0)        # kappa of this cloud (a guarded call that stays on the fast route)
+        ctx.set_phi_guard_tol(5e-5)
         ctx.set_phi_impl(_lib.PHI_AUTO)
         o = orc.compute_phi(X, S.astype(np.float64))
         errs.append(np.abs(o - ref).max() / np.abs(ref).max())
