@@ -180,9 +180,13 @@ int stein_ctx_set_phi_guard_tol(stein_ctx *ctx, float tol) {
 // conditioning guard -- what STEIN_PHI_AUTO resolves to for a leading dimension of 256
 constexpr int PHI_FLASH_GUARDED = STEIN_PHI_FLASH_TC5 + 1;
 static bool is_pair_impl(int impl) { return impl >= STEIN_PHI_FLASH_TC2 && impl <= PHI_FLASH_GUARDED; }
+// leading dimensions that make a matrix eligible for the tensor-core kernels whatever d is: the zero pad
+// columns are then simply treated as coordinates
+static bool is_tc_ld(int64_t ld) { return ld == 128 || ld == 256 || ld == 512 || ld == 768 || ld == 1024; }
 
 static int pick_phi_impl(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t d) {
     if (ctx->phi_impl != STEIN_PHI_AUTO) return ctx->phi_impl;
+    if (panel::panel_supported(ctx, n_total, stein_ld(d))) return PHI_FLASH_GUARDED;      // panel kernels, guarded
     if (flash_tc2_supported(ctx, n_local, n_total, d)) return PHI_FLASH_GUARDED;
     return flash_tc_supported(ctx, n_local, n_total, d) ? STEIN_PHI_FLASH_TC : STEIN_PHI_DENSE_SIMT;
 }
@@ -193,6 +197,8 @@ int64_t stein_phi_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t
     int64_t b = dense_workspace_bytes(n_local, n_total, d);
     if (flash_tc_supported(ctx, n_local, n_total, d))
         b = std::max(b, flash_tc_workspace_bytes(ctx, n_local, n_total, d));
+    if (panel::panel_supported(ctx, n_total, stein_ld(d)))
+        b = std::max(b, panel::panel_workspace_bytes(ctx, n_local, n_total, stein_ld(d)));
     return b;
 }
 
@@ -211,8 +217,11 @@ int stein_phi(stein_ctx *ctx, const float *X_all_dev, const float *S_all_dev, co
     // A leading dimension of 128 / 256 makes the matrix eligible for the tensor-core kernels
     // whatever d is: the zero pad columns are then simply treated as coordinates.
     const int64_t d_true = d;
-    if ((ld == 128 || ld == 256) && d < ld) d = ld;
+    if (is_tc_ld(ld) && d < ld) d = ld;
     const int impl = pick_phi_impl(ctx, n_local, n_total, d);
+    if (is_pair_impl(impl) && impl >= STEIN_PHI_FLASH_TC4 && panel::panel_supported(ctx, n_total, ld))
+        return panel::phi_panel(ctx, X_all_dev, S_all_dev, r_all_dev, n_total, d, d_true, ld, row_begin, n_local, h2,
+                                workspace_dev, workspace_bytes, phi_dev, sumsq_dev, impl - STEIN_PHI_FLASH_TC2);
     if (is_pair_impl(impl)) {
         if (!flash_tc2_supported(ctx, n_local, n_total, d))
             return fail(ctx, STEIN_ERR_UNSUPPORTED, "CTA-pair flash phi does not take n=%lld d=%lld",
@@ -237,7 +246,7 @@ namespace stein {
 // Same dispatch as stein_phi; a no-op for the kernels that have nothing to hoist.
 int phi_prepare_x(stein_ctx *ctx, const float *X_all, int64_t n_total, int64_t d, int64_t ld, int64_t n_local,
                   void *ws, int64_t ws_bytes) {
-    if ((ld == 128 || ld == 256) && d < ld) d = ld;
+    if (is_tc_ld(ld) && d < ld) d = ld;
     const int impl = pick_phi_impl(ctx, n_local, n_total, d);
     if (is_pair_impl(impl) && flash_tc2_supported(ctx, n_local, n_total, d))
         return flash_tc2_prepare_x(ctx, X_all, n_total, d, ld, n_local, ws, ws_bytes, impl - STEIN_PHI_FLASH_TC2);

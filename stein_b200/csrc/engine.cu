@@ -148,6 +148,7 @@ int stein_engine_create(stein_engine **out, stein_ctx *ctx, int64_t n_total, int
     // tensor-core median and phi kernels apply (pad columns are zero and stay zero).
     e->ld = stein_ld(d);
     if (n_total >= 2048 && d <= 256) e->ld = d <= 128 ? 128 : 256;
+    else if (n_total >= 2048 && d <= 1024) e->ld = stein::round_up(d, 256);     // 512 / 768 / 1024: the panel kernels
     e->world = ctx->has_comm ? ctx->comm.world : 1;
     e->rank = ctx->has_comm ? ctx->comm.rank : 0;
     e->q = stein_rows_padded((n_total + e->world - 1) / e->world);

@@ -1895,6 +1895,8 @@ int flash_tc2_prepare_x(stein_ctx *ctx, const float *X_all, int64_t n_total, int
 
 }  // namespace stein
 
+#include "phi_panel.cuh"
+
 // Test hook (not part of the public header): runs the flash kernel on (X, S = 0) and
 // returns the raw GEMM1 tile outputs G = X X^T as computed on the tensor cores
 // (rows_padded(n) x rows_padded(n), fp32) so the tests can bound its error.

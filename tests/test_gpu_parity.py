@@ -1174,3 +1174,54 @@ def test_learning_rate_schedule_reaches_the_engine(ctx):
         sampler.train_on_batch({model.X: Xd, model.y: yd})
         assert abs(gd.learning_rate - ogd.learning_rate) <= 1e-15
     assert np.abs(sampler.samples - theta).max() <= RTOL_PHI * np.abs(theta).max()
+
+
+# --------------------------------------------------------------------------- #
+# round 2: more than 256 coordinates on the tensor cores (config E shapes)     #
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("mode", ["fast", "precise", "auto"])
+@pytest.mark.parametrize("n,d", [(1000, 512), (4096, 512), (2500, 700), (4096, 1024), (5000, 1000)])
+def test_phi_panel_kernels_match_oracle(ctx, n, d, mode):
+    """Leading dimension 512 / 768 / 1024: the K-streaming panel kernels (panel_gemm.cuh, phi_panel.cuh)
+    against the oracle (abstract_stein_sampler.py:100-105), 1e-4, pads zero, sum(phi^2) consistent."""
+    from stein_b200 import _lib
+    X = _particles(n, d, 3 * n + d)
+    S = _particles(n, d, 5 * n + d) - X
+    code = {"fast": _lib.PHI_FLASH_TC4, "precise": _lib.PHI_FLASH_TC5, "auto": _lib.PHI_AUTO}[mode]
+    phi, sumsq, bw = _phi_gpu(ctx, X, S, code)
+    ref = orc.compute_phi(X, S.astype(np.float64))
+    assert bw.tobytes() == orc.kernel_and_grad(X)[2].tobytes()
+    fro, mx = _rel(phi, ref)
+    print("panel %s n=%d d=%d: fro %.2e max %.2e" % (mode, n, d, fro, mx))
+    _assert_close(phi, ref)
+    assert abs(sumsq - (phi ** 2).sum()) <= 1e-6 * (phi ** 2).sum()
+    if mode == "auto":
+        assert ctx.phi_route()["route"] == "fast"
+
+
+def test_phi_panel_config_e_shape_and_shard(ctx):
+    """n = 8 192, d = 1 024 on the Gaussian-mixture cloud of BASELINE.json config E, as one block and as the
+    shard-shaped call of rank 1 of 4 (row_begin = 2 048), against the oracle rows."""
+    import torch
+    from stein_b200 import _lib
+    n, d = 8192, 1024
+    rng = np.random.default_rng(77)
+    X = _cloud("gmm", n, d, rng).astype(np.float32)
+    means = np.zeros((4, d), np.float32)
+    means[0, 0], means[1, 0], means[2, 1], means[3, 1] = 2, -2, 2, -2
+    S = orc.score_gmm(X, means).astype(np.float32)
+    phi, sumsq, bw = _phi_gpu(ctx, X, S, _lib.PHI_AUTO)
+    ref = orc.compute_phi(X, S.astype(np.float64))
+    _assert_close(phi, ref)
+    # shard-shaped: rows [2048, 4096) against all columns
+    Xd, Sd = ctx.to_padded(X), ctx.to_padded(S)
+    rows, ld = Xd.shape
+    r = torch.empty(rows, dtype=torch.float32, device=Xd.device)
+    ctx.check(ctx.lib.stein_row_norms(ctx.handle, _ptr(Xd), n, d, ld, _ptr(r)))
+    nb = int(ctx.lib.stein_phi_workspace_bytes(ctx.handle, 2048, n, d))
+    ws = torch.empty(nb, dtype=torch.uint8, device=Xd.device)
+    out = torch.full((2048, ld), float("nan"), dtype=torch.float32, device=Xd.device)
+    ss = torch.zeros(1, dtype=torch.float64, device=Xd.device)
+    ctx.check(ctx.lib.stein_phi(ctx.handle, _ptr(Xd), _ptr(Sd), _ptr(r), n, d, ld, 2048, 2048, float(bw), _ptr(ws), nb,
+                                _ptr(out), _ptr(ss)))
+    _assert_close(out.cpu().numpy()[:, :d], ref[2048:4096])
