@@ -24,6 +24,7 @@
 #include <functional>
 
 #include "pair_chain.cuh"
+#include "panel_gemm.cuh"
 #include "tc_common.cuh"
 
 namespace stein {
@@ -714,6 +715,59 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
     }
 }
 
+// =====================================================================================
+// Sweep for more than 256 coordinates (leading dimension 512 / 768 / 1024): the row tile no longer
+// fits next to the ring (A hi alone would be 256 KB at d = 1 024), so both operands stream along K
+// through the main loop of panel_gemm.cuh -- 256 x 256 tiles (pair rows I2, pair columns J2 >= I2),
+// the same three FP16 passes (hi.hi, lo.hi, hi.lo) and the same classification, applied to the two
+// 128-column halves of the accumulator.
+// =====================================================================================
+struct Sweep3Policy {
+    static constexpr int STAGES = 6;
+    static constexpr size_t TAIL_BYTES = SW_TAIL_BYTES;
+    struct Params : pg::Core {
+        SweepParams sp;
+        int T2;                       // 256-row tiles per side
+        long long t_begin, t_end;     // range of this launch in the row-major order of the upper triangle of T2 x T2
+    };
+    __device__ static bool tile(const Params &p, long long k, int cl, int ncl, int &ti, int &tj) {
+        const long long NT = p.t_end - p.t_begin;
+        const long long my0 = p.t_begin + NT * cl / ncl, my1 = p.t_begin + NT * (cl + 1) / ncl;
+        if (my0 + k >= my1) return false;
+        tri_tile(my0 + k, p.T2, ti, tj);
+        return true;
+    }
+    __device__ static void init_shared(uint8_t *tail, int tid) {
+        unsigned int *sHist = reinterpret_cast<unsigned int *>(tail + SW_TAIL_HIST);
+        for (int b = tid; b < SW_HIST_BINS; b += pg::THREADS) sHist[b] = 0u;
+    }
+    struct Epilogue {
+        TileClassifier<2> tc;
+        int I2, J2, ew_tid;
+        uint32_t rank;
+        __device__ Epilogue(const Params &p, uint8_t *tail, int warp, int lane, uint32_t rank_)
+            : tc(p.sp, tail, warp, lane), I2(0), J2(0), ew_tid((warp - 4) * 32 + lane), rank(rank_) {}
+        __device__ void tile_begin(int ti, int tj) {
+            I2 = ti;
+            J2 = tj;
+        }
+        __device__ void unit(uint32_t acc_tmem, int, bool) {
+            const int I = 2 * I2 + (int)rank;
+            const long long i = (long long)I * 128 + tc.row;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const int J = 2 * J2 + h;
+                tc.classify(acc_tmem + (uint32_t)h * 128u, i, J, J > I ? 2u : (J == I ? 1u : 0u));
+            }
+            tc.flush(false);
+        }
+        __device__ void finish() {
+            tc.flush(true);
+            tc.finish(ew_tid);
+        }
+    };
+};
+
 // ---- helpers ---------------------------------------------------------------------------
 // hi = fp16(s x), lo = fp16(s x - hi): 22 bits of s x (entries far below the largest one end in
 // the FP16 subnormals; that absolute error is covered by the slack terms, see eps_coeff)
@@ -774,36 +828,41 @@ pilot_h16_kernel(uint32_t *__restrict__ keys, unsigned long long m, const uint4 
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     const unsigned long long ngroups = (m + 31ull) / 32ull;
     const float inv_s2 = __ldg(scale + 2);
-    const bool active = lane < chunks;
     for (unsigned long long g = warp; g < ngroups; g += nwarps) {
         const unsigned long long e = g * 32ull + lane;
         const uint64_t h = splitmix64(seed + (uint64_t)e);
         const uint32_t i = (uint32_t)((h >> 32) % (uint64_t)n), j = (uint32_t)((h & 0xffffffffull) % (uint64_t)n);
         float v[32];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            uint4 A[8], B[8];
+        for (int k = 0; k < 32; ++k) v[k] = 0.0f;
+        // rows of more than 256 coordinates: 256 at a time (one 16-byte load per lane and row each)
+        for (int seg = 0; seg * 32 < chunks; ++seg) {
+            const bool active = seg * 32 + lane < chunks;
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const uint32_t it = __shfl_sync(0xffffffffu, i, 8 * b + t), jt = __shfl_sync(0xffffffffu, j, 8 * b + t);
-                A[t] = B[t] = make_uint4(0u, 0u, 0u, 0u);
-                if (active) {
-                    A[t] = __ldg(Xh + (size_t)it * chunks + lane);
-                    B[t] = __ldg(Xh + (size_t)jt * chunks + lane);
+            for (int b = 0; b < 4; ++b) {
+                uint4 A[8], B[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const uint32_t it = __shfl_sync(0xffffffffu, i, 8 * b + t), jt = __shfl_sync(0xffffffffu, j, 8 * b + t);
+                    A[t] = B[t] = make_uint4(0u, 0u, 0u, 0u);
+                    if (active) {
+                        A[t] = __ldg(Xh + (size_t)it * chunks + seg * 32 + lane);
+                        B[t] = __ldg(Xh + (size_t)jt * chunks + seg * 32 + lane);
+                    }
                 }
-            }
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const uint32_t a[4] = {A[t].x, A[t].y, A[t].z, A[t].w}, c[4] = {B[t].x, B[t].y, B[t].z, B[t].w};
-                float acc = 0.0f;
+                for (int t = 0; t < 8; ++t) {
+                    const uint32_t a[4] = {A[t].x, A[t].y, A[t].z, A[t].w}, c[4] = {B[t].x, B[t].y, B[t].z, B[t].w};
+                    float acc = 0.0f;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&a[q]));
-                    const float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&c[q]));
-                    acc = fmaf(fa.x, fb.x, acc);
-                    acc = fmaf(fa.y, fb.y, acc);
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&a[q]));
+                        const float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&c[q]));
+                        acc = fmaf(fa.x, fb.x, acc);
+                        acc = fmaf(fa.y, fb.y, acc);
+                    }
+                    v[8 * b + t] += acc;
                 }
-                v[8 * b + t] = acc;
             }
         }
         // butterfly: after the step with stride s, a lane keeps the half of the pairs whose index
@@ -1091,6 +1150,8 @@ static float eps_coeff(int64_t d) {
     return (float)(2.0 * (per_xx + ldexp(1.0, -22)));
 }
 constexpr float EPS_ABS = 2.384185791015625e-07f;    // 2^-22 (d <= 256: 2^-26 * 16 / 16 = 2^-26, x16 margin)
+// the subnormal term grows with sqrt(d): keep the margin beyond 256 coordinates
+static float eps_abs_coeff(int64_t d) { return d > 256 ? EPS_ABS * sqrtf((float)d / 256.0f) : EPS_ABS; }
 
 struct PilotSpec {
     const uint32_t *keys_dev;       // this rank's slice of the pilot keys
@@ -1311,7 +1372,8 @@ int pilot_window(stein_ctx *ctx, const uint32_t *keys_dev, int64_t m, uint64_t r
 
 // ld: leading dimension of the particle matrix (its zero pad columns count as coordinates)
 bool median_tc_supported(int64_t n, int64_t ld) {
-    return (ld == 128 || ld == 256) && (uint64_t)n * (uint64_t)n >= (1ull << 24) && n < (1ll << 31);
+    return (ld == 128 || ld == 256 || ld == 512 || ld == 768 || ld == 1024) && (uint64_t)n * (uint64_t)n >= (1ull << 24) &&
+           n < (1ll << 31);
 }
 
 // returns STEIN_OK with keys filled, 1 = "not bracketed, use the FFMA route", <0 = error
@@ -1324,13 +1386,12 @@ bool median_tc_has_hint(const stein_ctx *ctx) { return hint_usable(ctx); }
 // Returns like median_tc.
 static int median_tc_device_tail(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t d, int64_t ld,
                                  const uint64_t ranks[2], float c_half, SweepParams *p, uint32_t keys_out[2]) {
-    (void)d;
     MedianArena &A = g_arena;
     const int world = ctx->has_comm ? ctx->comm.world : 1;
     uint32_t *bp = reinterpret_cast<uint32_t *>(A.counters + CNT_BANDP);
     int *d_overflow2 = reinterpret_cast<int *>(A.counters + CNT_OVERFLOW2);
     pick_band_kernel<<<1, 1024, 0, ctx->stream>>>(A.counters, CNT_BELOW, CNT_LISTED, CNT_OVERFLOW, CNT_HIST, CNT_RMAX,
-                                                 CNT_HPARAMS, ranks[0], ranks[1], c_half, EPS_ABS,
+                                                 CNT_HPARAMS, ranks[0], ranks[1], c_half, eps_abs_coeff(d),
                                                  (uint32_t)HIST_MAX_BINS, bp);
     STEIN_CHECK_LAUNCH(ctx);
     band_filter_kernel<<<16 * ctx->num_sms, BF_THREADS, 0, ctx->stream>>>(
@@ -1453,8 +1514,10 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     MedianArena &A = g_arena;
     const int world = ctx->has_comm ? ctx->comm.world : 1, rank = ctx->has_comm ? ctx->comm.rank : 0;
     // CTA-pair sweep unless the single-CTA kernel is asked for (STEIN_MEDIAN_TC1, tests / comparison)
-    const bool pair = ctx->median_impl != STEIN_MEDIAN_TC1 && ctx->num_sms >= 2 && DP <= 64 * SW2_KB;
-    const int64_t ntiles = pair ? num_pair_tiles(T) : T * (T + 1) / 2;
+    const bool wide = DP > 64 * SW2_KB;                  // more than 256 coordinates: K-streaming sweep (Sweep3Policy)
+    const bool pair = ctx->median_impl != STEIN_MEDIAN_TC1 && ctx->num_sms >= 2 && !wide;
+    const int64_t T2 = (T + 1) / 2;
+    const int64_t ntiles = wide ? T2 * (T2 + 1) / 2 : (pair ? num_pair_tiles(T) : T * (T + 1) / 2);
     const int64_t t0 = ntiles * rank / world, t1 = ntiles * (rank + 1) / world;
     const float c_half = eps_coeff(d);
 
@@ -1527,7 +1590,44 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
                                                    (int)smem2));
         attr_set = true;
     }
-    if (t1 > t0) {
+    if (t1 > t0 && wide) {
+        RegionTimer timer(ctx, STEIN_REGION_SWEEP);
+        pg::Maps maps;
+        memset(&maps, 0, sizeof(maps));
+        // table entries (a, b): (0, 0) hi.hi, (1, 1) lo.hi, (0, 2) hi.lo
+        const void *am[3] = {A.Xh, A.Xl, A.Xh}, *bm[3] = {A.Xh, A.Xh, A.Xl};
+        for (int m = 0; m < 3; ++m) {
+            STEIN_TRY(make_tensor_map_2d(ctx, &maps.a[m], am[m], 2, (uint64_t)DP, (uint64_t)rows, (uint64_t)DP * 2, 128));
+            STEIN_TRY(make_tensor_map_2d(ctx, &maps.b[m], bm[m], 2, (uint64_t)DP, (uint64_t)rows, (uint64_t)DP * 2, 128));
+        }
+        Sweep3Policy::Params sp{};
+        sp.n_stage = 6;
+        for (int h = 0; h < 2; ++h) {
+            sp.table[3 * h + 0] = {0, 0, 64 * h, 0};
+            sp.table[3 * h + 1] = {1, 1, 64 * h, 0};
+            sp.table[3 * h + 2] = {0, 2, 64 * h, 0};
+        }
+        sp.groups_per_unit = (int)(DP / 128);
+        sp.units_per_tile = 1;
+        sp.ka0 = sp.kb0 = 0;
+        sp.a_row0 = sp.b_row0 = 0;
+        sp.route = nullptr;
+        sp.my_route = 0;
+        sp.sp = p;
+        sp.T2 = (int)T2;
+        sp.t_begin = t0;
+        sp.t_end = t1;
+        const size_t smem3 = pg::smem_bytes<Sweep3Policy::STAGES>(Sweep3Policy::TAIL_BYTES);
+        static bool attr3 = false;
+        if (!attr3) {
+            STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(pg::panel_gemm_kernel<Sweep3Policy>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            attr3 = true;
+        }
+        const int clusters = (int)std::min<int64_t>(ctx->num_sms / 2, t1 - t0);
+        pg::panel_gemm_kernel<Sweep3Policy><<<2 * clusters, pg::THREADS, smem3, ctx->stream>>>(maps, sp);
+        STEIN_CHECK_LAUNCH(ctx);
+    } else if (t1 > t0) {
         RegionTimer timer(ctx, STEIN_REGION_SWEEP);
         if (pair) {
             CUtensorMap mapXh64, mapXl64;
@@ -1571,7 +1671,7 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     const float bin_w = 1.0f / hscale;
     const float t_lo = hlo + (float)(bstar - 1) * bin_w, t_hi = hlo + (float)(bstar + 2) * bin_w;
     // the exact value at a rank differs from the D~ value at that rank by at most max eps
-    const float eps_abs = EPS_ABS * rmax;
+    const float eps_abs = eps_abs_coeff(d) * rmax;
     const float delta = c_half * 2.0f * rmax * 1.0001f + eps_abs + 2.0f * fmaxf(fabsf(t_lo), fabsf(t_hi)) * 1.2e-7f;
     const float tlo = t_lo - delta, thi = t_hi + delta;
 

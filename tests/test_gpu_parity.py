@@ -1225,3 +1225,26 @@ def test_phi_panel_config_e_shape_and_shard(ctx):
     ctx.check(ctx.lib.stein_phi(ctx.handle, _ptr(Xd), _ptr(Sd), _ptr(r), n, d, ld, 2048, 2048, float(bw), _ptr(ws), nb,
                                 _ptr(out), _ptr(ss)))
     _assert_close(out.cpu().numpy()[:, :d], ref[2048:4096])
+
+
+@pytest.mark.parametrize("n,d,kind", [(4096, 512, "gauss"), (4096, 1024, "gauss"), (4225, 700, "gauss"),
+                                      (5000, 1024, "gmm"), (4500, 1000, "small")])
+def test_median_tensor_core_route_beyond_256_coordinates(ctx, n, d, kind):
+    """Leading dimension 512 / 768 / 1024: the K-streaming tcgen05 sweep (Sweep3Policy on the main loop of
+    panel_gemm.cuh) + contract recomputation of the candidates == the all-FFMA route == the C oracle,
+    bit for bit (compute_median.py:4-16 over abstract_kernel.py:33-35); one distance sweep."""
+    from stein_b200 import _lib
+    rng = np.random.default_rng(n + d)
+    if kind == "gmm":
+        X = _cloud("gmm", n, d, rng).astype(np.float32)
+    else:
+        X = rng.standard_normal((n, d)).astype(np.float32) * (0.01 if kind == "small" else 1.0)
+    tc = _median_with(ctx, X, _lib.MEDIAN_TC)
+    ff = _median_with(ctx, X, _lib.MEDIAN_FFMA)
+    assert tc[0].tobytes() == ff[0].tobytes()
+    assert (tc[1][0].tobytes(), tc[1][1].tobytes()) == (ff[1][0].tobytes(), ff[1][1].tobytes())
+    assert tc[2] == 1
+    if n <= 4500:
+        m_ref, mid_ref = orc.median_chain(X, radix=True)
+        assert tc[0].tobytes() == m_ref.tobytes()
+        assert (tc[1][0].tobytes(), tc[1][1].tobytes()) == (mid_ref[0].tobytes(), mid_ref[1].tobytes())
