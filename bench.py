@@ -149,6 +149,12 @@ def cpu_baseline(n, d, target_seconds=15.0):
             "interactions_per_sec": it_s * n * n}
 
 
+def workload_config(n, d, world):
+    """The `config` object both arms print (same keys, same values for the same workload)."""
+    return {"workload": "gaussian_target_n%d_d%d" % (n, d), "n_particles": n, "dim": d,
+            "optimizer": "adam", "parallelism": "particle_rows_x%d" % world}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -166,9 +172,9 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64",
             "data": "synthetic",
-            "config": {"workload": "gaussian_target_n%d_d%d" % (n, d), "n_particles": n, "dim": d,
-                       "note": "reference needs TensorFlow 1.12 (not installable); this is the NumPy/BLAS "
-                               "port of its per-iteration math on the host cores"},
+            "config": workload_config(n, d, args.gpus),
+            "note": "reference needs TensorFlow 1.12 (not installable); this is the NumPy/BLAS port of its "
+                    "per-iteration math on the host cores, timed on a bounded row slab and scaled by n/rows",
             "interactions_per_sec": v * n * n,
             "cpu_baseline": {k: sample[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -217,7 +223,19 @@ def run_ours(args):
         model.scores(eng)          # S = -X on the device
         eng.step()
 
-    for _ in range(args.warmup):
+    def timed_once():
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        one_step()
+        b.record()
+        barrier()
+        return a.elapsed_time(b)
+
+    # cold numbers (reported, not part of `value`): the very first iteration of the engine (no window
+    # hint: host-driven median, first-use allocations) ...
+    cold_first_ms = timed_once()
+    for _ in range(max(args.warmup - 1, 0)):
         one_step()
     barrier()
 
@@ -242,16 +260,31 @@ def run_ours(args):
     launches = ctx.launch_count - launches0
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     import ctypes
-    phi_ms, phi_n = ctypes.c_double(), ctypes.c_int64()
-    sw_ms, sw_n = ctypes.c_double(), ctypes.c_int64()
-    ctx.check(ctx.lib.stein_ctx_profile_read(ctx.handle, 0, ctypes.byref(phi_ms), ctypes.byref(phi_n)))
-    ctx.check(ctx.lib.stein_ctx_profile_read(ctx.handle, 1, ctypes.byref(sw_ms), ctypes.byref(sw_n)))
+
+    def region(k):
+        ms, cnt = ctypes.c_double(), ctypes.c_int64()
+        ctx.check(ctx.lib.stein_ctx_profile_read(ctx.handle, k, ctypes.byref(ms), ctypes.byref(cnt)))
+        return ms, cnt
+
+    phi_ms, phi_n = region(0)
+    sw_ms, sw_n = region(1)
+    regions = {name: region(k)[0].value / args.steps for k, name in
+               [(2, "median"), (3, "phi_prep"), (4, "phi_tail"), (5, "step_push"), (6, "collectives"), (7, "head")]}
     ctx.check(ctx.lib.stein_ctx_profile_enable(ctx.handle, 0))
+    route = ctx.phi_route()
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     info = eng.last()
+
+    # ... and a step whose median window hint misses (the particles jumped: the speculative sweep
+    # around the old window is wasted and the host-driven route runs, 2 sweeps)
+    eng.set_particles(eng.get_particles(np.float32) * np.float32(1.25))      # collective on a sharded engine
+    hint_miss_ms = timed_once()
+    hint_miss_sweeps = eng.last()["sweeps"]
+    eng.set_particles(eng.get_particles(np.float32) * np.float32(0.8))
+    one_step()
 
     # ---- end to end through the host-buffer entry point (what a NumPy caller of
     # update_particles(grads_array) sees): pinned fp32 scores in, particles out
@@ -270,6 +303,13 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
+    # where the end-to-end time goes: the particle download alone (PCIe), same buffers
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        eng.get_particles(np.float32, out=X_np)
+    d2h_ms = (time.perf_counter() - t0) / 5 * 1e3
+    config_e = run_config_e(args, ctx, world, rank, dev, barrier) if args.config_e_steps > 0 else None
     n_local, peer_push = eng.n_local, eng.peer_push
     eng.close()          # collective when the peers are connected (every rank is idle here)
 
@@ -287,39 +327,49 @@ def run_ours(args):
     achieved = f_phi / (phi_avg_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     code = args_phi_impl_code(ctx, args)
-    if code == 0:       # what AUTO resolves to (stein_b200/csrc/ctx.cu pick_phi_impl)
-        ldp = (d + 31) // 32 * 32
-        code = 5 if ldp == 256 else (2 if ldp == 128 else 1)
+    ldp = (d + 31) // 32 * 32
+    if code == 0:       # what AUTO resolves to (stein_b200/csrc/ctx.cu pick_phi_impl + the conditioning guard)
+        code = {"fast": 5, "precise": 6, "ffma": 1}.get(route["route"], 5) if ldp == 256 else (2 if ldp == 128 else 1)
     impl = {1: "dense_simt_fp32", 2: "flash_tcgen05", 3: "flash_tcgen05_cta_pair",
-            4: "flash_tcgen05_cta_pair_fp8_gemm2", 5: "flash_tcgen05_cta_pair_fp16_fp8"}[code]
+            4: "flash_tcgen05_cta_pair_fp8_gemm2", 5: "flash_tcgen05_cta_pair_fp16_fp8",
+            6: "flash_tcgen05_cta_pair_fp16x3"}[code]
     executed = {1: "FP32 FFMA", 2: "3 BF16 passes per GEMM", 3: "3 BF16 passes per GEMM",
                 4: "GEMM1 3 BF16 passes; GEMM2 1 FP16 + 2 FP8 passes",
-                5: "1 FP16 + 2 FP8 passes per GEMM (= 2 BF16-pass equivalents of tensor time each)"}[code]
+                5: "1 FP16 + 2 FP8 passes per GEMM (= 2 BF16-pass equivalents of tensor time each)",
+                6: "3 FP16 passes per GEMM"}[code]
+    # tensor work actually issued, in BF16-pass equivalents: 2 GEMMs of n_local x n x d, passes as above
+    passes = {1: 0.0, 2: 3.0, 3: 3.0, 4: 2.5, 5: 2.0, 6: 3.0}[code]
+    executed_tflops = passes * 2.0 * 2.0 * n_local * n * (ldp if code >= 2 else d) / (phi_ms.value / max(phi_n.value, 1) * 1e-3) / 1e12
     traffic, traffic_src = ncu_traffic("flash_phi2_kernel") if (code >= 3 and world == 1 and (n, d) == (N_PARTICLES, DIM)) \
         else (None, None)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "gaussian_target_n%d_d%d" % (n, d), "n_particles": n, "dim": d,
-                   "optimizer": "adam", "parallelism": "particle_rows_x%d" % world,
-                   "collectives": ("none" if world == 1 else
+        "config": workload_config(n, d, world),
+        "details": {"collectives": ("none" if world == 1 else
                                    "scores: NCCL all-gather on a side stream; particles: pushed to the peers by "
                                    "the optimizer kernel; small all-reduces: %s"
                                    % ("one kernel each over NVLink peer memory"
                                       if os.environ.get("STEIN_PEER_REDUCE", "1") != "0" else "NCCL")
                                    if peer_push else "NCCL (library-driven)"),
-                   "phi_impl": impl, "median_sweeps_last_step": info["sweeps"],
-                   "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set "
-                         "is also > 126 MB"},
+                    "phi_impl": impl, "phi_route": route, "median_sweeps_last_step": info["sweeps"],
+                    "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set "
+                          "is also > 126 MB"},
         "interactions_per_sec": value * n * n,
         "gpu_launches": int(launches),
         "wall_s_timed_region": wall,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "phi (%s)" % impl, "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                     "peak_source": peaks["source"] + ", bf16 dense sustained",
-                     "executed_arithmetic": executed,
+                     "unit": "TFLOP/s", "frac": achieved / peak,
+                     "frac_burst": achieved / peaks["bf16_tflops"], "peak_burst": peaks["bf16_tflops"],
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "traffic_kind": "static (one ncu --set full capture of this kernel at this shape, committed "
+                                     "under profiles/; not re-measured by this run)" if traffic is not None else None,
+                     "peak_source": peaks["source"] + ": `peak` = bf16 dense sustained (seconds-long loop under the "
+                                    "power cap), `peak_burst` = best of 10 in isolation; the timed region here is "
+                                    "short, so frac_burst is the conservative reading",
+                     "executed_arithmetic": executed, "executed_bf16_equiv_tflops": executed_tflops,
                      "algorithmic_flops_per_launch": f_phi, "avg_launch_ms": phi_avg_ms,
                      "launches_timed": int(phi_n.value),
                      "share_of_step": phi_ms.value / total_ms if world == 1 else None,
@@ -330,12 +380,101 @@ def run_ours(args):
                 "call": "stein_engine_update_particles_host (pinned fp32 scores H2D -> iteration -> "
                         "particles D2H), max over ranks of wall time"},
         "bandwidth_last_step": info["bandwidth"],
+        # device time per iteration by phase (CUDA events on the ctx stream, rank 0): head = barrier /
+        # all-gather of the particles + row norms; median = the whole median call including its host round
+        # trip (the sweep is part of it); phi_prep = centring, guard, operand arrays; phi = main kernel;
+        # phi_tail = finalize + sum(phi^2); step_push = clip + optimizer (+ peer push); collectives = the
+        # all-reduce kernels (already contained in median / phi_tail / head); idle = the rest of the step
+        "phases_ms": dict(regions, phi=phi_ms.value / args.steps, sweep=sw_ms.value / args.steps,
+                          idle=ms_per_step - (regions["head"] + regions["median"] + regions["phi_prep"] +
+                                              phi_ms.value / args.steps + regions["phi_tail"] + regions["step_push"])),
+        "cold": {"first_iteration_ms": cold_first_ms, "hint_miss_step_ms": hint_miss_ms,
+                 "hint_miss_sweeps": hint_miss_sweeps,
+                 "note": "not part of `value`: the timed steps ride the previous iteration's median window "
+                         "(1 sweep); a step after a jump of the particles pays 2 sweeps"},
     }
+    line["e2e"]["d2h_ms_alone"] = d2h_ms
+    line["e2e"]["note"] = ("synchronous contract (the caller holds the new particles when the call returns): the "
+                           "%.1f MB download crosses PCIe after the optimizer kernel and cannot overlap it; "
+                           "scores upload overlaps the median" % (X_np.nbytes / 1e6))
+    if config_e is not None:
+        line["config_e"] = config_e
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(n, d, target_seconds=args.ref_seconds)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_config_e(args, ctx, world, rank, dev, barrier):
+    """BASELINE.json configs[4]: Gaussian-mixture target (means +-2 e1, +-2 e2, sigma = 1), n = 262 144 particles,
+    d = 1 024, particle rows sharded over the ranks, global exact median bandwidth.  A sub-record of the
+    bench line (the headline `value` stays on config D).  Never raises: an error is reported in the record."""
+    import ctypes
+    import torch
+    rec = {"workload": "gaussian_mixture_n%d_d%d" % (args.config_e_n, args.config_e_d), "n_particles": args.config_e_n,
+           "dim": args.config_e_d, "n_gpus": world, "steps": args.config_e_steps}
+    try:
+        from stein_b200.engine import SvgdEngine
+        from stein_b200.log_p import GaussianMixtureTarget
+        n, d = args.config_e_n, args.config_e_d
+        eng = SvgdEngine(n, d, "adam", learning_rate=1e-2, ctx=ctx)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1234 + rank)
+        Xl = eng.particles_dev
+        Xl[:eng.n_local, :d] = torch.randn((eng.n_local, d), generator=gen, device=dev, dtype=torch.float32)
+        means = np.zeros((4, d), np.float32)
+        means[0, 0], means[1, 0], means[2, 1], means[3, 1] = 2, -2, 2, -2
+        model = GaussianMixtureTarget(d, means=means)
+
+        def step():
+            model.scores(eng)
+            eng.step()
+
+        step()                                  # cold: host-driven median, allocations
+        barrier()
+        ctx.check(ctx.lib.stein_ctx_profile_enable(ctx.handle, 1))
+        for k in range(8):
+            ctx.lib.stein_ctx_profile_read(ctx.handle, k, None, None)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(args.config_e_steps):
+            step()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b) / args.config_e_steps
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+        def region(k):
+            v, c = ctypes.c_double(), ctypes.c_int64()
+            ctx.check(ctx.lib.stein_ctx_profile_read(ctx.handle, k, ctypes.byref(v), ctypes.byref(c)))
+            return v.value / args.config_e_steps
+        phi_ms, sweep_ms, median_ms = region(0), region(1), region(2)
+        ctx.check(ctx.lib.stein_ctx_profile_enable(ctx.handle, 0))
+        info, route = eng.last(), ctx.phi_route()
+        n_local = eng.n_local
+        eng.close()
+        peaks = load_peaks()
+        f_phi = algorithmic_flops_phi(n, d) * (n_local / float(n))
+        ach = f_phi / (phi_ms * 1e-3) / 1e12
+        rec.update({
+            "ms_per_step": ms, "value": 1000.0 / ms, "unit": UNIT, "interactions_per_sec": 1000.0 / ms * n * n,
+            "bandwidth_last_step": info["bandwidth"], "median_sweeps_last_step": info["sweeps"], "phi_route": route,
+            "phases_ms": {"phi_panel_kernels": phi_ms, "median": median_ms, "sweep": sweep_ms},
+            "roofline": {"bound": "tensor", "kernel": "phi panel kernels (exp-GEMM + P.Y GEMM, FP16 + 2 FP8 passes each)",
+                         "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": ach / peaks["bf16_tflops_sustained"], "frac_burst": ach / peaks["bf16_tflops"],
+                         "algorithmic_flops_per_launch_group": f_phi, "traffic": None},
+            "data": "synthetic: X ~ N(0, I) per rank, scores by stein_score_gaussian_mixture on the device",
+        })
+    except Exception as exc:          # the headline record must survive a failure here
+        rec["error"] = "%s: %s" % (type(exc).__name__, exc)
+    return rec
 
 
 def args_phi_impl_code(ctx, args):
@@ -355,6 +494,10 @@ def main():
     ap.add_argument("--phi-impl", default=None, choices=[None, "auto", "dense", "flash", "flash2", "flash3", "flash4"])
     ap.add_argument("--ref-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config-e-steps", type=int, default=2,
+                    help="timed iterations of the config-E sub-record (n = 262 144, d = 1 024); 0 = skip")
+    ap.add_argument("--config-e-n", type=int, default=262144)
+    ap.add_argument("--config-e-d", type=int, default=1024)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

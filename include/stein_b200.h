@@ -119,11 +119,18 @@ int stein_ctx_phi_route(stein_ctx *ctx, int32_t *route, float *kappa, float *pre
 int stein_ctx_set_phi_guard_tol(stein_ctx *ctx, float tol);
 
 /* Optional per-region device timing (CUDA events on the ctx stream), used by
- * bench.py for the live roofline figure.  Regions: 0 = phi main kernel(s),
- * 1 = median distance sweeps.  read() synchronises the stream, returns the
- * accumulated milliseconds and launch count since the last reset, and resets. */
-#define STEIN_REGION_PHI 0
-#define STEIN_REGION_SWEEP 1
+ * bench.py for the live roofline figure and the per-phase timeline of an iteration.
+ * read() synchronises the stream, returns the accumulated milliseconds and the number
+ * of timed intervals of that region since the last reset, and resets. */
+#define STEIN_REGION_PHI 0        /* phi main kernel(s)                                          */
+#define STEIN_REGION_SWEEP 1      /* median distance sweep(s)                                    */
+#define STEIN_REGION_MEDIAN 2     /* whole median call: split, pilot, sweep, band, select, host round trip (contains 1 and part of 6) */
+#define STEIN_REGION_PHI_PREP 3   /* phi call up to its main kernel: centring, guard, operand arrays */
+#define STEIN_REGION_PHI_TAIL 4   /* finalize + sum(phi^2)                                        */
+#define STEIN_REGION_OPT 5        /* clip + optimizer kernel (+ peer push)                        */
+#define STEIN_REGION_COLL 6       /* collectives of the iteration (all-reduces, barrier word, all-gathers on the ctx stream) */
+#define STEIN_REGION_HEAD 7       /* start of the iteration: barrier / all-gather of the particles, row norms */
+#define STEIN_REGION_COUNT 8
 int stein_ctx_profile_enable(stein_ctx *ctx, int enable);
 int stein_ctx_profile_read(stein_ctx *ctx, int region, double *ms_total, int64_t *launches);
 

@@ -67,7 +67,7 @@ struct stein_ctx {
     int64_t pilot_cap = 0;
     // optional region timing (bench.py): event pairs recorded on `stream`
     bool profile = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[2];
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[STEIN_REGION_COUNT];
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;
 };
 

@@ -87,7 +87,7 @@ int stein_ctx_destroy(stein_ctx *ctx) {
     if (ctx->d_guard) cudaFree(ctx->d_guard);
     if (ctx->h_guard) cudaFreeHost(ctx->h_guard);
     if (ctx->ev_guard) cudaEventDestroy(ctx->ev_guard);
-    for (int r = 0; r < 2; ++r)
+    for (int r = 0; r < STEIN_REGION_COUNT; ++r)
         for (auto &ev : ctx->prof_events[r]) ctx->prof_pool.push_back(ev);
     for (auto &ev : ctx->prof_pool) {
         cudaEventDestroy(ev.first);
@@ -144,7 +144,7 @@ int stein_ctx_profile_enable(stein_ctx *ctx, int enable) {
 
 int stein_ctx_profile_read(stein_ctx *ctx, int region, double *ms_total, int64_t *launches) {
     STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
-    STEIN_REQUIRE(ctx, region == STEIN_REGION_PHI || region == STEIN_REGION_SWEEP, "unknown region");
+    STEIN_REQUIRE(ctx, region >= 0 && region < STEIN_REGION_COUNT, "unknown region");
     STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     double total = 0.0;
     for (auto &ev : ctx->prof_events[region]) {

@@ -275,6 +275,7 @@ static int step_bandwidth(stein_engine *e, float *bw_out) {
     stein_ctx *ctx = e->ctx;
     const int64_t rows_all = e->q * e->world;
     ctx->xprep.X = nullptr;
+    RegionTimer head(ctx, STEIN_REGION_HEAD);
     if (e->world > 1) {
         if (e->peers_open && e->x_all_current) {
             // every rank pushed its updated rows into this buffer during its last optimizer
@@ -289,6 +290,7 @@ static int step_bandwidth(stein_engine *e, float *bw_out) {
     }
     // abstract_kernel.py:34 -- r = sum(T*T, 1), contract order
     STEIN_TRY(stein_row_norms(ctx, e->X_all, rows_all, e->d, e->ld, e->r_all));
+    head.stop();
     if (e->fixed_bw > 0.0f) {
         e->last_med = nanf("");
         e->last_bw = e->fixed_bw;
@@ -302,8 +304,10 @@ static int step_bandwidth(stein_engine *e, float *bw_out) {
     ctx->median_owner = reinterpret_cast<const void *>(e->uid);
     ctx->presync_fn = engine_presync;
     ctx->presync_arg = e;
+    RegionTimer mtimer(ctx, STEIN_REGION_MEDIAN);
     const int mrc = stein_median_sqdist(ctx, e->X_all, e->r_all, e->n_total, e->d, e->ld, &med, nullptr,
                                         &e->last_sweeps);
+    mtimer.stop();
     ctx->median_owner = nullptr;
     ctx->presync_fn = nullptr;
     ctx->presync_arg = nullptr;
@@ -347,6 +351,7 @@ static int step_update(stein_engine *e, float bw, bool scores_gathered) {
         for (int r = 0; r < e->world; ++r)
             if (r != e->rank) peers.dst[peers.n++] = reinterpret_cast<float4 *>(e->peer_X[r] + (int64_t)e->rank * e->q * e->ld);
     }
+    RegionTimer otimer(ctx, STEIN_REGION_OPT);
     if (e->opt == STEIN_OPT_ADAM) {
         STEIN_TRY(clip_adam_step(ctx, e->X_local(), e->phi, e->m1, e->m2, count, e->sumsq, e->lr, e->p1, e->p2,
                                  e->n_iters, peers));

@@ -144,6 +144,7 @@ static int peer_reduce_run(stein_ctx *ctx, void *buf, int64_t count, bool f64) {
 // The all-reduces of the library: over peer memory when an engine has installed its mailboxes
 // and the vector fits a slot, else through the hook of stein_comm.
 int allreduce_u64(stein_ctx *ctx, void *buf_dev, int64_t count) {
+    RegionTimer timer(ctx, STEIN_REGION_COLL);
     if (ctx->peer_reduce && count <= MB_CAP) return peer_reduce_run(ctx, buf_dev, count, false);
     if (ctx->comm.allreduce_sum_u64(ctx->comm.user, buf_dev, count) != 0)
         return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
@@ -151,6 +152,7 @@ int allreduce_u64(stein_ctx *ctx, void *buf_dev, int64_t count) {
 }
 
 int allreduce_f64(stein_ctx *ctx, void *buf_dev, int64_t count) {
+    RegionTimer timer(ctx, STEIN_REGION_COLL);
     if (ctx->peer_reduce && count <= MB_CAP) return peer_reduce_run(ctx, buf_dev, count, true);
     if (ctx->comm.allreduce_sum_f64(ctx->comm.user, buf_dev, count) != 0)
         return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_f64 hook failed");

@@ -1757,6 +1757,7 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
         return STEIN_OK;
     }
 
+    RegionTimer prep_timer(ctx, STEIN_REGION_PHI_PREP);
     const float l2e = 1.4426950408889634f;
     dim3 gy((unsigned)(cols / 32), (unsigned)(DP / 32)), by(32, 8);
     // what every route of the column-scaled modes needs: the column maxima / scales of Y
@@ -1856,6 +1857,7 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
+    prep_timer.stop();
     {
         RegionTimer timer(ctx, STEIN_REGION_PHI);
         if (mode == 0)
@@ -1868,6 +1870,7 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
             flash_phi2_kernel<2, 2><<<2 * G2, FL_THREADS, smem, ctx->stream>>>(maps, p);
         STEIN_CHECK_LAUNCH(ctx);
     }
+    RegionTimer tail_timer(ctx, STEIN_REGION_PHI_TAIL);
     const int64_t rows_valid = std::max<int64_t>(0, std::min<int64_t>(n_local, n_total - row_begin));
     const int64_t total4 = rows * ld / 4;
     const int blocks = (int)std::min<int64_t>((total4 + 255) / 256, FINALIZE_MAX_BLOCKS);

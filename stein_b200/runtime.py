@@ -71,14 +71,15 @@ class Context:
     def rows_padded(self, n):
         return int(self.lib.stein_rows_padded(n))
 
-    def to_padded(self, array):
-        """host (n x d) -> zero-padded fp32 device tensor (rows_padded x ld)."""
+    def to_padded(self, array, ld=None):
+        """host (n x d) -> zero-padded fp32 device tensor (rows_padded x ld); ld defaults to stein_ld(d)
+        (pass 128 / 256 / 512 / 768 / 1024 to make the matrix eligible for the tensor-core kernels)."""
         torch = _torch()
         a = np.ascontiguousarray(np.asarray(array, dtype=np.float32))
         if a.ndim != 2:
             raise ValueError("expected a 2-D (n_particles x n_params) array")
         n, d = a.shape
-        out = torch.zeros((self.rows_padded(n), self.ld(d)), dtype=torch.float32,
+        out = torch.zeros((self.rows_padded(n), int(ld) if ld else self.ld(d)), dtype=torch.float32,
                           device="cuda:%d" % self.device)
         out[:n, :d] = torch.from_numpy(a).to(out.device)
         return out

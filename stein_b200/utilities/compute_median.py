@@ -35,7 +35,12 @@ def median_sqdist(theta, return_middle=False):
     ctx = context()
     a = np.asarray(theta, dtype=np.float32)
     n, d = a.shape
-    X = ctx.to_padded(a)
+    # like stein_engine_create: many particles of up to 1 024 coordinates get a leading dimension the
+    # tensor-core kernels take (the zero pad columns are extra coordinates: same distances)
+    ld = None
+    if n >= 2048 and d <= 1024:
+        ld = 128 if d <= 128 else -(-d // 256) * 256
+    X = ctx.to_padded(a, ld)
     import torch
     r = torch.empty(X.shape[0], dtype=torch.float32, device=X.device)
     ctx.check(ctx.lib.stein_row_norms(ctx.handle, ptr(X), n, d, X.shape[1], ptr(r)))

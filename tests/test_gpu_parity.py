@@ -191,12 +191,12 @@ def test_kernel_and_grad_matches_oracle(ctx, n, d):
     _assert_close(dK, dK_ref, 2e-5)
 
 
-def _phi_gpu(ctx, X, S, impl):
+def _phi_gpu(ctx, X, S, impl, ld=None):
     """stein_row_norms -> stein_median_sqdist -> stein_phi through the C ABI."""
     import torch
     from stein_b200 import _lib
     n, d = X.shape
-    Xd, Sd = ctx.to_padded(X), ctx.to_padded(S)
+    Xd, Sd = ctx.to_padded(X, ld), ctx.to_padded(S, ld)
     rows, ld = Xd.shape
     r = torch.empty(rows, dtype=torch.float32, device=Xd.device)
     ctx.check(ctx.lib.stein_row_norms(ctx.handle, _ptr(Xd), n, d, ld, _ptr(r)))
@@ -205,7 +205,7 @@ def _phi_gpu(ctx, X, S, impl):
     bw = ctx.lib.stein_bandwidth(med.value, n)
     ctx.set_phi_impl(impl)
     try:
-        nb = int(ctx.lib.stein_phi_workspace_bytes(ctx.handle, n, n, d))
+        nb = int(ctx.lib.stein_phi_workspace_bytes(ctx.handle, n, n, ld))
         ws = torch.empty(nb, dtype=torch.uint8, device=Xd.device)
         phi = torch.full_like(Xd, float("nan"))
         sumsq = torch.zeros(1, dtype=torch.float64, device=Xd.device)
@@ -1188,7 +1188,7 @@ def test_phi_panel_kernels_match_oracle(ctx, n, d, mode):
     X = _particles(n, d, 3 * n + d)
     S = _particles(n, d, 5 * n + d) - X
     code = {"fast": _lib.PHI_FLASH_TC4, "precise": _lib.PHI_FLASH_TC5, "auto": _lib.PHI_AUTO}[mode]
-    phi, sumsq, bw = _phi_gpu(ctx, X, S, code)
+    phi, sumsq, bw = _phi_gpu(ctx, X, S, code, ld=-(-d // 256) * 256)      # what the engine pads such rows to
     ref = orc.compute_phi(X, S.astype(np.float64))
     assert bw.tobytes() == orc.kernel_and_grad(X)[2].tobytes()
     fro, mx = _rel(phi, ref)
