@@ -213,6 +213,21 @@ int stein_kernel_and_grad(stein_ctx *ctx, const float *X_dev, const float *r_dev
                           int64_t d, int64_t ld, float bandwidth, float *K_dev, int64_t ldk,
                           float *dK_dev, void *workspace_dev, int64_t workspace_bytes);
 
+/* ---- other kernel operators through the plugin point ----------------
+ * replaces  AbstractKernel.kernel_and_grad  stein/kernels/abstract_kernel.py:45-62  for an inverse
+ * multiquadric kernel K_ij = (1 + D_ij / h^2)^beta (beta < 0), with the reference's gradient recipe
+ * dK = -0.5 d(sum K)/d theta (squared_exponential_kernel.py:23,32).  Dense, small n, same layout as
+ * stein_kernel_and_grad.                                                                     */
+int stein_imq_kernel_and_grad(stein_ctx *ctx, const float *X_dev, const float *r_dev, int64_t n,
+                              int64_t d, int64_t ld, float bandwidth, float beta, float *K_dev,
+                              int64_t ldk, float *dK_dev, void *workspace_dev, int64_t workspace_bytes);
+/* replaces  AbstractSteinSampler.compute_phi  abstract_stein_sampler.py:100-105  for ANY kernel
+ * operator: phi = (K S + dK) / n from a dense K (rows_padded(n) x ldk, pads zero) and dK (n x ld) as a
+ * kernel_and_grad returned them; sum(phi^2) -> *sumsq_dev.  workspace: rows_padded(n)*ld*4 + 9 480 bytes. */
+int stein_phi_from_kernel(stein_ctx *ctx, const float *K_dev, int64_t ldk, const float *dK_dev,
+                          const float *S_dev, int64_t n, int64_t d, int64_t ld, void *workspace_dev,
+                          int64_t workspace_bytes, float *phi_dev, double *sumsq_dev);
+
 /* ---- kernel (4): norm clip + optimizer step --------------------------------
  * replaces  AbstractSteinSampler.update_particles  abstract_stein_sampler.py:125-126
  *           AdamGradientDescent.update             adam_gradient_descent.py:41-58
@@ -291,6 +306,11 @@ int stein_engine_step(stein_engine *eng);
  * -- no clip, no optimizer step.  For callers that bring their own AbstractGradientDescent
  * (stein/optimizers/abstract_gradient_descent.py:32-52). */
 int stein_engine_phi_only(stein_engine *eng);
+/* clip + optimizer step (abstract_stein_sampler.py:125-126) on the phi and sum(phi^2) that are already
+ * in the engine's buffers (stein_engine_buffers / stein_engine_sumsq_dev), e.g. written by
+ * stein_phi_from_kernel for a user-defined kernel operator.  Single-GPU engines. */
+int stein_engine_apply_phi(stein_engine *eng);
+int stein_engine_sumsq_dev(stein_engine *eng, double **sumsq_dev);
 /* optimizer hyper-parameters for the following steps (the reference reads learning_rate / decay /
  * betas from the gd object at every update(), adam_gradient_descent.py:41-58) */
 int stein_engine_set_hyper(stein_engine *eng, double learning_rate, double decay, double p1, double p2);

@@ -158,6 +158,26 @@ def kernel_and_grad(theta, chain=True):
     return K, dK, bw
 
 
+def imq_kernel_and_grad(theta, beta=-0.5, chain=True):
+    """An inverse multiquadric operator behind the reference's plugin point
+    (stein/kernels/abstract_kernel.py:45-62), built with the reference's recipes: the distance matrix and
+    bandwidth of abstract_kernel.py:33-40, K = (1 + D / h^2)^beta in fp32, and
+    dK = -0.5 * d(sum K)/d theta_i (squared_exponential_kernel.py:23,32)
+       = (-2 beta / h^2) (x_i sum_j G_ij - sum_j G_ij x_j),  G = (1 + D / h^2)^(beta - 1).
+    Returns (K fp32, dK fp32, bandwidth fp32).  tests/test_oracle.py checks the closed form of dK
+    against torch autograd of sum(K)."""
+    T = _f32(theta)
+    D = sqdist_chain(T) if chain else sqdist(T)
+    h = bandwidth(compute_median(D), T.shape[0])
+    h2 = np.float32(h) * np.float32(h)
+    base = np.float32(1.0) + np.maximum(D, np.float32(0.0)) / h2
+    K = np.power(base, np.float32(beta)).astype(np.float32)
+    G = np.power(base, np.float32(beta - 1.0)).astype(np.float32)
+    coef = np.float32(-2.0 * beta) / h2
+    dK = ((T * G.sum(axis=1, dtype=np.float32)[:, None] - G @ T) * coef).astype(np.float32)
+    return K, dK, h
+
+
 def compute_phi(theta_array, grads_array, chain=True):
     """stein/samplers/abstract_stein_sampler.py:100-105: float64 NumPy GEMM of
     the fp32 K against the (float64) score matrix, plus the fp32 dK, over n."""

@@ -71,6 +71,10 @@ SIGNATURES = {
                                  c_vp, c_i64, c_vp, c_vp]),
     "stein_kernel_and_grad": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_vp,
                                              c_i64, c_vp, c_vp, c_i64]),
+    "stein_imq_kernel_and_grad": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_vp,
+                                                 c_i64, c_vp, c_vp, c_i64]),
+    "stein_phi_from_kernel": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64,
+                                             c_vp, c_vp]),
     "stein_clip_adam_step": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_f64, c_f64,
                                             c_f64, c_i64]),
     "stein_clip_adagrad_step": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_f64, c_f64,
@@ -96,6 +100,8 @@ SIGNATURES = {
     "stein_engine_get_phi": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int]),
     "stein_engine_step": (ctypes.c_int, [c_vp]),
     "stein_engine_phi_only": (ctypes.c_int, [c_vp]),
+    "stein_engine_apply_phi": (ctypes.c_int, [c_vp]),
+    "stein_engine_sumsq_dev": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp)]),
     "stein_engine_set_hyper": (ctypes.c_int, [c_vp, c_f64, c_f64, c_f64, c_f64]),
     "stein_engine_update_particles_host": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int]),
     "stein_engine_ipc_handle": (ctypes.c_int, [c_vp, c_vp]),

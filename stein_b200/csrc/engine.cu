@@ -337,10 +337,17 @@ static int step_phi(stein_engine *e, float bw, bool scores_gathered) {
     return STEIN_OK;
 }
 
+static int step_optimizer(stein_engine *e);
+
 // Phase 2: phi, clip, optimizer step.
 static int step_update(stein_engine *e, float bw, bool scores_gathered) {
-    stein_ctx *ctx = e->ctx;
     STEIN_TRY(step_phi(e, bw, scores_gathered));
+    return step_optimizer(e);
+}
+
+// Phase 2b: clip + optimizer on the phi / sum(phi^2) in the engine's buffers.
+static int step_optimizer(stein_engine *e) {
+    stein_ctx *ctx = e->ctx;
     // abstract_stein_sampler.py:125-126
     const int64_t count = e->q * e->ld;
     // peers: the same rows inside the other ranks' X_all.  Safe to overwrite now: the all-reduce
@@ -427,6 +434,20 @@ int stein_engine_phi_only(stein_engine *e) {
     float bw = 0.f;
     STEIN_TRY(step_bandwidth(e, &bw));
     return step_phi(e, bw, false);
+}
+
+int stein_engine_apply_phi(stein_engine *e) {
+    if (!e) return STEIN_ERR_INVALID;
+    stein_ctx *ctx = e->ctx;
+    STEIN_REQUIRE(ctx, e->world == 1, "stein_engine_apply_phi: single-GPU engines only");
+    STEIN_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return step_optimizer(e);
+}
+
+int stein_engine_sumsq_dev(stein_engine *e, double **sumsq_dev) {
+    if (!e || !sumsq_dev) return STEIN_ERR_INVALID;
+    *sumsq_dev = e->sumsq;
+    return STEIN_OK;
 }
 
 int stein_engine_set_hyper(stein_engine *e, double learning_rate, double decay, double p1, double p2) {

@@ -19,10 +19,17 @@
 
 namespace stein {
 
-// K[i, j] = exp(-D_ij / h2 / 2) for local rows i (global row row0 + i) x all columns
+// Kernel functions of the squared distance (the plugin point stein/kernels/abstract_kernel.py:45-62):
+//   KF_SE   exp(-D / h^2 / 2)                      squared_exponential_kernel.py:22
+//   KF_IMQ  (1 + D / h^2)^beta                     inverse multiquadric (beta < 0; not in the reference)
+// KF_IMQ with beta - 1 gives the weights of its gradient term.
+constexpr int KF_SE = 0, KF_IMQ = 1;
+
+// K[i, j] = k(D_ij) for local rows i (global row row0 + i) x all columns
+template <int KF>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
-gram_exp_kernel(const float *__restrict__ X, const float *__restrict__ r, int64_t n, int64_t ld,
-                int64_t row0, float h2, float *__restrict__ K, int64_t ldk) {
+gram_fn_kernel(const float *__restrict__ X, const float *__restrict__ r, int64_t n, int64_t ld,
+               int64_t row0, float h2, float beta, float *__restrict__ K, int64_t ldk) {
     __shared__ GemmSmem gs;
     const int64_t m0 = row0 + (int64_t)blockIdx.y * TILE;   // global particle row of the tile
     const int64_t n0 = (int64_t)blockIdx.x * TILE;
@@ -43,7 +50,8 @@ gram_exp_kernel(const float *__restrict__ X, const float *__restrict__ r, int64_
             const int64_t j = n0 + acc_col(c);
             const float dist = (ri[a] + rj[c]) - 2.0f * acc[a][c];
             // squared_exponential_kernel.py:22 -- exp(-D / square(bandwidth) / 2.)
-            out[c] = (i < n && j < n) ? expf(-dist / h2 / 2.0f) : 0.0f;
+            const float kv = KF == KF_SE ? expf(-dist / h2 / 2.0f) : powf(1.0f + fmaxf(dist, 0.0f) / h2, beta);
+            out[c] = (i < n && j < n) ? kv : 0.0f;
         }
         float *dst = K + (i - row0) * ldk + n0;
         const int tx = threadIdx.x % 16;
@@ -235,8 +243,8 @@ int phi_dense(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
     for (int64_t s0 = 0; s0 < rows; s0 += slab) {
         const int64_t sr = std::min(slab, rows - s0);
         dim3 g1((unsigned)(cols / TILE), (unsigned)(sr / TILE));
-        gram_exp_kernel<<<g1, GEMM_THREADS, 0, ctx->stream>>>(X_all, r_all, n_total, ld,
-                                                              row_begin + s0, h2, K, cols);
+        gram_fn_kernel<KF_SE><<<g1, GEMM_THREADS, 0, ctx->stream>>>(X_all, r_all, n_total, ld, row_begin + s0, h2, 0.0f,
+                                                                    K, cols);
         STEIN_CHECK_LAUNCH(ctx);
         rowsum_kernel<<<(unsigned)((sr + 7) / 8), 256, 0, ctx->stream>>>(K, sr, cols, cols, ksum + s0);
         STEIN_CHECK_LAUNCH(ctx);
@@ -268,7 +276,7 @@ extern "C" int stein_kernel_and_grad(stein_ctx *ctx, const float *X_dev, const f
     float *ksum = KX + rows * ld;
     const float h2 = bandwidth * bandwidth;
     dim3 g1((unsigned)(rows / TILE), (unsigned)(rows / TILE));
-    gram_exp_kernel<<<g1, GEMM_THREADS, 0, ctx->stream>>>(X_dev, r_dev, n, ld, 0, h2, K_dev, ldk);
+    gram_fn_kernel<KF_SE><<<g1, GEMM_THREADS, 0, ctx->stream>>>(X_dev, r_dev, n, ld, 0, h2, 0.0f, K_dev, ldk);
     STEIN_CHECK_LAUNCH(ctx);
     rowsum_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ctx->stream>>>(K_dev, rows, rows, ldk, ksum);
     STEIN_CHECK_LAUNCH(ctx);
@@ -278,6 +286,92 @@ extern "C" int stein_kernel_and_grad(stein_ctx *ctx, const float *X_dev, const f
     const int64_t total = rows * ld;
     dk_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(X_dev, KX, ksum, n, rows, ld,
                                                                        1.0f / h2, dK_dev);
+    STEIN_CHECK_LAUNCH(ctx);
+    return STEIN_OK;
+}
+
+
+// Inverse multiquadric kernel through the same plugin point:
+//   K_ij  = (1 + D_ij / h^2)^beta,  beta < 0
+//   dK_i  = -0.5 d(sum K)/d theta_i   (the reference's recipe, squared_exponential_kernel.py:23,32)
+//         = (-2 beta / h^2) (x_i sum_j G_ij - sum_j G_ij x_j),   G_ij = (1 + D_ij / h^2)^(beta - 1)
+// Dense (small n), like stein_kernel_and_grad: G is formed in the K buffer first, then K itself.
+extern "C" int stein_imq_kernel_and_grad(stein_ctx *ctx, const float *X_dev, const float *r_dev, int64_t n,
+                                         int64_t d, int64_t ld, float bandwidth, float beta, float *K_dev,
+                                         int64_t ldk, float *dK_dev, void *ws, int64_t ws_bytes) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    STEIN_REQUIRE(ctx, X_dev && r_dev && K_dev && dK_dev && ws, "null pointer");
+    STEIN_REQUIRE(ctx, ld >= d && ld % LD_ALIGN == 0, "bad ld");
+    STEIN_REQUIRE(ctx, beta < 0.0f && beta > -64.0f, "beta must be negative");
+    STEIN_REQUIRE(ctx, bandwidth > 0.0f, "bandwidth must be positive");
+    const int64_t rows = stein_rows_padded(n);
+    STEIN_REQUIRE(ctx, ldk >= rows && ldk % 4 == 0, "ldk=%lld must be >= %lld and a multiple of 4",
+                  (long long)ldk, (long long)rows);
+    STEIN_REQUIRE(ctx, ws_bytes >= rows * ld * 4 + rows * 4, "workspace too small");
+    float *GX = (float *)ws;
+    float *gsum = GX + rows * ld;
+    const float h2 = bandwidth * bandwidth;
+    dim3 g1((unsigned)(rows / TILE), (unsigned)(rows / TILE));
+    gram_fn_kernel<KF_IMQ><<<g1, GEMM_THREADS, 0, ctx->stream>>>(X_dev, r_dev, n, ld, 0, h2, beta - 1.0f, K_dev, ldk);
+    STEIN_CHECK_LAUNCH(ctx);
+    rowsum_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ctx->stream>>>(K_dev, rows, rows, ldk, gsum);
+    STEIN_CHECK_LAUNCH(ctx);
+    dim3 g2((unsigned)((ld + TILE - 1) / TILE), (unsigned)(rows / TILE));
+    gemm_nn_kernel<<<g2, GEMM_THREADS, 0, ctx->stream>>>(K_dev, ldk, rows, X_dev, ld, GX, ld);
+    STEIN_CHECK_LAUNCH(ctx);
+    const int64_t total = rows * ld;
+    dk_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(X_dev, GX, gsum, n, rows, ld, -2.0f * beta / h2,
+                                                                       dK_dev);
+    STEIN_CHECK_LAUNCH(ctx);
+    gram_fn_kernel<KF_IMQ><<<g1, GEMM_THREADS, 0, ctx->stream>>>(X_dev, r_dev, n, ld, 0, h2, beta, K_dev, ldk);
+    STEIN_CHECK_LAUNCH(ctx);
+    return STEIN_OK;
+}
+
+namespace stein {
+// phi = (K S + dK) / n, block partial of sum(phi^2)
+__global__ void __launch_bounds__(256)
+phi_from_kernel_finalize(const float *__restrict__ KS, const float *__restrict__ dK, int64_t rows_valid, int64_t rows,
+                         int64_t ld, float inv_n, float *__restrict__ phi, double *__restrict__ partials) {
+    double local = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < rows * ld; e += (int64_t)gridDim.x * blockDim.x) {
+        const float v = (e / ld) < rows_valid ? (KS[e] + dK[e]) * inv_n : 0.0f;
+        phi[e] = v;
+        local += (double)v * v;
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = local;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = red[0];
+}
+}  // namespace stein
+
+// compute_phi for ANY kernel operator (abstract_stein_sampler.py:100-105): K (n x n, device, leading
+// dimension ldk, pad rows / columns zero) and dK (n x ld) as an AbstractKernel.kernel_and_grad returned
+// them, S the scores: phi = (K S + dK) / n on the device, sum(phi^2) for the clip.
+extern "C" int stein_phi_from_kernel(stein_ctx *ctx, const float *K_dev, int64_t ldk, const float *dK_dev,
+                                     const float *S_dev, int64_t n, int64_t d, int64_t ld, void *ws,
+                                     int64_t ws_bytes, float *phi_dev, double *sumsq_dev) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    STEIN_REQUIRE(ctx, K_dev && dK_dev && S_dev && ws && phi_dev && sumsq_dev, "null pointer");
+    STEIN_REQUIRE(ctx, n >= 1 && d >= 1 && ld >= d && ld % LD_ALIGN == 0, "bad shape");
+    const int64_t rows = stein_rows_padded(n);
+    STEIN_REQUIRE(ctx, ldk >= rows && ldk % 4 == 0, "ldk=%lld must be >= %lld and a multiple of 4",
+                  (long long)ldk, (long long)rows);
+    STEIN_REQUIRE(ctx, ws_bytes >= rows * ld * 4 + FINALIZE_MAX_BLOCKS * 8 + 8, "workspace too small");
+    float *KS = (float *)ws;
+    double *partials = (double *)(((uintptr_t)(KS + rows * ld) + 7) & ~(uintptr_t)7);
+    dim3 g2((unsigned)((ld + TILE - 1) / TILE), (unsigned)(rows / TILE));
+    gemm_nn_kernel<<<g2, GEMM_THREADS, 0, ctx->stream>>>(K_dev, ldk, rows, S_dev, ld, KS, ld);
+    STEIN_CHECK_LAUNCH(ctx);
+    const int blocks = (int)std::min<int64_t>((rows * ld + 255) / 256, FINALIZE_MAX_BLOCKS);
+    phi_from_kernel_finalize<<<blocks, 256, 0, ctx->stream>>>(KS, dK_dev, n, rows, ld, 1.0f / (float)n, phi_dev, partials);
+    STEIN_CHECK_LAUNCH(ctx);
+    reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(partials, blocks, sumsq_dev);
     STEIN_CHECK_LAUNCH(ctx);
     return STEIN_OK;
 }

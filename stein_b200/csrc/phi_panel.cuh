@@ -19,6 +19,8 @@
 // Tensor work per pair of kernels = the algorithmic 2 GEMMs; HBM traffic = the operand arrays once per
 // panel (L2 serves the reuse inside a launch).
 #pragma once
+#include <stdlib.h>
+
 #include "panel_gemm.cuh"
 
 namespace stein {
@@ -26,7 +28,18 @@ namespace panel {
 
 using namespace pg;
 
-constexpr int64_t P_BUDGET_TILES = 256;      // 256 x 256 x 4 B tiles of P per block: 64 MiB
+// 256 x 256 x 4 B tiles of P per block (default 256 = 64 MiB, L2-sized; environment STEIN_PANEL_TILES)
+static int64_t p_budget_tiles() {
+    static int64_t v = 0;
+    if (!v) {
+        v = 256;
+        if (const char *e = getenv("STEIN_PANEL_TILES")) {
+            const long long x = atoll(e);
+            if (x >= 2 && x <= (1 << 20)) v = x;
+        }
+    }
+    return v;
+}
 
 // ---------------------------------------------------------------------------------------------
 // kernel A: exponentials of one block of the kernel matrix
@@ -240,8 +253,8 @@ static PanelPlan panel_plan(const stein_ctx *ctx, int64_t n_local, int64_t n_tot
     double best = 1e300;
     pl.rp = 1;
     pl.cc = 2;
-    for (int64_t rp = 1; rp <= std::min<int64_t>(R, P_BUDGET_TILES / 2); ++rp) {
-        for (int64_t cc = 2; cc <= std::min<int64_t>(C, P_BUDGET_TILES / rp); cc += 2) {
+    for (int64_t rp = 1; rp <= std::min<int64_t>(R, p_budget_tiles() / 2); ++rp) {
+        for (int64_t cc = 2; cc <= std::min<int64_t>(C, p_budget_tiles() / rp); cc += 2) {
             const int64_t nr = R / rp, rr = R % rp, nc = C / cc, cr = C % cc;
             double cost = (double)nr * (double)nc * block_cost(rp, cc);
             if (rr) cost += (double)nc * block_cost(rr, cc);
@@ -403,6 +416,10 @@ int phi_panel(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
     }
     const int G = std::max(1, ctx->num_sms / 2);
     const int64_t R = pl.rowsP / 256, C = pl.colsP / 256;
+    if (getenv("STEIN_PANEL_VERBOSE"))
+        fprintf(stderr, "[stein] panel plan: %lld x %lld tiles, blocks of %lld x %lld (%lld launches), P block %.1f MiB\n",
+                (long long)R, (long long)C, (long long)pl.rp, (long long)pl.cc,
+                (long long)(2 * ((R + pl.rp - 1) / pl.rp) * ((C + pl.cc - 1) / pl.cc)), pl.rp * pl.cc * 0.25);
     {
         RegionTimer timer(ctx, STEIN_REGION_PHI);
         for (int64_t r0 = 0; r0 < R; r0 += pl.rp) {

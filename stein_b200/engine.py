@@ -77,6 +77,14 @@ class SvgdEngine:
     def phi_dev(self):
         return self._view(self.phi_ptr)
 
+    @property
+    def sumsq_dev(self):
+        """1-element float64 device tensor: sum(phi^2) that the clip of the next apply_phi() reads."""
+        from .distributed import _DevMem
+        p = ctypes.c_void_p()
+        self.ctx.check(self.lib.stein_engine_sumsq_dev(self.handle, ctypes.byref(p)))
+        return _torch().as_tensor(_DevMem(p.value, 1, "<f8"), device="cuda:%d" % self.ctx.device)
+
     # ---- host transfers --------------------------------------------------------
     def _host(self, a):
         a = np.asarray(a)
@@ -137,6 +145,11 @@ class SvgdEngine:
         """compute_phi() on the scores in the S buffer, into the phi buffer; no optimizer step."""
         self.ctx.sync_stream()
         self.ctx.check(self.lib.stein_engine_phi_only(self.handle))
+
+    def apply_phi(self):
+        """Clip + optimizer step on the phi / sum(phi^2) currently in the engine's buffers."""
+        self.ctx.sync_stream()
+        self.ctx.check(self.lib.stein_engine_apply_phi(self.handle))
 
     def set_hyper(self, learning_rate, decay, p1, p2):
         self.ctx.check(self.lib.stein_engine_set_hyper(self.handle, float(learning_rate), float(decay),

@@ -84,6 +84,17 @@ class Context:
         out[:n, :d] = torch.from_numpy(a).to(out.device)
         return out
 
+    def to_square(self, K):
+        """host (n x n) kernel matrix -> zero-padded fp32 device tensor (rows_padded x rows_padded)."""
+        torch = _torch()
+        a = np.ascontiguousarray(np.asarray(K, dtype=np.float32))
+        if a.ndim != 2 or a.shape[0] != a.shape[1]:
+            raise ValueError("expected a square (n_particles x n_particles) kernel matrix")
+        rows = self.rows_padded(a.shape[0])
+        out = torch.zeros((rows, rows), dtype=torch.float32, device="cuda:%d" % self.device)
+        out[:a.shape[0], :a.shape[0]] = torch.from_numpy(a).to(out.device)
+        return out
+
     def dense(self, array, dtype=np.float32):
         """host array -> contiguous device tensor, no padding (data matrices)."""
         torch = _torch()

@@ -90,11 +90,15 @@ class AbstractSteinSampler:
         """(K.S + dK) / n for host arrays (abstract_stein_sampler.py:76-105), through
         the fused GPU path: median -> bandwidth -> phi, K never materialised."""
         import torch
-        if not isinstance(self.kernel, SquaredExponentialKernel):
-            raise NotImplementedError("only the squared-exponential kernel has a fused phi path")
         ctx = context()
         theta_array = np.asarray(theta_array)
         n, d = theta_array.shape
+        if not isinstance(self.kernel, SquaredExponentialKernel):
+            # any other kernel operator (abstract_kernel.py:45-62): the reference's own formula
+            # (K.dot(S) + dK) / n (:105), with the GEMM on the device
+            K, dK = self.kernel.kernel_and_grad(theta_array)
+            return self._phi_from_kernel(ctx, ctx.to_square(K), ctx.to_padded(dK), ctx.to_padded(grads_array),
+                                         n, d)[0][:n, :d].double().cpu().numpy()
         X, S = ctx.to_padded(theta_array), ctx.to_padded(grads_array)
         rows, ld = X.shape
         r = torch.empty(rows, dtype=torch.float32, device=X.device)
@@ -108,14 +112,54 @@ class AbstractSteinSampler:
                                     ptr(ws), ws_bytes, ptr(phi), ptr(sumsq)))
         return phi[:n, :d].double().cpu().numpy()
 
+    @staticmethod
+    def _phi_from_kernel(ctx, K, dK, S, n, d, phi=None, sumsq=None):
+        """(K S + dK) / n on the device (stein_phi_from_kernel); returns (phi, sumsq) tensors."""
+        import torch
+        rows, ld = S.shape
+        phi = torch.empty_like(S) if phi is None else phi
+        sumsq = torch.zeros(1, dtype=torch.float64, device=S.device) if sumsq is None else sumsq
+        ws = torch.empty(rows * ld * 4 + 16384, dtype=torch.uint8, device=S.device)
+        ctx.check(ctx.lib.stein_phi_from_kernel(ctx.handle, ptr(K), K.shape[1], ptr(dK), ptr(S), n, d, ld, ptr(ws),
+                                                ws.numel(), ptr(phi), ptr(sumsq)))
+        return phi, sumsq
+
+    def _plugin_kernel_step(self):
+        """One iteration with a kernel operator other than the squared-exponential one: K and dK from
+        `self.kernel` (on the device when the operator offers kernel_and_grad_dev, else through its
+        host arrays like the reference), phi = (K S + dK) / n, then the engine's clip + optimizer."""
+        import torch
+        e, ctx = self._engine, self._engine.ctx
+        if e.n_local != e.n_particles:
+            raise NotImplementedError("kernel operators other than SquaredExponentialKernel run on one GPU")
+        n, d = e.n_particles, e.n_params
+        X, S = e.particles_dev, e.scores_dev
+        if hasattr(self.kernel, "kernel_and_grad_dev"):
+            r = torch.empty(e.rows_padded, dtype=torch.float32, device=X.device)
+            ctx.check(ctx.lib.stein_row_norms(ctx.handle, ptr(X), n, d, e.ld, ptr(r)))
+            K, dK = self.kernel.kernel_and_grad_dev(ctx, X, r, n, d)
+        else:
+            Kh, dKh = self.kernel.kernel_and_grad(e.get_particles(np.float64))
+            K = ctx.to_square(Kh)
+            dK = torch.zeros_like(X)
+            dK[:n, :d] = torch.from_numpy(np.ascontiguousarray(dKh, dtype=np.float32)).to(X.device)
+        self._phi_from_kernel(ctx, K, dK, S, n, d, phi=e.phi_dev, sumsq=e.sumsq_dev)
+
     def update_particles(self, grads_array):
         """abstract_stein_sampler.py:107-127 for a host score matrix."""
         e = self._engine
         grads_array = np.ascontiguousarray(grads_array)
-        if isinstance(self.gd, FusedGradientDescent):
+        fused_kernel = isinstance(self.kernel, SquaredExponentialKernel)
+        if isinstance(self.gd, FusedGradientDescent) and fused_kernel:
             self._sync_kernel_bandwidth()
             self.gd._push_hyper()          # the reference reads lr / decay / betas at every update()
             e.update_particles_host(grads_array)
+            self.gd._after_engine_step()
+        elif isinstance(self.gd, FusedGradientDescent):
+            e.set_scores(grads_array)
+            self._plugin_kernel_step()
+            self.gd._push_hyper()
+            e.apply_phi()
             self.gd._after_engine_step()
         else:
             # user-defined step rule: same sequence as the reference, phi from the GPU
@@ -137,6 +181,8 @@ class AbstractSteinSampler:
     def _device_phi_only(self):
         """phi for the scores in the engine, without the optimizer step (stein_engine_phi_only:
         the engine's own workspace, leading dimension and row shard)."""
+        if not isinstance(self.kernel, SquaredExponentialKernel):
+            return self._plugin_kernel_step()
         self._sync_kernel_bandwidth()
         self._engine.phi_only()
 

@@ -24,10 +24,16 @@ class SteinSampler(AbstractSteinSampler):
         e = self._engine
         e.ctx.sync_stream()
         self.log_p.scores(e, batch_feed)                 # S stays on the device
-        if isinstance(self.gd, FusedGradientDescent):
+        if isinstance(self.gd, FusedGradientDescent) and isinstance(self.kernel, SquaredExponentialKernel):
             self._sync_kernel_bandwidth()
             self.gd._push_hyper()          # the reference reads lr / decay / betas at every update()
             e.step()
+            self.gd._after_engine_step()
+        elif isinstance(self.gd, FusedGradientDescent):
+            # another kernel operator assigned to `self.kernel` (abstract_kernel.py:45-62)
+            self._plugin_kernel_step()
+            self.gd._push_hyper()
+            e.apply_phi()
             self.gd._after_engine_step()
         else:
             self._device_phi_only()

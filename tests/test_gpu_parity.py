@@ -1248,3 +1248,56 @@ def test_median_tensor_core_route_beyond_256_coordinates(ctx, n, d, kind):
         m_ref, mid_ref = orc.median_chain(X, radix=True)
         assert tc[0].tobytes() == m_ref.tobytes()
         assert (tc[1][0].tobytes(), tc[1][1].tobytes()) == (mid_ref[0].tobytes(), mid_ref[1].tobytes())
+
+
+# --------------------------------------------------------------------------- #
+# round 2: other kernel operators through the plugin point #
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("n,d,beta", [(50, 3, -0.5), (300, 55, -0.5), (129, 33, -1.0)])
+def test_imq_kernel_and_grad_matches_oracle(ctx, n, d, beta):
+    from stein_b200.kernels import InverseMultiquadricKernel
+    X = _particles(n, d, n + d, 0.7)
+    kern = InverseMultiquadricKernel(n, beta=beta)
+    K, dK = kern.kernel_and_grad(X)
+    K_ref, dK_ref, h = orc.imq_kernel_and_grad(X, beta=beta)
+    assert np.float32(kern.bandwidth).tobytes() == h.tobytes()
+    assert np.abs(K - K_ref).max() <= 2e-5
+    assert np.abs(dK - dK_ref).max() <= 1e-4 * np.abs(dK_ref).max()
+
+
+@pytest.mark.parametrize("kind", ["imq_device", "user_numpy"])
+def test_sampler_runs_another_kernel_operator(ctx, kind):
+    """`sampler.kernel = <another AbstractKernel>` (the reference's plugin point): the iteration becomes
+    phi = (K S + dK) / n from that operator (abstract_stein_sampler.py:100-105), clip, optimizer --
+    with the built-in IMQ operator (CUDA) and with a user-defined operator that returns NumPy arrays."""
+    from stein_b200.kernels import AbstractKernel, InverseMultiquadricKernel
+    from stein_b200.log_p import LinearRegression
+    from stein_b200.optimizers import AdamGradientDescent
+    from stein_b200.samplers import SteinSampler
+
+    class NumpyIMQ(AbstractKernel):            # what a user of the reference would write
+        def kernel_and_grad(self, theta):
+            K, dK, _ = orc.imq_kernel_and_grad(theta, beta=-0.5)
+            return K, dK
+
+    n, F, N = 200, 7, 64
+    rng = np.random.default_rng(6)
+    Xd = rng.standard_normal((N, F)).astype(np.float32)
+    yd = rng.standard_normal((N, 1)).astype(np.float32)
+    model = LinearRegression(F)
+    np.random.seed(5)
+    sampler = SteinSampler(n, model.log_p, AdamGradientDescent(learning_rate=0.05))
+    sampler.kernel = InverseMultiquadricKernel(n) if kind == "imq_device" else NumpyIMQ(n)
+    theta = sampler.samples.copy()
+    gd = orc.AdamGradientDescent(learning_rate=0.05)
+    for _ in range(3):
+        S = orc.score_linear(theta, Xd, yd)
+        K, dK, _ = orc.imq_kernel_and_grad(theta, beta=-0.5)
+        phi = orc.clip((K.astype(np.float64) @ S + dK) / n)
+        theta = theta + gd.update(phi)
+        sampler.train_on_batch({model.X: Xd, model.y: yd})
+    _assert_close(sampler.samples, theta, 2e-4)
+    # compute_phi(theta, grads) with the plugged operator
+    S = orc.score_linear(theta, Xd, yd)
+    K, dK, _ = orc.imq_kernel_and_grad(theta, beta=-0.5)
+    _assert_close(sampler.compute_phi(theta, S), (K.astype(np.float64) @ S + dK) / n)

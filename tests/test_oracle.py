@@ -182,3 +182,22 @@ def test_blocked_iteration_matches_dense():
     bw = orc.kernel_and_grad(T, chain=False)[2]
     assert bw == bw_b
     np.testing.assert_allclose(phi_b, phi, rtol=1e-5, atol=1e-8)
+
+
+def test_imq_kernel_and_grad_against_autograd():
+    """The inverse multiquadric operator of the oracle (plugin point abstract_kernel.py:45-62): its
+    closed-form dK equals the reference's recipe -0.5 * d(sum K)/d theta_i
+    (squared_exponential_kernel.py:23,32) evaluated by autograd, bandwidth held fixed (stop_gradient,
+    abstract_kernel.py:40)."""
+    import torch
+    rng = np.random.default_rng(5)
+    theta = rng.standard_normal((23, 4)).astype(np.float32)
+    for beta in (-0.5, -1.0):
+        K, dK, h = orc.imq_kernel_and_grad(theta, beta=beta)
+        T = torch.tensor(theta, dtype=torch.float64, requires_grad=True)
+        r = (T * T).sum(1, keepdim=True)
+        D = r + r.T - 2 * T @ T.T
+        Kt = (1.0 + D / float(h) ** 2) ** beta
+        (g,) = torch.autograd.grad(Kt.sum(), T)
+        np.testing.assert_allclose(K, Kt.detach().numpy(), rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(dK, -0.5 * g.numpy(), rtol=1e-4, atol=2e-5 * np.abs(g.numpy()).max())
