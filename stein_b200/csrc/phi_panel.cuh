@@ -10,8 +10,8 @@
 // Beyond d = 256 the fused flash schedule does not exist: the O accumulator of a 128-row tile
 // (128 x d fp32) exceeds tensor memory, so either GEMM1 is recomputed for every 256-column slice of O
 // (2.5 x the tensor work at d = 1 024) or K crosses memory once.  It crosses once, but never as an
-// n x n object: the local rows are cut into PANELS and the columns into CHUNKS such that one block of
-// P = exp(-D / 2h^2) (2 B FP16 + 2 x 1 B FP8 per entry, <= 64 MiB) stays in the 126 MB L2 between the
+// n x n object: the local rows are cut into PANELS and the columns into CHUNKS, and one block of
+// P = exp(-D / 2h^2) (2 B FP16 + 2 x 1 B FP8 per entry, <= 256 MiB, see p_budget_tiles) lives between the
 // two kernels that touch it:
 //   kernel A (ExpPolicy)  P[panel, chunk] = exp2(c1 X_panel X_chunk^T + a_i + b_j), row sums per tile
 //   kernel B (AccPolicy)  O[panel, :]    += P[panel, chunk] Y[chunk, :]
@@ -28,11 +28,15 @@ namespace panel {
 
 using namespace pg;
 
-// 256 x 256 x 4 B tiles of P per block (default 256 = 64 MiB, L2-sized; environment STEIN_PANEL_TILES)
+// 256 x 256 x 4 B tiles of P per block (environment STEIN_PANEL_TILES).  Measured at n = 32 768, d = 1 024 on
+// one B200: an L2-sized block (256 tiles = 64 MiB) runs the two kernels at 487 TFLOP/s algorithmic -- 190
+// launches of ~60 us each, K loops of 1 024 -- while 1 024 tiles (240 MiB, 40 launches) reach 769: the P block
+// then streams through HBM (its four column-slice readers run side by side and share it in L2), which the
+// tensor-bound kernels hide.  4 096 tiles are slower again (712: wave quantisation of the few launches).
 static int64_t p_budget_tiles() {
     static int64_t v = 0;
     if (!v) {
-        v = 256;
+        v = 1024;
         if (const char *e = getenv("STEIN_PANEL_TILES")) {
             const long long x = atoll(e);
             if (x >= 2 && x <= (1 << 20)) v = x;

@@ -1301,3 +1301,73 @@ def test_sampler_runs_another_kernel_operator(ctx, kind):
     S = orc.score_linear(theta, Xd, yd)
     K, dK, _ = orc.imq_kernel_and_grad(theta, beta=-0.5)
     _assert_close(sampler.compute_phi(theta, S), (K.astype(np.float64) @ S + dK) / n)
+
+
+# --------------------------------------------------------------------------- #
+# round 2: graph recognition (the reference's scripts leave torch autograd)     #
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("kind", ["linear", "linear_1feature", "logistic", "bnn", "unknown"])
+def test_graph_recognition_dispatches_to_the_score_kernels(ctx, kind):
+    """A `log_p` tensor recorded by the TF1 stand-in from one of the reference's three example graphs
+    (examples/*/main.py, restated in tests/test_tf_compat.py) is recognised -- by signature, then verified
+    against its own autograd scores -- and served by stein_score_linear / _logistic / _bnn; the training-set
+    size baked into the graph is recovered.  Same scores as the autograd path to 2e-5; a graph that is
+    none of the three stays on autograd."""
+    import sys
+    import torch
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "compat")
+    if compat not in sys.path:
+        sys.path.insert(0, compat)
+    import tensorflow as tf
+    here = os.path.dirname(os.path.abspath(__file__))
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    import test_tf_compat as graphs
+    from stein_b200.optimizers import AdamGradientDescent
+    from stein_b200.samplers import SteinSampler
+    rng = np.random.default_rng(9)
+    n, B = 96, 40
+    if kind in ("linear", "linear_1feature"):
+        F = 1 if kind == "linear_1feature" else 6
+        g = graphs.linear_graph(F)
+    elif kind == "logistic":
+        F = 9
+        g = graphs.logistic_graph(F, 464809.0, float(B))
+    elif kind == "bnn":
+        F, H = 5, 12
+        g = graphs.bnn_graph(F, H, 455.0, float(B))
+    else:
+        F = 4
+        tf.reset_default_graph()
+        with tf.variable_scope("model"):
+            X = tf.placeholder(tf.float32, shape=[None, F])
+            y = tf.placeholder(tf.float32, shape=[None, 1])
+            w = tf.Variable(tf.zeros([F, 1]))
+            log_p = -tf.reduce_sum(tf.square(tf.matmul(X, w) - y)) - 3.0 * tf.reduce_sum(tf.square(w))   # not the example
+        g = dict(X=X, y=y, log_p=log_p)
+    Xb = rng.standard_normal((B, F)).astype(np.float32)
+    yb = (rng.random((B, 1)) > 0.5).astype(np.float32) if kind == "logistic" else rng.standard_normal((B, 1)).astype(np.float32)
+    np.random.seed(7)
+    sampler = SteinSampler(n, g["log_p"], AdamGradientDescent(learning_rate=1e-2))
+    lp, e = sampler.log_p, sampler.engine
+    feed = {g["X"]: Xb, g["y"]: yb}
+    lp.scores(e, feed)                                   # first call: probe + recognition
+    d = lp.n_params
+    S_used = e.scores_dev[:n, :d].clone()
+    S_auto = lp.graph_scores(e.particles_dev[:n, :d], lp._feed_tensors(feed, e.ctx.dense)).to(torch.float32)
+    want = {"linear": "linear", "linear_1feature": "linear", "logistic": "logistic", "bnn": "bnn", "unknown": None}[kind]
+    assert lp.recognised == want, lp.recognised
+    scale = S_auto.abs().amax(dim=0).clamp_min(1e-30)
+    assert float(((S_used - S_auto).abs() / scale).amax()) <= 2e-5
+    if kind == "logistic":
+        assert lp._fast[0].n_train == 464809.0
+    if kind == "bnn":
+        assert lp._fast[0].n_train == 455.0
+    # a second batch of another size goes through the same kernel
+    Xb2, yb2 = Xb[:17], yb[:17]
+    lp.scores(e, {g["X"]: Xb2, g["y"]: yb2})
+    S2 = e.scores_dev[:n, :d].clone()
+    S2_auto = lp.graph_scores(e.particles_dev[:n, :d], lp._feed_tensors({g["X"]: Xb2, g["y"]: yb2}, e.ctx.dense))
+    scale2 = S2_auto.abs().amax(dim=0).clamp_min(1e-30)
+    # (the logistic / bnn graphs bake n_batch in: a batch of another size goes back to autograd -- exact either way)
+    assert float(((S2 - S2_auto.to(torch.float32)).abs() / scale2).amax()) <= 2e-5
