@@ -7,7 +7,7 @@
 // (fp32 fma chain, see median.cu / oracle/svgd_oracle.c) -- tensor cores cannot
 // produce those bits.  They are used as a FILTER instead:
 //   1. the sweep computes D~ = r_i + r_j - 2 g~ with g~ from a 3-pass FP16-split GEMM
-//      (|D~ - D| <= eps_ij = c_half (r_i + r_j), a worst-case bound, see eps_coeff());
+//      (|D~ - D| <= eps_ij = e_i + e_j, a worst-case bound with a per-row error budget, see err_budget_kernel);
 //      pairs that are certainly below the pilot window [wlo, whi] are counted, pairs
 //      certainly above are dropped, the rest (~0.7 %) are appended to a list with D~;
 //   2. a radix select over the listed D~ gives t~, the D~ value at the target rank;
@@ -67,7 +67,9 @@ struct SweepParams {
     long long n;
     const float *r;
     const uint32_t *Xh, *Xl;      // FP16 split of s X viewed as 32-bit words (DP / 2 per row)
-    float wlo, whi, c_half;
+    float wlo, whi;
+    const float *e;               // per-row error budget e_i: |D~_ij - D_ij| <= e_i + e_j (err_budget_kernel)
+    const float *emax;            // device: max_i e_i
     const float *window;          // device [wlo, whi] replacing the two fields above when non-NULL (set by
                                   // pilot_pick_kernel without a host round trip)
     const float *rmax;            // device: max_i r_i (bounds the column part of the error term)
@@ -117,12 +119,12 @@ __device__ __forceinline__ void next_tile(int &I, int &J, int T) {
 }
 
 // ---- classification of one 128 x 128 tile of g = x_i . x_j (shared by both sweep kernels) ----
-// With D~ = r_i + r_j - 2 g and |D~ - D| <= c (r_i + r_j):
-//   certainly above the window  <=>  g < (1-c)/2 (r_i + r_j) - whi/2
-//   certainly below the window  <=>  g > (1+c)/2 (r_i + r_j) - wlo/2
-// Written with t = g - B_j, B_j = (1-c)/2 r_j (one shared-memory value per column):
-//   above  <=>  t < lo_i,   lo_i = (1-c)/2 r_i - whi/2
-//   below  <=>  t > hi_i,   hi_i = (1+c)/2 r_i + c rmax - wlo/2   (rmax >= r_j: conservative)
+// With D~ = r_i + r_j - 2 g and |D~ - D| <= e_i + e_j:
+//   certainly above the window  <=>  g < (r_i - e_i)/2 + (r_j - e_j)/2 - whi/2
+//   certainly below the window  <=>  g > (r_i + e_i)/2 + (r_j + e_j)/2 - wlo/2
+// Written with t = g - B_j, B_j = (r_j - e_j)/2 (one shared-memory value per column):
+//   above  <=>  t < lo_i,   lo_i = (r_i - e_i)/2 - whi/2
+//   below  <=>  t > hi_i,   hi_i = (r_i + e_i)/2 + emax - wlo/2   (emax >= e_j: conservative)
 // and everything else is listed.  lo_i / hi_i are moved outwards by `slack` (>> the fp32 rounding
 // of these few operations); that only enlarges the listed set, whose members are resolved from
 // their own D~ later.  "below" and "above" are decided by the sign of one subtraction each, so
@@ -143,7 +145,7 @@ struct TileClassifier {
     unsigned int *sHist, *wCount;
     int wg, row, lane;
     uint32_t lane_addr;
-    float cm, cp, rmax, hlo, hscale, s2, inv_s2, wlo, whi;
+    float rmax, emax, hlo, hscale, s2, inv_s2, wlo, whi;
     unsigned int below, listed;
 
     __device__ TileClassifier(const SweepParams &p_, uint8_t *tail, int warp, int lane_)
@@ -157,9 +159,8 @@ struct TileClassifier {
         wg = ew >> 2;
         row = q * 32 + lane;
         lane_addr = (uint32_t)(q * 32) << 16;
-        cm = 0.5f * (1.0f - p.c_half);
-        cp = 0.5f * (1.0f + p.c_half);
         rmax = __ldg(p.rmax);
+        emax = __ldg(p.emax);
         wlo = p.window ? __ldg(p.window) : p.wlo;
         whi = p.window ? __ldg(p.window + 1) : p.whi;
         // g arrives scaled by s^2 (the operands are s X): the thresholds are scaled instead of g --
@@ -167,7 +168,7 @@ struct TileClassifier {
         s2 = __ldg(p.scale + 1);
         inv_s2 = __ldg(p.scale + 2);
         // histogram range of the listed D~: the window widened by the largest possible error term
-        const float hpad = 4.0f * p.c_half * rmax + 1e-5f * fmaxf(fabsf(wlo), fabsf(whi));
+        const float hpad = 4.0f * emax + 1e-5f * fmaxf(fabsf(wlo), fabsf(whi));
         hlo = wlo - hpad;
         hscale = (float)SW_HIST_BINS / fmaxf((whi + hpad) - hlo, 1e-30f);
         if (blockIdx.x == 0 && ew == 0 && lane == 0) {
@@ -182,20 +183,22 @@ struct TileClassifier {
     __device__ void classify(uint32_t s_tmem, long long i, int J, unsigned int w) {
         if (w == 0u) return;
         const bool row_ok = i < p.n;
-        const float r_i = row_ok ? p.r[i] : 0.0f;
+        const float r_i = row_ok ? p.r[i] : 0.0f, e_i = row_ok ? p.e[i] : 0.0f;
         const float *rj = p.r + (size_t)J * 128 + wg * WCOLS;    // this warp's columns
+        const float *ej = p.e + (size_t)J * 128 + wg * WCOLS;
         // column terms (the previous tile's are no longer read: same warp, program order)
         {
             const long long j0 = (long long)J * 128 + wg * WCOLS + lane;
 #pragma unroll
             for (int cc = 0; cc < CHUNKS; ++cc)
-                wCol[32 * cc + lane] = j0 + 32 * cc < p.n ? cm * __ldg(rj + 32 * cc + lane) * s2 : INFINITY;
+                wCol[32 * cc + lane] =
+                    j0 + 32 * cc < p.n ? 0.5f * (__ldg(rj + 32 * cc + lane) - __ldg(ej + 32 * cc + lane)) * s2 : INFINITY;
             __syncwarp();
         }
         const float slack = (r_i + rmax) * 9.5367431640625e-07f;   // 2^-20
         // rows beyond n: lo_i = hi_i = +inf, so every pair is "above" (neither counted nor listed)
-        const float lo_i = row_ok ? (cm * r_i - 0.5f * whi - 2.0f * slack) * s2 : INFINITY;
-        const float hi_i = row_ok ? (cp * r_i + p.c_half * rmax - 0.5f * wlo + 2.0f * slack) * s2 : INFINITY;
+        const float lo_i = row_ok ? (0.5f * (r_i - e_i) - 0.5f * whi - 2.0f * slack) * s2 : INFINITY;
+        const float hi_i = row_ok ? (0.5f * (r_i + e_i) + emax - 0.5f * wlo + 2.0f * slack) * s2 : INFINITY;
 #pragma unroll 1
         for (int cc = 0; cc < CHUNKS; ++cc) {
             const int ch = wg * CHUNKS + cc;
@@ -770,7 +773,7 @@ struct Sweep3Policy {
 
 // ---- helpers ---------------------------------------------------------------------------
 // hi = fp16(s x), lo = fp16(s x - hi): 22 bits of s x (entries far below the largest one end in
-// the FP16 subnormals; that absolute error is covered by the slack terms, see eps_coeff)
+// the FP16 subnormals; that absolute error is covered by the slack terms, see err_budget_kernel / EPS_ABS)
 __global__ void split_f16_kernel(const float *__restrict__ X, int64_t count4, const float *__restrict__ scale,
                                  __half *__restrict__ Xh, __half *__restrict__ Xl) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -788,11 +791,52 @@ __global__ void split_f16_kernel(const float *__restrict__ X, int64_t count4, co
     reinterpret_cast<uint2 *>(Xl)[e] = *reinterpret_cast<uint2 *>(l);
 }
 
+// Per-row error budget of the filter: |D~_ij - D_ij| <= e_i + e_j with e_i = sum_m w_m x_im^2.
+// The error of g = x_i . x_j is a sum of per-step roundings, each relative to the running sum at
+// that step, so a product that enters early is hit by more of them than a late one:
+//   contract fma chain (what D is DEFINED by): step k rounds to nearest, <= 2^-24 |s_k| and
+//     |s_k| <= (1 + 2^-24)^k sum_{m <= k} |x_m y_m|  =>  weight 2^-24 (ld - m + 1) on |x_m y_m|   [rigorous];
+//   tensor-core accumulation: one truncation per MMA (<= 2^-23 of the running sum), 12 MMAs per block of
+//     64 coordinates in ascending order in all three sweep kernels  =>  <= 12 (nkb - kb(m)) truncations after
+//     product m entered, weight 2^-23 each, doubled as a margin (the datapath is not documented);
+//   FP16 split (dropped lo.lo, rounding of lo) 3 * 2^-22, doubled; final roundings of D~ and D: 2^-21.
+// err(D) = 2 err(g) <= 2 sum_m w_m |x_m||y_m| <= sum_m w_m x_m^2 + sum_m w_m y_m^2 (Cauchy-Schwarz, AM-GM).
+// The flat bound this replaces (weight of the first coordinate for all of them) was 2.6x (d = 256) to
+// 3x (d = 1024) larger, and with it the band of pairs whose distance is recomputed exactly.
+__global__ void __launch_bounds__(256)
+err_budget_kernel(const float *__restrict__ X, int64_t rows, int64_t n, int64_t ld, float *__restrict__ e) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nkb = (int)(ld / 64);
+    float acc = 0.0f;
+    if (row < n) {
+        for (int64_t m = lane; m < ld; m += 32) {
+            const float x = X[row * ld + m];
+            const float w = 5.9664e-08f * (float)(ld - m + 1)                       // 2^-24 * 1.001
+                            + 2.38418579e-07f * 12.0f * (float)(nkb - (int)(m >> 6))    // 2^-22 (= 2 x 2^-23)
+                            + 1.90734863e-06f;                                      // 2^-19
+            acc = fmaf(w * x, x, acc);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) e[row] = acc * 1.001f;      // the fp32 evaluation of the budget itself
+}
+
 __global__ void __launch_bounds__(1024)
-max_kernel(const float *__restrict__ r, int64_t n, float *__restrict__ out, float *__restrict__ scale_out) {
+max_kernel(const float *__restrict__ r, const float *__restrict__ e, int64_t n, float *__restrict__ out,
+           float *__restrict__ emax_out, float *__restrict__ scale_out) {
     __shared__ float red[32];
-    float m = 0.0f;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, r[i]);
+    __shared__ float red_e[32];
+    float m = 0.0f, me = 0.0f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        m = fmaxf(m, r[i]);
+        me = fmaxf(me, e[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) me = fmaxf(me, __shfl_xor_sync(0xffffffffu, me, o));
+    if ((threadIdx.x & 31) == 0) red_e[threadIdx.x >> 5] = me;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
@@ -801,8 +845,12 @@ max_kernel(const float *__restrict__ r, int64_t n, float *__restrict__ out, floa
         m = red[threadIdx.x];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        me = red_e[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) me = fmaxf(me, __shfl_xor_sync(0xffffffffu, me, o));
         if (threadIdx.x == 0) {
             *out = m;
+            *emax_out = me;
             // s = 2^-e with sqrt(rmax) s in [128, 256): no entry of s X exceeds 256
             int e = 0;
             if (m > 0.0f && m < INFINITY) e = ilogbf(sqrtf(m)) - 7;
@@ -988,8 +1036,8 @@ pilot_pick_kernel(const unsigned long long *__restrict__ bins, uint32_t key_lo, 
 // thresholds and the key window of the final select.  cnt = counters block (u64 slots).
 __global__ void __launch_bounds__(1024)
 pick_band_kernel(const unsigned long long *__restrict__ cnt, int slot_below, int slot_listed, int slot_overflow,
-                 int slot_hist, int slot_rmax, int slot_hparams, unsigned long long rank0, unsigned long long rank1,
-                 float c_half, float eps_abs_coeff, uint32_t max_bins, uint32_t *__restrict__ bp) {
+                 int slot_hist, int slot_rmax, int slot_emax, int slot_hparams, unsigned long long rank0,
+                 unsigned long long rank1, float eps_abs_coeff, uint32_t max_bins, uint32_t *__restrict__ bp) {
     __shared__ unsigned long long wsum[32];
     __shared__ int s_bin;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -1031,13 +1079,14 @@ pick_band_kernel(const unsigned long long *__restrict__ cnt, int slot_below, int
     const bool ok = cnt[slot_overflow] == 0 && below <= rank0 && rank1 < below + listed && bstar > 0 &&
                     bstar < SW_HIST_BINS - 1;
     const float rmax = __uint_as_float((uint32_t)cnt[slot_rmax]);
+    const float emax = __uint_as_float((uint32_t)cnt[slot_emax]);
     const uint32_t hp0 = (uint32_t)cnt[slot_hparams], hp1 = (uint32_t)(cnt[slot_hparams] >> 32);
     const float hlo = __uint_as_float(hp0), hscale = __uint_as_float(hp1);
     // t~ lies in bin bstar; one extra bin on either side covers the rounding of the bin function
     const float bin_w = 1.0f / hscale;
     const float t_lo = hlo + (float)(bstar - 1) * bin_w, t_hi = hlo + (float)(bstar + 2) * bin_w;
     const float eps_abs = eps_abs_coeff * rmax;
-    const float delta = c_half * 2.0f * rmax * 1.0001f + eps_abs + 2.0f * fmaxf(fabsf(t_lo), fabsf(t_hi)) * 1.2e-7f;
+    const float delta = 2.0f * emax * 1.0001f + eps_abs + 2.0f * fmaxf(fabsf(t_lo), fabsf(t_hi)) * 1.2e-7f;
     const float tlo = t_lo - delta, thi = t_hi + delta;
     const uint32_t klo = float_to_key(tlo - 2.0f * delta), khi = float_to_key(thi + 2.0f * delta);
     const unsigned long long span = (unsigned long long)khi - klo + 1;
@@ -1061,8 +1110,8 @@ pick_band_kernel(const unsigned long long *__restrict__ cnt, int slot_below, int
 constexpr int BF_THREADS = 256;
 constexpr int BF_STAGE = 1024;
 __global__ void __launch_bounds__(BF_THREADS)
-band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, const float *__restrict__ r,
-                   float tlo, float thi, float c_half, float eps_abs, unsigned long long *__restrict__ below_out,
+band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, const float *__restrict__ ebud,
+                   float tlo, float thi, float eps_abs, unsigned long long *__restrict__ below_out,
                    unsigned long long *__restrict__ bandw_out, unsigned long long *__restrict__ bandlen_out,
                    uint2 *__restrict__ band_ij, unsigned long long band_cap, int *__restrict__ overflow,
                    const unsigned long long *__restrict__ m_dev = nullptr, const uint32_t *__restrict__ bp = nullptr) {
@@ -1103,7 +1152,7 @@ band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, con
         if (e < b1) {
             pe = list[e];
             const uint32_t i = pe.i, j = pe.jw & 0x7fffffffu, w = (pe.jw >> 31) ? 2u : 1u;
-            const float eps = c_half * (r[i] + r[j]) + eps_abs;
+            const float eps = ebud[i] + ebud[j] + eps_abs;
             if (pe.dt + eps < tlo) {
                 below += w;
             } else if (pe.dt - eps <= thi) {
@@ -1138,17 +1187,10 @@ band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, con
     }
 }
 
-// worst-case |D~ - D_contract| <= eps_coeff(d) * (r_i + r_j) + EPS_ABS * rmax:
-//   FP16 2-term split of s X: dropped lo.lo and the rounding of lo, <= 3 * 2^-22 |x_i||x_j|
-//     (plus, for entries that end in the FP16 subnormals, <= 2^-25 absolute per entry of s X,
-//      i.e. <= 2^-23 sqrt(d) sqrt(rmax) / s <= 2^-26 d^(1/2) rmax / 16 in D: the EPS_ABS term);
-//   tensor-core accumulation (truncating, 3 d/16 adds of magnitude <= |x_i||x_j|): 3d/16 * 2^-23;
-//   contract fma chain: d * 2^-24 |x_i||x_j|;  |x_i||x_j| <= (r_i + r_j)/2;  final roundings 2^-22.
-// All doubled once more as a safety margin.
-static float eps_coeff(int64_t d) {
-    const double per_xx = 3.0 * ldexp(1.0, -22) + (3.0 * d / 16.0) * ldexp(1.0, -23) + d * ldexp(1.0, -24);
-    return (float)(2.0 * (per_xx + ldexp(1.0, -22)));
-}
+// worst-case |D~ - D_contract| <= e_i + e_j + EPS_ABS * rmax: the per-row budgets e_i (err_budget_kernel)
+// cover the FP16 split, the tensor-core accumulation, the contract chain and the final roundings; for
+// entries that end in the FP16 subnormals the split adds <= 2^-25 absolute per entry of s X,
+// i.e. <= 2^-23 sqrt(d) sqrt(rmax) / s <= 2^-26 d^(1/2) rmax / 16 in D: the EPS_ABS term.
 constexpr float EPS_ABS = 2.384185791015625e-07f;    // 2^-22 (d <= 256: 2^-26 * 16 / 16 = 2^-26, x16 margin)
 // the subnormal term grows with sqrt(d): keep the margin beyond 256 coordinates
 static float eps_abs_coeff(int64_t d) { return d > 256 ? EPS_ABS * sqrtf((float)d / 256.0f) : EPS_ABS; }
@@ -1161,6 +1203,8 @@ struct PilotSpec {
 
 struct MedianArena {
     __half *Xh = nullptr, *Xl = nullptr;
+    float *e = nullptr;                       // per-row error budget (err_budget_kernel), x_rows entries
+    int64_t e_rows = 0;
     PairEntry *list = nullptr;
     uint2 *band = nullptr;
     unsigned long long *counters = nullptr;   // CNT_TOTAL u64, layout below
@@ -1186,7 +1230,8 @@ constexpr int CNT_BAND_LEN = CNT_G1_END + 4, CNT_RMAX = CNT_G1_END + 5, CNT_HPAR
 constexpr int CNT_SCALE = CNT_G1_END + 7;      // 3 floats: s, s^2, 1/s^2
 constexpr int CNT_WINDOW = CNT_G1_END + 9;     // device-picked pilot window: 2 floats, 2 keys, status word
 constexpr int CNT_BANDP = CNT_G1_END + 12;     // device-picked band parameters (BP_* words below)
-constexpr int CNT_TOTAL = CNT_G1_END + 18;
+constexpr int CNT_EMAX = CNT_G1_END + 18;      // 1 float: max_i e_i
+constexpr int CNT_TOTAL = CNT_G1_END + 20;
 
 
 static MedianArena g_arena;   // one per process (one GPU per process)
@@ -1210,6 +1255,14 @@ static int ensure_arena(stein_ctx *ctx, int64_t rows, int64_t DP, uint64_t pairs
         STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.Xh, rows * DP * 2));
         STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.Xl, rows * DP * 2));
         A.x_elems = rows * DP;
+    }
+    if (rows + 256 > A.e_rows && rows > 0) {
+        if (A.e) cudaFree(A.e);
+        A.e = nullptr;
+        // 256 spare entries: the wide sweep's last 256-row tile may reach past the 128-padded rows (masked reads)
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.e, (rows + 256) * 4));
+        STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(A.e, 0, (rows + 256) * 4, ctx->stream));
+        A.e_rows = rows + 256;
     }
     // the pilot window holds ~0.7 % of the pairs; room for 2 % (upper-triangular count)
     const unsigned long long want = pairs ? std::max<unsigned long long>(1ull << 20, pairs / 50) : 0ull;
@@ -1385,17 +1438,17 @@ bool median_tc_has_hint(const stein_ctx *ctx) { return hint_usable(ctx); }
 // counters and that histogram in ONE round trip.  Same formulas as the host-driven path below.
 // Returns like median_tc.
 static int median_tc_device_tail(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t d, int64_t ld,
-                                 const uint64_t ranks[2], float c_half, SweepParams *p, uint32_t keys_out[2]) {
+                                 const uint64_t ranks[2], SweepParams *p, uint32_t keys_out[2]) {
     MedianArena &A = g_arena;
     const int world = ctx->has_comm ? ctx->comm.world : 1;
     uint32_t *bp = reinterpret_cast<uint32_t *>(A.counters + CNT_BANDP);
     int *d_overflow2 = reinterpret_cast<int *>(A.counters + CNT_OVERFLOW2);
     pick_band_kernel<<<1, 1024, 0, ctx->stream>>>(A.counters, CNT_BELOW, CNT_LISTED, CNT_OVERFLOW, CNT_HIST, CNT_RMAX,
-                                                 CNT_HPARAMS, ranks[0], ranks[1], c_half, eps_abs_coeff(d),
+                                                 CNT_EMAX, CNT_HPARAMS, ranks[0], ranks[1], eps_abs_coeff(d),
                                                  (uint32_t)HIST_MAX_BINS, bp);
     STEIN_CHECK_LAUNCH(ctx);
     band_filter_kernel<<<16 * ctx->num_sms, BF_THREADS, 0, ctx->stream>>>(
-        A.list, A.list_cap, r, 0.f, 0.f, c_half, 0.f, A.counters + CNT_BELOW2, A.counters + CNT_BANDW,
+        A.list, A.list_cap, A.e, 0.f, 0.f, 0.f, A.counters + CNT_BELOW2, A.counters + CNT_BANDW,
         A.counters + CNT_BAND_LEN, A.band, A.band_cap, d_overflow2, A.counters + CNT_LIST_LEN, bp);
     STEIN_CHECK_LAUNCH(ctx);
     if (world > 1) STEIN_TRY(allreduce_u64(ctx, A.counters + CNT_BELOW2, 3));
@@ -1476,7 +1529,10 @@ int median_tc_begin(stein_ctx *ctx, const float *X, const float *r, int64_t n, i
     A.fresh = false;
     STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(A.counters, 0, CNT_TOTAL * 8, ctx->stream));
     float *d_scale = reinterpret_cast<float *>(A.counters + CNT_SCALE);
-    max_kernel<<<1, 1024, 0, ctx->stream>>>(r, n, reinterpret_cast<float *>(A.counters + CNT_RMAX), d_scale);
+    err_budget_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, ctx->stream>>>(X, rows, n, ld, A.e);
+    STEIN_CHECK_LAUNCH(ctx);
+    max_kernel<<<1, 1024, 0, ctx->stream>>>(r, A.e, n, reinterpret_cast<float *>(A.counters + CNT_RMAX),
+                                           reinterpret_cast<float *>(A.counters + CNT_EMAX), d_scale);
     STEIN_CHECK_LAUNCH(ctx);
     const int64_t count4 = rows * ld / 4;
     split_f16_kernel<<<(unsigned)((count4 + 255) / 256), 256, 0, ctx->stream>>>(X, count4, d_scale, A.Xh, A.Xl);
@@ -1519,7 +1575,6 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     const int64_t T2 = (T + 1) / 2;
     const int64_t ntiles = wide ? T2 * (T2 + 1) / 2 : (pair ? num_pair_tiles(T) : T * (T + 1) / 2);
     const int64_t t0 = ntiles * rank / world, t1 = ntiles * (rank + 1) / world;
-    const float c_half = eps_coeff(d);
 
     // counters zeroed, largest row norm, scale, FP16 split: already there when the caller ran
     // median_tc_begin for its pilot and this is the first sweep since
@@ -1568,7 +1623,8 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     p.wlo = key_to_float(win_lo_key);
     p.whi = key_to_float(win_hi_key);
     p.window = spec ? reinterpret_cast<const float *>(A.counters + CNT_WINDOW) : nullptr;
-    p.c_half = c_half;
+    p.e = A.e;
+    p.emax = reinterpret_cast<const float *>(A.counters + CNT_EMAX);
     p.rmax = d_rmax;
     p.scale = d_scale;
     p.hist = A.counters + CNT_HIST;
@@ -1645,12 +1701,12 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     // below / listed / overflow / histogram of the listed D~ become global quantities with ONE
     // all-reduce; the list itself (and its length) stays rank-local
     if (world > 1) STEIN_TRY(allreduce_u64(ctx, A.counters, CNT_G1_END));
-    if (spec) return median_tc_device_tail(ctx, X, r, n, d, ld, ranks, c_half, &p, keys_out);
+    if (spec) return median_tc_device_tail(ctx, X, r, n, d, ld, ranks, &p, keys_out);
     unsigned long long *h = A.h_pinned + HIST_MAX_BINS + 2;
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h, A.counters, CNT_TOTAL * 8, cudaMemcpyDeviceToHost, ctx->stream));
     STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const unsigned long long list_len = std::min<unsigned long long>(h[CNT_LIST_LEN], A.list_cap);
-    const float rmax = *reinterpret_cast<float *>(h + CNT_RMAX);
+    const float rmax = *reinterpret_cast<float *>(h + CNT_RMAX), emax = *reinterpret_cast<float *>(h + CNT_EMAX);
     const float hlo = reinterpret_cast<float *>(h + CNT_HPARAMS)[0], hscale = reinterpret_cast<float *>(h + CNT_HPARAMS)[1];
     const uint64_t below = h[CNT_BELOW], listed = h[CNT_LISTED];
     if (h[CNT_OVERFLOW]) return 1;
@@ -1672,12 +1728,12 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     const float t_lo = hlo + (float)(bstar - 1) * bin_w, t_hi = hlo + (float)(bstar + 2) * bin_w;
     // the exact value at a rank differs from the D~ value at that rank by at most max eps
     const float eps_abs = eps_abs_coeff(d) * rmax;
-    const float delta = c_half * 2.0f * rmax * 1.0001f + eps_abs + 2.0f * fmaxf(fabsf(t_lo), fabsf(t_hi)) * 1.2e-7f;
+    const float delta = 2.0f * emax * 1.0001f + eps_abs + 2.0f * fmaxf(fabsf(t_lo), fabsf(t_hi)) * 1.2e-7f;
     const float tlo = t_lo - delta, thi = t_hi + delta;
 
     if (list_len) {
         const unsigned grid = (unsigned)std::min<unsigned long long>((list_len + 255) / 256, 16ull * ctx->num_sms);
-        band_filter_kernel<<<grid, BF_THREADS, 0, ctx->stream>>>(A.list, list_len, r, tlo, thi, c_half, eps_abs,
+        band_filter_kernel<<<grid, BF_THREADS, 0, ctx->stream>>>(A.list, list_len, A.e, tlo, thi, eps_abs,
                                                                 A.counters + CNT_BELOW2, A.counters + CNT_BANDW,
                                                                 A.counters + CNT_BAND_LEN, A.band, A.band_cap,
                                                                 d_overflow2);

@@ -58,6 +58,8 @@ mbox_allreduce_kernel(T *__restrict__ buf, int count, const MboxPtrs mb, int ran
                       unsigned long long epoch, int *__restrict__ err) {
     const int g = blockIdx.x, G = gridDim.x;
     const int i0 = (int)((long long)count * g / G), i1 = (int)((long long)count * (g + 1) / G);
+    __shared__ int s_dead;          // this block gave up waiting (the host-mapped error word is only ever WRITTEN here:
+    if (threadIdx.x == 0) s_dead = 0;   // reading it would cost every thread a PCIe round trip)
     const size_t pbase = (size_t)(epoch & 1ull) * MB_PARITY_WORDS;
     // 1. this rank's slice into slot [rank] of every mailbox (own included)
     for (int r = 0; r < world; ++r) {
@@ -75,6 +77,7 @@ mbox_allreduce_kernel(T *__restrict__ buf, int count, const MboxPtrs mb, int ran
         while (ld_acquire_sys(f) < epoch) {
             if (global_timer_ns() - t0 > MB_TIMEOUT_NS) {
                 *err = 1;
+                s_dead = 1;
                 break;
             }
         }
@@ -83,7 +86,7 @@ mbox_allreduce_kernel(T *__restrict__ buf, int count, const MboxPtrs mb, int ran
     // 4. the slots in rank order (L2 loads: the lines were written by other GPUs).  After a timeout
     // the slots are not trustworthy: the result is poisoned (all bits set: NaN / a count no bracket
     // check accepts) and the host reports the error word at its next look.
-    const bool dead = *reinterpret_cast<volatile int *>(err) != 0;
+    const bool dead = s_dead != 0;
     const T *src = reinterpret_cast<const T *>(mb.base[rank] + pbase + MB_FLAGS);
     for (int i = i0 + (int)threadIdx.x; i < i1; i += (int)blockDim.x) {
         T s = __ldcg(src + i);
