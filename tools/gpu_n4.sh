@@ -1,10 +1,14 @@
 #!/bin/bash
-# 4-GPU visit: oracle check, bench with the peer-memory all-reduces, bench with NCCL all-reduces
+# N-GPU visit: oracle check of the sharded path, bench with timeline + config E.
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1"
-timeout 300 $TR --master-port 29511 tools/multi_gpu_check.py > gpurun_out/mgc4.log 2>&1; echo "mgc_rc=$?"
-grep -c " ok" gpurun_out/mgc4.log; grep -i "fail\|error\|timed out" gpurun_out/mgc4.log | head -5
-timeout 300 $TR --master-port 29512 bench.py --gpus 4 --steps 20 --warmup 3 > gpurun_out/bench_n4.log 2> gpurun_out/bench_n4.err; echo "bench_rc=$?"
-tail -1 gpurun_out/bench_n4.log | cut -c1-260
-STEIN_PEER_REDUCE=0 timeout 300 $TR --master-port 29513 bench.py --gpus 4 --steps 20 --warmup 3 > gpurun_out/bench_n4_nccl.log 2> gpurun_out/bench_n4_nccl.err; echo "bench_nccl_rc=$?"
-tail -1 gpurun_out/bench_n4_nccl.log | cut -c1-260
+N=${1:-4}
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 400 $TR --master-port 29511 tools/multi_gpu_check.py > gpurun_out/r02_mgc$N.log 2>&1; echo "mgc_rc=$?"
+grep -c " ok" gpurun_out/r02_mgc$N.log; grep -i "fail\|error\|timed out" gpurun_out/r02_mgc$N.log | head -5
+timeout 600 $TR --master-port 29512 bench.py --gpus $N --steps 20 --warmup 3 --config-e-steps 2 > gpurun_out/r02_bench_n$N.log 2> gpurun_out/r02_bench_n$N.err; echo "bench_rc=$?"
+python - <<PY
+import json
+l=json.loads(open('gpurun_out/r02_bench_n$N.log').read().strip().splitlines()[-1])
+print("value",l["value"],"ms",l["ms_per_step"],"e2e",l["e2e"]["value"])
+print(l["phases_ms"]); print(l["config_e"].get("ms_per_step"), l["config_e"].get("phases_ms"), l["config_e"].get("error"))
+PY

@@ -24,7 +24,8 @@ def main():
     ctx = context(local)
     make_comm(ctx)
     ok = True
-    for n, d, push in [(1000, 33, True), (5000, 256, True), (5000, 256, False), (4097, 128, True)]:
+    for n, d, push in [(1000, 33, True), (5000, 256, True), (5000, 256, False), (4097, 128, True), (4200, 1024, True),
+                       (4500, 600, True)]:
         rng = np.random.default_rng(n)
         X = rng.standard_normal((n, d)).astype(np.float32).astype(np.float64)
         mean = rng.standard_normal(d)
