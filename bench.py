@@ -182,7 +182,35 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Best effort: run this rank (and first-touch its pinned buffers) on the NUMA node its GPU hangs off.
+    With N ranks streaming particles over PCIe at once, buffers that all live on one socket share that
+    socket's links and the inter-socket fabric.  Returns a short description for the bench line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:          # 00000000:1b:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "numa node %d (%d cpus)" % (node, len(cpus))
+        return "numa node %d (no allowed cpu)" % node
+    except Exception as exc:       # containers without /sys, no NVML, ...
+        return "not bound (%s)" % type(exc).__name__
+
+
 def run_ours(args):
+    numa = bind_to_gpu_numa_node(int(os.environ.get("LOCAL_RANK", "0")))
     import torch
     import torch.distributed as dist
     from stein_b200 import _lib
@@ -394,6 +422,7 @@ def run_ours(args):
                          "(1 sweep); a step after a jump of the particles pays 2 sweeps"},
     }
     line["e2e"]["d2h_ms_alone"] = d2h_ms
+    line["e2e"]["host_placement"] = numa
     line["e2e"]["note"] = ("synchronous contract (the caller holds the new particles when the call returns): the "
                            "%.1f MB download crosses PCIe after the optimizer kernel and cannot overlap it; "
                            "scores upload overlaps the median" % (X_np.nbytes / 1e6))

@@ -51,8 +51,14 @@ struct stein_ctx {
     // phi route guard (phi_tc.cu): device / pinned words [kappa, max centred norm^2] of the last guarded
     // phi call, the event that marks their copy, the route that call took (0 fast, 1 precise, 2 FP32
     // FFMA; -1 none yet) and the predicted error up to which a faster route is taken
-    float *d_guard = nullptr, *h_guard = nullptr;
-    cudaEvent_t ev_guard = nullptr;
+    float *d_guard = nullptr, *h_guard = nullptr;       // two slots of 4 floats each, alternating per call
+    cudaEvent_t ev_guard[2] = {nullptr, nullptr};
+    uint64_t guard_calls = 0;
+    // Set by an engine around its phi call: within one engine's iteration sequence the cloud moves slowly,
+    // so the route may be decided from the PREVIOUS iteration's kappa (already on the host: no round trip)
+    // while this iteration's value travels for the next one.  guard_lag_owner: whose value the other slot
+    // holds (NULL: nobody's -- the next guarded call waits for its own value).
+    const void *guard_owner = nullptr, *guard_lag_owner = nullptr;
     int last_route = -1;
     float last_kappa = 0.0f, last_pred_fast = 0.0f;
     float phi_guard_tol = 5.0e-5f;

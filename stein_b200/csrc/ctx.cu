@@ -86,7 +86,8 @@ int stein_ctx_destroy(stein_ctx *ctx) {
     if (ctx->h_sel) cudaFreeHost(ctx->h_sel);
     if (ctx->d_guard) cudaFree(ctx->d_guard);
     if (ctx->h_guard) cudaFreeHost(ctx->h_guard);
-    if (ctx->ev_guard) cudaEventDestroy(ctx->ev_guard);
+    for (int k = 0; k < 2; ++k)
+        if (ctx->ev_guard[k]) cudaEventDestroy(ctx->ev_guard[k]);
     for (int r = 0; r < STEIN_REGION_COUNT; ++r)
         for (auto &ev : ctx->prof_events[r]) ctx->prof_pool.push_back(ev);
     for (auto &ev : ctx->prof_pool) {

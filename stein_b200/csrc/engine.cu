@@ -242,6 +242,8 @@ int stein_engine_buffers(stein_engine *e, float **X_local_dev, float **S_local_d
 int stein_engine_set_particles(stein_engine *e, const void *X_host, int is_f64) {
     if (!e) return STEIN_ERR_INVALID;
     e->x_all_current = false;      // the other ranks' copies of these rows are stale now
+    if (e->ctx->guard_lag_owner == reinterpret_cast<const void *>(e->uid))
+        e->ctx->guard_lag_owner = nullptr;     // a new cloud: the next phi call waits for its own conditioning number
     STEIN_TRY(upload(e, X_host, is_f64, e->X_local()));
     STEIN_CHECK_CUDA(e->ctx, cudaStreamSynchronize(e->ctx->stream));
     return STEIN_OK;
@@ -330,9 +332,13 @@ static int step_phi(stein_engine *e, float bw, bool scores_gathered) {
         if (ctx->comm.allgather_f32(ctx->comm.user, e->S_local(), e->S_all, cnt) != 0)
             return fail(ctx, STEIN_ERR_COMM, "allgather_f32 hook failed");
     }
-    // abstract_stein_sampler.py:100-105
-    STEIN_TRY(stein_phi(ctx, e->X_all, e->S_all, e->r_all, e->n_total, e->d, e->ld, e->row_begin,
-                        std::max<int64_t>(e->n_local, 1), bw, e->ws, e->ws_bytes, e->phi, e->sumsq));
+    // abstract_stein_sampler.py:100-105.  The conditioning guard of the phi call may decide from the previous
+    // iteration's kappa (guard_owner): successive clouds of one engine differ by one small step.
+    ctx->guard_owner = reinterpret_cast<const void *>(e->uid);
+    const int prc = stein_phi(ctx, e->X_all, e->S_all, e->r_all, e->n_total, e->d, e->ld, e->row_begin,
+                              std::max<int64_t>(e->n_local, 1), bw, e->ws, e->ws_bytes, e->phi, e->sumsq);
+    ctx->guard_owner = nullptr;
+    STEIN_TRY(prc);
     if (e->world > 1) STEIN_TRY(allreduce_f64(ctx, e->sumsq, 1));
     return STEIN_OK;
 }

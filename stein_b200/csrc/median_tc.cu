@@ -1208,8 +1208,8 @@ struct MedianArena {
     PairEntry *list = nullptr;
     uint2 *band = nullptr;
     unsigned long long *counters = nullptr;   // CNT_TOTAL u64, layout below
-    unsigned long long *bins = nullptr;       // HIST_MAX_BINS + 2
-    unsigned long long *h_pinned = nullptr;   // HIST_MAX_BINS + 2 window counts, then CNT_TOTAL counters
+    unsigned long long *bins = nullptr;       // HIST_MAX_BINS + 8 (window counts, then 3 words riding on the last all-reduce)
+    unsigned long long *h_pinned = nullptr;   // HIST_MAX_BINS + 8 window counts, then CNT_TOTAL counters
     int64_t x_elems = 0;
     unsigned long long list_cap = 0, band_cap = 0;
     // centre of the last pilot window (keys): successive iterations move the median only slightly
@@ -1245,8 +1245,8 @@ static int ensure_arena(stein_ctx *ctx, int64_t rows, int64_t DP, uint64_t pairs
     MedianArena &A = g_arena;
     if (!A.counters) {
         STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.counters, CNT_TOTAL * 8));
-        STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.bins, (HIST_MAX_BINS + 2) * 8));
-        STEIN_CHECK_CUDA(ctx, cudaMallocHost(&A.h_pinned, (HIST_MAX_BINS + 2 + CNT_TOTAL) * 8));
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.bins, (HIST_MAX_BINS + 8) * 8));
+        STEIN_CHECK_CUDA(ctx, cudaMallocHost(&A.h_pinned, (HIST_MAX_BINS + 8 + CNT_TOTAL) * 8));
     }
     if (rows * DP > A.x_elems && rows * DP > 0) {
         if (A.Xh) cudaFree(A.Xh);
@@ -1451,7 +1451,8 @@ static int median_tc_device_tail(stein_ctx *ctx, const float *X, const float *r,
         A.list, A.list_cap, A.e, 0.f, 0.f, 0.f, A.counters + CNT_BELOW2, A.counters + CNT_BANDW,
         A.counters + CNT_BAND_LEN, A.band, A.band_cap, d_overflow2, A.counters + CNT_LIST_LEN, bp);
     STEIN_CHECK_LAUNCH(ctx);
-    if (world > 1) STEIN_TRY(allreduce_u64(ctx, A.counters + CNT_BELOW2, 3));
+    // (the three global words of the filter -- below, band weight, overflow -- are only read by the host:
+    //  they ride on the all-reduce of the band histogram below instead of taking one of their own)
     STEIN_TRY(launch_pair_chain<0>(ctx, A.band, A.band_cap, X, r, n, ld, 0, A.counters + CNT_BAND_LEN));
     static bool attr_set = false;
     if (!attr_set) {
@@ -1463,9 +1464,13 @@ static int median_tc_device_tail(stein_ctx *ctx, const float *X, const float *r,
     window_hist_kernel<1><<<4 * ctx->num_sms, 256, (HIST_MAX_BINS + 1) * 4, ctx->stream>>>(
         A.band, A.band_cap, A.counters + CNT_BAND_LEN, 0u, 0u, (uint32_t)HIST_MAX_BINS, A.bins, bp);
     STEIN_CHECK_LAUNCH(ctx);
-    if (world > 1) STEIN_TRY(allreduce_u64(ctx, A.bins, HIST_MAX_BINS + 1));
-    unsigned long long *h = A.h_pinned + HIST_MAX_BINS + 2;
-    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.h_pinned, A.bins, (HIST_MAX_BINS + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (world > 1) {
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.bins + HIST_MAX_BINS + 1, A.counters + CNT_BELOW2, 3 * 8,
+                                              cudaMemcpyDeviceToDevice, ctx->stream));
+        STEIN_TRY(allreduce_u64(ctx, A.bins, HIST_MAX_BINS + 4));
+    }
+    unsigned long long *h = A.h_pinned + HIST_MAX_BINS + 8;
+    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.h_pinned, A.bins, (HIST_MAX_BINS + 4) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h, A.counters, CNT_TOTAL * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (ctx->presync_fn) {
         // the caller has bandwidth-independent work for this stream: queue it behind the copies and
@@ -1488,11 +1493,13 @@ static int median_tc_device_tail(stein_ctx *ctx, const float *X, const float *r,
     memcpy(&p->whi, &wv[1], 4);
     A.last_center = (uint32_t)(((uint64_t)wv[2] + wv[3]) / 2);
     const uint32_t *hbp = reinterpret_cast<const uint32_t *>(h + CNT_BANDP);
-    if (hbp[BP_STATUS] != 0u || h[CNT_OVERFLOW2] || h[CNT_BAND_LEN] > A.band_cap) return 1;
+    // global (below2, band weight, overflow2): all-reduced at the tail of the histogram on sharded runs
+    const unsigned long long *g3 = world > 1 ? A.h_pinned + HIST_MAX_BINS + 1 : h + CNT_BELOW2;
+    if (hbp[BP_STATUS] != 0u || g3[2] || h[CNT_BAND_LEN] > A.band_cap) return 1;
     float tlo, thi;
     memcpy(&tlo, &hbp[BP_TLO], 4);
     memcpy(&thi, &hbp[BP_THI], 4);
-    const uint64_t c1 = h[CNT_BELOW] + h[CNT_BELOW2], band_w = h[CNT_BANDW];
+    const uint64_t c1 = h[CNT_BELOW] + g3[0], band_w = g3[1];
     if (!(c1 <= ranks[0] && ranks[1] < c1 + band_w)) return 1;
     uint64_t rk[2] = {ranks[0] - c1, ranks[1] - c1};
     uint32_t k01[2] = {0u, 0u};
@@ -1702,7 +1709,7 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     // all-reduce; the list itself (and its length) stays rank-local
     if (world > 1) STEIN_TRY(allreduce_u64(ctx, A.counters, CNT_G1_END));
     if (spec) return median_tc_device_tail(ctx, X, r, n, d, ld, ranks, &p, keys_out);
-    unsigned long long *h = A.h_pinned + HIST_MAX_BINS + 2;
+    unsigned long long *h = A.h_pinned + HIST_MAX_BINS + 8;
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h, A.counters, CNT_TOTAL * 8, cudaMemcpyDeviceToHost, ctx->stream));
     STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const unsigned long long list_len = std::min<unsigned long long>(h[CNT_LIST_LEN], A.list_cap);

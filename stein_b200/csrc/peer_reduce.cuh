@@ -6,7 +6,7 @@ namespace stein {
 
 constexpr int MB_RANKS = MAX_PEERS + 1;
 constexpr int MB_BLOCKS = 16;                        // slices (CTAs, flags) per all-reduce
-constexpr int MB_CAP = HIST_MAX_BINS + 2;            // 8-byte words per rank slot
+constexpr int MB_CAP = HIST_MAX_BINS + 8;            // 8-byte words per rank slot
 constexpr size_t MB_FLAGS = (size_t)MB_RANKS * MB_BLOCKS;                   // flag words per parity
 constexpr size_t MB_PARITY_WORDS = MB_FLAGS + (size_t)MB_RANKS * MB_CAP;    // flags, then the rank slots
 // bytes an engine appends to its particle buffer (zero-initialised, exported with it through IPC)

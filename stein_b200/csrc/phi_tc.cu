@@ -1556,19 +1556,28 @@ reduce_partials2_kernel(const double *__restrict__ partials, int count, double *
 // route: 0 fast, 1 precise, 2 FP32 FFMA.  `have_fast` / `have_precise`: the routes this kernel family offers.
 static int guard_begin(stein_ctx *ctx, const float *rc, int64_t n_total, float h2) {
     if (!ctx->d_guard) {
-        STEIN_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_guard, 16));
-        STEIN_CHECK_CUDA(ctx, cudaMallocHost(&ctx->h_guard, 16));
-        STEIN_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_guard, cudaEventDisableTiming));
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_guard, 32));
+        STEIN_CHECK_CUDA(ctx, cudaMallocHost(&ctx->h_guard, 32));
+        for (int k = 0; k < 2; ++k)
+            STEIN_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_guard[k], cudaEventDisableTiming));
     }
-    phi_guard_kernel<<<1, 1024, 0, ctx->stream>>>(rc, n_total, h2, ctx->d_guard);
+    const int slot = (int)(++ctx->guard_calls & 1);
+    phi_guard_kernel<<<1, 1024, 0, ctx->stream>>>(rc, n_total, h2, ctx->d_guard + 4 * slot);
     STEIN_CHECK_LAUNCH(ctx);
-    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_guard, ctx->d_guard, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    STEIN_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_guard, ctx->stream));
+    STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_guard + 4 * slot, ctx->d_guard + 4 * slot, 8, cudaMemcpyDeviceToHost,
+                                          ctx->stream));
+    STEIN_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_guard[slot], ctx->stream));
     return STEIN_OK;
 }
 static int guard_end(stein_ctx *ctx, int64_t d_true, bool have_fast, bool have_precise, bool bf16_only, int *route) {
-    STEIN_CHECK_CUDA(ctx, cudaEventSynchronize(ctx->ev_guard));
-    const float kappa = ctx->h_guard[0];
+    const int slot = (int)(ctx->guard_calls & 1);
+    // inside an engine's iteration sequence: decide from the previous iteration's value (its copy finished
+    // long ago) and let this iteration's value travel for the next decision
+    const bool lagged = ctx->guard_owner != nullptr && ctx->guard_lag_owner == ctx->guard_owner;
+    const int use = lagged ? slot ^ 1 : slot;
+    STEIN_CHECK_CUDA(ctx, cudaEventSynchronize(ctx->ev_guard[use]));
+    ctx->guard_lag_owner = ctx->guard_owner;
+    const float kappa = ctx->h_guard[4 * use];
     const float sk = sqrtf(fmaxf(kappa, 0.0f)), rd = 1.0f / sqrtf((float)std::max<int64_t>(d_true, 1));
     const float pred_fast = 1.0e-5f * kappa * rd + 1.2e-6f * kappa + 7.6e-6f * sk;
     const float pred_precise = bf16_only ? 1.0e-6f * kappa + 7.6e-6f * sk : 1.2e-6f * kappa + 3.0e-6f * sk;
