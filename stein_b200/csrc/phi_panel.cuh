@@ -28,15 +28,16 @@ namespace panel {
 
 using namespace pg;
 
-// 256 x 256 x 4 B tiles of P per block (environment STEIN_PANEL_TILES).  Measured at n = 32 768, d = 1 024 on
-// one B200: an L2-sized block (256 tiles = 64 MiB) runs the two kernels at 487 TFLOP/s algorithmic -- 190
+// 256 x 256 x 4 B tiles of P per block (environment STEIN_PANEL_TILES).  Measured on one B200.  n = 32 768,
+// d = 1 024: an L2-sized block (256 tiles = 64 MiB) runs the two kernels at 487 TFLOP/s algorithmic -- 190
 // launches of ~60 us each, K loops of 1 024 -- while 1 024 tiles (240 MiB, 40 launches) reach 769: the P block
 // then streams through HBM (its four column-slice readers run side by side and share it in L2), which the
-// tensor-bound kernels hide.  4 096 tiles are slower again (712: wave quantisation of the few launches).
+// tensor-bound kernels hide.  One rank's share of config E (32 768 rows x 262 144 columns), second repetition
+// (power-capped clocks): 1 024 tiles 682, 1 536: 705, 2 048: 709, 3 072: 711 TFLOP/s -- 2 048 it is (481 MiB).
 static int64_t p_budget_tiles() {
     static int64_t v = 0;
     if (!v) {
-        v = 1024;
+        v = 2048;
         if (const char *e = getenv("STEIN_PANEL_TILES")) {
             const long long x = atoll(e);
             if (x >= 2 && x <= (1 << 20)) v = x;
@@ -48,10 +49,22 @@ static int64_t p_budget_tiles() {
 // ---------------------------------------------------------------------------------------------
 // kernel A: exponentials of one block of the kernel matrix
 // ---------------------------------------------------------------------------------------------
+// Tensor maps of the P arrays for the epilogue's TMA stores (boxes of 32 rows x 32 columns, dense rows)
+struct PStoreMaps {
+    CUtensorMap p16, pl, ph;      // pl: E4M3 residual (fast) or FP16 residual (precise); ph: E4M3 of P (fast only)
+};
+
 struct ExpPolicy {
-    static constexpr int STAGES = 6;
-    static constexpr size_t TAIL_BYTES = 2 * 256 * 4 + 128 * 4 + 64;
+    // 5 ring stages + 32 KB of staging: a warp's 32 x 32 block of P goes to shared memory and leaves through
+    // TMA stores.  (Direct stores -- every thread its own row, 16 bytes at a time -- cost 32 L2 transactions
+    // per warp instruction and held this kernel at 47 % tensor-pipe activity: the epilogue, not the MMAs,
+    // set the pace.)
+    static constexpr int STAGES = 5;
+    static constexpr size_t STAGING_PER_WARP = 4096;
+    static constexpr size_t TAIL_STAGING = 3072;     // offset of the staging area in the tail (128-byte aligned)
+    static constexpr size_t TAIL_BYTES = TAIL_STAGING + EPI_WARPS * STAGING_PER_WARP + 64;
     struct Params : Core {
+        const PStoreMaps *smaps;     // device copy of the store maps (64-byte aligned)
         int tiles_i, tiles_j;        // tile grid of this launch (256-row x 256-column tiles)
         const float *nrm;            // -r_j log2(e) / (2 h^2) by global particle index; -inf beyond n
         float c1;                    // log2(e) / h^2
@@ -76,6 +89,7 @@ struct ExpPolicy {
     struct Epilogue {
         const Params &p;
         float *sB, *sK;
+        uint8_t *stg;                // this warp's staging: [P16 32 x 64 B | pl 32 x 32 B (64 B precise) | ph 32 x 32 B]
         int q, wg, row, lane, tid256;
         uint32_t lane_addr, rank;
         float c1, a_i, ksum;
@@ -85,6 +99,7 @@ struct ExpPolicy {
             : p(p_), lane(lane_), rank(rank_), par(0) {
             sB = reinterpret_cast<float *>(tail);
             sK = sB + 2 * 256;
+            stg = tail + TAIL_STAGING + (size_t)(warp - 4) * STAGING_PER_WARP;
             q = warp & 3;
             wg = (warp - 4) >> 2;
             row = q * 32 + lane;
@@ -131,21 +146,33 @@ struct ExpPolicy {
                         }
                     }
                 }
-                const size_t e = (size_t)prow * (size_t)p.pcols + (size_t)tj * 256 + (size_t)ch * 32;   // element index
-                uint4 *d16 = reinterpret_cast<uint4 *>(p.P16 + e);
+                // this warp's 32 rows x 32 columns through shared memory and out by TMA (the previous block's
+                // stores must have finished reading the staging area)
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+                uint4 *s16 = reinterpret_cast<uint4 *>(stg + lane * 64);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) d16[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+                for (int k = 0; k < 4; ++k) s16[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
                 if (p.precise) {
-                    uint4 *dl = reinterpret_cast<uint4 *>(p.Pl16 + e);
+                    uint4 *sl = reinterpret_cast<uint4 *>(stg + 2048 + lane * 64);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        dl[k] = make_uint4(w[16 + 4 * k], w[17 + 4 * k], w[18 + 4 * k], w[19 + 4 * k]);
+                        sl[k] = make_uint4(w[16 + 4 * k], w[17 + 4 * k], w[18 + 4 * k], w[19 + 4 * k]);
                 } else {
-                    uint4 *dl = reinterpret_cast<uint4 *>(p.Pl8 + e), *dh = reinterpret_cast<uint4 *>(p.Ph8 + e);
-                    dl[0] = make_uint4(w[16], w[17], w[18], w[19]);
-                    dl[1] = make_uint4(w[20], w[21], w[22], w[23]);
-                    dh[0] = make_uint4(w[24], w[25], w[26], w[27]);
-                    dh[1] = make_uint4(w[28], w[29], w[30], w[31]);
+                    uint4 *sl = reinterpret_cast<uint4 *>(stg + 2048 + lane * 32), *sh = reinterpret_cast<uint4 *>(stg + 3072 + lane * 32);
+                    sl[0] = make_uint4(w[16], w[17], w[18], w[19]);
+                    sl[1] = make_uint4(w[20], w[21], w[22], w[23]);
+                    sh[0] = make_uint4(w[24], w[25], w[26], w[27]);
+                    sh[1] = make_uint4(w[28], w[29], w[30], w[31]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    const int c0 = tj * 256 + ch * 32, r0 = (int)(prow - lane);      // first column / row of the block
+                    tma_store_2d(&p.smaps->p16, stg, c0, r0);
+                    tma_store_2d(&p.smaps->pl, stg + 2048, c0, r0);
+                    if (!p.precise) tma_store_2d(&p.smaps->ph, stg + 3072, c0, r0);
+                    tma_store_commit();
                 }
             }
             // row sum of this tile: the two warpgroups own 128 columns each
@@ -153,7 +180,10 @@ struct ExpPolicy {
             named_bar_sync(2, EPI_THREADS);
             if (wg == 0) p.ksp[(size_t)prow * p.ksp_ld + tj] = ksum + sK[row];
         }
-        __device__ void finish() {}
+        __device__ void finish() {
+            if (lane == 0) tma_store_wait_all();      // the stores of this CTA are complete before it exits
+            __syncwarp();
+        }
     };
 };
 
@@ -289,6 +319,7 @@ int64_t panel_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t n_t
     b += pl.rp * 256 * pl.cc * 256 * 4;                        // one block of P
     b += pl.rp * 256 * pl.cc * 4;                              // its row sums per column tile
     b += FINALIZE_MAX_BLOCKS * 8;
+    b += 1024;                                                 // tensor maps of the epilogue's TMA stores
     return b + 8192;
 }
 
@@ -339,6 +370,8 @@ int phi_panel(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
     uint8_t *PL = (uint8_t *)pws;       pws += prow_cap * pcols * 2;    // Pl8 | Ph8, or Pl16
     float *ksp = (float *)pws;          pws += prow_cap * pl.cc * 4;
     double *partials = (double *)(((uintptr_t)pws + 7) & ~(uintptr_t)7);
+    pws = (char *)partials + FINALIZE_MAX_BLOCKS * 8;
+    PStoreMaps *d_smaps = (PStoreMaps *)(((uintptr_t)pws + 127) & ~(uintptr_t)127);
 
     xscale_kernel<<<1, 1024, 0, ctx->stream>>>(cen.blockmax, cen.nblockmax, xscale);
     STEIN_CHECK_LAUNCH(ctx);
@@ -409,6 +442,22 @@ int phi_panel(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
         STEIN_TRY(mapy(&mB.b[2], YTL + cols * ld, 1));            // y8l
     }
 
+    // store maps of kernel A's epilogue: boxes of 32 x 32 elements, dense rows in shared memory
+    {
+        PStoreMaps hm;
+        memset(&hm, 0, sizeof(hm));
+        STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.p16, P16, 2, (uint64_t)pcols, (uint64_t)prow_cap, (uint64_t)pcols * 2, 32, 32, false));
+        if (precise) {
+            STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.pl, PL, 2, (uint64_t)pcols, (uint64_t)prow_cap, (uint64_t)pcols * 2, 32, 32, false));
+            hm.ph = hm.pl;
+        } else {
+            STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.pl, PL, 1, (uint64_t)pcols, (uint64_t)prow_cap, (uint64_t)pcols, 32, 32, false));
+            STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.ph, PL + prow_cap * pcols, 1, (uint64_t)pcols, (uint64_t)prow_cap,
+                                             (uint64_t)pcols, 32, 32, false));
+        }
+        // pageable source: the runtime stages the bytes before returning
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(d_smaps, &hm, sizeof(hm), cudaMemcpyHostToDevice, ctx->stream));
+    }
     using KA = ExpPolicy;
     using KB = AccPolicy;
     const size_t smemA = smem_bytes<KA::STAGES>(KA::TAIL_BYTES), smemB = smem_bytes<KB::STAGES>(KB::TAIL_BYTES);
@@ -445,6 +494,7 @@ int phi_panel(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
                 pa.c1 = l2e / h2;
                 pa.c1mul = xscale + 1;
                 pa.precise = precise ? 1 : 0;
+                pa.smaps = d_smaps;
                 pa.P16 = P16;
                 pa.Pl8 = PL;
                 pa.Ph8 = PL + prow_cap * pcols;

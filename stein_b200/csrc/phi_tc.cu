@@ -1343,8 +1343,21 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
+static int make_tensor_map_2d_box(stein_ctx *ctx, CUtensorMap *map, const void *base, int elem_bytes, uint64_t inner,
+                                  uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows,
+                                  bool swizzle128);
+
 int make_tensor_map_2d(stein_ctx *ctx, CUtensorMap *map, const void *base, int elem_bytes, uint64_t inner,
                        uint64_t outer, uint64_t row_stride_bytes, uint32_t box_rows) {
+    return make_tensor_map_2d_box(ctx, map, base, elem_bytes, inner, outer, row_stride_bytes,
+                                  (uint32_t)(128 / elem_bytes), box_rows, true);      // 128-byte rows
+}
+
+// general form: box of box_inner elements x box_rows rows; swizzle128 = false: dense rows in shared memory
+// (the layout TMA STORES of the panel kernels read)
+static int make_tensor_map_2d_box(stein_ctx *ctx, CUtensorMap *map, const void *base, int elem_bytes, uint64_t inner,
+                                  uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows,
+                                  bool swizzle128) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -1356,14 +1369,14 @@ int make_tensor_map_2d(stein_ctx *ctx, CUtensorMap *map, const void *base, int e
     }
     const cuuint64_t gdim[2] = {inner, outer};
     const cuuint64_t gstride[1] = {row_stride_bytes};
-    const cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), box_rows};   // 128-byte rows
+    const cuuint32_t box[2] = {box_inner, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     // (16-bit data is only moved, never converted: the BF16 type also serves FP16 arrays)
     const CUtensorMapDataType dt = elem_bytes == 1   ? CU_TENSOR_MAP_DATA_TYPE_UINT8
                                    : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                                      : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    const CUresult rc = encode(map, dt, 2, (void *)base, gdim, gstride, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    const CUresult rc = encode(map, dt, 2, (void *)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) return fail(ctx, STEIN_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)rc);
     return STEIN_OK;

@@ -69,6 +69,17 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
           "r"(c_outer)
         : "memory");
 }
+// shared::cta -> global store of one box (dense rows in shared memory); bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *smem_src, int32_t c_inner, int32_t c_outer) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
