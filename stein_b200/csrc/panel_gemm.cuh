@@ -63,6 +63,14 @@ struct Core {
     int a_row0, b_row0;        // A rows of tile row 0 / B rows of tile column 0 (in the arrays' own row numbering)
     const int *route;          // device-side route word (phi_guard_kernel) or NULL
     int my_route;              // this launch runs only when *route == my_route
+    // L2 eviction priority of the A / B operand loads (tc::L2_EVICT_*; 0 = normal): an operand that the launch
+    // reads many times should outlive the streams that pass through L2 once
+    unsigned long long pol_a, pol_b;
+    // A operand stored BOX-MAJOR (the P block of phi_panel.cuh): box (row tile rt of 128 rows, K block kb) is one
+    // contiguous 16 KB piece [128 rows][128 bytes] at row (rt * nkb + kb) * 128 of a [rows][128 B] array, with
+    // nkb = a_nkb16 K blocks of 64 two-byte elements or a_nkb8 blocks of 128 one-byte elements per row tile.
+    // 0: plain row-major A (coordinates = K element, row).
+    int a_blocked, a_nkb16, a_nkb8;
 };
 
 struct Barriers {
@@ -134,6 +142,7 @@ panel_gemm_kernel(const __grid_constant__ Maps maps, const typename Policy::Para
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t full0_addr = mapa_shared(smem_u32(&bars->full[0]), 0);
+            const uint64_t pol_a = p.pol_a ? p.pol_a : L2_EVICT_NORMAL, pol_b = p.pol_b ? p.pol_b : L2_EVICT_NORMAL;
             int ti, tj;
             for (long long k = 0; Policy::tile(p, k, cl, ncl, ti, tj); ++k) {
                 const int arow = p.a_row0 + ti * 256 + (int)rank * 128;
@@ -148,8 +157,15 @@ panel_gemm_kernel(const __grid_constant__ Maps maps, const typename Policy::Para
                             if (leader) mbar_expect_tx(&bars->full[stage], 2u * STAGE_BYTES);
                             uint8_t *dst = sRing + (size_t)stage * STAGE_BYTES;
                             const uint32_t fa = full0_addr + 8u * (uint32_t)stage;
-                            tma_load_2d_pair(dst, &maps.a[st.a], fa, p.ka0 + g * 128 + st.koff, arow);
-                            tma_load_2d_pair(dst + BOX_BYTES, &maps.b[st.b], fa, p.kb0 + g * 128 + st.koff, brow);
+                            if (p.a_blocked) {
+                                const int kk = p.ka0 + g * 128 + st.koff;
+                                const int rt = ti * 2 + (int)rank;
+                                const int orow = st.f8 ? (rt * p.a_nkb8 + (kk >> 7)) * 128 : (rt * p.a_nkb16 + (kk >> 6)) * 128;
+                                tma_load_2d_pair_hint(dst, &maps.a[st.a], fa, 0, orow, pol_a);
+                            } else {
+                                tma_load_2d_pair_hint(dst, &maps.a[st.a], fa, p.ka0 + g * 128 + st.koff, arow, pol_a);
+                            }
+                            tma_load_2d_pair_hint(dst + BOX_BYTES, &maps.b[st.b], fa, p.kb0 + g * 128 + st.koff, brow, pol_b);
                         }
                         __syncwarp();
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -12,7 +12,10 @@
 // (2.5 x the tensor work at d = 1 024) or K crosses memory once.  It crosses once, but never as an
 // n x n object: the local rows are cut into PANELS and the columns into CHUNKS, and one block of
 // P = exp(-D / 2h^2) (2 B FP16 + 2 x 1 B FP8 per entry, <= 256 MiB, see p_budget_tiles) lives between the
-// two kernels that touch it:
+// two kernels that touch it.  The block is stored BOX-MAJOR -- every [128 rows][128 bytes] box that kernel B's
+// TMA loads is one contiguous 16 KB piece -- so that kernel A's stores and kernel B's loads both move whole
+// 128-byte lines with DRAM-page locality (in a row-major block the 32-byte row pieces of the FP8 arrays,
+// 26 KB apart, held kernel A at 39 % tensor-pipe activity; without its stores it ran at 95 %):
 //   kernel A (ExpPolicy)  P[panel, chunk] = exp2(c1 X_panel X_chunk^T + a_i + b_j), row sums per tile
 //   kernel B (AccPolicy)  O[panel, :]    += P[panel, chunk] Y[chunk, :]
 // Both are instances of the K-streaming main loop of panel_gemm.cuh (256 x 256 tiles, CTA pairs).
@@ -70,10 +73,12 @@ struct ExpPolicy {
         float c1;                    // log2(e) / h^2
         const float *c1mul;          // device: undoes the power-of-two scaling of X
         int precise;
+        int debug_skip;              // 0 in production; 1: no epilogue work, 2: TMEM loads only, 3: no stores
         uint16_t *P16;               // [panel rows][pcols] FP16
         uint8_t *Pl8, *Ph8;          // fast: E4M3 of (P - P16) 2^12 / of P
         uint16_t *Pl16;              // precise: FP16 of (P - P16) 2^12
-        long long pcols;             // row length of the P arrays
+        long long pcols;             // columns of the P block (capacity)
+        int nkb16, nkb8;             // boxes per row tile: pcols / 64 (two-byte arrays), pcols / 128 (one-byte arrays)
         float *ksp;                  // [panel rows][ksp_ld] row sums of P per column tile
         int ksp_ld;
     };
@@ -118,12 +123,14 @@ struct ExpPolicy {
         }
         __device__ void unit(uint32_t acc_tmem, int, bool) {
             const float *bj = sB + par * 256;
+            if (p.debug_skip == 1) return;                      // timing experiments only (STEIN_PANEL_DEBUG_SKIP)
 #pragma unroll 1
             for (int cc = 0; cc < 4; ++cc) {
                 const int ch = wg * 4 + cc;                     // 32-column chunk of the 256-column tile
                 uint32_t v[32];
                 tmem_ld32(acc_tmem + lane_addr + ch * 32, v);
                 tmem_wait_ld();
+                if (p.debug_skip == 2) continue;
                 uint32_t w[32];
 #pragma unroll
                 for (int c2 = 0; c2 < 16; ++c2) {
@@ -146,6 +153,7 @@ struct ExpPolicy {
                         }
                     }
                 }
+                if (p.debug_skip == 3) continue;
                 // this warp's 32 rows x 32 columns through shared memory and out by TMA (the previous block's
                 // stores must have finished reading the staging area)
                 if (lane == 0) tma_store_wait_read();
@@ -168,10 +176,18 @@ struct ExpPolicy {
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    const int c0 = tj * 256 + ch * 32, r0 = (int)(prow - lane);      // first column / row of the block
-                    tma_store_2d(&p.smaps->p16, stg, c0, r0);
-                    tma_store_2d(&p.smaps->pl, stg + 2048, c0, r0);
-                    if (!p.precise) tma_store_2d(&p.smaps->ph, stg + 3072, c0, r0);
+                    // box-major destination: row tile rt, K block of the 32 columns, 32 rows from q * 32
+                    const int rt = (int)((prow - lane) >> 7), r32 = (int)((prow - lane) & 127);
+                    const int o16 = (rt * p.nkb16 + tj * 4 + (ch >> 1)) * 128 + r32, i16 = (ch & 1) * 32;
+                    const int o8 = (rt * p.nkb8 + tj * 2 + (ch >> 2)) * 128 + r32, i8 = (ch & 3) * 32;
+                    // the P block streams through L2 once on its way to kernel B: evict it before the operands
+                    tma_store_2d_hint(&p.smaps->p16, stg, i16, o16, L2_EVICT_FIRST);
+                    if (p.precise) {
+                        tma_store_2d_hint(&p.smaps->pl, stg + 2048, i16, o16, L2_EVICT_FIRST);
+                    } else if (p.debug_skip != 4) {
+                        tma_store_2d_hint(&p.smaps->pl, stg + 2048, i8, o8, L2_EVICT_FIRST);
+                        tma_store_2d_hint(&p.smaps->ph, stg + 3072, i8, o8, L2_EVICT_FIRST);
+                    }
                     tma_store_commit();
                 }
             }
@@ -301,6 +317,8 @@ static PanelPlan panel_plan(const stein_ctx *ctx, int64_t n_local, int64_t n_tot
             }
         }
     }
+    if (const char *e = getenv("STEIN_PANEL_RP")) pl.rp = std::max<int64_t>(1, std::min<int64_t>(R, atoll(e)));
+    if (const char *e = getenv("STEIN_PANEL_CC")) pl.cc = std::max<int64_t>(2, std::min<int64_t>(C, atoll(e) / 2 * 2));
     return pl;
 }
 
@@ -413,8 +431,11 @@ int phi_panel(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
     auto mapy = [&](CUtensorMap *m, const void *base, int eb) {
         return make_tensor_map_2d(ctx, m, base, eb, (uint64_t)cols, (uint64_t)ld, (uint64_t)cols * eb, 128);
     };
+    // P arrays, box-major: [prow_cap / 128 row tiles x nkb boxes x 128 rows][128 bytes]
+    const int64_t nkb16 = pcols / 64, nkb8 = pcols / 128;
     auto mapp = [&](CUtensorMap *m, const void *base, int eb) {
-        return make_tensor_map_2d(ctx, m, base, eb, (uint64_t)pcols, (uint64_t)prow_cap, (uint64_t)pcols * eb, 128);
+        return make_tensor_map_2d(ctx, m, base, eb, (uint64_t)(128 / eb), (uint64_t)(prow_cap * (eb == 2 ? nkb16 : nkb8)), 128,
+                                  128);
     };
     STEIN_TRY(mapx(&mA.a[0], X16, 2));
     STEIN_TRY(mapx(&mA.b[0], X16, 2));
@@ -446,14 +467,14 @@ int phi_panel(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
     {
         PStoreMaps hm;
         memset(&hm, 0, sizeof(hm));
-        STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.p16, P16, 2, (uint64_t)pcols, (uint64_t)prow_cap, (uint64_t)pcols * 2, 32, 32, false));
+        STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.p16, P16, 2, 64, (uint64_t)(prow_cap * nkb16), 128, 32, 32, false));
         if (precise) {
-            STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.pl, PL, 2, (uint64_t)pcols, (uint64_t)prow_cap, (uint64_t)pcols * 2, 32, 32, false));
+            STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.pl, PL, 2, 64, (uint64_t)(prow_cap * nkb16), 128, 32, 32, false));
             hm.ph = hm.pl;
         } else {
-            STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.pl, PL, 1, (uint64_t)pcols, (uint64_t)prow_cap, (uint64_t)pcols, 32, 32, false));
-            STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.ph, PL + prow_cap * pcols, 1, (uint64_t)pcols, (uint64_t)prow_cap,
-                                             (uint64_t)pcols, 32, 32, false));
+            STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.pl, PL, 1, 128, (uint64_t)(prow_cap * nkb8), 128, 32, 32, false));
+            STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.ph, PL + prow_cap * pcols, 1, 128, (uint64_t)(prow_cap * nkb8), 128, 32, 32,
+                                             false));
         }
         // pageable source: the runtime stages the bytes before returning
         STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(d_smaps, &hm, sizeof(hm), cudaMemcpyHostToDevice, ctx->stream));
@@ -488,18 +509,24 @@ int phi_panel(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
                 pa.b_row0 = (int)(c0 * 256);
                 pa.route = nullptr;
                 pa.my_route = 0;
+                pa.pol_a = pa.pol_b = L2_EVICT_LAST;           // the X arrays are read once per tile; P passes through once
+                if (const char *e = getenv("STEIN_PANEL_NOHINT")) pa.pol_a = pa.pol_b = atoi(e) ? L2_EVICT_NORMAL : pa.pol_a;
                 pa.tiles_i = (int)r;
                 pa.tiles_j = (int)c;
                 pa.nrm = nrm;
                 pa.c1 = l2e / h2;
                 pa.c1mul = xscale + 1;
                 pa.precise = precise ? 1 : 0;
+                pa.debug_skip = getenv("STEIN_PANEL_DEBUG_SKIP") ? atoi(getenv("STEIN_PANEL_DEBUG_SKIP")) : 0;
                 pa.smaps = d_smaps;
                 pa.P16 = P16;
                 pa.Pl8 = PL;
                 pa.Ph8 = PL + prow_cap * pcols;
                 pa.Pl16 = (uint16_t *)PL;
                 pa.pcols = pcols;
+                pa.nkb16 = (int)nkb16;
+                pa.nkb8 = (int)nkb8;
+                pa.a_blocked = 0;
                 pa.ksp = ksp;
                 pa.ksp_ld = (int)pl.cc;
                 const int gridA = 2 * (int)std::min<int64_t>(G, r * c);
@@ -516,6 +543,11 @@ int phi_panel(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
                 pb.b_row0 = 0;
                 pb.route = nullptr;
                 pb.my_route = 0;
+                pb.a_blocked = 1;
+                pb.a_nkb16 = (int)nkb16;
+                pb.a_nkb8 = (int)nkb8;
+                pb.pol_a = L2_EVICT_FIRST;                     // P: consumed here, never needed again
+                pb.pol_b = L2_EVICT_LAST;                      // Y^T of this chunk: read by every row tile
                 pb.tiles_i = (int)r;
                 pb.tiles_j = (int)(ld / 256);
                 pb.O = O;

@@ -69,6 +69,27 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
           "r"(c_outer)
         : "memory");
 }
+// L2 eviction-priority hints for TMA traffic (the encoded policies `createpolicy.fractional.L2::evict_*` returns for
+// fraction 1.0; same constants as cute::TMA::CacheHintSm90)
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_pair_hint(void *smem_dst, const CUtensorMap *map, uint32_t leader_bar_addr,
+                                                      int32_t c_inner, int32_t c_outer, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar_addr), "r"(c_inner),
+          "r"(c_outer), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap *map, const void *smem_src, int32_t c_inner,
+                                                  int32_t c_outer, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer), "l"(policy)
+                 : "memory");
+}
 // shared::cta -> global store of one box (dense rows in shared memory); bulk-group completion
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *smem_src, int32_t c_inner, int32_t c_outer) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

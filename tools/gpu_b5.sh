@@ -1,0 +1,5 @@
+#!/bin/bash
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "panel" 2>&1 | tail -3
+run() { echo "== $*"; env "$@" STEIN_PANEL_VERBOSE=1 STEIN_SKIP_MEDIAN=1 timeout 600 python tools/panel_bench.py 65536 1024 2 32768 2>&1 | tail -2; }
+run STEIN_PANEL_DEBUG_SKIP=0
+run STEIN_PANEL_DEBUG_SKIP=3
