@@ -18,6 +18,11 @@
 // 26 KB apart, held kernel A at 39 % tensor-pipe activity; without its stores it ran at 95 %):
 //   kernel A (ExpPolicy)  P[panel, chunk] = exp2(c1 X_panel X_chunk^T + a_i + b_j), row sums per tile
 //   kernel B (AccPolicy)  O[panel, :]    += P[panel, chunk] Y[chunk, :]
+// (Measured alternative, not kept: ONE cooperative launch per panel that alternates the two phases over
+//  L2-sized blocks with grid barriers in between.  P then never reaches DRAM and kernel A's operands are not
+//  evicted by its write stream, but each phase is only 1-2 waves of tiles long: the drained pipelines and the
+//  exposed last epilogue per phase cost more than the traffic saved -- 18.0 ms against 14.5 ms for 32 768 rows
+//  x 65 536 columns, d = 1 024.)
 // Both are instances of the K-streaming main loop of panel_gemm.cuh (256 x 256 tiles, CTA pairs).
 // Tensor work per pair of kernels = the algorithmic 2 GEMMs; HBM traffic = the operand arrays once per
 // panel (L2 serves the reuse inside a launch).
@@ -100,7 +105,7 @@ struct ExpPolicy {
         float c1, a_i, ksum;
         long long prow;
         int tj, par;
-        int b_row0;                  // first column of the current block (the fused kernel moves it per block)
+        int b_row0;                  // first column of the current block
         __device__ Epilogue(const Params &p_, uint8_t *tail, int warp, int lane_, uint32_t rank_)
             : p(p_), lane(lane_), rank(rank_), par(0), b_row0(p_.b_row0) {
             sB = reinterpret_cast<float *>(tail);
@@ -234,7 +239,7 @@ struct AccPolicy {
         uint32_t lane_addr, rank;
         long long prow;
         int tj;
-        int first, ksp_n;            // of the current block (the fused kernel changes them per block)
+        int first, ksp_n;            // of the current block
         float acc[128];              // fp32 round-to-nearest running sum of the drained units (the tensor
                                      // core accumulates with truncation: the chains inside TMEM stay short)
         __device__ Epilogue(const Params &p_, uint8_t *, int warp, int lane_, uint32_t rank_)
@@ -281,249 +286,6 @@ struct AccPolicy {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Fused form: ONE cooperative launch per row panel.  All clusters alternate between the two phases
-//     phase A  P[panel, block b] = exp(...)            (the tiles of kernel A above)
-//     -- grid barrier --
-//     phase B  O[panel, :] += P[panel, block b] Y[b]   (the tiles of kernel B above)
-//     -- grid barrier --
-// over column blocks small enough that P (box-major, <= ~40 MB), the panel's X operands, its O accumulator
-// and the block's column operands all stay in the 126 MB L2: P never reaches DRAM and the operands are not
-// evicted by it.  (As two launches per block the stream of P writes -- 0.5 GB per launch -- pushed the clean
-// operand lines out of L2: kernel A re-read 1 GB from DRAM per launch and ran at 57 % tensor-pipe activity,
-// against 96 % with its stores disabled.)  The TMA ring, the tensor-memory accumulators and the three warp
-// roles of panel_gemm.cuh carry on across phases; only tile lists, tensor maps and epilogues switch.
-// Grid barrier: the cooperative-groups pattern on a monotonic counter (all CTAs are co-resident: one per SM,
-// cooperative launch); a wait of more than ~4 s traps instead of hanging the GPU.
-// ---------------------------------------------------------------------------------------------
-struct FusedParams {
-    ExpPolicy::Params pa;        // phase A: tiles_i = row tiles of the panel, b_row0 = first column of block 0
-    AccPolicy::Params pb;        // phase B: tiles_i likewise, tiles_j = ld / 256
-    int nblocks, cb, ctot;       // column blocks, column tiles per block, column tiles in total (even)
-    unsigned int *gbar;          // grid-barrier counter, zero at launch
-};
-
-__device__ __forceinline__ void grid_barrier(unsigned int *gbar, unsigned int target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(gbar, 1u);
-        const long long t0 = clock64();
-        unsigned int v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gbar) : "memory");
-            if (clock64() - t0 > 8000000000ll) __trap();
-        } while (v < target);
-        __threadfence();
-        asm volatile("fence.proxy.async;" ::: "memory");      // what other SMs stored is ordered before this SM's TMA loads
-    }
-    __syncthreads();
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-panel_fused_kernel(const __grid_constant__ Maps mapsA, const __grid_constant__ Maps mapsB, const FusedParams fp) {
-    constexpr int STAGES = ExpPolicy::STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t *sRing = smem;
-    uint8_t *tail0 = sRing + (size_t)STAGES * STAGE_BYTES;
-    Barriers *bars = reinterpret_cast<Barriers *>(tail0);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail0 + 224);
-    uint8_t *tail = tail0 + 256;
-
-    const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-    const int ncl = (int)gridDim.x / 2, cl = (int)blockIdx.x / 2;
-    const ExpPolicy::Params &pa = fp.pa;
-    const AccPolicy::Params &pb = fp.pb;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&bars->full[s], 1);
-            mbar_init(&bars->empty[s], 1);
-        }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&bars->acc_full[b], 1);
-            mbar_init(&bars->acc_empty[b], 2 * EPI_WARPS);
-        }
-        fence_barrier_init();
-        fence_proxy_async();
-        for (int m = 0; m < MAX_MAPS; ++m) {
-            tma_prefetch_desc(&mapsA.a[m]);
-            tma_prefetch_desc(&mapsA.b[m]);
-            tma_prefetch_desc(&mapsB.a[m]);
-            tma_prefetch_desc(&mapsB.b[m]);
-        }
-    }
-    if (warp == 1) tmem_alloc_pair(tmem_slot, pg::TMEM_COLS);
-    tcgen05_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    tcgen05_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    const unsigned int nctas = gridDim.x;
-    unsigned int gen = 0;
-
-    // tiles of a phase: A -- row tile fastest (neighbouring clusters share the column tile);
-    //                   B -- column slice fastest (the slices of a row tile share its P rows)
-    auto tile_a = [&](long long k, int c, int &ti, int &tj) {
-        const long long t = (long long)cl + k * ncl;
-        if (t >= (long long)pa.tiles_i * c) return false;
-        ti = (int)(t % pa.tiles_i);
-        tj = (int)(t / pa.tiles_i);
-        return true;
-    };
-    auto tile_b = [&](long long k, int &ti, int &tj) {
-        const long long t = (long long)cl + k * ncl;
-        if (t >= (long long)pb.tiles_i * pb.tiles_j) return false;
-        tj = (int)(t % pb.tiles_j);
-        ti = (int)(t / pb.tiles_j);
-        return true;
-    };
-
-    if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        int stage = 0;
-        uint32_t phase = 0;
-        long long uc = 0;
-        const uint32_t full0_addr = mapa_shared(smem_u32(&bars->full[0]), 0);
-        const uint32_t idesc16 = make_idesc(FMT_F16, 256, 256);
-        const uint32_t idesc8 = make_idesc_ab(FMT8_E4M3, FMT8_E5M2, 256, 256);
-        // one tile's loads (producer) / MMAs (issuer); `core` = the phase's stage table
-        auto produce_tile = [&](const Maps &maps, const Core &core, int ngroups, int ka0, int kb0, int arow, int brow, int ti) {
-            for (int g = 0; g < ngroups; ++g) {
-#pragma unroll 1
-                for (int s = 0; s < core.n_stage; ++s) {
-                    const Stage st = core.table[s];
-                    mbar_wait(&bars->empty[stage], phase ^ 1, 2);
-                    if (elect_one_sync()) {
-                        if (leader) mbar_expect_tx(&bars->full[stage], 2u * STAGE_BYTES);
-                        uint8_t *dst = sRing + (size_t)stage * STAGE_BYTES;
-                        const uint32_t fa = full0_addr + 8u * (uint32_t)stage;
-                        const int kk = ka0 + g * 128 + st.koff;
-                        if (core.a_blocked) {
-                            const int rt = ti * 2 + (int)rank;
-                            const int orow = st.f8 ? (rt * core.a_nkb8 + (kk >> 7)) * 128 : (rt * core.a_nkb16 + (kk >> 6)) * 128;
-                            tma_load_2d_pair_hint(dst, &maps.a[st.a], fa, 0, orow, L2_EVICT_NORMAL);
-                        } else {
-                            tma_load_2d_pair_hint(dst, &maps.a[st.a], fa, kk, arow, L2_EVICT_NORMAL);
-                        }
-                        tma_load_2d_pair_hint(dst + BOX_BYTES, &maps.b[st.b], fa, kb0 + g * 128 + st.koff, brow, L2_EVICT_NORMAL);
-                    }
-                    __syncwarp();
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        };
-        auto mma_tile = [&](const Core &core, int units, int groups_per_unit) {
-            for (int u = 0; u < units; ++u, ++uc) {
-                const int b = (int)(uc & 1);
-                if (uc >= 2) {
-                    mbar_wait(&bars->acc_empty[b], (uint32_t)(((uc >> 1) - 1) & 1), 7);
-                    tcgen05_fence_after();
-                }
-                const uint32_t d_tmem = tmem + (uint32_t)b * 256u;
-                for (int g = 0; g < groups_per_unit; ++g) {
-#pragma unroll 1
-                    for (int s = 0; s < core.n_stage; ++s) {
-                        const int f8 = core.table[s].f8;
-                        mbar_wait(&bars->full[stage], phase, 4);
-                        tcgen05_fence_after();
-                        const uint32_t base = smem_u32(sRing + (size_t)stage * STAGE_BYTES);
-                        const uint64_t ad = make_kmajor_sw128_desc(base), bd = make_kmajor_sw128_desc(base + BOX_BYTES);
-                        const uint32_t first = (g | s) != 0;
-                        if (elect_one_sync()) {
-                            if (f8) {
-#pragma unroll
-                                for (int k4 = 0; k4 < 4; ++k4) umma2_f8_ss(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc8, (first | k4) != 0);
-                            } else {
-#pragma unroll
-                                for (int k4 = 0; k4 < 4; ++k4) umma2_f16_ss(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc16, (first | k4) != 0);
-                            }
-                            tcgen05_commit_pair(&bars->empty[stage]);
-                            if (g == groups_per_unit - 1 && s == core.n_stage - 1) tcgen05_commit_pair(&bars->acc_full[b]);
-                        }
-                        __syncwarp();
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                    }
-                }
-            }
-        };
-        for (int blk = 0; blk < fp.nblocks; ++blk) {
-            const int c0 = blk * fp.cb, c = min(fp.cb, fp.ctot - c0);
-            int ti, tj;
-            // ---- phase A
-            if (warp == 0) {
-                for (long long k = 0; tile_a(k, c, ti, tj); ++k)
-                    produce_tile(mapsA, pa, pa.groups_per_unit, 0, 0, pa.a_row0 + ti * 256 + (int)rank * 128,
-                                 pa.b_row0 + (c0 + tj) * 256 + (int)rank * 128, ti);
-            } else if (warp == 1 && leader) {
-                for (long long k = 0; tile_a(k, c, ti, tj); ++k) mma_tile(pa, 1, pa.groups_per_unit);
-            }
-            grid_barrier(fp.gbar, ++gen * nctas);
-            // ---- phase B
-            if (warp == 0) {
-                for (long long k = 0; tile_b(k, ti, tj); ++k)
-                    produce_tile(mapsB, pb, (c / 2) * pb.groups_per_unit, 0, pb.kb0 + c0 * 256, 0, tj * 256 + (int)rank * 128, ti);
-            } else if (warp == 1 && leader) {
-                for (long long k = 0; tile_b(k, ti, tj); ++k) mma_tile(pb, c / 2, pb.groups_per_unit);
-            }
-            grid_barrier(fp.gbar, ++gen * nctas);
-        }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-        const uint32_t acc_empty_addr0 = mapa_shared(smem_u32(&bars->acc_empty[0]), 0);
-        const uint32_t acc_empty_addr1 = mapa_shared(smem_u32(&bars->acc_empty[1]), 0);
-        long long uc = 0;
-        ExpPolicy::Epilogue ea(pa, tail, warp, lane, rank);
-        AccPolicy::Epilogue eb(pb, tail, warp, lane, rank);
-        auto release = [&](int b) {
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(b ? acc_empty_addr1 : acc_empty_addr0);
-        };
-        for (int blk = 0; blk < fp.nblocks; ++blk) {
-            const int c0 = blk * fp.cb, c = min(fp.cb, fp.ctot - c0);
-            int ti, tj;
-            ea.b_row0 = pa.b_row0 + c0 * 256;
-            for (long long k = 0; tile_a(k, c, ti, tj); ++k, ++uc) {
-                ea.tile_begin(ti, tj);
-                const int b = (int)(uc & 1);
-                mbar_wait(&bars->acc_full[b], (uint32_t)((uc >> 1) & 1), 8);
-                tcgen05_fence_after();
-                ea.unit(tmem + (uint32_t)b * 256u, 0, true);
-                release(b);
-            }
-            ea.finish();                                      // this CTA's P stores are complete ...
-            if (lane == 0) asm volatile("fence.proxy.async;" ::: "memory");
-            grid_barrier(fp.gbar, ++gen * nctas);             // ... and everybody's are visible
-            eb.first = blk == 0 ? pb.first : 0;
-            eb.ksp_n = c;
-            const int units = c / 2;
-            for (long long k = 0; tile_b(k, ti, tj); ++k) {
-                eb.tile_begin(ti, tj);
-                for (int u = 0; u < units; ++u, ++uc) {
-                    const int b = (int)(uc & 1);
-                    mbar_wait(&bars->acc_full[b], (uint32_t)((uc >> 1) & 1), 8);
-                    tcgen05_fence_after();
-                    eb.unit(tmem + (uint32_t)b * 256u, u, u == units - 1);
-                    release(b);
-                }
-            }
-            grid_barrier(fp.gbar, ++gen * nctas);             // P and the row sums of this block may be overwritten
-        }
-    }
-
-    tcgen05_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    if (warp == 1) {
-        tcgen05_fence_after();
-        tmem_dealloc_pair(tmem, pg::TMEM_COLS);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 struct PanelPlan {
@@ -567,59 +329,12 @@ static PanelPlan panel_plan(const stein_ctx *ctx, int64_t n_local, int64_t n_tot
     return pl;
 }
 
-static bool fused_enabled() {
-    const char *e = getenv("STEIN_PANEL_FUSED");
-    return !(e && e[0] == '0');
-}
-
-// Block shape of the fused kernel: everything a block touches must stay in L2 -- the P block, the panel's
-// O accumulator and X operands (4 bytes per entry each), the block's column operands of X and of Y^T.
-static PanelPlan fused_plan(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t ld) {
-    PanelPlan pl = panel_plan(ctx, n_local, n_total, ld);      // rows, cols, paddings
-    const int64_t R = pl.rowsP / 256, C = pl.colsP / 256, G = std::max(1, ctx->num_sms / 2), NS = ld / 256;
-    const double budget = 92.0 * 1048576.0, tbar = 5000.0;
-    const double tA = (double)(ld / 128) * 4 * 512, tile_bytes = 256.0 * ld * 4;
-    double best = 1e300;
-    pl.rp = 1;
-    pl.cc = 2;
-    for (int64_t rp = 1; rp <= R; ++rp) {
-        for (int64_t cb = 2; cb <= std::min<int64_t>(C, 64); cb += 2) {
-            const double bytes = rp * cb * 262144.0 + 2.0 * rp * tile_bytes + 2.0 * cb * tile_bytes;
-            if (bytes > budget && !(rp == 1 && cb == 2)) continue;
-            auto block_cost = [&](int64_t r, int64_t c) {
-                return (double)((r * c + G - 1) / G) * tA + (double)((r * NS + G - 1) / G) * (double)(c * 4096) + 2.0 * tbar;
-            };
-            const int64_t nr = R / rp, rr = R % rp, nc = C / cb, cr = C % cb;
-            double cost = (double)nr * nc * block_cost(rp, cb);
-            if (rr) cost += (double)nc * block_cost(rr, cb);
-            if (cr) cost += (double)nr * block_cost(rp, cr);
-            if (rr && cr) cost += block_cost(rr, cr);
-            cost += 20000.0 * (double)(nr + (rr ? 1 : 0));          // one launch per panel
-            if (cost < best) {
-                best = cost;
-                pl.rp = rp;
-                pl.cc = cb;
-            }
-        }
-    }
-    if (const char *e = getenv("STEIN_PANEL_RP")) pl.rp = std::max<int64_t>(1, std::min<int64_t>(R, atoll(e)));
-    if (const char *e = getenv("STEIN_PANEL_CC")) pl.cc = std::max<int64_t>(2, std::min<int64_t>(C, atoll(e) / 2 * 2));
-    return pl;
-}
-
 bool panel_supported(const stein_ctx *ctx, int64_t n_total, int64_t ld) {
     return (ld == 512 || ld == 768 || ld == 1024) && n_total >= 2 && ctx->num_sms >= 2 && n_total < (1ll << 30);
 }
 
 int64_t panel_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t ld) {
-    PanelPlan pl = panel_plan(ctx, n_local, n_total, ld);
-    {   // room for either form (the environment may switch between calls)
-        const PanelPlan pf = fused_plan(ctx, n_local, n_total, ld);
-        if (pf.rp * pf.cc > pl.rp * pl.cc) {
-            pl.rp = std::max(pl.rp, pf.rp);
-            pl.cc = std::max(pl.cc, pf.cc);
-        }
-    }
+    const PanelPlan pl = panel_plan(ctx, n_local, n_total, ld);
     int64_t b = 0;
     b += 5 * pl.cols * ld * 2;                                 // X16, XL, B8 (or Yx), YT16, YTL
     b += (pl.colsP + 256) * 4;                                 // nrm
@@ -629,7 +344,7 @@ int64_t panel_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t n_t
     b += pl.rp * 256 * pl.cc * 256 * 4;                        // one block of P
     b += pl.rp * 256 * pl.cc * 4;                              // its row sums per column tile
     b += FINALIZE_MAX_BLOCKS * 8;
-    b += 1024;                                                 // tensor maps of the epilogue's TMA stores, grid-barrier word
+    b += 1024;                                                 // tensor maps of the epilogue's TMA stores
     return b + 8192;
 }
 
@@ -656,8 +371,7 @@ int phi_panel(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
     STEIN_REQUIRE(ctx, panel_supported(ctx, n_total, ld), "panel phi needs a leading dimension of 512, 768 or 1024");
     STEIN_REQUIRE(ctx, ws_bytes >= panel_workspace_bytes(ctx, n_local, n_total, ld), "phi workspace too small");
     STEIN_REQUIRE(ctx, row_begin % TILE == 0, "row_begin must be a multiple of %d", TILE);
-    const bool fused = fused_enabled();
-    const PanelPlan pl = fused ? fused_plan(ctx, n_local, n_total, ld) : panel_plan(ctx, n_local, n_total, ld);
+    const PanelPlan pl = panel_plan(ctx, n_local, n_total, ld);
     const int64_t cols = pl.cols, rows = pl.rows;
     char *pws = (char *)ws;
     __half *X16 = (__half *)pws;        pws += cols * ld * 2;
@@ -683,7 +397,6 @@ int phi_panel(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
     double *partials = (double *)(((uintptr_t)pws + 7) & ~(uintptr_t)7);
     pws = (char *)partials + FINALIZE_MAX_BLOCKS * 8;
     PStoreMaps *d_smaps = (PStoreMaps *)(((uintptr_t)pws + 127) & ~(uintptr_t)127);
-    unsigned int *d_gbar = reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(d_smaps) + 512);
 
     xscale_kernel<<<1, 1024, 0, ctx->stream>>>(cen.blockmax, cen.nblockmax, xscale);
     STEIN_CHECK_LAUNCH(ctx);
@@ -785,75 +498,10 @@ int phi_panel(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
     const int G = std::max(1, ctx->num_sms / 2);
     const int64_t R = pl.rowsP / 256, C = pl.colsP / 256;
     if (getenv("STEIN_PANEL_VERBOSE"))
-        fprintf(stderr, "[stein] panel plan (%s): %lld x %lld tiles, blocks of %lld x %lld (%lld launches), P block %.1f MiB\n",
-                fused ? "fused" : "two kernels", (long long)R, (long long)C, (long long)pl.rp, (long long)pl.cc,
-                (long long)(fused ? (R + pl.rp - 1) / pl.rp : 2 * ((R + pl.rp - 1) / pl.rp) * ((C + pl.cc - 1) / pl.cc)),
-                pl.rp * pl.cc * 0.25);
-    if (fused) {
-        // one cooperative launch per row panel: phases A / B alternate over the column blocks inside the kernel
-        const size_t smemF = smem_bytes<KA::STAGES>(KA::TAIL_BYTES);
-        static bool attr_f = false;
-        if (!attr_f) {
-            STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(panel_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemF));
-            attr_f = true;
-        }
-        RegionTimer timer(ctx, STEIN_REGION_PHI);
-        for (int64_t r0 = 0; r0 < R; r0 += pl.rp) {
-            const int64_t r = std::min(pl.rp, R - r0);
-            FusedParams fp{};
-            KA::Params &pa = fp.pa;
-            fill_table(pa, precise);
-            pa.groups_per_unit = (int)(ld / 128);
-            pa.units_per_tile = 1;
-            pa.a_row0 = (int)(row_begin + r0 * 256);
-            pa.b_row0 = 0;
-            pa.tiles_i = (int)r;
-            pa.tiles_j = (int)pl.cc;
-            pa.nrm = nrm;
-            pa.c1 = l2e / h2;
-            pa.c1mul = xscale + 1;
-            pa.precise = precise ? 1 : 0;
-            pa.smaps = d_smaps;
-            pa.pcols = pcols;
-            pa.nkb16 = (int)nkb16;
-            pa.nkb8 = (int)nkb8;
-            pa.ksp = ksp;
-            pa.ksp_ld = (int)pl.cc;
-            KB::Params &pb = fp.pb;
-            fill_table(pb, precise);
-            pb.groups_per_unit = 4;
-            pb.a_blocked = 1;
-            pb.a_nkb16 = (int)nkb16;
-            pb.a_nkb8 = (int)nkb8;
-            pb.kb0 = 0;
-            pb.tiles_i = (int)r;
-            pb.tiles_j = (int)(ld / 256);
-            pb.O = O;
-            pb.ldo = ld;
-            pb.prow0 = r0 * 256;
-            pb.first = 1;
-            pb.ksp = ksp;
-            pb.ksp_ld = (int)pl.cc;
-            pb.ksum = ksum;
-            fp.cb = (int)pl.cc;
-            fp.ctot = (int)C;
-            fp.nblocks = (int)((C + pl.cc - 1) / pl.cc);
-            fp.gbar = d_gbar;
-            STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(d_gbar, 0, 4, ctx->stream));
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(2 * G);
-            cfg.blockDim = dim3(THREADS);
-            cfg.dynamicSmemBytes = smemF;
-            cfg.stream = ctx->stream;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeCooperative;
-            attr[0].val.cooperative = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            STEIN_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, panel_fused_kernel, mA, mB, fp));
-            ctx->launches++;
-        }
-    } else {
+        fprintf(stderr, "[stein] panel plan: %lld x %lld tiles, blocks of %lld x %lld (%lld launches), P block %.1f MiB\n",
+                (long long)R, (long long)C, (long long)pl.rp, (long long)pl.cc,
+                (long long)(2 * ((R + pl.rp - 1) / pl.rp) * ((C + pl.cc - 1) / pl.cc)), pl.rp * pl.cc * 0.25);
+    {
         RegionTimer timer(ctx, STEIN_REGION_PHI);
         for (int64_t r0 = 0; r0 < R; r0 += pl.rp) {
             const int64_t r = std::min(pl.rp, R - r0);
