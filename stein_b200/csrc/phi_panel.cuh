@@ -68,12 +68,13 @@ struct ExpPolicy {
     // per warp instruction and held this kernel at 47 % tensor-pipe activity: the epilogue, not the MMAs,
     // set the pace.)
     static constexpr int STAGES = 5;
-    static constexpr size_t STAGING_PER_WARP = 4096;
+    static constexpr size_t STAGING_PER_WARP = 6144;
     static constexpr size_t TAIL_STAGING = 3072;     // offset of the staging area in the tail (128-byte aligned)
     static constexpr size_t TAIL_BYTES = TAIL_STAGING + EPI_WARPS * STAGING_PER_WARP + 64;
     struct Params : Core {
         const PStoreMaps *smaps;     // device copy of the store maps (64-byte aligned)
         int tiles_i, tiles_j;        // tile grid of this launch (256-row x 256-column tiles)
+        int win_a, win_b;            // the clusters work on a window of win_a row tiles x win_b column tiles at a time
         const float *nrm;            // -r_j log2(e) / (2 h^2) by global particle index; -inf beyond n
         float c1;                    // log2(e) / h^2
         const float *c1mul;          // device: undoes the power-of-two scaling of X
@@ -87,19 +88,41 @@ struct ExpPolicy {
         float *ksp;                  // [panel rows][ksp_ld] row sums of P per column tile
         int ksp_ld;
     };
-    __device__ static bool tile(const Params &p, long long k, int cl, int ncl, int &ti, int &tj) {
-        const long long t = (long long)cl + k * ncl;
-        if (t >= (long long)p.tiles_i * p.tiles_j) return false;
-        ti = (int)(t % p.tiles_i);       // neighbouring clusters share the column tile (B operand) through L2
-        tj = (int)(t / p.tiles_i);
-        return true;
+    // Tile order.  The stream of P stores (0.5 GB per launch) pushes the operand lines out of L2 between two uses
+    // (measured: with the clusters on 37 row tiles x 2 column tiles per wave, every wave re-read its 39 MB of
+    // operands from DRAM -- 1 GB per launch, 57 % tensor-pipe activity against 96 % without the stores).  What
+    // DOES hit is a line that several clusters want at the same moment.  So a wave is a WINDOW of win_a row tiles
+    // x win_b column tiles (win_a * win_b <= clusters, win_a + win_b as small as possible: 9 x 8 on 74 clusters):
+    // each row tile is shared by win_b clusters, each column tile by win_a, and a wave brings win_a + win_b
+    // tiles of operands from DRAM instead of one per cluster.
+    __device__ static bool tile(const Params &p, long long k, int cl, int, int &ti, int &tj) {
+        const int a = p.win_a, b = p.win_b;
+        if (cl >= a * b) return false;
+        const int ci = cl % a, cj = cl / a;
+        const int nwi = (p.tiles_i + a - 1) / a, nwj = (p.tiles_j + b - 1) / b;
+        // the k-th window (column windows fastest) in which this cluster's cell exists
+        long long seen = -1;
+        for (int wi = 0; wi < nwi; ++wi) {
+            if (wi * a + ci >= p.tiles_i) break;
+            for (int wj = 0; wj < nwj; ++wj) {
+                if (wj * b + cj >= p.tiles_j) break;
+                if (++seen == k) {
+                    ti = wi * a + ci;
+                    tj = wj * b + cj;
+                    return true;
+                }
+            }
+        }
+        return false;
     }
     __device__ static void init_shared(uint8_t *, int) {}
 
     struct Epilogue {
         const Params &p;
         float *sB, *sK;
-        uint8_t *stg;                // this warp's staging: [P16 32 x 64 B | pl 32 x 32 B (64 B precise) | ph 32 x 32 B]
+        uint8_t *stg;                // this warp's staging: [P16 32 x 64 B | pl 32 x 64 B | ph 32 x 64 B]; the FP8 arrays
+                                     // collect TWO chunks per row before they leave: 64-byte pieces (32-byte ones cost
+                                     // 2.4 x more per byte -- partial DRAM write granules)
         int q, wg, row, lane, tid256;
         uint32_t lane_addr, rank;
         float c1, a_i, ksum;
@@ -173,7 +196,8 @@ struct ExpPolicy {
                     for (int k = 0; k < 4; ++k)
                         sl[k] = make_uint4(w[16 + 4 * k], w[17 + 4 * k], w[18 + 4 * k], w[19 + 4 * k]);
                 } else {
-                    uint4 *sl = reinterpret_cast<uint4 *>(stg + 2048 + lane * 32), *sh = reinterpret_cast<uint4 *>(stg + 3072 + lane * 32);
+                    uint4 *sl = reinterpret_cast<uint4 *>(stg + 2048 + lane * 64 + (ch & 1) * 32);
+                    uint4 *sh = reinterpret_cast<uint4 *>(stg + 4096 + lane * 64 + (ch & 1) * 32);
                     sl[0] = make_uint4(w[16], w[17], w[18], w[19]);
                     sl[1] = make_uint4(w[20], w[21], w[22], w[23]);
                     sh[0] = make_uint4(w[24], w[25], w[26], w[27]);
@@ -185,14 +209,14 @@ struct ExpPolicy {
                     // box-major destination: row tile rt, K block of the 32 columns, 32 rows from q * 32
                     const int rt = (int)((prow - lane) >> 7), r32 = (int)((prow - lane) & 127);
                     const int o16 = (rt * p.nkb16 + tj * 4 + (ch >> 1)) * 128 + r32, i16 = (ch & 1) * 32;
-                    const int o8 = (rt * p.nkb8 + tj * 2 + (ch >> 2)) * 128 + r32, i8 = (ch & 3) * 32;
+                    const int o8 = (rt * p.nkb8 + tj * 2 + (ch >> 2)) * 128 + r32, i8 = ((ch >> 1) & 1) * 64;
                     // the P block streams through L2 once on its way to kernel B: evict it before the operands
                     tma_store_2d_hint(&p.smaps->p16, stg, i16, o16, L2_EVICT_FIRST);
                     if (p.precise) {
                         tma_store_2d_hint(&p.smaps->pl, stg + 2048, i16, o16, L2_EVICT_FIRST);
-                    } else if (p.debug_skip != 4) {
+                    } else if ((ch & 1) && p.debug_skip != 4) {      // both halves of the 64-byte pieces are there
                         tma_store_2d_hint(&p.smaps->pl, stg + 2048, i8, o8, L2_EVICT_FIRST);
-                        tma_store_2d_hint(&p.smaps->ph, stg + 3072, i8, o8, L2_EVICT_FIRST);
+                        tma_store_2d_hint(&p.smaps->ph, stg + 4096, i8, o8, L2_EVICT_FIRST);
                     }
                     tma_store_commit();
                 }
@@ -293,9 +317,32 @@ struct PanelPlan {
     int64_t rp, cc;                            // row tiles per panel, column tiles per chunk (even)
 };
 
+// Window of kernel A's tile order for a block of r x c tiles on G clusters (see ExpPolicy::tile): returns the
+// cost in wave units -- waves times a penalty for the operand bytes a wave brings from DRAM, which grow with
+// win_a + win_b (measured: 37 x 2 runs 1.53 x slower than the MMAs alone would, 9 x 8 is the minimum).
+static double best_window(int64_t r, int64_t c, int64_t G, int *wa, int *wb) {
+    double best = 1e300;
+    for (int64_t a = 1; a <= G; ++a) {
+        const int64_t b = G / a;
+        if (b < 1) break;
+        const double waves = (double)(((r + a - 1) / a) * ((c + b - 1) / b));
+        const double pen = 1.0 + 0.53 * std::max<double>(0.0, (double)(a + b) - 17.0) / 22.0;
+        if (waves * pen < best) {
+            best = waves * pen;
+            if (wa) *wa = (int)a;
+            if (wb) *wb = (int)b;
+        }
+    }
+    return best;
+}
+
 // Cost model of the panel / chunk loop in units of (tile x 128 K elements) per cluster wave: picks the
 // block shape that wastes the fewest cluster slots to wave quantisation within the L2 budget.
 static PanelPlan panel_plan(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t ld) {
+    // the search below costs milliseconds: remember the last shape (an engine asks for the same one every iteration)
+    static int64_t c_key[4] = {-1, -1, -1, -1};
+    static PanelPlan c_plan;
+    if (c_key[0] == n_local && c_key[1] == n_total && c_key[2] == ld && c_key[3] == ctx->num_sms) return c_plan;
     PanelPlan pl;
     pl.rows = stein_rows_padded(n_local);
     pl.rowsP = round_up(pl.rows, 256);
@@ -305,7 +352,7 @@ static PanelPlan panel_plan(const stein_ctx *ctx, int64_t n_local, int64_t n_tot
     const int64_t R = pl.rowsP / 256, C = pl.colsP / 256, G = std::max(1, ctx->num_sms / 2), NS = ld / 256;
     // waves of one (row tiles r, column tiles c) block: kernel A then kernel B, plus launch overheads
     auto block_cost = [&](int64_t r, int64_t c) {
-        return (double)((r * c + G - 1) / G) * (double)(ld / 128) + (double)((r * NS + G - 1) / G) * (double)(c * 2) + 2.0;
+        return best_window(r, c, G, nullptr, nullptr) * (double)(ld / 128) + (double)((r * NS + G - 1) / G) * (double)(c * 2) + 2.0;
     };
     double best = 1e300;
     pl.rp = 1;
@@ -326,6 +373,11 @@ static PanelPlan panel_plan(const stein_ctx *ctx, int64_t n_local, int64_t n_tot
     }
     if (const char *e = getenv("STEIN_PANEL_RP")) pl.rp = std::max<int64_t>(1, std::min<int64_t>(R, atoll(e)));
     if (const char *e = getenv("STEIN_PANEL_CC")) pl.cc = std::max<int64_t>(2, std::min<int64_t>(C, atoll(e) / 2 * 2));
+    c_key[0] = n_local;
+    c_key[1] = n_total;
+    c_key[2] = ld;
+    c_key[3] = ctx->num_sms;
+    c_plan = pl;
     return pl;
 }
 
@@ -479,8 +531,8 @@ int phi_panel(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
             STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.pl, PL, 2, 64, (uint64_t)(prow_cap * nkb16), 128, 32, 32, false));
             hm.ph = hm.pl;
         } else {
-            STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.pl, PL, 1, 128, (uint64_t)(prow_cap * nkb8), 128, 32, 32, false));
-            STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.ph, PL + prow_cap * pcols, 1, 128, (uint64_t)(prow_cap * nkb8), 128, 32, 32,
+            STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.pl, PL, 1, 128, (uint64_t)(prow_cap * nkb8), 128, 64, 32, false));
+            STEIN_TRY(make_tensor_map_2d_box(ctx, &hm.ph, PL + prow_cap * pcols, 1, 128, (uint64_t)(prow_cap * nkb8), 128, 64, 32,
                                              false));
         }
         // pageable source: the runtime stages the bytes before returning
@@ -520,6 +572,8 @@ int phi_panel(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
                 if (const char *e = getenv("STEIN_PANEL_NOHINT")) pa.pol_a = pa.pol_b = atoi(e) ? L2_EVICT_NORMAL : pa.pol_a;
                 pa.tiles_i = (int)r;
                 pa.tiles_j = (int)c;
+                const int clustersA = (int)std::min<int64_t>(G, r * c);
+                best_window(r, c, clustersA, &pa.win_a, &pa.win_b);
                 pa.nrm = nrm;
                 pa.c1 = l2e / h2;
                 pa.c1mul = xscale + 1;
@@ -536,7 +590,7 @@ int phi_panel(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
                 pa.a_blocked = 0;
                 pa.ksp = ksp;
                 pa.ksp_ld = (int)pl.cc;
-                const int gridA = 2 * (int)std::min<int64_t>(G, r * c);
+                const int gridA = 2 * clustersA;
                 panel_gemm_kernel<KA><<<gridA, THREADS, smemA, ctx->stream>>>(mA, pa);
                 STEIN_CHECK_LAUNCH(ctx);
 
