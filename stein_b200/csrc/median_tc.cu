@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <functional>
+#include <vector>
 
 #include "pair_chain.cuh"
 #include "panel_gemm.cuh"
@@ -728,17 +729,25 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
 struct Sweep3Policy {
     static constexpr int STAGES = 6;
     static constexpr size_t TAIL_BYTES = SW_TAIL_BYTES;
+    // Tile order: the FP16 hi / lo arrays of 262 144 x 1 024 particles are 1 GB -- far beyond L2 -- so an
+    // operand tile only hits when several clusters want it at the same moment.  A wave is therefore a WINDOW of
+    // win_a row tiles x win_b column tiles of the upper triangle (9 x 8 on 74 clusters: 17 MB of operands from
+    // DRAM per wave instead of up to 148 MB with one private tile pair per cluster, which made the sweep
+    // HBM-bound at ~64 % of the tensor rate).  `wins` lists this rank's windows (host-built: those that
+    // touch the upper triangle, row-window major).
     struct Params : pg::Core {
         SweepParams sp;
         int T2;                       // 256-row tiles per side
-        long long t_begin, t_end;     // range of this launch in the row-major order of the upper triangle of T2 x T2
+        int win_a, win_b;
+        const int2 *wins;             // (row window, column window) of step k
+        int nwins;
     };
-    __device__ static bool tile(const Params &p, long long k, int cl, int ncl, int &ti, int &tj) {
-        const long long NT = p.t_end - p.t_begin;
-        const long long my0 = p.t_begin + NT * cl / ncl, my1 = p.t_begin + NT * (cl + 1) / ncl;
-        if (my0 + k >= my1) return false;
-        tri_tile(my0 + k, p.T2, ti, tj);
-        return true;
+    __device__ static int tile(const Params &p, long long k, int cl, int, int &ti, int &tj) {
+        if (k >= p.nwins || cl >= p.win_a * p.win_b) return 0;
+        const int2 w = p.wins[k];
+        ti = w.x * p.win_a + cl % p.win_a;
+        tj = w.y * p.win_b + cl / p.win_a;
+        return (ti < p.T2 && tj < p.T2 && tj >= ti) ? 1 : 2;
     }
     __device__ static void init_shared(uint8_t *tail, int tid) {
         unsigned int *sHist = reinterpret_cast<unsigned int *>(tail + SW_TAIL_HIST);
@@ -1580,7 +1589,21 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     const bool wide = DP > 64 * SW2_KB;                  // more than 256 coordinates: K-streaming sweep (Sweep3Policy)
     const bool pair = ctx->median_impl != STEIN_MEDIAN_TC1 && ctx->num_sms >= 2 && !wide;
     const int64_t T2 = (T + 1) / 2;
-    const int64_t ntiles = wide ? T2 * (T2 + 1) / 2 : (pair ? num_pair_tiles(T) : T * (T + 1) / 2);
+    // wide sweep: windows of 256 x 256 tiles over the upper triangle (Sweep3Policy); the ranks split the window list
+    std::vector<int2> wins;
+    int win_a = 1, win_b = 1;
+    if (wide) {
+        const int G = std::max(1, ctx->num_sms / 2);
+        win_a = std::max(1, (int)std::floor(std::sqrt((double)G)));
+        while (win_a > 1 && (G / win_a) * win_a < (G / (win_a + 1)) * (win_a + 1)) ++win_a;      // 74 clusters: 9 x 8
+        if ((G / (win_a + 1)) * (win_a + 1) > (G / win_a) * win_a) ++win_a;
+        win_b = std::max(1, G / win_a);
+        const int64_t nwi = (T2 + win_a - 1) / win_a, nwj = (T2 + win_b - 1) / win_b;
+        for (int64_t wi = 0; wi < nwi; ++wi)
+            for (int64_t wj = 0; wj < nwj; ++wj)
+                if ((wj + 1) * win_b - 1 >= wi * win_a) wins.push_back(make_int2((int)wi, (int)wj));   // touches tj >= ti
+    }
+    const int64_t ntiles = wide ? (int64_t)wins.size() : (pair ? num_pair_tiles(T) : T * (T + 1) / 2);
     const int64_t t0 = ntiles * rank / world, t1 = ntiles * (rank + 1) / world;
 
     // counters zeroed, largest row norm, scale, FP16 split: already there when the caller ran
@@ -1678,8 +1701,22 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
         sp.my_route = 0;
         sp.sp = p;
         sp.T2 = (int)T2;
-        sp.t_begin = t0;
-        sp.t_end = t1;
+        sp.win_a = win_a;
+        sp.win_b = win_b;
+        // this rank's windows, in a small library-owned device buffer (re-uploaded: a few KB, pageable source)
+        static int2 *d_wins = nullptr;
+        static size_t d_wins_cap = 0;
+        const size_t nw = (size_t)(t1 - t0);
+        if (nw > d_wins_cap) {
+            STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (d_wins) cudaFree(d_wins);
+            d_wins = nullptr;
+            STEIN_CHECK_CUDA(ctx, cudaMalloc(&d_wins, nw * sizeof(int2)));
+            d_wins_cap = nw;
+        }
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(d_wins, wins.data() + t0, nw * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+        sp.wins = d_wins;
+        sp.nwins = (int)nw;
         const size_t smem3 = pg::smem_bytes<Sweep3Policy::STAGES>(Sweep3Policy::TAIL_BYTES);
         static bool attr3 = false;
         if (!attr3) {
@@ -1687,7 +1724,7 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
             attr3 = true;
         }
-        const int clusters = (int)std::min<int64_t>(ctx->num_sms / 2, t1 - t0);
+        const int clusters = win_a * win_b;
         pg::panel_gemm_kernel<Sweep3Policy><<<2 * clusters, pg::THREADS, smem3, ctx->stream>>>(maps, sp);
         STEIN_CHECK_LAUNCH(ctx);
     } else if (t1 > t0) {

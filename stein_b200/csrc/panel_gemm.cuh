@@ -86,8 +86,9 @@ constexpr size_t smem_bytes(size_t tail) {
 // Policy interface:
 //   struct Params : Core { ... };
 //   static constexpr int STAGES; static constexpr size_t TAIL_BYTES;
-//   __device__ static bool tile(const Params &, long long k, int cluster, int nclusters, int &ti, int &tj);
-//        the k-th tile of this cluster (false: no more); A rows = a_row0 + 256 ti + 128 rank,
+//   __device__ static int tile(const Params &, long long k, int cluster, int nclusters, int &ti, int &tj);
+//        step k of this cluster: 0 = no more steps, 1 = tile (ti, tj), 2 = nothing to do at this step (the
+//        cluster's cell of the window lies outside the problem); A rows = a_row0 + 256 ti + 128 rank,
 //        B rows = b_row0 + 256 tj + 128 rank
 //   struct Epilogue { __device__ Epilogue(const Params &, uint8_t *tail, int warp, int lane, uint32_t rank);
 //        __device__ void tile_begin(int ti, int tj);
@@ -144,7 +145,8 @@ panel_gemm_kernel(const __grid_constant__ Maps maps, const typename Policy::Para
             const uint32_t full0_addr = mapa_shared(smem_u32(&bars->full[0]), 0);
             const uint64_t pol_a = p.pol_a ? p.pol_a : L2_EVICT_NORMAL, pol_b = p.pol_b ? p.pol_b : L2_EVICT_NORMAL;
             int ti, tj;
-            for (long long k = 0; Policy::tile(p, k, cl, ncl, ti, tj); ++k) {
+            for (long long k = 0, rc; (rc = Policy::tile(p, k, cl, ncl, ti, tj)) != 0; ++k) {
+                if (rc == 2) continue;
                 const int arow = p.a_row0 + ti * 256 + (int)rank * 128;
                 const int brow = p.b_row0 + tj * 256 + (int)rank * 128;
                 const int ngroups = p.units_per_tile * p.groups_per_unit;
@@ -181,7 +183,8 @@ panel_gemm_kernel(const __grid_constant__ Maps maps, const typename Policy::Para
             uint32_t phase = 0;
             long long uc = 0;      // accumulation units issued so far (TMEM buffer = uc & 1)
             int ti, tj;
-            for (long long k = 0; Policy::tile(p, k, cl, ncl, ti, tj); ++k) {
+            for (long long k = 0, rc; (rc = Policy::tile(p, k, cl, ncl, ti, tj)) != 0; ++k) {
+                if (rc == 2) continue;
                 for (int u = 0; u < p.units_per_tile; ++u, ++uc) {
                     const int b = (int)(uc & 1);
                     if (uc >= 2) {
@@ -226,7 +229,8 @@ panel_gemm_kernel(const __grid_constant__ Maps maps, const typename Policy::Para
         const uint32_t acc_empty_addr1 = mapa_shared(smem_u32(&bars->acc_empty[1]), 0);
         long long uc = 0;
         int ti, tj;
-        for (long long k = 0; Policy::tile(p, k, cl, ncl, ti, tj); ++k) {
+        for (long long k = 0, rc; (rc = Policy::tile(p, k, cl, ncl, ti, tj)) != 0; ++k) {
+                if (rc == 2) continue;
             epi.tile_begin(ti, tj);
             for (int u = 0; u < p.units_per_tile; ++u, ++uc) {
                 const int b = (int)(uc & 1);

@@ -95,25 +95,13 @@ struct ExpPolicy {
     // x win_b column tiles (win_a * win_b <= clusters, win_a + win_b as small as possible: 9 x 8 on 74 clusters):
     // each row tile is shared by win_b clusters, each column tile by win_a, and a wave brings win_a + win_b
     // tiles of operands from DRAM instead of one per cluster.
-    __device__ static bool tile(const Params &p, long long k, int cl, int, int &ti, int &tj) {
+    __device__ static int tile(const Params &p, long long k, int cl, int, int &ti, int &tj) {
         const int a = p.win_a, b = p.win_b;
-        if (cl >= a * b) return false;
-        const int ci = cl % a, cj = cl / a;
         const int nwi = (p.tiles_i + a - 1) / a, nwj = (p.tiles_j + b - 1) / b;
-        // the k-th window (column windows fastest) in which this cluster's cell exists
-        long long seen = -1;
-        for (int wi = 0; wi < nwi; ++wi) {
-            if (wi * a + ci >= p.tiles_i) break;
-            for (int wj = 0; wj < nwj; ++wj) {
-                if (wj * b + cj >= p.tiles_j) break;
-                if (++seen == k) {
-                    ti = wi * a + ci;
-                    tj = wj * b + cj;
-                    return true;
-                }
-            }
-        }
-        return false;
+        if (cl >= a * b || k >= (long long)nwi * nwj) return 0;
+        ti = (int)(k / nwj) * a + cl % a;          // column windows fastest: the row tiles of a window stay
+        tj = (int)(k % nwj) * b + cl / a;
+        return (ti < p.tiles_i && tj < p.tiles_j) ? 1 : 2;
     }
     __device__ static void init_shared(uint8_t *, int) {}
 
@@ -248,12 +236,12 @@ struct AccPolicy {
         int ksp_ld, ksp_n;
         float *ksum;                 // [local rows]
     };
-    __device__ static bool tile(const Params &p, long long k, int cl, int ncl, int &ti, int &tj) {
+    __device__ static int tile(const Params &p, long long k, int cl, int ncl, int &ti, int &tj) {
         const long long t = (long long)cl + k * ncl;
-        if (t >= (long long)p.tiles_i * p.tiles_j) return false;
+        if (t >= (long long)p.tiles_i * p.tiles_j) return 0;
         tj = (int)(t % p.tiles_j);       // the slices of one row tile run side by side: its P rows come from L2 once
         ti = (int)(t / p.tiles_j);
-        return true;
+        return 1;
     }
     __device__ static void init_shared(uint8_t *, int) {}
 
