@@ -79,7 +79,7 @@ struct SweepParams {
     // derived in the kernel from the window and rmax (a device value)
     unsigned long long *hist;     // [SW_HIST_BINS] weighted counts of the listed D~ (accumulated)
     unsigned long long *cnt_below, *cnt_listed, *cnt_len;   // weighted below / listed counts, list length
-    float *hparams_out;           // [2]: the (hlo, hscale) actually used, for the host
+    const float *hparams_out;     // [2]: (hlo, hscale), written by hparams_kernel before the sweep
     int *overflow;
     PairEntry *list;
     unsigned long long list_cap;
@@ -168,14 +168,10 @@ struct TileClassifier {
         // exact, s is a power of two
         s2 = __ldg(p.scale + 1);
         inv_s2 = __ldg(p.scale + 2);
-        // histogram range of the listed D~: the window widened by the largest possible error term
-        const float hpad = 4.0f * emax + 1e-5f * fmaxf(fabsf(wlo), fabsf(whi));
-        hlo = wlo - hpad;
-        hscale = (float)SW_HIST_BINS / fmaxf((whi + hpad) - hlo, 1e-30f);
-        if (blockIdx.x == 0 && ew == 0 && lane == 0) {
-            p.hparams_out[0] = hlo;
-            p.hparams_out[1] = hscale;
-        }
+        // histogram range of the listed D~: the window widened by the largest possible error term -- computed once
+        // per rank by hparams_kernel (one source for the sweep, pick_band_kernel and the host)
+        hlo = __ldg(p.hparams_out);
+        hscale = __ldg(p.hparams_out + 1);
         if (lane == 0) *wCount = 0u;
         __syncwarp();
     }
@@ -781,6 +777,22 @@ struct Sweep3Policy {
 };
 
 // ---- helpers ---------------------------------------------------------------------------
+// Histogram range of the listed D~ (the TileClassifier's formula, same arithmetic), written by EVERY rank before
+// its sweep: a rank whose share of the tiles is empty launches no sweep kernel, yet its pick_band_kernel needs
+// the same (hlo, hscale) as everybody else's -- rank-dependent band parameters end in ranks that disagree about
+// the number of all-reduces that follow.
+__global__ void hparams_kernel(const float *__restrict__ window, float wlo, float whi, const float *__restrict__ emax,
+                               float *__restrict__ hparams_out) {
+    if (window) {
+        wlo = window[0];
+        whi = window[1];
+    }
+    const float hpad = 4.0f * emax[0] + 1e-5f * fmaxf(fabsf(wlo), fabsf(whi));
+    const float hlo = wlo - hpad;
+    hparams_out[0] = hlo;
+    hparams_out[1] = (float)SW_HIST_BINS / fmaxf((whi + hpad) - hlo, 1e-30f);
+}
+
 // hi = fp16(s x), lo = fp16(s x - hi): 22 bits of s x (entries far below the largest one end in
 // the FP16 subnormals; that absolute error is covered by the slack terms, see err_budget_kernel / EPS_ABS)
 __global__ void split_f16_kernel(const float *__restrict__ X, int64_t count4, const float *__restrict__ scale,
@@ -1676,6 +1688,8 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
                                                    (int)smem2));
         attr_set = true;
     }
+    hparams_kernel<<<1, 1, 0, ctx->stream>>>(p.window, p.wlo, p.whi, p.emax, reinterpret_cast<float *>(A.counters + CNT_HPARAMS));
+    STEIN_CHECK_LAUNCH(ctx);
     if (t1 > t0 && wide) {
         RegionTimer timer(ctx, STEIN_REGION_SWEEP);
         pg::Maps maps;
