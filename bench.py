@@ -296,6 +296,19 @@ def run_ours(args):
 
     phi_ms, phi_n = region(0)
     sw_ms, sw_n = region(1)
+    # per-phase timeline: a second pass of the same K steps with every region timed (28 more event records per
+    # iteration -- kept out of the pass that `value` comes from)
+    ctx.check(ctx.lib.stein_ctx_profile_enable(ctx.handle, 2))
+    barrier()
+    tl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in tl:
+        flush.zero_()
+        a.record()
+        one_step()
+        b.record()
+    barrier()
+    tl_ms_per_step = sum(a.elapsed_time(b) for a, b in tl) / args.steps
+    tl_phi, tl_sweep = region(0)[0].value / args.steps, region(1)[0].value / args.steps
     regions = {name: region(k)[0].value / args.steps for k, name in
                [(2, "median"), (3, "phi_prep"), (4, "phi_tail"), (5, "step_push"), (6, "collectives"), (7, "head")]}
     ctx.check(ctx.lib.stein_ctx_profile_enable(ctx.handle, 0))
@@ -408,14 +421,15 @@ def run_ours(args):
                 "call": "stein_engine_update_particles_host (pinned fp32 scores H2D -> iteration -> "
                         "particles D2H), max over ranks of wall time"},
         "bandwidth_last_step": info["bandwidth"],
-        # device time per iteration by phase (CUDA events on the ctx stream, rank 0): head = barrier /
+        # device time per iteration by phase (CUDA events on the ctx stream, rank 0; a SEPARATE pass of K steps with
+        # all regions timed, `step_total_in_this_pass` per iteration): head = barrier /
         # all-gather of the particles + row norms; median = the whole median call including its host round
         # trip (the sweep is part of it); phi_prep = centring, guard, operand arrays; phi = main kernel;
         # phi_tail = finalize + sum(phi^2); step_push = clip + optimizer (+ peer push); collectives = the
         # all-reduce kernels (already contained in median / phi_tail / head); idle = the rest of the step
-        "phases_ms": dict(regions, phi=phi_ms.value / args.steps, sweep=sw_ms.value / args.steps,
-                          idle=ms_per_step - (regions["head"] + regions["median"] + regions["phi_prep"] +
-                                              phi_ms.value / args.steps + regions["phi_tail"] + regions["step_push"])),
+        "phases_ms": dict(regions, phi=tl_phi, sweep=tl_sweep, step_total_in_this_pass=tl_ms_per_step,
+                          idle=tl_ms_per_step - (regions["head"] + regions["median"] + regions["phi_prep"] +
+                                                 tl_phi + regions["phi_tail"] + regions["step_push"])),
         "cold": {"first_iteration_ms": cold_first_ms, "hint_miss_step_ms": hint_miss_ms,
                  "hint_miss_sweeps": hint_miss_sweeps,
                  "note": "not part of `value`: the timed steps ride the previous iteration's median window "
@@ -462,7 +476,7 @@ def run_config_e(args, ctx, world, rank, dev, barrier):
 
         step()                                  # cold: host-driven median, allocations
         barrier()
-        ctx.check(ctx.lib.stein_ctx_profile_enable(ctx.handle, 1))
+        ctx.check(ctx.lib.stein_ctx_profile_enable(ctx.handle, 2))
         for k in range(8):
             ctx.lib.stein_ctx_profile_read(ctx.handle, k, None, None)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -131,6 +131,8 @@ int stein_ctx_set_phi_guard_tol(stein_ctx *ctx, float tol);
 #define STEIN_REGION_COLL 6       /* collectives of the iteration (all-reduces, barrier word, all-gathers on the ctx stream) */
 #define STEIN_REGION_HEAD 7       /* start of the iteration: barrier / all-gather of the particles, row norms */
 #define STEIN_REGION_COUNT 8
+/* enable: 0 off; 1 = regions PHI and SWEEP only (two event pairs per iteration: what bench.py keeps on inside
+ * its timed region); 2 = all regions (the per-phase timeline, measured in a separate pass) */
 int stein_ctx_profile_enable(stein_ctx *ctx, int enable);
 int stein_ctx_profile_read(stein_ctx *ctx, int region, double *ms_total, int64_t *launches);
 

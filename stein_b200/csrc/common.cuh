@@ -72,7 +72,7 @@ struct stein_ctx {
     uint32_t *h_sel = nullptr;      // pinned
     int64_t pilot_cap = 0;
     // optional region timing (bench.py): event pairs recorded on `stream`
-    bool profile = false;
+    int profile = 0;                // 0 off, 1 = regions PHI / SWEEP only, 2 = all regions (timeline)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[STEIN_REGION_COUNT];
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;
 };
@@ -121,7 +121,7 @@ struct RegionTimer {
     int region;
     std::pair<cudaEvent_t, cudaEvent_t> ev{};
     bool on;
-    RegionTimer(stein_ctx *c, int r) : ctx(c), region(r), on(c->profile) {
+    RegionTimer(stein_ctx *c, int r) : ctx(c), region(r), on(c->profile >= (r <= STEIN_REGION_SWEEP ? 1 : 2)) {
         if (!on) return;
         if (!ctx->prof_pool.empty()) {
             ev = ctx->prof_pool.back();

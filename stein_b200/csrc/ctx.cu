@@ -139,7 +139,7 @@ const char *stein_last_error(const stein_ctx *ctx) {
 
 int stein_ctx_profile_enable(stein_ctx *ctx, int enable) {
     STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
-    ctx->profile = enable != 0;
+    ctx->profile = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
     return STEIN_OK;
 }
 
