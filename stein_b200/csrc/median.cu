@@ -300,8 +300,11 @@ struct PilotSpec {
     const uint32_t *keys_dev;
     unsigned long long m_local;
     unsigned long long rank_lo, rank_hi;
+    int direct;
 };
 bool median_tc_has_hint(const stein_ctx *ctx);
+bool median_tc_direct_ok(const stein_ctx *ctx);
+void median_tc_note_result(const stein_ctx *ctx, uint32_t k0, uint32_t k1, bool direct_missed);
 int median_tc_begin(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t ld);
 void median_tc_reset(void);
 int median_tc_pilot(stein_ctx *ctx, uint32_t *keys_dev, unsigned long long m, const float *r, int64_t n, int64_t ld,
@@ -476,6 +479,7 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
     bool done[2] = {false, false};
     uint32_t key[2] = {0u, 0u};
     int sweeps = 0;
+    bool direct_missed = false;
     if (pilot_m) {
         // sample ranks m/2 -+ 3.5 sqrt(m): the true median lies between them with
         // probability ~1 - 1e-11; a miss is caught below and falls back to the
@@ -486,21 +490,32 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
         const int64_t s0 = pilot_m * pr / pw, s1 = pilot_m * (pr + 1) / pw;
         const bool tc_ok = ctx->median_impl != STEIN_MEDIAN_FFMA && median_tc_supported(n, ld);
         median_tc_reset();
-        if (tc_ok) {
-            // the tensor-core route splits s X into FP16 hi + lo anyway: the pilot only has to
-            // PLACE the window (every use of it is checked), so it reads the hi half alone
-            STEIN_TRY(median_tc_begin(ctx, X_dev, r_dev, n, ld));
-            STEIN_TRY(median_tc_pilot(ctx, ctx->d_pilot_keys + s0, (unsigned long long)(s1 - s0), r_dev, n, ld,
-                                      0x5eedull + (uint64_t)s0));
-        } else {
-            STEIN_TRY(launch_pair_chain<1>(ctx, ctx->d_pilot_keys + s0, (unsigned long long)(s1 - s0), X_dev, r_dev, n,
-                                           ld, 0x5eedull + (uint64_t)s0));
-        }
         const uint64_t delta = (uint64_t)(3.5 * sqrt((double)pilot_m));
-        // steady state: pilot histogram, window pick and sweep chained on the device
-        if (tc_ok && median_tc_has_hint(ctx)) {
+        auto run_pilot = [&]() -> int {
+            if (tc_ok) {
+                // the tensor-core route splits s X into FP16 hi + lo anyway: the pilot only has to
+                // PLACE the window (every use of it is checked), so it reads the hi half alone
+                return median_tc_pilot(ctx, ctx->d_pilot_keys + s0, (unsigned long long)(s1 - s0), r_dev, n, ld,
+                                       0x5eedull + (uint64_t)s0);
+            }
+            return launch_pair_chain<1>(ctx, ctx->d_pilot_keys + s0, (unsigned long long)(s1 - s0), X_dev, r_dev, n, ld,
+                                        0x5eedull + (uint64_t)s0);
+        };
+        if (tc_ok) STEIN_TRY(median_tc_begin(ctx, X_dev, r_dev, n, ld));
+        // steady state of an engine: no pilot at all while the median drifts slowly (median_tc_direct_ok)
+        if (tc_ok && median_tc_direct_ok(ctx)) {
+            const PilotSpec spec = {nullptr, 0ull, 0ull, 0ull, 1};
+            const int rc = median_tc(ctx, X_dev, r_dev, n, d, ld, ranks, 0u, 0u, key, &sweeps, &spec);
+            if (rc < 0) return rc;
+            if (rc == STEIN_OK) done[0] = done[1] = true;
+            else direct_missed = true;
+        }
+        if (!(done[0] && done[1])) STEIN_TRY(run_pilot());
+        // steady state with a pilot: pilot histogram, window pick and sweep chained on the device (not after a
+        // pilot-less miss: the median jumped, the host-driven route below places the window from scratch)
+        if (!(done[0] && done[1]) && !direct_missed && tc_ok && median_tc_has_hint(ctx)) {
             const PilotSpec spec = {ctx->d_pilot_keys + s0, (unsigned long long)(s1 - s0), pilot_m / 2 - delta,
-                                    pilot_m / 2 + delta};
+                                    pilot_m / 2 + delta, 0};
             const int rc = median_tc(ctx, X_dev, r_dev, n, d, ld, ranks, 0u, 0u, key, &sweeps, &spec);
             if (rc < 0) return rc;
             if (rc == STEIN_OK) done[0] = done[1] = true;
@@ -582,6 +597,8 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
         }
     }
     if (!(done[0] && done[1])) return fail(ctx, STEIN_ERR_INTERNAL, "median select did not converge");
+    if (pilot_m && ctx->median_impl != STEIN_MEDIAN_FFMA && median_tc_supported(n, ld))
+        median_tc_note_result(ctx, key[0], key[1], direct_missed);
     const float lo = key_to_float(key[0]), hi = key_to_float(key[1]);
     // compute_median.py:13 -- tf.reduce_mean of two fp32 values
     *median_host = (dim % 2 == 0) ? (lo + hi) / 2.0f : lo;

@@ -69,6 +69,7 @@ struct SweepParams {
     const float *r;
     const uint32_t *Xh, *Xl;      // FP16 split of s X viewed as 32-bit words (DP / 2 per row)
     float wlo, whi;
+    int direct_window;            // host-side note: the window was not derived from a pilot (median_tc_direct_ok)
     const float *e;               // per-row error budget e_i: |D~_ij - D_ij| <= e_i + e_j (err_budget_kernel)
     const float *emax;            // device: max_i e_i
     const float *window;          // device [wlo, whi] replacing the two fields above when non-NULL (set by
@@ -1220,6 +1221,8 @@ struct PilotSpec {
     const uint32_t *keys_dev;       // this rank's slice of the pilot keys
     unsigned long long m_local;
     unsigned long long rank_lo, rank_hi;   // ranks in the WHOLE sample that bracket the median
+    int direct;                     // 1: no pilot at all -- the window is the previous iteration's, recentred on its
+                                    // exact median (median_tc_direct_ok); keys_dev / m_local / rank_* unused
 };
 
 struct MedianArena {
@@ -1236,9 +1239,14 @@ struct MedianArena {
     // centre of the last pilot window (keys): successive iterations move the median only slightly
     uint32_t last_center = 0u;
     bool have_last = false;
+    // pilot-less steady state: half-width (keys) of the last pilot-derived window, the exact median key of the
+    // last two iterations, and how many iterations to stay on the pilot after a miss
+    uint32_t last_half = 0u, med_key = 0u, prev_med_key = 0u;
+    int med_keys_known = 0, direct_cooldown = 0;
     const void *hint_owner = nullptr;     // the engine (stein_ctx::median_owner) the hint belongs to
     cudaEvent_t ev_tail = nullptr;        // marks the D2H copies of the device-driven tail
     bool fresh = false;                   // median_tc_begin ran and no sweep has used its counters yet
+    bool split_valid = false;             // Xh / Xl / scale / budget belong to the particles of the current call
 };
 
 // counters block (u64 slots).  Slots [0, CNT_G1_END) are global quantities after the sweep (one
@@ -1453,6 +1461,42 @@ bool median_tc_supported(int64_t n, int64_t ld) {
 // returns STEIN_OK with keys filled, 1 = "not bracketed, use the FFMA route", <0 = error
 bool median_tc_has_hint(const stein_ctx *ctx) { return hint_usable(ctx); }
 
+// Successive SVGD iterations move the median by a small fraction of the pilot window (which is +-3.5 sigma of
+// a 2^20-pair sample quantile wide).  While the last step moved it by less than an eighth of the window's
+// half-width, the next window is simply the last one recentred on the last EXACT median: no pilot sample, no
+// pilot histogram, no all-reduce of it.  Every consumer of the window still checks that the rank is bracketed;
+// a miss falls back to the pilot route and keeps it for a few iterations.
+bool median_tc_direct_ok(const stein_ctx *ctx) {
+    const MedianArena &A = g_arena;
+    if (!hint_usable(ctx) || A.med_keys_known < 2 || A.last_half == 0u || A.direct_cooldown > 0) return false;
+    if (const char *e = getenv("STEIN_MEDIAN_PILOTLESS"))
+        if (e[0] == '0') return false;
+    const uint32_t drift = A.med_key > A.prev_med_key ? A.med_key - A.prev_med_key : A.prev_med_key - A.med_key;
+    return (uint64_t)drift * 8u < A.last_half;
+}
+// bookkeeping after a median call of an engine sequence (keys of the two middle values)
+void median_tc_note_result(const stein_ctx *ctx, uint32_t k0, uint32_t k1, bool direct_missed) {
+    MedianArena &A = g_arena;
+    if (ctx->median_owner == nullptr || A.hint_owner != ctx->median_owner) {
+        A.med_keys_known = 0;
+        return;
+    }
+    A.prev_med_key = A.med_key;
+    A.med_key = (uint32_t)(((uint64_t)k0 + k1) / 2);
+    A.med_keys_known = std::min(A.med_keys_known + 1, 2);
+    if (direct_missed) A.direct_cooldown = 8;
+    else if (A.direct_cooldown > 0) --A.direct_cooldown;
+}
+
+// window word block for the sweep: [wlo, whi] floats, [klo, khi] keys, ok flag
+__global__ void set_window_kernel(uint32_t klo, uint32_t khi, uint32_t *__restrict__ out) {
+    out[0] = __float_as_uint(key_to_float(klo));
+    out[1] = __float_as_uint(key_to_float(khi));
+    out[2] = klo;
+    out[3] = khi;
+    out[4] = 1u;
+}
+
 // Steady-state tail of the tensor-core route (spec != NULL in median_tc): everything after the
 // sweep is chained on the device -- band thresholds (pick_band_kernel), band filter, exact
 // distances, histogram of the exact keys over a device-picked window -- and the host reads the
@@ -1513,6 +1557,7 @@ static int median_tc_device_tail(stein_ctx *ctx, const float *X, const float *r,
     memcpy(&p->wlo, &wv[0], 4);
     memcpy(&p->whi, &wv[1], 4);
     A.last_center = (uint32_t)(((uint64_t)wv[2] + wv[3]) / 2);
+    if (!p->direct_window) A.last_half = (wv[3] - wv[2]) / 2u + 1u;
     const uint32_t *hbp = reinterpret_cast<const uint32_t *>(h + CNT_BANDP);
     // global (below2, band weight, overflow2): all-reduced at the tail of the histogram on sharded runs
     const unsigned long long *g3 = world > 1 ? A.h_pinned + HIST_MAX_BINS + 1 : h + CNT_BELOW2;
@@ -1566,15 +1611,19 @@ int median_tc_begin(stein_ctx *ctx, const float *X, const float *r, int64_t n, i
     split_f16_kernel<<<(unsigned)((count4 + 255) / 256), 256, 0, ctx->stream>>>(X, count4, d_scale, A.Xh, A.Xl);
     STEIN_CHECK_LAUNCH(ctx);
     A.fresh = true;
+    A.split_valid = true;
     return STEIN_OK;
 }
-void median_tc_reset(void) { g_arena.fresh = false; }
+void median_tc_reset(void) {
+    g_arena.fresh = false;
+    g_arena.split_valid = false;
+}
 
 // Pilot keys of samples [s0, s0 + m) from the FP16 hi array (needs median_tc_begin on this X).
 int median_tc_pilot(stein_ctx *ctx, uint32_t *keys_dev, unsigned long long m, const float *r, int64_t n, int64_t ld,
                     uint64_t seed) {
     MedianArena &A = g_arena;
-    if (!A.fresh) return fail(ctx, STEIN_ERR_INTERNAL, "median_tc_pilot without median_tc_begin");
+    if (!A.split_valid) return fail(ctx, STEIN_ERR_INTERNAL, "median_tc_pilot without median_tc_begin");
     if (m == 0) return STEIN_OK;
     const unsigned long long ngroups = (m + 31ull) / 32ull;
     const unsigned grid = (unsigned)std::min<unsigned long long>((ngroups + 7) / 8, 8ull * ctx->num_sms);
@@ -1627,7 +1676,13 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     int *d_overflow = reinterpret_cast<int *>(A.counters + CNT_OVERFLOW);
     int *d_overflow2 = reinterpret_cast<int *>(A.counters + CNT_OVERFLOW2);
 
-    if (spec) {
+    if (spec && spec->direct) {
+        // pilot-less: the last window, recentred on the last exact median
+        const uint32_t c = A.med_key, half = A.last_half;
+        set_window_kernel<<<1, 1, 0, ctx->stream>>>(c > half ? c - half : 0u, c < 0xffffffffu - half ? c + half : 0xffffffffu,
+                                                   reinterpret_cast<uint32_t *>(A.counters + CNT_WINDOW));
+        STEIN_CHECK_LAUNCH(ctx);
+    } else if (spec) {
         // one histogram pass over +-2^20 keys around the last window, then the device picks the bins
         const uint32_t c = A.last_center, half = 1u << 20;
         const KeyWindow w = window_over(c > half ? c - half : 0u, c < 0xffffffffu - half ? c + half : 0xffffffffu);
@@ -1665,6 +1720,7 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     p.wlo = key_to_float(win_lo_key);
     p.whi = key_to_float(win_hi_key);
     p.window = spec ? reinterpret_cast<const float *>(A.counters + CNT_WINDOW) : nullptr;
+    p.direct_window = (spec && spec->direct) ? 1 : 0;
     p.e = A.e;
     p.emax = reinterpret_cast<const float *>(A.counters + CNT_EMAX);
     p.rmax = d_rmax;
