@@ -304,6 +304,7 @@ struct PilotSpec {
 };
 bool median_tc_has_hint(const stein_ctx *ctx);
 bool median_tc_direct_ok(const stein_ctx *ctx);
+void median_tc_count_direct_hit(void);
 void median_tc_note_result(const stein_ctx *ctx, uint32_t k0, uint32_t k1, bool direct_missed);
 int median_tc_begin(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t ld);
 void median_tc_reset(void);
@@ -507,8 +508,12 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
             const PilotSpec spec = {nullptr, 0ull, 0ull, 0ull, 1};
             const int rc = median_tc(ctx, X_dev, r_dev, n, d, ld, ranks, 0u, 0u, key, &sweeps, &spec);
             if (rc < 0) return rc;
-            if (rc == STEIN_OK) done[0] = done[1] = true;
-            else direct_missed = true;
+            if (rc == STEIN_OK) {
+                done[0] = done[1] = true;
+                median_tc_count_direct_hit();
+            } else {
+                direct_missed = true;
+            }
         }
         if (!(done[0] && done[1])) STEIN_TRY(run_pilot());
         // steady state with a pilot: pilot histogram, window pick and sweep chained on the device (not after a

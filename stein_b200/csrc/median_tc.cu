@@ -1243,6 +1243,7 @@ struct MedianArena {
     // last two iterations, and how many iterations to stay on the pilot after a miss
     uint32_t last_half = 0u, med_key = 0u, prev_med_key = 0u;
     int med_keys_known = 0, direct_cooldown = 0;
+    long long direct_hits = 0, direct_misses = 0;      // statistics (stein_debug_median_direct_stats)
     const void *hint_owner = nullptr;     // the engine (stein_ctx::median_owner) the hint belongs to
     cudaEvent_t ev_tail = nullptr;        // marks the D2H copies of the device-driven tail
     bool fresh = false;                   // median_tc_begin ran and no sweep has used its counters yet
@@ -1474,6 +1475,7 @@ bool median_tc_direct_ok(const stein_ctx *ctx) {
     const uint32_t drift = A.med_key > A.prev_med_key ? A.med_key - A.prev_med_key : A.prev_med_key - A.med_key;
     return (uint64_t)drift * 8u < A.last_half;
 }
+void median_tc_count_direct_hit(void) { ++g_arena.direct_hits; }
 // bookkeeping after a median call of an engine sequence (keys of the two middle values)
 void median_tc_note_result(const stein_ctx *ctx, uint32_t k0, uint32_t k1, bool direct_missed) {
     MedianArena &A = g_arena;
@@ -1484,8 +1486,12 @@ void median_tc_note_result(const stein_ctx *ctx, uint32_t k0, uint32_t k1, bool 
     A.prev_med_key = A.med_key;
     A.med_key = (uint32_t)(((uint64_t)k0 + k1) / 2);
     A.med_keys_known = std::min(A.med_keys_known + 1, 2);
-    if (direct_missed) A.direct_cooldown = 8;
-    else if (A.direct_cooldown > 0) --A.direct_cooldown;
+    if (direct_missed) {
+        A.direct_cooldown = 8;
+        ++A.direct_misses;
+    } else if (A.direct_cooldown > 0) {
+        --A.direct_cooldown;
+    }
 }
 
 // window word block for the sweep: [wlo, whi] floats, [klo, khi] keys, ok flag
@@ -1891,6 +1897,11 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
 
 }  // namespace stein
 
+// Test hook: how many median calls of engine sequences ran pilot-less (hits) / tried and fell back (misses).
+extern "C" void stein_debug_median_direct_stats(long long *hits, long long *misses) {
+    if (hits) *hits = stein::g_arena.direct_hits;
+    if (misses) *misses = stein::g_arena.direct_misses;
+}
 // Test hooks (pure host functions): enumeration of the CTA-pair sweep's tiles.
 extern "C" long long stein_debug_num_pair_tiles(long long T) { return stein::num_pair_tiles(T); }
 extern "C" void stein_debug_pair_tile(long long t, int T, int *I2, int *J) { stein::pair_tile(t, T, *I2, *J); }

@@ -1371,3 +1371,35 @@ def test_graph_recognition_dispatches_to_the_score_kernels(ctx, kind):
     scale2 = S2_auto.abs().amax(dim=0).clamp_min(1e-30)
     # (the logistic / bnn graphs bake n_batch in: a batch of another size goes back to autograd -- exact either way)
     assert float(((S2 - S2_auto.to(torch.float32)).abs() / scale2).amax()) <= 2e-5
+
+
+def test_median_pilotless_steady_state_is_bit_exact(ctx):
+    """While the median drifts slowly (tiny steps) an engine's iterations skip the pilot sample and reuse the
+    last window, recentred on the last exact median; the result is still the oracle's, bit for bit, and a
+    jump of the particles falls back to the pilot routes (compute_median.py:4-16)."""
+    from stein_b200.engine import SvgdEngine
+    n, d = 4608, 256
+    X = _particles(n, d, 41)
+    eng = SvgdEngine(n, d, "adam", learning_rate=1e-6)
+    hits0, miss0 = ctypes.c_longlong(), ctypes.c_longlong()
+    ctx.lib.stein_debug_median_direct_stats(ctypes.byref(hits0), ctypes.byref(miss0))
+    eng.set_particles(X)
+    for it in range(6):
+        Xin = eng.get_particles(np.float32)
+        eng.set_scores(-Xin)
+        eng.step()
+        m_ref, _ = orc.median_chain(Xin, radix=True)
+        assert np.float32(eng.last()["median"]).tobytes() == m_ref.tobytes(), it
+    hits, miss = ctypes.c_longlong(), ctypes.c_longlong()
+    ctx.lib.stein_debug_median_direct_stats(ctypes.byref(hits), ctypes.byref(miss))
+    assert hits.value - hits0.value >= 3 and miss.value == miss0.value, (hits.value - hits0.value, miss.value - miss0.value)
+    # a jump: the pilot-less attempt misses once, the step still returns the exact median
+    eng.particles_dev.mul_(3.0)
+    Xin = eng.get_particles(np.float32)
+    eng.set_scores(-Xin)
+    eng.step()
+    m_ref, _ = orc.median_chain(Xin, radix=True)
+    assert np.float32(eng.last()["median"]).tobytes() == m_ref.tobytes()
+    ctx.lib.stein_debug_median_direct_stats(ctypes.byref(hits), ctypes.byref(miss))
+    assert miss.value - miss0.value == 1
+    eng.close()
