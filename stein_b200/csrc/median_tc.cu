@@ -1449,6 +1449,11 @@ int pilot_window(stein_ctx *ctx, const uint32_t *keys_dev, int64_t m, uint64_t r
     *hi_key = (uint32_t)hi;
     last_center = (uint32_t)((lo + hi) / 2);
     have_last = true;
+    if (g_arena.hint_owner != ctx->median_owner) {      // another engine's sequence starts: its own pilot-less history
+        g_arena.med_keys_known = 0;
+        g_arena.direct_cooldown = 0;
+        g_arena.last_half = 0u;
+    }
     g_arena.hint_owner = ctx->median_owner;
     return STEIN_OK;
 }
@@ -1469,6 +1474,9 @@ bool median_tc_has_hint(const stein_ctx *ctx) { return hint_usable(ctx); }
 // a miss falls back to the pilot route and keeps it for a few iterations.
 bool median_tc_direct_ok(const stein_ctx *ctx) {
     const MedianArena &A = g_arena;
+    if (getenv("STEIN_MEDIAN_DEBUG"))
+        fprintf(stderr, "[stein] direct_ok: hint %d known %d half %u cooldown %d keys %u %u\n", (int)hint_usable(ctx),
+                A.med_keys_known, A.last_half, A.direct_cooldown, A.med_key, A.prev_med_key);
     if (!hint_usable(ctx) || A.med_keys_known < 2 || A.last_half == 0u || A.direct_cooldown > 0) return false;
     if (const char *e = getenv("STEIN_MEDIAN_PILOTLESS"))
         if (e[0] == '0') return false;
