@@ -39,7 +39,7 @@ def algorithmic_flops_phi(n, d):
 def ncu_traffic(kernel_substr):
     """DRAM bytes per launch (read + write) of the dominant kernel from the committed ncu
     --set full summary (profiles/, written by tools/ncu_summary.py), or None."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
+    path = os.path.join(ROOT, "profiles", "r02_ncu_full_summary.json")
     try:
         data = json.load(open(path))
     except (OSError, ValueError):

@@ -39,6 +39,11 @@ struct stein_engine {
     void *stage = nullptr;  // device staging for float64 host arrays
     cudaStream_t copy_stream = nullptr;  // score upload overlapped with the median (update_particles_host)
     cudaEvent_t ev_scores = nullptr, ev_ready = nullptr;
+    // The part of the phi preparation that needs neither the bandwidth nor the scores (centring, scale of X, the
+    // X operand arrays) runs on this stream NEXT TO the median: HBM-bound kernels beside the tensor-bound sweep.
+    cudaStream_t prep_stream = nullptr;
+    cudaEvent_t ev_x = nullptr, ev_prep = nullptr;
+    bool prep_pending = false;
     // peer push of the updated particles (CUDA IPC views of the other ranks' X_all)
     float *peer_X[stein::MAX_PEERS + 1] = {nullptr};   // indexed by rank; own entry unused
     bool peers_open = false;
@@ -181,6 +186,9 @@ int stein_engine_create(stein_engine **out, stein_ctx *ctx, int64_t n_total, int
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_scores, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_ready, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->prep_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_x, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_prep, cudaEventDisableTiming);
     if (err != cudaSuccess) {
         stein_engine_destroy(e);
         return fail(ctx, err == cudaErrorMemoryAllocation ? STEIN_ERR_NOMEM : STEIN_ERR_CUDA,
@@ -215,6 +223,12 @@ int stein_engine_destroy(stein_engine *e) {
         cudaStreamSynchronize(e->copy_stream);
         cudaStreamDestroy(e->copy_stream);
     }
+    if (e->prep_stream) {
+        cudaStreamSynchronize(e->prep_stream);
+        cudaStreamDestroy(e->prep_stream);
+    }
+    if (e->ev_x) cudaEventDestroy(e->ev_x);
+    if (e->ev_prep) cudaEventDestroy(e->ev_prep);
     if (e->ev_scores) cudaEventDestroy(e->ev_scores);
     if (e->ev_ready) cudaEventDestroy(e->ev_ready);
     delete e;
@@ -264,8 +278,8 @@ int stein_engine_get_phi(stein_engine *e, void *phi_host, int is_f64) {
     return download(e, e->phi, phi_host, is_f64);
 }
 
-// Called by the median right before its host round trip (stein_ctx::presync_fn): the part of the
-// phi preparation that needs neither the bandwidth nor the scores (centring, scale of X).
+// The part of the phi preparation that needs neither the bandwidth nor the scores (centring, scale of X, the X
+// operand arrays in the fast format); step_bandwidth enqueues it on the engine's prep stream beside the median.
 static int engine_presync(void *arg) {
     stein_engine *e = static_cast<stein_engine *>(arg);
     return phi_prepare_x(e->ctx, e->X_all, e->n_total, e->d, e->ld, std::max<int64_t>(e->n_local, 1), e->ws,
@@ -302,17 +316,25 @@ static int step_bandwidth(stein_engine *e, float *bw_out) {
     }
     // compute_median.py + abstract_kernel.py:40
     float med = 0.f;
+    // the bandwidth-independent part of the phi preparation, on its own stream beside the median
+    {
+        STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_x, ctx->stream));
+        STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(e->prep_stream, e->ev_x, 0));
+        cudaStream_t main_stream = ctx->stream;
+        ctx->stream = e->prep_stream;
+        const int prc = engine_presync(e);
+        ctx->stream = main_stream;
+        if (prc != STEIN_OK) return prc;
+        STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_prep, e->prep_stream));
+        e->prep_pending = true;
+    }
     // successive medians of one engine move slowly: window hint allowed (owner = the engine's uid)
     ctx->median_owner = reinterpret_cast<const void *>(e->uid);
-    ctx->presync_fn = engine_presync;
-    ctx->presync_arg = e;
     RegionTimer mtimer(ctx, STEIN_REGION_MEDIAN);
     const int mrc = stein_median_sqdist(ctx, e->X_all, e->r_all, e->n_total, e->d, e->ld, &med, nullptr,
                                         &e->last_sweeps);
     mtimer.stop();
     ctx->median_owner = nullptr;
-    ctx->presync_fn = nullptr;
-    ctx->presync_arg = nullptr;
     if (mrc != STEIN_OK) return mrc;
     const float bw = stein_bandwidth(med, e->n_total);
     e->last_med = med;
@@ -331,6 +353,10 @@ static int step_phi(stein_engine *e, float bw, bool scores_gathered) {
         const int64_t cnt = e->q * e->ld;
         if (ctx->comm.allgather_f32(ctx->comm.user, e->S_local(), e->S_all, cnt) != 0)
             return fail(ctx, STEIN_ERR_COMM, "allgather_f32 hook failed");
+    }
+    if (e->prep_pending) {      // the side-stream preparation of this iteration's X
+        STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e->ev_prep, 0));
+        e->prep_pending = false;
     }
     // abstract_stein_sampler.py:100-105.  The conditioning guard of the phi call may decide from the previous
     // iteration's kappa (guard_owner): successive clouds of one engine differ by one small step.

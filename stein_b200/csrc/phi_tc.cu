@@ -1304,6 +1304,14 @@ __global__ void prep_x_route_kernel(const float *__restrict__ X, const float *__
             reinterpret_cast<uint32_t *>(B8l)[e] = tc::pack_e5m2x2(lo[0], lo[1]) | (tc::pack_e5m2x2(lo[2], lo[3]) << 16);
         }
     }
+    // (half_l2e_over_h2 < 0: the bandwidth is not known yet -- the arrays are prepared ahead, nrm_kernel follows)
+    if (half_l2e_over_h2 >= 0.0f && e < nrm_rows) nrm[e] = (e < n) ? -r[e] * half_l2e_over_h2 : -INFINITY;
+}
+
+// exponent terms alone: nrm[j] = -r_j log2(e) / (2 h^2), -inf beyond n
+__global__ void nrm_kernel(const float *__restrict__ r, int64_t n, float half_l2e_over_h2, float *__restrict__ nrm,
+                           int64_t nrm_rows) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < nrm_rows) nrm[e] = (e < n) ? -r[e] * half_l2e_over_h2 : -INFINITY;
 }
 
@@ -1775,6 +1783,15 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
         STEIN_CHECK_LAUNCH(ctx);
     }
     if (only_prepare) {
+        // ahead of the bandwidth: also the X operand arrays, in the FAST format (what the guard picks for every
+        // well-conditioned cloud; the precise route redoes them)
+        if (scaled && mode_in != 3) {
+            const int64_t tot = cols * DP / 4;
+            prep_x_route_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(
+                Xc, rc, cols, n_total, ld, -1.0f, xscale, nullptr, 0, (__half *)Xh, (uint8_t *)Xl, (uint8_t *)Xl + cols * DP, B8h,
+                B8l, nrm, 0);
+            STEIN_CHECK_LAUNCH(ctx);
+        }
         ctx->xprep = {X_all, ws, n_total, n_local, d, mode_in};
         return STEIN_OK;
     }
@@ -1806,7 +1823,11 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
     const int forced_precise = mode == 3 ? 1 : 0;
     {
         const int64_t tot = std::max<int64_t>(cols * DP / 4, cols + 256);
-        if (scaled) {
+        if (scaled && prepared && !forced_precise) {
+            // the arrays were written ahead of the bandwidth (flash_tc2_prepare_x): only the exponent terms are left
+            nrm_kernel<<<(unsigned)((cols + 256 + 255) / 256), 256, 0, ctx->stream>>>(rc, n_total, 0.5f * l2e / h2, nrm,
+                                                                                       cols + 256);
+        } else if (scaled) {
             // FP16 array in the place of Xh; fast: a8l, a8h share the place of Xl and b8h, b8l have their
             // own; precise: the FP16 residual takes the place of Xl
             prep_x_route_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(
