@@ -135,6 +135,11 @@ int stein_ctx_set_phi_guard_tol(stein_ctx *ctx, float tol);
  * its timed region); 2 = all regions (the per-phase timeline, measured in a separate pass) */
 int stein_ctx_profile_enable(stein_ctx *ctx, int enable);
 int stein_ctx_profile_read(stein_ctx *ctx, int region, double *ms_total, int64_t *launches);
+/* Fine-grained timeline of the ctx stream (tools/step_trace.py): while enabled the library records a
+ * labelled event after each stage of an iteration; _read waits for the device and writes
+ * "label<TAB>milliseconds since the previous mark" lines (in enqueue order) into buf.             */
+int stein_ctx_trace_enable(stein_ctx *ctx, int enable);
+int stein_ctx_trace_read(stein_ctx *ctx, char *buf, int64_t cap);
 
 int64_t stein_ld(int64_t d);           /* leading dimension for d columns     */
 int64_t stein_rows_padded(int64_t n);  /* rows to allocate for n particles    */
@@ -317,9 +322,24 @@ int stein_engine_sumsq_dev(stein_engine *eng, double **sumsq_dev);
  * betas from the gd object at every update(), adam_gradient_descent.py:41-58) */
 int stein_engine_set_hyper(stein_engine *eng, double learning_rate, double decay, double p1, double p2);
 /* the host-buffer drop-in: H2D scores -> step -> D2H particles (X_host_out may
- * be NULL to leave the particles on the device)                               */
+ * be NULL to leave the particles on the device).  Replaces update_particles(grads_array),
+ * stein/samplers/abstract_stein_sampler.py:107-127.  Synchronous contract: the caller holds the
+ * updated particles when the call returns.  With X_host_out given the call also ENQUEUES the start
+ * of the next iteration (row norms, operand preparation and, in the steady state of the median,
+ * the device part of the exact median -- they need only the particles, not the caller's next
+ * scores) behind the optimizer kernel, so that this work runs while the particles cross PCIe and
+ * while the caller evaluates its scores; the next call (or stein_engine_step / _phi_only) collects
+ * the result.  Results are the same bits with and without this prefetch (environment
+ * STEIN_PREFETCH=0 or stein_engine_set_prefetch(eng, 0) turn it off).                          */
 int stein_engine_update_particles_host(stein_engine *eng, const void *S_host, void *X_host_out,
                                        int is_f64);
+int stein_engine_set_prefetch(stein_engine *eng, int on);
+/* how many next-iteration medians were enqueued ahead / later collected by a step */
+int stein_engine_prefetch_stats(const stein_engine *eng, int64_t *begun, int64_t *used);
+/* A caller that writes the particle buffer of stein_engine_buffers itself (instead of
+ * stein_engine_set_particles) says so here before its next step: anything derived from the old
+ * particles (a prefetched median, the peers' copies of the rows) is dropped.                  */
+int stein_engine_particles_changed(stein_engine *eng);
 /* Peer push (optional, ranks on one node): each rank exports the CUDA-IPC handle of its particle
  * buffer (STEIN_IPC_HANDLE_BYTES), the handles of all ranks are concatenated in rank order by any
  * means, and every rank imports them.  From then on the optimizer kernel stores the updated rows

@@ -104,6 +104,11 @@ SIGNATURES = {
     "stein_engine_sumsq_dev": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp)]),
     "stein_engine_set_hyper": (ctypes.c_int, [c_vp, c_f64, c_f64, c_f64, c_f64]),
     "stein_engine_update_particles_host": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int]),
+    "stein_ctx_trace_enable": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "stein_ctx_trace_read": (ctypes.c_int, [c_vp, ctypes.c_char_p, c_i64]),
+    "stein_engine_set_prefetch": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "stein_engine_prefetch_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
+    "stein_engine_particles_changed": (ctypes.c_int, [c_vp]),
     "stein_engine_ipc_handle": (ctypes.c_int, [c_vp, c_vp]),
     "stein_engine_set_peer_handles": (ctypes.c_int, [c_vp, c_vp]),
     "stein_engine_set_bandwidth": (ctypes.c_int, [c_vp, c_f32]),

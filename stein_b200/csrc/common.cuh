@@ -59,6 +59,8 @@ struct stein_ctx {
     // while this iteration's value travels for the next one.  guard_lag_owner: whose value the other slot
     // holds (NULL: nobody's -- the next guarded call waits for its own value).
     const void *guard_owner = nullptr, *guard_lag_owner = nullptr;
+    // set around a median call whose host part is collected later (median_sqdist_begin / _resume)
+    int median_defer = 0;
     int last_route = -1;
     float last_kappa = 0.0f, last_pred_fast = 0.0f;
     float phi_guard_tol = 5.0e-5f;
@@ -75,6 +77,10 @@ struct stein_ctx {
     int profile = 0;                // 0 off, 1 = regions PHI / SWEEP only, 2 = all regions (timeline)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[STEIN_REGION_COUNT];
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;
+    // optional fine-grained timeline (tools/step_trace.py): labelled events on `stream`, read by stein_ctx_trace_read
+    int trace = 0;
+    std::vector<std::pair<const char *, cudaEvent_t>> trace_marks;
+    std::vector<cudaEvent_t> trace_pool;
 };
 
 namespace stein {
@@ -86,6 +92,16 @@ void nccl_release(stein_ctx *ctx);   // comm_nccl.cu
 // in-place sums across the ranks, ordered on the ctx stream (peer_reduce.cu)
 int allreduce_u64(stein_ctx *ctx, void *buf_dev, int64_t count);
 int allreduce_f64(stein_ctx *ctx, void *buf_dev, int64_t count);
+
+// Median of the squared distances in two halves (median.cu): _begin enqueues the device part when the pilot-less
+// steady state applies (MEDIAN_DEFERRED) or does nothing (MEDIAN_NOT_DEFERRED); _resume collects the result.
+constexpr int MEDIAN_FULL = 0, MEDIAN_BEGIN = 1, MEDIAN_RESUME = 2;
+constexpr int MEDIAN_DEFERRED = 3, MEDIAN_NOT_DEFERRED = 4;
+int median_sqdist_begin(stein_ctx *ctx, const float *X_dev, const float *r_dev, int64_t n, int64_t d, int64_t ld);
+int median_sqdist_resume(stein_ctx *ctx, const float *X_dev, const float *r_dev, int64_t n, int64_t d, int64_t ld,
+                         float *median_host, int32_t *sweeps_host);
+bool median_sqdist_deferred_pending(void);
+bool median_sqdist_can_defer(const stein_ctx *ctx, int64_t n, int64_t ld);
 
 #define STEIN_CHECK_CUDA(ctx, expr)                                                        \
     do {                                                                                   \
@@ -140,6 +156,20 @@ struct RegionTimer {
     }
     ~RegionTimer() { stop(); }
 };
+
+// labelled timeline mark: completes when everything enqueued before it on the ctx stream has finished
+inline void trace_mark(stein_ctx *ctx, const char *label) {
+    if (!ctx->trace) return;
+    cudaEvent_t ev;
+    if (!ctx->trace_pool.empty()) {
+        ev = ctx->trace_pool.back();
+        ctx->trace_pool.pop_back();
+    } else {
+        cudaEventCreate(&ev);
+    }
+    cudaEventRecord(ev, ctx->stream);
+    ctx->trace_marks.emplace_back(label, ev);
+}
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 

@@ -1,6 +1,7 @@
 // ctx.cu -- context lifetime, error text, collective hooks, phi dispatch.
 #include <stdarg.h>
 #include <stdlib.h>
+#include <algorithm>
 
 #include "phi_common.cuh"
 
@@ -90,6 +91,8 @@ int stein_ctx_destroy(stein_ctx *ctx) {
         if (ctx->ev_guard[k]) cudaEventDestroy(ctx->ev_guard[k]);
     for (int r = 0; r < STEIN_REGION_COUNT; ++r)
         for (auto &ev : ctx->prof_events[r]) ctx->prof_pool.push_back(ev);
+    for (auto &m : ctx->trace_marks) cudaEventDestroy(m.second);
+    for (auto &ev : ctx->trace_pool) cudaEventDestroy(ev);
     for (auto &ev : ctx->prof_pool) {
         cudaEventDestroy(ev.first);
         cudaEventDestroy(ev.second);
@@ -157,6 +160,32 @@ int stein_ctx_profile_read(stein_ctx *ctx, int region, double *ms_total, int64_t
     if (ms_total) *ms_total = total;
     if (launches) *launches = (int64_t)ctx->prof_events[region].size();
     ctx->prof_events[region].clear();
+    return STEIN_OK;
+}
+
+int stein_ctx_trace_enable(stein_ctx *ctx, int enable) {
+    STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    ctx->trace = enable != 0;
+    return STEIN_OK;
+}
+
+// "label<TAB>ms since the previous mark" per line, in enqueue order; clears the marks
+int stein_ctx_trace_read(stein_ctx *ctx, char *buf, int64_t cap) {
+    STEIN_REQUIRE(ctx, ctx != nullptr && buf != nullptr && cap > 0, "bad arguments");
+    STEIN_CHECK_CUDA(ctx, cudaDeviceSynchronize());
+    std::string out;
+    for (size_t k = 0; k < ctx->trace_marks.size(); ++k) {
+        float ms = 0.f;
+        if (k > 0) STEIN_CHECK_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->trace_marks[k - 1].second, ctx->trace_marks[k].second));
+        char line[160];
+        snprintf(line, sizeof(line), "%s\t%.6f\n", ctx->trace_marks[k].first, (double)ms);
+        out += line;
+    }
+    for (auto &m : ctx->trace_marks) ctx->trace_pool.push_back(m.second);
+    ctx->trace_marks.clear();
+    const size_t ncopy = std::min<size_t>(out.size(), (size_t)cap - 1);
+    memcpy(buf, out.data(), ncopy);
+    buf[ncopy] = 0;
     return STEIN_OK;
 }
 

@@ -44,6 +44,12 @@ struct stein_engine {
     cudaStream_t prep_stream = nullptr;
     cudaEvent_t ev_x = nullptr, ev_prep = nullptr;
     bool prep_pending = false;
+    // update_particles_host: the next iteration's head and median are enqueued behind the optimizer kernel, so they
+    // run while the updated particles cross PCIe (the median needs only the particles, not the caller's next scores)
+    bool prefetch = true;
+    bool bw_pending = false;        // a deferred median (median_sqdist_begin) of the current particles is in flight
+    int64_t prefetch_begun = 0, prefetch_used = 0;
+    cudaEvent_t ev_update = nullptr;    // after the optimizer kernel: the download and the next score upload wait for it
     // peer push of the updated particles (CUDA IPC views of the other ranks' X_all)
     float *peer_X[stein::MAX_PEERS + 1] = {nullptr};   // indexed by rank; own entry unused
     bool peers_open = false;
@@ -106,25 +112,30 @@ static int upload(stein_engine *e, const void *host, int is_f64, float *dst) {
     return upload(e, host, is_f64, dst, e->ctx->stream);
 }
 
-static int download(stein_engine *e, const float *src, void *host, int is_f64) {
+static int download_async(stein_engine *e, const float *src, void *host, int is_f64, cudaStream_t stream) {
     stein_ctx *ctx = e->ctx;
     STEIN_REQUIRE(ctx, host != nullptr, "null host pointer");
     if (e->n_local == 0) return STEIN_OK;
     if (!is_f64) {
         if (e->ld == e->d) {
-            STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(host, src, e->n_local * e->d * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(host, src, e->n_local * e->d * 4, cudaMemcpyDeviceToHost, stream));
         } else {
             STEIN_CHECK_CUDA(ctx, cudaMemcpy2DAsync(host, e->d * 4, src, e->ld * 4, e->d * 4, e->n_local,
-                                                    cudaMemcpyDeviceToHost, ctx->stream));
+                                                    cudaMemcpyDeviceToHost, stream));
         }
     } else {
         const int64_t total = e->n_local * e->d;
-        padded_to_f64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+        padded_to_f64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
             src, e->n_local, e->d, e->ld, (double *)e->stage);
         STEIN_CHECK_LAUNCH(ctx);
-        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(host, e->stage, total * 8, cudaMemcpyDeviceToHost,
-                                              ctx->stream));
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(host, e->stage, total * 8, cudaMemcpyDeviceToHost, stream));
     }
+    return STEIN_OK;
+}
+
+static int download(stein_engine *e, const float *src, void *host, int is_f64) {
+    stein_ctx *ctx = e->ctx;
+    STEIN_TRY(download_async(e, src, host, is_f64, ctx->stream));
     STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return STEIN_OK;
 }
@@ -189,6 +200,8 @@ int stein_engine_create(stein_engine **out, stein_ctx *ctx, int64_t n_total, int
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->prep_stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_x, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_prep, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_update, cudaEventDisableTiming);
+    if (const char *env = getenv("STEIN_PREFETCH")) e->prefetch = env[0] != '0';
     if (err != cudaSuccess) {
         stein_engine_destroy(e);
         return fail(ctx, err == cudaErrorMemoryAllocation ? STEIN_ERR_NOMEM : STEIN_ERR_CUDA,
@@ -229,6 +242,7 @@ int stein_engine_destroy(stein_engine *e) {
     }
     if (e->ev_x) cudaEventDestroy(e->ev_x);
     if (e->ev_prep) cudaEventDestroy(e->ev_prep);
+    if (e->ev_update) cudaEventDestroy(e->ev_update);
     if (e->ev_scores) cudaEventDestroy(e->ev_scores);
     if (e->ev_ready) cudaEventDestroy(e->ev_ready);
     delete e;
@@ -256,6 +270,7 @@ int stein_engine_buffers(stein_engine *e, float **X_local_dev, float **S_local_d
 int stein_engine_set_particles(stein_engine *e, const void *X_host, int is_f64) {
     if (!e) return STEIN_ERR_INVALID;
     e->x_all_current = false;      // the other ranks' copies of these rows are stale now
+    e->bw_pending = false;         // a prefetched median belongs to the old particles
     if (e->ctx->guard_lag_owner == reinterpret_cast<const void *>(e->uid))
         e->ctx->guard_lag_owner = nullptr;     // a new cloud: the next phi call waits for its own conditioning number
     STEIN_TRY(upload(e, X_host, is_f64, e->X_local()));
@@ -286,12 +301,14 @@ static int engine_presync(void *arg) {
                          e->ws_bytes);
 }
 
-// Phase 1 needs only the particles: all-gather X, row norms, exact median, bandwidth.
-static int step_bandwidth(stein_engine *e, float *bw_out) {
+// Start of an iteration, needs only the particles: all-gather X (or the barrier behind the peer push), row norms,
+// and the bandwidth-independent part of the phi preparation on its own stream.
+static int step_head(stein_engine *e) {
     stein_ctx *ctx = e->ctx;
     const int64_t rows_all = e->q * e->world;
     ctx->xprep.X = nullptr;
     RegionTimer head(ctx, STEIN_REGION_HEAD);
+    trace_mark(ctx, "step:begin");
     if (e->world > 1) {
         if (e->peers_open && e->x_all_current) {
             // every rank pushed its updated rows into this buffer during its last optimizer
@@ -307,6 +324,29 @@ static int step_bandwidth(stein_engine *e, float *bw_out) {
     // abstract_kernel.py:34 -- r = sum(T*T, 1), contract order
     STEIN_TRY(stein_row_norms(ctx, e->X_all, rows_all, e->d, e->ld, e->r_all));
     head.stop();
+    trace_mark(ctx, "head:row norms");
+    if (e->fixed_bw > 0.0f) return STEIN_OK;
+    // the bandwidth-independent part of the phi preparation, on its own stream beside the median
+    STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_x, ctx->stream));
+    STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(e->prep_stream, e->ev_x, 0));
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = e->prep_stream;
+    const int prc = engine_presync(e);
+    ctx->stream = main_stream;
+    if (prc != STEIN_OK) return prc;
+    STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_prep, e->prep_stream));
+    e->prep_pending = true;
+    return STEIN_OK;
+}
+
+// Phase 1: head, exact median, bandwidth.  When the previous update_particles_host call has already enqueued the
+// head and the device part of the median for these particles (step_prefetch), only its result is collected.
+static int step_bandwidth(stein_engine *e, float *bw_out) {
+    stein_ctx *ctx = e->ctx;
+    const bool resume = e->bw_pending && median_sqdist_deferred_pending();
+    e->bw_pending = false;
+    if (resume) e->prefetch_used += 1;
+    if (!resume) STEIN_TRY(step_head(e));
     if (e->fixed_bw > 0.0f) {
         e->last_med = nanf("");
         e->last_bw = e->fixed_bw;
@@ -316,23 +356,13 @@ static int step_bandwidth(stein_engine *e, float *bw_out) {
     }
     // compute_median.py + abstract_kernel.py:40
     float med = 0.f;
-    // the bandwidth-independent part of the phi preparation, on its own stream beside the median
-    {
-        STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_x, ctx->stream));
-        STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(e->prep_stream, e->ev_x, 0));
-        cudaStream_t main_stream = ctx->stream;
-        ctx->stream = e->prep_stream;
-        const int prc = engine_presync(e);
-        ctx->stream = main_stream;
-        if (prc != STEIN_OK) return prc;
-        STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_prep, e->prep_stream));
-        e->prep_pending = true;
-    }
     // successive medians of one engine move slowly: window hint allowed (owner = the engine's uid)
     ctx->median_owner = reinterpret_cast<const void *>(e->uid);
     RegionTimer mtimer(ctx, STEIN_REGION_MEDIAN);
-    const int mrc = stein_median_sqdist(ctx, e->X_all, e->r_all, e->n_total, e->d, e->ld, &med, nullptr,
-                                        &e->last_sweeps);
+    e->last_sweeps = 0;
+    const int mrc = resume ? median_sqdist_resume(ctx, e->X_all, e->r_all, e->n_total, e->d, e->ld, &med, &e->last_sweeps)
+                           : stein_median_sqdist(ctx, e->X_all, e->r_all, e->n_total, e->d, e->ld, &med, nullptr,
+                                                 &e->last_sweeps);
     mtimer.stop();
     ctx->median_owner = nullptr;
     if (mrc != STEIN_OK) return mrc;
@@ -343,6 +373,27 @@ static int step_bandwidth(stein_engine *e, float *bw_out) {
         return fail(ctx, STEIN_ERR_INVALID,
                     "median squared distance is %g: bandwidth undefined (all particles equal?)", (double)med);
     *bw_out = bw;
+    return STEIN_OK;
+}
+
+// The next iteration's head and (in the pilot-less steady state of the median) the device part of its median,
+// enqueued right behind the optimizer kernel.  No host wait: step_bandwidth of the next call collects the result.
+static int step_prefetch(stein_engine *e) {
+    stein_ctx *ctx = e->ctx;
+    if (!e->prefetch || e->fixed_bw > 0.0f || e->bw_pending) return STEIN_OK;
+    if (e->world > 1 && !(e->peers_open && e->x_all_current)) return STEIN_OK;   // the all-gather hook may block
+    ctx->median_owner = reinterpret_cast<const void *>(e->uid);
+    // (asked before the head is enqueued: a head without a deferred median would only be repeated)
+    const bool can = median_sqdist_can_defer(ctx, e->n_total, e->ld);
+    int rc = STEIN_OK;
+    if (can) {
+        rc = step_head(e);
+        if (rc == STEIN_OK) rc = median_sqdist_begin(ctx, e->X_all, e->r_all, e->n_total, e->d, e->ld);
+    }
+    ctx->median_owner = nullptr;
+    if (rc < 0) return rc;
+    e->bw_pending = can && rc == MEDIAN_DEFERRED;
+    if (e->bw_pending) e->prefetch_begun += 1;
     return STEIN_OK;
 }
 
@@ -390,6 +441,7 @@ static int step_optimizer(stein_engine *e) {
         for (int r = 0; r < e->world; ++r)
             if (r != e->rank) peers.dst[peers.n++] = reinterpret_cast<float4 *>(e->peer_X[r] + (int64_t)e->rank * e->q * e->ld);
     }
+    e->bw_pending = false;      // (a median prefetched for the particles this step replaces would be stale)
     RegionTimer otimer(ctx, STEIN_REGION_OPT);
     if (e->opt == STEIN_OPT_ADAM) {
         STEIN_TRY(clip_adam_step(ctx, e->X_local(), e->phi, e->m1, e->m2, count, e->sumsq, e->lr, e->p1, e->p2,
@@ -400,6 +452,7 @@ static int step_optimizer(stein_engine *e) {
         STEIN_TRY(clip_adagrad_step(ctx, e->X_local(), e->phi, e->m1, count, e->sumsq, e->lr, e->p1, e->n_iters,
                                     peers));
     }
+    trace_mark(ctx, "step:optimizer + push");
     if (peers.n) e->x_all_current = true;
     e->n_iters += 1;
     return STEIN_OK;
@@ -442,10 +495,11 @@ int stein_engine_update_particles_host(stein_engine *e, const void *S_host, void
     if (!e) return STEIN_ERR_INVALID;
     stein_ctx *ctx = e->ctx;
     STEIN_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-    // The median needs the particles only: the scores travel on a second stream while it runs
-    // (the S buffer's last reader, the previous phi, is ordered before the copy by ev_ready).
-    STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_ready, ctx->stream));
-    STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(e->copy_stream, e->ev_ready, 0));
+    // The median needs the particles only: the scores travel on a second stream while it runs.  The S buffer's
+    // last reader is the previous phi: ev_update (recorded behind the previous optimizer kernel) orders the copy
+    // after it when a prefetched median is already queued on the ctx stream, else an event recorded now.
+    if (!e->bw_pending) STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_update, ctx->stream));
+    STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(e->copy_stream, e->ev_update, 0));
     STEIN_TRY(upload(e, S_host, is_f64, e->S_local(), e->copy_stream));
     bool gathered = false;
     STEIN_TRY(gather_scores_async(e, &gathered));
@@ -455,7 +509,36 @@ int stein_engine_update_particles_host(stein_engine *e, const void *S_host, void
     STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e->ev_scores, 0));
     if (rc != STEIN_OK) return rc;
     STEIN_TRY(step_update(e, bw, gathered));
-    if (X_host_out) return stein_engine_get_particles(e, X_host_out, is_f64);
+    if (!X_host_out) return STEIN_OK;
+    // The updated particles cross PCIe on the copy stream while the ctx stream already runs the next iteration's
+    // head and median (they need only the particles): the caller holds the new particles when this returns, and
+    // the next call finds its bandwidth (nearly) ready.
+    STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_update, ctx->stream));
+    STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(e->copy_stream, e->ev_update, 0));
+    STEIN_TRY(download_async(e, e->X_local(), X_host_out, is_f64, e->copy_stream));
+    const int prc = step_prefetch(e);
+    STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(e->copy_stream));
+    return prc;
+}
+
+int stein_engine_set_prefetch(stein_engine *e, int on) {
+    if (!e) return STEIN_ERR_INVALID;
+    e->prefetch = on != 0;
+    return STEIN_OK;
+}
+
+int stein_engine_prefetch_stats(const stein_engine *e, int64_t *begun, int64_t *used) {
+    if (!e) return STEIN_ERR_INVALID;
+    if (begun) *begun = e->prefetch_begun;
+    if (used) *used = e->prefetch_used;
+    return STEIN_OK;
+}
+
+int stein_engine_particles_changed(stein_engine *e) {
+    if (!e) return STEIN_ERR_INVALID;
+    e->x_all_current = false;
+    e->bw_pending = false;
+    if (e->ctx->guard_lag_owner == reinterpret_cast<const void *>(e->uid)) e->ctx->guard_lag_owner = nullptr;
     return STEIN_OK;
 }
 

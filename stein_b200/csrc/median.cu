@@ -306,6 +306,9 @@ bool median_tc_has_hint(const stein_ctx *ctx);
 bool median_tc_direct_ok(const stein_ctx *ctx);
 void median_tc_count_direct_hit(void);
 void median_tc_note_result(const stein_ctx *ctx, uint32_t k0, uint32_t k1, bool direct_missed);
+bool median_tc_deferred_pending(void);
+void median_tc_cancel_deferred(void);
+int median_tc_finish_deferred(stein_ctx *ctx, uint32_t keys_out[2]);
 int median_tc_begin(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t ld);
 void median_tc_reset(void);
 int median_tc_pilot(stein_ctx *ctx, uint32_t *keys_dev, unsigned long long m, const float *r, int64_t n, int64_t ld,
@@ -434,11 +437,49 @@ int stein_median_values(stein_ctx *ctx, const float *V_dev, int64_t m, float *me
     return STEIN_OK;
 }
 
+// mode MEDIAN_FULL: the whole call.  MEDIAN_BEGIN: only when the pilot-less steady state applies (else returns
+// MEDIAN_NOT_DEFERRED with nothing enqueued) -- enqueues the device part of the median and returns
+// MEDIAN_DEFERRED without waiting for it.  MEDIAN_RESUME: collects that median; a miss continues on the routes of
+// the full call.  (engine.cu: the next iteration's median runs behind the download of the updated particles.)
+static int median_sqdist_impl(stein_ctx *ctx, const float *X_dev, const float *r_dev, int64_t n, int64_t d,
+                              int64_t ld, float *median_host, float *mid_host, int32_t *sweeps_host, int mode);
+}  // extern "C"
+
+namespace stein {
+int median_sqdist_begin(stein_ctx *ctx, const float *X_dev, const float *r_dev, int64_t n, int64_t d, int64_t ld) {
+    return median_sqdist_impl(ctx, X_dev, r_dev, n, d, ld, nullptr, nullptr, nullptr, MEDIAN_BEGIN);
+}
+int median_sqdist_resume(stein_ctx *ctx, const float *X_dev, const float *r_dev, int64_t n, int64_t d, int64_t ld,
+                         float *median_host, int32_t *sweeps_host) {
+    return median_sqdist_impl(ctx, X_dev, r_dev, n, d, ld, median_host, nullptr, sweeps_host, MEDIAN_RESUME);
+}
+bool median_sqdist_deferred_pending(void) { return median_tc_deferred_pending(); }
+// which route a deferred median took: 1 pilot-less (window recentred on the last exact median), 2 pilot sample +
+// device-picked window around the last one
+static int g_deferred_kind = 0;
+bool median_sqdist_can_defer(const stein_ctx *ctx, int64_t n, int64_t ld) {
+    return (uint64_t)n * (uint64_t)n >= (1ull << 24) && ctx->median_impl != STEIN_MEDIAN_FFMA &&
+           median_tc_supported(n, ld) && (median_tc_direct_ok(ctx) || median_tc_has_hint(ctx));
+}
+}  // namespace stein
+
+extern "C" {
+
 int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, int64_t n, int64_t d,
                         int64_t ld, float *median_host, float *mid_host, int32_t *sweeps_host) {
     STEIN_REQUIRE(ctx, ctx != nullptr, "null ctx");
+    return median_sqdist_impl(ctx, X_dev, r_dev, n, d, ld, median_host, mid_host, sweeps_host, MEDIAN_FULL);
+}
+
+static int median_sqdist_impl(stein_ctx *ctx, const float *X_dev, const float *r_dev, int64_t n, int64_t d,
+                              int64_t ld, float *median_host, float *mid_host, int32_t *sweeps_host, int mode) {
     STEIN_TRY(check_layout(ctx, X_dev, n, d, ld));
-    STEIN_REQUIRE(ctx, median_host != nullptr, "null output pointer");
+    STEIN_REQUIRE(ctx, median_host != nullptr || mode == MEDIAN_BEGIN, "null output pointer");
+    if (mode == MEDIAN_BEGIN) {
+        if (!median_sqdist_can_defer(ctx, n, ld)) return MEDIAN_NOT_DEFERRED;
+    } else if (mode == MEDIAN_FULL) {
+        median_tc_cancel_deferred();      // a deferred median of another call is void once the arena is reused
+    }
     const uint64_t dim = (uint64_t)n * (uint64_t)n;
     // compute_median.py:9-15: 0-based ascending ranks of the middle value(s)
     const uint64_t ranks[2] = {dim % 2 == 0 ? dim / 2 - 1 : dim / 2, dim / 2};
@@ -490,7 +531,7 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
         const int pw = ctx->has_comm ? ctx->comm.world : 1, pr = ctx->has_comm ? ctx->comm.rank : 0;
         const int64_t s0 = pilot_m * pr / pw, s1 = pilot_m * (pr + 1) / pw;
         const bool tc_ok = ctx->median_impl != STEIN_MEDIAN_FFMA && median_tc_supported(n, ld);
-        median_tc_reset();
+        if (mode != MEDIAN_RESUME) median_tc_reset();
         const uint64_t delta = (uint64_t)(3.5 * sqrt((double)pilot_m));
         auto run_pilot = [&]() -> int {
             if (tc_ok) {
@@ -502,11 +543,25 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
             return launch_pair_chain<1>(ctx, ctx->d_pilot_keys + s0, (unsigned long long)(s1 - s0), X_dev, r_dev, n, ld,
                                         0x5eedull + (uint64_t)s0);
         };
-        if (tc_ok) STEIN_TRY(median_tc_begin(ctx, X_dev, r_dev, n, ld));
+        if (tc_ok && mode != MEDIAN_RESUME) STEIN_TRY(median_tc_begin(ctx, X_dev, r_dev, n, ld));
         // steady state of an engine: no pilot at all while the median drifts slowly (median_tc_direct_ok)
-        if (tc_ok && median_tc_direct_ok(ctx)) {
+        const bool resume_direct = mode == MEDIAN_RESUME && g_deferred_kind == 1;
+        const bool resume_pilot = mode == MEDIAN_RESUME && g_deferred_kind == 2;
+        if (resume_direct || (mode != MEDIAN_RESUME && tc_ok && median_tc_direct_ok(ctx))) {
             const PilotSpec spec = {nullptr, 0ull, 0ull, 0ull, 1};
-            const int rc = median_tc(ctx, X_dev, r_dev, n, d, ld, ranks, 0u, 0u, key, &sweeps, &spec);
+            int rc;
+            if (resume_direct) {
+                rc = median_tc_finish_deferred(ctx, key);
+                sweeps += 1;
+            } else {
+                ctx->median_defer = mode == MEDIAN_BEGIN ? 1 : 0;
+                rc = median_tc(ctx, X_dev, r_dev, n, d, ld, ranks, 0u, 0u, key, &sweeps, &spec);
+                ctx->median_defer = 0;
+                if (mode == MEDIAN_BEGIN) {
+                    g_deferred_kind = 1;
+                    return rc == 3 ? MEDIAN_DEFERRED : (rc < 0 ? rc : fail(ctx, STEIN_ERR_INTERNAL, "median not deferred"));
+                }
+            }
             if (rc < 0) return rc;
             if (rc == STEIN_OK) {
                 done[0] = done[1] = true;
@@ -515,13 +570,25 @@ int stein_median_sqdist(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
                 direct_missed = true;
             }
         }
-        if (!(done[0] && done[1])) STEIN_TRY(run_pilot());
+        if (!(done[0] && done[1]) && !resume_pilot) STEIN_TRY(run_pilot());
         // steady state with a pilot: pilot histogram, window pick and sweep chained on the device (not after a
         // pilot-less miss: the median jumped, the host-driven route below places the window from scratch)
-        if (!(done[0] && done[1]) && !direct_missed && tc_ok && median_tc_has_hint(ctx)) {
+        if (resume_pilot || (!(done[0] && done[1]) && !direct_missed && tc_ok && median_tc_has_hint(ctx))) {
             const PilotSpec spec = {ctx->d_pilot_keys + s0, (unsigned long long)(s1 - s0), pilot_m / 2 - delta,
                                     pilot_m / 2 + delta, 0};
-            const int rc = median_tc(ctx, X_dev, r_dev, n, d, ld, ranks, 0u, 0u, key, &sweeps, &spec);
+            int rc;
+            if (resume_pilot) {
+                rc = median_tc_finish_deferred(ctx, key);
+                sweeps += 1;
+            } else {
+                ctx->median_defer = mode == MEDIAN_BEGIN ? 1 : 0;
+                rc = median_tc(ctx, X_dev, r_dev, n, d, ld, ranks, 0u, 0u, key, &sweeps, &spec);
+                ctx->median_defer = 0;
+                if (mode == MEDIAN_BEGIN) {
+                    g_deferred_kind = 2;
+                    return rc == 3 ? MEDIAN_DEFERRED : (rc < 0 ? rc : fail(ctx, STEIN_ERR_INTERNAL, "median not deferred"));
+                }
+            }
             if (rc < 0) return rc;
             if (rc == STEIN_OK) done[0] = done[1] = true;
         }

@@ -1247,6 +1247,12 @@ struct MedianArena {
     const void *hint_owner = nullptr;     // the engine (stein_ctx::median_owner) the hint belongs to
     cudaEvent_t ev_tail = nullptr;        // marks the D2H copies of the device-driven tail
     bool fresh = false;                   // median_tc_begin ran and no sweep has used its counters yet
+    // deferred tail (stein_ctx::median_defer): everything is enqueued, the host part waits in median_tc_finish_deferred
+    struct Deferred {
+        bool active = false;
+        uint64_t ranks[2] = {0, 0};
+        int64_t d = 0;
+    } deferred;
     bool split_valid = false;             // Xh / Xl / scale / budget belong to the particles of the current call
 };
 
@@ -1511,6 +1517,9 @@ __global__ void set_window_kernel(uint32_t klo, uint32_t khi, uint32_t *__restri
     out[4] = 1u;
 }
 
+static SweepParams g_deferred_params;     // window words of the deferred sweep (MedianArena::deferred)
+static int median_tc_tail_host(stein_ctx *ctx, int64_t d, const uint64_t ranks[2], SweepParams *p, uint32_t keys_out[2]);
+
 // Steady-state tail of the tensor-core route (spec != NULL in median_tc): everything after the
 // sweep is chained on the device -- band thresholds (pick_band_kernel), band filter, exact
 // distances, histogram of the exact keys over a device-picked window -- and the host reads the
@@ -1530,9 +1539,11 @@ static int median_tc_device_tail(stein_ctx *ctx, const float *X, const float *r,
         A.list, A.list_cap, A.e, 0.f, 0.f, 0.f, A.counters + CNT_BELOW2, A.counters + CNT_BANDW,
         A.counters + CNT_BAND_LEN, A.band, A.band_cap, d_overflow2, A.counters + CNT_LIST_LEN, bp);
     STEIN_CHECK_LAUNCH(ctx);
+    trace_mark(ctx, "median:pick band + filter");
     // (the three global words of the filter -- below, band weight, overflow -- are only read by the host:
     //  they ride on the all-reduce of the band histogram below instead of taking one of their own)
     STEIN_TRY(launch_pair_chain<0>(ctx, A.band, A.band_cap, X, r, n, ld, 0, A.counters + CNT_BAND_LEN));
+    trace_mark(ctx, "median:exact band");
     static bool attr_set = false;
     if (!attr_set) {
         STEIN_CHECK_CUDA(ctx, cudaFuncSetAttribute(window_hist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1551,6 +1562,18 @@ static int median_tc_device_tail(stein_ctx *ctx, const float *X, const float *r,
     unsigned long long *h = A.h_pinned + HIST_MAX_BINS + 8;
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.h_pinned, A.bins, (HIST_MAX_BINS + 4) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h, A.counters, CNT_TOTAL * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    trace_mark(ctx, "median:band histogram + D2H");
+    if (ctx->median_defer) {
+        // the caller collects the result later (median_tc_finish_deferred): nothing below needs the host now
+        if (!A.ev_tail) STEIN_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&A.ev_tail, cudaEventDisableTiming));
+        STEIN_CHECK_CUDA(ctx, cudaEventRecord(A.ev_tail, ctx->stream));
+        A.deferred.active = true;
+        A.deferred.ranks[0] = ranks[0];
+        A.deferred.ranks[1] = ranks[1];
+        A.deferred.d = d;
+        g_deferred_params = *p;
+        return 3;
+    }
     if (ctx->presync_fn) {
         // the caller has bandwidth-independent work for this stream: queue it behind the copies and
         // wait for the copies only, so the GPU is busy during the host's part of the round trip
@@ -1563,6 +1586,16 @@ static int median_tc_device_tail(stein_ctx *ctx, const float *X, const float *r,
         STEIN_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
 
+    return median_tc_tail_host(ctx, d, ranks, p, keys_out);
+}
+
+// Host half of the device-driven tail: reads the counters / histogram the tail copied to pinned memory (the
+// caller has waited for the copies).  Same return values as median_tc.
+static int median_tc_tail_host(stein_ctx *ctx, int64_t d, const uint64_t ranks[2], SweepParams *p, uint32_t keys_out[2]) {
+    MedianArena &A = g_arena;
+    (void)d;
+    const int world = ctx->has_comm ? ctx->comm.world : 1;
+    unsigned long long *h = A.h_pinned + HIST_MAX_BINS + 8;
     const uint32_t *wv = reinterpret_cast<const uint32_t *>(h + CNT_WINDOW);
     if (!wv[4]) {                // the pilot ranks were not inside the histogram around the old window
         A.have_last = false;
@@ -1626,11 +1659,23 @@ int median_tc_begin(stein_ctx *ctx, const float *X, const float *r, int64_t n, i
     STEIN_CHECK_LAUNCH(ctx);
     A.fresh = true;
     A.split_valid = true;
+    trace_mark(ctx, "median:budget + max + split");
     return STEIN_OK;
 }
 void median_tc_reset(void) {
     g_arena.fresh = false;
     g_arena.split_valid = false;
+}
+bool median_tc_deferred_pending(void) { return g_arena.deferred.active; }
+void median_tc_cancel_deferred(void) { g_arena.deferred.active = false; }
+// Collects a median whose device part was enqueued with stein_ctx::median_defer set: waits for the D2H copies of
+// the tail and runs its host half.  Returns like median_tc (0 keys found, 1 / 2 take the other routes, < 0 error).
+int median_tc_finish_deferred(stein_ctx *ctx, uint32_t keys_out[2]) {
+    MedianArena &A = g_arena;
+    if (!A.deferred.active) return fail(ctx, STEIN_ERR_INTERNAL, "no deferred median to collect");
+    A.deferred.active = false;
+    STEIN_CHECK_CUDA(ctx, cudaEventSynchronize(A.ev_tail));
+    return median_tc_tail_host(ctx, A.deferred.d, A.deferred.ranks, &g_deferred_params, keys_out);
 }
 
 // Pilot keys of samples [s0, s0 + m) from the FP16 hi array (needs median_tc_begin on this X).
@@ -1826,6 +1871,7 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
         STEIN_CHECK_LAUNCH(ctx);
     }
     if (sweeps) *sweeps += 1;
+    trace_mark(ctx, "median:sweep");
     // below / listed / overflow / histogram of the listed D~ become global quantities with ONE
     // all-reduce; the list itself (and its length) stays rank-local
     if (world > 1) STEIN_TRY(allreduce_u64(ctx, A.counters, CNT_G1_END));

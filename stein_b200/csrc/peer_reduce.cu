@@ -148,7 +148,12 @@ static int peer_reduce_run(stein_ctx *ctx, void *buf, int64_t count, bool f64) {
 // and the vector fits a slot, else through the hook of stein_comm.
 int allreduce_u64(stein_ctx *ctx, void *buf_dev, int64_t count) {
     RegionTimer timer(ctx, STEIN_REGION_COLL);
-    if (ctx->peer_reduce && count <= MB_CAP) return peer_reduce_run(ctx, buf_dev, count, false);
+    if (ctx->peer_reduce && count <= MB_CAP) {
+        trace_mark(ctx, "(before all-reduce)");
+        const int rc = peer_reduce_run(ctx, buf_dev, count, false);
+        trace_mark(ctx, count == 1 ? "all-reduce:1 word" : (count > 8192 ? "all-reduce:band histogram" : "all-reduce:sweep counters"));
+        return rc;
+    }
     if (ctx->comm.allreduce_sum_u64(ctx->comm.user, buf_dev, count) != 0)
         return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_u64 hook failed");
     return STEIN_OK;
@@ -156,7 +161,12 @@ int allreduce_u64(stein_ctx *ctx, void *buf_dev, int64_t count) {
 
 int allreduce_f64(stein_ctx *ctx, void *buf_dev, int64_t count) {
     RegionTimer timer(ctx, STEIN_REGION_COLL);
-    if (ctx->peer_reduce && count <= MB_CAP) return peer_reduce_run(ctx, buf_dev, count, true);
+    if (ctx->peer_reduce && count <= MB_CAP) {
+        trace_mark(ctx, "(before all-reduce)");
+        const int rc = peer_reduce_run(ctx, buf_dev, count, true);
+        trace_mark(ctx, "all-reduce:sumsq");
+        return rc;
+    }
     if (ctx->comm.allreduce_sum_f64(ctx->comm.user, buf_dev, count) != 0)
         return fail(ctx, STEIN_ERR_COMM, "allreduce_sum_f64 hook failed");
     return STEIN_OK;

@@ -1797,6 +1797,7 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
     }
 
     RegionTimer prep_timer(ctx, STEIN_REGION_PHI_PREP);
+    trace_mark(ctx, "phi:enter");
     const float l2e = 1.4426950408889634f;
     dim3 gy((unsigned)(cols / 32), (unsigned)(DP / 32)), by(32, 8);
     // what every route of the column-scaled modes needs: the column maxima / scales of Y
@@ -1821,6 +1822,7 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
         STEIN_TRY(enqueue_colscale());
     }
     const int forced_precise = mode == 3 ? 1 : 0;
+    trace_mark(ctx, "phi:guard+colscale");
     {
         const int64_t tot = std::max<int64_t>(cols * DP / 4, cols + 256);
         if (scaled && prepared && !forced_precise) {
@@ -1901,6 +1903,7 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
         attr_set = true;
     }
     prep_timer.stop();
+    trace_mark(ctx, "phi:operands");
     {
         RegionTimer timer(ctx, STEIN_REGION_PHI);
         if (mode == 0)
@@ -1914,6 +1917,7 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
         STEIN_CHECK_LAUNCH(ctx);
     }
     RegionTimer tail_timer(ctx, STEIN_REGION_PHI_TAIL);
+    trace_mark(ctx, "phi:main");
     const int64_t rows_valid = std::max<int64_t>(0, std::min<int64_t>(n_local, n_total - row_begin));
     const int64_t total4 = rows * ld / 4;
     const int blocks = (int)std::min<int64_t>((total4 + 255) / 256, FINALIZE_MAX_BLOCKS);
@@ -1923,6 +1927,7 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
     STEIN_CHECK_LAUNCH(ctx);
     reduce_partials2_kernel<<<1, 256, 0, ctx->stream>>>(partials, blocks, sumsq);
     STEIN_CHECK_LAUNCH(ctx);
+    trace_mark(ctx, "phi:finalize");
     return STEIN_OK;
 }
 

@@ -67,7 +67,14 @@ class SvgdEngine:
 
     @property
     def particles_dev(self):
+        """View of the local particle rows (the score kernels read it).  A caller that WRITES through it calls
+        particles_changed() before the next step."""
         return self._view(self.x_ptr)
+
+    def particles_changed(self):
+        """The particle buffer was modified through particles_dev: drop what the engine derived ahead of time
+        from the old particles (the prefetched median of update_particles_host, the peers' copies of the rows)."""
+        self.ctx.check(self.lib.stein_engine_particles_changed(self.handle))
 
     @property
     def scores_dev(self):
@@ -140,6 +147,15 @@ class SvgdEngine:
             self.handle, S_host.ctypes.data_as(ctypes.c_void_p),
             X_out.ctypes.data_as(ctypes.c_void_p) if X_out is not None else None, f64))
         return X_out
+
+    def set_prefetch(self, on):
+        """update_particles_host enqueues the next iteration's median behind the particle download (default on)."""
+        self.ctx.check(self.lib.stein_engine_set_prefetch(self.handle, int(bool(on))))
+
+    def prefetch_stats(self):
+        b, u = ctypes.c_int64(), ctypes.c_int64()
+        self.ctx.check(self.lib.stein_engine_prefetch_stats(self.handle, ctypes.byref(b), ctypes.byref(u)))
+        return {"begun": b.value, "used": u.value}
 
     def phi_only(self):
         """compute_phi() on the scores in the S buffer, into the phi buffer; no optimizer step."""

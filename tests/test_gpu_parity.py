@@ -1403,3 +1403,63 @@ def test_median_pilotless_steady_state_is_bit_exact(ctx):
     ctx.lib.stein_debug_median_direct_stats(ctypes.byref(hits), ctypes.byref(miss))
     assert miss.value - miss0.value == 1
     eng.close()
+
+
+def test_update_particles_host_prefetches_the_next_median(ctx):
+    """update_particles_host enqueues the next iteration's head and median behind the optimizer kernel (they need
+    only the particles) so that they run while the particles cross PCIe.  Same bits as the plain step sequence:
+    particles after every iteration, median and bandwidth; exact against the oracle's median rule
+    (abstract_stein_sampler.py:107-127, compute_median.py:4-16); dropped when the particles are replaced."""
+    from stein_b200.engine import SvgdEngine
+    n, d, iters = 4608, 256, 8
+    X = _particles(n, d, 43)
+
+    def run(prefetch):
+        eng = SvgdEngine(n, d, "adam", learning_rate=1e-4)
+        eng.set_prefetch(prefetch)
+        eng.set_particles(X)
+        out, meds = [], []
+        Xin = X.copy()
+        for it in range(iters):
+            Xout = np.empty_like(Xin)
+            eng.update_particles_host(-Xin, Xout)
+            info = eng.last()
+            if it in (0, iters - 1) or prefetch:
+                m_ref, _ = orc.median_chain(Xin, radix=True)
+                assert np.float32(info["median"]).tobytes() == m_ref.tobytes(), (prefetch, it)
+            out.append(Xout)
+            meds.append((info["median"], info["bandwidth"], info["sweeps"]))
+            Xin = Xout
+        stats = eng.prefetch_stats()
+        return eng, out, meds, stats
+
+    eng, out_a, meds_a, stats_a = run(True)
+    assert stats_a["begun"] >= 3 and stats_a["used"] == stats_a["begun"] - 1, stats_a   # (the last one is still pending)
+    # the pending median belongs to the particles it was computed from: new particles drop it ...
+    Y = _particles(n, d, 44, 1.7)
+    eng.set_particles(Y)
+    Yout = np.empty_like(Y)
+    eng.update_particles_host(-Y, Yout)
+    m_ref, _ = orc.median_chain(Y, radix=True)
+    assert np.float32(eng.last()["median"]).tobytes() == m_ref.tobytes()
+    # ... and so does a write through the device view that is announced
+    for _ in range(3):
+        Yin = Yout
+        Yout = np.empty_like(Yin)
+        eng.update_particles_host(-Yin, Yout)
+    assert eng.prefetch_stats()["begun"] > stats_a["begun"]
+    eng.particles_dev.mul_(1.5)
+    eng.particles_changed()
+    Z = eng.get_particles(np.float32)
+    eng.set_scores(-Z)
+    eng.step()
+    m_ref, _ = orc.median_chain(Z, radix=True)
+    assert np.float32(eng.last()["median"]).tobytes() == m_ref.tobytes()
+    eng.close()
+
+    eng, out_b, meds_b, stats_b = run(False)
+    eng.close()
+    assert stats_b == {"begun": 0, "used": 0}
+    assert meds_a == meds_b
+    for a, b in zip(out_a, out_b):
+        np.testing.assert_array_equal(a, b)
