@@ -48,6 +48,8 @@ struct stein_ctx {
         int64_t n_total, n_local, d;
         int mode;
     } xprep{nullptr, nullptr, 0, 0, 0, 0};
+    // set by flash_tc2_prepare_s: the column maxima of these scores (and of the prepared X) are in the workspace
+    const void *sprep_S = nullptr, *sprep_ws = nullptr;
     // phi route guard (phi_tc.cu): device / pinned words [kappa, max centred norm^2] of the last guarded
     // phi call, the event that marks their copy, the route that call took (0 fast, 1 precise, 2 FP32
     // FFMA; -1 none yet) and the predicted error up to which a faster route is taken
@@ -102,6 +104,8 @@ int median_sqdist_resume(stein_ctx *ctx, const float *X_dev, const float *r_dev,
                          float *median_host, int32_t *sweeps_host);
 bool median_sqdist_deferred_pending(void);
 bool median_sqdist_can_defer(const stein_ctx *ctx, int64_t n, int64_t ld);
+bool median_sqdist_wants_fused_begin(const stein_ctx *ctx, int64_t n, int64_t ld);
+int median_sqdist_begin_with_norms(stein_ctx *ctx, const float *X_dev, float *r_dev, int64_t rows_r, int64_t n, int64_t ld);
 
 #define STEIN_CHECK_CUDA(ctx, expr)                                                        \
     do {                                                                                   \

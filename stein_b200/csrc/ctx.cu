@@ -282,4 +282,13 @@ int phi_prepare_x(stein_ctx *ctx, const float *X_all, int64_t n_total, int64_t d
         return flash_tc2_prepare_x(ctx, X_all, n_total, d, ld, n_local, ws, ws_bytes, impl - STEIN_PHI_FLASH_TC2);
     return STEIN_OK;
 }
+// ... and, once the scores are there, the bandwidth-independent column maxima behind the column scales of Y
+int phi_prepare_s(stein_ctx *ctx, const float *X_all, const float *S_all, int64_t n_total, int64_t d, int64_t ld,
+                  int64_t n_local, void *ws, int64_t ws_bytes) {
+    if (is_tc_ld(ld) && d < ld) d = ld;
+    const int impl = pick_phi_impl(ctx, n_local, n_total, d);
+    if (is_pair_impl(impl) && flash_tc2_supported(ctx, n_local, n_total, d))
+        return flash_tc2_prepare_s(ctx, X_all, S_all, n_total, d, ld, n_local, ws, ws_bytes, impl - STEIN_PHI_FLASH_TC2);
+    return STEIN_OK;
+}
 }  // namespace stein

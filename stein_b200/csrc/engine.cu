@@ -307,6 +307,7 @@ static int step_head(stein_engine *e) {
     stein_ctx *ctx = e->ctx;
     const int64_t rows_all = e->q * e->world;
     ctx->xprep.X = nullptr;
+    ctx->sprep_S = nullptr;
     RegionTimer head(ctx, STEIN_REGION_HEAD);
     trace_mark(ctx, "step:begin");
     if (e->world > 1) {
@@ -321,8 +322,12 @@ static int step_head(stein_engine *e) {
                 return fail(ctx, STEIN_ERR_COMM, "allgather_f32 hook failed");
         }
     }
-    // abstract_kernel.py:34 -- r = sum(T*T, 1), contract order
-    STEIN_TRY(stein_row_norms(ctx, e->X_all, rows_all, e->d, e->ld, e->r_all));
+    // abstract_kernel.py:34 -- r = sum(T*T, 1), contract order; when the tensor-core median will run on these
+    // particles, its first stage (error budgets, scale, FP16 split) comes out of the same read
+    if (e->fixed_bw <= 0.0f && median_sqdist_wants_fused_begin(ctx, e->n_total, e->ld))
+        STEIN_TRY(median_sqdist_begin_with_norms(ctx, e->X_all, e->r_all, rows_all, e->n_total, e->ld));
+    else
+        STEIN_TRY(stein_row_norms(ctx, e->X_all, rows_all, e->d, e->ld, e->r_all));
     head.stop();
     trace_mark(ctx, "head:row norms");
     if (e->fixed_bw > 0.0f) return STEIN_OK;
@@ -339,14 +344,38 @@ static int step_head(stein_engine *e) {
     return STEIN_OK;
 }
 
+// The part of the phi preparation that needs the scores but not the bandwidth (column maxima of S and of the
+// centred X), on the prep stream behind the X-side preparation, beside the median.  scores_ready: the event behind
+// which S_all is complete (NULL: the scores were written on the ctx stream).
+static int step_prepare_s(stein_engine *e, cudaEvent_t scores_ready) {
+    stein_ctx *ctx = e->ctx;
+    if (!e->prep_pending) return STEIN_OK;
+    if (scores_ready) {
+        STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(e->prep_stream, scores_ready, 0));
+    } else {
+        STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_x, ctx->stream));
+        STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(e->prep_stream, e->ev_x, 0));
+    }
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = e->prep_stream;
+    const int prc = phi_prepare_s(ctx, e->X_all, e->S_all, e->n_total, e->d, e->ld, std::max<int64_t>(e->n_local, 1),
+                                  e->ws, e->ws_bytes);
+    ctx->stream = main_stream;
+    if (prc != STEIN_OK) return prc;
+    STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_prep, e->prep_stream));
+    return STEIN_OK;
+}
+
 // Phase 1: head, exact median, bandwidth.  When the previous update_particles_host call has already enqueued the
 // head and the device part of the median for these particles (step_prefetch), only its result is collected.
-static int step_bandwidth(stein_engine *e, float *bw_out) {
+// scores_in_place: S_all is complete behind `scores_ready` (or, NULL, in ctx stream order).
+static int step_bandwidth(stein_engine *e, float *bw_out, bool scores_in_place = false, cudaEvent_t scores_ready = nullptr) {
     stein_ctx *ctx = e->ctx;
     const bool resume = e->bw_pending && median_sqdist_deferred_pending();
     e->bw_pending = false;
     if (resume) e->prefetch_used += 1;
     if (!resume) STEIN_TRY(step_head(e));
+    if (scores_in_place) STEIN_TRY(step_prepare_s(e, scores_ready));
     if (e->fixed_bw > 0.0f) {
         e->last_med = nanf("");
         e->last_bw = e->fixed_bw;
@@ -484,7 +513,7 @@ int stein_engine_step(stein_engine *e) {
         STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_scores, e->copy_stream));
     }
     float bw = 0.f;
-    const int rc = step_bandwidth(e, &bw);
+    const int rc = step_bandwidth(e, &bw, gathered || e->world == 1, gathered ? e->ev_scores : nullptr);
     if (gathered) STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e->ev_scores, 0));
     if (rc != STEIN_OK) return rc;
     return step_update(e, bw, gathered);
@@ -505,7 +534,7 @@ int stein_engine_update_particles_host(stein_engine *e, const void *S_host, void
     STEIN_TRY(gather_scores_async(e, &gathered));
     STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_scores, e->copy_stream));
     float bw = 0.f;
-    const int rc = step_bandwidth(e, &bw);
+    const int rc = step_bandwidth(e, &bw, gathered || e->world == 1, e->ev_scores);
     STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e->ev_scores, 0));
     if (rc != STEIN_OK) return rc;
     STEIN_TRY(step_update(e, bw, gathered));
@@ -547,7 +576,7 @@ int stein_engine_phi_only(stein_engine *e) {
     stein_ctx *ctx = e->ctx;
     STEIN_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
     float bw = 0.f;
-    STEIN_TRY(step_bandwidth(e, &bw));
+    STEIN_TRY(step_bandwidth(e, &bw, e->world == 1, nullptr));
     return step_phi(e, bw, false);
 }
 

@@ -311,6 +311,7 @@ void median_tc_cancel_deferred(void);
 int median_tc_finish_deferred(stein_ctx *ctx, uint32_t keys_out[2]);
 int median_tc_begin(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t ld);
 void median_tc_reset(void);
+bool median_tc_take_begun(const float *X);
 int median_tc_pilot(stein_ctx *ctx, uint32_t *keys_dev, unsigned long long m, const float *r, int64_t n, int64_t ld,
                     uint64_t seed);
 int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t d, int64_t ld,
@@ -454,6 +455,15 @@ int median_sqdist_resume(stein_ctx *ctx, const float *X_dev, const float *r_dev,
     return median_sqdist_impl(ctx, X_dev, r_dev, n, d, ld, median_host, nullptr, sweeps_host, MEDIAN_RESUME);
 }
 bool median_sqdist_deferred_pending(void) { return median_tc_deferred_pending(); }
+int median_tc_begin_with_norms(stein_ctx *ctx, const float *X, float *r, int64_t rows_r, int64_t n, int64_t ld);
+// Row norms of `rows_r` rows and, when the tensor-core median route will take these particles, its first stage
+// (error budgets, scale, FP16 split) from the same read.  Returns false if only the norms are needed.
+bool median_sqdist_wants_fused_begin(const stein_ctx *ctx, int64_t n, int64_t ld) {
+    return (uint64_t)n * (uint64_t)n >= (1ull << 24) && ctx->median_impl != STEIN_MEDIAN_FFMA && median_tc_supported(n, ld);
+}
+int median_sqdist_begin_with_norms(stein_ctx *ctx, const float *X_dev, float *r_dev, int64_t rows_r, int64_t n, int64_t ld) {
+    return median_tc_begin_with_norms(ctx, X_dev, r_dev, rows_r, n, ld);
+}
 // which route a deferred median took: 1 pilot-less (window recentred on the last exact median), 2 pilot sample +
 // device-picked window around the last one
 static int g_deferred_kind = 0;
@@ -531,7 +541,9 @@ static int median_sqdist_impl(stein_ctx *ctx, const float *X_dev, const float *r
         const int pw = ctx->has_comm ? ctx->comm.world : 1, pr = ctx->has_comm ? ctx->comm.rank : 0;
         const int64_t s0 = pilot_m * pr / pw, s1 = pilot_m * (pr + 1) / pw;
         const bool tc_ok = ctx->median_impl != STEIN_MEDIAN_FFMA && median_tc_supported(n, ld);
-        if (mode != MEDIAN_RESUME) median_tc_reset();
+        // (the engine may have run the first stage together with the row norms: median_tc_begin_with_norms)
+        const bool begun = mode != MEDIAN_RESUME && tc_ok && median_tc_take_begun(X_dev);
+        if (mode != MEDIAN_RESUME && !begun) median_tc_reset();
         const uint64_t delta = (uint64_t)(3.5 * sqrt((double)pilot_m));
         auto run_pilot = [&]() -> int {
             if (tc_ok) {
@@ -543,7 +555,7 @@ static int median_sqdist_impl(stein_ctx *ctx, const float *X_dev, const float *r
             return launch_pair_chain<1>(ctx, ctx->d_pilot_keys + s0, (unsigned long long)(s1 - s0), X_dev, r_dev, n, ld,
                                         0x5eedull + (uint64_t)s0);
         };
-        if (tc_ok && mode != MEDIAN_RESUME) STEIN_TRY(median_tc_begin(ctx, X_dev, r_dev, n, ld));
+        if (tc_ok && mode != MEDIAN_RESUME && !begun) STEIN_TRY(median_tc_begin(ctx, X_dev, r_dev, n, ld));
         // steady state of an engine: no pilot at all while the median drifts slowly (median_tc_direct_ok)
         const bool resume_direct = mode == MEDIAN_RESUME && g_deferred_kind == 1;
         const bool resume_pilot = mode == MEDIAN_RESUME && g_deferred_kind == 2;

@@ -846,6 +846,73 @@ err_budget_kernel(const float *__restrict__ X, int64_t rows, int64_t n, int64_t 
     if (lane == 0) e[row] = acc * 1.001f;      // the fp32 evaluation of the budget itself
 }
 
+// Row norms (contract order: one fp32 fma chain per row, abstract_kernel.py:34 as oracle/svgd_oracle.c defines it)
+// AND the error budgets of err_budget_kernel from ONE read of the particles: a block stages 32 rows x 256
+// coordinates in shared memory (coalesced), warp 0 walks the 32 chains (lane = row), warps 1..7 take the budgets
+// with err_budget_kernel's own lane / order assignment, so both results have the bits of the separate kernels.
+constexpr int XS_ROWS = 32, XS_COLS = 256;
+__global__ void __launch_bounds__(256)
+x_stats_kernel(const float *__restrict__ X, int64_t rows_r, int64_t rows_e, int64_t n, int64_t ld,
+               float *__restrict__ r, float *__restrict__ e) {
+    __shared__ float tile[XS_ROWS][XS_COLS + 1];
+    const int64_t row0 = (int64_t)blockIdx.x * XS_ROWS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = (int)(ld / 64);
+    float chain = 0.0f;
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int64_t c0 = 0; c0 < ld; c0 += XS_COLS) {
+        const int width = (int)min((int64_t)XS_COLS, ld - c0), w4 = width / 4;
+        for (int idx = threadIdx.x; idx < XS_ROWS * w4; idx += 256) {
+            const int rr = idx / w4, c4 = idx - rr * w4;
+            const int64_t row = row0 + rr;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < rows_r) v = *reinterpret_cast<const float4 *>(X + row * ld + c0 + 4 * c4);
+            tile[rr][4 * c4 + 0] = v.x;
+            tile[rr][4 * c4 + 1] = v.y;
+            tile[rr][4 * c4 + 2] = v.z;
+            tile[rr][4 * c4 + 3] = v.w;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int k = 0; k < width; ++k) {
+                const float x = tile[lane][k];
+                chain = __fmaf_rn(x, x, chain);
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 5; ++a) {
+                const int rr = warp - 1 + 7 * a;
+                if (rr >= XS_ROWS) break;
+                float v = acc[a];
+                for (int k = lane; k < width; k += 32) {
+                    const int64_t m = c0 + k;
+                    const float x = tile[rr][k];
+                    const float w = 5.9664e-08f * (float)(ld - m + 1)
+                                    + 2.38418579e-07f * 12.0f * (float)(nkb - (int)(m >> 6))
+                                    + 1.90734863e-06f;
+                    v = fmaf(w * x, x, v);
+                }
+                acc[a] = v;
+            }
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {
+        if (row0 + lane < rows_r) r[row0 + lane] = chain;
+    } else {
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            const int rr = warp - 1 + 7 * a;
+            if (rr >= XS_ROWS) break;
+            float v = acc[a];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            const int64_t row = row0 + rr;
+            if (lane == 0 && row < rows_e) e[row] = row < n ? v * 1.001f : 0.0f;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(1024)
 max_kernel(const float *__restrict__ r, const float *__restrict__ e, int64_t n, float *__restrict__ out,
            float *__restrict__ emax_out, float *__restrict__ scale_out) {
@@ -1241,7 +1308,7 @@ struct MedianArena {
     bool have_last = false;
     // pilot-less steady state: half-width (keys) of the last pilot-derived window, the exact median key of the
     // last two iterations, and how many iterations to stay on the pilot after a miss
-    uint32_t last_half = 0u, med_key = 0u, prev_med_key = 0u;
+    uint32_t last_half = 0u, med_key = 0u, prev_med_key = 0u, prev2_med_key = 0u;
     int med_keys_known = 0, direct_cooldown = 0;
     long long direct_hits = 0, direct_misses = 0;      // statistics (stein_debug_median_direct_stats)
     const void *hint_owner = nullptr;     // the engine (stein_ctx::median_owner) the hint belongs to
@@ -1254,6 +1321,7 @@ struct MedianArena {
         int64_t d = 0;
     } deferred;
     bool split_valid = false;             // Xh / Xl / scale / budget belong to the particles of the current call
+    const float *begun_X = nullptr;       // median_tc_begin_with_norms ran on these particles (median_tc_take_begun)
 };
 
 // counters block (u64 slots).  Slots [0, CNT_G1_END) are global quantities after the sweep (one
@@ -1473,21 +1541,30 @@ bool median_tc_supported(int64_t n, int64_t ld) {
 // returns STEIN_OK with keys filled, 1 = "not bracketed, use the FFMA route", <0 = error
 bool median_tc_has_hint(const stein_ctx *ctx) { return hint_usable(ctx); }
 
-// Successive SVGD iterations move the median by a small fraction of the pilot window (which is +-3.5 sigma of
-// a 2^20-pair sample quantile wide).  While the last step moved it by less than an eighth of the window's
-// half-width, the next window is simply the last one recentred on the last EXACT median: no pilot sample, no
+// Successive SVGD iterations move the median smoothly: by a small fraction of the pilot window (which is +-3.5
+// sigma of a 2^20-pair sample quantile wide), or -- early in a run, while the cloud contracts or expands -- by a
+// larger but steady amount per step.  The next window is therefore the last one recentred on the EXTRAPOLATED
+// exact median, last + (last - previous), as long as that prediction was good for the last step: the second
+// difference of the last three exact medians is below an eighth of the window's half-width.  No pilot sample, no
 // pilot histogram, no all-reduce of it.  Every consumer of the window still checks that the rank is bracketed;
 // a miss falls back to the pilot route and keeps it for a few iterations.
+static int64_t direct_step(const MedianArena &A) { return (int64_t)A.med_key - (int64_t)A.prev_med_key; }
+static uint32_t direct_center(const MedianArena &A) {
+    const int64_t c = (int64_t)A.med_key + direct_step(A);
+    return (uint32_t)std::min<int64_t>(std::max<int64_t>(c, 0), 0xffffffffll);
+}
 bool median_tc_direct_ok(const stein_ctx *ctx) {
     const MedianArena &A = g_arena;
     if (getenv("STEIN_MEDIAN_DEBUG"))
-        fprintf(stderr, "[stein] direct_ok: hint %d known %d half %u cooldown %d keys %u %u\n", (int)hint_usable(ctx),
-                A.med_keys_known, A.last_half, A.direct_cooldown, A.med_key, A.prev_med_key);
-    if (!hint_usable(ctx) || A.med_keys_known < 2 || A.last_half == 0u || A.direct_cooldown > 0) return false;
+        fprintf(stderr, "[stein] direct_ok: hint %d known %d half %u cooldown %d keys %u %u %u\n", (int)hint_usable(ctx),
+                A.med_keys_known, A.last_half, A.direct_cooldown, A.med_key, A.prev_med_key, A.prev2_med_key);
+    if (!hint_usable(ctx) || A.med_keys_known < 3 || A.last_half == 0u || A.direct_cooldown > 0) return false;
     if (const char *e = getenv("STEIN_MEDIAN_PILOTLESS"))
         if (e[0] == '0') return false;
-    const uint32_t drift = A.med_key > A.prev_med_key ? A.med_key - A.prev_med_key : A.prev_med_key - A.med_key;
-    return (uint64_t)drift * 8u < A.last_half;
+    const int64_t prev_step = (int64_t)A.prev_med_key - (int64_t)A.prev2_med_key;
+    const uint64_t second = (uint64_t)std::llabs(direct_step(A) - prev_step);
+    // (a step of many window widths is not a slow drift, however steady)
+    return second * 8u < A.last_half && (uint64_t)std::llabs(direct_step(A)) < 4ull * A.last_half;
 }
 void median_tc_count_direct_hit(void) { ++g_arena.direct_hits; }
 // bookkeeping after a median call of an engine sequence (keys of the two middle values)
@@ -1497,9 +1574,10 @@ void median_tc_note_result(const stein_ctx *ctx, uint32_t k0, uint32_t k1, bool 
         A.med_keys_known = 0;
         return;
     }
+    A.prev2_med_key = A.prev_med_key;
     A.prev_med_key = A.med_key;
     A.med_key = (uint32_t)(((uint64_t)k0 + k1) / 2);
-    A.med_keys_known = std::min(A.med_keys_known + 1, 2);
+    A.med_keys_known = std::min(A.med_keys_known + 1, 3);
     if (direct_missed) {
         A.direct_cooldown = 8;
         ++A.direct_misses;
@@ -1665,6 +1743,40 @@ int median_tc_begin(stein_ctx *ctx, const float *X, const float *r, int64_t n, i
 void median_tc_reset(void) {
     g_arena.fresh = false;
     g_arena.split_valid = false;
+    g_arena.begun_X = nullptr;
+}
+// median_tc_begin that also produces the row norms (stein_row_norms' bits) for `rows_r` rows of X: one read of the
+// particles instead of two (engine.cu, start of an iteration).  The next median call on the same X finds its first
+// stage done (median_tc_take_begun).
+int median_tc_begin_with_norms(stein_ctx *ctx, const float *X, float *r, int64_t rows_r, int64_t n, int64_t ld) {
+    const int64_t rows = stein_rows_padded(n), T = (n + TILE - 1) / TILE;
+    const uint64_t pairs = (uint64_t)T * (T + 1) / 2 * TILE * TILE;
+    STEIN_TRY(ensure_arena(ctx, rows, ld, pairs));
+    MedianArena &A = g_arena;
+    median_tc_reset();
+    A.deferred.active = false;
+    STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(A.counters, 0, CNT_TOTAL * 8, ctx->stream));
+    float *d_scale = reinterpret_cast<float *>(A.counters + CNT_SCALE);
+    const int64_t rows_k = std::max(rows_r, rows);
+    x_stats_kernel<<<(unsigned)((rows_k + XS_ROWS - 1) / XS_ROWS), 256, 0, ctx->stream>>>(X, rows_r, rows, n, ld, r, A.e);
+    STEIN_CHECK_LAUNCH(ctx);
+    max_kernel<<<1, 1024, 0, ctx->stream>>>(r, A.e, n, reinterpret_cast<float *>(A.counters + CNT_RMAX),
+                                           reinterpret_cast<float *>(A.counters + CNT_EMAX), d_scale);
+    STEIN_CHECK_LAUNCH(ctx);
+    const int64_t count4 = rows * ld / 4;
+    split_f16_kernel<<<(unsigned)((count4 + 255) / 256), 256, 0, ctx->stream>>>(X, count4, d_scale, A.Xh, A.Xl);
+    STEIN_CHECK_LAUNCH(ctx);
+    A.fresh = true;
+    A.split_valid = true;
+    A.begun_X = X;
+    trace_mark(ctx, "head:norms + budget + max + split");
+    return STEIN_OK;
+}
+// true (once) when median_tc_begin_with_norms ran on exactly these particles and nothing has used the arena since
+bool median_tc_take_begun(const float *X) {
+    const bool hit = g_arena.begun_X != nullptr && g_arena.begun_X == X && g_arena.fresh;
+    g_arena.begun_X = nullptr;
+    return hit;
 }
 bool median_tc_deferred_pending(void) { return g_arena.deferred.active; }
 void median_tc_cancel_deferred(void) { g_arena.deferred.active = false; }
@@ -1736,8 +1848,8 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
     int *d_overflow2 = reinterpret_cast<int *>(A.counters + CNT_OVERFLOW2);
 
     if (spec && spec->direct) {
-        // pilot-less: the last window, recentred on the last exact median
-        const uint32_t c = A.med_key, half = A.last_half;
+        // pilot-less: the last window, recentred on the extrapolated exact median
+        const uint32_t c = direct_center(A), half = A.last_half;
         set_window_kernel<<<1, 1, 0, ctx->stream>>>(c > half ? c - half : 0u, c < 0xffffffffu - half ? c + half : 0xffffffffu,
                                                    reinterpret_cast<uint32_t *>(A.counters + CNT_WINDOW));
         STEIN_CHECK_LAUNCH(ctx);

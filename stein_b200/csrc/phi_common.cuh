@@ -40,6 +40,8 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
 // the bandwidth-independent kernels of phi_flash_tc2, enqueued ahead of the call (ctx->xprep)
 int flash_tc2_prepare_x(stein_ctx *ctx, const float *X_all, int64_t n_total, int64_t d, int64_t ld,
                         int64_t n_local, void *ws, int64_t ws_bytes, int mode);
+int flash_tc2_prepare_s(stein_ctx *ctx, const float *X_all, const float *S_all, int64_t n_total, int64_t d, int64_t ld,
+                        int64_t n_local, void *ws, int64_t ws_bytes, int mode);
 // panel kernels (phi_panel.cuh): leading dimension 512 / 768 / 1024.  mode 2 fast, 3 precise, 4 guarded
 namespace panel {
 bool panel_supported(const stein_ctx *ctx, int64_t n_total, int64_t ld);
@@ -51,5 +53,7 @@ int phi_panel(stein_ctx *ctx, const float *X_all, const float *S_all, const floa
 // what stein_phi would run for this problem: prepares its X side if that kernel supports it (ctx.cu)
 int phi_prepare_x(stein_ctx *ctx, const float *X_all, int64_t n_total, int64_t d, int64_t ld, int64_t n_local,
                   void *ws, int64_t ws_bytes);
+int phi_prepare_s(stein_ctx *ctx, const float *X_all, const float *S_all, int64_t n_total, int64_t d, int64_t ld,
+                  int64_t n_local, void *ws, int64_t ws_bytes);
 
 }  // namespace stein

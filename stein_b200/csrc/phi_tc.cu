@@ -1131,6 +1131,54 @@ colmax_partial_kernel(const float *__restrict__ X, const float *__restrict__ S, 
         part[(int64_t)blockIdx.x * ld + c] = fmaxf(m0, m1);
     }
 }
+// The same scale from bandwidth-INDEPENDENT column maxima: max |y_c| <= max |s_c| + max |x_c| / h2.  A power-of-two
+// scale only has to keep the column inside the FP16 / E5M2 range (the bound is at most 2x the true maximum: one
+// binade of headroom), so the two maxima can be taken ahead of the bandwidth, beside the median
+// (flash_tc2_prepare_s), and combined by colscale_sx_kernel once h is known.
+__global__ void __launch_bounds__(256)
+colmax_sx_partial_kernel(const float *__restrict__ X, const float *__restrict__ S, int64_t n, int64_t ld,
+                         float *__restrict__ partS /* [CM_BLOCKS][ld] */, float *__restrict__ partX) {
+    for (int64_t c = threadIdx.x; c < ld; c += blockDim.x) {
+        float s0 = 0.0f, s1 = 0.0f, x0 = 0.0f, x1 = 0.0f;
+        int64_t i = blockIdx.x;
+        for (; i + CM_BLOCKS < n; i += 2 * CM_BLOCKS) {
+            s0 = fmaxf(s0, fabsf(S[i * ld + c]));
+            x0 = fmaxf(x0, fabsf(X[i * ld + c]));
+            s1 = fmaxf(s1, fabsf(S[(i + CM_BLOCKS) * ld + c]));
+            x1 = fmaxf(x1, fabsf(X[(i + CM_BLOCKS) * ld + c]));
+        }
+        if (i < n) {
+            s0 = fmaxf(s0, fabsf(S[i * ld + c]));
+            x0 = fmaxf(x0, fabsf(X[i * ld + c]));
+        }
+        partS[(int64_t)blockIdx.x * ld + c] = fmaxf(s0, s1);
+        partX[(int64_t)blockIdx.x * ld + c] = fmaxf(x0, x1);
+    }
+}
+__global__ void __launch_bounds__(256)
+colscale_sx_kernel(const float *__restrict__ partS, const float *__restrict__ partX, int64_t ld, float inv_h2,
+                   float *__restrict__ down, float *__restrict__ up) {
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per column
+    const int lane = threadIdx.x & 31;
+    if (c >= ld) return;
+    float ms = 0.0f, mx = 0.0f;
+    for (int b = lane; b < CM_BLOCKS; b += 32) {
+        ms = fmaxf(ms, partS[(int64_t)b * ld + c]);
+        mx = fmaxf(mx, partX[(int64_t)b * ld + c]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane != 0) return;
+    const float m = ms + mx * inv_h2;
+    int e = 0;
+    if (m > 0.0f && m < INFINITY) e = ilogbf(m) - 7;        // m 2^-e in [128, 256)
+    e = max(-100, min(100, e));
+    down[c] = ldexpf(1.0f, -e);
+    up[c] = ldexpf(1.0f, e);
+}
 __global__ void __launch_bounds__(256)
 colscale_kernel(const float *__restrict__ part, int64_t ld, float *__restrict__ down, float *__restrict__ up) {
     const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per column
@@ -1504,7 +1552,7 @@ int64_t flash_tc_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t 
     b += p1.cols * p1.DP * 2 * 4;                       // Xh, Xl, YTh, YTl (bf16)
     b += (p1.cols + 256) * 4;                           // nrm
     b += centred_bytes(p1.cols, p1.DP);                 // centred particles, their norms, column means
-    b += ((int64_t)CM_BLOCKS + 2) * p1.DP * 4 + 64;     // column maxima / scales of Y (mixed-precision GEMM2)
+    b += ((int64_t)2 * CM_BLOCKS + 2) * p1.DP * 4 + 64; // column maxima (of S, of X) / scales of Y (mixed-precision GEMM2)
     b += p1.cols * p1.DP * 2 + 64;                      // b8h, b8l of X (mixed-precision GEMM1)
     b += std::max(slot_bytes(p1), slot_bytes(p2));
     b += FINALIZE_MAX_BLOCKS * 8;
@@ -1739,7 +1787,10 @@ bool flash_tc2_supported(const stein_ctx *ctx, int64_t n_local, int64_t n_total,
 // that in ctx->xprep; the next full call on the same (X, workspace, shape, mode) skips them.
 static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all, const float *r_all, int64_t n_total,
                          int64_t d, int64_t d_true, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
-                         int64_t ws_bytes, float *phi, double *sumsq, int mode, bool only_prepare) {
+                         int64_t ws_bytes, float *phi, double *sumsq, int mode, int stage) {
+    // stage 0: the whole call; 1: only what needs neither the bandwidth nor the scores (flash_tc2_prepare_x);
+    // 2: only the column maxima of S and of the centred X (flash_tc2_prepare_s, after stage 1 on the same problem)
+    const bool only_prepare = stage == 1;
     // mode 0: BF16x3 for both GEMMs; 1: mixed-precision GEMM2; 2: mixed precision for both (fast);
     // 3: three FP16 passes for both (precise); 4: fast / precise / FP32 FFMA, picked by the conditioning guard
     const bool autoroute = mode == 4;
@@ -1767,12 +1818,20 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
     int *d_tile_nslots = nullptr;
     // the bandwidth-independent part (centring, global scale of X) may already have been enqueued
     // by flash_prepare_x while the host waited for the median
-    const bool prepared = !only_prepare && xprep_consume(ctx, X_all, ws, n_total, n_local, d, mode_in);
+    if (stage == 2) {
+        const stein_ctx::XPrep &x = ctx->xprep;
+        if (!(ycols && x.X == X_all && x.ws == ws && x.n_total == n_total && x.n_local == n_local && x.d == d &&
+              x.mode == mode_in))
+            return STEIN_OK;         // nothing prepared for this problem: the full call takes the maxima itself
+    }
+    const bool prepared = stage == 2 || (!only_prepare && xprep_consume(ctx, X_all, ws, n_total, n_local, d, mode_in));
+    const bool smax_ready = stage == 0 && prepared && ctx->sprep_S == S_all && ctx->sprep_ws == ws;
+    if (stage == 0) ctx->sprep_S = nullptr;
     Centred cen{};
     STEIN_TRY(make_centred(ctx, X_all, n_total, d, cols, ld, pws, &cen, !prepared));
     const float *Xc = cen.Xc, *rc = cen.rc;
     pws = (char *)(((uintptr_t)pws + 15) & ~(uintptr_t)15);
-    float *cmax_part = (float *)pws;     pws += (int64_t)CM_BLOCKS * DP * 4;
+    float *cmax_part = (float *)pws;     pws += (int64_t)2 * CM_BLOCKS * DP * 4;     // of S, then of Xc
     float *cs_down = (float *)pws;       pws += DP * 4;
     float *cs_up = (float *)pws;         pws += DP * 4;
     float *xscale = (float *)pws;        pws += 16;       // [0] = 2^-e on X, [1] = 2^(2e) on c1
@@ -1781,6 +1840,14 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
     if (scaled && !prepared) {
         xscale_kernel<<<1, 1024, 0, ctx->stream>>>(cen.blockmax, cen.nblockmax, xscale);
         STEIN_CHECK_LAUNCH(ctx);
+    }
+    if (stage == 2) {
+        colmax_sx_partial_kernel<<<CM_BLOCKS, 256, 0, ctx->stream>>>(cen.Xc, S_all, n_total, ld, cmax_part,
+                                                                    cmax_part + (int64_t)CM_BLOCKS * DP);
+        STEIN_CHECK_LAUNCH(ctx);
+        ctx->sprep_S = S_all;
+        ctx->sprep_ws = ws;
+        return STEIN_OK;
     }
     if (only_prepare) {
         // ahead of the bandwidth: also the X operand arrays, in the FAST format (what the guard picks for every
@@ -1802,9 +1869,13 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
     dim3 gy((unsigned)(cols / 32), (unsigned)(DP / 32)), by(32, 8);
     // what every route of the column-scaled modes needs: the column maxima / scales of Y
     auto enqueue_colscale = [&]() -> int {
-        colmax_partial_kernel<<<CM_BLOCKS, 256, 0, ctx->stream>>>(Xc, S_all, n_total, ld, 1.0f / h2, cmax_part);
-        STEIN_CHECK_LAUNCH(ctx);
-        colscale_kernel<<<(unsigned)((DP * 32 + 255) / 256), 256, 0, ctx->stream>>>(cmax_part, DP, cs_down, cs_up);
+        if (!smax_ready) {
+            colmax_sx_partial_kernel<<<CM_BLOCKS, 256, 0, ctx->stream>>>(Xc, S_all, n_total, ld, cmax_part,
+                                                                        cmax_part + (int64_t)CM_BLOCKS * DP);
+            STEIN_CHECK_LAUNCH(ctx);
+        }
+        colscale_sx_kernel<<<(unsigned)((DP * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+            cmax_part, cmax_part + (int64_t)CM_BLOCKS * DP, DP, 1.0f / h2, cs_down, cs_up);
         STEIN_CHECK_LAUNCH(ctx);
         return STEIN_OK;
     };
@@ -1935,13 +2006,21 @@ int phi_flash_tc2(stein_ctx *ctx, const float *X_all, const float *S_all, const 
                   int64_t d, int64_t d_true, int64_t ld, int64_t row_begin, int64_t n_local, float h2, void *ws,
                   int64_t ws_bytes, float *phi, double *sumsq, int mode) {
     return flash_tc2_run(ctx, X_all, S_all, r_all, n_total, d, d_true, ld, row_begin, n_local, h2, ws, ws_bytes, phi,
-                         sumsq, mode, false);
+                         sumsq, mode, 0);
 }
 
 int flash_tc2_prepare_x(stein_ctx *ctx, const float *X_all, int64_t n_total, int64_t d, int64_t ld,
                         int64_t n_local, void *ws, int64_t ws_bytes, int mode) {
     return flash_tc2_run(ctx, X_all, nullptr, nullptr, n_total, d, d, ld, 0, n_local, 1.0f, ws, ws_bytes, nullptr,
-                         nullptr, mode, true);
+                         nullptr, mode, 1);
+}
+
+// After flash_tc2_prepare_x on the same problem, once the scores are in S_all: the bandwidth-independent column
+// maxima behind the column scales of Y.  A no-op when nothing was prepared.
+int flash_tc2_prepare_s(stein_ctx *ctx, const float *X_all, const float *S_all, int64_t n_total, int64_t d, int64_t ld,
+                        int64_t n_local, void *ws, int64_t ws_bytes, int mode) {
+    return flash_tc2_run(ctx, X_all, S_all, nullptr, n_total, d, d, ld, 0, n_local, 1.0f, ws, ws_bytes, nullptr,
+                         nullptr, mode, 2);
 }
 
 }  // namespace stein
