@@ -517,10 +517,67 @@ static int64_t num_pair_tiles(int64_t T) {
     return nt;
 }
 
+// Tile ranges of the clusters of one launch (pair tile indices; n + 1 entries, n = 0: the even split of
+// [t_begin, t_end)).  A cluster pays for every pair row it enters (its A operand: 2 x 128 rows x ld, loaded behind
+// a drained MMA pipeline) about as much as for a tile, and the rows at the bottom of the triangle are short: an even
+// split of the TILES leaves the last cluster with dozens of row changes while all others wait for it (and, sharded,
+// the last rank).  sweep_chunk_bounds cuts the tile sequence into world x clusters chunks of equal COST
+// (tiles + beta per row entered), the same cut on every rank; rank r owns chunks [r clusters, (r + 1) clusters).
+constexpr int SW2_MAX_CLUSTERS = 80;
+struct SweepBounds {
+    int n;
+    int b[SW2_MAX_CLUSTERS + 1];
+};
+static std::vector<long long> sweep_chunk_bounds(int64_t T, int parts, double beta) {
+    const int64_t R = (T + 1) / 2, NT = num_pair_tiles(T);
+    auto cut = [&](double C, std::vector<long long> *out) -> int {
+        int chunks = 0;
+        long long pos = 0;
+        double cost = 0.0;
+        if (out) out->assign(1, 0);
+        for (int64_t i = 0; i < R; ++i) {
+            long long rem = T - 2 * i;
+            while (rem > 0) {
+                if (cost > 0.0 && cost + beta + 1.0 > C) {      // no room for this row's operand and one tile
+                    ++chunks;
+                    if (out) out->push_back(pos);
+                    cost = 0.0;
+                }
+                cost += beta;
+                const long long room = std::max<long long>(1, (long long)std::floor(C - cost));
+                const long long take = std::min(rem, room);
+                cost += (double)take;
+                rem -= take;
+                pos += take;
+                if (rem > 0) {                                   // chunk full in the middle of the row
+                    ++chunks;
+                    if (out) out->push_back(pos);
+                    cost = 0.0;
+                }
+            }
+        }
+        if (cost > 0.0) {
+            ++chunks;
+            if (out) out->push_back(pos);
+        }
+        return chunks;
+    };
+    double lo = 1.0 + beta, hi = (double)NT + beta * (double)R + 1.0;
+    for (int it = 0; it < 60 && hi - lo > 1e-3; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (cut(mid, nullptr) <= parts) hi = mid;
+        else lo = mid;
+    }
+    std::vector<long long> b;
+    cut(hi, &b);
+    while ((int)b.size() < parts + 1) b.push_back(NT);          // (fewer chunks than parts: empty ones at the end)
+    return b;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SW2_THREADS, 1)
 sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
                  const __grid_constant__ CUtensorMap mapXh64, const __grid_constant__ CUtensorMap mapXl64,
-                 const SweepParams p) {
+                 const SweepParams p, const __grid_constant__ SweepBounds bnd) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *sA = smem;                                              // A hi: SW2_KB x 16 KB
@@ -535,8 +592,8 @@ sweep2_tc_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constan
     const bool leader = rank == 0;
     const long long NT = p.t_end - p.t_begin;
     const int ncl = (int)gridDim.x / 2, cl = (int)blockIdx.x / 2;
-    const long long my0 = p.t_begin + NT * cl / ncl;
-    const long long my1 = p.t_begin + NT * (cl + 1) / ncl;
+    const long long my0 = bnd.n ? (long long)bnd.b[cl] : p.t_begin + NT * cl / ncl;
+    const long long my1 = bnd.n ? (long long)bnd.b[cl + 1] : p.t_begin + NT * (cl + 1) / ncl;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < SW2_STAGES; ++s) {
@@ -1836,7 +1893,31 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
                 if ((wj + 1) * win_b - 1 >= wi * win_a) wins.push_back(make_int2((int)wi, (int)wj));   // touches tj >= ti
     }
     const int64_t ntiles = wide ? (int64_t)wins.size() : (pair ? num_pair_tiles(T) : T * (T + 1) / 2);
-    const int64_t t0 = ntiles * rank / world, t1 = ntiles * (rank + 1) / world;
+    int64_t t0 = ntiles * rank / world, t1 = ntiles * (rank + 1) / world;
+    // CTA-pair sweep: cost-balanced chunks (sweep_chunk_bounds), cached per shape
+    SweepBounds bnd;
+    bnd.n = 0;
+    const int ncl_full = ctx->num_sms / 2;
+    if (pair && ncl_full <= SW2_MAX_CLUSTERS && ntiles >= 4ll * world * ncl_full && ntiles < (1ll << 31)) {
+        static std::vector<long long> cached;
+        static int64_t c_T = -1;
+        static int c_parts = -1;
+        static double c_beta = -1.0;
+        double beta = 1.5;      // measured at config D: 0 (even tile split) 2.53-2.59 ms, 1-2: 2.45 ms, 3: 2.49 ms
+        if (const char *env = getenv("STEIN_SWEEP_BETA")) beta = atof(env);
+        if (beta > 0.0) {
+            if (c_T != T || c_parts != world * ncl_full || c_beta != beta) {
+                cached = sweep_chunk_bounds(T, world * ncl_full, beta);
+                c_T = T;
+                c_parts = world * ncl_full;
+                c_beta = beta;
+            }
+            bnd.n = ncl_full;
+            for (int c = 0; c <= ncl_full; ++c) bnd.b[c] = (int)cached[(size_t)rank * ncl_full + c];
+            t0 = bnd.b[0];
+            t1 = bnd.b[ncl_full];
+        }
+    }
 
     // counters zeroed, largest row norm, scale, FP16 split: already there when the caller ran
     // median_tc_begin for its pilot and this is the first sweep since
@@ -1974,8 +2055,8 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
             CUtensorMap mapXh64, mapXl64;
             STEIN_TRY(make_tensor_map_2d(ctx, &mapXh64, A.Xh, 2, (uint64_t)DP, (uint64_t)rows, (uint64_t)DP * 2, 64));
             STEIN_TRY(make_tensor_map_2d(ctx, &mapXl64, A.Xl, 2, (uint64_t)DP, (uint64_t)rows, (uint64_t)DP * 2, 64));
-            const int clusters = (int)std::min<int64_t>(ctx->num_sms / 2, t1 - t0);
-            sweep2_tc_kernel<<<2 * clusters, SW2_THREADS, smem2, ctx->stream>>>(mapXh, mapXl, mapXh64, mapXl64, p);
+            const int clusters = bnd.n ? bnd.n : (int)std::min<int64_t>(ctx->num_sms / 2, t1 - t0);
+            sweep2_tc_kernel<<<2 * clusters, SW2_THREADS, smem2, ctx->stream>>>(mapXh, mapXl, mapXh64, mapXl64, p, bnd);
         } else {
             const int grid = (int)std::min<int64_t>(ctx->num_sms, t1 - t0);
             sweep_tc_kernel<<<grid, SW_THREADS, smem1, ctx->stream>>>(mapXh, mapXl, p);
@@ -2070,4 +2151,9 @@ extern "C" void stein_debug_median_direct_stats(long long *hits, long long *miss
 }
 // Test hooks (pure host functions): enumeration of the CTA-pair sweep's tiles.
 extern "C" long long stein_debug_num_pair_tiles(long long T) { return stein::num_pair_tiles(T); }
+// Test hook (pure host function): the cost-balanced chunk boundaries of the CTA-pair sweep (parts + 1 entries).
+extern "C" void stein_debug_sweep_chunk_bounds(long long T, int parts, double beta, long long *out) {
+    const std::vector<long long> b = stein::sweep_chunk_bounds(T, parts, beta);
+    for (int k = 0; k <= parts; ++k) out[k] = b[(size_t)k];
+}
 extern "C" void stein_debug_pair_tile(long long t, int T, int *I2, int *J) { stein::pair_tile(t, T, *I2, *J); }

@@ -292,6 +292,34 @@ def test_pair_sweep_tile_enumeration(lib, T):
     assert (np.diag(full) == 1).all() and (full[iu] == 2).all() and (full[il] == 0).all()
 
 
+@pytest.mark.parametrize("T,parts,beta", [(512, 74, 1.0), (512, 8 * 74, 1.0), (36, 2 * 74, 1.0), (513, 4 * 74, 2.5),
+                                          (128, 74, 0.5)])
+def test_sweep_chunks_are_a_cost_balanced_partition(lib, T, parts, beta):
+    """The CTA-pair sweep deals its tiles to world x clusters chunks of equal cost, tiles + beta per pair row
+    entered (csrc/median_tc.cu sweep_chunk_bounds): the chunks are a partition of the tile sequence in order,
+    and no chunk costs more than the ideal share plus one row change and one tile."""
+    f = lib.stein_debug_sweep_chunk_bounds
+    f.restype, f.argtypes = None, [ctypes.c_longlong, ctypes.c_int, ctypes.c_double, ctypes.POINTER(ctypes.c_longlong)]
+    out = (ctypes.c_longlong * (parts + 1))()
+    f(T, parts, beta, out)
+    b = np.array(list(out))
+    rows = [T - 2 * i for i in range((T + 1) // 2)]
+    nt = sum(rows)
+    assert b[0] == 0 and b[-1] == nt and (np.diff(b) >= 0).all()
+    starts = np.concatenate([[0], np.cumsum(rows)])          # first tile of every pair row
+    def cost(a, e):
+        if e <= a:
+            return 0.0
+        first, last = np.searchsorted(starts, a, "right") - 1, np.searchsorted(starts, e - 1, "right") - 1
+        return (e - a) + beta * (last - first + 1)
+    costs = np.array([cost(b[k], b[k + 1]) for k in range(parts)])
+    ideal = (nt + beta * len(rows)) / parts
+    assert costs.max() <= ideal + 2 * beta + 2, (costs.max(), ideal)
+    # the even split of the tiles it replaces leaves its last chunk with far more row changes
+    even = np.array([cost(nt * k // parts, nt * (k + 1) // parts) for k in range(parts)])
+    assert costs.max() <= even.max() + 1e-9
+
+
 def test_kernel_plugin_bandwidth_argument():
     """abstract_kernel.py:17 takes (n_particles, sess); the optional `bandwidth` selects the
     fixed-bandwidth kernel and is validated on the host."""

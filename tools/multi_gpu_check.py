@@ -34,7 +34,7 @@ def main():
         eng.set_particles(np.ascontiguousarray(X[b:b + nl]))
         gd = orc.AdamGradientDescent(0.1, 0.999)
         Xref = X.copy()
-        for it in range(3):
+        for it in range(6):
             S = (mean - Xref) * 2.0
             bw_ref = orc.kernel_and_grad(Xref)[2] if n <= 1500 else None
             out = np.empty((nl, d))
@@ -54,6 +54,9 @@ def main():
                 else:       # more ranks than 128-row tiles: this rank owns no particle
                     err = 0.0
                 good = err < 1e-4
+                # the exact median of the reference's rule (compute_median.py:4-16), bit for bit
+                m_ref, _ = orc.median_chain(Xref.astype(np.float32), radix=True)
+                good = good and np.float32(info["median"]).tobytes() == m_ref.tobytes()
                 # all ranks must hold the same bandwidth bits
                 t = torch.tensor([np.float32(info["bandwidth"]).view(np.int32).item()], device="cuda")
                 lo, hi = t.clone(), t.clone()
@@ -68,6 +71,8 @@ def main():
                   % (rank, n, d, eng.peer_push, it, info["bandwidth"], info["sweeps"], err, "ok" if good else "FAIL"),
                   flush=True)
             ok = ok and good
+        if rank == 0:
+            print("n=%d d=%d push=%s: prefetched medians %r" % (n, d, eng.peer_push, eng.prefetch_stats()), flush=True)
         eng.close()
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
