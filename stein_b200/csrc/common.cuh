@@ -102,7 +102,8 @@ constexpr int MEDIAN_DEFERRED = 3, MEDIAN_NOT_DEFERRED = 4;
 int median_sqdist_begin(stein_ctx *ctx, const float *X_dev, const float *r_dev, int64_t n, int64_t d, int64_t ld);
 int median_sqdist_resume(stein_ctx *ctx, const float *X_dev, const float *r_dev, int64_t n, int64_t d, int64_t ld,
                          float *median_host, int32_t *sweeps_host);
-bool median_sqdist_deferred_pending(void);
+bool median_sqdist_deferred_pending(const void *owner);
+void median_tc_forget_owner(const void *owner);     // an engine is destroyed: drop its median history
 bool median_sqdist_can_defer(const stein_ctx *ctx, int64_t n, int64_t ld);
 bool median_sqdist_wants_fused_begin(const stein_ctx *ctx, int64_t n, int64_t ld);
 int median_sqdist_begin_with_norms(stein_ctx *ctx, const float *X_dev, float *r_dev, int64_t rows_r, int64_t n, int64_t ld);

@@ -223,6 +223,7 @@ int stein_engine_destroy(stein_engine *e) {
     if (!e) return STEIN_OK;
     cudaSetDevice(e->ctx->device);
     cudaStreamSynchronize(e->ctx->stream);
+    median_tc_forget_owner(reinterpret_cast<const void *>(e->uid));
     release_peer_reduce(e);
     if (e->peers_open)
         for (int r = 0; r < e->world; ++r)
@@ -371,7 +372,7 @@ static int step_prepare_s(stein_engine *e, cudaEvent_t scores_ready) {
 // scores_in_place: S_all is complete behind `scores_ready` (or, NULL, in ctx stream order).
 static int step_bandwidth(stein_engine *e, float *bw_out, bool scores_in_place = false, cudaEvent_t scores_ready = nullptr) {
     stein_ctx *ctx = e->ctx;
-    const bool resume = e->bw_pending && median_sqdist_deferred_pending();
+    const bool resume = e->bw_pending && median_sqdist_deferred_pending(reinterpret_cast<const void *>(e->uid));
     e->bw_pending = false;
     if (resume) e->prefetch_used += 1;
     if (!resume) STEIN_TRY(step_head(e));

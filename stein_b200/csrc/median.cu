@@ -306,7 +306,7 @@ bool median_tc_has_hint(const stein_ctx *ctx);
 bool median_tc_direct_ok(const stein_ctx *ctx);
 void median_tc_count_direct_hit(void);
 void median_tc_note_result(const stein_ctx *ctx, uint32_t k0, uint32_t k1, bool direct_missed);
-bool median_tc_deferred_pending(void);
+bool median_tc_deferred_pending(const void *owner);
 void median_tc_cancel_deferred(void);
 int median_tc_finish_deferred(stein_ctx *ctx, uint32_t keys_out[2]);
 int median_tc_begin(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t ld);
@@ -454,7 +454,7 @@ int median_sqdist_resume(stein_ctx *ctx, const float *X_dev, const float *r_dev,
                          float *median_host, int32_t *sweeps_host) {
     return median_sqdist_impl(ctx, X_dev, r_dev, n, d, ld, median_host, nullptr, sweeps_host, MEDIAN_RESUME);
 }
-bool median_sqdist_deferred_pending(void) { return median_tc_deferred_pending(); }
+bool median_sqdist_deferred_pending(const void *owner) { return median_tc_deferred_pending(owner); }
 int median_tc_begin_with_norms(stein_ctx *ctx, const float *X, float *r, int64_t rows_r, int64_t n, int64_t ld);
 // Row norms of `rows_r` rows and, when the tensor-core median route will take these particles, its first stage
 // (error budgets, scale, FP16 split) from the same read.  Returns false if only the norms are needed.

@@ -17,6 +17,7 @@
 //      arithmetic (FFMA chain, pair_chain.cuh) and the exact rank is selected among those keys.
 // Every step checks that the target rank is bracketed; if not (pilot window missed,
 // list overflow) the caller falls back to the all-FFMA route of median.cu.
+#include <map>
 #include <cuda_fp16.h>
 #include <math.h>
 
@@ -1360,20 +1361,13 @@ struct MedianArena {
     unsigned long long *h_pinned = nullptr;   // HIST_MAX_BINS + 8 window counts, then CNT_TOTAL counters
     int64_t x_elems = 0;
     unsigned long long list_cap = 0, band_cap = 0;
-    // centre of the last pilot window (keys): successive iterations move the median only slightly
-    uint32_t last_center = 0u;
-    bool have_last = false;
-    // pilot-less steady state: half-width (keys) of the last pilot-derived window, the exact median key of the
-    // last two iterations, and how many iterations to stay on the pilot after a miss
-    uint32_t last_half = 0u, med_key = 0u, prev_med_key = 0u, prev2_med_key = 0u;
-    int med_keys_known = 0, direct_cooldown = 0;
     long long direct_hits = 0, direct_misses = 0;      // statistics (stein_debug_median_direct_stats)
-    const void *hint_owner = nullptr;     // the engine (stein_ctx::median_owner) the hint belongs to
     cudaEvent_t ev_tail = nullptr;        // marks the D2H copies of the device-driven tail
     bool fresh = false;                   // median_tc_begin ran and no sweep has used its counters yet
     // deferred tail (stein_ctx::median_defer): everything is enqueued, the host part waits in median_tc_finish_deferred
     struct Deferred {
         bool active = false;
+        const void *owner = nullptr;      // stein_ctx::median_owner of the call that enqueued it
         uint64_t ranks[2] = {0, 0};
         int64_t d = 0;
     } deferred;
@@ -1397,9 +1391,31 @@ constexpr int CNT_TOTAL = CNT_G1_END + 20;
 
 static MedianArena g_arena;   // one per process (one GPU per process)
 
+// What one engine's sequence of iterations remembers about its median (stein_ctx::median_owner identifies the
+// sequence): several engines of a process each keep their own history, whatever order they step in.
+struct HintState {
+    // centre of the last pilot window (keys): successive iterations move the median only slightly
+    uint32_t last_center = 0u;
+    bool have_last = false;
+    // pilot-less steady state: half-width (keys) of the last pilot-derived window, the exact median key of the
+    // last three iterations, and how many iterations to stay on the pilot after a miss
+    uint32_t last_half = 0u, med_key = 0u, prev_med_key = 0u, prev2_med_key = 0u;
+    int med_keys_known = 0, direct_cooldown = 0;
+};
+static std::map<const void *, HintState> g_hints;
+static HintState &hint_of(const stein_ctx *ctx) {
+    static HintState none;
+    if (ctx->median_owner == nullptr) {      // an independent call: no history in, none kept
+        none = HintState();
+        return none;
+    }
+    return g_hints[ctx->median_owner];
+}
+void median_tc_forget_owner(const void *owner) { g_hints.erase(owner); }
+
 // the hint is only used within one engine's sequence of iterations
 static bool hint_usable(const stein_ctx *ctx) {
-    return g_arena.have_last && ctx->median_owner != nullptr && g_arena.hint_owner == ctx->median_owner;
+    return ctx->median_owner != nullptr && hint_of(ctx).have_last;
 }
 
 static int ensure_arena(stein_ctx *ctx, int64_t rows, int64_t DP, uint64_t pairs) {
@@ -1554,8 +1570,9 @@ int pilot_window(stein_ctx *ctx, const uint32_t *keys_dev, int64_t m, uint64_t r
     // Successive SVGD iterations move the median by a fraction of a percent: first try ONE pass
     // over +-2^20 keys (about +-9 % in value, 128 keys per bin) around the last window.  The
     // result is only used when both ranks fall inside; otherwise the two generic passes run.
-    uint32_t &last_center = g_arena.last_center;
-    bool &have_last = g_arena.have_last;
+    HintState &H = hint_of(ctx);
+    uint32_t &last_center = H.last_center;
+    bool &have_last = H.have_last;
     uint64_t lo = 0, hi = 0;
     bool found = false;
     if (hint_usable(ctx)) {
@@ -1580,12 +1597,6 @@ int pilot_window(stein_ctx *ctx, const uint32_t *keys_dev, int64_t m, uint64_t r
     *hi_key = (uint32_t)hi;
     last_center = (uint32_t)((lo + hi) / 2);
     have_last = true;
-    if (g_arena.hint_owner != ctx->median_owner) {      // another engine's sequence starts: its own pilot-less history
-        g_arena.med_keys_known = 0;
-        g_arena.direct_cooldown = 0;
-        g_arena.last_half = 0u;
-    }
-    g_arena.hint_owner = ctx->median_owner;
     return STEIN_OK;
 }
 
@@ -1605,13 +1616,14 @@ bool median_tc_has_hint(const stein_ctx *ctx) { return hint_usable(ctx); }
 // difference of the last three exact medians is below an eighth of the window's half-width.  No pilot sample, no
 // pilot histogram, no all-reduce of it.  Every consumer of the window still checks that the rank is bracketed;
 // a miss falls back to the pilot route and keeps it for a few iterations.
-static int64_t direct_step(const MedianArena &A) { return (int64_t)A.med_key - (int64_t)A.prev_med_key; }
-static uint32_t direct_center(const MedianArena &A) {
+static int64_t direct_step(const HintState &A) { return (int64_t)A.med_key - (int64_t)A.prev_med_key; }
+static uint32_t direct_center(const HintState &A) {
     const int64_t c = (int64_t)A.med_key + direct_step(A);
     return (uint32_t)std::min<int64_t>(std::max<int64_t>(c, 0), 0xffffffffll);
 }
 bool median_tc_direct_ok(const stein_ctx *ctx) {
-    const MedianArena &A = g_arena;
+    if (ctx->median_owner == nullptr) return false;
+    const HintState &A = hint_of(ctx);
     if (getenv("STEIN_MEDIAN_DEBUG"))
         fprintf(stderr, "[stein] direct_ok: hint %d known %d half %u cooldown %d keys %u %u %u\n", (int)hint_usable(ctx),
                 A.med_keys_known, A.last_half, A.direct_cooldown, A.med_key, A.prev_med_key, A.prev2_med_key);
@@ -1626,18 +1638,15 @@ bool median_tc_direct_ok(const stein_ctx *ctx) {
 void median_tc_count_direct_hit(void) { ++g_arena.direct_hits; }
 // bookkeeping after a median call of an engine sequence (keys of the two middle values)
 void median_tc_note_result(const stein_ctx *ctx, uint32_t k0, uint32_t k1, bool direct_missed) {
-    MedianArena &A = g_arena;
-    if (ctx->median_owner == nullptr || A.hint_owner != ctx->median_owner) {
-        A.med_keys_known = 0;
-        return;
-    }
+    if (ctx->median_owner == nullptr) return;
+    HintState &A = hint_of(ctx);
     A.prev2_med_key = A.prev_med_key;
     A.prev_med_key = A.med_key;
     A.med_key = (uint32_t)(((uint64_t)k0 + k1) / 2);
     A.med_keys_known = std::min(A.med_keys_known + 1, 3);
     if (direct_missed) {
         A.direct_cooldown = 8;
-        ++A.direct_misses;
+        ++g_arena.direct_misses;
     } else if (A.direct_cooldown > 0) {
         --A.direct_cooldown;
     }
@@ -1703,6 +1712,7 @@ static int median_tc_device_tail(stein_ctx *ctx, const float *X, const float *r,
         if (!A.ev_tail) STEIN_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&A.ev_tail, cudaEventDisableTiming));
         STEIN_CHECK_CUDA(ctx, cudaEventRecord(A.ev_tail, ctx->stream));
         A.deferred.active = true;
+        A.deferred.owner = ctx->median_owner;
         A.deferred.ranks[0] = ranks[0];
         A.deferred.ranks[1] = ranks[1];
         A.deferred.d = d;
@@ -1732,14 +1742,15 @@ static int median_tc_tail_host(stein_ctx *ctx, int64_t d, const uint64_t ranks[2
     const int world = ctx->has_comm ? ctx->comm.world : 1;
     unsigned long long *h = A.h_pinned + HIST_MAX_BINS + 8;
     const uint32_t *wv = reinterpret_cast<const uint32_t *>(h + CNT_WINDOW);
+    HintState &H = hint_of(ctx);
     if (!wv[4]) {                // the pilot ranks were not inside the histogram around the old window
-        A.have_last = false;
+        H.have_last = false;
         return 2;
     }
     memcpy(&p->wlo, &wv[0], 4);
     memcpy(&p->whi, &wv[1], 4);
-    A.last_center = (uint32_t)(((uint64_t)wv[2] + wv[3]) / 2);
-    if (!p->direct_window) A.last_half = (wv[3] - wv[2]) / 2u + 1u;
+    H.last_center = (uint32_t)(((uint64_t)wv[2] + wv[3]) / 2);
+    if (!p->direct_window) H.last_half = (wv[3] - wv[2]) / 2u + 1u;
     const uint32_t *hbp = reinterpret_cast<const uint32_t *>(h + CNT_BANDP);
     // global (below2, band weight, overflow2): all-reduced at the tail of the histogram on sharded runs
     const unsigned long long *g3 = world > 1 ? A.h_pinned + HIST_MAX_BINS + 1 : h + CNT_BELOW2;
@@ -1835,7 +1846,7 @@ bool median_tc_take_begun(const float *X) {
     g_arena.begun_X = nullptr;
     return hit;
 }
-bool median_tc_deferred_pending(void) { return g_arena.deferred.active; }
+bool median_tc_deferred_pending(const void *owner) { return g_arena.deferred.active && g_arena.deferred.owner == owner; }
 void median_tc_cancel_deferred(void) { g_arena.deferred.active = false; }
 // Collects a median whose device part was enqueued with stein_ctx::median_defer set: waits for the D2H copies of
 // the tail and runs its host half.  Returns like median_tc (0 keys found, 1 / 2 take the other routes, < 0 error).
@@ -1930,13 +1941,13 @@ int median_tc(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t
 
     if (spec && spec->direct) {
         // pilot-less: the last window, recentred on the extrapolated exact median
-        const uint32_t c = direct_center(A), half = A.last_half;
+        const uint32_t c = direct_center(hint_of(ctx)), half = hint_of(ctx).last_half;
         set_window_kernel<<<1, 1, 0, ctx->stream>>>(c > half ? c - half : 0u, c < 0xffffffffu - half ? c + half : 0xffffffffu,
                                                    reinterpret_cast<uint32_t *>(A.counters + CNT_WINDOW));
         STEIN_CHECK_LAUNCH(ctx);
     } else if (spec) {
         // one histogram pass over +-2^20 keys around the last window, then the device picks the bins
-        const uint32_t c = A.last_center, half = 1u << 20;
+        const uint32_t c = hint_of(ctx).last_center, half = 1u << 20;
         const KeyWindow w = window_over(c > half ? c - half : 0u, c < 0xffffffffu - half ? c + half : 0xffffffffu);
         static bool attr2 = false;
         if (!attr2) {

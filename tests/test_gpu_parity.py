@@ -1463,3 +1463,48 @@ def test_update_particles_host_prefetches_the_next_median(ctx):
     assert meds_a == meds_b
     for a, b in zip(out_a, out_b):
         np.testing.assert_array_equal(a, b)
+
+
+def test_two_engines_interleaved_keep_their_own_median_history(ctx):
+    """Two engines stepping alternately in one process: each keeps its own median history (window hint, pilot-less
+    steady state) and the prefetched median of one is void once the other has used the arena.  Every engine's
+    trajectory has the bits of its solo run; the medians are the oracle's (compute_median.py:4-16)."""
+    from stein_b200.engine import SvgdEngine
+    n, d, iters = 4608, 256, 7
+    X0 = {"a": _particles(n, d, 51), "b": _particles(n, d, 52, 2.0)}
+
+    def solo(X):
+        eng = SvgdEngine(n, d, "adam", learning_rate=1e-5)
+        eng.set_particles(X)
+        outs, meds, Xin = [], [], X
+        for _ in range(iters):
+            Xout = np.empty_like(Xin)
+            eng.update_particles_host(-Xin, Xout)
+            outs.append(Xout)
+            meds.append(eng.last()["median"])
+            Xin = Xout
+        eng.close()
+        return outs, meds
+
+    ref = {k: solo(X) for k, X in X0.items()}
+    hits0, miss0 = ctypes.c_longlong(), ctypes.c_longlong()
+    ctx.lib.stein_debug_median_direct_stats(ctypes.byref(hits0), ctypes.byref(miss0))
+    engs = {k: SvgdEngine(n, d, "adam", learning_rate=1e-5) for k in X0}
+    cur = dict(X0)
+    for k in engs:
+        engs[k].set_particles(X0[k])
+    for it in range(iters):
+        for k in ("a", "b"):
+            Xout = np.empty_like(cur[k])
+            engs[k].update_particles_host(-cur[k], Xout)
+            assert np.float32(engs[k].last()["median"]).tobytes() == np.float32(ref[k][1][it]).tobytes(), (k, it)
+            np.testing.assert_array_equal(Xout, ref[k][0][it])
+            if it == iters - 1:
+                m_ref, _ = orc.median_chain(cur[k], radix=True)
+                assert np.float32(engs[k].last()["median"]).tobytes() == m_ref.tobytes()
+            cur[k] = Xout
+    hits, miss = ctypes.c_longlong(), ctypes.c_longlong()
+    ctx.lib.stein_debug_median_direct_stats(ctypes.byref(hits), ctypes.byref(miss))
+    assert hits.value - hits0.value >= 4 and miss.value == miss0.value       # both reached the pilot-less state
+    for e in engs.values():
+        e.close()
