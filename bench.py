@@ -427,7 +427,8 @@ def run_ours(args):
         "bandwidth_last_step": info["bandwidth"],
         # device time per iteration by phase (CUDA events on the ctx stream, rank 0; a SEPARATE pass of K steps with
         # all regions timed, `step_total_in_this_pass` per iteration): head = barrier /
-        # all-gather of the particles + row norms; median = the whole median call including its host round
+        # all-gather of the particles + row norms, error budgets, scale and FP16 split of the median (one
+        # read of the particles); median = the rest of the median call including its host round
         # trip (the sweep is part of it); phi_prep = centring, guard, operand arrays; phi = main kernel;
         # phi_tail = finalize + sum(phi^2); step_push = clip + optimizer (+ peer push); collectives = the
         # all-reduce kernels (already contained in median / phi_tail / head); idle = the rest of the step

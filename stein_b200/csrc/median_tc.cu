@@ -1255,7 +1255,8 @@ pick_band_kernel(const unsigned long long *__restrict__ cnt, int slot_below, int
 // the global cursor is advanced once per ~1000 band entries (one atomic per entry, and even one
 // per warp, serialised on that single address: 77 % of the kernel was spent waiting for it).
 constexpr int BF_THREADS = 256;
-constexpr int BF_STAGE = 1024;
+constexpr int BF_UNROLL = 4;               // entries per thread and round: 4 independent load / gather chains in flight
+constexpr int BF_STAGE = 4096;
 __global__ void __launch_bounds__(BF_THREADS)
 band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, const float *__restrict__ ebud,
                    float tlo, float thi, float eps_abs, unsigned long long *__restrict__ below_out,
@@ -1292,32 +1293,46 @@ band_filter_kernel(const PairEntry *__restrict__ list, unsigned long long m, con
         if (threadIdx.x == 0) s_count = 0u;
         __syncthreads();
     };
-    for (unsigned long long e0 = b0; e0 < b1; e0 += BF_THREADS) {
-        const unsigned long long e = e0 + threadIdx.x;
-        bool in_band = false;
-        PairEntry pe{};
-        if (e < b1) {
-            pe = list[e];
-            const uint32_t i = pe.i, j = pe.jw & 0x7fffffffu, w = (pe.jw >> 31) ? 2u : 1u;
-            const float eps = ebud[i] + ebud[j] + eps_abs;
-            if (pe.dt + eps < tlo) {
-                below += w;
-            } else if (pe.dt - eps <= thi) {
-                bw += w;
-                in_band = true;
+    for (unsigned long long e0 = b0; e0 < b1; e0 += BF_UNROLL * BF_THREADS) {
+        PairEntry pe[BF_UNROLL];
+        bool valid[BF_UNROLL], in_band[BF_UNROLL];
+#pragma unroll
+        for (int u = 0; u < BF_UNROLL; ++u) {
+            const unsigned long long e = e0 + (unsigned long long)u * BF_THREADS + threadIdx.x;
+            valid[u] = e < b1;
+            pe[u] = PairEntry{};
+            if (valid[u]) pe[u] = list[e];
+        }
+        float eps[BF_UNROLL];
+#pragma unroll
+        for (int u = 0; u < BF_UNROLL; ++u) {
+            eps[u] = 0.0f;
+            if (valid[u]) eps[u] = ebud[pe[u].i] + ebud[pe[u].jw & 0x7fffffffu] + eps_abs;
+        }
+#pragma unroll
+        for (int u = 0; u < BF_UNROLL; ++u) {
+            in_band[u] = false;
+            if (valid[u]) {
+                const uint32_t w = (pe[u].jw >> 31) ? 2u : 1u;
+                if (pe[u].dt + eps[u] < tlo) {
+                    below += w;
+                } else if (pe[u].dt - eps[u] <= thi) {
+                    bw += w;
+                    in_band[u] = true;
+                }
+            }
+            const unsigned int vote = __ballot_sync(0xffffffffu, in_band[u]);
+            if (vote) {
+                unsigned int base = 0u;
+                if (lane == 0) base = atomicAdd(&s_count, (unsigned)__popc(vote));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (in_band[u]) stage[base + (unsigned)__popc(vote & ((1u << lane) - 1u))] = make_uint2(pe[u].i, pe[u].jw);
             }
         }
-        const unsigned int vote = __ballot_sync(0xffffffffu, in_band);
-        if (vote) {
-            unsigned int base = 0u;
-            if (lane == 0) base = atomicAdd(&s_count, (unsigned)__popc(vote));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (in_band) stage[base + (unsigned)__popc(vote & ((1u << lane) - 1u))] = make_uint2(pe.i, pe.jw);
-        }
-        // flush while one more round of at most BF_THREADS entries is still guaranteed to fit
+        // flush while one more round of at most BF_UNROLL * BF_THREADS entries is still guaranteed to fit
         // (decided on the round count, which is uniform without reading the shared counter)
-        pending += BF_THREADS;
-        if (pending > BF_STAGE - BF_THREADS) {
+        pending += BF_UNROLL * BF_THREADS;
+        if (pending > BF_STAGE - BF_UNROLL * BF_THREADS) {
             flush();
             pending = 0;
         }

@@ -12,9 +12,9 @@ from stein.optimizers import AdamGradientDescent  # noqa: E402
 from stein.samplers import SteinSampler  # noqa: E402
 
 
-def run(name, model, n_particles, feed_fn, iters=200):
+def run(name, model, n_particles, feed_fn, iters=int(os.environ.get("SMALL_ITERS", "200"))):
     sampler = SteinSampler(n_particles, model.log_p, AdamGradientDescent(learning_rate=1e-1))
-    for _ in range(20):
+    for _ in range(int(os.environ.get("SMALL_WARM", "20"))):
         sampler.train_on_batch(feed_fn())
     torch.cuda.synchronize()
     t0 = time.perf_counter()
