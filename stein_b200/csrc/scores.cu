@@ -69,8 +69,19 @@ glm_score_kernel(const float *__restrict__ theta, int64_t F, int64_t ld, const f
     const int part = tid / fstride, fl = tid % fstride;
     for (int64_t c0 = 0; c0 < N; c0 += GLM_CHUNK) {
         const int cn = (int)min((int64_t)GLM_CHUNK, N - c0);
-        // phase 1: residuals, one warp per data row
-        for (int b = warp; b < cn; b += nwarps) {
+        // phase 1: residuals.  Few features (the linear example has 10): one THREAD per data row -- a warp per row
+        // would leave most lanes idle and spend its time in the shuffle reduction (99 us -> see profiles/).
+        if (F <= 16) {
+            for (int b = tid; b < cn; b += SCORE_THREADS) {
+                const float *xr = Xd + (c0 + b) * F;
+                float z = 0.0f;
+                for (int64_t f = 0; f < F; ++f) z = fmaf(xr[f], w[f], z);
+                const float yy = y[c0 + b];
+                e[b] = (MODEL == 0) ? (yy - z) : (yy - 1.0f / (1.0f + expf(-z)));
+            }
+        }
+        // otherwise one warp per data row
+        for (int b = warp; b < cn && F > 16; b += nwarps) {
             const float *xr = Xd + (c0 + b) * F;
             float z = 0.0f;
             for (int64_t f = lane; f < F; f += 32) z = fmaf(xr[f], w[f], z);
@@ -283,7 +294,8 @@ static int glm_launch(stein_ctx *ctx, int model, const float *theta, int64_t n, 
     const int64_t dparam = F + (model == 1 ? 1 : 0);
     STEIN_REQUIRE(ctx, n >= 1 && F >= 1 && N >= 1 && ld >= dparam, "bad shape n=%lld F=%lld N=%lld ld=%lld",
                   (long long)n, (long long)F, (long long)N, (long long)ld);
-    const int fstride = (int)std::min<int64_t>(round_up(F, 32), SCORE_THREADS);
+    int fstride = 8;            // smallest power of two >= F (threads of one row-part), at most the block
+    while (fstride < F && fstride < SCORE_THREADS) fstride *= 2;
     const int nparts = SCORE_THREADS / fstride;
     const size_t smem = sizeof(float) * (size_t)(F + GLM_CHUNK + (int64_t)nparts * F);
     STEIN_REQUIRE(ctx, smem <= 200 * 1024, "F=%lld too large for the score kernel", (long long)F);
