@@ -334,6 +334,15 @@ int stein_engine_set_hyper(stein_engine *eng, double learning_rate, double decay
 int stein_engine_update_particles_host(stein_engine *eng, const void *S_host, void *X_host_out,
                                        int is_f64);
 int stein_engine_set_prefetch(stein_engine *eng, int on);
+/* stein_engine_step / _update_particles_host enqueue phi BEFORE the host has collected the median: in the steady
+ * state of the median its final select also runs on the device and leaves the bandwidth in device memory for the
+ * kernels of phi; the host verifies (same keys, same bits of h) behind the phi kernel and launches the optimizer
+ * only after that -- on a mismatch, or when the median had to take another route, phi is run again with the
+ * host's value.  Same results; default on for sharded engines (where the round trip's wake-up jitter is
+ * maximised over the ranks by the next all-reduce), off on one GPU; environment STEIN_DEVICE_BW=0 / 1.  _stats: iterations that took
+ * this form / that had to repeat phi.                                                                         */
+int stein_engine_set_device_bandwidth(stein_engine *eng, int on);
+int stein_engine_device_bandwidth_stats(const stein_engine *eng, int64_t *used, int64_t *redone);
 /* how many next-iteration medians were enqueued ahead / later collected by a step */
 int stein_engine_prefetch_stats(const stein_engine *eng, int64_t *begun, int64_t *used);
 /* A caller that writes the particle buffer of stein_engine_buffers itself (instead of

@@ -107,6 +107,8 @@ SIGNATURES = {
     "stein_ctx_trace_enable": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "stein_ctx_trace_read": (ctypes.c_int, [c_vp, ctypes.c_char_p, c_i64]),
     "stein_engine_set_prefetch": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "stein_engine_set_device_bandwidth": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "stein_engine_device_bandwidth_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "stein_engine_prefetch_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "stein_engine_particles_changed": (ctypes.c_int, [c_vp]),
     "stein_engine_ipc_handle": (ctypes.c_int, [c_vp, c_vp]),

@@ -63,6 +63,9 @@ struct stein_ctx {
     const void *guard_owner = nullptr, *guard_lag_owner = nullptr;
     // set around a median call whose host part is collected later (median_sqdist_begin / _resume)
     int median_defer = 0;
+    // set by an engine around a phi call that runs BEFORE the host has collected the deferred median: the kernels
+    // take the bandwidth from this device block (median_sqdist_device_bandwidth) instead of the host argument
+    const float *dev_bw = nullptr;
     int last_route = -1;
     float last_kappa = 0.0f, last_pred_fast = 0.0f;
     float phi_guard_tol = 5.0e-5f;
@@ -103,6 +106,10 @@ int median_sqdist_begin(stein_ctx *ctx, const float *X_dev, const float *r_dev, 
 int median_sqdist_resume(stein_ctx *ctx, const float *X_dev, const float *r_dev, int64_t n, int64_t d, int64_t ld,
                          float *median_host, int32_t *sweeps_host);
 bool median_sqdist_deferred_pending(const void *owner);
+// device-side result of a deferred median: [h, h^2, 1/h^2, log2(e)/h^2, log2(e)/(2 h^2)] for the kernels that follow it
+// on the stream; after _resume: whether that result is the one the host accepted (and its h)
+const float *median_sqdist_device_bandwidth(void);
+bool median_sqdist_device_select_valid(float *bandwidth);
 void median_tc_forget_owner(const void *owner);     // an engine is destroyed: drop its median history
 bool median_sqdist_can_defer(const stein_ctx *ctx, int64_t n, int64_t ld);
 bool median_sqdist_wants_fused_begin(const stein_ctx *ctx, int64_t n, int64_t ld);

@@ -242,6 +242,7 @@ int stein_phi(stein_ctx *ctx, const float *X_all_dev, const float *S_all_dev, co
     STEIN_REQUIRE(ctx, n_total >= 1 && d >= 1 && ld >= d && ld % LD_ALIGN == 0, "bad shape");
     STEIN_REQUIRE(ctx, row_begin >= 0 && n_local >= 1 && row_begin % TILE == 0,
                   "row_begin=%lld must be a non-negative multiple of %d", (long long)row_begin, TILE);
+    if (ctx->dev_bw) bandwidth = 1.0f;       // (internal: the kernels read the bandwidth from the device block)
     STEIN_REQUIRE(ctx, bandwidth > 0.0f && bandwidth == bandwidth, "bandwidth must be positive and finite");
     const float h2 = bandwidth * bandwidth;  // squared_exponential_kernel.py:22 tf.square(bandwidth)
     // A leading dimension of 128 / 256 makes the matrix eligible for the tensor-core kernels
@@ -249,6 +250,9 @@ int stein_phi(stein_ctx *ctx, const float *X_all_dev, const float *S_all_dev, co
     const int64_t d_true = d;
     if (is_tc_ld(ld) && d < ld) d = ld;
     const int impl = pick_phi_impl(ctx, n_local, n_total, d);
+    if (ctx->dev_bw && !(is_pair_impl(impl) && !panel::panel_supported(ctx, n_total, ld) &&
+                         flash_tc2_supported(ctx, n_local, n_total, d)))
+        return PHI_DEV_BW_NA;                // only the CTA-pair flash kernels take the device block
     if (is_pair_impl(impl) && impl >= STEIN_PHI_FLASH_TC4 && panel::panel_supported(ctx, n_total, ld))
         return panel::phi_panel(ctx, X_all_dev, S_all_dev, r_all_dev, n_total, d, d_true, ld, row_begin, n_local, h2,
                                 workspace_dev, workspace_bytes, phi_dev, sumsq_dev, impl - STEIN_PHI_FLASH_TC2);

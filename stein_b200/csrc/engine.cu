@@ -49,6 +49,11 @@ struct stein_engine {
     bool prefetch = true;
     bool bw_pending = false;        // a deferred median (median_sqdist_begin) of the current particles is in flight
     int64_t prefetch_begun = 0, prefetch_used = 0;
+    // step / update_particles_host: phi is enqueued BEFORE the host has collected the median, its kernels take the
+    // bandwidth from the device-side select of the deferred median (median_sqdist_device_bandwidth); the host
+    // verifies afterwards, behind the phi kernel instead of in front of it
+    bool device_bw = true;
+    int64_t devbw_used = 0, devbw_redone = 0;
     cudaEvent_t ev_update = nullptr;    // after the optimizer kernel: the download and the next score upload wait for it
     // peer push of the updated particles (CUDA IPC views of the other ranks' X_all)
     float *peer_X[stein::MAX_PEERS + 1] = {nullptr};   // indexed by rank; own entry unused
@@ -202,6 +207,10 @@ int stein_engine_create(stein_engine **out, stein_ctx *ctx, int64_t n_total, int
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_prep, cudaEventDisableTiming);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_update, cudaEventDisableTiming);
     if (const char *env = getenv("STEIN_PREFETCH")) e->prefetch = env[0] != '0';
+    // (on one GPU the host round trip it hides costs 0.017 ms, the device-side select and its copy 0.02-0.05 ms:
+    //  default on for sharded engines only, where the round trip's jitter is maximised over the ranks)
+    e->device_bw = ctx->has_comm && ctx->comm.world > 1;
+    if (const char *env = getenv("STEIN_DEVICE_BW")) e->device_bw = env[0] != '0';
     if (err != cudaSuccess) {
         stein_engine_destroy(e);
         return fail(ctx, err == cudaErrorMemoryAllocation ? STEIN_ERR_NOMEM : STEIN_ERR_CUDA,
@@ -370,7 +379,7 @@ static int step_prepare_s(stein_engine *e, cudaEvent_t scores_ready) {
 // Phase 1: head, exact median, bandwidth.  When the previous update_particles_host call has already enqueued the
 // head and the device part of the median for these particles (step_prefetch), only its result is collected.
 // scores_in_place: S_all is complete behind `scores_ready` (or, NULL, in ctx stream order).
-static int step_bandwidth(stein_engine *e, float *bw_out, bool scores_in_place = false, cudaEvent_t scores_ready = nullptr) {
+static int step_bandwidth(stein_engine *e, float *bw_out, bool scores_in_place, cudaEvent_t scores_ready) {
     stein_ctx *ctx = e->ctx;
     const bool resume = e->bw_pending && median_sqdist_deferred_pending(reinterpret_cast<const void *>(e->uid));
     e->bw_pending = false;
@@ -445,12 +454,72 @@ static int step_phi(stein_engine *e, float bw, bool scores_gathered) {
     const int prc = stein_phi(ctx, e->X_all, e->S_all, e->r_all, e->n_total, e->d, e->ld, e->row_begin,
                               std::max<int64_t>(e->n_local, 1), bw, e->ws, e->ws_bytes, e->phi, e->sumsq);
     ctx->guard_owner = nullptr;
+    if (prc == PHI_DEV_BW_NA) return prc;
     STEIN_TRY(prc);
-    if (e->world > 1) STEIN_TRY(allreduce_f64(ctx, e->sumsq, 1));
+    if (e->world > 1 && !ctx->dev_bw) STEIN_TRY(allreduce_f64(ctx, e->sumsq, 1));
     return STEIN_OK;
 }
 
+static int step_bandwidth(stein_engine *e, float *bw_out, bool scores_in_place, cudaEvent_t scores_ready);
 static int step_optimizer(stein_engine *e);
+
+// One iteration with phi AHEAD of the host: the head and the device part of the median are enqueued (or already
+// are: step_prefetch), phi follows on the stream reading the bandwidth the device-side select left in device
+// memory, and only then the host collects the median.  It finds the same keys (same logic, same inputs) -- if not,
+// or if the median had to take another route, phi is simply run again with the host's value.  The optimizer is
+// launched after that check, so nothing irreversible ever uses an unverified bandwidth.  The host round trip of
+// the median thus sits behind the phi kernel instead of in front of it (on 8 GPUs its wake-up jitter, maximised
+// over the ranks by the next all-reduce, cost ~0.15 ms of a 1.65 ms step).
+// Returns STEIN_OK with *done = false when this form does not apply (the caller takes the plain sequence).
+static int step_device_bandwidth(stein_engine *e, bool scores_in_place, cudaEvent_t scores_ready, bool *done) {
+    stein_ctx *ctx = e->ctx;
+    *done = false;
+    if (!e->device_bw || e->fixed_bw > 0.0f || !scores_in_place) return STEIN_OK;
+    const void *owner = reinterpret_cast<const void *>(e->uid);
+    bool pending = e->bw_pending && median_sqdist_deferred_pending(owner);
+    const bool was_prefetched = pending;
+    bool prepared_s = false;
+    if (!pending) {
+        e->bw_pending = false;
+        ctx->median_owner = owner;
+        const bool can = median_sqdist_can_defer(ctx, e->n_total, e->ld);
+        ctx->median_owner = nullptr;
+        if (!can) return STEIN_OK;
+        STEIN_TRY(step_head(e));
+        STEIN_TRY(step_prepare_s(e, scores_ready));      // (ahead of the median's kernels, as in the plain sequence)
+        prepared_s = true;
+        ctx->median_owner = owner;
+        RegionTimer mtimer(ctx, STEIN_REGION_MEDIAN);
+        const int rc = median_sqdist_begin(ctx, e->X_all, e->r_all, e->n_total, e->d, e->ld);
+        mtimer.stop();
+        ctx->median_owner = nullptr;
+        if (rc < 0) return rc;
+        if (rc != MEDIAN_DEFERRED) return fail(ctx, STEIN_ERR_INTERNAL, "median not deferred");
+        e->bw_pending = true;
+    }
+    if (!prepared_s) STEIN_TRY(step_prepare_s(e, scores_ready));
+    if (scores_ready) STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, scores_ready, 0));
+    ctx->dev_bw = median_sqdist_device_bandwidth();
+    const int prc = ctx->dev_bw ? step_phi(e, 1.0f, true) : PHI_DEV_BW_NA;
+    ctx->dev_bw = nullptr;
+    if (prc != STEIN_OK && prc != PHI_DEV_BW_NA) return prc;
+    // the host's median (waits for the copies behind the median's tail -- long done unless phi was not enqueued)
+    float bw = 0.f;
+    STEIN_TRY(step_bandwidth(e, &bw, false, nullptr));
+    if (!was_prefetched) e->prefetch_used -= 1;      // (collected a median this very call enqueued)
+    float dev_h = 0.f;
+    const bool valid = prc == STEIN_OK && median_sqdist_device_select_valid(&dev_h) && memcmp(&dev_h, &bw, 4) == 0;
+    if (valid) {
+        e->devbw_used += 1;
+        if (e->world > 1) STEIN_TRY(allreduce_f64(ctx, e->sumsq, 1));
+    } else {
+        if (prc == STEIN_OK) e->devbw_redone += 1;
+        STEIN_TRY(step_phi(e, bw, true));
+    }
+    STEIN_TRY(step_optimizer(e));
+    *done = true;
+    return STEIN_OK;
+}
 
 // Phase 2: phi, clip, optimizer step.
 static int step_update(stein_engine *e, float bw, bool scores_gathered) {
@@ -513,6 +582,9 @@ int stein_engine_step(stein_engine *e) {
         STEIN_TRY(gather_scores_async(e, &gathered));
         STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_scores, e->copy_stream));
     }
+    bool done = false;
+    STEIN_TRY(step_device_bandwidth(e, gathered || e->world == 1, gathered ? e->ev_scores : nullptr, &done));
+    if (done) return STEIN_OK;
     float bw = 0.f;
     const int rc = step_bandwidth(e, &bw, gathered || e->world == 1, gathered ? e->ev_scores : nullptr);
     if (gathered) STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e->ev_scores, 0));
@@ -534,11 +606,15 @@ int stein_engine_update_particles_host(stein_engine *e, const void *S_host, void
     bool gathered = false;
     STEIN_TRY(gather_scores_async(e, &gathered));
     STEIN_CHECK_CUDA(ctx, cudaEventRecord(e->ev_scores, e->copy_stream));
-    float bw = 0.f;
-    const int rc = step_bandwidth(e, &bw, gathered || e->world == 1, e->ev_scores);
-    STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e->ev_scores, 0));
-    if (rc != STEIN_OK) return rc;
-    STEIN_TRY(step_update(e, bw, gathered));
+    bool done = false;
+    STEIN_TRY(step_device_bandwidth(e, gathered || e->world == 1, e->ev_scores, &done));
+    if (!done) {
+        float bw = 0.f;
+        const int rc = step_bandwidth(e, &bw, gathered || e->world == 1, e->ev_scores);
+        STEIN_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e->ev_scores, 0));
+        if (rc != STEIN_OK) return rc;
+        STEIN_TRY(step_update(e, bw, gathered));
+    }
     if (!X_host_out) return STEIN_OK;
     // The updated particles cross PCIe on the copy stream while the ctx stream already runs the next iteration's
     // head and median (they need only the particles): the caller holds the new particles when this returns, and
@@ -554,6 +630,19 @@ int stein_engine_update_particles_host(stein_engine *e, const void *S_host, void
 int stein_engine_set_prefetch(stein_engine *e, int on) {
     if (!e) return STEIN_ERR_INVALID;
     e->prefetch = on != 0;
+    return STEIN_OK;
+}
+
+int stein_engine_set_device_bandwidth(stein_engine *e, int on) {
+    if (!e) return STEIN_ERR_INVALID;
+    e->device_bw = on != 0;
+    return STEIN_OK;
+}
+
+int stein_engine_device_bandwidth_stats(const stein_engine *e, int64_t *used, int64_t *redone) {
+    if (!e) return STEIN_ERR_INVALID;
+    if (used) *used = e->devbw_used;
+    if (redone) *redone = e->devbw_redone;
     return STEIN_OK;
 }
 

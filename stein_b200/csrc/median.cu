@@ -309,6 +309,8 @@ void median_tc_note_result(const stein_ctx *ctx, uint32_t k0, uint32_t k1, bool 
 bool median_tc_deferred_pending(const void *owner);
 void median_tc_cancel_deferred(void);
 int median_tc_finish_deferred(stein_ctx *ctx, uint32_t keys_out[2]);
+const float *median_tc_device_bandwidth(void);
+bool median_tc_device_select_valid(float *bandwidth);
 int median_tc_begin(stein_ctx *ctx, const float *X, const float *r, int64_t n, int64_t ld);
 void median_tc_reset(void);
 bool median_tc_take_begun(const float *X);
@@ -455,6 +457,8 @@ int median_sqdist_resume(stein_ctx *ctx, const float *X_dev, const float *r_dev,
     return median_sqdist_impl(ctx, X_dev, r_dev, n, d, ld, median_host, nullptr, sweeps_host, MEDIAN_RESUME);
 }
 bool median_sqdist_deferred_pending(const void *owner) { return median_tc_deferred_pending(owner); }
+const float *median_sqdist_device_bandwidth(void) { return median_tc_device_bandwidth(); }
+bool median_sqdist_device_select_valid(float *bandwidth) { return median_tc_device_select_valid(bandwidth); }
 int median_tc_begin_with_norms(stein_ctx *ctx, const float *X, float *r, int64_t rows_r, int64_t n, int64_t ld);
 // Row norms of `rows_r` rows and, when the tensor-core median route will take these particles, its first stage
 // (error budgets, scale, FP16 split) from the same read.  Returns false if only the norms are needed.

@@ -1365,6 +1365,8 @@ struct PilotSpec {
                                     // exact median (median_tc_direct_ok); keys_dev / m_local / rank_* unused
 };
 
+constexpr int DSEL_WORDS = 16;      // device select block (MedianArena::dsel)
+
 struct MedianArena {
     __half *Xh = nullptr, *Xl = nullptr;
     float *e = nullptr;                       // per-row error budget (err_budget_kernel), x_rows entries
@@ -1378,10 +1380,14 @@ struct MedianArena {
     unsigned long long list_cap = 0, band_cap = 0;
     long long direct_hits = 0, direct_misses = 0;      // statistics (stein_debug_median_direct_stats)
     cudaEvent_t ev_tail = nullptr;        // marks the D2H copies of the device-driven tail
+    // device-side final select of a deferred median (tail_select_kernel): 4 u32 [status, key0, key1, -] followed by
+    // 5 floats [bandwidth, h^2, 1/h^2, log2(e)/h^2, log2(e)/(2 h^2)] that the phi kernels can read without the host
+    uint32_t *dsel = nullptr, *h_dsel = nullptr;
     bool fresh = false;                   // median_tc_begin ran and no sweep has used its counters yet
     // deferred tail (stein_ctx::median_defer): everything is enqueued, the host part waits in median_tc_finish_deferred
     struct Deferred {
         bool active = false;
+        bool dev_valid = false;           // the device-side select of this median agrees with the host's result
         const void *owner = nullptr;      // stein_ctx::median_owner of the call that enqueued it
         uint64_t ranks[2] = {0, 0};
         int64_t d = 0;
@@ -1403,6 +1409,88 @@ constexpr int CNT_BANDP = CNT_G1_END + 12;     // device-picked band parameters 
 constexpr int CNT_EMAX = CNT_G1_END + 18;      // 1 float: max_i e_i
 constexpr int CNT_TOTAL = CNT_G1_END + 20;
 
+
+// Device-side counterpart of median_tc_tail_host: the final select of the steady-state tail, so that the kernels
+// of phi can take the bandwidth from device memory while the host is still on its way to the same result (the
+// host verifies: same status, same keys; engine.cu).  compute_median.py:9-15 (middle value / mean of the two
+// middle values) and abstract_kernel.py:40 (h = sqrt(med / ln n)), in the host's fp32 operations.
+// out: u32 [status (0 = usable), key0, key1, -], then floats [h, h^2, 1/h^2, log2(e)/h^2, log2(e)/(2 h^2)].
+__global__ void __launch_bounds__(1024)
+tail_select_kernel(const unsigned long long *__restrict__ cnt, const unsigned long long *__restrict__ bins,
+                   int distributed, unsigned long long rank0, unsigned long long rank1, unsigned long long band_cap,
+                   int even, float ln_n, uint32_t *__restrict__ out) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ long long s_bin[2];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t < 2) s_bin[t] = -1;
+    const uint32_t *wv = reinterpret_cast<const uint32_t *>(cnt + CNT_WINDOW);
+    const uint32_t *hbp = reinterpret_cast<const uint32_t *>(cnt + CNT_BANDP);
+    const unsigned long long *g3 = distributed ? bins + HIST_MAX_BINS + 1 : cnt + CNT_BELOW2;
+    const uint32_t nbins = min(hbp[BP_NBINS], (uint32_t)HIST_MAX_BINS);
+    const unsigned long long c1 = cnt[CNT_BELOW] + g3[0], band_w = g3[1];
+    const bool pre = wv[4] != 0u && hbp[BP_STATUS] == 0u && g3[2] == 0ull && cnt[CNT_BAND_LEN] <= band_cap &&
+                     c1 <= rank0 && rank1 < c1 + band_w && hbp[BP_SHIFT] == 0u;
+    const unsigned long long rk0 = rank0 - c1, rk1 = rank1 - c1;
+    unsigned long long loc[16], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t b = 16u * t + k;
+        loc[k] = (pre && b < nbins) ? bins[1 + b] : 0ull;
+        tot += loc[k];
+    }
+    unsigned long long incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = wsum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    unsigned long long cum = bins[0] + wsum[warp] + incl - tot;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        if (rk0 >= cum && rk0 < cum + loc[k]) s_bin[0] = 16 * t + k;
+        if (rk1 >= cum && rk1 < cum + loc[k]) s_bin[1] = 16 * t + k;
+        cum += loc[k];
+    }
+    __syncthreads();
+    if (t != 0) return;
+    uint32_t status = 1u, k0 = 0u, k1 = 0u;
+    float h = 0.0f;
+    if (pre && s_bin[0] >= 0 && s_bin[1] >= 0 && rk0 >= bins[0]) {
+        k0 = hbp[BP_KLO] + (uint32_t)s_bin[0];
+        k1 = hbp[BP_KLO] + (uint32_t)s_bin[1];
+        const float m0 = key_to_float(k0), m1 = key_to_float(k1);
+        const float tlo = __uint_as_float(hbp[BP_TLO]), thi = __uint_as_float(hbp[BP_THI]);
+        const float wlo = __uint_as_float(wv[0]), whi = __uint_as_float(wv[1]);
+        if (m0 >= tlo && m1 <= thi && m0 >= wlo && m1 <= whi) {
+            const float med = even ? __fdiv_rn(__fadd_rn(m0, m1), 2.0f) : m0;
+            h = __fsqrt_rn(__fdiv_rn(med, ln_n));
+            if (h > 0.0f && h == h && h < INFINITY) status = 0u;
+        }
+    }
+    const float h2 = __fmul_rn(h, h), l2e = 1.4426950408889634f;
+    out[0] = status;
+    out[1] = k0;
+    out[2] = k1;
+    out[3] = 0u;
+    float *f = reinterpret_cast<float *>(out + 4);
+    f[0] = h;
+    f[1] = h2;
+    f[2] = __fdiv_rn(1.0f, h2);
+    f[3] = __fdiv_rn(l2e, h2);
+    f[4] = __fdiv_rn(__fmul_rn(0.5f, l2e), h2);
+}
 
 static MedianArena g_arena;   // one per process (one GPU per process)
 
@@ -1439,6 +1527,9 @@ static int ensure_arena(stein_ctx *ctx, int64_t rows, int64_t DP, uint64_t pairs
         STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.counters, CNT_TOTAL * 8));
         STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.bins, (HIST_MAX_BINS + 8) * 8));
         STEIN_CHECK_CUDA(ctx, cudaMallocHost(&A.h_pinned, (HIST_MAX_BINS + 8 + CNT_TOTAL) * 8));
+        STEIN_CHECK_CUDA(ctx, cudaMalloc(&A.dsel, DSEL_WORDS * 4));
+        STEIN_CHECK_CUDA(ctx, cudaMallocHost(&A.h_dsel, DSEL_WORDS * 4));
+        STEIN_CHECK_CUDA(ctx, cudaMemsetAsync(A.dsel, 0xff, DSEL_WORDS * 4, ctx->stream));
     }
     if (rows * DP > A.x_elems && rows * DP > 0) {
         if (A.Xh) cudaFree(A.Xh);
@@ -1721,12 +1812,20 @@ static int median_tc_device_tail(stein_ctx *ctx, const float *X, const float *r,
     unsigned long long *h = A.h_pinned + HIST_MAX_BINS + 8;
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.h_pinned, A.bins, (HIST_MAX_BINS + 4) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(h, A.counters, CNT_TOTAL * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->median_defer) {
+        const uint64_t dim = (uint64_t)n * (uint64_t)n;
+        tail_select_kernel<<<1, 1024, 0, ctx->stream>>>(A.counters, A.bins, world > 1 ? 1 : 0, ranks[0], ranks[1],
+                                                       A.band_cap, dim % 2 == 0 ? 1 : 0, (float)log((double)n), A.dsel);
+        STEIN_CHECK_LAUNCH(ctx);
+        STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(A.h_dsel, A.dsel, DSEL_WORDS * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     trace_mark(ctx, "median:band histogram + D2H");
     if (ctx->median_defer) {
         // the caller collects the result later (median_tc_finish_deferred): nothing below needs the host now
         if (!A.ev_tail) STEIN_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&A.ev_tail, cudaEventDisableTiming));
         STEIN_CHECK_CUDA(ctx, cudaEventRecord(A.ev_tail, ctx->stream));
         A.deferred.active = true;
+        A.deferred.dev_valid = false;
         A.deferred.owner = ctx->median_owner;
         A.deferred.ranks[0] = ranks[0];
         A.deferred.ranks[1] = ranks[1];
@@ -1870,7 +1969,19 @@ int median_tc_finish_deferred(stein_ctx *ctx, uint32_t keys_out[2]) {
     if (!A.deferred.active) return fail(ctx, STEIN_ERR_INTERNAL, "no deferred median to collect");
     A.deferred.active = false;
     STEIN_CHECK_CUDA(ctx, cudaEventSynchronize(A.ev_tail));
-    return median_tc_tail_host(ctx, A.deferred.d, A.deferred.ranks, &g_deferred_params, keys_out);
+    const int rc = median_tc_tail_host(ctx, A.deferred.d, A.deferred.ranks, &g_deferred_params, keys_out);
+    A.deferred.dev_valid = rc == STEIN_OK && A.h_dsel[0] == 0u && A.h_dsel[1] == keys_out[0] && A.h_dsel[2] == keys_out[1];
+    return rc;
+}
+// The bandwidth block of the device-side select of the deferred median (5 floats, see tail_select_kernel); valid
+// for the kernels that follow the median on the stream.  NULL before the first deferred median.
+const float *median_tc_device_bandwidth(void) {
+    return g_arena.dsel ? reinterpret_cast<const float *>(g_arena.dsel + 4) : nullptr;
+}
+// after median_tc_finish_deferred: did the device-side select produce the keys the host accepted, and its h
+bool median_tc_device_select_valid(float *bandwidth) {
+    if (bandwidth) memcpy(bandwidth, g_arena.h_dsel + 4, 4);
+    return g_arena.deferred.dev_valid;
 }
 
 // Pilot keys of samples [s0, s0 + m) from the FP16 hi array (needs median_tc_begin on this X).

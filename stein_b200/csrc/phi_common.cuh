@@ -43,6 +43,8 @@ int flash_tc2_prepare_x(stein_ctx *ctx, const float *X_all, int64_t n_total, int
 int flash_tc2_prepare_s(stein_ctx *ctx, const float *X_all, const float *S_all, int64_t n_total, int64_t d, int64_t ld,
                         int64_t n_local, void *ws, int64_t ws_bytes, int mode);
 // panel kernels (phi_panel.cuh): leading dimension 512 / 768 / 1024.  mode 2 fast, 3 precise, 4 guarded
+// returned by a phi call that was asked to take the bandwidth from the device (ctx->dev_bw) but cannot
+constexpr int PHI_DEV_BW_NA = 5;
 namespace panel {
 bool panel_supported(const stein_ctx *ctx, int64_t n_total, int64_t ld);
 int64_t panel_workspace_bytes(const stein_ctx *ctx, int64_t n_local, int64_t n_total, int64_t ld);

@@ -499,6 +499,7 @@ struct Flash2Params {
     long long row_begin;  // first global particle row of the local block (multiple of 128)
     const float *c1mul;   // device: factor on c1 that undoes the power-of-two scaling of X (scaled modes), or NULL
     const int *route;     // device: route picked by phi_guard_kernel (0 fast / 1 precise), or NULL = run unconditionally
+    const float *c1dev;   // device: log2(e) / h^2 from the device-side median select, replaces c1 when non-NULL
     float c1;
     const float *nrm;
     SlotLayout out;
@@ -891,7 +892,8 @@ flash_phi2_kernel(const __grid_constant__ Phi2Maps maps, const Flash2Params p) {
         int t, j0, j1, slot;
         long long jj = 0, oc = 0;
         // GEMM1 of the mixed-precision mode works on X 2^-e: S carries 2^-2e, undone here (exact)
-        const float c1 = (G1F8 || G1H) ? p.c1 * __ldg(p.c1mul) : p.c1;
+        const float c1base = p.c1dev ? __ldg(p.c1dev) : p.c1;
+        const float c1 = (G1F8 || G1H) ? c1base * __ldg(p.c1mul) : c1base;
         float acc[ocols];
         while (it.next(t, j0, j1, slot)) {
             const size_t grow = (size_t)p.row_begin + ((size_t)t * 2 + rank) * 128 + row;   // global particle row
@@ -1157,7 +1159,8 @@ colmax_sx_partial_kernel(const float *__restrict__ X, const float *__restrict__ 
 }
 __global__ void __launch_bounds__(256)
 colscale_sx_kernel(const float *__restrict__ partS, const float *__restrict__ partX, int64_t ld, float inv_h2,
-                   float *__restrict__ down, float *__restrict__ up) {
+                   float *__restrict__ down, float *__restrict__ up, const float *__restrict__ hd = nullptr) {
+    if (hd) inv_h2 = hd[2];
     const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per column
     const int lane = threadIdx.x & 31;
     if (c >= ld) return;
@@ -1295,8 +1298,10 @@ __global__ void prep_x8_kernel(const float *__restrict__ X, const float *__restr
 // therefore as good as the reference itself on any cloud, at 1/25 of the speed.
 // diag[0] = kappa, diag[1] = max_i |x_i - mean|^2
 __global__ void __launch_bounds__(1024)
-phi_guard_kernel(const float *__restrict__ rc, int64_t n, float h2, float *__restrict__ diag) {
+phi_guard_kernel(const float *__restrict__ rc, int64_t n, float h2, float *__restrict__ diag,
+                 const float *__restrict__ hd = nullptr) {
     __shared__ float red[32];
+    if (hd) h2 = hd[1];           // bandwidth block of the device-side median select (median_tc.cu)
     float m = 0.0f;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, rc[i]);
 #pragma unroll
@@ -1320,8 +1325,10 @@ __global__ void prep_x_route_kernel(const float *__restrict__ X, const float *__
                                     int64_t ld, float half_l2e_over_h2, const float *__restrict__ xscale,
                                     const int *__restrict__ route, int forced, __half *__restrict__ X16,
                                     uint8_t *__restrict__ A8l, uint8_t *__restrict__ A8h, uint8_t *__restrict__ B8h,
-                                    uint8_t *__restrict__ B8l, float *__restrict__ nrm, int64_t nrm_rows) {
+                                    uint8_t *__restrict__ B8l, float *__restrict__ nrm, int64_t nrm_rows,
+                                    const float *__restrict__ hd = nullptr) {
     const int precise = route ? *route : forced;
+    if (hd && half_l2e_over_h2 >= 0.0f) half_l2e_over_h2 = hd[4];
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t ld4 = ld / 4;
     if (e < rows * ld4) {
@@ -1358,7 +1365,8 @@ __global__ void prep_x_route_kernel(const float *__restrict__ X, const float *__
 
 // exponent terms alone: nrm[j] = -r_j log2(e) / (2 h^2), -inf beyond n
 __global__ void nrm_kernel(const float *__restrict__ r, int64_t n, float half_l2e_over_h2, float *__restrict__ nrm,
-                           int64_t nrm_rows) {
+                           int64_t nrm_rows, const float *__restrict__ hd = nullptr) {
+    if (hd) half_l2e_over_h2 = hd[4];
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < nrm_rows) nrm[e] = (e < n) ? -r[e] * half_l2e_over_h2 : -INFINITY;
 }
@@ -1368,8 +1376,10 @@ __global__ void nrm_kernel(const float *__restrict__ r, int64_t n, float half_l2
 __global__ void prep_yt_route_kernel(const float *__restrict__ X, const float *__restrict__ S, int64_t rows, int64_t ld,
                                      float inv_h2, const float *__restrict__ down, const int *__restrict__ route,
                                      int forced, __half *__restrict__ YT16, uint8_t *__restrict__ YT8h,
-                                     uint8_t *__restrict__ YT8l, __half *__restrict__ YTx) {
+                                     uint8_t *__restrict__ YT8l, __half *__restrict__ YTx,
+                                     const float *__restrict__ hd = nullptr) {
     const int precise = route ? *route : forced;
+    if (hd) inv_h2 = hd[2];
     __shared__ float tile[32][33];
     const int64_t j0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
     for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
@@ -1564,7 +1574,8 @@ __global__ void __launch_bounds__(256)
 finalize_slots_kernel(const SlotLayout L, const int *__restrict__ tile_nslots,
                       const float *__restrict__ X_local, int64_t rows_valid, int64_t rows, int64_t ld,
                       float inv_h2, float inv_n, const float *__restrict__ colscale /* or NULL */,
-                      float *__restrict__ phi, double *__restrict__ partials) {
+                      float *__restrict__ phi, double *__restrict__ partials, const float *__restrict__ hd = nullptr) {
+    if (hd) inv_h2 = hd[2];
     const int64_t ld4 = ld / 4;
     const int64_t total4 = rows * ld4;
     double local = 0.0;
@@ -1623,7 +1634,7 @@ reduce_partials2_kernel(const double *__restrict__ partials, int count, double *
 // guard_begin enqueues the kappa kernel and the copy of its result; the caller then enqueues whatever
 // every route needs (so the GPU has work while the host waits) and calls guard_end, which returns the
 // route: 0 fast, 1 precise, 2 FP32 FFMA.  `have_fast` / `have_precise`: the routes this kernel family offers.
-static int guard_begin(stein_ctx *ctx, const float *rc, int64_t n_total, float h2) {
+static int guard_begin(stein_ctx *ctx, const float *rc, int64_t n_total, float h2, const float *hd = nullptr) {
     if (!ctx->d_guard) {
         STEIN_CHECK_CUDA(ctx, cudaMalloc(&ctx->d_guard, 32));
         STEIN_CHECK_CUDA(ctx, cudaMallocHost(&ctx->h_guard, 32));
@@ -1631,7 +1642,7 @@ static int guard_begin(stein_ctx *ctx, const float *rc, int64_t n_total, float h
             STEIN_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_guard[k], cudaEventDisableTiming));
     }
     const int slot = (int)(++ctx->guard_calls & 1);
-    phi_guard_kernel<<<1, 1024, 0, ctx->stream>>>(rc, n_total, h2, ctx->d_guard + 4 * slot);
+    phi_guard_kernel<<<1, 1024, 0, ctx->stream>>>(rc, n_total, h2, ctx->d_guard + 4 * slot, hd);
     STEIN_CHECK_LAUNCH(ctx);
     STEIN_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_guard + 4 * slot, ctx->d_guard + 4 * slot, 8, cudaMemcpyDeviceToHost,
                                           ctx->stream));
@@ -1791,6 +1802,10 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
     // stage 0: the whole call; 1: only what needs neither the bandwidth nor the scores (flash_tc2_prepare_x);
     // 2: only the column maxima of S and of the centred X (flash_tc2_prepare_s, after stage 1 on the same problem)
     const bool only_prepare = stage == 1;
+    // Bandwidth from the device (ctx->dev_bw, set by the engine around a call that runs ahead of the host's median
+    // result): only on the guarded route with everything prepared and the guard decided from the previous
+    // iteration -- otherwise PHI_DEV_BW_NA and the caller comes back with the host value.
+    const float *hd = stage == 0 ? ctx->dev_bw : nullptr;
     // mode 0: BF16x3 for both GEMMs; 1: mixed-precision GEMM2; 2: mixed precision for both (fast);
     // 3: three FP16 passes for both (precise); 4: fast / precise / FP32 FFMA, picked by the conditioning guard
     const bool autoroute = mode == 4;
@@ -1818,6 +1833,13 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
     int *d_tile_nslots = nullptr;
     // the bandwidth-independent part (centring, global scale of X) may already have been enqueued
     // by flash_prepare_x while the host waited for the median
+    if (hd) {
+        const stein_ctx::XPrep &x = ctx->xprep;
+        const bool hit = x.X == X_all && x.ws == ws && x.n_total == n_total && x.n_local == n_local && x.d == d &&
+                         x.mode == mode_in;
+        const bool lagged = ctx->guard_owner != nullptr && ctx->guard_lag_owner == ctx->guard_owner;
+        if (!(autoroute && hit && lagged)) return PHI_DEV_BW_NA;
+    }
     if (stage == 2) {
         const stein_ctx::XPrep &x = ctx->xprep;
         if (!(ycols && x.X == X_all && x.ws == ws && x.n_total == n_total && x.n_local == n_local && x.d == d &&
@@ -1875,17 +1897,21 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
             STEIN_CHECK_LAUNCH(ctx);
         }
         colscale_sx_kernel<<<(unsigned)((DP * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-            cmax_part, cmax_part + (int64_t)CM_BLOCKS * DP, DP, 1.0f / h2, cs_down, cs_up);
+            cmax_part, cmax_part + (int64_t)CM_BLOCKS * DP, DP, 1.0f / h2, cs_down, cs_up, hd);
         STEIN_CHECK_LAUNCH(ctx);
         return STEIN_OK;
     };
     if (autoroute) {
         // the route of this call: kappa from the device, decision on the host (guard_end); the column
         // scales of Y keep the GPU busy during the round trip
-        STEIN_TRY(guard_begin(ctx, rc, n_total, h2));
+        STEIN_TRY(guard_begin(ctx, rc, n_total, h2, hd));
         STEIN_TRY(enqueue_colscale());
         int route = 0;
         STEIN_TRY(guard_end(ctx, d_true, true, true, false, &route));
+        if (route == 2 && hd) {      // the FFMA path wants the host's bandwidth: hand the prepared state back
+            ctx->xprep = {X_all, ws, n_total, n_local, d, mode_in};
+            return PHI_DEV_BW_NA;
+        }
         if (route == 2)      // badly conditioned cloud: the reference's own fp32 arithmetic (raw particles, raw norms)
             return phi_dense(ctx, X_all, S_all, r_all, n_total, d, ld, row_begin, n_local, h2, ws, ws_bytes, phi, sumsq);
         mode = route == 0 ? 2 : 3;
@@ -1899,13 +1925,13 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
         if (scaled && prepared && !forced_precise) {
             // the arrays were written ahead of the bandwidth (flash_tc2_prepare_x): only the exponent terms are left
             nrm_kernel<<<(unsigned)((cols + 256 + 255) / 256), 256, 0, ctx->stream>>>(rc, n_total, 0.5f * l2e / h2, nrm,
-                                                                                       cols + 256);
+                                                                                       cols + 256, hd);
         } else if (scaled) {
             // FP16 array in the place of Xh; fast: a8l, a8h share the place of Xl and b8h, b8l have their
             // own; precise: the FP16 residual takes the place of Xl
             prep_x_route_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(
                 Xc, rc, cols, n_total, ld, 0.5f * l2e / h2, xscale, nullptr, forced_precise, (__half *)Xh, (uint8_t *)Xl,
-                (uint8_t *)Xl + cols * DP, B8h, B8l, nrm, cols + 256);
+                (uint8_t *)Xl + cols * DP, B8h, B8l, nrm, cols + 256, hd);
         } else {
             prep_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(Xc, rc, cols, n_total, ld,
                                                                                  0.5f * l2e / h2, Xh, Xl, nrm, cols + 256);
@@ -1916,7 +1942,7 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
             // precise: the FP16 residual takes the place of YTl, the 2^-12 copy that of b8h + b8l
             prep_yt_route_kernel<<<gy, by, 0, ctx->stream>>>(Xc, S_all, cols, ld, 1.0f / h2, cs_down, nullptr, forced_precise,
                                                             (__half *)YTh, (uint8_t *)YTl, (uint8_t *)YTl + cols * DP,
-                                                            (__half *)B8h);
+                                                            (__half *)B8h, hd);
         } else {
             prep_yt_kernel<<<gy, by, 0, ctx->stream>>>(Xc, S_all, cols, ld, 1.0f / h2, YTh, YTl);
         }
@@ -1959,6 +1985,7 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
     p.out = L;
     p.row_begin = row_begin;
     p.c1mul = scaled ? xscale + 1 : nullptr;
+    p.c1dev = hd ? hd + 3 : nullptr;
     p.route = nullptr;
     const size_t smem = flash_smem_bytes(DP);
     static bool attr_set = false;
@@ -1994,7 +2021,7 @@ static int flash_tc2_run(stein_ctx *ctx, const float *X_all, const float *S_all,
     const int blocks = (int)std::min<int64_t>((total4 + 255) / 256, FINALIZE_MAX_BLOCKS);
     finalize_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(L, d_tile_nslots, Xc + row_begin * ld, rows_valid, rows, ld,
                                                            1.0f / h2, 1.0f / (float)n_total, ycols ? cs_up : nullptr, phi,
-                                                           partials);
+                                                           partials, hd);
     STEIN_CHECK_LAUNCH(ctx);
     reduce_partials2_kernel<<<1, 256, 0, ctx->stream>>>(partials, blocks, sumsq);
     STEIN_CHECK_LAUNCH(ctx);

@@ -152,6 +152,15 @@ class SvgdEngine:
         """update_particles_host enqueues the next iteration's median behind the particle download (default on)."""
         self.ctx.check(self.lib.stein_engine_set_prefetch(self.handle, int(bool(on))))
 
+    def set_device_bandwidth(self, on):
+        """phi is enqueued ahead of the host's median result, reading the bandwidth from the device (default on)."""
+        self.ctx.check(self.lib.stein_engine_set_device_bandwidth(self.handle, int(bool(on))))
+
+    def device_bandwidth_stats(self):
+        u, r = ctypes.c_int64(), ctypes.c_int64()
+        self.ctx.check(self.lib.stein_engine_device_bandwidth_stats(self.handle, ctypes.byref(u), ctypes.byref(r)))
+        return {"used": u.value, "redone": r.value}
+
     def prefetch_stats(self):
         b, u = ctypes.c_int64(), ctypes.c_int64()
         self.ctx.check(self.lib.stein_engine_prefetch_stats(self.handle, ctypes.byref(b), ctypes.byref(u)))

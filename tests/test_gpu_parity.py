@@ -599,16 +599,26 @@ def test_sampler_linear_regression_known_answer(ctx, golden_dir):
     # same trajectory on the oracle from the same start
     theta_ref = sampler.samples.copy()
     gd_ref = orc.AdamGradientDescent(learning_rate=1e-1)
+    centre, spread = [], []
     for it in range(500):
         sampler.train_on_batch({model.X: X, model.y: y})
         if it < 5:
             S = orc.score_linear(theta_ref, X.astype(np.float32), y.astype(np.float32))
             theta_ref, _ = orc.update_particles(theta_ref, S, gd_ref)
             _assert_close(sampler.samples, theta_ref, 2e-4)
+        if it >= 400:
+            centre.append(sampler.samples.mean())
+            spread.append(sampler.samples.std())
     est = np.array(list(sampler.theta.values()))[0].mean(axis=0).ravel()      # main.py:51
-    assert abs(est[0] - g["post_mean"][0]) < 5e-3
     sd = np.sqrt(g["post_cov"][0, 0])
-    assert 0.5 * sd < sampler.samples.std() < 1.5 * sd
+    # Adam at lr = 0.1 keeps the cloud swinging around the posterior: on the oracle (4 seeds) the mean of ONE
+    # iteration wanders over +-0.4 sd and the spread over 0.7 .. 1.5 sd -- any rounding-level change picks another
+    # phase -- while their averages over the last 100 iterations sit within 0.012 sd of the analytic mean and at
+    # 1.03 .. 1.11 sd.  The averages are the known answer; the last iterate only has to be in the swing.
+    assert abs(np.mean(centre) - g["post_mean"][0]) < 0.1 * sd, (np.mean(centre) - g["post_mean"][0]) / sd
+    assert 0.85 * sd < np.mean(spread) < 1.35 * sd, np.mean(spread) / sd
+    assert abs(est[0] - g["post_mean"][0]) < 0.6 * sd
+    assert 0.4 * sd < sampler.samples.std() < 2.0 * sd
     pred = sampler.function_posterior(model.y_hat, {model.X: X[:7]}, axis=0)
     np.testing.assert_allclose(pred, X[:7, 0] * sampler.samples.mean(), rtol=1e-4, atol=1e-6)
 
@@ -1414,9 +1424,10 @@ def test_update_particles_host_prefetches_the_next_median(ctx):
     n, d, iters = 4608, 256, 8
     X = _particles(n, d, 43)
 
-    def run(prefetch):
+    def run(prefetch, device_bw=True):
         eng = SvgdEngine(n, d, "adam", learning_rate=1e-4)
         eng.set_prefetch(prefetch)
+        eng.set_device_bandwidth(device_bw)
         eng.set_particles(X)
         out, meds = [], []
         Xin = X.copy()
@@ -1435,6 +1446,9 @@ def test_update_particles_host_prefetches_the_next_median(ctx):
 
     eng, out_a, meds_a, stats_a = run(True)
     assert stats_a["begun"] >= 3 and stats_a["used"] == stats_a["begun"] - 1, stats_a   # (the last one is still pending)
+    # ... and phi ran ahead of the host's median result, on the device-side select (verified by the host each time)
+    dbw = eng.device_bandwidth_stats()
+    assert dbw["used"] >= 3 and dbw["redone"] == 0, dbw
     # the pending median belongs to the particles it was computed from: new particles drop it ...
     Y = _particles(n, d, 44, 1.7)
     eng.set_particles(Y)
@@ -1458,11 +1472,19 @@ def test_update_particles_host_prefetches_the_next_median(ctx):
     eng.close()
 
     eng, out_b, meds_b, stats_b = run(False)
+    assert eng.device_bandwidth_stats()["used"] >= 3
     eng.close()
     assert stats_b == {"begun": 0, "used": 0}
     assert meds_a == meds_b
     for a, b in zip(out_a, out_b):
         np.testing.assert_array_equal(a, b)
+    # the plain sequence (host collects the median, then launches phi): same bits again
+    eng, out_c, meds_c, stats_c = run(False, device_bw=False)
+    assert eng.device_bandwidth_stats() == {"used": 0, "redone": 0} and stats_c == {"begun": 0, "used": 0}
+    eng.close()
+    assert meds_a == meds_c
+    for a, c in zip(out_a, out_c):
+        np.testing.assert_array_equal(a, c)
 
 
 def test_two_engines_interleaved_keep_their_own_median_history(ctx):

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 visit: prefetch test, N=1 bench, N=1 step trace
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "median or pilotless or hint or interleaved" 2>&1 | tail -5 > gpurun_out/r02_pytest_prefetch.log
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "median or pilotless or hint or interleaved or prefetch or engine or trajectory or deterministic or sampler or full_size" 2>&1 | tail -5 > gpurun_out/r02_pytest_prefetch.log
 cat gpurun_out/r02_pytest_prefetch.log
 timeout 300 python tools/step_trace.py > gpurun_out/r02_trace_n1.log 2>&1; tail -30 gpurun_out/r02_trace_n1.log | cut -c1-150
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --config-e-steps 0 > gpurun_out/tmp_bench.log 2>gpurun_out/tmp_bench.err

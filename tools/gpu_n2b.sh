@@ -3,7 +3,7 @@
 N=${1:-2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 600 $TR --master-port 29511 tools/multi_gpu_check.py > gpurun_out/r02_mgc$N.log 2>&1; echo "mgc_rc=$?"
+MGC_QUICK=${MGC_QUICK:-1} timeout 600 $TR --master-port 29511 tools/multi_gpu_check.py > gpurun_out/r02_mgc$N.log 2>&1; echo "mgc_rc=$?"
 grep -c " ok" gpurun_out/r02_mgc$N.log; grep -i "fail\|error\|timed out" gpurun_out/r02_mgc$N.log | head -5; grep "prefetched" gpurun_out/r02_mgc$N.log
 timeout 300 $TR --master-port 29512 tools/step_trace.py > gpurun_out/r02_trace_n$N.log 2> gpurun_out/r02_trace_n$N.err
 grep -v "^{" gpurun_out/r02_trace_n$N.log | cut -c1-150

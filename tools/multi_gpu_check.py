@@ -24,8 +24,11 @@ def main():
     ctx = context(local)
     make_comm(ctx)
     ok = True
-    for n, d, push in [(1000, 33, True), (5000, 256, True), (5000, 256, False), (4097, 128, True), (4200, 1024, True),
-                       (4500, 600, True)]:
+    cases = [(1000, 33, True), (5000, 256, True), (5000, 256, False), (4097, 128, True), (4200, 1024, True),
+             (4500, 600, True)]
+    if os.environ.get("MGC_QUICK"):
+        cases = [(1000, 33, True), (5000, 256, True), (4200, 1024, True)]
+    for n, d, push in cases:
         rng = np.random.default_rng(n)
         X = rng.standard_normal((n, d)).astype(np.float32).astype(np.float64)
         mean = rng.standard_normal(d)
@@ -72,7 +75,8 @@ def main():
                   flush=True)
             ok = ok and good
         if rank == 0:
-            print("n=%d d=%d push=%s: prefetched medians %r" % (n, d, eng.peer_push, eng.prefetch_stats()), flush=True)
+            print("n=%d d=%d push=%s: prefetched medians %r, phi ahead of the host's median %r"
+                  % (n, d, eng.peer_push, eng.prefetch_stats(), eng.device_bandwidth_stats()), flush=True)
         eng.close()
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
