@@ -68,15 +68,32 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons DURING the timed region: NVML polled from a thread every few milliseconds
+    (the timed region is only 0.1-0.2 s long: `nvidia-smi -lms` needs longer than that to print its first line);
+    nvidia-smi is the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.thread = index, [], None, None, None
+        self.stop_flag = threading.Event()
+        self.samples = []          # (sm MHz, reasons bitmask)
+        self.max_mhz = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -87,11 +104,34 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self.stop_flag.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                mask = int(reasons_fn(self.handle)) if reasons_fn else 0
+                self.samples.append((mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            sm = sorted(m for m, _ in self.samples)
+            mask = 0
+            for _, k in self.samples:
+                mask |= k
+            return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_min_mhz": (sm[0] if sm else None),
+                    "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                    "reasons": sorted(nm for nm, bit in self.BITS.items() if mask & bit), "source": "nvml, 4 ms period"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -116,7 +156,7 @@ class ClockSampler:
         sm_sorted = sorted(sm)
         return {"sm_mhz": (sm_sorted[len(sm_sorted) // 2] if sm_sorted else None),
                 "sm_max_mhz": (max(mx) if mx else None), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 def cpu_baseline(n, d, target_seconds=15.0):
