@@ -129,7 +129,7 @@ int stein_ctx_set_phi_guard_tol(stein_ctx *ctx, float tol);
 #define STEIN_REGION_PHI_TAIL 4   /* finalize + sum(phi^2)                                        */
 #define STEIN_REGION_OPT 5        /* clip + optimizer kernel (+ peer push)                        */
 #define STEIN_REGION_COLL 6       /* collectives of the iteration (all-reduces, barrier word, all-gathers on the ctx stream) */
-#define STEIN_REGION_HEAD 7       /* start of the iteration: barrier / all-gather of the particles, row norms */
+#define STEIN_REGION_HEAD 7       /* start of the iteration: barrier / all-gather of the particles, row norms (+ error budgets, scale and FP16 split of the median when its tensor-core route applies: one read of the particles) */
 #define STEIN_REGION_COUNT 8
 /* enable: 0 off; 1 = regions PHI and SWEEP only (two event pairs per iteration: what bench.py keeps on inside
  * its timed region); 2 = all regions (the per-phase timeline, measured in a separate pass) */
